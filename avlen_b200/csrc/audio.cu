@@ -1,0 +1,658 @@
+// Batched audiogoal rendering + log-magnitude spectrogram.
+//
+// Replaces, for a whole batch of environments in one launch:
+//   soundspaces/simulator.py:644-699   SoundSpacesSim._compute_audiogoal
+//   soundspaces/tasks/nav.py:87-101    SpectrogramSensor.compute_spectrogram
+//
+// One persistent CTA per SM walks over environments.  Per environment the
+// binaural waveform is the causal FIR  y[c][n] = sum_k rir[k][c] * src[base+n-k]
+// (all three reference branches reduce to this), evaluated
+// as a 32768-point circular convolution through a 16384-point complex FFT that
+// lives entirely in shared memory (packed-real trick, in-place DIF forward /
+// DIT inverse so no digit-reversal pass is needed).  The (2, sr) waveform never
+// leaves shared memory unless the audiogoal output is requested: the STFT
+// (n_fft 512, hop 160, periodic Hann 400 centred, reflect padding), |.|, the
+// zero-padded 4x4 block mean and log1p are computed from the shared-memory
+// copy and only the (65, 26, 2) spectrogram is written.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kM = 16384;  // complex FFT length
+constexpr int kP = 32768;  // circular convolution length (real samples)
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kBufElems = kM + (kM >> 4) + (kM >> 8);  // padded float2 count
+constexpr int kFrameElems = 272;                        // 256 + 16 pad
+constexpr int kNfft = 512, kHop = 160, kWin = 400, kBins = 257, kFB = 65;
+
+typedef float2 cf;
+
+__device__ __forceinline__ int padi(int p) { return p + (p >> 4) + (p >> 8); }
+__device__ __forceinline__ int padf(int p) { return p + (p >> 4); }
+__device__ __forceinline__ cf cmul(cf a, cf b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cf cmulc(cf a, cf b) {  // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cf cconj(cf a) { return make_float2(a.x, -a.y); }
+
+// y_q = sum_m x_m exp(SIGN * 2*pi*i*m*q/4), in place, natural order
+template <int SIGN>
+__device__ __forceinline__ void fft4(cf& a, cf& b, cf& c, cf& d) {
+  cf t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+  cf r3 = (SIGN < 0) ? make_float2(t3.y, -t3.x) : make_float2(-t3.y, t3.x);  // (+-i) * t3
+  a = cadd(t0, t2);
+  c = csub(t0, t2);
+  b = cadd(t1, r3);
+  d = csub(t1, r3);
+}
+
+// constant exp(SIGN*2*pi*i*k/16)
+template <int SIGN>
+__device__ __forceinline__ cf w16(int k) {
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+  float re, im;
+  switch (k) {
+    case 1: re = c1; im = s1; break;
+    case 2: re = r; im = r; break;
+    case 3: re = s1; im = c1; break;
+    case 4: re = 0.f; im = 1.f; break;
+    case 6: re = -r; im = r; break;
+    case 9: re = -c1; im = -s1; break;
+    default: re = 1.f; im = 0.f; break;
+  }
+  return make_float2(re, SIGN < 0 ? -im : im);
+}
+
+// 16-point DFT: y_q = sum_m x_m exp(SIGN*2*pi*i*m*q/16); y_q is left in x[o16(q)]
+__host__ __device__ constexpr int o16(int q) { return 4 * (q & 3) + (q >> 2); }
+
+template <int SIGN>
+__device__ __forceinline__ void fft16(cf (&x)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    fft4<SIGN>(x[j], x[j + 4], x[j + 8], x[j + 12]);  // x[j + 4*q0] = t_{q0}[j]
+#pragma unroll
+    for (int q0 = 1; q0 < 4; ++q0)
+      if (j > 0) x[j + 4 * q0] = cmul(x[j + 4 * q0], w16<SIGN>(j * q0));
+  }
+#pragma unroll
+  for (int q0 = 0; q0 < 4; ++q0) fft4<SIGN>(x[4 * q0], x[4 * q0 + 1], x[4 * q0 + 2], x[4 * q0 + 3]);
+}
+
+// tw[q] = w^q, q = 1..15 (multiplication tree, depth <= 4)
+__device__ __forceinline__ void tw_powers(cf w, cf (&t)[16]) {
+  t[0] = make_float2(1.f, 0.f);
+  t[1] = w;
+  t[2] = cmul(w, w);
+  t[3] = cmul(t[2], w);
+  t[4] = cmul(t[2], t[2]);
+  t[5] = cmul(t[4], w);
+  t[6] = cmul(t[3], t[3]);
+  t[7] = cmul(t[4], t[3]);
+  t[8] = cmul(t[4], t[4]);
+  t[9] = cmul(t[8], w);
+  t[10] = cmul(t[5], t[5]);
+  t[11] = cmul(t[8], t[3]);
+  t[12] = cmul(t[6], t[6]);
+  t[13] = cmul(t[8], t[5]);
+  t[14] = cmul(t[7], t[7]);
+  t[15] = cmul(t[8], t[7]);
+}
+
+// One radix-16 butterfly of an in-place DIF stage on a block of size n = 16*s:
+//   buf[base + j + q*s] <- (sum_m buf[base + j + m*s] w16^{mq}) * w_n^{jq}
+// PADF selects the padding function (big buffer / frame buffer).
+template <bool BIG>
+__device__ __forceinline__ int padx(int p) { return BIG ? padi(p) : padf(p); }
+
+template <bool BIG>
+__device__ __forceinline__ void r16_fwd(cf* buf, int base, int j, int s, bool twiddle, cf w) {
+  cf x[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) x[m] = buf[padx<BIG>(base + j + m * s)];
+  fft16<-1>(x);
+  if (twiddle) {
+    cf t[16];
+    tw_powers(w, t);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) x[o16(q)] = cmul(x[o16(q)], t[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[padx<BIG>(base + j + q * s)] = x[o16(q)];
+}
+
+// Inverse of r16_fwd up to the factor 16.
+template <bool BIG>
+__device__ __forceinline__ void r16_inv(cf* buf, int base, int j, int s, bool twiddle, cf w) {
+  cf x[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) x[q] = buf[padx<BIG>(base + j + q * s)];
+  if (twiddle) {
+    cf t[16];
+    tw_powers(w, t);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) x[q] = cmulc(x[q], t[q]);
+  }
+  fft16<+1>(x);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) buf[padx<BIG>(base + j + m * s)] = x[o16(m)];
+}
+
+// tw[k] = exp(-2*pi*i*k/32768), k in [0, 16384]
+// In-place DIF forward FFT of the 16384-point buffer; radices 4,16,16,16.
+// Output X[k], k = q1 + 4 q2 + 64 q3 + 1024 q4, is left at rev(k) = q1*4096 + q2*256 + q3*16 + q4.
+__device__ void fft_big_fwd(cf* buf, const cf* __restrict__ tw) {
+  const int tid = threadIdx.x;
+  for (int u = tid; u < 4096; u += kThreads) {
+    cf a = buf[padi(u)], b = buf[padi(u + 4096)], c = buf[padi(u + 8192)], d = buf[padi(u + 12288)];
+    fft4<-1>(a, b, c, d);
+    cf w1 = tw[2 * u];
+    cf w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    buf[padi(u)] = a;
+    buf[padi(u + 4096)] = cmul(b, w1);
+    buf[padi(u + 8192)] = cmul(c, w2);
+    buf[padi(u + 12288)] = cmul(d, w3);
+  }
+  __syncthreads();
+  for (int u = tid; u < 1024; u += kThreads) {
+    int b = u >> 8, j = u & 255;
+    r16_fwd<true>(buf, b * 4096, j, 256, true, tw[8 * j]);  // w_4096^j
+  }
+  __syncthreads();
+  for (int u = tid; u < 1024; u += kThreads) {
+    int b = u >> 4, j = u & 15;
+    r16_fwd<true>(buf, b * 256, j, 16, true, tw[128 * j]);  // w_256^j
+  }
+  __syncthreads();
+  for (int u = tid; u < 1024; u += kThreads) r16_fwd<true>(buf, u * 16, 0, 1, false, make_float2(1.f, 0.f));
+  __syncthreads();
+}
+
+// Exact inverse of fft_big_fwd up to the factor 16384 (digit-reversed in, natural out).
+__device__ void fft_big_inv(cf* buf, const cf* __restrict__ tw) {
+  const int tid = threadIdx.x;
+  for (int u = tid; u < 1024; u += kThreads) r16_inv<true>(buf, u * 16, 0, 1, false, make_float2(1.f, 0.f));
+  __syncthreads();
+  for (int u = tid; u < 1024; u += kThreads) {
+    int b = u >> 4, j = u & 15;
+    r16_inv<true>(buf, b * 256, j, 16, true, tw[128 * j]);
+  }
+  __syncthreads();
+  for (int u = tid; u < 1024; u += kThreads) {
+    int b = u >> 8, j = u & 255;
+    r16_inv<true>(buf, b * 4096, j, 256, true, tw[8 * j]);
+  }
+  __syncthreads();
+  for (int u = tid; u < 4096; u += kThreads) {
+    cf w1 = tw[2 * u];
+    cf w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+    cf a = buf[padi(u)];
+    cf b = cmulc(buf[padi(u + 4096)], w1);
+    cf c = cmulc(buf[padi(u + 8192)], w2);
+    cf d = cmulc(buf[padi(u + 12288)], w3);
+    fft4<+1>(a, b, c, d);
+    buf[padi(u)] = a;
+    buf[padi(u + 4096)] = b;
+    buf[padi(u + 8192)] = c;
+    buf[padi(u + 12288)] = d;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int rev_big(int k) {
+  return ((k & 3) << 12) | (((k >> 2) & 15) << 8) | (((k >> 6) & 15) << 4) | ((k >> 10) & 15);
+}
+
+// Spectrum of the packed real signal at bin k (0 <= k <= kM) from the
+// digit-reversed half-size complex spectrum in buf:  X[k] = E + W^k O.
+__device__ __forceinline__ cf unpack_bin(cf zk, cf zmk_conj, cf wk) {
+  cf e = make_float2(0.5f * (zk.x + zmk_conj.x), 0.5f * (zk.y + zmk_conj.y));
+  cf d = csub(zk, zmk_conj);                      // (Zk - conj Zmk)
+  cf o = make_float2(0.5f * d.y, -0.5f * d.x);    // d / (2i)
+  return cadd(e, cmul(wk, o));
+}
+
+struct EnvTerm {
+  const float* src;   // clip base pointer
+  long long base;     // absolute sample index of output sample 0 inside the clip
+  const float* rir;   // interleaved (L, 2)
+  int L;
+};
+
+// Fill buf with the packed circular source sequence u (see header comment):
+//   u[m] = src[base + m]      0 <= m < sr
+//   u[P - j] = src[base - j]  1 <= j <= L-1  (0 where base - j < 0)
+__device__ void load_source(cf* buf, const EnvTerm& t, int sr) {
+  for (int n = threadIdx.x; n < kM; n += kThreads) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int m = 2 * n + h;
+      float x = 0.f;
+      if (m < sr) {
+        x = __ldg(t.src + t.base + m);
+      } else if (m > kP - t.L) {
+        long long idx = t.base - (kP - m);
+        if (idx >= 0) x = __ldg(t.src + idx);
+      }
+      v[h] = x;
+    }
+    buf[padi(n)] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+}
+
+__device__ void load_rir(cf* buf, const EnvTerm& t, int c) {
+  for (int n = threadIdx.x; n < kM; n += kThreads) {
+    int k0 = 2 * n, k1 = 2 * n + 1;
+    float a = (k0 < t.L) ? __ldg(t.rir + 2 * (long long)k0 + c) : 0.f;
+    float b = (k1 < t.L) ? __ldg(t.rir + 2 * (long long)k1 + c) : 0.f;
+    buf[padi(n)] = make_float2(a, b);
+  }
+  __syncthreads();
+}
+
+// buf holds the digit-reversed spectrum of a packed real signal.  Write its
+// real-signal spectrum X[0..kM] in natural order to xs (global scratch).
+__device__ void store_spectrum(const cf* buf, const cf* __restrict__ tw, cf* xs) {
+  for (int k = threadIdx.x; k <= kM / 2; k += kThreads) {
+    if (k == 0) {
+      cf z = buf[padi(0)];
+      __stcg(&xs[0], make_float2(z.x + z.y, 0.f));
+      __stcg(&xs[kM], make_float2(z.x - z.y, 0.f));
+    } else {
+      cf zk = buf[padi(rev_big(k))], zm = buf[padi(rev_big(kM - k))];
+      cf wk = tw[k];
+      cf xk = unpack_bin(zk, cconj(zm), wk);
+      // W^{M-k} = -conj(W^k)
+      cf xm = unpack_bin(zm, cconj(zk), make_float2(-wk.x, wk.y));
+      __stcg(&xs[k], xk);
+      if (k != kM / 2) __stcg(&xs[kM - k], xm);
+    }
+  }
+  __syncthreads();
+}
+
+// buf holds the digit-reversed half-size spectrum of the packed RIR channel.
+// Multiply with the source spectrum xs (natural order, global), optionally add
+// / store the running sum yacc, and (when `finish`) repack the product in place
+// as the half-size spectrum of the packed real result, scaled by 1/M.
+__device__ void spectral_multiply(cf* buf, const cf* __restrict__ tw, const cf* xs, cf* yacc,
+                                  bool add_acc, bool finish) {
+  const float scale = 1.0f / (float)kM;  // inverse half-size FFT is unnormalised
+  for (int k = threadIdx.x; k <= kM / 2; k += kThreads) {
+    cf yk, ym, wk;
+    if (k == 0) {
+      cf z = buf[padi(0)];
+      cf x0 = __ldcg(&xs[0]), xM = __ldcg(&xs[kM]);
+      yk = make_float2((z.x + z.y) * x0.x, 0.f);   // Y[0]  (real)
+      ym = make_float2((z.x - z.y) * xM.x, 0.f);   // Y[M]  (real)
+      wk = make_float2(1.f, 0.f);
+    } else {
+      cf zk = buf[padi(rev_big(k))], zm = buf[padi(rev_big(kM - k))];
+      wk = tw[k];
+      cf ak = unpack_bin(zk, cconj(zm), wk);
+      cf am = unpack_bin(zm, cconj(zk), make_float2(-wk.x, wk.y));
+      yk = cmul(ak, __ldcg(&xs[k]));
+      ym = cmul(am, __ldcg(&xs[kM - k]));
+    }
+    if (add_acc) {
+      yk = cadd(yk, __ldcg(&yacc[k]));
+      ym = cadd(ym, __ldcg(&yacc[kM - k]));
+    }
+    if (!finish) {
+      __stcg(&yacc[k], yk);
+      if (k != kM / 2) __stcg(&yacc[kM - k], ym);
+      continue;
+    }
+    // repack: Zy[k] = E + i O, E = (Y[k] + conj Y[M-k])/2, O = (Y[k] - conj Y[M-k])/2 * conj(W^k)
+    if (k == 0) {
+      float e = 0.5f * (yk.x + ym.x), o = 0.5f * (yk.x - ym.x);
+      buf[padi(0)] = make_float2(e * scale, o * scale);
+    } else {
+      cf ymc = cconj(ym);
+      cf e = make_float2(0.5f * (yk.x + ymc.x), 0.5f * (yk.y + ymc.y));
+      cf d = make_float2(0.5f * (yk.x - ymc.x), 0.5f * (yk.y - ymc.y));
+      cf o = cmulc(d, wk);
+      buf[padi(rev_big(k))] = make_float2((e.x - o.y) * scale, (e.y + o.x) * scale);
+      if (k != kM / 2) {
+        // Zy[M-k]: E' = conj(E), O' = (Y[M-k] - conj Y[k])/2 * conj(W^{M-k}) = -conj(d) * (-W^k) = conj(d) * W^k
+        cf o2 = cmul(cconj(d), wk);
+        buf[padi(rev_big(kM - k))] = make_float2((e.x - o2.y) * scale, (-e.y + o2.x) * scale);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- STFT part
+
+struct SmemSamples {  // waveform held in the big FFT buffer (packed, padded)
+  const float* f;
+  __device__ __forceinline__ float operator()(int i) const { return f[2 * padi(i >> 1) + (i & 1)]; }
+};
+struct GmemSamples {
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+};
+
+// STFT -> |.| -> 4x4 zero-padded block mean -> log1p for one channel.
+// fb: per-warp frame buffers (2 * kFrameElems float2 per warp); win: 512-float window in smem.
+// out: spectrogram base pointer for this env, layout (65, TB, 2); writes channel c.
+template <class Samples>
+__device__ void stft_channel(const Samples& y, int sr, cf* fb, const float* win,
+                             const cf* __restrict__ tw, float* out, int c) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, l = lane & 15;
+  const int n_frames = 1 + sr / kHop;
+  const int n_tb = (n_frames + 3) >> 2;
+  cf* z = fb + (warp * 2 + half) * kFrameElems;
+  const int rounds = (n_tb + 7) >> 3;
+  for (int r = 0; r < rounds; ++r) {
+    const int f = 32 * r + 2 * warp + half;
+    const bool valid = f < n_frames;
+    // windowed frame, packed as 256 complex
+    const int start = kHop * f - kNfft / 2;
+#pragma unroll 4
+    for (int t = 0; t < 16; ++t) {
+      int j = l + 16 * t;
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int i = 2 * j + h;
+        float x = 0.f;
+        if (valid && i >= (kNfft - kWin) / 2 && i < (kNfft + kWin) / 2) {
+          int idx = start + i;
+          if (idx < 0) idx = -idx;
+          if (idx >= sr) idx = 2 * (sr - 1) - idx;
+          x = win[i] * y(idx);
+        }
+        v[h] = x;
+      }
+      z[padf(j)] = make_float2(v[0], v[1]);
+    }
+    __syncwarp();
+    // 256-point complex FFT = 16 x 16, one radix-16 butterfly per lane per stage
+    r16_fwd<false>(z, 0, l, 16, true, tw[128 * l]);  // w_256^l
+    __syncwarp();
+    r16_fwd<false>(z, 16 * l, 0, 1, false, make_float2(1.f, 0.f));
+    __syncwarp();
+    // real spectrum magnitudes: bins k and 256-k, k = 1..127 (8 per lane), plus 0, 128, 256
+    float mg[18];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      int k = 1 + l + 16 * t;  // 1..128
+      int km = 256 - k;
+      cf zk = z[padf(((k & 15) << 4) | (k >> 4))];
+      cf zm = z[padf(((km & 15) << 4) | (km >> 4))];
+      cf wk = tw[64 * k];  // exp(-2 pi i k / 512)
+      cf xk = unpack_bin(zk, cconj(zm), wk);
+      cf xm = unpack_bin(zm, cconj(zk), make_float2(-wk.x, wk.y));
+      mg[2 * t] = sqrtf(fmaf(xk.x, xk.x, xk.y * xk.y));
+      mg[2 * t + 1] = sqrtf(fmaf(xm.x, xm.x, xm.y * xm.y));
+    }
+    cf z0 = z[0];
+    mg[16] = fabsf(z0.x + z0.y);
+    mg[17] = fabsf(z0.x - z0.y);
+    __syncwarp();
+    float* mag = reinterpret_cast<float*>(z);  // 257 floats inside this frame's 544-float buffer
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      int k = 1 + l + 16 * t;
+      mag[k] = mg[2 * t];
+      if (k != 128) mag[256 - k] = mg[2 * t + 1];
+    }
+    if (l == 0) {
+      mag[0] = mg[16];
+      mag[256] = mg[17];
+    }
+    __syncthreads();
+    // 4x4 block mean (zero padded) + log1p for the 8 time blocks of this round
+    for (int o = threadIdx.x; o < 8 * kFB; o += kThreads) {
+      int gl = o / kFB, kb = o - gl * kFB;
+      int tb = 8 * r + gl;
+      if (tb < n_tb) {
+        float s = 0.f;
+#pragma unroll
+        for (int df = 0; df < 4; ++df) {
+          int fl = 4 * gl + df;  // frame index local to the round: warp = fl/2, half = fl&1
+          if (32 * r + fl < n_frames) {
+            const float* m = reinterpret_cast<const float*>(fb + fl * kFrameElems);
+#pragma unroll
+            for (int dk = 0; dk < 4; ++dk) {
+              int k = 4 * kb + dk;
+              if (k < kBins) s += m[k];
+            }
+          }
+        }
+        out[(kb * n_tb + tb) * 2 + c] = log1pf(s * 0.0625f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ void fill_window(float* win) {
+  for (int i = threadIdx.x; i < kNfft; i += kThreads) {
+    int n = i - (kNfft - kWin) / 2;
+    float w = 0.f;
+    if (n >= 0 && n < kWin) w = (float)(0.5 - 0.5 * cospi(2.0 * (double)n / (double)kWin));
+    win[i] = w;
+  }
+}
+
+struct RenderArgs {
+  int n_envs, sr;
+  const float* sounds;
+  const long long* clip_off;   // start of the env's clip inside `sounds`
+  const int* index;            // _audio_index (seconds into the clip)
+  const float* rirs;
+  const long long* rir_off;    // in frames (2 floats per frame)
+  const int* rir_len;
+  const int* silent;
+  // distractor (all null when absent)
+  const long long* d_clip_off;
+  const long long* d_rir_off;
+  const int* d_rir_len;
+  float* audiogoal;            // (N, 2, sr) or null
+  float* spectrogram;          // (N, 65, TB, 2)
+  const cf* tw;
+  cf* scratch;                 // per CTA: 3 * (kM + 1) float2
+  int* status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) audio_render_kernel(RenderArgs a) {
+  AVL_DYN_SMEM(smem_raw);
+  cf* buf = reinterpret_cast<cf*>(smem_raw);
+  cf* fb = buf + kBufElems;
+  float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
+  fill_window(win);
+  cf* xs0 = a.scratch + (size_t)blockIdx.x * 3 * (kM + 1);
+  cf* xs1 = xs0 + (kM + 1);
+  cf* yacc = xs1 + (kM + 1);
+  const int sr = a.sr;
+  const int n_tb = ((1 + sr / kHop) + 3) >> 2;
+  const int lmax = kP - sr + 1;
+  __syncthreads();
+
+  for (int e = blockIdx.x; e < a.n_envs; e += gridDim.x) {
+    EnvTerm term[2];
+    int nterms = 0;
+    const bool silent = a.silent[e] != 0;
+    if (!silent) {
+      int L = a.rir_len[e];
+      if (L > lmax) { L = lmax; if (threadIdx.x == 0) atomicExch(a.status, 1); }
+      if (L > 0) {
+        term[nterms].src = a.sounds + a.clip_off[e];
+        term[nterms].base = (long long)a.index[e] * sr;
+        term[nterms].rir = a.rirs + 2 * a.rir_off[e];
+        term[nterms].L = L;
+        ++nterms;
+      }
+      if (a.d_clip_off != nullptr) {
+        int Ld = a.d_rir_len[e];
+        if (Ld > lmax) { Ld = lmax; if (threadIdx.x == 0) atomicExch(a.status, 1); }
+        if (Ld > 0) {
+          term[nterms].src = a.sounds + a.d_clip_off[e];
+          term[nterms].base = 0;
+          term[nterms].rir = a.rirs + 2 * a.d_rir_off[e];
+          term[nterms].L = Ld;
+          ++nterms;
+        }
+      }
+    }
+    float* spec = a.spectrogram + (size_t)e * kFB * n_tb * 2;
+    if (nterms == 0) {  // exact zeros: log1p(0) = 0 (belief_predictor.py:159 relies on it)
+      for (int i = threadIdx.x; i < kFB * n_tb * 2; i += kThreads) spec[i] = 0.f;
+      if (a.audiogoal) {
+        float* ag = a.audiogoal + (size_t)e * 2 * sr;
+        for (int i = threadIdx.x; i < 2 * sr; i += kThreads) ag[i] = 0.f;
+      }
+      continue;
+    }
+    for (int t = 0; t < nterms; ++t) {
+      load_source(buf, term[t], sr);
+      fft_big_fwd(buf, a.tw);
+      store_spectrum(buf, a.tw, t == 0 ? xs0 : xs1);
+    }
+    for (int c = 0; c < 2; ++c) {
+      for (int t = 0; t < nterms; ++t) {
+        load_rir(buf, term[t], c);
+        fft_big_fwd(buf, a.tw);
+        spectral_multiply(buf, a.tw, t == 0 ? xs0 : xs1, yacc, t > 0, t == nterms - 1);
+      }
+      fft_big_inv(buf, a.tw);
+      SmemSamples y{reinterpret_cast<const float*>(buf)};
+      if (a.audiogoal) {
+        float* ag = a.audiogoal + ((size_t)e * 2 + c) * sr;
+        for (int i = threadIdx.x; i < sr; i += kThreads) ag[i] = y(i);
+      }
+      stft_channel(y, sr, fb, win, a.tw, spec, c);
+    }
+  }
+}
+
+// Stand-alone SpectrogramSensor.compute_spectrogram for a batch of waveforms (N, 2, sr).
+__global__ void __launch_bounds__(kThreads, 1)
+spectrogram_kernel(const float* audio, int n, int sr, float* spectrogram, const cf* tw) {
+  AVL_DYN_SMEM(smem_raw);
+  cf* fb = reinterpret_cast<cf*>(smem_raw);
+  float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
+  fill_window(win);
+  __syncthreads();
+  const int n_tb = ((1 + sr / kHop) + 3) >> 2;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    for (int c = 0; c < 2; ++c) {
+      GmemSamples y{audio + ((size_t)e * 2 + c) * sr};
+      stft_channel(y, sr, fb, win, tw, spectrogram + (size_t)e * kFB * n_tb * 2, c);
+    }
+  }
+}
+
+__global__ void twiddle_init_kernel(cf* tw) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= kM) {
+    double s, c;
+    sincospi((double)k / (double)kM, &s, &c);
+    tw[k] = make_float2((float)c, (float)(-s));
+  }
+}
+
+#ifndef AVL_HOST_EMUL
+struct AudioCtx {
+  int sr;
+  int grid;
+  cf* tw;
+  cf* scratch;
+  int* status;
+};
+
+constexpr size_t kRenderSmem = (size_t)(kBufElems + kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
+constexpr size_t kSpecSmem = (size_t)(kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
+
+#endif  // AVL_HOST_EMUL
+
+}  // namespace
+
+#ifndef AVL_HOST_EMUL
+// Creates the audio context (twiddle table + per-CTA spectrum scratch).  The
+// only allocation the audio path ever makes.  sr must satisfy 512 <= sr <= 16769.
+AVL_API int avl_audio_create(int sr, void** handle) {
+  if (!handle) return AVL_ERR_ARG;
+  if (sr < kNfft) return AVL_ERR_UNSUPPORTED;
+  AudioCtx* ctx = new AudioCtx();
+  ctx->sr = sr;
+  ctx->grid = avl_num_sms();
+  AVL_CUDA_CHECK(cudaMalloc(&ctx->tw, sizeof(cf) * (kM + 1)));
+  AVL_CUDA_CHECK(cudaMalloc(&ctx->scratch, sizeof(cf) * 3 * (kM + 1) * (size_t)ctx->grid));
+  AVL_CUDA_CHECK(cudaMalloc(&ctx->status, sizeof(int)));
+  AVL_CUDA_CHECK(cudaMemset(ctx->status, 0, sizeof(int)));
+  twiddle_init_kernel<<<avl_div_up(kM + 1, 256), 256>>>(ctx->tw);
+  AVL_LAUNCH_CHECK();
+  AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRenderSmem));
+  AVL_CUDA_CHECK(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem));
+  AVL_CUDA_CHECK(cudaDeviceSynchronize());
+  *handle = ctx;
+  return AVL_OK;
+}
+
+AVL_API int avl_audio_destroy(void* handle) {
+  AudioCtx* ctx = static_cast<AudioCtx*>(handle);
+  if (!ctx) return AVL_ERR_ARG;
+  cudaFree(ctx->tw);
+  cudaFree(ctx->scratch);
+  cudaFree(ctx->status);
+  delete ctx;
+  return AVL_OK;
+}
+
+// Sticky device-side status of earlier render calls (synchronises the device):
+// 0 ok, 1 = some RIR was longer than 32768 - sr + 1 samples and was truncated.
+AVL_API int avl_audio_status(void* handle, int* status_out) {
+  AudioCtx* ctx = static_cast<AudioCtx*>(handle);
+  if (!ctx || !status_out) return AVL_ERR_ARG;
+  AVL_CUDA_CHECK(cudaMemcpy(status_out, ctx->status, sizeof(int), cudaMemcpyDeviceToHost));
+  return AVL_OK;
+}
+
+// Fused rows A + B.  All pointers are device pointers.  See include/avlen_b200.h.
+AVL_API int avl_audio_render_spectrogram(void* handle, int n_envs, const float* sounds, const long long* clip_off,
+                                         const int* index, const float* rirs, const long long* rir_off,
+                                         const int* rir_len, const int* silent, const long long* d_clip_off,
+                                         const long long* d_rir_off, const int* d_rir_len, float* audiogoal_out,
+                                         float* spectrogram_out, void* stream) {
+  AudioCtx* ctx = static_cast<AudioCtx*>(handle);
+  if (!ctx || n_envs < 0) return AVL_ERR_ARG;
+  if (n_envs == 0) return AVL_OK;
+  if (!sounds || !clip_off || !index || !rirs || !rir_off || !rir_len || !silent || !spectrogram_out) return AVL_ERR_ARG;
+  if ((d_clip_off != nullptr) != (d_rir_off != nullptr) || (d_clip_off != nullptr) != (d_rir_len != nullptr)) return AVL_ERR_ARG;
+  if (ctx->sr > kP / 2 + 385) return AVL_ERR_UNSUPPORTED;  // fused path needs sr + L - 1 <= 32768
+  RenderArgs a;
+  a.n_envs = n_envs; a.sr = ctx->sr; a.sounds = sounds; a.clip_off = clip_off; a.index = index;
+  a.rirs = rirs; a.rir_off = rir_off; a.rir_len = rir_len; a.silent = silent;
+  a.d_clip_off = d_clip_off; a.d_rir_off = d_rir_off; a.d_rir_len = d_rir_len;
+  a.audiogoal = audiogoal_out; a.spectrogram = spectrogram_out; a.tw = ctx->tw; a.scratch = ctx->scratch;
+  a.status = ctx->status;
+  int grid = n_envs < ctx->grid ? n_envs : ctx->grid;
+  audio_render_kernel<<<grid, kThreads, kRenderSmem, (cudaStream_t)stream>>>(a);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+// Row B alone: (N, 2, sr) waveforms -> (N, 65, ceil((1 + sr/160)/4), 2).
+AVL_API int avl_audio_spectrogram(void* handle, int n, const float* audio, float* spectrogram_out, void* stream) {
+  AudioCtx* ctx = static_cast<AudioCtx*>(handle);
+  if (!ctx || n < 0) return AVL_ERR_ARG;
+  if (n == 0) return AVL_OK;
+  if (!audio || !spectrogram_out) return AVL_ERR_ARG;
+  int grid = n < 2 * ctx->grid ? n : 2 * ctx->grid;
+  spectrogram_kernel<<<grid, kThreads, kSpecSmem, (cudaStream_t)stream>>>(audio, n, ctx->sr, spectrogram_out, ctx->tw);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

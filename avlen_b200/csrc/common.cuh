@@ -1,0 +1,64 @@
+// Shared helpers for the avlen_b200 CUDA library (sm_100a only).
+#pragma once
+#ifdef AVL_HOST_EMUL
+// CPU emulation build used only by tests/ (tests/emul/cuda_emul.h)
+#include "cuda_emul.h"
+#define AVL_DYN_SMEM(name) unsigned char* name = ::smem_raw
+#else
+#include <cuda_runtime.h>
+#define AVL_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+#include <stdint.h>
+#include <math.h>
+
+#define AVL_OK 0
+#define AVL_ERR_ARG (-1)         // null pointer / negative size / inconsistent shapes
+#define AVL_ERR_UNSUPPORTED (-2) // size outside what the kernels are built for
+#define AVL_ERR_CUDA (-3)        // a CUDA runtime call failed (see avl_last_cuda_error)
+
+extern "C" int avl_set_cuda_error(int e);
+
+#define AVL_CUDA_CHECK(expr)                                  \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) {                                  \
+      avl_set_cuda_error((int)_e);                            \
+      return AVL_ERR_CUDA;                                    \
+    }                                                         \
+  } while (0)
+
+#define AVL_LAUNCH_CHECK() AVL_CUDA_CHECK(cudaGetLastError())
+
+#define AVL_API extern "C" __attribute__((visibility("default")))
+
+static inline int avl_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (all threads must call); result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* red /* >=33 floats smem */) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) red[32] = r;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+int avl_num_sms();

@@ -1,0 +1,30 @@
+// Library-wide state: last CUDA error, device properties, version.
+#include "common.cuh"
+
+static int g_last_cuda_error = 0;
+static int g_num_sms = 0;
+
+extern "C" int avl_set_cuda_error(int e) {
+  g_last_cuda_error = e;
+  return e;
+}
+
+int avl_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_num_sms = n;
+  }
+  return g_num_sms;
+}
+
+AVL_API int avl_version(void) { return 100; }
+
+// cudaError_t of the last failed runtime call made by this library (0 = none).
+AVL_API int avl_last_cuda_error(void) { return g_last_cuda_error; }
+
+AVL_API const char* avl_last_cuda_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_cuda_error); }
+
+AVL_API int avl_device_sm_count(void) { return avl_num_sms(); }
