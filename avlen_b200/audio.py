@@ -1,0 +1,143 @@
+"""Batched audiogoal + spectrogram observation builder (§8b "Audio sensors").
+
+Host-side mirror of
+
+* ``SoundSpacesSim._compute_audiogoal`` / ``get_current_audiogoal_observation`` /
+  ``get_current_spectrogram_observation``  (soundspaces/simulator.py:644-734)
+* ``SpectrogramSensor.compute_spectrogram``  (soundspaces/tasks/nav.py:87-101)
+
+The reference computes one environment per worker process on the CPU; here a
+whole batch of environments is rendered by one CUDA launch and the results stay
+on the device so they can feed ``RolloutStorage.insert`` without a host hop.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_FFT, HOP, WIN, FREQ_BLOCKS = 512, 160, 400, 65
+
+
+def spectrogram_shape(sr: int):
+    """(65, ceil((1 + sr // 160) / 4), 2) — (65, 26, 2) at 16 kHz, (65, 69, 2) at 44.1 kHz (nav.py:78)."""
+    return (FREQ_BLOCKS, (1 + sr // HOP + 3) // 4, 2)
+
+
+class AudioRenderer:
+    """Owns the CUDA audio context (FFT twiddles + per-SM spectrum scratch) for one sampling rate."""
+
+    def __init__(self, sampling_rate: int = 16000, device="cuda"):
+        self.sr = int(sampling_rate)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.AvlenError("AudioRenderer needs a CUDA device")
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().avl_audio_create(self.sr, ctypes.byref(h)), "avl_audio_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().avl_audio_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def max_rir_len(self):
+        return 32768 - self.sr + 1
+
+    def render(self, sounds, clip_off, index, rirs, rir_off, rir_len, silent, d_clip_off=None, d_rir_off=None,
+               d_rir_len=None, want_audiogoal=True, out_audiogoal=None, out_spectrogram=None):
+        """Rows A+B fused for N environments.
+
+        sounds: flat f32 bank of mono clips; clip_off (N,) int64 start of each env's clip;
+        index (N,) int32 = ``_audio_index`` (second of the clip to render; 0 for 1-s clips);
+        rirs: f32 bank of interleaved (L, 2) RIRs; rir_off (N,) int64 in frames; rir_len (N,) int32 (0 = empty file);
+        silent (N,) int32 (step count beyond the sound duration, simulator.py:646).
+        Optional distractor triple adds a second source from the start of its clip (simulator.py:682-697).
+        Returns ``(audiogoal (N, 2, sr) or None, spectrogram (N, 65, 26, 2))``.
+        """
+        n = int(clip_off.shape[0])
+        dev = self.device
+        spec = out_spectrogram if out_spectrogram is not None else torch.empty(
+            (n,) + spectrogram_shape(self.sr), device=dev, dtype=torch.float32)
+        ag = None
+        if want_audiogoal:
+            ag = out_audiogoal if out_audiogoal is not None else torch.empty(
+                (n, 2, self.sr), device=dev, dtype=torch.float32)
+        i64, i32 = torch.int64, torch.int32
+        _lib.call("avl_audio_render_spectrogram", self._h, n, _lib.fptr(sounds), _lib.dptr(clip_off, i64),
+                  _lib.dptr(index, i32), _lib.fptr(rirs), _lib.dptr(rir_off, i64), _lib.dptr(rir_len, i32),
+                  _lib.dptr(silent, i32), _lib.dptr(d_clip_off, i64), _lib.dptr(d_rir_off, i64),
+                  _lib.dptr(d_rir_len, i32), _lib.fptr(ag), _lib.fptr(spec), _lib.stream())
+        return ag, spec
+
+    def compute_spectrogram(self, audio, out=None):
+        """Row B alone for a batch: (N, 2, sr) float32 CUDA tensor -> (N, 65, 26, 2)."""
+        n = int(audio.shape[0])
+        if tuple(audio.shape[1:]) != (2, self.sr):
+            raise _lib.AvlenError(f"expected (N, 2, {self.sr}) audio, got {tuple(audio.shape)}")
+        spec = out if out is not None else torch.empty((n,) + spectrogram_shape(self.sr), device=audio.device,
+                                                       dtype=torch.float32)
+        _lib.call("avl_audio_spectrogram", self._h, n, _lib.fptr(audio), _lib.fptr(spec), _lib.stream())
+        return spec
+
+    def status(self) -> int:
+        s = ctypes.c_int(0)
+        _lib.check(_lib.lib().avl_audio_status(self._h, ctypes.byref(s)), "avl_audio_status")
+        return s.value
+
+    # ---- host-buffer entry (the reference-facing call: numpy in, numpy out) ----
+    def render_host(self, batch: dict, want_audiogoal=False, pinned_out=None):
+        """Same as :meth:`render` but with HOST descriptors (numpy) and a host result, copies included.
+
+        ``sounds`` / ``rirs`` banks may already be CUDA tensors (resident assets) or numpy arrays.
+        """
+        dev = self.device
+
+        def up(x, dt=None):
+            if x is None:
+                return None
+            if torch.is_tensor(x):
+                return x if x.is_cuda else x.to(dev, non_blocking=True)
+            t = torch.from_numpy(np.ascontiguousarray(x))
+            return t.to(dev, non_blocking=True)
+
+        ag, spec = self.render(up(batch["sounds"]), up(batch["clip_off"]), up(batch["index"]), up(batch["rirs"]),
+                               up(batch["rir_off"]), up(batch["rir_len"]), up(batch["silent"]),
+                               up(batch.get("d_clip_off")), up(batch.get("d_rir_off")), up(batch.get("d_rir_len")),
+                               want_audiogoal=want_audiogoal)
+        if pinned_out is not None:
+            pinned_out.copy_(spec, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return (ag.cpu() if ag is not None else None), pinned_out
+        return (ag.cpu().numpy() if ag is not None else None), spec.cpu().numpy()
+
+
+class SpectrogramSensor:
+    """Drop-in for the static method the task sensors call (nav.py:87): one (2, sr) waveform -> (65, 26, 2)."""
+
+    cls_uuid = "spectrogram"
+    _renderers: dict = {}
+
+    @staticmethod
+    def compute_spectrogram(audio_data, device="cuda"):
+        was_numpy = not torch.is_tensor(audio_data)
+        a = torch.as_tensor(np.asarray(audio_data, dtype=np.float32) if was_numpy else audio_data,
+                            dtype=torch.float32).to(device)
+        sr = int(a.shape[-1])
+        key = (sr, str(a.device))
+        r = SpectrogramSensor._renderers.get(key)
+        if r is None:
+            r = SpectrogramSensor._renderers[key] = AudioRenderer(sr, a.device)
+        out = r.compute_spectrogram(a.reshape(1, 2, sr).contiguous())[0]
+        return out.cpu().numpy() if was_numpy else out
