@@ -4,9 +4,12 @@
 // CPU emulation build used only by tests/ (tests/emul/cuda_emul.h)
 #include "cuda_emul.h"
 #define AVL_DYN_SMEM(name) unsigned char* name = ::smem_raw
+#define AVL_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emul::launch(dim3(grid), dim3(block), [&] { kern(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
 #define AVL_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#define AVL_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 #include <stdint.h>
 #include <math.h>

@@ -1,0 +1,493 @@
+// SIMT building blocks shared by the policy kernels: strided GEMM with fused epilogue / split-K,
+// im2col-gather GEMM (convolution), LayerNorm, varlen attention.  fp32 throughout.
+// These are the reference-accurate kernels; the tcgen05 tensor-core GEMM (gemm_tc.cu) takes over
+// the large dense contractions and is parity-tested against these.
+#pragma once
+#include "common.cuh"
+
+namespace avl {
+
+// ------------------------------------------------------------------------------------------ GEMM
+// C[m, n] (+)= sum_k A(m, k) * B(n, k)   (+ bias[n]) (ReLU) (+ residual[m, n])
+struct GemmOperand {
+  const float* p;
+  long long s_row;  // stride between rows (m for A, n for B)
+  long long s_k;    // stride along k
+};
+
+struct ConvGeom {  // implicit-GEMM view of an NHWC convolution input
+  int N, H, W, C, KH, KW, stride, pad, OH, OW;
+};
+
+struct GemmEpilogue {
+  const float* bias;      // [N] or null
+  const float* scale;     // [N] or null: per-column scale applied before bias (folded BatchNorm)
+  const float* residual;  // [M, ldr] or null
+  long long ldr;
+  int relu;
+  int accumulate;  // C += result (single split) ; with splits > 1 atomics are always used
+  const int* m_dev;  // optional device-side row count: M = min(*m_dev, M)
+  const int* k_dev;  // optional device-side reduction length: K = min(*k_dev, K)
+};
+
+constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
+
+template <bool CONV>
+__device__ __forceinline__ float gemm_load_a(const GemmOperand& A, const ConvGeom& g, int m, int k, int M, int K,
+                                             long long row_base, int oh_s, int ow_s) {
+  if (m >= M || k >= K) return 0.f;
+  if (!CONV) return __ldg(A.p + row_base + (long long)k * A.s_k);
+  int ci = k % g.C;
+  int rs = k / g.C;
+  int s = rs % g.KW, r = rs / g.KW;
+  int ih = oh_s + r, iw = ow_s + s;
+  if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.f;
+  return __ldg(A.p + row_base + ((long long)ih * g.W + iw) * g.C + ci);
+}
+
+// A_KC: A is k-contiguous (row-major [M][K]) -> threads walk k fastest when loading; otherwise m fastest.
+template <bool CONV, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GTHREADS, 2) gemm_kernel(GemmOperand A, GemmOperand B, float* C, long long ldc, int M,
+                                                        int N, int K, ConvGeom g, GemmEpilogue ep, int k_per_split) {
+  __shared__ __align__(16) float As[GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  if (ep.m_dev) M = min(M, *ep.m_dev);
+  if (ep.k_dev) K = min(K, *ep.k_dev);
+  const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+  if (m0 >= M) return;
+  const int kbeg = blockIdx.z * k_per_split;
+  if (kbeg >= K && gridDim.z > 1) return;
+  const int kend = min(K, kbeg + k_per_split);
+  const int ty = tid >> 4, tx = tid & 15;
+
+  // per-thread load coordinates (fixed across k tiles)
+  constexpr int A_PER = GBM * GBK / GTHREADS;  // 8
+  constexpr int B_PER = GBN * GBK / GTHREADS;  // 4
+  int a_m[A_PER], a_k[A_PER];
+  long long a_base[A_PER];
+  int a_oh[A_PER], a_ow[A_PER];
+#pragma unroll
+  for (int j = 0; j < A_PER; ++j) {
+    int i = tid + GTHREADS * j;
+    if (A_KC) { a_m[j] = i / GBK; a_k[j] = i % GBK; } else { a_k[j] = i / GBM; a_m[j] = i % GBM; }
+    int m = m0 + a_m[j];
+    a_oh[j] = a_ow[j] = 0;
+    if (CONV) {
+      int ow = m % g.OW;
+      int t = m / g.OW;
+      int oh = t % g.OH;
+      int n = t / g.OH;
+      a_base[j] = (long long)n * g.H * g.W * g.C;
+      a_oh[j] = oh * g.stride - g.pad;
+      a_ow[j] = ow * g.stride - g.pad;
+    } else {
+      a_base[j] = (long long)m * A.s_row;
+    }
+  }
+  int b_n[B_PER], b_k[B_PER];
+#pragma unroll
+  for (int j = 0; j < B_PER; ++j) {
+    int i = tid + GTHREADS * j;
+    if (B_KC) { b_n[j] = i / GBK; b_k[j] = i % GBK; } else { b_k[j] = i / GBN; b_n[j] = i % GBN; }
+  }
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[A_PER], rb[B_PER];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j)
+      ra[j] = gemm_load_a<CONV>(A, g, m0 + a_m[j], k0 + a_k[j], M, kend, a_base[j], a_oh[j], a_ow[j]);
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int n = n0 + b_n[j], k = k0 + b_k[j];
+      rb[j] = (n < N && k < kend) ? __ldg(B.p + (long long)n * B.s_row + (long long)k * B.s_k) : 0.f;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) As[a_k[j]][a_m[j]] = ra[j];
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) Bs[b_k[j]][b_n[j]] = rb[j];
+    __syncthreads();
+    if (k0 + GBK < kend) fetch(k0 + GBK);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      float a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[k][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool atomic = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      float* c = C + (long long)m * ldc + n;
+      if (atomic) {
+        atomicAdd(c, v);
+      } else {
+        if (ep.scale) v *= ep.scale[n];
+        if (ep.bias) v += ep.bias[n];
+        if (ep.residual) v += ep.residual[(long long)m * ep.ldr + n];
+        if (ep.relu) v = fmaxf(v, 0.f);
+        if (ep.accumulate) v += *c;
+        *c = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- LayerNorm
+// y = LN(x (+ res)) * gamma + beta over `cols` (<= 1024, multiple of 32) ; one warp per row.
+// Saves mean / rstd for the backward pass when the pointers are non-null.
+constexpr int LN_MAX_PER_LANE = 16;  // cols <= 512
+
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* y,
+                                     float* mean_out, float* rstd_out, const int* rows_dev, int rows_max, int cols,
+                                     float eps) {
+  const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int per = cols >> 5;
+  float v[LN_MAX_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < per) {
+      int c = lane + 32 * i;
+      float t = x[(size_t)row * cols + c];
+      if (res) t += res[(size_t)row * cols + c];
+      v[i] = t;
+      s += t;
+    }
+  }
+  float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < per) {
+      float d = v[i] - mean;
+      q += d * d;
+    }
+  }
+  float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < per) {
+      int c = lane + 32 * i;
+      y[(size_t)row * cols + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+  }
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// dx = LN backward; xin = (x + res) is recomputed from y:  xhat = (y - beta) / gamma is avoided by
+// passing the saved normalised input implicitly: we recompute xhat from x(+res), mean, rstd.
+// dgamma / dbeta are accumulated with atomics into [cols] buffers (pre-zeroed or accumulating).
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, const float* __restrict__ dy, float* dx,
+                                     float* dgamma, float* dbeta, const int* rows_dev, int rows_max, int cols) {
+  AVL_DYN_SMEM(ln_raw);  // 2 * cols floats
+  float* ln_smem = reinterpret_cast<float*>(ln_raw);
+  const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int per = cols >> 5;
+  float* sg = ln_smem;
+  float* sb = ln_smem + cols;
+  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) ln_smem[i] = 0.f;
+  __syncthreads();
+  float ag[LN_MAX_PER_LANE], ab[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) ag[i] = ab[i] = 0.f;
+  for (int row = blockIdx.x * nwarps + warp; row < rows; row += gridDim.x * nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      if (i < per) {
+        int c = lane + 32 * i;
+        float t = x[(size_t)row * cols + c];
+        if (res) t += res[(size_t)row * cols + c];
+        xh[i] = (t - mu) * rs;
+        float d = dy[(size_t)row * cols + c];
+        ag[i] += d * xh[i];
+        ab[i] += d;
+        g[i] = d * gamma[c];
+        s1 += g[i];
+        s2 += g[i] * xh[i];
+      }
+    }
+    s1 = warp_sum(s1) / (float)cols;
+    s2 = warp_sum(s2) / (float)cols;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      if (i < per) {
+        int c = lane + 32 * i;
+        dx[(size_t)row * cols + c] = rs * (g[i] - s1 - xh[i] * s2);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    if (i < per) {
+      int c = lane + 32 * i;
+      atomicAdd(&sg[c], ag[i]);
+      atomicAdd(&sb[c], ab[i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[c], sg[c]);
+    if (dbeta) atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
+// column sums of a [rows, cols] matrix accumulated into out[cols] (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ x, long long ld, const int* rows_dev, int rows_max, int cols,
+                              float* out) {
+  const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) s += x[(size_t)r * ld + c];
+  atomicAdd(&out[c], s);
+}
+
+// dx = dy * (y > 0) in place on dy (ReLU backward given the forward output)
+__global__ void relu_bwd_kernel(float* dy, const float* __restrict__ y, const int* rows_dev, long long rows_max,
+                                int cols) {
+  const long long n = (rows_dev ? min((long long)*rows_dev, rows_max) : rows_max) * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (y[i] <= 0.f) dy[i] = 0.f;
+}
+
+// --------------------------------------------------------------------------- varlen self-attention
+// qkv: [R, 3*D] packed rows (q | k | v), heads of 32; off[b]..off[b+1] are sample b's rows.
+// One CTA per (sample, head).  Scores never leave shared memory; lse is saved for the backward.
+constexpr int ATT_HD = 32;      // head dim
+constexpr int ATT_MAXV = 320;   // max tokens per sample
+constexpr int ATT_WARPS = 8;
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, float* out, float* lse, int D,
+                     float scale) {
+  AVL_DYN_SMEM(smem_raw);
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int r0 = off[b], V = off[b + 1] - r0;
+  float* Ks = reinterpret_cast<float*>(smem_raw);   // [V][33]
+  float* Vs = Ks + ATT_MAXV * 33;                   // [V][33]
+  float* Ps = Vs + ATT_MAXV * 33;                   // [warps][ATT_MAXV]
+  float* Qs = Ps + ATT_WARPS * ATT_MAXV;            // [warps][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = 3 * D;
+  for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
+    int j = i >> 5, d = i & 31;
+    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + d;
+    Ks[j * 33 + d] = row[D];
+    Vs[j * 33 + d] = row[2 * D];
+  }
+  __syncthreads();
+  float* ps = Ps + warp * ATT_MAXV;
+  float* qs = Qs + warp * 32;
+  for (int i = warp; i < V; i += ATT_WARPS) {
+    qs[lane] = qkv[(size_t)(r0 + i) * ld + h * ATT_HD + lane] * scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < V; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) s = fmaf(qs[d], Ks[j * 33 + d], s);
+      ps[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < V; j += 32) {
+      float p = __expf(ps[j] - mx);
+      ps[j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o = 0.f;
+    for (int j = 0; j < V; ++j) o = fmaf(ps[j], Vs[j * 33 + lane], o);
+    out[(size_t)(r0 + i) * D + h * ATT_HD + lane] = o / sum;
+    if (lane == 0 && lse) lse[(size_t)(r0 + i) * (D / ATT_HD) + h] = mx + __logf(sum);
+    __syncwarp();
+  }
+}
+
+// Backward with recomputation.  dqkv receives (dq | dk | dv) rows.
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_self_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, const float* __restrict__ out,
+                     const float* __restrict__ lse, const float* __restrict__ dout, float* dqkv, int D, float scale) {
+  AVL_DYN_SMEM(smem_raw);
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int r0 = off[b], V = off[b + 1] - r0;
+  float* Qs = reinterpret_cast<float*>(smem_raw);  // [V][33] (pre-scaled)
+  float* Ks = Qs + ATT_MAXV * 33;
+  float* Vs = Ks + ATT_MAXV * 33;
+  float* Gs = Vs + ATT_MAXV * 33;                  // dO
+  float* Ls = Gs + ATT_MAXV * 33;                  // lse [V]
+  float* Ds = Ls + ATT_MAXV;                       // D_i = dO_i . O_i  [V]
+  float* Wa = Ds + ATT_MAXV;                       // [warps][ATT_MAXV]
+  float* Wb = Wa + ATT_WARPS * ATT_MAXV;           // [warps][ATT_MAXV]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = 3 * D, H = D / ATT_HD;
+  for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
+    int j = i >> 5, d = i & 31;
+    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + d;
+    Qs[j * 33 + d] = row[0] * scale;
+    Ks[j * 33 + d] = row[D];
+    Vs[j * 33 + d] = row[2 * D];
+    Gs[j * 33 + d] = dout[(size_t)(r0 + j) * D + h * ATT_HD + d];
+  }
+  for (int i = threadIdx.x; i < V; i += blockDim.x) Ls[i] = lse[(size_t)(r0 + i) * H + h];
+  __syncthreads();
+  // D_i
+  for (int i = warp; i < V; i += ATT_WARPS) {
+    float t = Gs[i * 33 + lane] * out[(size_t)(r0 + i) * D + h * ATT_HD + lane];
+    t = warp_sum(t);
+    if (lane == 0) Ds[i] = t;
+  }
+  __syncthreads();
+  float* wa = Wa + warp * ATT_MAXV;
+  float* wb = Wb + warp * ATT_MAXV;
+  // pass 1: dQ_i = scale * sum_j dS_ij K_j
+  for (int i = warp; i < V; i += ATT_WARPS) {
+    const float li = Ls[i], di = Ds[i];
+    for (int j = lane; j < V; j += 32) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        s = fmaf(Qs[i * 33 + d], Ks[j * 33 + d], s);
+        dp = fmaf(Gs[i * 33 + d], Vs[j * 33 + d], dp);
+      }
+      float p = __expf(s - li);
+      wa[j] = p * (dp - di);
+    }
+    __syncwarp();
+    float dq = 0.f;
+    for (int j = 0; j < V; ++j) dq = fmaf(wa[j], Ks[j * 33 + lane], dq);
+    dqkv[(size_t)(r0 + i) * ld + h * ATT_HD + lane] = dq * scale;
+    __syncwarp();
+  }
+  // pass 2: dK_j = sum_i dS_ij Qs_i (Qs already carries the scale), dV_j = sum_i P_ij dO_i
+  for (int j = warp; j < V; j += ATT_WARPS) {
+    for (int i = lane; i < V; i += 32) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        s = fmaf(Qs[i * 33 + d], Ks[j * 33 + d], s);
+        dp = fmaf(Gs[i * 33 + d], Vs[j * 33 + d], dp);
+      }
+      float p = __expf(s - Ls[i]);
+      wa[i] = p;
+      wb[i] = p * (dp - Ds[i]);
+    }
+    __syncwarp();
+    float dk = 0.f, dv = 0.f;
+    for (int i = 0; i < V; ++i) {
+      dk = fmaf(wb[i], Qs[i * 33 + lane], dk);
+      dv = fmaf(wa[i], Gs[i * 33 + lane], dv);
+    }
+    dqkv[(size_t)(r0 + j) * ld + D + h * ATT_HD + lane] = dk;
+    dqkv[(size_t)(r0 + j) * ld + 2 * D + h * ATT_HD + lane] = dv;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------- decoder cross-attention (1 query / sample)
+// q: [B, D]; kv: [R, 2*D] (k | v); one CTA per sample, one warp per head (D/32 warps).
+__global__ void attn_cross_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                      const int* __restrict__ off, float* out, float* probs /* [R, H] */, int D,
+                                      float scale) {
+  AVL_DYN_SMEM(smem_raw);
+  float* Ps = reinterpret_cast<float*>(smem_raw);  // [H][ATT_MAXV]
+  const int b = blockIdx.x;
+  const int r0 = off[b], V = off[b + 1] - r0;
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, H = D / ATT_HD;
+  float* ps = Ps + h * ATT_MAXV;
+  const float qd = q[(size_t)b * D + h * ATT_HD + lane] * scale;
+  float mx = -INFINITY;
+  for (int j = 0; j < V; ++j) {
+    float s = warp_sum(qd * kv[(size_t)(r0 + j) * 2 * D + h * ATT_HD + lane]);
+    if (lane == 0) ps[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < V; j += 32) {
+    float p = __expf(ps[j] - mx);
+    ps[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  __syncwarp();
+  float o = 0.f;
+  for (int j = 0; j < V; ++j) {
+    float p = ps[j] * inv;
+    o = fmaf(p, kv[(size_t)(r0 + j) * 2 * D + D + h * ATT_HD + lane], o);
+    if (lane == 0 && probs) probs[(size_t)(r0 + j) * H + h] = p;
+  }
+  out[(size_t)b * D + h * ATT_HD + lane] = o;
+}
+
+__global__ void attn_cross_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                      const int* __restrict__ off, const float* __restrict__ probs,
+                                      const float* __restrict__ dout, float* dq, float* dkv, int D, float scale) {
+  AVL_DYN_SMEM(smem_raw);
+  float* Ws = reinterpret_cast<float*>(smem_raw);  // [H][ATT_MAXV] dP
+  const int b = blockIdx.x;
+  const int r0 = off[b], V = off[b + 1] - r0;
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, H = D / ATT_HD;
+  float* ws = Ws + h * ATT_MAXV;
+  const float g = dout[(size_t)b * D + h * ATT_HD + lane];
+  const float qd = q[(size_t)b * D + h * ATT_HD + lane];
+  float dsum = 0.f;  // D = sum_j p_j dP_j
+  for (int j = 0; j < V; ++j) {
+    float p = probs[(size_t)(r0 + j) * H + h];
+    float dp = warp_sum(g * kv[(size_t)(r0 + j) * 2 * D + D + h * ATT_HD + lane]);
+    if (lane == 0) ws[j] = dp;
+    dsum = fmaf(p, dp, dsum);
+    dkv[(size_t)(r0 + j) * 2 * D + D + h * ATT_HD + lane] = p * g;  // dV
+  }
+  __syncwarp();
+  float dqa = 0.f;
+  for (int j = 0; j < V; ++j) {
+    float p = probs[(size_t)(r0 + j) * H + h];
+    float ds = p * (ws[j] - dsum) * scale;
+    dqa = fmaf(ds, kv[(size_t)(r0 + j) * 2 * D + h * ATT_HD + lane], dqa);
+    dkv[(size_t)(r0 + j) * 2 * D + h * ATT_HD + lane] = ds * qd;  // dK
+  }
+  dq[(size_t)b * D + h * ATT_HD + lane] = dqa;
+}
+
+}  // namespace avl

@@ -55,6 +55,14 @@ extern thread_local int linear_tid;
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDeviceToHost = 2,
+       cudaMemcpyHostToDevice = 1 };
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memcpy(d, s, n); return 0; }
 
 static inline void __syncthreads() { emul::ctx->block_bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emul::ctx->warp_bar[emul::linear_tid >> 5]->arrive_and_wait(); }
@@ -96,6 +104,9 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdividef(float a, float b) { return a / b; }
 #define __expf(a) expf(a)
+#define __logf(a) logf(a)
+using std::min;
+using std::max;
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 static inline double cospi(double x) { return cos(M_PI * x); }

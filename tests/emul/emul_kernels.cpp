@@ -10,6 +10,7 @@ int avl_num_sms() { return 2; }
 
 #include "../../avlen_b200/csrc/audio.cu"
 #include "../../avlen_b200/csrc/rl.cu"
+#include "../../avlen_b200/csrc/smt.cu"
 
 #define EMUL_API extern "C" __attribute__((visibility("default")))
 
