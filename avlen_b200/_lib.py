@@ -21,6 +21,7 @@ _SIGNATURES = {
     "avl_version": [],
     "avl_last_cuda_error": [],
     "avl_device_sm_count": [],
+    "avl_launch_count": [],
     "avl_audio_create": [I, ctypes.POINTER(c_void_p)],
     "avl_audio_destroy": [P],
     "avl_audio_status": [P, ctypes.POINTER(c_int)],
@@ -38,7 +39,7 @@ _SIGNATURES = {
     "avl_grad_sumsq": [P, L, P, P, P],
     "avl_clip_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P, F, P],
 }
-_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
+_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_launch_count": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
 
 _lib = None
 

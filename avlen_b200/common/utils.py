@@ -1,0 +1,136 @@
+"""Torch-side pieces of ss_baselines/common/utils.py that sit on the hot path:
+``CustomFixedCategorical``, ``CategoricalNet``, ``batch_obs``, ``linear_decay`` — same names and semantics,
+arithmetic on the CUDA kernels of csrc/rl.cu."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import nn as K
+from .. import ops
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the hand-written GEMM (forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return K.linear(x.contiguous(), w, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        rows, N = gy.shape
+        Kd = w.shape[1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            K.call("avl_gemm", K.fptr(gy), N, 1, K.fptr(w), 1, Kd, gx.data_ptr(), Kd, rows, Kd, N, None, 0, 0, 1,
+                   K.stream())
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros_like(w)
+            K.call("avl_gemm", K.fptr(gy), 1, N, K.fptr(x), 1, Kd, gw.data_ptr(), Kd, N, Kd, rows, None, 0, 0,
+                   max(1, min(64, rows // 256)), K.stream())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = torch.zeros(N, device=gy.device, dtype=torch.float32)
+            ones = torch.ones(rows, 1, device=gy.device, dtype=torch.float32)
+            K.call("avl_gemm", K.fptr(gy), 1, N, K.fptr(ones), 1, 1, gb.data_ptr(), 1, N, 1, rows, None, 0, 0,
+                   max(1, min(64, rows // 256)), K.stream())
+        return gx, gw, gb
+
+
+def cuda_linear(x, w, b=None):
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (b is not None and b.requires_grad)):
+        return _LinearFn.apply(x, w, b)
+    return K.linear(x.contiguous(), w, b)
+
+
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.reshape(x.size(0), -1)
+
+
+class CustomFixedCategorical:
+    """common/utils.py:44-58 without materialising a torch.distributions object: keeps the logits and answers
+    sample()/mode()/log_probs()/entropy()/probs through the categorical kernels.  ``sample`` draws its uniforms
+    from torch's CUDA generator and applies inverse-CDF selection (bit-exact given the uniforms)."""
+
+    def __init__(self, logits):
+        self.logits = logits
+        self._act_cache = None
+
+    def _act(self, uniforms):
+        return ops.categorical_act(self.logits.detach().contiguous(), uniforms)
+
+    def sample(self, sample_shape=None, uniforms=None):
+        if uniforms is None:
+            uniforms = torch.rand(self.logits.shape[0], device=self.logits.device, dtype=torch.float32)
+        a, lp, p = self._act(uniforms.contiguous())
+        self._act_cache = (a, lp, p)
+        return a
+
+    def mode(self):
+        a, lp, p = self._act(None)
+        self._act_cache = (a, lp, p)
+        return a
+
+    def log_probs(self, actions):
+        if self._act_cache is not None and self._act_cache[0] is actions:
+            return self._act_cache[1]
+        lp, _, _ = ops.categorical_eval(self.logits, actions)
+        return lp
+
+    def entropy(self):
+        acts = torch.zeros(self.logits.shape[0], 1, device=self.logits.device, dtype=torch.int64)
+        _, ent, _ = ops.categorical_eval(self.logits, acts)
+        return ent
+
+    @property
+    def probs(self):
+        if self._act_cache is not None:
+            return self._act_cache[2]
+        acts = torch.zeros(self.logits.shape[0], 1, device=self.logits.device, dtype=torch.int64)
+        return ops.categorical_eval(self.logits.detach(), acts)[2]
+
+
+class CategoricalNet(nn.Module):
+    """common/utils.py:61-72: Linear head (orthogonal init, gain 0.01) returning ``(distribution, logits)``."""
+
+    def __init__(self, num_inputs, num_outputs):
+        super().__init__()
+        self.linear = nn.Linear(num_inputs, num_outputs)
+        nn.init.orthogonal_(self.linear.weight, gain=0.01)
+        nn.init.constant_(self.linear.bias, 0)
+
+    def forward(self, x):
+        x = cuda_linear(x, self.linear.weight, self.linear.bias)
+        return CustomFixedCategorical(logits=x), x
+
+
+def linear_decay(epoch: int, total_num_updates: int) -> float:
+    return 1 - (epoch / float(total_num_updates))
+
+
+def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, pinned: Optional[Dict] = None):
+    """common/utils.py:129-156: list of per-env observation dicts -> dict of stacked float32 tensors on ``device``.
+
+    The reference inflates uint8 images to fp32 on the host before the copy; here each sensor is stacked once into
+    pinned staging memory in its source dtype and converted on the device after an asynchronous copy."""
+    out = {}
+    for sensor in observations[0]:
+        arr = np.stack([np.asarray(o[sensor]) for o in observations])
+        t = torch.from_numpy(arr)
+        if pinned is not None:
+            buf = pinned.get(sensor)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = pinned[sensor] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            buf.copy_(t)
+            t = buf
+        out[sensor] = t.to(device=device, non_blocking=True).to(dtype=torch.float32)
+    return out

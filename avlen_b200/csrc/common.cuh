@@ -30,7 +30,12 @@ extern "C" int avl_set_cuda_error(int e);
     }                                                         \
   } while (0)
 
-#define AVL_LAUNCH_CHECK() AVL_CUDA_CHECK(cudaGetLastError())
+extern "C" void avl_count_launch();
+#define AVL_LAUNCH_CHECK()                \
+  do {                                    \
+    avl_count_launch();                   \
+    AVL_CUDA_CHECK(cudaGetLastError());   \
+  } while (0)
 
 #define AVL_API extern "C" __attribute__((visibility("default")))
 

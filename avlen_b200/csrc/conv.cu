@@ -1,0 +1,291 @@
+// Encoder building blocks: NHWC convolution / fully-connected as an
+// im2col-gather GEMM with weights in the reference's native OIHW layout, GroupNorm(16) with fused
+// residual + ReLU, the 128->64 area resize with the /255 RGB normalisation, max / average pooling.
+// fp32 SIMT reference-accurate path (see gemm_tc.cu for the tensor-core path).
+#include "nn_kernels.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ GroupNorm (NHWC, one CTA per sample)
+// smt_resnet.py:22-33: nn.GroupNorm(16, C), eps 1e-5, affine.  y = gn(x) (+ residual) (ReLU).
+constexpr int GN_THREADS = 512;
+__global__ void __launch_bounds__(GN_THREADS) groupnorm_nhwc_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ residual, float* y,
+                                                                    int HW, int C, int groups, float eps, int relu) {
+  __shared__ float ps[GN_THREADS], pq[GN_THREADS];
+  __shared__ float gmean[64], grstd[64];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int c = tid % C;            // C divides GN_THREADS
+  const int rows_per_iter = GN_THREADS / C;
+  const int cg = C / groups;
+  const float* xs = x + (size_t)n * HW * C;
+  float s = 0.f, q = 0.f;
+  for (int p = tid / C; p < HW; p += rows_per_iter) {
+    float v = xs[(size_t)p * C + c];
+    s += v;
+    q += v * v;
+  }
+  ps[tid] = s;
+  pq[tid] = q;
+  __syncthreads();
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int t = 0; t < GN_THREADS; ++t) {
+      if ((t % C) / cg == tid) { S += (double)ps[t]; Q += (double)pq[t]; }
+    }
+    double cnt = (double)HW * cg;
+    double m = S / cnt;
+    double var = Q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    gmean[tid] = (float)m;
+    grstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int g = c / cg;
+  const float a = grstd[g] * gamma[c];
+  const float b = beta[c] - gmean[g] * a;
+  float* ys = y + (size_t)n * HW * C;
+  const float* rs = residual ? residual + (size_t)n * HW * C : nullptr;
+  for (int p = tid / C; p < HW; p += rows_per_iter) {
+    size_t i = (size_t)p * C + c;
+    float v = fmaf(xs[i], a, b);
+    if (rs) v += rs[i];
+    if (relu) v = fmaxf(v, 0.f);
+    ys[i] = v;
+  }
+}
+
+// -------------------------------------------------- area resize (exact 2x2 mean) + optional scale (rgb / 255)
+// smt_cnn.py:83-95 + common/utils.py:515-517 (interpolate(mode="area") 128 -> 64).  NHWC in, NHWC out.
+__global__ void resize_half_kernel(const float* __restrict__ x, float* y, int N, int H, int W, int C, float scale) {
+  const int OH = H / 2, OW = W / 2;
+  long long total = (long long)N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    const float* p = x + (((long long)n * H + 2 * oh) * W + 2 * ow) * C + c;
+    // the reference divides by 255 first, then averages (smt_cnn.py:83-86)
+    float a = p[0] * scale, b = p[C] * scale, d = p[(long long)W * C] * scale, e = p[(long long)W * C + C] * scale;
+    y[i] = (a + b + d + e) * 0.25f;
+  }
+}
+
+// cat([rgb / 255, depth], channel) for the av_nav VisualCNN (visual_cnn.py:143-150).  NHWC.
+__global__ void concat_rgbd_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, float* y,
+                                   long long pixels, int c_rgb, int c_depth, float rgb_scale) {
+  const int C = c_rgb + c_depth;
+  long long total = pixels * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    y[i] = (c < c_rgb) ? rgb[p * c_rgb + c] * rgb_scale : depth[p * c_depth + (c - c_rgb)];
+  }
+}
+
+// append `extra` (N, E) as E constant planes to an NHWC tensor (category label planes, audio_cnn.py:144-147)
+__global__ void append_planes_kernel(const float* __restrict__ x, const float* __restrict__ extra, float* y,
+                                     int N, int HW, int C, int E) {
+  const int CO = C + E;
+  long long total = (long long)N * HW * CO;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % CO);
+    long long p = i / CO;
+    int n = (int)(p / HW);
+    y[i] = (c < C) ? x[p * C + c] : extra[(long long)n * E + (c - C)];
+  }
+}
+
+// max pool 3x3 stride 2 pad 1 (torchvision resnet18 stem), NHWC
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* y, int N, int H, int W, int C, int OH,
+                                    int OW) {
+  long long total = (long long)N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int ow = (int)(t % OW);
+    t /= OW;
+    int oh = (int)(t % OH);
+    int n = (int)(t / OH);
+    float m = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        m = fmaxf(m, x[(((long long)n * H + ih) * W + iw) * C + c]);
+      }
+    }
+    y[i] = m;
+  }
+}
+
+// global average pool NHWC -> (N, C)
+__global__ void avgpool_kernel(const float* __restrict__ x, float* y, int N, int HW, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  int c = i % C, n = i / C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += x[((long long)n * HW + p) * C + c];
+  y[i] = s / (float)HW;
+}
+
+// y[b, :] = W[:, a_b] + bias  (Linear on a one-hot action, policy.py:628-635 + action_encoder)
+__global__ void onehot_linear_kernel(const long long* __restrict__ actions, const float* __restrict__ W,
+                                     const float* __restrict__ bias, float* y, long long ldy, int B, int out_dim,
+                                     int n_actions) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * out_dim) return;
+  int o = i % out_dim, b = i / out_dim;
+  int a = (int)actions[b];
+  float v = bias[o];
+  if (a >= 0 && a < n_actions) v += W[o * n_actions + a];
+  y[(long long)b * ldy + o] = v;
+}
+
+// copy src (rows, cols) into a column slice of dst (rows, ldd)
+__global__ void copy_cols_kernel(const float* __restrict__ src, long long lds, float* dst, long long ldd, int rows,
+                                 int cols) {
+  long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cols);
+    long long r = i / cols;
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+static int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  long long cap = (long long)avl_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// NHWC convolution (also fully-connected layers after a flatten, as a kernel covering the whole map):
+//   y[n, oh, ow, co] = act( scale[co] * sum_{r,s,ci} x[n, oh*stride - pad + r, ow*stride - pad + s, ci] * w[co, ci, r, s]
+//                           + bias[co] + residual[n, oh, ow, co] )
+// x: (N, H, W, C) ; w: (Cout, C, KH, KW) reference-native OIHW ; y: rows of length ldy (>= Cout), so the
+// result can be written straight into a column slice of a wider feature matrix.
+AVL_API int avl_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w, int Cout, int KH, int KW,
+                           int stride, int pad, const float* scale, const float* bias, const float* residual,
+                           long long ldr, int relu, float* y, long long ldy, void* stream) {
+  if (N < 0 || H < 1 || W < 1 || C < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 || pad < 0) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !w || !y) return AVL_ERR_ARG;
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.C = C; g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
+  g.OH = (H + 2 * pad - KH) / stride + 1;
+  g.OW = (W + 2 * pad - KW) / stride + 1;
+  if (g.OH < 1 || g.OW < 1) return AVL_ERR_ARG;
+  long long M = (long long)N * g.OH * g.OW;
+  if (M > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  const int K = KH * KW * C;
+  GemmEpilogue ep;
+  ep.bias = bias; ep.scale = scale; ep.residual = residual; ep.ldr = ldr; ep.relu = relu; ep.accumulate = 0;
+  ep.m_dev = nullptr; ep.k_dev = nullptr;
+  GemmOperand A = {x, 0, 1}, B = {w, (long long)K, 1};
+  dim3 grid(avl_div_up(M, GBM), avl_div_up(Cout, GBN), 1);
+  auto kern = gemm_kernel<true, true, true>;
+  AVL_LAUNCH(kern, grid, GTHREADS, 0, (cudaStream_t)stream, A, B, y, ldy, (int)M, Cout, K, g, ep, K);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                              int N, int HW, int C, int groups, float eps, int relu, void* stream) {
+  if (N < 0 || HW < 1 || C < 1 || groups < 1 || groups > 64 || C % groups || GN_THREADS % C) return AVL_ERR_UNSUPPORTED;
+  if (N == 0) return AVL_OK;
+  if (!x || !gamma || !beta || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(groupnorm_nhwc_kernel, N, GN_THREADS, 0, (cudaStream_t)stream, x, gamma, beta, residual, y, HW, C, groups,
+             eps, relu);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, float scale, void* stream) {
+  if (N < 0 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(resize_half_kernel, ew_grid((long long)N * H * W * C / 4), 256, 0, (cudaStream_t)stream, x, y, N, H, W, C,
+             scale);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_concat_rgbd(const float* rgb, const float* depth, float* y, long long pixels, int c_rgb, int c_depth,
+                            float rgb_scale, void* stream) {
+  if (pixels < 0 || c_rgb < 0 || c_depth < 0 || c_rgb + c_depth < 1) return AVL_ERR_ARG;
+  if (pixels == 0) return AVL_OK;
+  if (!y || (c_rgb && !rgb) || (c_depth && !depth)) return AVL_ERR_ARG;
+  AVL_LAUNCH(concat_rgbd_kernel, ew_grid(pixels * (c_rgb + c_depth)), 256, 0, (cudaStream_t)stream, rgb, depth, y,
+             pixels, c_rgb, c_depth, rgb_scale);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_append_planes(const float* x, const float* extra, float* y, int N, int HW, int C, int E,
+                              void* stream) {
+  if (N < 0 || HW < 1 || C < 1 || E < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !extra || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(append_planes_kernel, ew_grid((long long)N * HW * (C + E)), 256, 0, (cudaStream_t)stream, x, extra, y, N,
+             HW, C, E);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  if (N < 0 || H < 1 || W < 1 || C < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !y) return AVL_ERR_ARG;
+  int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  AVL_LAUNCH(maxpool3x3s2_kernel, ew_grid((long long)N * OH * OW * C), 256, 0, (cudaStream_t)stream, x, y, N, H, W, C,
+             OH, OW);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_avgpool_global(const float* x, float* y, int N, int HW, int C, void* stream) {
+  if (N < 0 || HW < 1 || C < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(avgpool_kernel, avl_div_up((long long)N * C, 256), 256, 0, (cudaStream_t)stream, x, y, N, HW, C);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_onehot_linear(const long long* actions, const float* W, const float* bias, float* y, long long ldy,
+                              int B, int out_dim, int n_actions, void* stream) {
+  if (B < 0 || out_dim < 1 || n_actions < 1) return AVL_ERR_ARG;
+  if (B == 0) return AVL_OK;
+  if (!actions || !W || !bias || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(onehot_linear_kernel, avl_div_up((long long)B * out_dim, 256), 256, 0, (cudaStream_t)stream, actions, W,
+             bias, y, ldy, B, out_dim, n_actions);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_copy_cols(const float* src, long long lds, float* dst, long long ldd, int rows, int cols,
+                          void* stream) {
+  if (rows < 0 || cols < 0) return AVL_ERR_ARG;
+  if (rows == 0 || cols == 0) return AVL_OK;
+  if (!src || !dst) return AVL_ERR_ARG;
+  AVL_LAUNCH(copy_cols_kernel, ew_grid((long long)rows * cols), 256, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows,
+             cols);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}

@@ -3,6 +3,9 @@
 
 static int g_last_cuda_error = 0;
 static int g_num_sms = 0;
+static long long g_launches = 0;
+
+extern "C" void avl_count_launch() { ++g_launches; }
 
 extern "C" int avl_set_cuda_error(int e) {
   g_last_cuda_error = e;
@@ -28,3 +31,6 @@ AVL_API int avl_last_cuda_error(void) { return g_last_cuda_error; }
 AVL_API const char* avl_last_cuda_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_cuda_error); }
 
 AVL_API int avl_device_sm_count(void) { return avl_num_sms(); }
+
+// Number of kernels this library has launched so far in this process (bench.py's gpu_launches).
+AVL_API long long avl_launch_count(void) { return g_launches; }

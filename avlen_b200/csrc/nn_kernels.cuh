@@ -5,7 +5,7 @@
 #pragma once
 #include "common.cuh"
 
-namespace avl {
+namespace {  // internal linkage: this header is included by several translation units
 
 // ------------------------------------------------------------------------------------------ GEMM
 // C[m, n] (+)= sum_k A(m, k) * B(n, k)   (+ bias[n]) (ReLU) (+ residual[m, n])
@@ -106,7 +106,13 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_kernel(GemmOperand A, GemmOp
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       int n = n0 + b_n[j], k = k0 + b_k[j];
-      rb[j] = (n < N && k < kend) ? __ldg(B.p + (long long)n * B.s_row + (long long)k * B.s_k) : 0.f;
+      if (CONV) {
+        // weights stay in the reference's native OIHW layout: k = (r*KW + s)*C + ci
+        long long o = (long long)n * B.s_row + (long long)(k % g.C) * (g.KH * g.KW) + (k / g.C);
+        rb[j] = (n < N && k < kend) ? __ldg(B.p + o) : 0.f;
+      } else {
+        rb[j] = (n < N && k < kend) ? __ldg(B.p + (long long)n * B.s_row + (long long)k * B.s_k) : 0.f;
+      }
     }
   };
   fetch(kbeg);
@@ -490,4 +496,4 @@ __global__ void attn_cross_bwd_kernel(const float* __restrict__ q, const float* 
   dq[(size_t)b * D + h * ATT_HD + lane] = dqa;
 }
 
-}  // namespace avl
+}  // namespace

@@ -17,7 +17,6 @@
 #include "nn_kernels.cuh"
 
 namespace {
-using namespace avl;
 
 // ------------------------------------------------------------------------------ token compaction
 __device__ __forceinline__ bool slot_valid(float m) { return !((1.f - m) > 0.f); }  // smt_state_encoder.py:107
@@ -166,6 +165,7 @@ struct Launcher {
   cudaStream_t s;
   int err = 0;
   void check() {
+    avl_count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess && !err) { avl_set_cuda_error((int)e); err = AVL_ERR_CUDA; }
   }

@@ -1,0 +1,133 @@
+"""Functional wrappers over the encoder kernels (csrc/conv.cu): NHWC convolution / FC, GroupNorm(+residual+ReLU),
+area resize, pooling.  CUDA tensors in, CUDA tensors out, no CPU path."""
+from __future__ import annotations
+
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import call, dptr, fptr, stream
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+_lib.register({
+    "avl_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
+    "avl_groupnorm_fwd": [P, P, P, P, P, I, I, I, I, F, I, P],
+    "avl_resize_half": [P, P, I, I, I, I, F, P],
+    "avl_concat_rgbd": [P, P, P, L, I, I, F, P],
+    "avl_append_planes": [P, P, P, I, I, I, I, P],
+    "avl_maxpool3x3s2": [P, P, I, I, I, I, P],
+    "avl_avgpool_global": [P, P, I, I, I, P],
+    "avl_onehot_linear": [P, P, P, P, L, I, I, I, P],
+    "avl_copy_cols": [P, L, P, L, I, I, P],
+    "avl_gemm": [P, L, L, P, L, L, P, L, I, I, I, P, I, I, I, P],
+    "avl_layernorm_fwd": [P, P, P, P, P, P, I, I, P],
+    "avl_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, P],
+    "avl_attn_self_fwd": [P, P, I, I, P, P, P],
+    "avl_attn_self_bwd": [P, P, I, I, P, P, P, P, P],
+    "avl_attn_cross_fwd": [P, P, P, I, I, P, P, P],
+    "avl_attn_cross_bwd": [P, P, P, P, P, I, I, P, P, P],
+})
+
+
+def conv_out(size, k, stride, pad):
+    return (size + 2 * pad - k) // stride + 1
+
+
+def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=None, out=None):
+    """x (N,H,W,C) NHWC; w (Cout,C,KH,KW) OIHW (the reference's nn.Conv2d layout). Returns (N,OH,OW,Cout)."""
+    N, H, W, C = x.shape
+    Cout, Cw, KH, KW = w.shape
+    assert Cw == C, (Cw, C)
+    OH, OW = conv_out(H, KH, stride, pad), conv_out(W, KW, stride, pad)
+    if out is None:
+        out = torch.empty((N, OH, OW, Cout), device=x.device, dtype=torch.float32)
+        ldy = Cout
+    else:  # (N*OH*OW, >=Cout) strided destination (column slice of a feature matrix)
+        assert out.stride(-1) == 1
+        ldy = out.stride(0)
+    ldr = Cout if residual is not None else 0
+    call("avl_conv2d_fwd", fptr(x), N, H, W, C, fptr(w), Cout, KH, KW, stride, pad, fptr(scale), fptr(bias),
+         fptr(residual), ldr, int(relu), out.data_ptr(), ldy, stream())
+    return out
+
+
+def linear_flat(x_nhwc, w, bias=None, relu=False, out=None):
+    """nn.Linear applied to the NCHW-flattened activation, computed from the NHWC tensor: the (O, C*H*W) weight is
+    viewed as an (O, C, H, W) kernel covering the whole map (no repacking of the reference's weights)."""
+    N, H, W, C = x_nhwc.shape
+    O = w.shape[0]
+    y = conv2d(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu, out=out)
+    return y.view(N, O) if out is None else out
+
+
+def linear(x, w, bias=None, relu=False, out=None):
+    """y = x @ w.T + b for row-major x (rows, K), w (N, K)."""
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((rows, N), device=x.device, dtype=torch.float32)
+    call("avl_gemm", fptr(x), x.stride(0), 1, fptr(w), K, 1, out.data_ptr(), out.stride(0), rows, N, K, fptr(bias),
+         int(relu), 0, 1, stream())
+    return out
+
+
+def groupnorm(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, out=None):
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    call("avl_groupnorm_fwd", fptr(x), fptr(gamma), fptr(beta), fptr(residual), fptr(out), N, H * W, C, groups,
+         float(eps), int(relu), stream())
+    return out
+
+
+def resize_half(x, scale=1.0):
+    N, H, W, C = x.shape
+    y = torch.empty((N, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
+    call("avl_resize_half", fptr(x), fptr(y), N, H, W, C, float(scale), stream())
+    return y
+
+
+def concat_rgbd(rgb, depth, rgb_scale=1.0 / 255.0):
+    N, H, W, _ = (rgb if rgb is not None else depth).shape
+    cr = rgb.shape[-1] if rgb is not None else 0
+    cd = depth.shape[-1] if depth is not None else 0
+    y = torch.empty((N, H, W, cr + cd), device=(rgb if rgb is not None else depth).device, dtype=torch.float32)
+    call("avl_concat_rgbd", fptr(rgb), fptr(depth), fptr(y), N * H * W, cr, cd, float(rgb_scale), stream())
+    return y
+
+
+def append_planes(x, extra):
+    N, H, W, C = x.shape
+    E = extra.shape[1]
+    y = torch.empty((N, H, W, C + E), device=x.device, dtype=torch.float32)
+    call("avl_append_planes", fptr(x), fptr(extra.contiguous()), fptr(y), N, H * W, C, E, stream())
+    return y
+
+
+def maxpool3x3s2(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, conv_out(H, 3, 2, 1), conv_out(W, 3, 2, 1), C), device=x.device, dtype=torch.float32)
+    call("avl_maxpool3x3s2", fptr(x), fptr(y), N, H, W, C, stream())
+    return y
+
+
+def avgpool_global(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    call("avl_avgpool_global", fptr(x), fptr(y), N, H * W, C, stream())
+    return y
+
+
+def onehot_linear(actions, w, bias, out):
+    """out[:, :] = one_hot(actions) @ w.T + bias written into a (B, out_dim) column slice."""
+    B = actions.shape[0]
+    call("avl_onehot_linear", dptr(actions.reshape(B).contiguous(), torch.int64), fptr(w), fptr(bias), out.data_ptr(),
+         out.stride(0), B, w.shape[0], w.shape[1], stream())
+    return out
+
+
+def copy_cols(src, dst):
+    rows, cols = src.shape
+    call("avl_copy_cols", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, stream())
+    return dst

@@ -1,0 +1,142 @@
+"""DD-PPO trainer entry (ss_baselines/savi/ddppo/algo/ddppo_trainer.py:61-1200), registered as ``"ddppo"``:
+``trainer = baseline_registry.get_trainer("ddppo")(config); trainer.train()`` (savi/run.py:110-121).
+
+One process per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment, as torchrun sets them);
+environments, rollout storage, external memories, belief state and audio rendering are rank-local (no exchange
+during rollouts); the update exchanges ONE flat gradient all-reduce per minibatch over NCCL.  Straggler
+preemption (ddppo_trainer.py:952-959) is kept as an option: ranks stop collecting once more than ``sync_frac`` of
+the ranks have finished and at least a quarter of the rollout is done (counter in the torch.distributed store).
+"""
+from __future__ import annotations
+
+import os
+import time
+import types
+
+import torch
+import torch.distributed as distrib
+
+from ...common import spaces
+from ...common.baseline_registry import baseline_registry
+from ...synth_env import SyntheticVectorEnv
+from ..models.belief_predictor import BeliefPredictor
+from ..models.rollout_storage import RolloutStorage
+from ..ppo.policy import AudioNavSMTPolicy
+from ..ppo.ppo_trainer import PPOTrainer
+from .ddppo import DDPPO
+
+
+def savi_config(**overrides):
+    """Values of ss_baselines/savi/config/semantic_audionav/savi.yaml (:10-66) as a flat namespace."""
+    cfg = dict(NUM_PROCESSES=64, NUM_UPDATES=2, clip_param=0.2, ppo_epoch=2, num_mini_batch=2, value_loss_coef=0.5,
+               entropy_coef=0.05, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, num_steps=150, hidden_size=512,
+               use_gae=True, gamma=0.99, tau=0.95, use_normalized_advantage=False, policy_type="smt",
+               use_belief_predictor=True, use_external_memory=True, memory_size=150, smt_hidden_size=256, nhead=8,
+               num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu", freeze_encoders=True,
+               pretraining=False, use_label_belief=True, use_location_belief=True, online_training=True,
+               sync_frac=0.6, distrib_backend="nccl", use_preemption=False, seed=1234, sampling_rate=16000,
+               host_buffers=False, has_distractor_sound=False)
+    cfg.update(overrides)
+    return types.SimpleNamespace(**cfg)
+
+
+def init_distrib(backend="nccl"):
+    """ddp_utils.py:129-182 without SLURM: rank / world from torchrun's environment variables."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not distrib.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        distrib.init_process_group(backend=backend, rank=rank, world_size=world)
+    return local_rank, rank, world
+
+
+@baseline_registry.register_trainer(name="ddppo")
+class DDPPOTrainer(PPOTrainer):
+    SHORT_ROLLOUT_THRESHOLD: float = 0.25
+
+    def __init__(self, config=None):
+        super().__init__(config or savi_config())
+        self.rollouts = None
+        self.world_size, self.world_rank = 1, 0
+
+    def _setup_actor_critic_agent(self, ppo_cfg, observation_space=None):
+        cfg = ppo_cfg
+        obs_space = observation_space or spaces.savi_observation_space(cfg.sampling_rate)
+        self.obs_space = obs_space
+        self.actor_critic = AudioNavSMTPolicy(
+            observation_space=obs_space, action_space=spaces.Discrete(4), hidden_size=cfg.smt_hidden_size,
+            nhead=cfg.nhead, num_encoder_layers=cfg.num_encoder_layers, num_decoder_layers=cfg.num_decoder_layers,
+            dropout=cfg.dropout, activation=cfg.activation, pretraining=cfg.pretraining,
+            use_category_input=cfg.has_distractor_sound)
+        self.actor_critic.to(self.device)
+        if cfg.freeze_encoders:
+            self.actor_critic.net.freeze_encoders()
+            self.actor_critic.net.set_eval_encoders()
+        self.actor_critic.net.smt_state_encoder.rows_per_sample_cap = cfg.memory_size + 1
+        if cfg.use_belief_predictor:
+            bcfg = types.SimpleNamespace(use_label_belief=cfg.use_label_belief, online_training=cfg.online_training,
+                                         use_location_belief=cfg.use_location_belief, weighting_factor=0.5,
+                                         current_pred_only=False)
+            self.belief_predictor = BeliefPredictor(bcfg, self.device, None, None, cfg.smt_hidden_size,
+                                                    cfg.NUM_PROCESSES, cfg.has_distractor_sound).to(self.device)
+            self.belief_predictor.freeze_encoders()
+            self.belief_predictor.set_eval_encoders()
+        self.agent = DDPPO(actor_critic=self.actor_critic, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,
+                           num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
+                           entropy_coef=cfg.entropy_coef, lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm,
+                           use_normalized_advantage=cfg.use_normalized_advantage)
+
+    def setup(self, envs=None):
+        cfg = self.config
+        local_rank, self.world_rank, self.world_size = init_distrib(cfg.distrib_backend)
+        self.device = torch.device("cuda", local_rank)
+        torch.cuda.set_device(self.device)
+        torch.manual_seed(cfg.seed + self.world_rank)
+        self.envs = envs or SyntheticVectorEnv(cfg.NUM_PROCESSES, self.device, seed=cfg.seed + self.world_rank,
+                                               sr=cfg.sampling_rate, host_buffers=cfg.host_buffers,
+                                               distractor=cfg.has_distractor_sound)
+        self._setup_actor_critic_agent(cfg)
+        if self.world_size > 1:
+            self.agent.init_distributed(find_unused_params=True)
+        em_size = cfg.memory_size + cfg.num_steps  # ddppo_trainer.py:656-657
+        dim = self.actor_critic.net.memory_dim
+        self.rollouts = RolloutStorage(cfg.num_steps, self.envs.num_envs, self.obs_space, spaces.Discrete(4),
+                                       cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
+                                       cfg.memory_size, 3, 3, dim, dim, dim + 32, 256, num_recurrent_layers=1,
+                                       max_dialog_len=77)
+        self.rollouts.to(self.device)
+        observations = self.envs.reset()
+        if self.belief_predictor is not None:
+            self.belief_predictor.update(observations, None)
+        for sensor in self.rollouts.observations:
+            self.rollouts.observations[sensor][0].copy_(observations[sensor])
+        return self
+
+    def collect_rollout(self):
+        """The 150-step rollout loop (ddppo_trainer.py:894-959)."""
+        cfg = self.config
+        store = distrib.distributed_c10d._get_default_store() if (self.world_size > 1 and cfg.use_preemption) else None
+        for step in range(cfg.num_steps):
+            self._collect_rollout_step(self.rollouts)
+            if store is not None and step >= cfg.num_steps * self.SHORT_ROLLOUT_THRESHOLD:
+                if int(store.add("num_done", 0)) > cfg.sync_frac * self.world_size:
+                    break
+        if store is not None:
+            store.add("num_done", 1)
+        return self.rollouts.step * self.envs.num_envs
+
+    def train(self):
+        if self.rollouts is None:
+            self.setup()
+        cfg = self.config
+        t0 = time.time()
+        count_steps = 0
+        stats = None
+        for _update in range(cfg.NUM_UPDATES):
+            count_steps += self.collect_rollout()
+            stats = self._update_agent(cfg, self.rollouts)
+        torch.cuda.synchronize()
+        fps = count_steps * self.world_size / max(1e-9, time.time() - t0)
+        return {"fps": fps, "value_loss": stats[0], "action_loss": stats[1], "dist_entropy": stats[2]}

@@ -1,0 +1,283 @@
+"""SAVi / AVLEN policies (ss_baselines/savi/ppo/policy.py:39-674) behind the reference's API, on CUDA kernels.
+
+``Policy.act / get_value / evaluate_actions`` keep the reference signatures, argument meaning and return order
+(SURVEY.md §8b).  Parameter names and shapes equal the reference's ``state_dict`` (Appendix A) so checkpoints load.
+"""
+from __future__ import annotations
+
+import abc
+import itertools
+import logging
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ... import nn as K
+from ...common.utils import CategoricalNet, cuda_linear
+from ..models.audio_cnn import AudioCNN
+from ..models.smt_cnn import SMTCNN
+from ..models.smt_state_encoder import IndexedMemory, SMTStateEncoder
+
+SPECTROGRAM, POSE, CATEGORY = "spectrogram", "pose", "category"
+CATEGORY_BELIEF, LOCATION_BELIEF = "category_belief", "location_belief"
+
+
+class CriticHead(nn.Module):
+    def __init__(self, input_size):
+        super().__init__()
+        self.fc = nn.Linear(input_size, 1)
+        nn.init.orthogonal_(self.fc.weight)
+        nn.init.constant_(self.fc.bias, 0)
+
+    def forward(self, x):
+        return cuda_linear(x, self.fc.weight, self.fc.bias)
+
+
+class CriticHead2(nn.Module):
+    def __init__(self, input_size):
+        super().__init__()
+        self.fc = nn.Linear(input_size, 2)
+        nn.init.orthogonal_(self.fc.weight)
+        nn.init.constant_(self.fc.bias, 0)
+
+    def forward(self, x):
+        return cuda_linear(x, self.fc.weight, self.fc.bias)
+
+
+class Policy(nn.Module):
+    """policy.py:39-276.  Every policy owns all seven heads, used or not (Appendix A)."""
+
+    def __init__(self, net, dim_actions, dim_actions_option=2):
+        super().__init__()
+        self.net = net
+        self.dim_actions = dim_actions
+        self.dim_actions_option = dim_actions_option
+        self.action_distribution_option = CategoricalNet(self.net.output_size, self.dim_actions_option)
+        self.action_distribution_goal = CategoricalNet(self.net.output_size, self.dim_actions)
+        self.action_distribution_vln = CategoricalNet(self.net.output_size, self.dim_actions)
+        self.critic_goal = CriticHead(self.net.output_size)
+        self.critic_option = CriticHead(self.net.output_size)
+        self.uncertainty_option = CriticHead2(self.net.output_size)
+        self.critic_vln = CriticHead(self.net.output_size)
+
+    def forward(self, *x):
+        raise NotImplementedError
+
+    def act(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks,
+            deterministic=False, uniforms=None):
+        features, rnn_hidden_states, ext_memory_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks)
+        distribution, _ = self.action_distribution_goal(features)
+        value = self.critic_goal(features)
+        action = distribution.mode() if deterministic else distribution.sample(uniforms=uniforms)
+        action_log_probs = distribution.log_probs(action)
+        return value, action, action_log_probs, rnn_hidden_states, ext_memory_feats, distribution.probs
+
+    def act_option(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks,
+                   query_state, last_query_info, deterministic=False, uniforms=None):
+        features, rnn_hidden_states, ext_memory_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks, query_state,
+            last_query_info)
+        distribution, _ = self.action_distribution_option(features)
+        value = self.critic_option(features)
+        unct = self.uncertainty_option(features)
+        action = distribution.mode() if deterministic else distribution.sample(uniforms=uniforms)
+        action_log_probs = distribution.log_probs(action)
+        return value, unct, action, action_log_probs, rnn_hidden_states, ext_memory_feats, distribution.probs
+
+    def get_value(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks):
+        features, _, _ = self.net(observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks)
+        return self.critic_goal(features)
+
+    def get_value_option(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks,
+                         query_state, last_query_info):
+        features, _, _ = self.net(observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks,
+                                  query_state, last_query_info)
+        return self.critic_option(features)
+
+    def evaluate_actions(self, observations, rnn_hidden_states, prev_actions, masks, action, ext_memory,
+                         ext_memory_masks):
+        features, rnn_hidden_states, ext_memory_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks)
+        distribution, _ = self.action_distribution_goal(features)
+        value = self.critic_goal(features)
+        action_log_probs = distribution.log_probs(action)
+        distribution_entropy = distribution.entropy().mean()
+        return value, action_log_probs, distribution_entropy, rnn_hidden_states, ext_memory_feats
+
+    def evaluate_actions_option(self, observations, rnn_hidden_states, prev_actions, masks, action, ext_memory,
+                                ext_memory_masks, query_state, last_query_info):
+        features, rnn_hidden_states, ext_memory_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks, query_state,
+            last_query_info)
+        distribution, _ = self.action_distribution_option(features)
+        value = self.critic_option(features)
+        unct = self.uncertainty_option(features)
+        action_log_probs = distribution.log_probs(action)
+        distribution_entropy = distribution.entropy().mean()
+        return (value, unct, action_log_probs, distribution_entropy, rnn_hidden_states, ext_memory_feats,
+                distribution.probs)
+
+    # ---- fused path used by PPO.update: features -> raw head outputs, no distribution objects -------------
+    def evaluate_heads(self, which, observations, rnn_hidden_states, prev_actions, masks, ext_memory,
+                       ext_memory_masks, *extra):
+        features, _, _ = self.net(observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks,
+                                  *extra)
+        if which == "goal":
+            head, critic = self.action_distribution_goal, self.critic_goal
+        elif which == "option":
+            head, critic = self.action_distribution_option, self.critic_option
+        else:
+            head, critic = self.action_distribution_vln, self.critic_vln
+        logits = cuda_linear(features, head.linear.weight, head.linear.bias)
+        value = critic(features)
+        unct = self.uncertainty_option(features) if which == "option" else None
+        return logits, value, unct
+
+
+class Net(nn.Module, metaclass=abc.ABCMeta):
+    @abc.abstractmethod
+    def forward(self, observations, rnn_hidden_states, prev_actions, masks):
+        pass
+
+    @property
+    @abc.abstractmethod
+    def output_size(self):
+        pass
+
+    @property
+    @abc.abstractmethod
+    def num_recurrent_layers(self):
+        pass
+
+    @property
+    @abc.abstractmethod
+    def is_blind(self):
+        pass
+
+
+class AudioNavSMTNet(Net):
+    """policy.py:501-674: SMTCNN(rgb, depth) | action embedding | AudioCNN(spectrogram) | [category] | pose
+    -> scene-memory transformer with the belief vector as decoder query."""
+
+    def __init__(self, observation_space, action_space, hidden_size=128, use_pretrained=False, pretrained_path="",
+                 use_belief_as_goal=True, use_label_belief=True, use_location_belief=True, use_belief_encoding=False,
+                 normalize_category_distribution=False, use_category_input=False, **kwargs):
+        super().__init__()
+        self._use_action_encoding = True
+        self._use_residual_connection = False
+        self._use_belief_as_goal = use_belief_as_goal
+        self._use_label_belief = use_label_belief
+        self._use_location_belief = use_location_belief
+        self._hidden_size = hidden_size
+        self._action_size = action_space.n
+        self._use_belief_encoder = use_belief_encoding
+        self._normalize_category_distribution = normalize_category_distribution
+        self._use_category_input = use_category_input
+        if not use_belief_as_goal or use_belief_encoding:
+            raise _lib.AvlenError("only use_belief_as_goal=True, use_belief_encoding=False is built "
+                                  "(the setting of every reference yaml)")
+        assert SPECTROGRAM in observation_space.spaces
+        self.goal_encoder = AudioCNN(observation_space, 128, SPECTROGRAM)
+        audio_feature_dims = 128
+        self.visual_encoder = SMTCNN(observation_space)
+        self.action_encoder = nn.Linear(self._action_size, 16)
+        nfeats = self.visual_encoder.feature_dims + 16 + audio_feature_dims
+        self._cat_col = nfeats
+        if self._use_category_input:
+            nfeats += 21
+        assert POSE in observation_space.spaces
+        pose_dims = observation_space.spaces[POSE].shape[0]
+        pose_indices = (nfeats, nfeats + pose_dims)
+        nfeats += pose_dims
+        self._feature_size = nfeats
+        self.smt_state_encoder = SMTStateEncoder(nfeats, dim_feedforward=hidden_size, pose_indices=pose_indices,
+                                                 **kwargs)
+        self.state_size = self.smt_state_encoder.hidden_state_size
+        if use_pretrained:
+            assert pretrained_path != ""
+            self.pretrained_initialization(pretrained_path)
+        self.train()
+
+    @property
+    def memory_dim(self):
+        return self._feature_size
+
+    @property
+    def output_size(self):
+        return self.smt_state_encoder.hidden_state_size
+
+    @property
+    def is_blind(self):
+        return False
+
+    @property
+    def num_recurrent_layers(self):
+        return -1
+
+    def _belief(self, observations, n, device):
+        belief = torch.zeros((n, self._hidden_size), device=device)
+        if self._use_label_belief:
+            cb = observations[CATEGORY_BELIEF]
+            if self._normalize_category_distribution:
+                cb = nn.functional.softmax(cb, dim=1)
+            belief[:, :21] = cb
+        if self._use_location_belief:
+            belief[:, 21:23] = observations[LOCATION_BELIEF]
+        return belief
+
+    def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks):
+        x = self.get_features(observations, prev_actions)
+        belief = self._belief(observations, x.shape[0], x.device)
+        x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
+        return x_att, rnn_hidden_states, x
+
+    def pretrained_initialization(self, path):
+        logging.info(f"AudioNavSMTNet ===> Loading pretrained model from {path}")
+        state_dict = torch.load(path, map_location="cpu")["state_dict"]
+        cleaned = {k[len("actor_critic.net."):]: v for k, v in state_dict.items() if "actor_critic.net." in k}
+        self.load_state_dict(cleaned, strict=False)
+
+    def freeze_encoders(self):
+        """Freeze goal, visual and action encoders. Pose / fusion / transformer stay trainable (policy.py:643-653)."""
+        for p in itertools.chain(self.goal_encoder.parameters(), self.visual_encoder.parameters(),
+                                 self.action_encoder.parameters()):
+            p.requires_grad = False
+
+    def set_eval_encoders(self):
+        self.goal_encoder.eval()
+        self.visual_encoder.eval()
+
+    def get_features(self, observations, prev_actions):
+        """policy.py:660-674: [visual 128 | action 16 | audio 128 | (category 21) | pose 4] written straight into
+        the column slices of one feature matrix (no torch.cat)."""
+        n = observations[POSE].shape[0]
+        dev = observations[POSE].device
+        enc_trainable = torch.is_grad_enabled() and any(
+            p.requires_grad for p in itertools.chain(self.goal_encoder.parameters(), self.visual_encoder.parameters(),
+                                                     self.action_encoder.parameters()))
+        if enc_trainable:
+            raise _lib.AvlenError("encoder backward is not built yet: call net.freeze_encoders() "
+                                  "(savi.yaml: freeze_encoders True) or run under torch.no_grad()")
+        with torch.no_grad():
+            x = torch.empty((n, self._feature_size), device=dev, dtype=torch.float32)
+            self.visual_encoder(observations, out=x[:, 0:128])
+            if prev_actions.shape[1] == self._action_size:  # already one-hot (policy.py:629-630)
+                K.linear(prev_actions.float().contiguous(), self.action_encoder.weight, self.action_encoder.bias,
+                         out=x[:, 128:144])
+            else:
+                K.onehot_linear(prev_actions, self.action_encoder.weight, self.action_encoder.bias, x[:, 128:144])
+            self.goal_encoder(observations, out=x[:, 144:272])
+            col = 272
+            if self._use_category_input:
+                K.copy_cols(observations[CATEGORY].contiguous(), x[:, col:col + 21])
+                col += 21
+            K.copy_cols(observations[POSE].contiguous(), x[:, col:col + 4])
+        return x
+
+
+class AudioNavSMTPolicy(Policy):
+    def __init__(self, observation_space, action_space, hidden_size=128, **kwargs):
+        super().__init__(AudioNavSMTNet(observation_space, action_space, hidden_size=hidden_size, **kwargs),
+                         action_space.n)

@@ -1,0 +1,121 @@
+"""PPO (ss_baselines/savi/ppo/ppo.py:30-303; plain-SAVi loss = av_nav/ppo/ppo.py:60-151) on fused CUDA kernels.
+
+Per minibatch: policy heads -> ONE fused loss kernel that returns every loss term and the gradient of the total loss
+w.r.t. logits / value / uncertainty logits -> autograd backward from those -> one flat-buffer global-norm clip + Adam
+kernel.  No ``.item()`` inside the minibatch loop; the six scalars are read back once per update.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+EPS_PPO = 1e-5
+
+
+def flatten_parameters(module: nn.Module):
+    """Re-points every trainable parameter (and its .grad) into one flat fp32 buffer so that the gradient
+    all-reduce, the global-norm clip and Adam each touch a single contiguous array."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    n = sum(p.numel() for p in params)
+    dev = params[0].device
+    flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+    flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+    off = 0
+    for p in params:
+        k = p.numel()
+        flat_p[off:off + k].copy_(p.data.reshape(-1))
+        p.data = flat_p[off:off + k].view_as(p.data)
+        p.grad = flat_g[off:off + k].view_as(p.data)
+        off += k
+    return params, flat_p, flat_g
+
+
+class PPO(nn.Module):
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef, lr=None,
+                 eps=None, max_grad_norm=None, use_clipped_value_loss=True, use_normalized_advantage=True,
+                 unct_coef=0.5, policy_head="goal"):
+        super().__init__()
+        self.actor_critic = actor_critic
+        self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
+        self.value_loss_coef, self.entropy_coef, self.unct_coef = value_loss_coef, entropy_coef, unct_coef
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.use_normalized_advantage = use_normalized_advantage
+        self.policy_head = policy_head  # "goal": SAVi evaluate_actions ; "option": AVLEN evaluate_actions_option
+        self.device = next(actor_critic.parameters()).device
+        self._params, self._flat_p, self._flat_g = flatten_parameters(actor_critic)
+        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps)
+        self._loss = ops.PpoLoss(self.device)
+        self.world_size = 1
+
+    def forward(self, *x):
+        raise NotImplementedError
+
+    def get_advantages(self, rollouts):
+        return ops.advantages(rollouts.returns, rollouts.value_preds, rollouts.step, self.use_normalized_advantage,
+                              EPS_PPO)
+
+    def _reduce_gradients(self):
+        """DD-PPO hook: all-reduce of the flat gradient (overridden in ddppo.DDPPO)."""
+        return 1.0
+
+    def update(self, rollouts, perm_fn=None):
+        advantages = self.get_advantages(rollouts)
+        sums = torch.zeros(8, device=self.device)
+        n_updates = 0
+        option = self.policy_head == "option"
+        for _e in range(self.ppo_epoch):
+            perm = perm_fn(rollouts.rewards.size(1)) if perm_fn is not None else None
+            for sample in rollouts.recurrent_generator(advantages, self.num_mini_batch, perm=perm):
+                (obs_batch, hidden_batch, actions_batch, actions_option_batch, prev_actions_batch, value_preds_batch,
+                 return_batch, masks_batch, old_lp_batch, adv_targ, rl_masks_batch, unct_gt_batch, em_goal, em_option,
+                 _em_vln, _em_dialog, em_masks, _em_vln_masks, _all_dialog, query_state_batch, last_query_info,
+                 _agent_step) = sample
+                self._flat_g.zero_()
+                if option:
+                    logits, values, unct = self.actor_critic.evaluate_heads(
+                        "option", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_option, em_masks,
+                        query_state_batch, last_query_info)
+                    acts, rl_mask, ugt = actions_option_batch, rl_masks_batch.float(), unct_gt_batch
+                else:
+                    logits, values, unct = self.actor_critic.evaluate_heads(
+                        "goal", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_goal, em_masks)
+                    acts, rl_mask, ugt = actions_batch, None, None
+                out, dlogits, dvalues, dunct = self._loss(
+                    logits.detach(), acts, old_lp_batch, adv_targ, values.detach(), value_preds_batch, return_batch,
+                    rl_mask, None if unct is None else unct.detach(), ugt, self.clip_param, self.value_loss_coef,
+                    self.entropy_coef, self.unct_coef, self.use_clipped_value_loss)
+                self.before_backward(None)
+                heads, grads = [logits, values], [dlogits, dvalues]
+                if unct is not None:
+                    heads.append(unct)
+                    grads.append(dunct)
+                torch.autograd.backward(heads, grads)
+                self.after_backward(None)
+                scale = self._reduce_gradients()
+                self.before_step()
+                self.optimizer.step(self.max_grad_norm, grad_scale=scale)
+                self.after_step()
+                sums += out
+                n_updates += 1
+        s = (sums / max(1, n_updates)).tolist()  # the only host synchronisation of the update
+        value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]
+        # the reference returns the *sums* of the two debug means (ppo.py:279-280, :289)
+        return value_loss, action_loss, entropy, s[5] * n_updates, s[6] * n_updates, unct_loss
+
+    def before_backward(self, loss):
+        pass
+
+    def after_backward(self, loss):
+        pass
+
+    def before_step(self):
+        pass  # clip_grad_norm_ is fused into the optimizer kernel
+
+    def after_step(self):
+        pass
+
+    def state_dict(self, *a, **k):
+        return super().state_dict(*a, **k)  # keys prefixed 'actor_critic.' (checkpoint format, ppo_trainer.py:196)

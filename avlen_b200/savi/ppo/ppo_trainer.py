@@ -1,0 +1,57 @@
+"""The two hot loops of the SAVi trainer (ss_baselines/savi/ppo/ppo_trainer.py:323-897 ``_collect_rollout_step``,
+:1045-1093 ``_update_agent``) for the plain SMT policy (``policy_type: "smt"``), device-resident.
+
+The reference's per-env Python loops, ``.item()`` / ``.cpu()`` round trips and pipe traffic to env workers are not
+reproduced; the call sequence on the policy / belief predictor / storage objects is the reference's.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class PPOTrainer:
+    def __init__(self, config=None):
+        self.config = config
+        self.actor_critic = None
+        self.agent = None
+        self.belief_predictor = None
+        self.envs = None
+        self.device = None
+
+    @torch.no_grad()
+    def _collect_rollout_step(self, rollouts, current_episode_reward=None, running_episode_stats=None, uniforms=None):
+        """One environment step for all envs (ppo_trainer.py:323-897, smt policy path :606-623, :714-894)."""
+        s = rollouts.step
+        step_observation = {k: v[s] for k, v in rollouts.observations.items()}
+        values, actions, actions_log_probs, recurrent_hidden_states, external_memory_features, _probs = \
+            self.actor_critic.act(step_observation, rollouts.recurrent_hidden_states[s], rollouts.prev_actions[s],
+                                  rollouts.masks[s], rollouts.external_memory_goal[:, s],
+                                  rollouts.external_memory_masks[s], uniforms=uniforms)
+        observations, rewards, dones = self.envs.step(actions)
+        masks = (~dones).float().unsqueeze(1)
+        if current_episode_reward is not None:
+            current_episode_reward += rewards
+            if running_episode_stats is not None:
+                running_episode_stats["reward"] += (1 - masks) * current_episode_reward
+                running_episode_stats["count"] += 1 - masks
+            current_episode_reward *= masks
+        if self.belief_predictor is not None:  # :890-894: belief for the NEXT observation
+            self.belief_predictor.update(observations, dones)
+        rollouts.insert(observations, recurrent_hidden_states, actions, None, actions_log_probs, values, rewards, masks,
+                        masks, external_memory_features, None, None, None, None, None, None, None, None, None, None,
+                        None, None)
+        return self.envs.num_envs
+
+    def _update_agent(self, ppo_cfg, rollouts):
+        """ppo_trainer.py:1045-1093: bootstrap value, GAE, PPO.update, after_update."""
+        with torch.no_grad():
+            s = rollouts.step
+            last_observation = {k: v[s] for k, v in rollouts.observations.items()}
+            next_value = self.actor_critic.get_value(last_observation, rollouts.recurrent_hidden_states[s],
+                                                     rollouts.prev_actions[s], rollouts.masks[s],
+                                                     rollouts.external_memory_goal[:, s],
+                                                     rollouts.external_memory_masks[s])
+        rollouts.compute_returns(next_value, ppo_cfg.use_gae, ppo_cfg.gamma, ppo_cfg.tau)
+        value_loss, action_loss, dist_entropy, _vd, _rd, _ul = self.agent.update(rollouts)
+        rollouts.after_update()
+        return value_loss, action_loss, dist_entropy

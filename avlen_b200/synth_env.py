@@ -1,0 +1,107 @@
+"""Synthetic VectorEnv stand-in (SURVEY.md §8b "Trainer entry", §8d): generated Habitat-shaped observations.
+
+habitat-sim rendering and the SoundSpaces graph walk are out of scope (north_star); this class plays the role the
+reference's ``VectorEnv`` plays for the trainer — ``reset`` / ``step`` / ``num_envs`` — but every per-env quantity is
+a device tensor, the audio observation is produced by the batched CUDA renderer (rows A+B) and rewards / dones are
+drawn from a seeded generator (Bernoulli(1/80) dones, N(0,1) rewards).  With ``host_buffers=True`` the visual frames
+live in pinned host memory and are copied host->device every step, actions are read back to the host (the ``e2e``
+path of bench.py); otherwise a pool of frames is resident in HBM.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import synth
+from .audio import AudioRenderer
+
+
+class SyntheticVectorEnv:
+    def __init__(self, num_envs, device, seed=1234, sr=16000, pool=4, distractor=False, host_buffers=False,
+                 done_prob=1.0 / 80.0, rir_len=None):
+        self.num_envs, self.device, self.sr = num_envs, torch.device(device), sr
+        self.host_buffers = host_buffers
+        rng = np.random.default_rng(seed)
+        self._g = torch.Generator(device="cpu").manual_seed(seed)
+        self.pool = pool
+        n = num_envs
+        # visual frame pool: rgb kept as uint8 (what habitat returns), depth fp32
+        rgb = torch.from_numpy(rng.integers(0, 256, size=(pool, n, 128, 128, 3), dtype=np.uint8))
+        depth = torch.from_numpy(rng.random((pool, n, 128, 128, 1), dtype=np.float32))
+        if host_buffers:
+            self._rgb, self._depth = rgb.pin_memory(), depth.pin_memory()
+            self._actions_host = torch.zeros(n, 1, dtype=torch.int64).pin_memory()
+        else:
+            self._rgb, self._depth = rgb.to(self.device), depth.to(self.device)
+        self.h2d_bytes_per_step = (rgb[0].numel() + depth[0].numel() * 4) if host_buffers else 0
+        self.d2h_bytes_per_step = n * 8 if host_buffers else 0
+        # audio assets resident on the device (RIR bank + sound bank), per-env descriptors
+        b = synth.make_audio_batch(seed + 1, n, sr=sr, distractor=distractor, fixed_len=rir_len, silent_frac=0.0)
+        dev = self.device
+        self._audio = {k: torch.from_numpy(v).to(dev) for k, v in b.items() if isinstance(v, np.ndarray)}
+        self._clip_secs = torch.from_numpy((b["clip_len_all"][b["clip_id"]] // sr).astype(np.int32)).to(dev)
+        self.renderer = AudioRenderer(sr, dev)
+        self.done_prob = done_prob
+        self._t = 0
+        self._episode_step = torch.zeros(n, device=dev)
+        self._pose_xy = torch.zeros(n, 2, device=dev)
+        self._heading = torch.zeros(n, device=dev)
+        cat = torch.zeros(n, 21)
+        cat[torch.arange(n), torch.from_numpy(rng.integers(0, 21, n))] = 1.0
+        self._category = cat.to(dev)
+        self._silent_after = torch.from_numpy(rng.integers(20, 200, n).astype(np.float32)).to(dev)
+        # pre-drawn step randomness (so the timed loop has no host RNG work)
+        self._rand_pool = None
+
+    def _visual(self):
+        i = self._t % self.pool
+        if self.host_buffers:
+            rgb = self._rgb[i].to(self.device, non_blocking=True)
+            depth = self._depth[i].to(self.device, non_blocking=True)
+        else:
+            rgb, depth = self._rgb[i], self._depth[i]
+        return rgb.float(), depth  # batch_obs: everything becomes float32 (common/utils.py:149-154)
+
+    def _observe(self):
+        a = self._audio
+        silent = (self._episode_step > self._silent_after).to(torch.int32)  # simulator.py:646
+        _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
+                                       silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
+                                       want_audiogoal=False)
+        rgb, depth = self._visual()
+        pose = torch.cat([self._pose_xy, self._heading[:, None], self._episode_step[:, None]], 1)
+        n = self.num_envs
+        return {"rgb": rgb, "depth": depth, "spectrogram": spec, "pose": pose, "category": self._category,
+                "category_belief": torch.zeros(n, 21, device=self.device),
+                "location_belief": torch.zeros(n, 2, device=self.device)}
+
+    def reset(self):
+        self._t = 0
+        self._episode_step.zero_()
+        return self._observe()
+
+    def step(self, actions):
+        """actions: (N, 1) int64 device tensor.  Returns (obs dict, rewards (N,1), dones (N,) bool)."""
+        if self.host_buffers:  # the env worker needs the actions on the host (ppo_trainer.py:698-714)
+            self._actions_host.copy_(actions, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        n, dev = self.num_envs, self.device
+        self._t += 1
+        r = torch.rand(n, 3, device=dev)
+        dones = r[:, 0] < self.done_prob
+        a = actions.view(n)
+        # toy kinematics so that relative poses are non-trivial: FORWARD=1, LEFT=2, RIGHT=3 (simulator.py:494)
+        self._heading = torch.where(a == 2, self._heading + 0.5236, torch.where(a == 3, self._heading - 0.5236, self._heading))
+        fwd = (a == 1).float()
+        self._pose_xy = self._pose_xy + 0.5 * fwd[:, None] * torch.stack([torch.cos(self._heading), -torch.sin(self._heading)], 1)
+        self._episode_step = self._episode_step + 1
+        nd = (~dones).float()
+        self._episode_step = self._episode_step * nd
+        self._pose_xy = self._pose_xy * nd[:, None]
+        self._heading = self._heading * nd
+        self._audio["index"] = ((self._audio["index"] + 1) % self._clip_secs).to(torch.int32)  # simulator.py:668
+        rewards = (r[:, 1:2] - 0.5)
+        return self._observe(), rewards, dones
+
+    def close(self):
+        self.renderer.close()

@@ -7,10 +7,12 @@ AVL_EMUL_DEFINE_GLOBALS
 
 extern "C" int avl_set_cuda_error(int e) { return e; }
 int avl_num_sms() { return 2; }
+extern "C" void avl_count_launch() {}
 
 #include "../../avlen_b200/csrc/audio.cu"
 #include "../../avlen_b200/csrc/rl.cu"
 #include "../../avlen_b200/csrc/smt.cu"
+#include "../../avlen_b200/csrc/conv.cu"
 
 #define EMUL_API extern "C" __attribute__((visibility("default")))
 

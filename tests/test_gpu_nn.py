@@ -1,0 +1,178 @@
+"""GPU parity of the dense / encoder kernels (rows C, D, E, F, M) through the C-ABI against plain PyTorch fp32
+(same ops the reference calls) — tolerance 1e-3 relative (north_star), observed ~1e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / max(1e-12, float(b.abs().max())))
+
+
+@pytest.mark.parametrize("shape", [
+    # N, H, W, C, Cout, KH, KW, stride, pad
+    (5, 65, 26, 2, 32, 5, 5, 2, 0),     # AudioCNN conv1
+    (5, 31, 11, 32, 64, 3, 3, 2, 0),    # AudioCNN conv2
+    (5, 15, 5, 64, 64, 3, 3, 1, 0),     # AudioCNN conv3
+    (3, 128, 128, 4, 32, 8, 8, 4, 0),   # av_nav VisualCNN conv1
+    (3, 64, 64, 3, 16, 7, 7, 1, 3),     # custom_resnet18 conv1
+    (3, 64, 64, 16, 16, 3, 3, 1, 1),    # layer1
+    (3, 64, 64, 16, 32, 3, 3, 2, 1),    # layer2 downsampling 3x3
+    (3, 64, 64, 16, 32, 1, 1, 2, 0),    # layer2 downsample 1x1
+    (3, 8, 8, 128, 128, 3, 3, 1, 1),    # layer4
+    (3, 65, 26, 2, 64, 7, 7, 2, 3),     # torchvision resnet18 stem on the spectrogram
+    (7, 13, 3, 64, 128, 13, 3, 1, 0),   # FC 2496 -> 128 as a whole-map kernel
+])
+def test_conv2d_matches_torch(shape):
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, KH, KW, s, p = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, H, W, C, generator=g)
+    w = torch.randn(Co, C, KH, KW, generator=g) / (C * KH * KW) ** 0.5
+    b = torch.randn(Co, generator=g)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=s, padding=p)).permute(0, 2, 3, 1)
+    out = K.conv2d(x.cuda(), w.cuda(), b.cuda(), s, p, relu=True).cpu()
+    assert out.shape == ref.shape
+    assert rel(out, ref) < TOL
+
+
+def test_conv_scale_residual_and_strided_output():
+    from avlen_b200 import nn as K
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, 9, 4, 32, generator=g)
+    w = torch.randn(32, 32, 3, 3, generator=g) / 17
+    sc, b = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g)
+    res = torch.randn(4, 9, 4, 32, generator=g)
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, None, 1, 1) * sc.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+                 + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    out = K.conv2d(x.cuda(), w.cuda(), b.cuda(), 1, 1, relu=True, scale=sc.cuda(), residual=res.cuda()).cpu()
+    assert rel(out, ref) < TOL
+    # FC after NCHW flatten written into a column slice
+    xf = torch.randn(6, 8, 8, 128, generator=g)
+    wf = torch.randn(64, 128 * 8 * 8, generator=g) / 90
+    bf = torch.randn(64, generator=g)
+    ref = xf.permute(0, 3, 1, 2).reshape(6, -1) @ wf.t() + bf
+    big = torch.zeros(6, 200, device="cuda")
+    K.linear_flat(xf.cuda(), wf.cuda(), bf.cuda(), out=big[:, 70:134])
+    assert rel(big[:, 70:134].cpu(), ref) < TOL
+    assert float(big[:, :70].abs().max()) == 0 and float(big[:, 134:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("C,HW", [(16, (64, 64)), (32, (32, 32)), (64, (16, 16)), (128, (8, 8)), (128, (9, 4)), (16, (65, 26))])
+def test_groupnorm_residual_relu(C, HW):
+    from avlen_b200 import nn as K
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, *HW, C, generator=g) * 2 + 0.5
+    ga, be = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(3, *HW, C, generator=g)
+    ref = F.relu(F.group_norm(x.permute(0, 3, 1, 2), 16, ga, be, 1e-5) + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    out = K.groupnorm(x.cuda(), ga.cuda(), be.cuda(), 16, 1e-5, relu=True, residual=res.cuda()).cpu()
+    assert rel(out, ref) < TOL
+
+
+def test_resize_pool_concat():
+    from avlen_b200 import nn as K
+    g = torch.Generator().manual_seed(2)
+    rgb = torch.randint(0, 256, (3, 128, 128, 3), generator=g).float()
+    ref = F.interpolate(rgb.permute(0, 3, 1, 2) / 255.0, size=(64, 64), mode="area").permute(0, 2, 3, 1)
+    assert rel(K.resize_half(rgb.cuda(), 1 / 255.0).cpu(), ref) < 1e-6
+    x = torch.randn(3, 33, 13, 64, generator=g)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(K.maxpool3x3s2(x.cuda()).cpu(), ref)
+    assert rel(K.avgpool_global(x.cuda()).cpu(), x.mean((1, 2))) < 1e-5
+    depth = torch.rand(3, 128, 128, 1, generator=g)
+    ref = torch.cat([rgb / 255.0, depth], -1)
+    assert rel(K.concat_rgbd(rgb.cuda(), depth.cuda()).cpu(), ref) < 1e-6
+    cat = torch.rand(3, 21, generator=g)
+    sp = torch.rand(3, 65, 26, 2, generator=g)
+    ref = torch.cat([sp, cat.view(3, 1, 1, 21).expand(3, 65, 26, 21)], -1)
+    assert torch.equal(K.append_planes(sp.cuda(), cat.cuda()).cpu(), ref)
+
+
+@pytest.mark.parametrize("M,N,K_", [(4800, 256, 288), (301, 768, 256), (64, 4, 256), (5000, 16, 5), (1, 1, 256)])
+def test_gemm_and_linear_autograd(M, N, K_):
+    from avlen_b200.common.utils import cuda_linear
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K_, generator=g, requires_grad=True)
+    w = (torch.randn(N, K_, generator=g) / K_ ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g, requires_grad=True)
+    gy = torch.randn(M, N, generator=g)
+    (F.linear(x, w, b) * gy).sum().backward()
+    xd, wd, bd = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
+    y = cuda_linear(xd, wd, bd)
+    (y * gy.cuda()).sum().backward()
+    assert rel(y.detach().cpu(), F.linear(x, w, b).detach()) < TOL
+    assert rel(xd.grad.cpu(), x.grad) < TOL and rel(wd.grad.cpu(), w.grad) < TOL and rel(bd.grad.cpu(), b.grad) < TOL
+
+
+def test_layernorm_fwd_bwd():
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401  (registers signatures)
+    g = torch.Generator().manual_seed(5)
+    rows, cols = 1000, 256
+    x = torch.randn(rows, cols, generator=g, requires_grad=True)
+    res = torch.randn(rows, cols, generator=g)
+    ga = (torch.rand(cols, generator=g) + 0.5).requires_grad_(True)
+    be = torch.randn(cols, generator=g, requires_grad=True)
+    dy = torch.randn(rows, cols, generator=g)
+    ref = F.layer_norm(x + res, (cols,), ga, be, 1e-5)
+    (ref * dy).sum().backward()
+    xd, rd, gd, bd, dyd = (t.detach().cuda() for t in (x, res, ga, be, dy))
+    y, stats, dx = torch.empty_like(xd), torch.empty(2 * rows, device="cuda"), torch.empty_like(xd)
+    dg, db = torch.zeros(cols, device="cuda"), torch.zeros(cols, device="cuda")
+    _lib.call("avl_layernorm_fwd", xd.data_ptr(), rd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(),
+              stats.data_ptr(), rows, cols, _lib.stream())
+    _lib.call("avl_layernorm_bwd", xd.data_ptr(), rd.data_ptr(), gd.data_ptr(), stats.data_ptr(), dyd.data_ptr(),
+              dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, cols, _lib.stream())
+    assert rel(y.cpu(), ref.detach()) < TOL and rel(dx.cpu(), x.grad) < TOL
+    assert rel(dg.cpu(), ga.grad) < TOL and rel(db.cpu(), be.grad) < TOL
+
+
+def test_varlen_attention_fwd_bwd():
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401
+    g = torch.Generator().manual_seed(6)
+    lens = [1, 37, 301, 150, 2]
+    off = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+    R, D, H = int(off[-1]), 256, 8
+    qkv = torch.randn(R, 3 * D, generator=g, requires_grad=True)
+    dout = torch.randn(R, D, generator=g)
+    outs = []
+    for b, L in enumerate(lens):
+        s = int(off[b])
+        q, k, v = (qkv[s:s + L, i * D:(i + 1) * D].view(L, H, 32).transpose(0, 1) for i in range(3))
+        a = torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v
+        outs.append(a.transpose(0, 1).reshape(L, D))
+    ref = torch.cat(outs)
+    (ref * dout).sum().backward()
+    qd, od = qkv.detach().cuda(), off.cuda()
+    out, lse, dq = torch.empty(R, D, device="cuda"), torch.empty(R, H, device="cuda"), torch.empty(R, 3 * D, device="cuda")
+    _lib.call("avl_attn_self_fwd", qd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(), lse.data_ptr(), _lib.stream())
+    _lib.call("avl_attn_self_bwd", qd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(), lse.data_ptr(),
+              dout.cuda().data_ptr(), dq.data_ptr(), _lib.stream())
+    assert rel(out.cpu(), ref.detach()) < TOL and rel(dq.cpu(), qkv.grad) < TOL
+    # cross attention, one query per sample
+    q1 = torch.randn(len(lens), D, generator=g, requires_grad=True)
+    kv = torch.randn(R, 2 * D, generator=g, requires_grad=True)
+    d1 = torch.randn(len(lens), D, generator=g)
+    outs = []
+    for b, L in enumerate(lens):
+        s = int(off[b])
+        q = q1[b].view(H, 1, 32)
+        k = kv[s:s + L, :D].view(L, H, 32).transpose(0, 1)
+        v = kv[s:s + L, D:].view(L, H, 32).transpose(0, 1)
+        outs.append((torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v).reshape(D))
+    ref = torch.stack(outs)
+    (ref * d1).sum().backward()
+    qd, kvd = q1.detach().cuda(), kv.detach().cuda()
+    out, probs = torch.empty(len(lens), D, device="cuda"), torch.empty(R, H, device="cuda")
+    dq, dkv = torch.empty(len(lens), D, device="cuda"), torch.empty(R, 2 * D, device="cuda")
+    _lib.call("avl_attn_cross_fwd", qd.data_ptr(), kvd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(),
+              probs.data_ptr(), _lib.stream())
+    _lib.call("avl_attn_cross_bwd", qd.data_ptr(), kvd.data_ptr(), od.data_ptr(), probs.data_ptr(),
+              d1.cuda().data_ptr(), len(lens), D, dq.data_ptr(), dkv.data_ptr(), _lib.stream())
+    assert rel(out.cpu(), ref.detach()) < TOL and rel(dq.cpu(), q1.grad) < TOL and rel(dkv.cpu(), kv.grad) < TOL
