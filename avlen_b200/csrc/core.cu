@@ -4,6 +4,7 @@
 static int g_last_cuda_error = 0;
 static int g_num_sms = 0;
 static long long g_launches = 0;
+static int g_use_tc = 1;
 
 extern "C" void avl_count_launch() { ++g_launches; }
 
@@ -34,3 +35,11 @@ AVL_API int avl_device_sm_count(void) { return avl_num_sms(); }
 
 // Number of kernels this library has launched so far in this process (bench.py's gpu_launches).
 AVL_API long long avl_launch_count(void) { return g_launches; }
+
+// Tensor-core (tcgen05) path switch for the dense / conv GEMMs: 1 = on (default), 0 = fp32 SIMT kernels only.
+AVL_API int avl_set_tensor_cores(int enable) {
+  int old = g_use_tc;
+  g_use_tc = enable ? 1 : 0;
+  return old;
+}
+AVL_API int avl_get_tensor_cores(void) { return g_use_tc; }

@@ -197,14 +197,51 @@ static void launch_gemm(Launcher& L, GemmOperand A, bool a_kc, GemmOperand B, bo
   L.check();
 }
 
+#ifndef AVL_HOST_EMUL
+AVL_API int avl_tc_gemm(const float* A, long long lda, const float* B, float* C, long long ldc, int M, int N, int K,
+                           const float* scale, const float* bias, const float* residual, long long ldr, int relu,
+                           const int* m_dev, void* stream);
+AVL_API int avl_get_tensor_cores(void);
+static bool tc_ok(const float* X, long long ldx, const float* W, int rows, int K) {
+  return avl_get_tensor_cores() && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)X | (uintptr_t)W) & 15) == 0;
+}
+#else
+static bool tc_ok(const float*, long long, const float*, int, int) { return false; }
+static int avl_tc_gemm(const float*, long long, const float*, float*, long long, int, int, int, const float*,
+                       const float*, const float*, long long, int, const int*, void*) { return 0; }
+#endif
+
+__global__ void transpose_kernel(const float* __restrict__ w, long long ldw, float* wt, int rows, int cols) {
+  // wt[c][r] = w[r][c]
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int c = i % cols, r = i / cols;
+  wt[(size_t)c * rows + r] = w[(size_t)r * ldw + c];
+}
+
 // Y[rows, N] = X[rows, K] W[N, K]^T + b  (ReLU)
 static void lin_fwd(Launcher& L, const float* X, long long ldx, const float* W, const float* b, float* Y,
                     long long ldy, int rows, int N, int K, int relu, const int* rows_dev) {
+  if (tc_ok(X, ldx, W, rows, K)) {
+    int rc = avl_tc_gemm(X, ldx, W, Y, ldy, rows, N, K, nullptr, b, nullptr, 0, relu, rows_dev, L.s);
+    if (rc && !L.err) L.err = rc;
+    return;
+  }
   launch_gemm(L, {X, ldx, 1}, true, {W, (long long)K, 1}, true, Y, ldy, rows, N, K, make_ep(b, relu, rows_dev), 1);
 }
 // dX[rows, K] (+)= dY[rows, N] W[N, K]
 static void lin_bwd_x(Launcher& L, const float* dY, long long ldy, const float* W, long long ldw, float* dX,
-                      long long ldx, int rows, int N, int K, int accumulate, const int* rows_dev) {
+                      long long ldx, int rows, int N, int K, int accumulate, const int* rows_dev,
+                      float* wt_scratch = nullptr) {
+  if (wt_scratch && tc_ok(dY, ldy, wt_scratch, rows, N) && (ldx & 3) == 0) {
+    // B operand must be [K][N] N-contiguous: transpose the (small) weight once, then dX = dY . (W^T)^T
+    AVL_LAUNCH(transpose_kernel, avl_div_up((long long)N * K, 256), 256, 0, L.s, W, ldw, wt_scratch, N, K);
+    L.check();
+    int rc = avl_tc_gemm(dY, ldy, wt_scratch, dX, ldx, rows, K, N, nullptr, nullptr, accumulate ? dX : nullptr, ldx, 0,
+                         rows_dev, L.s);
+    if (rc && !L.err) L.err = rc;
+    return;
+  }
   GemmEpilogue ep = make_ep(nullptr, 0, rows_dev);
   ep.accumulate = accumulate;
   launch_gemm(L, {dY, ldy, 1}, true, {W, 1, ldw}, false, dX, ldx, rows, K, N, ep, 1);
@@ -296,7 +333,7 @@ struct TfBufs {  // saved forward activations of the transformer on R packed row
   float *QKV, *ATT, *LSE, *AO, *X1, *ST1, *FF1, *FF2, *X2, *ST2, *MEM, *ST3, *KV, *PROBS;
   float *TV, *SA, *T1, *STT1, *Q, *C, *CO, *T2, *STT2, *DF1, *DF2, *T3, *STT3, *STT4;
   // backward scratch
-  float *GA, *GB, *GC, *GQKV, *GKV, *gB1, *gB2, *gB3, *gB4;
+  float *GA, *GB, *GC, *GQKV, *GKV, *gB1, *gB2, *gB3, *gB4, *WT;
 };
 
 static void tf_alloc(Arena& a, TfBufs& t, size_t R, size_t B, int D, int H, bool bwd) {
@@ -315,8 +352,9 @@ static void tf_alloc(Arena& a, TfBufs& t, size_t R, size_t B, int D, int H, bool
     t.GQKV = a.take<float>(R * 3 * D); t.GKV = a.take<float>(R * 2 * D);
     t.gB1 = a.take<float>(B * D); t.gB2 = a.take<float>(B * D); t.gB3 = a.take<float>(B * D);
     t.gB4 = a.take<float>(B * D);
+    t.WT = a.take<float>((size_t)3 * D * 512);  // transposed-weight scratch (largest: in_proj 3D x D; fusion D x Fin)
   } else {
-    t.GA = t.GB = t.GC = t.GQKV = t.GKV = t.gB1 = t.gB2 = t.gB3 = t.gB4 = nullptr;
+    t.GA = t.GB = t.GC = t.GQKV = t.GKV = t.gB1 = t.gB2 = t.gB3 = t.gB4 = t.WT = nullptr;
   }
 }
 
@@ -380,7 +418,7 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
   lin_bwd_w(L, t.gB2, D, t.T1, D, gp(G, TP_DEC_CA_IN_W), D, gp(G, TP_DEC_CA_IN_B), B, D, D, nullptr);
   lin_bwd_x(L, t.gB2, D, P[TP_DEC_CA_IN_W], D, t.gB1, D, B, D, D, 1, nullptr);  // gB1 = gT1 (residual + q path)
   lin_bwd_w(L, t.GKV, 2 * D, t.MEM, D, gp_off(G, TP_DEC_CA_IN_W, DD), D, gp_off(G, TP_DEC_CA_IN_B, D), Rcap, 2 * D, D, total);
-  lin_bwd_x(L, t.GKV, 2 * D, P[TP_DEC_CA_IN_W] + DD, D, t.GA, D, Rcap, 2 * D, D, 0, total);  // GA = gMEM
+  lin_bwd_x(L, t.GKV, 2 * D, P[TP_DEC_CA_IN_W] + DD, D, t.GA, D, Rcap, 2 * D, D, 0, total, t.WT);  // GA = gMEM
   ln_bwd(L, tgt, t.SA, P[TP_DEC_N1_W], t.STT1, t.gB1, t.gB4, gp(G, TP_DEC_N1_W), gp(G, TP_DEC_N1_B), nullptr, B, D);
   // gB4 = grad wrt (tgt + SA)
   lin_bwd_w(L, t.gB4, D, t.TV, D, gp(G, TP_DEC_SA_OUT_W), D, gp(G, TP_DEC_SA_OUT_B), B, D, D, nullptr);
@@ -392,18 +430,18 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
   ln_bwd(L, t.X1, t.FF2, P[TP_ENC_N2_W], t.ST2, t.GB, t.GA, gp(G, TP_ENC_N2_W), gp(G, TP_ENC_N2_B), total, Rcap, D);
   // GA = grad wrt (X1 + FF2)
   lin_bwd_w(L, t.GA, D, t.FF1, D, gp(G, TP_ENC_L2_W), D, gp(G, TP_ENC_L2_B), Rcap, D, D, total);
-  lin_bwd_x(L, t.GA, D, P[TP_ENC_L2_W], D, t.GB, D, Rcap, D, D, 0, total);
+  lin_bwd_x(L, t.GA, D, P[TP_ENC_L2_W], D, t.GB, D, Rcap, D, D, 0, total, t.WT);
   relu_bwd(L, t.GB, t.FF1, total, Rcap, D);
   lin_bwd_w(L, t.GB, D, t.X1, D, gp(G, TP_ENC_L1_W), D, gp(G, TP_ENC_L1_B), Rcap, D, D, total);
-  lin_bwd_x(L, t.GB, D, P[TP_ENC_L1_W], D, t.GA, D, Rcap, D, D, 1, total);  // GA = gX1
+  lin_bwd_x(L, t.GB, D, P[TP_ENC_L1_W], D, t.GA, D, Rcap, D, D, 1, total, t.WT);  // GA = gX1
   ln_bwd(L, X0, t.AO, P[TP_ENC_N1_W], t.ST1, t.GA, t.GC, gp(G, TP_ENC_N1_W), gp(G, TP_ENC_N1_B), total, Rcap, D);
   // GC = grad wrt (X0 + AO)
   lin_bwd_w(L, t.GC, D, t.ATT, D, gp(G, TP_ENC_OUT_W), D, gp(G, TP_ENC_OUT_B), Rcap, D, D, total);
-  lin_bwd_x(L, t.GC, D, P[TP_ENC_OUT_W], D, t.GB, D, Rcap, D, D, 0, total);  // GB = gATT
+  lin_bwd_x(L, t.GC, D, P[TP_ENC_OUT_W], D, t.GB, D, Rcap, D, D, 0, total, t.WT);  // GB = gATT
   AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_WARPS * 32, kAttnBwdSmem, L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale);
   L.check();
   lin_bwd_w(L, t.GQKV, 3 * D, X0, D, gp(G, TP_ENC_IN_W), D, gp(G, TP_ENC_IN_B), Rcap, 3 * D, D, total);
-  lin_bwd_x(L, t.GQKV, 3 * D, P[TP_ENC_IN_W], D, t.GC, D, Rcap, 3 * D, D, 1, total);  // GC = gX0
+  lin_bwd_x(L, t.GQKV, 3 * D, P[TP_ENC_IN_W], D, t.GC, D, Rcap, 3 * D, D, 1, total, t.WT);  // GC = gX0
 }
 
 // ------------------------------------------------------------------------------------- SMT context
@@ -583,7 +621,7 @@ AVL_API int avl_smt_backward(int B, int M, int F, int D, int pi, int rows_cap, c
   tf_backward(L, params, grads, s.tf, s.X0, s.off, s.total, rows_cap, B, D, goal, gout);
   float* gX0 = s.tf.GC;
   lin_bwd_w(L, gX0, D, s.H1, D, gp(grads, SP_FUS2_W), D, gp(grads, SP_FUS2_B), rows_cap, D, D, s.total);
-  lin_bwd_x(L, gX0, D, params[SP_FUS2_W], D, s.GH1, D, rows_cap, D, D, 0, s.total);
+  lin_bwd_x(L, gX0, D, params[SP_FUS2_W], D, s.GH1, D, rows_cap, D, D, 0, s.total, s.tf.WT);
   relu_bwd(L, s.GH1, s.H1, s.total, rows_cap, D);
   lin_bwd_w(L, s.GH1, D, s.XIN, Fin, gp(grads, SP_FUS0_W), Fin, gp(grads, SP_FUS0_B), rows_cap, D, Fin, s.total);
   if (gp(grads, SP_POSE_W) || gp(grads, SP_POSE_B)) {
@@ -592,7 +630,7 @@ AVL_API int avl_smt_backward(int B, int M, int F, int D, int pi, int rows_cap, c
     lin_bwd_w(L, s.GPOSE, 16, s.POSE5, 8, gp(grads, SP_POSE_W), 5, gp(grads, SP_POSE_B), rows_cap, 16, 5, s.total);
   }
   if (need_dx) {
-    lin_bwd_x(L, s.GH1, D, params[SP_FUS0_W], Fin, s.GXIN, Fin, rows_cap, D, Fin, 0, s.total);
+    lin_bwd_x(L, s.GH1, D, params[SP_FUS0_W], Fin, s.GXIN, Fin, rows_cap, D, Fin, 0, s.total, s.tf.WT);
     AVL_LAUNCH(smt_scatter_dx_kernel, B, 128, 0, L.s, s.GXIN, s.off, B, F, pi, dx);
     L.check();
   }

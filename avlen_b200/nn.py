@@ -27,7 +27,34 @@ _lib.register({
     "avl_attn_self_bwd": [P, P, I, I, P, P, P, P, P],
     "avl_attn_cross_fwd": [P, P, P, I, I, P, P, P],
     "avl_attn_cross_bwd": [P, P, P, P, P, I, I, P, P, P],
+    "avl_tc_gemm": [P, L, P, P, L, I, I, I, P, P, P, L, I, P, P],
+    "avl_tc_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
+    "avl_set_tensor_cores": [I],
+    "avl_get_tensor_cores": [],
 })
+
+_packed_cache = {}
+
+
+def set_tensor_cores(enable: bool) -> bool:
+    """Switches the tcgen05 (TF32 tensor-core) path of the dense / conv GEMMs on or off; returns the old state."""
+    return bool(_lib.lib().avl_set_tensor_cores(int(bool(enable))))
+
+
+def tensor_cores_enabled() -> bool:
+    return bool(_lib.lib().avl_get_tensor_cores())
+
+
+def _packed_weight(w):
+    """(Cout, C, KH, KW) -> (Cout, KH, KW, C) K-contiguous copy for the tensor-core path, cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _packed_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    pk = w.detach().permute(0, 2, 3, 1).contiguous()
+    _packed_cache[key] = (w._version, pk)
+    return pk
+
 
 
 def conv_out(size, k, stride, pad):
@@ -47,6 +74,10 @@ def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=No
         assert out.stride(-1) == 1
         ldy = out.stride(0)
     ldr = Cout if residual is not None else 0
+    if C % 4 == 0 and N * OH * OW >= 512 and x.data_ptr() % 16 == 0 and tensor_cores_enabled():
+        call("avl_tc_conv2d_fwd", fptr(x), N, H, W, C, fptr(_packed_weight(w)), Cout, KH, KW, stride, pad, fptr(scale),
+             fptr(bias), fptr(residual), ldr, int(relu), out.data_ptr(), ldy, stream())
+        return out
     call("avl_conv2d_fwd", fptr(x), N, H, W, C, fptr(w), Cout, KH, KW, stride, pad, fptr(scale), fptr(bias),
          fptr(residual), ldr, int(relu), out.data_ptr(), ldy, stream())
     return out
@@ -67,6 +98,11 @@ def linear(x, w, bias=None, relu=False, out=None):
     N = w.shape[0]
     if out is None:
         out = torch.empty((rows, N), device=x.device, dtype=torch.float32)
+    if (rows >= 512 and K % 4 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0
+            and tensor_cores_enabled()):
+        call("avl_tc_gemm", fptr(x), x.stride(0), fptr(w), out.data_ptr(), out.stride(0), rows, N, K, None, fptr(bias),
+             None, 0, int(relu), None, stream())
+        return out
     call("avl_gemm", fptr(x), x.stride(0), 1, fptr(w), K, 1, out.data_ptr(), out.stride(0), rows, N, K, fptr(bias),
          int(relu), 0, 1, stream())
     return out

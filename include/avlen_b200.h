@@ -1,0 +1,164 @@
+/* avlen_b200 — C ABI of the B200 (sm_100a) hot path of AVLEN / SAVi (libavlen_b200.so).
+ *
+ * Conventions: plain C, every pointer is a DEVICE pointer unless stated otherwise, row-major, float = fp32,
+ * `stream` is a cudaStream_t passed as void*, every call only enqueues work (no hidden synchronisation unless the
+ * comment says so), the library never allocates except inside avl_audio_create.  Return value: 0 = ok,
+ * -1 = invalid argument, -2 = unsupported size, -3 = CUDA runtime error (see avl_last_cuda_error*).
+ *
+ * The reference (merlresearch/avlen) has no FFI on this path: its boundary is the Python class API in
+ * ss_baselines/ and soundspaces/.  Each entry point below cites the reference code it replaces (file:line under
+ * the reference root); avlen_b200/ mirrors the reference's Python classes and calls these through ctypes
+ * (INTEGRATION.md shows the binding a reference maintainer would add).
+ */
+#ifndef AVLEN_B200_H
+#define AVLEN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------- library */
+int avl_version(void);
+int avl_last_cuda_error(void);                 /* cudaError_t of the last failed runtime call (0 = none)  */
+const char* avl_last_cuda_error_string(void);
+int avl_device_sm_count(void);
+long long avl_launch_count(void);              /* kernels launched by this library so far in this process */
+int avl_set_tensor_cores(int enable);          /* 1 (default): tcgen05 TF32 path for dense/conv GEMMs; returns old */
+int avl_get_tensor_cores(void);
+
+/* ------------------------------------------------------------------------------- rows A + B: audio sensors
+ * soundspaces/simulator.py:644-699  SoundSpacesSim._compute_audiogoal   (causal FIR src * rir, 3 branches,
+ *                                   silent frame, empty RIR file, distractor :682-697)
+ * soundspaces/tasks/nav.py:87-101   SpectrogramSensor.compute_spectrogram (|STFT 512/160/400| -> 4x4 zero-padded
+ *                                   block mean -> log1p, channels last)                                        */
+int avl_audio_create(int sampling_rate, void** handle_out /* host */);
+int avl_audio_destroy(void* handle);
+int avl_audio_status(void* handle, int* status_out /* host; synchronises; 1 = an RIR was truncated */);
+/* sounds: flat bank of mono clips; clip_off[i]: start of env i's clip; index[i]: _audio_index (second rendered);
+ * rirs: bank of interleaved (L,2) RIRs; rir_off[i] in frames; rir_len[i] (0 = empty file -> zeros);
+ * silent[i] != 0 -> exact zeros; d_*: optional distractor source/RIR (all three or none);
+ * audiogoal_out (N,2,sr) may be NULL; spectrogram_out (N,65,ceil((1+sr/160)/4),2).                             */
+int avl_audio_render_spectrogram(void* handle, int n_envs, const float* sounds, const long long* clip_off,
+                                 const int* index, const float* rirs, const long long* rir_off, const int* rir_len,
+                                 const int* silent, const long long* d_clip_off, const long long* d_rir_off,
+                                 const int* d_rir_len, float* audiogoal_out, float* spectrogram_out, void* stream);
+int avl_audio_spectrogram(void* handle, int n, const float* audio /* (N,2,sr) */, float* spectrogram_out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------- rows N, O: returns / advantages
+ * ss_baselines/savi/models/rollout_storage.py:394-412, ss_baselines/common/rollout_storage.py:114-132 (bit-exact)
+ * ss_baselines/savi/ppo/ppo.py:90-95                                                                          */
+int avl_gae(const float* rewards, float* value_preds, const float* masks, const float* next_value, float* returns,
+            int steps, int n_envs, int use_gae, float gamma, float tau, void* stream);
+int avl_gae_f64(const float* rewards, float* value_preds, const float* masks, const float* next_value,
+                float* returns, int steps, int n_envs, int use_gae, double gamma, double tau, void* stream);
+int avl_advantages(const float* returns, const float* value_preds, float* adv, int count, int normalize, float eps,
+                   void* stream);
+
+/* --------------------------------------------------------------------------------- row I: categorical heads
+ * ss_baselines/common/utils.py:44-72 (CustomFixedCategorical sample/mode/log_probs/entropy, probs)
+ * uniforms == NULL -> mode() (first arg-max); else inverse-CDF sampling on the supplied uniforms.              */
+int avl_categorical_act(const float* logits, const float* uniforms, int B, int A, long long* actions,
+                        float* log_probs, float* probs, void* stream);
+int avl_categorical_eval(const float* logits, const long long* actions, int B, int A, float* log_probs,
+                         float* entropy, float* probs, void* stream);
+int avl_categorical_eval_bwd(const float* logits, const long long* actions, const float* g_log_probs,
+                             const float* g_entropy, int B, int A, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------- rows O + Q: fused PPO loss
+ * ss_baselines/savi/ppo/ppo.py:219-262 (rl_mask / uncertainty CE variant), ss_baselines/av_nav/ppo/ppo.py:93-131.
+ * out8 = [value_loss, action_loss, entropy, unct_loss, total, mean(values), mean(returns), normaliser];
+ * dlogits/dvalues/dunct = gradient of the total loss.  workspace: avl_ppo_loss_workspace(B) bytes, zeroed once. */
+long long avl_ppo_loss_workspace(int B);
+int avl_ppo_loss_fwd_bwd(int B, int A, const float* logits, const long long* actions, const float* old_lp,
+                         const float* adv, const float* values, const float* value_preds, const float* returns,
+                         const float* rl_mask, const float* unct, const long long* unct_gt, float clip,
+                         float value_coef, float ent_coef, float unct_coef, int use_clipped_value, float* dlogits,
+                         float* dvalues, float* dunct, float* out8, void* workspace, void* stream);
+
+/* ----------------------------------------------------------------------------- row G: external memory insert
+ * ss_baselines/savi/models/rollout_storage.py:930-941 (+ mask snapshot :284-286) on the single-copy ring buffer
+ * memory (total, N, dim), masks (N, total); bit-exact.                                                         */
+int avl_extmem_insert(float* memory, float* masks, const float* feats, const float* not_done, float* mask_snapshot,
+                      int n_envs, int total_size, int capacity, int dim, int idx, void* stream);
+
+/* --------------------------------------------------------------------- row M (scalar part): belief update
+ * ss_baselines/savi/models/belief_predictor.py:139-230 (EMA + odom<->base transforms), batched.                */
+int avl_belief_update(int n_envs, const float* spectrogram, int spec_elems_per_env, const float* pose,
+                      const unsigned char* dones, const float* pointgoal_pred, const float* label_pred,
+                      int label_stride, float weighting_factor, int current_pred_only, float* last_pointgoal,
+                      int* has_pointgoal, float* last_label, int* has_label, float* location_belief,
+                      float* category_belief, int* nonzero_scratch, void* stream);
+
+/* ----------------------------------------------------------------------- clip_grad_norm_ + Adam (flat buffers)
+ * ss_baselines/savi/ppo/ppo.py:62, :297-300 (torch.optim.Adam + nn.utils.clip_grad_norm_)                      */
+int avl_grad_sumsq(const float* grad, long long n, float* normsq_out, void* workspace /* 1032 floats, zeroed */,
+                   void* stream);
+int avl_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, int step, float max_norm, const float* normsq,
+                       float grad_scale, void* stream);
+
+/* --------------------------------------------------------------------- rows C, D, E, M: encoder building blocks
+ * NHWC activations, weights in the reference's nn.Conv2d / nn.Linear layout.
+ * ss_baselines/savi/models/audio_cnn.py:62-94,136-151; av_nav/models/visual_cnn.py:104-154;
+ * ss_baselines/savi/models/smt_resnet.py:14-164 (GroupNorm(16) + residual + ReLU); smt_cnn.py:78-95 (/255, area resize);
+ * belief_predictor.py:58-82 (torchvision resnet18: folded BatchNorm scale/bias, max-pool, global average pool).   */
+int avl_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w_oihw, int Cout, int KH, int KW,
+                   int stride, int pad, const float* scale, const float* bias, const float* residual, long long ldr,
+                   int relu, float* y, long long ldy, void* stream);
+int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w_ohwi, int Cout, int KH, int KW,
+                      int stride, int pad, const float* scale, const float* bias, const float* residual,
+                      long long ldr, int relu, float* y, long long ldy, void* stream);
+int avl_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int N,
+                      int HW, int C, int groups, float eps, int relu, void* stream);
+int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, float scale, void* stream);
+int avl_concat_rgbd(const float* rgb, const float* depth, float* y, long long pixels, int c_rgb, int c_depth,
+                    float rgb_scale, void* stream);
+int avl_append_planes(const float* x, const float* extra, float* y, int N, int HW, int C, int E, void* stream);
+int avl_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int avl_avgpool_global(const float* x, float* y, int N, int HW, int C, void* stream);
+int avl_onehot_linear(const long long* actions, const float* W, const float* bias, float* y, long long ldy, int B,
+                      int out_dim, int n_actions, void* stream);
+int avl_copy_cols(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, void* stream);
+
+/* ----------------------------------------------------------------------------------- dense building blocks
+ * C[M,N] (+)= sum_k A(m,k) B(n,k) with element strides; bias / ReLU / accumulate / split-K (atomic).           */
+int avl_gemm(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_n, long long sb_k, float* C,
+             long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits,
+             void* stream);
+/* tcgen05 TF32: C = act(scale * A[M,K] B[N,K]^T + bias + residual); m_dev = optional device row count.        */
+int avl_tc_gemm(const float* A, long long lda, const float* B, float* C, long long ldc, int M, int N, int K,
+                const float* scale, const float* bias, const float* residual, long long ldr, int relu,
+                const int* m_dev, void* stream);
+int avl_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                      float* stats, int rows, int cols, void* stream);
+int avl_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy,
+                      float* dx, float* dgamma, float* dbeta, int rows, int cols, void* stream);
+int avl_attn_self_fwd(const float* qkv, const int* off, int B, int D, float* out, float* lse, void* stream);
+int avl_attn_self_bwd(const float* qkv, const int* off, int B, int D, const float* out, const float* lse,
+                      const float* dout, float* dqkv, void* stream);
+int avl_attn_cross_fwd(const float* q, const float* kv, const int* off, int B, int D, float* out, float* probs,
+                       void* stream);
+int avl_attn_cross_bwd(const float* q, const float* kv, const int* off, const float* probs, const float* dout, int B,
+                       int D, float* dq, float* dkv, void* stream);
+
+/* ------------------------------------------------------------------- row F: scene-memory transformer encoder
+ * ss_baselines/savi/models/smt_state_encoder.py:109-276 around torch.nn.Transformer (1+1 layers, post-norm).
+ * params / grads: host arrays of avl_smt_param_count() device pointers, order documented in
+ * avlen_b200/savi/models/smt_state_encoder.py::SMT_PARAM_KEYS; gradients are accumulated (NULL = skip).         */
+int avl_smt_param_count(void);
+long long avl_smt_workspace_bytes(int B, int rows_cap, int F, int D, int with_backward, int need_dx);
+int avl_smt_forward(int B, int M, int F, int D, int pose_index, int pretraining, int rows_cap, const float* x,
+                    const float* memory, int n_mem_envs, const int* env_index, const float* masks, const float* goal,
+                    const float* const* params /* host array */, float* out, void* workspace, int with_backward,
+                    int need_dx, void* stream);
+int avl_smt_backward(int B, int M, int F, int D, int pose_index, int rows_cap, const float* goal,
+                     const float* const* params /* host array */, float* const* grads /* host array */,
+                     const float* gout, float* dx, float* dgoal, void* workspace, void* stream);
+int avl_smt_status(int B, int rows_cap, int F, int D, void* workspace, int* total_rows /* host */,
+                   int* overflow /* host */);   /* synchronises */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVLEN_B200_H */

@@ -1,0 +1,99 @@
+"""tcgen05 (TF32 tensor-core) GEMM / implicit-GEMM convolution against the fp32 SIMT kernels and PyTorch.
+Tolerance: TF32 operands (10-bit mantissa, truncated by the tensor core) with fp32 accumulation -> 2e-3 of the
+output's max magnitude (stated tolerance for the tensor-core encoders / dense layers)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL_TC = 2e-3
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / max(1e-12, float(b.abs().max())))
+
+
+@pytest.fixture(autouse=True)
+def _tc_on():
+    from avlen_b200 import nn as K
+    old = K.set_tensor_cores(True)
+    yield
+    K.set_tensor_cores(old)
+
+
+@pytest.mark.parametrize("M,N,K_", [(4800, 256, 288), (1000, 768, 256), (513, 16, 64), (9600, 512, 256), (777, 144, 256),
+                                    (2048, 256, 36), (600, 4, 256)])
+def test_tc_gemm_matches_fp32(M, N, K_):
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    g = torch.Generator().manual_seed(M + N + K_)
+    x = torch.randn(M, K_, generator=g).cuda()
+    w = (torch.randn(N, K_, generator=g) / K_ ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    ref = F.relu(x.double() @ w.double().t() + b.double() + res.double()).float()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _lib.call("avl_tc_gemm", x.data_ptr(), K_, w.data_ptr(), out.data_ptr(), N, M, N, K_, None, b.data_ptr(),
+              res.data_ptr(), N, 1, None, _lib.stream())
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert rel(out, ref) < TOL_TC
+    # device-side row count: rows beyond *m_dev are left untouched
+    out2 = torch.full((M, N), 7.0, device="cuda")
+    mdev = torch.tensor([M // 2 + 3], dtype=torch.int32, device="cuda")
+    _lib.call("avl_tc_gemm", x.data_ptr(), K_, w.data_ptr(), out2.data_ptr(), N, M, N, K_, None, b.data_ptr(),
+              res.data_ptr(), N, 1, mdev.data_ptr(), _lib.stream())
+    assert torch.equal(out2[: M // 2 + 3], out[: M // 2 + 3])
+    assert bool((out2[M // 2 + 3:] == 7.0).all())
+    assert K.tensor_cores_enabled()
+
+
+@pytest.mark.parametrize("shape", [
+    (40, 64, 64, 16, 16, 3, 3, 1, 1), (40, 64, 64, 16, 32, 3, 3, 2, 1), (40, 64, 64, 16, 32, 1, 1, 2, 0),
+    (40, 32, 32, 32, 32, 3, 3, 1, 1), (40, 16, 16, 64, 64, 3, 3, 1, 1), (40, 8, 8, 128, 128, 3, 3, 1, 1),
+    (600, 8, 8, 128, 64, 8, 8, 1, 0), (64, 31, 11, 32, 64, 3, 3, 2, 0), (64, 15, 5, 64, 64, 3, 3, 1, 0),
+    (600, 13, 3, 64, 128, 13, 3, 1, 0), (16, 17, 7, 64, 128, 3, 3, 2, 1), (16, 5, 2, 256, 512, 3, 3, 2, 1),
+])
+def test_tc_conv_matches_fp32(shape):
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, KH, KW, s, p = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    w = (torch.randn(Co, C, KH, KW, generator=g) / (C * KH * KW) ** 0.5).cuda()
+    b, sc = torch.randn(Co, generator=g).cuda(), (torch.rand(Co, generator=g) + 0.5).cuda()
+    K.set_tensor_cores(False)
+    ref = K.conv2d(x, w, b, s, p, relu=True, scale=sc)
+    K.set_tensor_cores(True)
+    out = K.conv2d(x, w, b, s, p, relu=True, scale=sc)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert rel(out, ref) < TOL_TC
+    tref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, None, s, p) * sc.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert rel(out, tref) < TOL_TC
+
+
+def test_policy_with_tensor_cores_matches_oracle():
+    """Whole SAVi act + evaluate path with the tensor-core kernels on: same checks as the fp32 path, TF32 tolerance."""
+    from tests._policy_helpers import make_memory, make_obs, oracle_and_cuda_policies
+    o, p = oracle_and_cuda_policies(5, False)
+    n, M = 16, 300
+    obs = make_obs(n, 11)
+    mem, masks = make_memory(M, n, 276, 12)
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1)), torch.ones(n, 1)
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}
+    with torch.no_grad():
+        v_r, a_r, lp_r, _, x_r, pr_r = o.act(obs, h, pa, mk, mem, masks, uniforms=None)
+        v, a, lp, _, x, pr = p.act(cu(obs), h.cuda(), pa.cuda(), mk.cuda(), mem.cuda(), masks.cuda(), deterministic=True)
+    assert rel(x.cpu(), x_r) < 5e-3
+    assert rel(pr.cpu(), pr_r) < 5e-3 and rel(v.cpu(), v_r) < 2e-2
+    act = torch.randint(0, 4, (n, 1))
+    v_r, lp_r, ent_r, _, _ = o.evaluate_actions(obs, h, pa, mk, act, mem, masks)
+    (v_r.sum() + 2 * lp_r.sum() + 0.5 * ent_r).backward()
+    v, lp, ent, _, _ = p.evaluate_actions(cu(obs), h.cuda(), pa.cuda(), mk.cuda(), act.cuda(), mem.cuda(), masks.cuda())
+    (v.sum() + 2 * lp.sum() + 0.5 * ent).backward()
+    og = dict(o.named_parameters())
+    worst = 0.0
+    for k, q in p.named_parameters():
+        if q.requires_grad and og[k].grad is not None and float(og[k].grad.abs().max()) > 1e-6:
+            worst = max(worst, rel(q.grad.cpu(), og[k].grad))
+    assert worst < 3e-2, worst
