@@ -59,13 +59,16 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_nhwc_kernel(const float*
 
 // -------------------------------------------------- area resize (exact 2x2 mean) + optional scale (rgb / 255)
 // smt_cnn.py:83-95 + common/utils.py:515-517 (interpolate(mode="area") 128 -> 64).  NHWC in, NHWC out.
-__global__ void resize_half_kernel(const float* __restrict__ x, float* y, int N, int H, int W, int C, float scale) {
+__global__ void resize_half_kernel(const float* __restrict__ x, float* y, int N, int H, int W, int C, int Cp,
+                                   float scale) {
+  // Cp >= C output channels; channels [C, Cp) are zero (16-byte channel padding for the tensor-core conv loader)
   const int OH = H / 2, OW = W / 2;
-  long long total = (long long)N * OH * OW * C;
+  long long total = (long long)N * OH * OW * Cp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    long long t = i / C;
+    int c = (int)(i % Cp);
+    long long t = i / Cp;
+    if (c >= C) { y[i] = 0.f; continue; }
     int ow = (int)(t % OW);
     t /= OW;
     int oh = (int)(t % OH);
@@ -101,6 +104,17 @@ __global__ void append_planes_kernel(const float* __restrict__ x, const float* _
     long long p = i / CO;
     int n = (int)(p / HW);
     y[i] = (c < C) ? x[p * C + c] : extra[(long long)n * E + (c - C)];
+  }
+}
+
+// y (rows, Cp) = [x (rows, C), zeros]  (channel padding to a multiple of 4 for the tensor-core conv loader)
+__global__ void pad_channels_kernel(const float* __restrict__ x, float* y, long long rows, int C, int Cp) {
+  long long total = rows * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long long r = i / Cp;
+    y[i] = (c < C) ? x[r * C + c] : 0.f;
   }
 }
 
@@ -216,12 +230,13 @@ AVL_API int avl_groupnorm_fwd(const float* x, const float* gamma, const float* b
   return AVL_OK;
 }
 
-AVL_API int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, float scale, void* stream) {
-  if (N < 0 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1) return AVL_ERR_ARG;
+AVL_API int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, int C_out, float scale,
+                            void* stream) {
+  if (N < 0 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1 || C_out < C) return AVL_ERR_ARG;
   if (N == 0) return AVL_OK;
   if (!x || !y) return AVL_ERR_ARG;
-  AVL_LAUNCH(resize_half_kernel, ew_grid((long long)N * H * W * C / 4), 256, 0, (cudaStream_t)stream, x, y, N, H, W, C,
-             scale);
+  AVL_LAUNCH(resize_half_kernel, ew_grid((long long)N * H * W * C_out / 4), 256, 0, (cudaStream_t)stream, x, y, N, H,
+             W, C, C_out, scale);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
@@ -244,6 +259,15 @@ AVL_API int avl_append_planes(const float* x, const float* extra, float* y, int 
   if (!x || !extra || !y) return AVL_ERR_ARG;
   AVL_LAUNCH(append_planes_kernel, ew_grid((long long)N * HW * (C + E)), 256, 0, (cudaStream_t)stream, x, extra, y, N,
              HW, C, E);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_pad_channels(const float* x, float* y, long long rows, int C, int C_out, void* stream) {
+  if (rows < 0 || C < 1 || C_out < C) return AVL_ERR_ARG;
+  if (rows == 0) return AVL_OK;
+  if (!x || !y) return AVL_ERR_ARG;
+  AVL_LAUNCH(pad_channels_kernel, ew_grid(rows * C_out), 256, 0, (cudaStream_t)stream, x, y, rows, C, C_out);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -13,7 +13,8 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 _lib.register({
     "avl_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
     "avl_groupnorm_fwd": [P, P, P, P, P, I, I, I, I, F, I, P],
-    "avl_resize_half": [P, P, I, I, I, I, F, P],
+    "avl_resize_half": [P, P, I, I, I, I, I, F, P],
+    "avl_pad_channels": [P, P, L, I, I, P],
     "avl_concat_rgbd": [P, P, P, L, I, I, F, P],
     "avl_append_planes": [P, P, P, I, I, I, I, P],
     "avl_maxpool3x3s2": [P, P, I, I, I, I, P],
@@ -45,15 +46,27 @@ def tensor_cores_enabled() -> bool:
     return bool(_lib.lib().avl_get_tensor_cores())
 
 
-def _packed_weight(w):
-    """(Cout, C, KH, KW) -> (Cout, KH, KW, C) K-contiguous copy for the tensor-core path, cached per weight version."""
-    key = (w.data_ptr(), tuple(w.shape))
+def _packed_weight(w, c_pad=None):
+    """(Cout, C, KH, KW) -> (Cout, KH, KW, Cp) K-contiguous copy for the tensor-core path (input channels zero-padded
+    to ``c_pad``), cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape), c_pad)
     hit = _packed_cache.get(key)
     if hit is not None and hit[0] == w._version:
         return hit[1]
-    pk = w.detach().permute(0, 2, 3, 1).contiguous()
+    pk = w.detach().permute(0, 2, 3, 1)
+    if c_pad is not None and c_pad != w.shape[1]:
+        pk = torch.nn.functional.pad(pk, (0, c_pad - w.shape[1]))
+    pk = pk.contiguous()
     _packed_cache[key] = (w._version, pk)
     return pk
+
+
+def pad_channels(x, c_out):
+    """NHWC channel zero-padding (C -> c_out)."""
+    N, H, W, C = x.shape
+    y = torch.empty((N, H, W, c_out), device=x.device, dtype=torch.float32)
+    call("avl_pad_channels", fptr(x), fptr(y), N * H * W, C, c_out, stream())
+    return y
 
 
 
@@ -65,8 +78,12 @@ def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=No
     """x (N,H,W,C) NHWC; w (Cout,C,KH,KW) OIHW (the reference's nn.Conv2d layout). Returns (N,OH,OW,Cout)."""
     N, H, W, C = x.shape
     Cout, Cw, KH, KW = w.shape
-    assert Cw == C, (Cw, C)
+    assert Cw == C or (Cw < C and C % 4 == 0), (Cw, C)  # x may carry zero-padded channels (tensor-core path)
     OH, OW = conv_out(H, KH, stride, pad), conv_out(W, KW, stride, pad)
+    tc = N * OH * OW >= 512 and x.data_ptr() % 16 == 0 and tensor_cores_enabled()
+    if tc and C % 4 != 0:
+        cp = (C + 3) // 4 * 4
+        x, C = pad_channels(x, cp), cp
     if out is None:
         out = torch.empty((N, OH, OW, Cout), device=x.device, dtype=torch.float32)
         ldy = Cout
@@ -74,10 +91,12 @@ def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=No
         assert out.stride(-1) == 1
         ldy = out.stride(0)
     ldr = Cout if residual is not None else 0
-    if C % 4 == 0 and N * OH * OW >= 512 and x.data_ptr() % 16 == 0 and tensor_cores_enabled():
-        call("avl_tc_conv2d_fwd", fptr(x), N, H, W, C, fptr(_packed_weight(w)), Cout, KH, KW, stride, pad, fptr(scale),
+    if tc:
+        call("avl_tc_conv2d_fwd", fptr(x), N, H, W, C, fptr(_packed_weight(w, C)), Cout, KH, KW, stride, pad, fptr(scale),
              fptr(bias), fptr(residual), ldr, int(relu), out.data_ptr(), ldy, stream())
         return out
+    if Cw != C:
+        raise _lib.AvlenError("channel-padded input needs the tensor-core path")
     call("avl_conv2d_fwd", fptr(x), N, H, W, C, fptr(w), Cout, KH, KW, stride, pad, fptr(scale), fptr(bias),
          fptr(residual), ldr, int(relu), out.data_ptr(), ldy, stream())
     return out
@@ -117,10 +136,12 @@ def groupnorm(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, ou
     return out
 
 
-def resize_half(x, scale=1.0):
+def resize_half(x, scale=1.0, c_out=None):
+    """Exact 2x2 area mean (x * scale first); ``c_out`` > C appends zero channels (tensor-core conv loader)."""
     N, H, W, C = x.shape
-    y = torch.empty((N, H // 2, W // 2, C), device=x.device, dtype=torch.float32)
-    call("avl_resize_half", fptr(x), fptr(y), N, H, W, C, float(scale), stream())
+    c_out = C if c_out is None else c_out
+    y = torch.empty((N, H // 2, W // 2, c_out), device=x.device, dtype=torch.float32)
+    call("avl_resize_half", fptr(x), fptr(y), N, H, W, C, c_out, float(scale), stream())
     return y
 
 

@@ -51,11 +51,13 @@ class SMTCNN(nn.Module):
                               dtype=torch.float32)
         col = 0
         if "rgb" in self.input_modalities:
-            x = K.resize_half(observations["rgb"].contiguous(), 1.0 / 255.0)  # /255 then 2x2 area mean (:83-86)
+            pad = 4 if (K.tensor_cores_enabled() and n * 4096 >= 512) else None  # 16-byte channel rows for the TC loader
+            x = K.resize_half(observations["rgb"].contiguous(), 1.0 / 255.0, pad)  # /255 then 2x2 area mean (:83-86)
             self.rgb_encoder(x, out=out[:, col:col + 64])
             col += 64
         if "depth" in self.input_modalities:
-            x = K.resize_half(observations["depth"].contiguous(), 1.0)
+            pad = 4 if (K.tensor_cores_enabled() and n * 4096 >= 512) else None
+            x = K.resize_half(observations["depth"].contiguous(), 1.0, pad)
             self.depth_encoder(x, out=out[:, col:col + 64])
             col += 64
         return out

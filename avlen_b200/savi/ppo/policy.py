@@ -191,7 +191,10 @@ class AudioNavSMTNet(Net):
         pose_dims = observation_space.spaces[POSE].shape[0]
         pose_indices = (nfeats, nfeats + pose_dims)
         nfeats += pose_dims
+        self._base_feature_size = nfeats
+        nfeats += self._extra_feature_dims()
         self._feature_size = nfeats
+        self._build_extra()
         self.smt_state_encoder = SMTStateEncoder(nfeats, dim_feedforward=hidden_size, pose_indices=pose_indices,
                                                  **kwargs)
         self.state_size = self.smt_state_encoder.hidden_state_size
@@ -199,6 +202,12 @@ class AudioNavSMTNet(Net):
             assert pretrained_path != ""
             self.pretrained_initialization(pretrained_path)
         self.train()
+
+    def _extra_feature_dims(self):
+        return 0
+
+    def _build_extra(self):
+        pass
 
     @property
     def memory_dim(self):
@@ -249,9 +258,10 @@ class AudioNavSMTNet(Net):
         self.goal_encoder.eval()
         self.visual_encoder.eval()
 
-    def get_features(self, observations, prev_actions):
+    def get_features(self, observations, prev_actions, extra_cols=0):
         """policy.py:660-674: [visual 128 | action 16 | audio 128 | (category 21) | pose 4] written straight into
-        the column slices of one feature matrix (no torch.cat)."""
+        the column slices of one feature matrix (no torch.cat); ``extra_cols`` trailing columns are left for the
+        caller (query-state embedding of the option net)."""
         n = observations[POSE].shape[0]
         dev = observations[POSE].device
         enc_trainable = torch.is_grad_enabled() and any(
@@ -261,7 +271,7 @@ class AudioNavSMTNet(Net):
             raise _lib.AvlenError("encoder backward is not built yet: call net.freeze_encoders() "
                                   "(savi.yaml: freeze_encoders True) or run under torch.no_grad()")
         with torch.no_grad():
-            x = torch.empty((n, self._feature_size), device=dev, dtype=torch.float32)
+            x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
             self.visual_encoder(observations, out=x[:, 0:128])
             if prev_actions.shape[1] == self._action_size:  # already one-hot (policy.py:629-630)
                 K.linear(prev_actions.float().contiguous(), self.action_encoder.weight, self.action_encoder.bias,
@@ -277,7 +287,50 @@ class AudioNavSMTNet(Net):
         return x
 
 
+class AudioNavOptionNet(AudioNavSMTNet):
+    """policy.py:919-1114 (pi_q): the SMT net whose current token carries the 32-d query-count embedding and whose
+    stored memory rows carry the 32-d last-query embedding (memory_dim 308, fusion input 320).  The unused
+    ``policy_selector`` / ``_qcnt_emb`` parameters are kept for checkpoint compatibility (Appendix A)."""
+
+    def __init__(self, observation_space, action_space, hidden_size=128, query_count_emb_size=32, **kwargs):
+        self._query_count_emb_size = query_count_emb_size
+        kwargs.pop("use_query_count", None)
+        super().__init__(observation_space, action_space, hidden_size=hidden_size, **kwargs)
+
+    def _extra_feature_dims(self):
+        return self._query_count_emb_size
+
+    def _build_extra(self):
+        self.policy_selector = nn.Linear(self._hidden_size, 2)
+        self._qcnt_emb = nn.Embedding(2, self._query_count_emb_size)
+
+    @property
+    def qcnt_emb(self):
+        return self._qcnt_emb
+
+    def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks, query_state,
+                last_query_info):
+        e = self._query_count_emb_size
+        x = self.get_features(observations, prev_actions, extra_cols=e)  # [x (276) | query_state (32)]
+        base = self._base_feature_size
+        with torch.no_grad():
+            K.copy_cols(query_state.contiguous(), x[:, base:base + e])
+        belief = self._belief(observations, x.shape[0], x.device)
+        x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
+        with torch.no_grad():  # memory rows: [x | last_query_info] (policy.py:1062-1063)
+            x_for_memory = x.clone()
+            K.copy_cols(last_query_info.contiguous(), x_for_memory[:, base:base + e])
+        return x_att, rnn_hidden_states, x_for_memory
+
+
 class AudioNavSMTPolicy(Policy):
     def __init__(self, observation_space, action_space, hidden_size=128, **kwargs):
         super().__init__(AudioNavSMTNet(observation_space, action_space, hidden_size=hidden_size, **kwargs),
                          action_space.n)
+
+
+class AudioNavOptionPolicy(Policy):
+    """policy.py:346-356: all three action heads have 2 outputs."""
+
+    def __init__(self, observation_space, action_space, hidden_size=128, **kwargs):
+        super().__init__(AudioNavOptionNet(observation_space, action_space, hidden_size=hidden_size, **kwargs), 2)

@@ -111,7 +111,8 @@ int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w
                       long long ldr, int relu, float* y, long long ldy, void* stream);
 int avl_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int N,
                       int HW, int C, int groups, float eps, int relu, void* stream);
-int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, float scale, void* stream);
+int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, int C_out, float scale, void* stream);
+int avl_pad_channels(const float* x, float* y, long long rows, int C, int C_out, void* stream);
 int avl_concat_rgbd(const float* rgb, const float* depth, float* y, long long pixels, int c_rgb, int c_depth,
                     float rgb_scale, void* stream);
 int avl_append_planes(const float* x, const float* extra, float* y, int N, int HW, int C, int E, void* stream);
