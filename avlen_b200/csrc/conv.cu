@@ -57,6 +57,69 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_nhwc_kernel(const float*
   }
 }
 
+// Split GroupNorm for large batches: (1) partial sums per (sample, group) from many CTAs per sample, accumulated in
+// double with atomics; (2) a fully parallel vectorised apply pass (+ residual, ReLU).  stats: [N][groups][2] doubles.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, double* stats, int HW, int C,
+                                                       int groups, int rows_per_cta) {
+  __shared__ float ps[256], pq[256];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int c = tid % C;  // C divides 256
+  const int rpi = 256 / C;
+  const int cg = C / groups;
+  const int p0 = blockIdx.y * rows_per_cta;
+  const int p1 = min(HW, p0 + rows_per_cta);
+  const float* xs = x + (size_t)n * HW * C;
+  float s = 0.f, q = 0.f;
+  for (int p = p0 + tid / C; p < p1; p += rpi) {
+    float v = xs[(size_t)p * C + c];
+    s += v;
+    q += v * v;
+  }
+  ps[tid] = s;
+  pq[tid] = q;
+  __syncthreads();
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int t = 0; t < 256; ++t)
+      if ((t % C) / cg == tid) { S += (double)ps[t]; Q += (double)pq[t]; }
+    atomicAdd(&stats[((size_t)n * groups + tid) * 2], S);
+    atomicAdd(&stats[((size_t)n * groups + tid) * 2 + 1], Q);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ residual, float* y, long long total4,
+                                                       int HW, int C, int groups, float eps, int relu) {
+  // one float4 (4 consecutive channels of one pixel; C % 4 == 0) per iteration
+  const int cg = C / groups;
+  const double cnt = (double)HW * cg;
+  const int c4n = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int n = (int)(pix / HW);
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 r = residual ? reinterpret_cast<const float4*>(residual)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cg;
+      const double S = stats[((size_t)n * groups + g) * 2], Q = stats[((size_t)n * groups + g) * 2 + 1];
+      const double m = S / cnt;
+      double var = Q / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c + j];
+      const float b = beta[c + j] - (float)m * a;
+      float t = fmaf(o[j], a, b) + rr[j];
+      o[j] = relu ? fmaxf(t, 0.f) : t;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // -------------------------------------------------- area resize (exact 2x2 mean) + optional scale (rgb / 255)
 // smt_cnn.py:83-95 + common/utils.py:515-517 (interpolate(mode="area") 128 -> 64).  NHWC in, NHWC out.
 __global__ void resize_half_kernel(const float* __restrict__ x, float* y, int N, int H, int W, int C, int Cp,
@@ -215,6 +278,28 @@ AVL_API int avl_conv2d_fwd(const float* x, int N, int H, int W, int C, const flo
   dim3 grid(avl_div_up(M, GBM), avl_div_up(Cout, GBN), 1);
   auto kern = gemm_kernel<true, true, true>;
   AVL_LAUNCH(kern, grid, GTHREADS, 0, (cudaStream_t)stream, A, B, y, ldy, (int)M, Cout, K, g, ep, K);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+// stats_scratch: optional N*groups*2 doubles; when given (and C % 4 == 0, C <= 256) the split two-kernel version
+// runs (many CTAs per sample), otherwise the one-CTA-per-sample kernel.
+AVL_API int avl_groupnorm_fwd_split(const float* x, const float* gamma, const float* beta, const float* residual,
+                                    float* y, int N, int HW, int C, int groups, float eps, int relu,
+                                    double* stats_scratch, void* stream) {
+  if (N < 0 || HW < 1 || C < 4 || (C & 3) || groups < 1 || groups > 64 || C % groups || 256 % C) return AVL_ERR_UNSUPPORTED;
+  if (N == 0) return AVL_OK;
+  if (!x || !gamma || !beta || !y || !stats_scratch) return AVL_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  AVL_CUDA_CHECK(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 2 * (size_t)N * groups, s));
+  int rows_per_cta = 8192 / C;  // 32 KB of activations per CTA
+  if (rows_per_cta > HW) rows_per_cta = HW;
+  int splits = avl_div_up(HW, rows_per_cta);
+  AVL_LAUNCH(gn_stats_kernel, dim3(N, splits), 256, 0, s, x, stats_scratch, HW, C, groups, rows_per_cta);
+  AVL_LAUNCH_CHECK();
+  long long total4 = (long long)N * HW * C / 4;
+  AVL_LAUNCH(gn_apply_kernel, ew_grid(total4), 256, 0, s, x, stats_scratch, gamma, beta, residual, y, total4, HW, C,
+             groups, eps, relu);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

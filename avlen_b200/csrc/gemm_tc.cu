@@ -32,7 +32,9 @@ __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   do {
+    if (++spins > (1u << 24)) __trap();  // a lost arrival must fault, never hang the device
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

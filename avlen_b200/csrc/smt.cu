@@ -203,7 +203,7 @@ AVL_API int avl_tc_gemm(const float* A, long long lda, const float* B, float* C,
                            const int* m_dev, void* stream);
 AVL_API int avl_get_tensor_cores(void);
 static bool tc_ok(const float* X, long long ldx, const float* W, int rows, int K) {
-  return avl_get_tensor_cores() && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)X | (uintptr_t)W) & 15) == 0;
+  return avl_get_tensor_cores() >= 2 && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)X | (uintptr_t)W) & 15) == 0;
 }
 #else
 static bool tc_ok(const float*, long long, const float*, int, int) { return false; }

@@ -13,6 +13,7 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 _lib.register({
     "avl_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
     "avl_groupnorm_fwd": [P, P, P, P, P, I, I, I, I, F, I, P],
+    "avl_groupnorm_fwd_split": [P, P, P, P, P, I, I, I, I, F, I, P, P],
     "avl_resize_half": [P, P, I, I, I, I, I, F, P],
     "avl_pad_channels": [P, P, L, I, I, P],
     "avl_concat_rgbd": [P, P, P, L, I, I, F, P],
@@ -35,15 +36,21 @@ _lib.register({
 })
 
 _packed_cache = {}
+_gn_scratch = {}
 
 
-def set_tensor_cores(enable: bool) -> bool:
-    """Switches the tcgen05 (TF32 tensor-core) path of the dense / conv GEMMs on or off; returns the old state."""
-    return bool(_lib.lib().avl_set_tensor_cores(int(bool(enable))))
+def set_tensor_cores(level) -> int:
+    """tcgen05 (TF32) level: 0/False = fp32 SIMT only, 1/True = encoder convs + FCs (default), 2 = also the SMT
+    dense layers.  Returns the previous level."""
+    return int(_lib.lib().avl_set_tensor_cores(int(level)))
+
+
+def tensor_cores_level() -> int:
+    return int(_lib.lib().avl_get_tensor_cores())
 
 
 def tensor_cores_enabled() -> bool:
-    return bool(_lib.lib().avl_get_tensor_cores())
+    return tensor_cores_level() >= 1
 
 
 def _packed_weight(w, c_pad=None):
@@ -118,7 +125,7 @@ def linear(x, w, bias=None, relu=False, out=None):
     if out is None:
         out = torch.empty((rows, N), device=x.device, dtype=torch.float32)
     if (rows >= 512 and K % 4 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0
-            and tensor_cores_enabled()):
+            and tensor_cores_level() >= 2):
         call("avl_tc_gemm", fptr(x), x.stride(0), fptr(w), out.data_ptr(), out.stride(0), rows, N, K, None, fptr(bias),
              None, 0, int(relu), None, stream())
         return out
@@ -131,6 +138,13 @@ def groupnorm(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, ou
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if C % 4 == 0 and 256 % C == 0 and N * H * W * C >= (1 << 20):
+        st = _gn_scratch.get(x.device)
+        if st is None or st.numel() < 2 * N * groups:
+            st = _gn_scratch[x.device] = torch.empty(max(2 * N * groups, 1 << 16), device=x.device, dtype=torch.float64)
+        call("avl_groupnorm_fwd_split", fptr(x), fptr(gamma), fptr(beta), fptr(residual), fptr(out), N, H * W, C,
+             groups, float(eps), int(relu), st.data_ptr(), stream())
+        return out
     call("avl_groupnorm_fwd", fptr(x), fptr(gamma), fptr(beta), fptr(residual), fptr(out), N, H * W, C, groups,
          float(eps), int(relu), stream())
     return out

@@ -23,7 +23,7 @@ int avl_last_cuda_error(void);                 /* cudaError_t of the last failed
 const char* avl_last_cuda_error_string(void);
 int avl_device_sm_count(void);
 long long avl_launch_count(void);              /* kernels launched by this library so far in this process */
-int avl_set_tensor_cores(int enable);          /* 1 (default): tcgen05 TF32 path for dense/conv GEMMs; returns old */
+int avl_set_tensor_cores(int level);           /* tcgen05 TF32: 0 off, 1 (default) encoder convs/FCs, 2 also SMT dense; returns old */
 int avl_get_tensor_cores(void);
 
 /* ------------------------------------------------------------------------------- rows A + B: audio sensors
@@ -111,6 +111,9 @@ int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w
                       long long ldr, int relu, float* y, long long ldy, void* stream);
 int avl_groupnorm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int N,
                       int HW, int C, int groups, float eps, int relu, void* stream);
+int avl_groupnorm_fwd_split(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                            int N, int HW, int C, int groups, float eps, int relu, double* stats_scratch,
+                            void* stream);
 int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, int C_out, float scale, void* stream);
 int avl_pad_channels(const float* x, float* y, long long rows, int C, int C_out, void* stream);
 int avl_concat_rgbd(const float* rgb, const float* depth, float* y, long long pixels, int c_rgb, int c_depth,

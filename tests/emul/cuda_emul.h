@@ -129,6 +129,19 @@ static inline float atomicAdd(float* p, float v) {
   }
 }
 
+static inline double atomicAdd(double* p, double v) {
+  auto* a = reinterpret_cast<std::atomic<uint64_t>*>(p);
+  uint64_t old = a->load();
+  for (;;) {
+    double f;
+    std::memcpy(&f, &old, 8);
+    f += v;
+    uint64_t nw;
+    std::memcpy(&nw, &f, 8);
+    if (a->compare_exchange_weak(old, nw)) { double r; std::memcpy(&r, &old, 8); return r; }
+  }
+}
+
 extern unsigned char smem_raw[];
 
 namespace emul {

@@ -47,3 +47,21 @@ def test_groupnorm(emul_lib, C, H, W):
                                     H * W, C, 16, 1e-5, 1, None)
     assert rc == 0
     assert (out - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("C,H,W", [(16, 12, 11), (64, 5, 4)])
+def test_groupnorm_split(emul_lib, C, H, W):
+    import numpy as np
+    g = torch.Generator().manual_seed(C + 1)
+    x = torch.randn(3, H, W, C, generator=g) * 2 + 1
+    ga, be = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(3, H, W, C, generator=g)
+    ref = F.relu(F.group_norm(x.permute(0, 3, 1, 2), 16, ga, be, 1e-5) + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    out = torch.zeros_like(x)
+    st = np.zeros(3 * 16 * 2, np.float64)
+    emul_lib.avl_groupnorm_fwd_split.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp, vp]
+    xn, gn, bn, rn, on = _np(x), _np(ga), _np(be), _np(res), out.numpy()
+    rc = emul_lib.avl_groupnorm_fwd_split(xn.ctypes.data, gn.ctypes.data, bn.ctypes.data, rn.ctypes.data,
+                                          on.ctypes.data, 3, H * W, C, 16, 1e-5, 1, st.ctypes.data, None)
+    assert rc == 0
+    assert (out - ref).abs().max() < 1e-4
