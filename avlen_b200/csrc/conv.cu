@@ -87,36 +87,44 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ residual, float* y, long long total4,
-                                                       int HW, int C, int groups, float eps, int relu) {
-  // one float4 (4 consecutive channels of one pixel; C % 4 == 0) per iteration
-  const int cg = C / groups;
+// per-(sample, channel) affine: y = x * a + b  with a = rstd * gamma, b = beta - mean * a
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float2* ab, int N, int HW, int C, int groups,
+                                   float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int c = i % C, n = i / C;
+  const int cg = C / groups, g = c / cg;
   const double cnt = (double)HW * cg;
+  const double S = stats[((size_t)n * groups + g) * 2], Q = stats[((size_t)n * groups + g) * 2 + 1];
+  const double m = S / cnt;
+  double var = Q / cnt - m * m;
+  if (var < 0.0) var = 0.0;
+  const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+  ab[i] = make_float2(a, beta[c] - (float)m * a);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float2* __restrict__ ab,
+                                                       const float* __restrict__ residual, float* y, long long total4,
+                                                       int HW, int C, int relu) {
+  // one float4 (4 consecutive channels of one pixel; C % 4 == 0) per iteration
   const int c4n = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
     const long long pix = i / c4n;
     const int n = (int)(pix / HW);
-    float4 v = reinterpret_cast<const float4*>(x)[i];
-    float4 r = residual ? reinterpret_cast<const float4*>(residual)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float o[4] = {v.x, v.y, v.z, v.w};
-    const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cg;
-      const double S = stats[((size_t)n * groups + g) * 2], Q = stats[((size_t)n * groups + g) * 2 + 1];
-      const double m = S / cnt;
-      double var = Q / cnt - m * m;
-      if (var < 0.0) var = 0.0;
-      const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c + j];
-      const float b = beta[c + j] - (float)m * a;
-      float t = fmaf(o[j], a, b) + rr[j];
-      o[j] = relu ? fmaxf(t, 0.f) : t;
-    }
-    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 r = residual ? reinterpret_cast<const float4*>(residual)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2* p = ab + (size_t)n * C + c;
+    const float2 p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2), p3 = __ldg(p + 3);
+    float4 o;
+    o.x = fmaf(v.x, p0.x, p0.y) + r.x;
+    o.y = fmaf(v.y, p1.x, p1.y) + r.y;
+    o.z = fmaf(v.z, p2.x, p2.y) + r.z;
+    o.w = fmaf(v.w, p3.x, p3.y) + r.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = o;
   }
 }
 
@@ -242,6 +250,30 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, long long lds, f
   }
 }
 
+__global__ void zero_cols_kernel(float* y, long long ldy, int rows, int cols) {
+  long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[(i / cols) * ldy + (i % cols)] = 0.f;
+}
+
+__global__ void epilogue_cols_kernel(float* y, long long ldy, int rows, int cols, const float* __restrict__ scale,
+                                     const float* __restrict__ bias, const float* __restrict__ residual, long long ldr,
+                                     int relu) {
+  long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cols);
+    long long r = i / cols;
+    float v = y[r * ldy + c];
+    if (scale) v *= scale[c];
+    if (bias) v += bias[c];
+    if (residual) v += residual[r * ldr + c];
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = v;
+  }
+}
+
 static int ew_grid(long long total) {
   long long g = (total + 255) / 256;
   long long cap = (long long)avl_num_sms() * 16;
@@ -277,13 +309,33 @@ AVL_API int avl_conv2d_fwd(const float* x, int N, int H, int W, int C, const flo
   GemmOperand A = {x, 0, 1}, B = {w, (long long)K, 1};
   dim3 grid(avl_div_up(M, GBM), avl_div_up(Cout, GBN), 1);
   auto kern = gemm_kernel<true, true, true>;
+  const int tiles = grid.x * grid.y;
+  if (tiles * 4 <= avl_num_sms() && K >= 1024) {
+    // few output tiles but a long reduction (FC layers at rollout batch sizes): split K over CTAs with atomic
+    // accumulation into a zeroed output, then apply the epilogue in a second tiny kernel
+    int splits = avl_num_sms() / tiles;
+    int kps = ((K + splits - 1) / splits + GBK - 1) / GBK * GBK;
+    if (kps < 128) kps = 128;
+    splits = (K + kps - 1) / kps;
+    grid.z = splits;
+    AVL_LAUNCH(zero_cols_kernel, ew_grid(M * Cout), 256, 0, (cudaStream_t)stream, y, ldy, (int)M, Cout);
+    AVL_LAUNCH_CHECK();
+    GemmEpilogue raw = ep;
+    raw.bias = raw.scale = raw.residual = nullptr; raw.relu = 0;
+    AVL_LAUNCH(kern, grid, GTHREADS, 0, (cudaStream_t)stream, A, B, y, ldy, (int)M, Cout, K, g, raw, kps);
+    AVL_LAUNCH_CHECK();
+    AVL_LAUNCH(epilogue_cols_kernel, ew_grid(M * Cout), 256, 0, (cudaStream_t)stream, y, ldy, (int)M, Cout, scale,
+               bias, residual, ldr, relu);
+    AVL_LAUNCH_CHECK();
+    return AVL_OK;
+  }
   AVL_LAUNCH(kern, grid, GTHREADS, 0, (cudaStream_t)stream, A, B, y, ldy, (int)M, Cout, K, g, ep, K);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
 
-// stats_scratch: optional N*groups*2 doubles; when given (and C % 4 == 0, C <= 256) the split two-kernel version
-// runs (many CTAs per sample), otherwise the one-CTA-per-sample kernel.
+// stats_scratch: N*groups*2 doubles followed by N*C float2 (i.e. (2*N*groups + N*C) * 8 bytes).  Three kernels:
+// partial sums from many CTAs per sample (double atomics), per-(n,c) affine, fully parallel float4 apply.
 AVL_API int avl_groupnorm_fwd_split(const float* x, const float* gamma, const float* beta, const float* residual,
                                     float* y, int N, int HW, int C, int groups, float eps, int relu,
                                     double* stats_scratch, void* stream) {
@@ -297,9 +349,12 @@ AVL_API int avl_groupnorm_fwd_split(const float* x, const float* gamma, const fl
   int splits = avl_div_up(HW, rows_per_cta);
   AVL_LAUNCH(gn_stats_kernel, dim3(N, splits), 256, 0, s, x, stats_scratch, HW, C, groups, rows_per_cta);
   AVL_LAUNCH_CHECK();
+  float2* ab = reinterpret_cast<float2*>(stats_scratch + 2 * (size_t)N * groups);
+  AVL_LAUNCH(gn_finalize_kernel, avl_div_up((long long)N * C, 256), 256, 0, s, stats_scratch, gamma, beta, ab, N, HW, C,
+             groups, eps);
+  AVL_LAUNCH_CHECK();
   long long total4 = (long long)N * HW * C / 4;
-  AVL_LAUNCH(gn_apply_kernel, ew_grid(total4), 256, 0, s, x, stats_scratch, gamma, beta, residual, y, total4, HW, C,
-             groups, eps, relu);
+  AVL_LAUNCH(gn_apply_kernel, ew_grid(total4), 256, 0, s, x, ab, residual, y, total4, HW, C, relu);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

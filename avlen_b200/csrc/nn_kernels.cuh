@@ -302,14 +302,15 @@ constexpr int ATT_WARPS = 8;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, float* out, float* lse, int D,
-                     float scale) {
+                     float scale, int vcap) {
+  // vcap: host-known upper bound on tokens per sample (<= ATT_MAXV); shared memory is carved for vcap tokens.
   AVL_DYN_SMEM(smem_raw);
   const int b = blockIdx.x, h = blockIdx.y;
-  const int r0 = off[b], V = off[b + 1] - r0;
+  const int r0 = off[b], V = min(off[b + 1] - r0, vcap);
   float* Ks = reinterpret_cast<float*>(smem_raw);   // [V][33]
-  float* Vs = Ks + ATT_MAXV * 33;                   // [V][33]
-  float* Ps = Vs + ATT_MAXV * 33;                   // [warps][ATT_MAXV]
-  float* Qs = Ps + ATT_WARPS * ATT_MAXV;            // [warps][32]
+  float* Vs = Ks + vcap * 33;                       // [V][33]
+  float* Ps = Vs + vcap * 33;                       // [warps][vcap]
+  float* Qs = Ps + ATT_WARPS * vcap;                // [warps][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = 3 * D;
   for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
@@ -319,7 +320,7 @@ attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off,
     Vs[j * 33 + d] = row[2 * D];
   }
   __syncthreads();
-  float* ps = Ps + warp * ATT_MAXV;
+  float* ps = Ps + warp * vcap;
   float* qs = Qs + warp * 32;
   for (int i = warp; i < V; i += ATT_WARPS) {
     qs[lane] = qkv[(size_t)(r0 + i) * ld + h * ATT_HD + lane] * scale;
@@ -352,18 +353,19 @@ attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off,
 // Backward with recomputation.  dqkv receives (dq | dk | dv) rows.
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_self_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, const float* __restrict__ out,
-                     const float* __restrict__ lse, const float* __restrict__ dout, float* dqkv, int D, float scale) {
+                     const float* __restrict__ lse, const float* __restrict__ dout, float* dqkv, int D, float scale,
+                     int vcap) {
   AVL_DYN_SMEM(smem_raw);
   const int b = blockIdx.x, h = blockIdx.y;
-  const int r0 = off[b], V = off[b + 1] - r0;
+  const int r0 = off[b], V = min(off[b + 1] - r0, vcap);
   float* Qs = reinterpret_cast<float*>(smem_raw);  // [V][33] (pre-scaled)
-  float* Ks = Qs + ATT_MAXV * 33;
-  float* Vs = Ks + ATT_MAXV * 33;
-  float* Gs = Vs + ATT_MAXV * 33;                  // dO
-  float* Ls = Gs + ATT_MAXV * 33;                  // lse [V]
-  float* Ds = Ls + ATT_MAXV;                       // D_i = dO_i . O_i  [V]
-  float* Wa = Ds + ATT_MAXV;                       // [warps][ATT_MAXV]
-  float* Wb = Wa + ATT_WARPS * ATT_MAXV;           // [warps][ATT_MAXV]
+  float* Ks = Qs + vcap * 33;
+  float* Vs = Ks + vcap * 33;
+  float* Gs = Vs + vcap * 33;                      // dO
+  float* Ls = Gs + vcap * 33;                      // lse [V]
+  float* Ds = Ls + vcap;                           // D_i = dO_i . O_i  [V]
+  float* Wa = Ds + vcap;                           // [warps][vcap]
+  float* Wb = Wa + ATT_WARPS * vcap;               // [warps][vcap]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = 3 * D, H = D / ATT_HD;
   for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
@@ -383,8 +385,8 @@ attn_self_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off,
     if (lane == 0) Ds[i] = t;
   }
   __syncthreads();
-  float* wa = Wa + warp * ATT_MAXV;
-  float* wb = Wb + warp * ATT_MAXV;
+  float* wa = Wa + warp * vcap;
+  float* wb = Wb + warp * vcap;
   // pass 1: dQ_i = scale * sum_j dS_ij K_j
   for (int i = warp; i < V; i += ATT_WARPS) {
     const float li = Ls[i], di = Ds[i];

@@ -294,8 +294,16 @@ static void relu_bwd(Launcher& L, float* dy, const float* y, const int* rows_dev
   L.check();
 }
 
-constexpr size_t kAttnFwdSmem = (size_t)(2 * ATT_MAXV * 33 + ATT_WARPS * ATT_MAXV + ATT_WARPS * 32) * sizeof(float);
-constexpr size_t kAttnBwdSmem = (size_t)(4 * ATT_MAXV * 33 + 2 * ATT_MAXV + 2 * ATT_WARPS * ATT_MAXV) * sizeof(float);
+static size_t attn_fwd_smem(int vcap) { return (size_t)(2 * vcap * 33 + ATT_WARPS * vcap + ATT_WARPS * 32) * sizeof(float); }
+static size_t attn_bwd_smem(int vcap) { return (size_t)(4 * vcap * 33 + 2 * vcap + 2 * ATT_WARPS * vcap) * sizeof(float); }
+static const size_t kAttnFwdSmem = attn_fwd_smem(ATT_MAXV);
+static const size_t kAttnBwdSmem = attn_bwd_smem(ATT_MAXV);
+static int attn_vcap(int rows_cap, int B) {  // per-sample token bound implied by the caller's row capacity
+  int v = (rows_cap + B - 1) / B;
+  if (v > ATT_MAXV) v = ATT_MAXV;
+  if (v < 1) v = 1;
+  return v;
+}
 static bool g_attn_attr_set = false;
 static int ensure_attn_attrs() {
   if (g_attn_attr_set) return AVL_OK;
@@ -363,8 +371,9 @@ static void tf_forward(Launcher& L, const float* const* P, const TfBufs& t, cons
                        const int* total, int Rcap, int B, int D, const float* tgt, float* out) {
   const int H = D / ATT_HD;
   const float scale = 1.0f / sqrtf((float)ATT_HD);
+  const int vcap = attn_vcap(Rcap, B);
   lin_fwd(L, X0, D, P[TP_ENC_IN_W], P[TP_ENC_IN_B], t.QKV, 3 * D, Rcap, 3 * D, D, 0, total);
-  AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, H), ATT_WARPS * 32, kAttnFwdSmem, L.s, t.QKV, off, t.ATT, t.LSE, D, scale);
+  AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, H), ATT_WARPS * 32, attn_fwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, D, scale, vcap);
   L.check();
   lin_fwd(L, t.ATT, D, P[TP_ENC_OUT_W], P[TP_ENC_OUT_B], t.AO, D, Rcap, D, D, 0, total);
   ln_fwd(L, X0, t.AO, P[TP_ENC_N1_W], P[TP_ENC_N1_B], t.X1, t.ST1, total, Rcap, D);
@@ -398,6 +407,7 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
                         const float* gout) {
   const int H = D / ATT_HD;
   const float scale = 1.0f / sqrtf((float)ATT_HD);
+  const int vcap = attn_vcap(Rcap, B);
   const size_t DD = (size_t)D * D;
   // ---- decoder
   ln_bwd(L, t.T3, nullptr, P[TP_DEC_NORM_W], t.STT4, gout, t.gB1, gp(G, TP_DEC_NORM_W), gp(G, TP_DEC_NORM_B), nullptr, B, D);
@@ -438,7 +448,7 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
   // GC = grad wrt (X0 + AO)
   lin_bwd_w(L, t.GC, D, t.ATT, D, gp(G, TP_ENC_OUT_W), D, gp(G, TP_ENC_OUT_B), Rcap, D, D, total);
   lin_bwd_x(L, t.GC, D, P[TP_ENC_OUT_W], D, t.GB, D, Rcap, D, D, 0, total, t.WT);  // GB = gATT
-  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_WARPS * 32, kAttnBwdSmem, L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale);
+  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_WARPS * 32, attn_bwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale, vcap);
   L.check();
   lin_bwd_w(L, t.GQKV, 3 * D, X0, D, gp(G, TP_ENC_IN_W), D, gp(G, TP_ENC_IN_B), Rcap, 3 * D, D, total);
   lin_bwd_x(L, t.GQKV, 3 * D, P[TP_ENC_IN_W], D, t.GC, D, Rcap, 3 * D, D, 1, total, t.WT);  // GC = gX0
@@ -515,7 +525,7 @@ AVL_API int avl_attn_self_fwd(const float* qkv, const int* off, int B, int D, fl
   int rc = ensure_attn_attrs();
   if (rc) return rc;
   AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, D / 32), ATT_WARPS * 32, kAttnFwdSmem, (cudaStream_t)stream, 
-      qkv, off, out, lse, D, 1.0f / sqrtf(32.f));
+      qkv, off, out, lse, D, 1.0f / sqrtf(32.f), ATT_MAXV);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
@@ -528,7 +538,7 @@ AVL_API int avl_attn_self_bwd(const float* qkv, const int* off, int B, int D, co
   int rc = ensure_attn_attrs();
   if (rc) return rc;
   AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, D / 32), ATT_WARPS * 32, kAttnBwdSmem, (cudaStream_t)stream, 
-      qkv, off, out, lse, dout, dqkv, D, 1.0f / sqrtf(32.f));
+      qkv, off, out, lse, dout, dqkv, D, 1.0f / sqrtf(32.f), ATT_MAXV);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

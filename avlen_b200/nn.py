@@ -140,8 +140,9 @@ def groupnorm(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, ou
         out = torch.empty_like(x)
     if C % 4 == 0 and 256 % C == 0 and N * H * W * C >= (1 << 20):
         st = _gn_scratch.get(x.device)
-        if st is None or st.numel() < 2 * N * groups:
-            st = _gn_scratch[x.device] = torch.empty(max(2 * N * groups, 1 << 16), device=x.device, dtype=torch.float64)
+        need = 2 * N * groups + N * C  # doubles: stats + (a, b) float2 per (n, c)
+        if st is None or st.numel() < need:
+            st = _gn_scratch[x.device] = torch.empty(max(need, 1 << 16), device=x.device, dtype=torch.float64)
         call("avl_groupnorm_fwd_split", fptr(x), fptr(gamma), fptr(beta), fptr(residual), fptr(out), N, H * W, C,
              groups, float(eps), int(relu), st.data_ptr(), stream())
         return out

@@ -6,7 +6,7 @@
 AVL_EMUL_DEFINE_GLOBALS
 
 extern "C" int avl_set_cuda_error(int e) { return e; }
-int avl_num_sms() { return 2; }
+int avl_num_sms() { return 8; }
 extern "C" void avl_count_launch() {}
 
 #include "../../avlen_b200/csrc/audio.cu"

@@ -14,7 +14,8 @@ def _np(t):
 
 
 @pytest.mark.parametrize("shape", [(2, 9, 7, 2, 5, 5, 5, 2, 0), (2, 8, 8, 3, 16, 7, 7, 1, 3), (1, 10, 6, 16, 32, 3, 3, 2, 1),
-                                   (2, 6, 6, 16, 32, 1, 1, 2, 0), (3, 4, 3, 8, 20, 4, 3, 1, 0)])
+                                   (2, 6, 6, 16, 32, 1, 1, 2, 0), (3, 4, 3, 8, 20, 4, 3, 1, 0),
+                                   (2, 8, 8, 32, 10, 8, 8, 1, 0)])  # last: split-K path (K = 2048, one output tile)
 def test_conv2d(emul_lib, shape):
     N, H, W, C, Co, KH, KW, s, p = shape
     g = torch.Generator().manual_seed(sum(shape))
@@ -58,7 +59,7 @@ def test_groupnorm_split(emul_lib, C, H, W):
     res = torch.randn(3, H, W, C, generator=g)
     ref = F.relu(F.group_norm(x.permute(0, 3, 1, 2), 16, ga, be, 1e-5) + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     out = torch.zeros_like(x)
-    st = np.zeros(3 * 16 * 2, np.float64)
+    st = np.zeros(3 * 16 * 2 + 3 * C, np.float64)
     emul_lib.avl_groupnorm_fwd_split.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp, vp]
     xn, gn, bn, rn, on = _np(x), _np(ga), _np(be), _np(res), out.numpy()
     rc = emul_lib.avl_groupnorm_fwd_split(xn.ctypes.data, gn.ctypes.data, bn.ctypes.data, rn.ctypes.data,

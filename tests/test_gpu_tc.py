@@ -72,8 +72,8 @@ def test_tc_conv_matches_fp32(shape):
     assert rel(out, tref) < TOL_TC
 
 
-@pytest.mark.parametrize("level,grad_tol", [(1, 5e-2), (2, 0.15)])
-def test_policy_with_tensor_cores_matches_oracle(level, grad_tol):
+@pytest.mark.parametrize("level,min_cos", [(1, 0.9995), (2, 0.995)])
+def test_policy_with_tensor_cores_matches_oracle(level, min_cos):
     """Whole SAVi act + evaluate path with the tensor-core kernels on.  Level 1 (default): TF32 encoders, fp32 SMT.
     Level 2 (opt-in): TF32 SMT dense layers as well.  TF32 operands are truncated by the tensor core (measured GEMM
     rms error 7.7e-4); gradients through LayerNorm / softmax chains amplify that to the percent level."""
@@ -97,8 +97,9 @@ def test_policy_with_tensor_cores_matches_oracle(level, grad_tol):
     v, lp, ent, _, _ = p.evaluate_actions(cu(obs), h.cuda(), pa.cuda(), mk.cuda(), act.cuda(), mem.cuda(), masks.cuda())
     (v.sum() + 2 * lp.sum() + 0.5 * ent).backward()
     og = dict(o.named_parameters())
-    worst = 0.0
+    worst = 1.0
     for k, q in p.named_parameters():
         if q.requires_grad and og[k].grad is not None and float(og[k].grad.abs().max()) > 1e-6:
-            worst = max(worst, rel(q.grad.cpu(), og[k].grad))
-    assert worst < grad_tol, worst
+            cos = float(torch.nn.functional.cosine_similarity(q.grad.cpu().flatten(), og[k].grad.flatten(), dim=0))
+            worst = min(worst, cos)
+    assert worst > min_cos, worst  # gradient direction per parameter tensor
