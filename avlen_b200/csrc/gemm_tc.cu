@@ -48,6 +48,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// .ca variant: the im2col gather re-reads every input pixel KH*KW times from neighbouring rows of the same CTA
+// tile; keeping those lines in L1 turns most of that traffic into L1 hits instead of L2 round trips.
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -117,7 +122,7 @@ struct TcArgs {
   const int* m_dev;
 };
 
-template <bool CONV>
+template <bool CONV, bool CA = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   AVL_DYN_SMEM(smem);
   __shared__ __align__(8) unsigned long long bars[TC_STAGES + 1];
@@ -208,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
           bytes = 16;
         }
       }
-      cp_async16(a_dst + row * 16, src, bytes);
+      if (CA) cp_async16_ca(a_dst + row * 16, src, bytes);
+      else cp_async16(a_dst + row * 16, src, bytes);
     }
     const uint32_t b_dst = smem_base + slot * stage_bytes + a_stage + c * b_plane;
     for (int row = r_first; row < bn; row += 16) {
@@ -286,6 +292,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   }
 }
 
+static int g_tc_ca = 1;
+
 static int pick_bn(int N) {
   int n16 = (N + 15) / 16 * 16;
   if (n16 <= 256) return n16;
@@ -304,16 +312,25 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   if (!attr_set) {
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
     attr_set = true;
   }
   dim3 grid(avl_div_up(p.M, TC_BM), avl_div_up(p.N, p.bn));
-  if (conv) tc_gemm_kernel<true><<<grid, TC_THREADS, smem, s>>>(p);
+  if (conv && g_tc_ca) tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, s>>>(p);
+  else if (conv) tc_gemm_kernel<true><<<grid, TC_THREADS, smem, s>>>(p);
   else tc_gemm_kernel<false><<<grid, TC_THREADS, smem, s>>>(p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
 
 }  // namespace
+
+// 1 (default): im2col gathers go through L1 (cp.async.ca); 0: L2 only (cp.async.cg).  Returns the old value.
+AVL_API int avl_set_tc_conv_l1(int on) {
+  int old = g_tc_ca;
+  g_tc_ca = on ? 1 : 0;
+  return old;
+}
 
 // Dense: C[M,N] = act(scale * A[M,K] B[N,K]^T + bias + residual).  A rows / B rows must be 16-byte aligned
 // (lda % 4 == 0, K % 4 == 0).  m_dev: optional device-side row count (packed SMT rows).

@@ -33,7 +33,15 @@ _lib.register({
     "avl_tc_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
     "avl_set_tensor_cores": [I],
     "avl_get_tensor_cores": [],
-})
+    "avl_set_tc_conv_l1": [I],
+    "avl_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "avl_conv2d_wgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "avl_relu_mask": [P, L, P, L, L, I, P],
+    "avl_groupnorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
+    "avl_gru_workspace_bytes": [I, I, I, I, I],
+    "avl_gru_forward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
+    "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+}, {"avl_gru_workspace_bytes": c_longlong})
 
 _packed_cache = {}
 _gn_scratch = {}
@@ -81,8 +89,21 @@ def conv_out(size, k, stride, pad):
     return (size + 2 * pad - k) // stride + 1
 
 
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=None, out=None):
-    """x (N,H,W,C) NHWC; w (Cout,C,KH,KW) OIHW (the reference's nn.Conv2d layout). Returns (N,OH,OW,Cout)."""
+    """x (N,H,W,C) NHWC; w (Cout,C,KH,KW) OIHW (the reference's nn.Conv2d layout). Returns (N,OH,OW,Cout).
+    Differentiable (custom backward on the dgrad / wgrad kernels) when an input requires grad."""
+    if _needs_grad(x, w, bias):
+        if scale is not None or residual is not None or out is not None:
+            raise _lib.AvlenError("the differentiable conv2d takes no scale / residual / out arguments")
+        return _ConvFn.apply(x, w, bias, int(stride), int(pad), bool(relu))
+    return _conv2d_raw(x, w, bias, stride, pad, relu, scale, residual, out)
+
+
+def _conv2d_raw(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=None, out=None):
     N, H, W, C = x.shape
     Cout, Cw, KH, KW = w.shape
     assert Cw == C or (Cw < C and C % 4 == 0), (Cw, C)  # x may carry zero-padded channels (tensor-core path)
@@ -109,12 +130,73 @@ def conv2d(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residual=No
     return out
 
 
+class _ConvFn(torch.autograd.Function):
+    """conv2d (+bias, +ReLU) with dgrad / wgrad on the hand-written kernels (csrc/nn_bwd.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, relu):
+        x = x.contiguous()
+        y = _conv2d_raw(x, w, bias, stride, pad, relu)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (stride, pad, relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        stride, pad, relu, has_bias = ctx.cfg
+        N, H, W, C = x.shape
+        Cout, Cw, KH, KW = w.shape
+        gy = gy.contiguous()
+        if relu:
+            gy = gy.clone()
+            call("avl_relu_mask", fptr(gy), Cout, fptr(y), Cout, gy.numel() // Cout, Cout, stream())
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            call("avl_conv2d_dgrad", fptr(gy), fptr(w.contiguous()), fptr(gx), N, H, W, C, Cout, KH, KW, stride, pad, 0,
+                 stream())
+        need_w, need_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        if need_w or need_b:
+            gw = torch.zeros_like(w, memory_format=torch.contiguous_format) if need_w else None
+            gb = torch.zeros(Cout, device=x.device, dtype=torch.float32) if need_b else None
+            call("avl_conv2d_wgrad", fptr(x), fptr(gy), fptr(gw), fptr(gb), N, H, W, C, Cout, KH, KW, stride, pad,
+                 stream())
+        return gx, gw, gb, None, None, None
+
+
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, groups, eps, relu):
+        x = x.contiguous()
+        y = _groupnorm_raw(x, gamma, beta, groups, eps, relu, residual.contiguous() if residual is not None else None)
+        ctx.save_for_backward(x, gamma, y if relu else None)
+        ctx.cfg = (groups, eps, relu, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, y = ctx.saved_tensors
+        groups, eps, relu, has_res = ctx.cfg
+        N, H, W, C = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[3]) else None
+        gg = torch.zeros_like(gamma) if ctx.needs_input_grad[1] else None
+        gb = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
+        call("avl_groupnorm_bwd", fptr(x), fptr(y), fptr(gy), fptr(gamma), fptr(gx), fptr(gres), fptr(gg), fptr(gb), N,
+             H * W, C, groups, eps, int(relu), stream())
+        return gx, gg, gb, gres, None, None, None
+
+
 def linear_flat(x_nhwc, w, bias=None, relu=False, out=None):
     """nn.Linear applied to the NCHW-flattened activation, computed from the NHWC tensor: the (O, C*H*W) weight is
     viewed as an (O, C, H, W) kernel covering the whole map (no repacking of the reference's weights)."""
     N, H, W, C = x_nhwc.shape
     O = w.shape[0]
-    y = conv2d(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu, out=out)
+    if _needs_grad(x_nhwc, w, bias):
+        return conv2d(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu).view(N, O)
+    y = _conv2d_raw(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu, out=out)
     return y.view(N, O) if out is None else out
 
 
@@ -135,6 +217,14 @@ def linear(x, w, bias=None, relu=False, out=None):
 
 
 def groupnorm(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, out=None):
+    """GroupNorm (+ residual) (+ ReLU) on NHWC.  Differentiable when an input requires grad (then ``out`` is
+    ignored: the GroupNorm input has to survive for the backward pass)."""
+    if _needs_grad(x, gamma, beta, residual):
+        return _GroupNormFn.apply(x, gamma, beta, residual, int(groups), float(eps), bool(relu))
+    return _groupnorm_raw(x, gamma, beta, groups, eps, relu, residual, out)
+
+
+def _groupnorm_raw(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=None, out=None):
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)

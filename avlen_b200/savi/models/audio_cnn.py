@@ -51,8 +51,7 @@ class AudioCNN(nn.Module):
 
     def forward(self, observations, out=None):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise _lib.AvlenError("AudioCNN backward is not built yet: freeze the encoder (net.freeze_encoders()) "
-                                  "or call under torch.no_grad()")
+            out = None  # differentiable path (conv dgrad / wgrad kernels): results are fresh autograd tensors
         x = observations[self._audiogoal_sensor].contiguous()
         if self._has_distractor_sound:
             x = K.append_planes(x, observations["category"])

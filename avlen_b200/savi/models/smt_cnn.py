@@ -46,6 +46,12 @@ class SMTCNN(nn.Module):
 
     def forward(self, observations, out=None):
         n = observations[self.input_modalities[0]].shape[0]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            feats = []
+            for name in self.input_modalities:
+                x = K.resize_half(observations[name].contiguous(), 1.0 / 255.0 if name == "rgb" else 1.0, None)
+                feats.append(getattr(self, name + "_encoder")(x))
+            return torch.cat(feats, dim=1)
         if out is None:
             out = torch.empty((n, self._feat_dims), device=observations[self.input_modalities[0]].device,
                               dtype=torch.float32)

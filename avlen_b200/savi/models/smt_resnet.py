@@ -80,8 +80,7 @@ class CustomResNet(nn.Module):
     def forward(self, x, out=None):
         """x: (N, H, W, C) NHWC float32.  Returns (N, num_classes) (optionally written into ``out``)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise _lib.AvlenError("custom_resnet18 backward is not built yet: freeze the encoder "
-                                  "(net.freeze_encoders()) or call under torch.no_grad()")
+            out = None  # differentiable path: K.conv2d / K.groupnorm switch to their autograd Functions
         x = K.conv2d(x, self.conv1.weight, None, 1, 3)
         x = K.groupnorm(x, self.bn1.weight, self.bn1.bias, self.bn1.num_groups, self.bn1.eps, relu=True, out=x)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):

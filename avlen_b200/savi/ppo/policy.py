@@ -268,8 +268,20 @@ class AudioNavSMTNet(Net):
             p.requires_grad for p in itertools.chain(self.goal_encoder.parameters(), self.visual_encoder.parameters(),
                                                      self.action_encoder.parameters()))
         if enc_trainable:
-            raise _lib.AvlenError("encoder backward is not built yet: call net.freeze_encoders() "
-                                  "(savi.yaml: freeze_encoders True) or run under torch.no_grad()")
+            # training encoders (savi_pretraining / savi_interactive yaml: freeze_encoders False): autograd path
+            parts = [self.visual_encoder(observations)]
+            if prev_actions.shape[1] == self._action_size:
+                onehot = prev_actions.float()
+            else:
+                onehot = torch.zeros(n, self._action_size, device=dev).scatter_(1, prev_actions.long(), 1.0)
+            parts.append(cuda_linear(onehot, self.action_encoder.weight, self.action_encoder.bias))
+            parts.append(self.goal_encoder(observations))
+            if self._use_category_input:
+                parts.append(observations[CATEGORY])
+            parts.append(observations[POSE])
+            if extra_cols:
+                parts.append(torch.zeros(n, extra_cols, device=dev))
+            return torch.cat(parts, dim=1)
         with torch.no_grad():
             x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
             self.visual_encoder(observations, out=x[:, 0:128])
@@ -313,12 +325,15 @@ class AudioNavOptionNet(AudioNavSMTNet):
         e = self._query_count_emb_size
         x = self.get_features(observations, prev_actions, extra_cols=e)  # [x (276) | query_state (32)]
         base = self._base_feature_size
-        with torch.no_grad():
-            K.copy_cols(query_state.contiguous(), x[:, base:base + e])
+        if x.requires_grad:  # encoders are training: keep the autograd graph intact (no in-place column writes)
+            x = torch.cat([x[:, :base], query_state.float()], dim=1)
+        else:
+            with torch.no_grad():
+                K.copy_cols(query_state.contiguous(), x[:, base:base + e])
         belief = self._belief(observations, x.shape[0], x.device)
         x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
         with torch.no_grad():  # memory rows: [x | last_query_info] (policy.py:1062-1063)
-            x_for_memory = x.clone()
+            x_for_memory = x.detach().clone()
             K.copy_cols(last_query_info.contiguous(), x_for_memory[:, base:base + e])
         return x_att, rnn_hidden_states, x_for_memory
 

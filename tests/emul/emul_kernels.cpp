@@ -13,6 +13,7 @@ extern "C" void avl_count_launch() {}
 #include "../../avlen_b200/csrc/rl.cu"
 #include "../../avlen_b200/csrc/smt.cu"
 #include "../../avlen_b200/csrc/conv.cu"
+#include "../../avlen_b200/csrc/nn_bwd.cu"
 
 #define EMUL_API extern "C" __attribute__((visibility("default")))
 
