@@ -658,3 +658,159 @@ AVL_API int avl_smt_status(int B, int rows_cap, int F, int D, void* workspace, i
   if (overflow) AVL_CUDA_CHECK(cudaMemcpy(overflow, s.err, sizeof(int), cudaMemcpyDeviceToHost));
   return AVL_OK;
 }
+
+// =====================================================================================================
+// Row K: DialogStateEncoder.single_forward (ss_baselines/savi/models/dialog_state_encoder.py:114-155).
+//   tokens of sample b = [state_memory[s, env(b)] for the valid slots s < K] + [x_att[b]]      (256-d each)
+//   with a dialog: token <- fusion_encoder(cat[token, d_emb[b]])  (512 -> 256 ReLU -> 256)       (:138-140)
+//   token += pe[agent_step[b]]   (sinusoidal table, max_len 100, dropout 0)                       (:142, :39)
+//   out = Transformer(src = tokens, tgt = goal, key padding = invalid slots)[-1]                 (:147-152)
+// Same packed-token design as the scene memory: only valid slots become rows.
+// params: TP_COUNT transformer pointers followed by fusion_encoder.{0,2}.{weight,bias}.
+namespace {
+enum { DP_FUS0_W = TP_COUNT, DP_FUS0_B, DP_FUS2_W, DP_FUS2_B, DP_COUNT };
+
+struct DlgBufs {
+  int *cnt, *off, *total, *err, *tok_slot, *tok_sample;
+  float *XIN, *PE, *H1, *X0, *GH1, *GXIN;
+  TfBufs tf;
+};
+
+static size_t dlg_layout(char* base, DlgBufs& s, size_t B, size_t R, int D, bool bwd) {
+  Arena a{base};
+  s.cnt = a.take<int>(B); s.off = a.take<int>(B + 1); s.total = a.take<int>(1); s.err = a.take<int>(1);
+  s.tok_slot = a.take<int>(R); s.tok_sample = a.take<int>(R);
+  s.XIN = a.take<float>(R * 2 * D); s.PE = a.take<float>(R * D); s.H1 = a.take<float>(R * D);
+  s.X0 = a.take<float>(R * D);
+  tf_alloc(a, s.tf, R, B, D, D / ATT_HD, bwd);
+  s.GH1 = bwd ? a.take<float>(R * D) : nullptr;
+  s.GXIN = bwd ? a.take<float>(R * 2 * D) : nullptr;
+  return a.off + 256;
+}
+
+// one warp per packed row: writes the token (+ d_emb) into XIN, the positional row into PE, and when there is no
+// dialog X0 = token + pe directly.
+__global__ void dlg_gather_kernel(const float* __restrict__ x_att, const float* __restrict__ mem,
+                                  const int* __restrict__ env_index, const float* __restrict__ d_emb,
+                                  const int* __restrict__ agent_step, const float* __restrict__ pe_table, int pe_len,
+                                  const int* __restrict__ tok_slot, const int* __restrict__ tok_sample,
+                                  const int* __restrict__ total, int rows_cap, int K, int n_mem_envs, int D,
+                                  float* XIN, float* PE, float* X0) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int R = min(*total, rows_cap);
+  if (r >= R) return;
+  const int b = tok_sample[r], slot = tok_slot[r];
+  const float* f = x_att + (size_t)b * D;
+  if (slot < K) {
+    const int env = env_index ? env_index[b] : b;
+    f = mem + ((size_t)slot * n_mem_envs + env) * D;
+  }
+  int st = agent_step[b];
+  st = st < 0 ? 0 : (st >= pe_len ? pe_len - 1 : st);
+  const float* pe = pe_table + (size_t)st * D;
+  if (d_emb) {
+    float* o = XIN + (size_t)r * 2 * D;
+    const float* de = d_emb + (size_t)b * D;
+    for (int c = lane; c < D; c += 32) {
+      o[c] = f[c];
+      o[D + c] = de[c];
+      PE[(size_t)r * D + c] = pe[c];
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) X0[(size_t)r * D + c] = f[c] + pe[c];
+  }
+}
+
+// dx_att[b] = g[last row of b][:D] ; dd_emb[b] = sum over the rows of b of g[row][D:2D]   (ldg = row stride of g)
+__global__ void dlg_scatter_kernel(const float* __restrict__ g, int ldg, const int* __restrict__ off, int D,
+                                   float* dx_att, float* dd_emb) {
+  const int b = blockIdx.x;
+  const int r0 = off[b], r1 = off[b + 1];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    if (dx_att) dx_att[(size_t)b * D + c] = g[(size_t)(r1 - 1) * ldg + c];
+    if (dd_emb) {
+      float s = 0.f;
+      for (int r = r0; r < r1; ++r) s += g[(size_t)r * ldg + D + c];
+      dd_emb[(size_t)b * D + c] = s;
+    }
+  }
+}
+}  // namespace
+
+AVL_API int avl_dialog_param_count(void) { return DP_COUNT; }
+
+AVL_API long long avl_dialog_workspace_bytes(int B, int K, int D, int with_backward) {
+  DlgBufs s;
+  return (long long)dlg_layout(nullptr, s, (size_t)B, (size_t)B * (K + 1), D, with_backward != 0);
+}
+
+// x_att [B, D]; memory_state [K, n_mem_envs, D]; env_index [B] or NULL; masks [B, K] float; d_emb [B, D] or NULL
+// (no dialog: the fusion MLP is skipped, :138); agent_step [B] int32; pe_table [pe_len, D]; goal [B, D]; out [B, D].
+AVL_API int avl_dialog_forward(int B, int K, int D, const float* x_att, const float* memory_state, int n_mem_envs,
+                               const int* env_index, const float* masks, const float* d_emb, const int* agent_step,
+                               const float* pe_table, int pe_len, const float* goal, const float* const* params,
+                               float* out, void* workspace, int with_backward, void* stream) {
+  if (B < 0 || K < 0 || D != 256 || pe_len < 1) return AVL_ERR_ARG;
+  if (K + 1 > ATT_MAXV) return AVL_ERR_UNSUPPORTED;
+  if (B == 0) return AVL_OK;
+  if (!x_att || !agent_step || !pe_table || !goal || !params || !out || !workspace) return AVL_ERR_ARG;
+  if (K > 0 && (!memory_state || !masks)) return AVL_ERR_ARG;
+  int rc = ensure_attn_attrs();
+  if (rc) return rc;
+  const int rows_cap = B * (K + 1);
+  DlgBufs s;
+  dlg_layout(static_cast<char*>(workspace), s, (size_t)B, (size_t)rows_cap, D, with_backward != 0);
+  Launcher L{(cudaStream_t)stream};
+  cudaMemsetAsync(s.err, 0, sizeof(int), L.s);
+  AVL_LAUNCH(smt_count_kernel, avl_div_up(B, 8), 256, 0, L.s, masks, B, K, 0, s.cnt);
+  L.check();
+  AVL_LAUNCH(smt_scan_kernel, 1, 1024, 0, L.s, s.cnt, B, s.off, s.total, rows_cap, s.err);
+  L.check();
+  AVL_LAUNCH(smt_fill_kernel, avl_div_up(B, 8), 256, 0, L.s, masks, s.off, B, K, 0, rows_cap, s.tok_slot, s.tok_sample);
+  L.check();
+  AVL_LAUNCH(dlg_gather_kernel, avl_div_up(rows_cap, 8), 256, 0, L.s, x_att, memory_state, env_index, d_emb, agent_step,
+             pe_table, pe_len, s.tok_slot, s.tok_sample, s.total, rows_cap, K, n_mem_envs, D, s.XIN, s.PE, s.X0);
+  L.check();
+  if (d_emb) {
+    lin_fwd(L, s.XIN, 2 * D, params[DP_FUS0_W], params[DP_FUS0_B], s.H1, D, rows_cap, D, 2 * D, 1, s.total);
+    // X0 = H1 W2^T + b2 + PE  (positional rows as the epilogue residual)
+    GemmEpilogue ep = make_ep(params[DP_FUS2_B], 0, s.total);
+    ep.residual = s.PE;
+    ep.ldr = D;
+    launch_gemm(L, {s.H1, (long long)D, 1}, true, {params[DP_FUS2_W], (long long)D, 1}, true, s.X0, D, rows_cap, D, D, ep, 1);
+  }
+  tf_forward(L, params, s.tf, s.X0, s.off, s.total, rows_cap, B, D, goal, out);
+  return L.err;
+}
+
+// grads: DP_COUNT table (accumulated, NULL = skip); dx_att [B, D], dd_emb [B, D], dgoal [B, D] overwritten (NULL = skip).
+AVL_API int avl_dialog_backward(int B, int K, int D, int has_dialog, const float* goal, const float* const* params,
+                                float* const* grads, const float* gout, float* dx_att, float* dd_emb, float* dgoal,
+                                void* workspace, void* stream) {
+  if (B < 0 || D != 256) return AVL_ERR_ARG;
+  if (B == 0) return AVL_OK;
+  if (!goal || !params || !gout || !workspace) return AVL_ERR_ARG;
+  const int rows_cap = B * (K + 1);
+  DlgBufs s;
+  dlg_layout(static_cast<char*>(workspace), s, (size_t)B, (size_t)rows_cap, D, true);
+  Launcher L{(cudaStream_t)stream};
+  tf_backward(L, params, grads, s.tf, s.X0, s.off, s.total, rows_cap, B, D, goal, gout);
+  float* gX0 = s.tf.GC;
+  if (has_dialog) {
+    lin_bwd_w(L, gX0, D, s.H1, D, gp(grads, DP_FUS2_W), D, gp(grads, DP_FUS2_B), rows_cap, D, D, s.total);
+    lin_bwd_x(L, gX0, D, params[DP_FUS2_W], D, s.GH1, D, rows_cap, D, D, 0, s.total, s.tf.WT);
+    relu_bwd(L, s.GH1, s.H1, s.total, rows_cap, D);
+    lin_bwd_w(L, s.GH1, D, s.XIN, 2 * D, gp(grads, DP_FUS0_W), 2 * D, gp(grads, DP_FUS0_B), rows_cap, D, 2 * D, s.total);
+    if (dx_att || dd_emb) {
+      lin_bwd_x(L, s.GH1, D, params[DP_FUS0_W], 2 * D, s.GXIN, 2 * D, rows_cap, D, 2 * D, 0, s.total, s.tf.WT);
+      AVL_LAUNCH(dlg_scatter_kernel, B, 256, 0, L.s, s.GXIN, 2 * D, s.off, D, dx_att, dd_emb);
+      L.check();
+    }
+  } else if (dx_att) {
+    AVL_LAUNCH(dlg_scatter_kernel, B, 256, 0, L.s, gX0, D, s.off, D, dx_att, (float*)nullptr);
+    L.check();
+  }
+  if (dgoal) cudaMemcpyAsync(dgoal, s.tf.gB4, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, L.s);
+  return L.err;
+}

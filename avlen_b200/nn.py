@@ -43,7 +43,6 @@ _lib.register({
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
 }, {"avl_gru_workspace_bytes": c_longlong})
 
-_packed_cache = {}
 _gn_scratch = {}
 
 
@@ -63,16 +62,25 @@ def tensor_cores_enabled() -> bool:
 
 def _packed_weight(w, c_pad=None):
     """(Cout, C, KH, KW) -> (Cout, KH, KW, Cp) K-contiguous copy for the tensor-core path (input channels zero-padded
-    to ``c_pad``), cached per weight version."""
-    key = (w.data_ptr(), tuple(w.shape), c_pad)
-    hit = _packed_cache.get(key)
+    to ``c_pad``), cached ON the owning parameter object per weight version (a cache keyed by address would hand a
+    new module, allocated where a freed one lived, the old module's weights)."""
+    owner = w._base if w._base is not None else w
+    cache = getattr(owner, "_avl_packed", None)
+    if cache is None:
+        cache = {}
+        try:
+            owner._avl_packed = cache
+        except AttributeError:
+            pass
+    key = (tuple(w.shape), c_pad, w.data_ptr())
+    hit = cache.get(key)
     if hit is not None and hit[0] == w._version:
         return hit[1]
     pk = w.detach().permute(0, 2, 3, 1)
     if c_pad is not None and c_pad != w.shape[1]:
         pk = torch.nn.functional.pad(pk, (0, c_pad - w.shape[1]))
     pk = pk.contiguous()
-    _packed_cache[key] = (w._version, pk)
+    cache[key] = (w._version, pk)
     return pk
 
 

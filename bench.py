@@ -151,7 +151,10 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (encoder conv as im2col-gather GEMM): layer1 3x3 conv 16->16 @64x64
+    # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM convolution (tc_gemm_kernel<CONV>), timed on its
+    # most expensive shape (custom_resnet18 layer1 conv3x3 16->16 @64x64, update-minibatch batch).  Arithmetic
+    # intensity in fp32 = 2*144*16 / (2*16*4) = 36 FLOP/B < the TF32 ridge (~110 FLOP/B) => HBM-bound: algorithmic
+    # bytes = read x + write y (+ weights), DESIGN.md section 4.
     hbm, tf, how = _peaks()
     B = args.envs * args.rollout_steps // cfg.num_mini_batch
     B = min(B, 4800)
@@ -167,11 +170,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     k_ms = c0.elapsed_time(c1) / 10
     flops = 2.0 * B * 64 * 64 * 16 * 144
-    ach = flops / (k_ms * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_kernel<CONV> (custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d)" % B,
-                "bound": "tensor", "achieved": round(ach, 3), "peak": tf, "unit": "TFLOP/s",
-                "frac": round(ach / tf, 5), "traffic": None, "peak_source": how,
-                "note": "fp32 SIMT im2col GEMM; algorithmic FLOPs = 2*B*64*64*16*(3*3*16)"}
+    nbytes = 2.0 * B * 64 * 64 * 16 * 4 + 16 * 144 * 4
+    ach = nbytes / (k_ms * 1e-3) / 1e9
+    tcl = K.tensor_cores_level()
+    roofline = {"kernel": ("tc_gemm_kernel<CONV> tcgen05 kind::tf32" if tcl >= 1 else "gemm_kernel<CONV> fp32 SIMT")
+                + " (custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d)" % B,
+                "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(ach / hbm, 5), "traffic": None, "peak_source": how,
+                "launch_ms": round(k_ms, 4), "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2),
+                "note": "algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound"}
     cpu = cpu_baseline_sample(1, quick=True) if not args.no_cpu else None
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",

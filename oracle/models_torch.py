@@ -318,6 +318,163 @@ class AudioNavSMTPolicy(nn.Module):
         return value, lp, ent.mean(), h, x
 
 
+# ---- ss_baselines/savi/models/dialog_state_encoder.py:18-160 ------------------------------------------------
+class PositionalEncoding(nn.Module):
+    def __init__(self, d_model, dropout=0.0, max_len=100):
+        super().__init__()
+        import math
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+        pe = torch.zeros(max_len, 1, d_model)
+        pe[:, 0, 0::2] = torch.sin(position * div_term)
+        pe[:, 0, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+    def forward(self, x, y):  # :33-40
+        return x + self.pe[y.long(), 0, :].unsqueeze(0)
+
+
+class DialogStateEncoder(nn.Module):
+    def __init__(self, input_size, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dim_feedforward=256,
+                 dropout=0.0, activation="relu", pretraining=False):
+        super().__init__()
+        self.fusion_encoder = nn.Sequential(nn.Linear(input_size, dim_feedforward), nn.ReLU(),
+                                            nn.Linear(dim_feedforward, dim_feedforward))
+        self.dialog_transformer = nn.Transformer(d_model=dim_feedforward, nhead=nhead,
+                                                 num_encoder_layers=num_encoder_layers,
+                                                 num_decoder_layers=num_decoder_layers,
+                                                 dim_feedforward=dim_feedforward, dropout=dropout, activation=activation)
+        self.pos_encode = PositionalEncoding(dim_feedforward, 0.0, 100)
+
+    def forward(self, x, memory_state, memory_masks, d_emb, agent_step, goal=None):  # :114-155
+        memory_masks = torch.cat([memory_masks, torch.ones([memory_masks.shape[0], 1])], dim=1)
+        memory_state = torch.cat([memory_state, x.unsqueeze(0)])
+        M, bs = memory_state.shape[:2]
+        if d_emb is not None:
+            memory_state = torch.cat([memory_state, d_emb.unsqueeze(0).repeat(M, 1, 1)], dim=-1)
+            memory_state = self.fusion_encoder(memory_state.view(M * bs, -1)).view(M, bs, -1)
+        memory_state = self.pos_encode(memory_state, agent_step)
+        t_masks = (1 - memory_masks) > 0
+        return self.dialog_transformer(memory_state, goal.unsqueeze(0), src_key_padding_mask=t_masks,
+                                       memory_key_padding_mask=t_masks)[-1]
+
+
+# ---- savi/ppo/policy.py:919-1114 AudioNavOptionNet (pi_q) ------------------------------------------------------
+class AudioNavOptionNet(AudioNavSMTNet):
+    def __init__(self, hidden_size=256, use_category_input=False, pretraining=False, action_size=4,
+                 normalize_category_distribution=False, query_count_emb_size=32):
+        super().__init__(hidden_size, use_category_input, pretraining, action_size, normalize_category_distribution)
+        pi = self.smt_state_encoder._pose_indices
+        self._feature_size += query_count_emb_size
+        self.smt_state_encoder = SMTStateEncoder(self._feature_size, dim_feedforward=hidden_size, pose_indices=pi,
+                                                 pretraining=pretraining)
+        self.policy_selector = nn.Linear(hidden_size, 2)
+        self._qcnt_emb = nn.Embedding(2, query_count_emb_size)
+
+    def forward(self, obs, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks, query_state,
+                last_query_info):
+        x = self.get_features(obs, prev_actions)
+        with torch.no_grad():  # :1041-1042 — the encoders receive no gradient from pi_q
+            x_query = torch.cat([x, query_state], 1)
+        belief = torch.zeros((x.shape[0], self._hidden_size))
+        belief[:, :21] = F.softmax(obs["category_belief"], dim=1) if self._normalize else obs["category_belief"]
+        belief[:, 21:23] = obs["location_belief"]
+        x_att = self.smt_state_encoder(x_query, ext_memory, ext_memory_masks, goal=belief)
+        with torch.no_grad():
+            x_for_memory = torch.cat([x, last_query_info], 1)
+        return x_att, rnn_hidden_states, x_for_memory
+
+
+class _PolicyHeads(nn.Module):
+    def _heads(self, hidden_size, dim_actions):
+        self.action_distribution_option = CategoricalNet(hidden_size, 2)
+        self.action_distribution_goal = CategoricalNet(hidden_size, dim_actions)
+        self.action_distribution_vln = CategoricalNet(hidden_size, dim_actions)
+        self.critic_goal = CriticHead(hidden_size)
+        self.critic_option = CriticHead(hidden_size)
+        self.uncertainty_option = CriticHead(hidden_size, 2)
+        self.critic_vln = CriticHead(hidden_size)
+
+
+class AudioNavOptionPolicy(_PolicyHeads):
+    """policy.py:346-356 (dim_actions 2) with act_option / evaluate_actions_option (:98-127, :207-235)."""
+
+    def __init__(self, hidden_size=256, **net_kwargs):
+        super().__init__()
+        self.net = AudioNavOptionNet(hidden_size=hidden_size, **net_kwargs)
+        self._heads(hidden_size, 2)
+
+    def act_option(self, obs, h, prev_actions, masks, em, em_masks, query_state, last_query_info, uniforms=None):
+        from .rl_torch import categorical_act
+        feats, h, x = self.net(obs, h, prev_actions, masks, em, em_masks, query_state, last_query_info)
+        logits = self.action_distribution_option(feats)
+        action, lp, probs = categorical_act(logits, uniforms)
+        return self.critic_option(feats), self.uncertainty_option(feats), action, lp, h, x, probs
+
+    def evaluate_actions_option(self, obs, h, prev_actions, masks, action, em, em_masks, query_state, last_query_info):
+        from .rl_torch import categorical_eval
+        feats, h, x = self.net(obs, h, prev_actions, masks, em, em_masks, query_state, last_query_info)
+        logits = self.action_distribution_option(feats)
+        lp, ent, probs = categorical_eval(logits, action)
+        return self.critic_option(feats), self.uncertainty_option(feats), lp, ent.mean(), h, x, probs
+
+
+# ---- savi/ppo/policy.py:676-917 AudioNavDialogNet (pi_l) -------------------------------------------------------
+class AudioNavDialogNet(AudioNavSMTNet):
+    def __init__(self, hidden_size=256, pretraining=False, action_size=4, clip_layers=12):
+        super().__init__(hidden_size, False, pretraining, action_size, False)
+        from .clip_torch import CLIPText
+        self.clip = CLIPText(layers=clip_layers)
+        self.dialog_layer = nn.Linear(512, hidden_size)
+        self.dialog_state_encoder = DialogStateEncoder(hidden_size + hidden_size, dim_feedforward=hidden_size)
+
+    def forward(self, obs, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog, ext_memory_masks,
+                all_dialog, agent_step):
+        x = self.get_features(obs, prev_actions)
+        belief = torch.zeros((x.shape[0], self._hidden_size))
+        belief[:, :21] = obs["category_belief"]
+        belief[:, 21:23] = obs["location_belief"]
+        x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
+        if all_dialog is not None:
+            with torch.no_grad():
+                dialog_emb = self.clip.encode_text(all_dialog).float()
+            dialog_emb = self.dialog_layer(dialog_emb)
+        else:
+            dialog_emb = None
+        x_att_dialog = self.dialog_state_encoder(x_att, ext_memory_dialog, ext_memory_masks, dialog_emb, agent_step,
+                                                 goal=belief)
+        return x_att_dialog, rnn_hidden_states, x, x_att_dialog
+
+
+class AudioNavDialogPolicy(_PolicyHeads):
+    """policy.py:334-344 with act_dialog / evaluate_actions_dialog (:130-162, :238-276)."""
+
+    def __init__(self, hidden_size=256, dim_actions=4, **net_kwargs):
+        super().__init__()
+        self.net = AudioNavDialogNet(hidden_size=hidden_size, action_size=dim_actions, **net_kwargs)
+        self._heads(hidden_size, dim_actions)
+
+    def act_dialog(self, obs, h, prev_actions, masks, em, em_dialog, em_masks, all_dialog, agent_step, uniforms=None,
+                   without_dialog=False):
+        from .rl_torch import categorical_act
+        if without_dialog:
+            all_dialog = None
+        feats, h, x, xd = self.net(obs, h, prev_actions, masks, em, em_dialog, em_masks, all_dialog, agent_step)
+        logits = self.action_distribution_vln(feats)
+        action, lp, probs = categorical_act(logits, uniforms)
+        return self.critic_vln(feats), action, lp, h, x, xd, probs
+
+    def evaluate_actions_dialog(self, obs, h, prev_actions, masks, action, em, em_dialog, em_masks, all_dialog,
+                                agent_step, without_dialog=False):
+        from .rl_torch import categorical_eval
+        if without_dialog:
+            all_dialog = None
+        feats, h, x, xd = self.net(obs, h, prev_actions, masks, em, em_dialog, em_masks, all_dialog, agent_step)
+        logits = self.action_distribution_vln(feats)
+        lp, ent, _ = categorical_eval(logits, action)
+        return None, lp, ent.mean(), h, x, xd, logits
+
+
 # ---- ss_baselines/av_nav/models/rnn_state_encoder.py:11-149 --------------------------------------------------
 class RNNStateEncoder(nn.Module):
     def __init__(self, input_size, hidden_size):

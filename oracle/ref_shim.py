@@ -60,7 +60,15 @@ def install():
     import numpy as np
 
     _stub("torchsummary", summary=lambda *a, **k: None)
-    _stub("clip", load=lambda *a, **k: (_Anything(), None), tokenize=lambda *a, **k: None)
+    def _clip_load(*a, **k):
+        # openai/CLIP is not installed: the reference's `clip.load("ViT-B/32")` receives the oracle's restatement of
+        # its text tower (oracle/clip_torch.py; `.transformer.width` is what policy.py:762 reads)
+        from . import clip_torch
+        m = clip_torch.CLIPText(layers=int(os.environ.get("AVLEN_SHIM_CLIP_LAYERS", "12")))
+        m.transformer.width = 512
+        return m, None
+
+    _stub("clip", load=_clip_load, tokenize=lambda *a, **k: None)
     try:
         import pynvml  # noqa: F401
         real_pynvml = sys.modules["pynvml"]

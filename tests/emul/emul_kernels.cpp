@@ -14,6 +14,7 @@ extern "C" void avl_count_launch() {}
 #include "../../avlen_b200/csrc/smt.cu"
 #include "../../avlen_b200/csrc/conv.cu"
 #include "../../avlen_b200/csrc/nn_bwd.cu"
+#include "../../avlen_b200/csrc/clip_text.cu"
 
 #define EMUL_API extern "C" __attribute__((visibility("default")))
 
