@@ -2,7 +2,7 @@
 // `clip.load("ViT-B/32")`, `self.clip.encode_text(all_dialog).float()` under no_grad; frozen,
 // ddppo_trainer.py:401-403).  openai/CLIP (unpinned git dependency, README.md:61) model.py `encode_text`:
 //   x = token_embedding[tokens] + positional_embedding                                  (B, 77, 512)
-//   12 x { x += out_proj(causal MHA_8x64(ln_1(x))) ; x += c_proj(QuickGELU(c_fc(ln_2(x)))) }
+//   layers (12) x { x += out_proj(causal MHA_8x64(ln_1(x))) ; x += c_proj(QuickGELU(c_fc(ln_2(x)))) }
 //   x = ln_final(x)[b, argmax(tokens[b])] @ text_projection                             (B, 512)
 //
 // B200-first restructuring (identical results): the dialog tensor is all-zero for every env that has no active
@@ -15,12 +15,12 @@
 
 namespace {
 
-constexpr int CL_W = 512, CL_HEADS = 8, CL_HD = 64, CL_FF = 2048, CL_LAYERS = 12, CL_MAXL = 128;
+constexpr int CL_W = 512, CL_HEADS = 8, CL_HD = 64, CL_FF = 2048, CL_MAXL = 128, CL_MAX_LAYERS = 48;
 enum { CP_TOK = 0, CP_POS, CP_LAYER0 };
 enum { CL_LN1_W = 0, CL_LN1_B, CL_IN_W, CL_IN_B, CL_OUT_W, CL_OUT_B, CL_LN2_W, CL_LN2_B, CL_FC_W, CL_FC_B, CL_PROJ_W,
        CL_PROJ_B, CL_PER_LAYER };
-constexpr int CP_LNF_W = CP_LAYER0 + CL_LAYERS * CL_PER_LAYER, CP_LNF_B = CP_LNF_W + 1, CP_TEXT_PROJ = CP_LNF_B + 1,
-              CP_COUNT = CP_TEXT_PROJ + 1;
+// after the per-layer entries: ln_final.weight, ln_final.bias, text_projection
+static inline int cp_lnf_w(int layers) { return CP_LAYER0 + layers * CL_PER_LAYER; }
 
 // slot[b] = packed index of sample b (non-zero rows first, in order); all-zero rows share slot n_active.
 // counts[0] = n_active + (any zero row ? 1 : 0) distinct sequences, counts[1] = that * L rows, eot[slot] = argmax.
@@ -246,7 +246,7 @@ static size_t clip_layout(char* base, ClipBufs& b, size_t B, size_t L) {
 
 }  // namespace
 
-AVL_API int avl_clip_text_param_count(void) { return CP_COUNT; }
+AVL_API int avl_clip_text_param_count(int layers) { return cp_lnf_w(layers) + 3; }
 
 AVL_API long long avl_clip_text_workspace_bytes(int B, int L) {
   ClipBufs b;
@@ -254,12 +254,12 @@ AVL_API long long avl_clip_text_workspace_bytes(int B, int L) {
 }
 
 // tokens (B, L) int64 (clip.tokenize layout: SOT, ids, EOT = largest id, zero padding; L <= 77 positions);
-// params: CP_COUNT device pointers in the order of avlen_b200/savi/models/clip_text.py::CLIP_PARAM_KEYS;
+// params: avl_clip_text_param_count(layers) device pointers in the order of avlen_b200/savi/models/clip_text.py::CLIP_PARAM_KEYS;
 // out (B, 512) fp32.  dedupe != 0: all-zero rows are encoded once (see header).  counts_out (optional, device,
 // 2 ints): distinct sequences / rows actually processed.
-AVL_API int avl_clip_text_forward(int B, int L, int vocab, const long long* tokens, const float* const* params,
-                                  float* out, void* workspace, int dedupe, void* stream) {
-  if (B < 0 || L < 1 || L > CL_MAXL || vocab < 1) return AVL_ERR_ARG;
+AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const long long* tokens,
+                                  const float* const* params, float* out, void* workspace, int dedupe, void* stream) {
+  if (B < 0 || L < 1 || L > CL_MAXL || vocab < 1 || layers < 1 || layers > CL_MAX_LAYERS) return AVL_ERR_ARG;
   if (B == 0) return AVL_OK;
   if (!tokens || !params || !out || !workspace) return AVL_ERR_ARG;
   ClipBufs b;
@@ -283,7 +283,7 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, const long long* toke
   int ew = avl_div_up((long long)R * CL_FF, 1024);
   int cap = avl_num_sms() * 16;
   if (ew > cap) ew = cap;
-  for (int l = 0; l < CL_LAYERS; ++l) {
+  for (int l = 0; l < layers; ++l) {
     const float* const* P = params + CP_LAYER0 + l * CL_PER_LAYER;
     clip_ln(c, b.X, P[CL_LN1_W], P[CL_LN1_B], b.XN, n_rows, R);
     clip_lin(c, b.XN, P[CL_IN_W], P[CL_IN_B], nullptr, b.QKV, R, 3 * CL_W, CL_W, n_rows);
@@ -298,7 +298,7 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, const long long* toke
   }
   AVL_LAUNCH(clip_take_eot_kernel, S, 128, 0, c.s, b.X, b.eot, n_seq, L, b.XE);
   c.check();
-  clip_ln(c, b.XE, params[CP_LNF_W], params[CP_LNF_B], b.XN, n_seq, S);
+  clip_ln(c, b.XE, params[cp_lnf_w(layers)], params[cp_lnf_w(layers) + 1], b.XN, n_seq, S);
   {  // EMB[s, n] = sum_k XN[s, k] * text_projection[k, n]
     GemmEpilogue ep;
     ep.bias = nullptr; ep.scale = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.relu = 0; ep.accumulate = 0;
@@ -306,7 +306,7 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, const long long* toke
     ConvGeom g = {};
     dim3 grid(avl_div_up(S, GBM), avl_div_up(CL_W, GBN), 1);
     auto kern = gemm_kernel<false, true, false>;
-    GemmOperand A = {b.XN, (long long)CL_W, 1}, Bo = {params[CP_TEXT_PROJ], 1, (long long)CL_W};
+    GemmOperand A = {b.XN, (long long)CL_W, 1}, Bo = {params[cp_lnf_w(layers) + 2], 1, (long long)CL_W};
     AVL_LAUNCH(kern, grid, GTHREADS, 0, c.s, A, Bo, b.EMB, (long long)CL_W, S, CL_W, CL_W, g, ep, CL_W);
     c.check();
   }

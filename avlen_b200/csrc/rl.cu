@@ -434,6 +434,61 @@ __global__ void adam_kernel(float* p, const float* __restrict__ g, float* m, flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row R: the imitation loss of PPO.update_dialog (ss_baselines/savi/ppo/ppo.py:134-142):
+//   rows = nonzero(o_masks);  loss = CrossEntropyLoss(weight = w)(logits[rows], o_actions[rows])
+//        = sum_i w[y_i] * (logsumexp(l_i) - l_i[y_i]) / sum_i w[y_i]
+// One CTA, two passes over B = NUM_DIALOG_STEPS * N rows: the row selection never leaves the device (the reference's
+// `nonzero` is a host synchronisation) and the gradient dlogits = mask * w[y] * (softmax - onehot) / sum w is written
+// in the same launch.  out[0] = loss, out[1] = sum of weights, out[2] = number of selected rows.  No selected row or
+// zero weight sum gives NaN like the reference (0/0).
+__global__ void masked_weighted_ce_kernel(const float* __restrict__ logits, const float* __restrict__ targets,
+                                          const long long* __restrict__ mask, const float* __restrict__ weight, int B,
+                                          int A, float* dlogits, float* out) {
+  __shared__ float red[33];
+  float ls = 0.f, ws = 0.f, cnt = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (mask[b] == 0) continue;
+    const float* l = logits + (size_t)b * A;
+    int y = (int)targets[b];
+    y = y < 0 ? 0 : (y >= A ? A - 1 : y);
+    float mx = l[0];
+    for (int a = 1; a < A; ++a) mx = fmaxf(mx, l[a]);
+    float se = 0.f;
+    for (int a = 0; a < A; ++a) se += expf(l[a] - mx);
+    const float w = weight ? weight[y] : 1.f;
+    ls += w * (logf(se) + mx - l[y]);
+    ws += w;
+    cnt += 1.f;
+  }
+  ls = block_sum(ls, red);
+  ws = block_sum(ws, red);
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) {
+    out[0] = ls / ws;
+    out[1] = ws;
+    out[2] = cnt;
+  }
+  if (!dlogits) return;
+  const float inv = 1.f / ws;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float* d = dlogits + (size_t)b * A;
+    if (mask[b] == 0) {
+      for (int a = 0; a < A; ++a) d[a] = 0.f;
+      continue;
+    }
+    const float* l = logits + (size_t)b * A;
+    int y = (int)targets[b];
+    y = y < 0 ? 0 : (y >= A ? A - 1 : y);
+    float mx = l[0];
+    for (int a = 1; a < A; ++a) mx = fmaxf(mx, l[a]);
+    float se = 0.f;
+    for (int a = 0; a < A; ++a) se += expf(l[a] - mx);
+    const float w = (weight ? weight[y] : 1.f) * inv;
+    for (int a = 0; a < A; ++a) d[a] = w * (expf(l[a] - mx) / se - (a == y ? 1.f : 0.f));
+  }
+}
+
 }  // namespace
 
 #ifndef AVL_HOST_EMUL
@@ -537,6 +592,18 @@ AVL_API int avl_ppo_loss_fwd_bwd(int B, int A, const float* logits, const long l
     AVL_LAUNCH_CHECK();
   }
   ppo_loss_kernel<<<avl_div_up(B, 256), 256, 0, s>>>(p);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+// logits (B, A); targets (B) float (o_actions storage dtype); mask (B) int64 (o_masks); weight (A) or NULL;
+// dlogits (B, A) or NULL; out3 (3 floats, device).
+AVL_API int avl_masked_weighted_ce(const float* logits, const float* targets, const long long* mask,
+                                   const float* weight, int B, int A, float* dlogits, float* out3, void* stream) {
+  if (B < 1 || A < 1) return AVL_ERR_ARG;
+  if (!logits || !targets || !mask || !out3) return AVL_ERR_ARG;
+  AVL_LAUNCH(masked_weighted_ce_kernel, 1, 1024, 0, (cudaStream_t)stream, logits, targets, mask, weight, B, A, dlogits,
+             out3);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -101,6 +101,31 @@ class PpoLoss:
         return out, dl, dv, du
 
 
+class _MaskedWeightedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, mask, weight):
+        B, A = logits.shape
+        logits = logits.contiguous()
+        d = torch.empty_like(logits)
+        out = torch.empty(3, device=logits.device, dtype=torch.float32)
+        call("avl_masked_weighted_ce", fptr(logits), fptr(targets.reshape(B).float().contiguous()),
+             dptr(mask.reshape(B).contiguous(), i64), fptr(weight), B, A, fptr(d), fptr(out), stream())
+        ctx.save_for_backward(d)
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g, _g_out):
+        (d,) = ctx.saved_tensors
+        return d * g, None, None, None
+
+
+def masked_weighted_ce(logits, targets, mask, weight=None):
+    """CrossEntropyLoss(weight)(logits[mask != 0], targets[mask != 0]) without leaving the device
+    (savi/ppo/ppo.py:134-142).  Returns (loss, stats) with stats = [loss, sum of weights, selected rows]."""
+    return _MaskedWeightedCE.apply(logits, targets, mask, weight)
+
+
 def extmem_insert(memory, masks, feats, not_done, snapshot, capacity, idx):
     """ExternalMemory.insert on the single-copy layout (total, N, dim) (rollout_storage.py:930-941)."""
     total, n, dim = memory.shape

@@ -18,10 +18,10 @@ import torch.nn as nn
 from ... import _lib
 
 _lib.register({
-    "avl_clip_text_param_count": [],
+    "avl_clip_text_param_count": [ctypes.c_int],
     "avl_clip_text_workspace_bytes": [ctypes.c_int, ctypes.c_int],
-    "avl_clip_text_forward": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p],
+    "avl_clip_text_forward": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p],
     "avl_clip_text_status": [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                              ctypes.POINTER(ctypes.c_int)],
 }, {"avl_clip_text_workspace_bytes": ctypes.c_longlong})
@@ -60,10 +60,11 @@ class _Transformer(nn.Module):
 
 
 class CLIPTextTower(nn.Module):
-    def __init__(self, dedupe_zero_rows=True, chunk=512):
+    def __init__(self, dedupe_zero_rows=True, chunk=512, layers=LAYERS):
         super().__init__()
-        self.context_length, self.vocab_size = CONTEXT, VOCAB
-        self.transformer = _Transformer(WIDTH, LAYERS, HEADS)
+        self.context_length, self.vocab_size, self.layers = CONTEXT, VOCAB, layers
+        self._keys = clip_param_keys(layers)
+        self.transformer = _Transformer(WIDTH, layers, HEADS)
         self.token_embedding = nn.Embedding(VOCAB, WIDTH)
         self.positional_embedding = nn.Parameter(torch.empty(CONTEXT, WIDTH))
         self.ln_final = nn.LayerNorm(WIDTH)
@@ -78,7 +79,7 @@ class CLIPTextTower(nn.Module):
     def initialize_parameters(self):  # openai/CLIP model.py initialize_parameters (text part)
         nn.init.normal_(self.token_embedding.weight, std=0.02)
         nn.init.normal_(self.positional_embedding, std=0.01)
-        proj_std = (WIDTH ** -0.5) * ((2 * LAYERS) ** -0.5)
+        proj_std = (WIDTH ** -0.5) * ((2 * self.layers) ** -0.5)
         attn_std, fc_std = WIDTH ** -0.5, (2 * WIDTH) ** -0.5
         for block in self.transformer.resblocks:
             nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
@@ -89,7 +90,7 @@ class CLIPTextTower(nn.Module):
 
     def _table(self):
         sd = dict(self.named_parameters())
-        ts = [sd[k] for k in CLIP_PARAM_KEYS]
+        ts = [sd[k] for k in self._keys]
         key = tuple(t.data_ptr() for t in ts)
         if key != self._ptr_key:
             for t in ts:
@@ -111,7 +112,7 @@ class CLIPTextTower(nn.Module):
             nbytes = int(_lib.lib().avl_clip_text_workspace_bytes(n, L))
             if self._ws is None or self._ws.numel() < nbytes:
                 self._ws = torch.empty(nbytes, dtype=torch.uint8, device=text.device)
-            _lib.call("avl_clip_text_forward", n, L, self.vocab_size, text[b0:b0 + n].data_ptr(), tab,
+            _lib.call("avl_clip_text_forward", n, L, self.vocab_size, self.layers, text[b0:b0 + n].data_ptr(), tab,
                       out[b0:b0 + n].data_ptr(), self._ws.data_ptr(), int(self.dedupe_zero_rows), _lib.stream())
             self._last = (n, L)
         return out

@@ -225,6 +225,37 @@ class RolloutStorage:
                 take(self.all_dialog), take(self.query_state), take(self.last_query_info), take(self.agent_step),
             )
 
+    def dialog_batching(self):
+        """Same 17-tuple as rollout_storage.py:414-588 (all envs in order, row = t * N + env).  Every entry is a VIEW
+        of the storage (``[:T]`` of a time-major tensor flattens without a copy) and the memories are
+        ``IndexedMemory`` handles, where the reference stacks copies of every buffer."""
+        T, N = self.step, self.num_envs
+        dev = self.rewards.device
+
+        def flat(t):
+            x = t[:T]
+            return x.reshape(T * N, *x.shape[2:])
+
+        row_env = torch.arange(N, device=dev, dtype=torch.int32).repeat(T)
+
+        def mem(em):
+            return IndexedMemory(em.memory, row_env) if em is not None else None
+
+        ext = self.use_external_memory
+        return (
+            {s: flat(v) for s, v in self.observations.items()},
+            self.recurrent_hidden_states[0],
+            flat(self.actions), flat(self.prev_actions), flat(self.value_preds), flat(self.returns), flat(self.masks),
+            flat(self.action_log_probs),
+            mem(self.em) if ext else None,
+            mem(self.em_vln) if ext else None,
+            mem(self.em_vln_dialog) if self.use_state_memory else None,
+            flat(self.em_masks) if ext else None,
+            flat(self.em_vln_masks) if (ext or self.use_state_memory) else None,
+            flat(self.all_dialog), flat(self.agent_step),
+            self.num_steps, self.num_envs,
+        )
+
     @property
     def external_memory_goal(self):
         return _CopiesView(self.em.memory)

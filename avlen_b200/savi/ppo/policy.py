@@ -16,6 +16,8 @@ from ... import _lib
 from ... import nn as K
 from ...common.utils import CategoricalNet, cuda_linear
 from ..models.audio_cnn import AudioCNN
+from ..models.clip_text import CLIPTextTower
+from ..models.dialog_state_encoder import DialogStateEncoder
 from ..models.smt_cnn import SMTCNN
 from ..models.smt_state_encoder import IndexedMemory, SMTStateEncoder
 
@@ -86,6 +88,21 @@ class Policy(nn.Module):
         action_log_probs = distribution.log_probs(action)
         return value, unct, action, action_log_probs, rnn_hidden_states, ext_memory_feats, distribution.probs
 
+    def act_dialog(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog,
+                   ext_memory_masks, all_dialog, agent_step, deterministic=False, without_dialog=False, uniforms=None):
+        """policy.py:130-162 (pi_l)."""
+        if without_dialog:
+            all_dialog = None
+        features, rnn_hidden_states, ext_memory_feats, ext_memory_dialog_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog, ext_memory_masks,
+            all_dialog, agent_step)
+        distribution, _ = self.action_distribution_vln(features)
+        value = self.critic_vln(features)
+        action = distribution.mode() if deterministic else distribution.sample(uniforms=uniforms)
+        action_log_probs = distribution.log_probs(action)
+        return (value, action, action_log_probs, rnn_hidden_states, ext_memory_feats, ext_memory_dialog_feats,
+                distribution.probs)
+
     def get_value(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks):
         features, _, _ = self.net(observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks)
         return self.critic_goal(features)
@@ -118,6 +135,20 @@ class Policy(nn.Module):
         distribution_entropy = distribution.entropy().mean()
         return (value, unct, action_log_probs, distribution_entropy, rnn_hidden_states, ext_memory_feats,
                 distribution.probs)
+
+    def evaluate_actions_dialog(self, observations, rnn_hidden_states, prev_actions, masks, action, ext_memory,
+                                ext_memory_dialog, ext_memory_masks, all_dialog, agent_step, without_dialog=False):
+        """policy.py:238-276: value is None; the raw logits are returned for the imitation loss (ppo.py:123-132)."""
+        if without_dialog:
+            all_dialog = None
+        features, rnn_hidden_states, ext_memory_feats, ext_memory_dialog_feats = self.net(
+            observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog, ext_memory_masks,
+            all_dialog, agent_step)
+        distribution, logit = self.action_distribution_vln(features)
+        action_log_probs = distribution.log_probs(action)
+        distribution_entropy = distribution.entropy().mean()
+        return (None, action_log_probs, distribution_entropy, rnn_hidden_states, ext_memory_feats,
+                ext_memory_dialog_feats, logit)
 
     # ---- fused path used by PPO.update: features -> raw head outputs, no distribution objects -------------
     def evaluate_heads(self, which, observations, rnn_hidden_states, prev_actions, masks, ext_memory,
@@ -197,6 +228,7 @@ class AudioNavSMTNet(Net):
         self._build_extra()
         self.smt_state_encoder = SMTStateEncoder(nfeats, dim_feedforward=hidden_size, pose_indices=pose_indices,
                                                  **kwargs)
+        self._post_init(kwargs)
         self.state_size = self.smt_state_encoder.hidden_state_size
         if use_pretrained:
             assert pretrained_path != ""
@@ -207,6 +239,9 @@ class AudioNavSMTNet(Net):
         return 0
 
     def _build_extra(self):
+        pass
+
+    def _post_init(self, kwargs):
         pass
 
     @property
@@ -312,7 +347,7 @@ class AudioNavOptionNet(AudioNavSMTNet):
     def _extra_feature_dims(self):
         return self._query_count_emb_size
 
-    def _build_extra(self):
+    def _post_init(self, kwargs):
         self.policy_selector = nn.Linear(self._hidden_size, 2)
         self._qcnt_emb = nn.Embedding(2, self._query_count_emb_size)
 
@@ -338,9 +373,52 @@ class AudioNavOptionNet(AudioNavSMTNet):
         return x_att, rnn_hidden_states, x_for_memory
 
 
+class AudioNavDialogNet(AudioNavSMTNet):
+    """policy.py:676-917 (pi_l): the SMT net followed by the CLIP-embedded dialog branch.  ``clip.*`` holds the text
+    tower only (frozen, ddppo_trainer.py:401-403); ``dialog_layer`` maps its 512-d embedding to the hidden size and
+    ``dialog_state_encoder`` attends over the K-step state memory."""
+
+    def __init__(self, observation_space, action_space, hidden_size=128, num_steps=5, clip_layers=12, **kwargs):
+        kwargs.pop("use_category_input", None)  # never appended by pi_l's get_features (policy.py:902-917)
+        self._clip_layers = clip_layers
+        self._num_steps = num_steps
+        super().__init__(observation_space, action_space, hidden_size=hidden_size, **kwargs)
+
+    def _post_init(self, kwargs):
+        self.clip = CLIPTextTower(layers=self._clip_layers)
+        self.dialog_layer = nn.Linear(512, self._hidden_size)
+        self.dialog_state_encoder = DialogStateEncoder(self._hidden_size + self._hidden_size,
+                                                       dim_feedforward=self._hidden_size, **kwargs)
+
+    def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog,
+                ext_memory_masks, all_dialog, agent_step):
+        x = self.get_features(observations, prev_actions)
+        belief = self._belief(observations, x.shape[0], x.device)
+        x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
+        if all_dialog is not None:
+            dialog_emb = self.clip.encode_text(all_dialog)  # no_grad, fp32 (policy.py:847-849)
+            dialog_emb = cuda_linear(dialog_emb, self.dialog_layer.weight, self.dialog_layer.bias)
+        else:
+            dialog_emb = None
+        # policy.py:862 hands the SAME mask to the scene memory and to the dialog memory; the dialog memory may be
+        # shorter than the mask (K slots): its slots are the first K mask columns
+        Kd = (ext_memory_dialog.memory if isinstance(ext_memory_dialog, IndexedMemory) else ext_memory_dialog).shape[0]
+        dmask = ext_memory_masks if ext_memory_masks.shape[1] == Kd else ext_memory_masks[:, :Kd]
+        x_att_dialog = self.dialog_state_encoder(x_att, ext_memory_dialog, dmask, dialog_emb, agent_step, goal=belief)
+        return x_att_dialog, rnn_hidden_states, x, x_att_dialog
+
+
 class AudioNavSMTPolicy(Policy):
     def __init__(self, observation_space, action_space, hidden_size=128, **kwargs):
         super().__init__(AudioNavSMTNet(observation_space, action_space, hidden_size=hidden_size, **kwargs),
+                         action_space.n)
+
+
+class AudioNavDialogPolicy(Policy):
+    """policy.py:334-344 (pi_l)."""
+
+    def __init__(self, observation_space, action_space, hidden_size=128, **kwargs):
+        super().__init__(AudioNavDialogNet(observation_space, action_space, hidden_size=hidden_size, **kwargs),
                          action_space.n)
 
 

@@ -47,6 +47,9 @@ class PPO(nn.Module):
         self.device = next(actor_critic.parameters()).device
         self._params, self._flat_p, self._flat_g = flatten_parameters(actor_critic)
         self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps)
+        # dialog pretraining (ppo.py:63, :70-76): its own Adam moments, lr 1e-5, class weights 'balanced'
+        self.dialog_optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=0.00001, eps=eps)
+        self.dialog_class_weight = torch.tensor([0, .33, .33, .33], device=self.device)
         self._loss = ops.PpoLoss(self.device)
         self.world_size = 1
 
@@ -104,6 +107,26 @@ class PPO(nn.Module):
         value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]
         # the reference returns the *sums* of the two debug means (ppo.py:279-280, :289)
         return value_loss, action_loss, entropy, s[5] * n_updates, s[6] * n_updates, unct_loss
+
+    def update_dialog(self, rollouts):
+        """ppo.py:99-154: one full-batch ``evaluate_actions_dialog`` over the NUM_DIALOG_STEPS x N rows, weighted
+        cross-entropy against the oracle actions on the rows with ``o_masks != 0`` (selected on the device), Adam
+        (lr 1e-5, no gradient clipping).  Returns the loss as a device scalar (the reference returns a tensor)."""
+        (obs_batch, hidden_batch, actions_batch, prev_actions_batch, _, _, masks_batch, _, _, external_memory,
+         external_memory_dialog, _em_masks, external_memory_vln_masks, all_dialog_batch, agent_step_batch, _num_steps,
+         _num_envs) = rollouts.dialog_batching()
+        self._flat_g.zero_()
+        (_, _, _, _, _, _, logits) = self.actor_critic.evaluate_actions_dialog(
+            obs_batch, hidden_batch, prev_actions_batch, masks_batch, actions_batch, external_memory,
+            external_memory_dialog, external_memory_vln_masks, all_dialog_batch, agent_step_batch.detach())
+        T = rollouts.step
+        dialog_loss, _stats = ops.masked_weighted_ce(logits, rollouts.o_actions[:T].reshape(-1),
+                                                     rollouts.o_masks[:T].reshape(-1), self.dialog_class_weight)
+        self.before_backward(dialog_loss)
+        dialog_loss.backward()
+        scale = self._reduce_gradients()
+        self.dialog_optimizer.step(None, grad_scale=scale)
+        return dialog_loss.detach()
 
     def before_backward(self, loss):
         pass

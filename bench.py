@@ -83,6 +83,8 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if args.tc_level is not None:
+        K.set_tensor_cores(args.tc_level)
     cfg = savi_config(NUM_PROCESSES=args.envs, num_steps=args.rollout_steps)
     tr = DDPPOTrainer(cfg).setup()
     dev = tr.device
@@ -292,6 +294,7 @@ def main():
     ap.add_argument("--rollout-steps", type=int, default=150)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tc-level", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 encoders (default), 2 + SMT")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

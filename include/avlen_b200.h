@@ -162,6 +162,67 @@ int avl_smt_backward(int B, int M, int F, int D, int pose_index, int rows_cap, c
 int avl_smt_status(int B, int rows_cap, int F, int D, void* workspace, int* total_rows /* host */,
                    int* overflow /* host */);   /* synchronises */
 
+/* ------------------------------------------------------------ rows C, D, E backward (encoders are trained in
+ * savi_pretraining.yaml / av_nav; the reference gets these from autograd over nn.Conv2d / nn.GroupNorm).
+ * dgrad: dx (N,H,W,C) (+)= ; wgrad: dw (Cout,C,KH,KW) += , dbias (Cout) += (either may be NULL).                 */
+int avl_conv2d_dgrad(const float* dy, const float* w_oihw, float* dx, int N, int H, int W, int C, int Cout, int KH,
+                     int KW, int stride, int pad, int accumulate, void* stream);
+int avl_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, int N, int H, int W, int C, int Cout,
+                     int KH, int KW, int stride, int pad, void* stream);
+int avl_relu_mask(float* dy, long long ldd, const float* y, long long ldy, long long rows, int cols, void* stream);
+int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const float* gamma, float* dx, float* dres,
+                      float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
+                      void* stream);
+int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
+
+/* ----------------------------------------------------------------------------- row H: GRU state encoder
+ * ss_baselines/av_nav/models/rnn_state_encoder.py:80-149 (single_forward T=1 / seq_forward) around
+ * nn.GRU(I -> H, 1 layer).  x (T*N, I) time-major; masks (T*N) float, 0 at episode starts (h_{t-1} * mask_t);
+ * weights in nn.GRU layout (gate order r, z, n).  Parameter gradients are accumulated.                          */
+long long avl_gru_workspace_bytes(int T, int N, int I, int H, int with_backward);
+int avl_gru_forward(int T, int N, int I, int H, const float* x, const float* h0, const float* masks,
+                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* out,
+                    float* h_last, void* workspace, int with_backward, void* stream);
+int avl_gru_backward(int T, int N, int I, int H, const float* x, const float* masks, const float* w_ih,
+                     const float* w_hh, const float* dout, const float* dh_last, float* dx, float* dh0, float* dw_ih,
+                     float* dw_hh, float* db_ih, float* db_hh, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------- row R: PPO.update_dialog imitation loss
+ * ss_baselines/savi/ppo/ppo.py:134-142: rows = nonzero(o_masks); CrossEntropyLoss(weight)(logits[rows],
+ * o_actions[rows]) forward + gradient in one launch, no host-side row selection.  out3 = {loss, sum w, #rows}.   */
+int avl_masked_weighted_ce(const float* logits, const float* targets, const long long* mask, const float* weight,
+                           int B, int A, float* dlogits, float* out3, void* stream);
+
+/* ------------------------------------------------------------------ row K: dialog state encoder (pi_l)
+ * ss_baselines/savi/models/dialog_state_encoder.py:114-155 (+ PositionalEncoding :18-40): tokens = valid slots of
+ * the K-slot state memory + the current SMT output; with a dialog each token is fused with the dialog embedding
+ * (512 -> 256 ReLU -> 256); + pe[agent_step]; nn.Transformer(1+1) decoded with the belief vector.
+ * params / grads: avl_dialog_param_count() device pointers (order: avlen_b200/savi/models/
+ * dialog_state_encoder.py::DIALOG_PARAM_KEYS).  d_emb NULL = no dialog (fusion skipped, :138).                   */
+int avl_dialog_param_count(void);
+long long avl_dialog_workspace_bytes(int B, int K, int D, int with_backward);
+int avl_dialog_forward(int B, int K, int D, const float* x_att, const float* memory_state, int n_mem_envs,
+                       const int* env_index, const float* masks, const float* d_emb, const int* agent_step,
+                       const float* pe_table, int pe_len, const float* goal,
+                       const float* const* params /* host array */, float* out, void* workspace, int with_backward,
+                       void* stream);
+int avl_dialog_backward(int B, int K, int D, int has_dialog, const float* goal,
+                        const float* const* params /* host array */, float* const* grads /* host array */,
+                        const float* gout, float* dx_att, float* dd_emb, float* dgoal, void* workspace,
+                        void* stream);
+
+/* --------------------------------------------------------------------------- row L: CLIP text tower (pi_l)
+ * ss_baselines/savi/ppo/policy.py:761-762 (clip.load("ViT-B/32")), :844-851 (encode_text(all_dialog).float(),
+ * no_grad, frozen).  tokens (B, L<=77) int64 in clip.tokenize layout; out (B, 512) fp32.  dedupe != 0: all-zero
+ * rows (envs without an active query) are encoded once.  params: avl_clip_text_param_count(layers) pointers in
+ * the order of avlen_b200/savi/models/clip_text.py::clip_param_keys.                                            */
+int avl_clip_text_param_count(int layers);
+long long avl_clip_text_workspace_bytes(int B, int L);
+int avl_clip_text_forward(int B, int L, int vocab, int layers, const long long* tokens,
+                          const float* const* params /* host array */, float* out, void* workspace, int dedupe,
+                          void* stream);
+int avl_clip_text_status(int B, int L, void* workspace, int* n_sequences /* host */, int* n_rows /* host */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -547,7 +547,7 @@ def seeded_state_dict(module: nn.Module, seed: int, scale: float = 1.0):
     sd = {}
     for k, v in module.state_dict().items():
         shape = tuple(v.shape)
-        if v.dtype not in (torch.float32, torch.float64):
+        if v.dtype not in (torch.float32, torch.float64) or k.endswith(".pe"):  # integer buffers, sinusoid table
             sd[k] = v.clone()
             continue
         if len(shape) >= 2:
@@ -557,5 +557,5 @@ def seeded_state_dict(module: nn.Module, seed: int, scale: float = 1.0):
             w = 1.0 + 0.1 * rng.standard_normal(shape)
         else:
             w = 0.05 * rng.standard_normal(shape)
-        sd[k] = torch.from_numpy(w.astype(np.float32))
+        sd[k] = torch.from_numpy(np.asarray(w, dtype=np.float32))
     return sd

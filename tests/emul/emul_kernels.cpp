@@ -130,3 +130,10 @@ EMUL_API int emul_clip_adam(float* param, const float* grad, float* m, float* v,
   });
   return 0;
 }
+
+EMUL_API int emul_masked_weighted_ce(const float* logits, const float* targets, const long long* mask,
+                                     const float* weight, int B, int A, float* dlogits, float* out3) {
+  emul::launch(dim3(1), dim3(1024),
+               [&] { masked_weighted_ce_kernel(logits, targets, mask, weight, B, A, dlogits, out3); });
+  return 0;
+}

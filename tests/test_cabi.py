@@ -20,6 +20,11 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 45
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/avlen_b200.h but not exported"
+    # ... and nothing is exported that the header does not declare (the header IS the boundary)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = sorted(ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("avl_"))
+    assert exported and not [e for e in exported if e not in names], [e for e in exported if e not in names]
     assert lib.avl_version() == 100
     lib.avl_smt_workspace_bytes.restype = ctypes.c_longlong
     assert lib.avl_smt_workspace_bytes(4, 4 * 301, 276, 256, 1, 0) > 0  # host-only size query

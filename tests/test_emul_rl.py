@@ -199,3 +199,29 @@ def test_clip_adam(emul_lib):
                                 1e-5, step, 0.2, 1.0, nsq.ctypes.data)
         assert np.sqrt(nsq[0]) == pytest.approx(ref_norm[step - 1], rel=1e-5)
         assert np.abs(p - _np(ref_p[step - 1])).max() < 1e-6
+
+
+def test_masked_weighted_ce_matches_torch(emul_lib):
+    """Row R (ppo.py:134-142): nonzero(o_masks) row selection + CrossEntropyLoss(weight) forward and gradient."""
+    import ctypes
+    import torch
+    g = torch.Generator().manual_seed(3)
+    B, A = 37, 4
+    logits = torch.randn(B, A, generator=g, requires_grad=True)
+    targets = torch.randint(0, A, (B,), generator=g).float()
+    mask = (torch.rand(B, generator=g) > 0.5).long()
+    mask[0] = 1
+    targets[0] = 2
+    w = torch.tensor([0, .33, .33, .33])
+    rows = torch.nonzero(mask).squeeze(-1)
+    ref = torch.nn.CrossEntropyLoss(weight=w)(logits[rows], targets[rows].long())
+    ref.backward()
+    ln, tn, mn, wn = logits.detach().numpy().copy(), targets.numpy().copy(), mask.numpy().copy(), w.numpy().copy()
+    d = np.zeros((B, A), np.float32)
+    out = np.zeros(3, np.float32)
+    vp = ctypes.c_void_p
+    emul_lib.emul_masked_weighted_ce.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    assert emul_lib.emul_masked_weighted_ce(ln.ctypes.data, tn.ctypes.data, mn.ctypes.data, wn.ctypes.data, B, A,
+                                            d.ctypes.data, out.ctypes.data) == 0
+    assert abs(out[0] - float(ref)) < 1e-5 and int(out[2]) == int(mask.sum())
+    assert np.abs(d - logits.grad.numpy()).max() < 1e-6

@@ -100,3 +100,89 @@ def test_av_nav_policy_keys_and_encoders():
     f_r, h_r = ref.net(obs, h, None, mk)
     f_m, h_m = mine._features(obs, h, mk)
     assert torch.allclose(f_r, f_m, atol=1e-5) and torch.allclose(h_r, h_m, atol=1e-5)
+
+
+def _mem(M, n, dim, g, pose_at):
+    em = torch.randn(M, n, dim, generator=g)
+    em[..., pose_at:pose_at + 4] = torch.cat([torch.randn(M, n, 2, generator=g) * 5, torch.rand(M, n, 1, generator=g) * 6 - 3,
+                                              torch.randint(0, 50, (M, n, 1), generator=g).float()], -1)
+    return em
+
+
+def test_option_policy_matches_reference():
+    """pi_q (policy.py:346-356, :919-1114): act_option / evaluate_actions_option of the unmodified reference."""
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavOptionPolicy(ref_shim.observation_space(), sp.Discrete(4), hidden_size=256, nhead=8,
+                                   num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
+                                   pretraining=False)
+    mine = OM.AudioNavOptionPolicy()
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    sd = OM.seeded_state_dict(mine, 6)
+    ref.load_state_dict(sd); mine.load_state_dict(sd)
+    ref.eval(); mine.eval()
+    g = torch.Generator().manual_seed(11)
+    n, M = 3, 40
+    obs = _obs(n, g)
+    em = _mem(M, n, 308, g, 272)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    qs, lq = torch.randn(n, 32, generator=g), torch.randn(n, 32, generator=g)
+    act = torch.randint(0, 2, (n, 1), generator=g)
+    r = ref.evaluate_actions_option(obs, h, pa, mk, act, em, emm, qs, lq)
+    m = mine.evaluate_actions_option(obs, h, pa, mk, act, em, emm, qs, lq)
+    for i in (0, 1, 2, 3, 5, 6):  # value, unct, log_probs, entropy, em_feats, probs
+        assert torch.allclose(r[i], m[i], atol=1e-6), i
+    with torch.no_grad():
+        r = ref.act_option(obs, h, pa, mk, em, emm, qs, lq, deterministic=True)
+        m = mine.act_option(obs, h, pa, mk, em, emm, qs, lq, uniforms=None)
+    assert torch.equal(r[2], m[2])
+    for i in (0, 1, 3, 5, 6):
+        assert torch.allclose(r[i], m[i], atol=1e-6), i
+
+
+@pytest.mark.parametrize("without_dialog", [False, True])
+def test_dialog_policy_matches_reference(without_dialog, monkeypatch):
+    """pi_l (policy.py:334-344, :676-917) with the CLIP tower replaced on BOTH sides by the oracle restatement of
+    openai/CLIP's text encoder (the third-party package is absent; 2 layers keep the test fast)."""
+    monkeypatch.setenv("AVLEN_SHIM_CLIP_LAYERS", "2")
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavDialogPolicy(ref_shim.observation_space(), sp.Discrete(4), hidden_size=256, nhead=8,
+                                   num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
+                                   pretraining=False)
+    mine = OM.AudioNavDialogPolicy(clip_layers=2)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    sd = OM.seeded_state_dict(mine, 7)
+    ref.load_state_dict(sd); mine.load_state_dict(sd)
+    ref.eval(); mine.eval()
+    g = torch.Generator().manual_seed(12)
+    n, M, Kd = 4, 30, 3
+    obs = _obs(n, g)
+    em = _mem(M, n, 276, g, 272)
+    emd = torch.randn(Kd, n, 256, generator=g)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    # the reference hands ONE mask tensor to both the scene memory and the dialog memory (policy.py:846,:862): they
+    # must have the same number of slots on this call path, so the dialog memory is padded to M here
+    emd_full = torch.zeros(M, n, 256)
+    emd_full[:Kd] = emd
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    dialog = torch.zeros(n, 77, dtype=torch.long)
+    for b, k in enumerate((6, 0, 12, 3)):
+        if k:
+            dialog[b, 0] = 49406
+            dialog[b, 1:1 + k] = torch.randint(1, 49000, (k,), generator=g)
+            dialog[b, 1 + k] = 49407
+    step = torch.randint(0, 3, (n,), generator=g)
+    act = torch.randint(0, 4, (n, 1), generator=g)
+    r = ref.evaluate_actions_dialog(obs, h, pa, mk, act, em, emd_full, emm, dialog, step, without_dialog=without_dialog)
+    m = mine.evaluate_actions_dialog(obs, h, pa, mk, act, em, emd_full, emm, dialog, step, without_dialog=without_dialog)
+    assert r[0] is None and m[0] is None
+    for i in (1, 2, 4, 5, 6):
+        assert torch.allclose(r[i], m[i], atol=2e-6), i
+    with torch.no_grad():
+        r = ref.act_dialog(obs, h, pa, mk, em, emd_full, emm, dialog, step, deterministic=True, without_dialog=without_dialog)
+        m = mine.act_dialog(obs, h, pa, mk, em, emd_full, emm, dialog, step, uniforms=None, without_dialog=without_dialog)
+    assert torch.equal(r[1], m[1])
+    for i in (0, 2, 4, 5, 6):
+        assert torch.allclose(r[i], m[i], atol=2e-6), i

@@ -21,6 +21,9 @@ def table(prof, title, n=18):
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+    if len(sys.argv) > 2:
+        from avlen_b200 import nn as K
+        K.set_tensor_cores(int(sys.argv[2]))
     cfg = savi_config(NUM_PROCESSES=64, num_steps=steps)
     tr = DDPPOTrainer(cfg).setup()
     tr.collect_rollout()
