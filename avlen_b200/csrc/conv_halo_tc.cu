@@ -1,0 +1,326 @@
+// Stride-1 "same" convolution (3x3 / 7x7, pad = K/2) on tcgen05 tensor cores WITHOUT im2col expansion.
+//
+// The generic implicit-GEMM kernel (gemm_tc.cu) gathers every input pixel KH*KW times into shared memory; at the
+// shallow encoder layers (C = 4..32 channels, the bulk of custom_resnet18's bytes, smt_resnet.py:56-164) that
+// 9x / 49x shared-memory fill — not HBM, not the tensor pipe — is what bounds it (profiles/r01_tc_conv_layer1*).
+// Here a CTA stages a strip of input rows ONCE, zero halo included, as 16-byte channel-chunk planes
+//     plane c (channels 4c..4c+3):  pixel (ir, ic) of the padded strip at  (ir * Wp + ic) * 16 bytes,  Wp = W + KW - 1
+// and computes the outputs ON THE PADDED GRID: output q = oh * Wp + ow reads, for tap (r, s), padded pixel
+// q + r * Wp + s.  Input and output share one pitch, so for ANY run of 128 consecutive q the A operand of tap (r, s)
+// is the same plane shifted by (r * Wp + s) * 16 bytes: a plain K-major SWIZZLE_NONE UMMA descriptor (rows 16 bytes
+// apart, SBO = 128, LBO = plane stride).  The KW - 1 outputs per row that fall on halo columns are computed and
+// dropped (3 % at W = 64).  Per 128 outputs the tensor core runs KH * KW * C / 8 MMAs (M 128, N = Cout, K 8) straight
+// from the staged strip.  The CTA is warp-specialised and persistent: loader warps cp.async strip i + 1 into the second
+// strip buffer while one elected thread issues the MMAs of strip i and four epilogue warps drain the double-buffered
+// TMEM accumulators (tcgen05.ld, scale / bias / residual / ReLU, NHWC store); the roles meet only at mbarriers.  C == 4 (conv1 on the channel-padded rgb / depth
+// input) pairs horizontally adjacent taps in one K = 8 MMA by setting LBO = 16 bytes (the next pixel).
+//
+// HBM traffic = read x once (+ (KH-1)/R halo rows, L2 hits) + write y once: the algorithmic bytes of DESIGN.md §4.
+#include "tc_common.cuh"
+
+#ifndef AVL_HOST_EMUL
+namespace {
+
+constexpr int HL_TILE = 128;
+constexpr int HL_MAX_MMA = 256;   // MMAs per tile: KH * KW * C / 8 (C == 4: KH * ceil(KW / 2))
+constexpr int HL_EPI_WARPS = 4;    // warps 0-3: epilogue (TMEM lane quadrant = warp index)
+constexpr int HL_MMA_WARP = 4;     // warp 4: one elected thread issues every tcgen05.mma
+constexpr int HL_LOAD_WARPS = 4;   // warps 5-8: cp.async producers of the next strip
+constexpr int HL_THREADS = 32 * (HL_EPI_WARPS + 1 + HL_LOAD_WARPS);
+constexpr int HL_LOAD_THREADS = 32 * HL_LOAD_WARPS;
+
+struct HaloArgs {
+  const float* x;
+  const float* w;  // packed (Cout, KH, KW, C)
+  float* y;
+  const float* bias;
+  const float* scale;
+  const float* residual;
+  long long ldy, ldr;
+  int relu;
+  int vec_store;       // y rows are 16-byte aligned
+  int N, H, W, C, Cout, KH, KW;
+  int R;               // output rows per strip
+  int Wp;              // padded pitch W + KW - 1
+  int tiles;           // ceil(R * Wp / 128)
+  int strips_per_img;  // ceil(H / R)
+  int total_strips;
+  int nc;              // C / 4 chunk planes of the input
+  int kwp;             // C == 4: KW rounded up to even (weight planes per kernel row), else KW
+  uint32_t in_plane;   // bytes per input chunk plane
+  uint32_t w_plane;    // bytes per weight chunk plane (Cout * 16)
+  int n_wplanes;
+  int n_mma;           // MMAs per 128-output tile
+  int ncols;           // TMEM columns per accumulator buffer (Cout)
+  int tmem_cols;       // allocation (power of two >= 32)
+};
+
+// Warp-specialised, persistent over strips.  Three roles run their own loops over the same (strip, tile) sequence
+// and meet only at mbarriers:
+//   loaders  : wait in_empty[b]  -> cp.async the strip into buffer b -> in_full[b]
+//   MMA      : wait in_full[b]; per tile: wait acc_empty[a] -> KH*KW*C/8 MMAs -> commit acc_full[a]; after the strip's
+//              last tile: commit in_empty[b]
+//   epilogue : wait acc_full[a] -> tcgen05.ld -> acc_empty[a] -> scale / bias / residual / ReLU -> NHWC store
+__global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(HaloArgs p) {
+  AVL_DYN_SMEM(smem);
+  __shared__ __align__(8) unsigned long long bars[8];  // in_full[2], in_empty[2], acc_full[2], acc_empty[2]
+  __shared__ uint32_t tmem_base_smem;
+  // per-MMA descriptor increments (16-byte units) for the (r, s, k-pair) sequence of one tile: building a descriptor
+  // from scratch costs ~30 dependent single-thread instructions, which (not the tensor pipe) bounded the first
+  // version of this kernel at ~240 cycles per MMA (profiles/r01_halo_conv_layer1_ncu_full.txt)
+  __shared__ __align__(8) uint2 mma_off[HL_MAX_MMA];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t in_bytes = (uint32_t)p.nc * p.in_plane;
+  const uint32_t in_base0 = w_base + (uint32_t)p.n_wplanes * p.w_plane;
+  const int pad = p.KH >> 1;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto IN_FULL = [&](int b) { return bar0 + 8u * b; };
+  auto IN_EMPTY = [&](int b) { return bar0 + 8u * (2 + b); };
+  auto ACC_FULL = [&](int a) { return bar0 + 8u * (4 + a); };
+  auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (6 + a); };
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(IN_FULL(b), HL_LOAD_THREADS);
+      mbar_init(IN_EMPTY(b), 1);
+      mbar_init(ACC_FULL(b), 1);
+      mbar_init(ACC_EMPTY(b), 32 * HL_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == HL_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // ---- one-time shared-memory setup: zero everything (halo columns, tails and the odd-KW pad plane stay zero for
+  // the life of the CTA), then the weights as chunk planes  plane(tap, c)[n] = w[n, tap, 4c..4c+3]
+  {
+    float4* z = reinterpret_cast<float4*>(smem);
+    const uint32_t n16 = ((uint32_t)p.n_wplanes * p.w_plane + 2 * in_bytes) >> 4;
+    for (uint32_t i = tid; i < n16; i += HL_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  {
+    const int taps = p.KH * p.KW;
+    const int per_n = taps * p.nc;  // 16-byte chunks per output channel
+    const int total = p.Cout * per_n;
+    for (int e = tid; e < total; e += HL_THREADS) {
+      const int n = e / per_n;
+      const int rest = e - n * per_n;  // tap * nc + c
+      int plane = rest;
+      if (p.nc == 1) {  // C == 4: planes indexed (r, s) with kwp planes per kernel row
+        const int r = rest / p.KW;
+        plane = r * p.kwp + (rest - r * p.KW);
+      }
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w) + e);
+      *reinterpret_cast<float4*>(smem + (size_t)plane * p.w_plane + (size_t)n * 16) = v;
+    }
+  }
+  for (int i = tid; i < p.n_mma; i += HL_THREADS) {
+    uint32_t a_off, b_off;
+    if (p.nc == 1) {
+      const int half = p.kwp >> 1;
+      const int r = i / half, s = (i - r * half) * 2;
+      a_off = (uint32_t)(r * p.Wp + s);
+      b_off = (uint32_t)(r * p.kwp + s) * (p.w_plane >> 4);
+    } else {
+      const int pairs = p.nc >> 1;
+      const int tap = i / pairs, j = (i - tap * pairs) * 2;
+      const int r = tap / p.KW, s = tap - r * p.KW;
+      a_off = (uint32_t)(r * p.Wp + s) + (uint32_t)j * (p.in_plane >> 4);
+      b_off = (uint32_t)(tap * p.nc + j) * (p.w_plane >> 4);
+    }
+    mma_off[i] = make_uint2(a_off, b_off);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp >= HL_MMA_WARP + 1) {
+    // ================================================================================ loaders
+    const int lt = tid - 32 * (HL_MMA_WARP + 1);
+    const int rows_in = p.R + p.KH - 1;
+    const int per_row = p.W * p.nc;  // 16-byte chunks per input row
+    const int items = rows_in * per_row;
+    int it_strip = 0;
+    for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
+      const int b = it_strip & 1;
+      mbar_wait(IN_EMPTY(b), (uint32_t)(((it_strip >> 1) & 1) ^ 1));  // first use of each buffer passes
+      const int n = strip / p.strips_per_img;
+      const int oh0 = (strip - n * p.strips_per_img) * p.R;
+      const float* xin = p.x + (long long)n * p.H * p.W * p.C;
+      const uint32_t dst0 = in_base0 + (uint32_t)b * in_bytes;
+      for (int it = lt; it < items; it += HL_LOAD_THREADS) {
+        const int ir = it / per_row;
+        const int rem = it - ir * per_row;  // iw * nc + c == float4 index within the image row
+        const int iw = rem / p.nc;
+        const int c = rem - iw * p.nc;
+        const int ih = oh0 - pad + ir;
+        const bool ok = ih >= 0 && ih < p.H;
+        const float* src = ok ? xin + ((long long)ih * p.W) * p.C + (long long)rem * 4 : p.x;
+        cp_async16(dst0 + (uint32_t)c * p.in_plane + (uint32_t)(ir * p.Wp + pad + iw) * 16, src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(IN_FULL(b));
+    }
+  } else if (warp == HL_MMA_WARP) {
+    // ================================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(HL_TILE, p.ncols);
+      const uint64_t bd0 = umma_desc(w_base, p.w_plane, 128);
+      int it_strip = 0, it_tile = 0;
+      for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
+        const int b = it_strip & 1;
+        const uint32_t in_base = in_base0 + (uint32_t)b * in_bytes;
+        mbar_wait(IN_FULL(b), (uint32_t)((it_strip >> 1) & 1));
+        tc_fence_after();
+        for (int t = 0; t < p.tiles; ++t, ++it_tile) {
+          const int a = it_tile & 1;
+          mbar_wait(ACC_EMPTY(a), (uint32_t)(((it_tile >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(a * p.ncols);
+          const uint64_t ad0 = umma_desc(in_base + (uint32_t)t * HL_TILE * 16, p.nc == 1 ? 16u : p.in_plane, 128);
+#pragma unroll 4
+          for (int i = 0; i < p.n_mma; ++i) {
+            const uint2 o = mma_off[i];
+            umma_tf32(d, ad0 + o.x, bd0 + o.y, idesc, i > 0 ? 1u : 0u);
+          }
+          umma_commit(ACC_FULL(a));
+        }
+        umma_commit(IN_EMPTY(b));  // arrives once every MMA that reads this strip buffer has completed
+      }
+      // no commit may still be in flight towards this CTA's barriers when the CTA retires
+      for (int b = 0; b < 2; ++b) {
+        const int uses = (it_strip + 1 - b) >> 1;
+        if (uses > 0) mbar_wait(IN_EMPTY(b), (uint32_t)((uses - 1) & 1));
+      }
+    }
+  } else {
+    // ================================================================================ epilogue
+    int it_tile = 0;
+    for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+      const int n = strip / p.strips_per_img;
+      const int oh0 = (strip - n * p.strips_per_img) * p.R;
+      for (int t = 0; t < p.tiles; ++t, ++it_tile) {
+        const int a = it_tile & 1;
+        const int q = t * HL_TILE + warp * 32 + lane;
+        const int ohl = q / p.Wp;
+        const int ow = q - ohl * p.Wp;
+        const int oh = oh0 + ohl;
+        const bool valid = ow < p.W && ohl < p.R && oh < p.H;
+        const long long pix = ((long long)n * p.H + oh) * p.W + ow;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.ncols);
+        mbar_wait(ACC_FULL(a), (uint32_t)((it_tile >> 1) & 1));
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          if (c0 + 16 >= p.Cout) {  // accumulator fully read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            mbar_arrive(ACC_EMPTY(a));
+          }
+          if (valid) {
+            float* yrow = p.y + pix * p.ldy + c0;
+            const float* rrow = p.residual ? p.residual + pix * p.ldr + c0 : nullptr;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float acc = __uint_as_float(v[j]);
+              if (p.scale) acc *= __ldg(p.scale + c0 + j);
+              if (p.bias) acc += __ldg(p.bias + c0 + j);
+              if (rrow) acc += rrow[j];
+              if (p.relu) acc = fmaxf(acc, 0.f);
+              o[j] = acc;
+            }
+            if (p.vec_store) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(yrow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) yrow[j] = o[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == HL_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+static int g_halo_on = 1;
+static int g_halo_rows = 8;
+
+}  // namespace
+
+// 1 (default): stride-1 same-padded convolutions with few channels use the halo-strip kernel; 0: always the
+// im2col-gather kernel.  rows > 0 sets the strip height.  Returns the previous on/off state.
+AVL_API int avl_set_tc_conv_halo(int on, int rows) {
+  int old = g_halo_on;
+  g_halo_on = on ? 1 : 0;
+  if (rows > 0) g_halo_rows = rows;
+  return old;
+}
+
+// Returns AVL_ERR_UNSUPPORTED (without launching) when the shape is outside what this kernel is built for; the
+// caller (avl_tc_conv2d_fwd) then falls back to the im2col-gather kernel.
+int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
+                         int stride, int pad, const float* scale, const float* bias, const float* residual,
+                         long long ldr, int relu, float* y, long long ldy, cudaStream_t stream) {
+  if (!g_halo_on) return AVL_ERR_UNSUPPORTED;
+  if (stride != 1 || KH != KW || !(KH & 1) || pad != KH / 2 || KH < 3) return AVL_ERR_UNSUPPORTED;
+  if (!(C == 4 || (C % 8 == 0 && C <= 64)) || (Cout % 16) || Cout > 128) return AVL_ERR_UNSUPPORTED;
+  if (W < 16 || ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15)) return AVL_ERR_UNSUPPORTED;
+  HaloArgs p = {};
+  p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
+  p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
+  p.R = g_halo_rows < H ? g_halo_rows : H;
+  p.Wp = W + KW - 1;
+  p.tiles = avl_div_up((long long)p.R * p.Wp, HL_TILE);
+  p.strips_per_img = avl_div_up(H, p.R);
+  long long total = (long long)N * p.strips_per_img;
+  if (total > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  p.total_strips = (int)total;
+  p.nc = C / 4;
+  p.kwp = (C == 4) ? ((KW + 1) & ~1) : KW;
+  const int in_pixels = p.tiles * HL_TILE + (KH - 1) * p.Wp + KW + 8;
+  p.in_plane = (uint32_t)in_pixels * 16;
+  p.w_plane = (uint32_t)Cout * 16;
+  p.n_wplanes = (C == 4) ? KH * p.kwp : KH * KW * p.nc;
+  p.n_mma = (C == 4) ? KH * (p.kwp / 2) : KH * KW * (p.nc / 2);
+  if (p.n_mma > HL_MAX_MMA) return AVL_ERR_UNSUPPORTED;
+  p.ncols = Cout;
+  int cols = 32;
+  while (cols < 2 * p.ncols) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)p.n_wplanes * p.w_plane + 2 * (size_t)p.nc * p.in_plane;  // double-buffered strip
+  if (smem > 200 * 1024 || smem + (1 << 14) > (1u << 18)) return AVL_ERR_UNSUPPORTED;  // descriptor addresses: 18 bits
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  while (per_sm > 1 && per_sm * cols > 512) --per_sm;
+  long long grid = (long long)avl_num_sms() * per_sm;
+  if (grid > total) grid = total;
+  tc_conv_halo_kernel<<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

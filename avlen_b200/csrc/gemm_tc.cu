@@ -14,7 +14,7 @@
 //   c * plane_stride + r * 16      (8-row core matrices are contiguous: SBO = 128 B, LBO = plane_stride)
 // plane_stride = rows*16 + 16 so that a warp's 16-byte cp.async writes spread over all banks.
 // One MMA consumes K = 8 fp32 (two chunks).  M tile = 128 (one TMEM lane per row), N tile <= 256.
-#include "nn_kernels.cuh"
+#include "tc_common.cuh"
 
 #ifndef AVL_HOST_EMUL
 namespace {
@@ -22,87 +22,10 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // floats per k-tile = 8 chunks of 16 B
 constexpr int TC_CHUNKS = TC_BK / 4;
-constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 128;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-  uint32_t done;
-  uint32_t spins = 0;
-  do {
-    if (++spins > (1u << 24)) __trap();  // a lost arrival must fault, never hang the device
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// .ca variant: the im2col gather re-reads every input pixel KH*KW times from neighbouring rows of the same CTA
-// tile; keeping those lines in L1 turns most of that traffic into L1 hits instead of L2 round trips.
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading byte offset,
-// stride byte offset (all >> 4), version = 1 (Blackwell), layout type 0 = SWIZZLE_NONE.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-  uint32_t d = 0;
-  d |= 1u << 4;                       // c_format = F32
-  d |= 2u << 7;                       // a_format = TF32
-  d |= 2u << 10;                      // b_format = TF32
-  d |= (uint32_t)(N >> 3) << 17;      // n_dim
-  d |= (uint32_t)(M >> 4) << 24;      // m_dim
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar_addr) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+constexpr int TC_STAGES = 4;          // shared-memory ring
+constexpr int TC_INFLIGHT = 2;        // cp.async groups a loader thread keeps in flight before it signals a stage full
+constexpr int TC_LOAD_THREADS = 128;  // warps 0-3: loaders, then the epilogue (TMEM lane quadrant = warp index)
+constexpr int TC_THREADS = 160;       // warp 4: one elected thread issues every tcgen05.mma
 
 struct TcArgs {
   const float* A;
@@ -125,7 +48,7 @@ struct TcArgs {
 template <bool CONV, bool CA = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   AVL_DYN_SMEM(smem);
-  __shared__ __align__(8) unsigned long long bars[TC_STAGES + 1];
+  __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];  // full[S], empty[S], done
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -145,11 +68,19 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const uint32_t stage_bytes = a_stage + b_stage;
   const uint32_t smem_base = smem_u32(smem);
 
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  const uint32_t DONE = bar0 + 8u * (2 * TC_STAGES);
   if (tid == 0) {
-    for (int i = 0; i <= TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(FULL(i), TC_LOAD_THREADS);
+      mbar_init(EMPTY(i), 1);
+    }
+    mbar_init(DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -225,39 +156,51 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
     }
   };
 
-  const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
-
-  for (int s = 0; s < TC_STAGES - 1; ++s) {
-    if (s < KT) load_tile(s, s);
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < KT; ++kt) {
-    const int nxt = kt + TC_STAGES - 1;
-    if (nxt < KT) {
-      const int slot = nxt % TC_STAGES;
-      if (nxt >= TC_STAGES) mbar_wait(smem_u32(&bars[slot]), (uint32_t)((nxt / TC_STAGES - 1) & 1));
-      load_tile(nxt, slot);
-    }
-    cp_async_commit();
-    cp_async_wait<TC_STAGES - 1>();
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const int slot = kt % TC_STAGES;
-      const uint32_t a_base = smem_base + slot * stage_bytes;
-      const uint32_t b_base = a_base + a_stage;
+  if (warp == 4) {
+    // ================================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, bn);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % TC_STAGES;
+        mbar_wait(FULL(slot), (uint32_t)((kt / TC_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t a_base = smem_base + slot * stage_bytes;
+        const uint64_t ad0 = umma_desc(a_base, a_plane, 128);
+        const uint64_t bd0 = umma_desc(a_base + a_stage, b_plane, 128);
 #pragma unroll
-      for (int q = 0; q < TC_BK / 8; ++q) {
-        uint64_t ad = umma_desc(a_base + 2 * q * a_plane, a_plane, 128);
-        uint64_t bd = umma_desc(b_base + 2 * q * b_plane, b_plane, 128);
-        umma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+        for (int q = 0; q < TC_BK / 8; ++q)
+          umma_tf32(tmem_base, ad0 + (uint64_t)((2 * q * a_plane) >> 4), bd0 + (uint64_t)((2 * q * b_plane) >> 4), idesc,
+                    (kt > 0 || q > 0) ? 1u : 0u);
+        umma_commit(EMPTY(slot));  // the stage may be refilled once these MMAs have read it
       }
-      umma_commit(smem_u32(&bars[slot]));
-      if (kt == KT - 1) umma_commit(smem_u32(&bars[TC_STAGES]));
+      umma_commit(DONE);
+      // no commit may still be in flight towards this CTA's barriers when the CTA retires
+      for (int kt = max(0, KT - TC_STAGES); kt < KT; ++kt) mbar_wait(EMPTY(kt % TC_STAGES), (uint32_t)((kt / TC_STAGES) & 1));
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    return;
+  }
+  // ==================================================================================== loaders (warps 0-3)
+  // Each thread keeps TC_INFLIGHT groups of cp.async in flight; a stage is signalled full by all 128 threads once
+  // their own copies for it have landed (wait_group) and been fenced towards the async proxy.
+  for (int kt = 0; kt < KT; ++kt) {
+    const int slot = kt % TC_STAGES;
+    if (kt >= TC_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / TC_STAGES - 1) & 1));
+    load_tile(kt, slot);
+    cp_async_commit();
+    if (kt >= TC_INFLIGHT) {
+      cp_async_wait<TC_INFLIGHT>();
+      fence_proxy_async();
+      mbar_arrive(FULL((kt - TC_INFLIGHT) % TC_STAGES));
     }
   }
-  mbar_wait(smem_u32(&bars[TC_STAGES]), 0);
+  cp_async_wait<0>();
+  fence_proxy_async();
+  for (int kt = max(0, KT - TC_INFLIGHT); kt < KT; ++kt) mbar_arrive(FULL(kt % TC_STAGES));
+  mbar_wait(DONE, 0);
   tc_fence_after();
 
   // ---- epilogue: thread = one output row (TMEM lane), 16 columns at a time
@@ -285,11 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-  }
+  __syncthreads();  // warp 4 deallocates TMEM after every epilogue warp has drained it
 }
 
 static int g_tc_ca = 1;
@@ -310,9 +249,9 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   size_t smem = (size_t)TC_STAGES * TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     attr_set = true;
   }
   dim3 grid(avl_div_up(p.M, TC_BM), avl_div_up(p.N, p.bn));
@@ -347,6 +286,10 @@ AVL_API int avl_tc_gemm(const float* A, long long lda, const float* B, float* C,
   return tc_launch(false, p, (cudaStream_t)stream);
 }
 
+int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
+                         int stride, int pad, const float* scale, const float* bias, const float* residual,
+                         long long ldr, int relu, float* y, long long ldy, cudaStream_t stream);  // conv_halo_tc.cu
+
 // NHWC convolution on the tensor cores.  w_packed: (Cout, KH, KW, C) (k = (r*KW + s)*C + ci), C % 4 == 0.
 AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH,
                               int KW, int stride, int pad, const float* scale, const float* bias,
@@ -355,6 +298,11 @@ AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const 
   if (N == 0) return AVL_OK;
   if (!x || !w_packed || !y) return AVL_ERR_ARG;
   if ((C & 3) || ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15)) return AVL_ERR_UNSUPPORTED;
+  {  // shallow stride-1 layers: halo-strip kernel (no im2col expansion); anything else falls through
+    int rc = avl_tc_conv_halo_try(x, N, H, W, C, w_packed, Cout, KH, KW, stride, pad, scale, bias, residual, ldr, relu,
+                                  y, ldy, (cudaStream_t)stream);
+    if (rc != AVL_ERR_UNSUPPORTED) return rc;
+  }
   TcArgs p = {};
   p.g.N = N; p.g.H = H; p.g.W = W; p.g.C = C; p.g.KH = KH; p.g.KW = KW; p.g.stride = stride; p.g.pad = pad;
   p.g.OH = (H + 2 * pad - KH) / stride + 1;

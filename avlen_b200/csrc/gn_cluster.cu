@@ -1,0 +1,149 @@
+// GroupNorm(16) (+ residual) (+ ReLU) on NHWC in ONE pass over HBM (smt_resnet.py:22-33, nn.GroupNorm eps 1e-5).
+//
+// A thread-block CLUSTER owns one sample: each of its CL CTAs stages 1/CL of the sample's pixels in shared memory
+// while accumulating per-channel sums, the per-group partial sums are exchanged through distributed shared memory
+// (every CTA reads its peers' partials after a cluster barrier), and the slice is normalised straight from shared
+// memory.  x is read once and y written once — the two-pass kernels (statistics pass + apply pass, conv.cu) read x
+// twice and need three launches.  With 64 environments in a rollout step this also turns 64 CTAs into 64 * CL.
+#include "common.cuh"
+
+#ifndef AVL_HOST_EMUL
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int GNC_THREADS = 256;
+constexpr int GNC_MAX_SLICE = 48 * 1024;  // bytes of one CTA's slice (dynamic shared memory)
+
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta,
+                                                                 const float* __restrict__ residual, float* y, int HW,
+                                                                 int C, int groups, float eps, int relu, int cl,
+                                                                 int pix_per_cta) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  __shared__ float acc_s[512], acc_q[512];  // per channel (C <= 512)
+  __shared__ double part[64][2];            // this CTA's per-group (sum, sumsq)
+  __shared__ float g_mean[64], g_rstd[64];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / cl;
+  const int nq = C >> 2;  // float4 per pixel; divides GNC_THREADS
+  const int p0 = rank * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int n4 = max(0, p1 - p0) * nq;
+  const float4* xs = reinterpret_cast<const float4*>(x + ((size_t)n * HW + p0) * C);
+  float4* tile = reinterpret_cast<float4*>(gsm);
+
+  for (int c = tid; c < C; c += GNC_THREADS) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
+  __syncthreads();
+  // ---- pass over HBM: stage + per-thread sums (a thread always sees the same 4 channels: nq divides the stride)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  for (int i = tid; i < n4; i += GNC_THREADS) {
+    const float4 v = __ldg(xs + i);
+    tile[i] = v;
+    s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1); q2 = fmaf(v.z, v.z, q2); q3 = fmaf(v.w, v.w, q3);
+  }
+  // lanes that share a channel quad inside the warp (nq < 32) combine first
+  for (int o = 16; o >= nq && o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    q2 += __shfl_xor_sync(0xffffffffu, q2, o); q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+  }
+  const int lane = tid & 31;
+  const int c0 = (tid % nq) * 4;
+  if (nq >= 32 || lane < nq) {
+    atomicAdd(&acc_s[c0], s0); atomicAdd(&acc_s[c0 + 1], s1); atomicAdd(&acc_s[c0 + 2], s2); atomicAdd(&acc_s[c0 + 3], s3);
+    atomicAdd(&acc_q[c0], q0); atomicAdd(&acc_q[c0 + 1], q1); atomicAdd(&acc_q[c0 + 2], q2); atomicAdd(&acc_q[c0 + 3], q3);
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { S += (double)acc_s[c]; Q += (double)acc_q[c]; }
+    part[tid][0] = S;
+    part[tid][1] = Q;
+  }
+  cluster.sync();
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0;
+    for (int r = 0; r < cl; ++r) {
+      const double* rp = cluster.map_shared_rank(&part[0][0], r);
+      S += rp[tid * 2];
+      Q += rp[tid * 2 + 1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double m = S / cnt;
+    double var = Q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    g_mean[tid] = (float)m;
+    g_rstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  cluster.sync();  // also: no CTA may retire while a peer still reads its partials
+  // ---- normalise from shared memory
+  float a[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j, g = c / cpg;
+    a[j] = g_rstd[g] * __ldg(gamma + c);
+    b[j] = __ldg(beta + c) - g_mean[g] * a[j];
+  }
+  float4* ys = reinterpret_cast<float4*>(y + ((size_t)n * HW + p0) * C);
+  const float4* rs = residual ? reinterpret_cast<const float4*>(residual + ((size_t)n * HW + p0) * C) : nullptr;
+  for (int i = tid; i < n4; i += GNC_THREADS) {
+    const float4 v = tile[i];
+    float4 o = make_float4(fmaf(v.x, a[0], b[0]), fmaf(v.y, a[1], b[1]), fmaf(v.z, a[2], b[2]), fmaf(v.w, a[3], b[3]));
+    if (rs) {
+      const float4 r = __ldg(rs + i);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    ys[i] = o;
+  }
+}
+
+}  // namespace
+
+// Returns AVL_ERR_UNSUPPORTED (nothing launched) for shapes outside this kernel: the caller falls back to the
+// two-pass kernels.  x, y, residual must be 16-byte aligned.
+AVL_API int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, const float* residual,
+                                      float* y, int N, int HW, int C, int groups, float eps, int relu, void* stream) {
+  if (N < 0 || HW < 1 || C < 1 || groups < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !gamma || !beta || !y) return AVL_ERR_ARG;
+  if ((C & 3) || C > 512 || groups > 64 || C % groups || GNC_THREADS % (C >> 2)) return AVL_ERR_UNSUPPORTED;
+  if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || ((uintptr_t)residual & 15)) return AVL_ERR_UNSUPPORTED;
+  const long long sample_bytes = (long long)HW * C * 4;
+  int cl = 1;
+  while (cl < 8 && sample_bytes / cl > 32 * 1024) cl <<= 1;
+  if (cl > HW) return AVL_ERR_UNSUPPORTED;
+  const int pix_per_cta = avl_div_up(HW, cl);
+  const size_t smem = (size_t)pix_per_cta * C * 4;
+  if (smem > (size_t)GNC_MAX_SLICE || (long long)N * cl > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(N * cl));
+  cfg.blockDim = dim3(GNC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, x, gamma, beta, residual, y, HW, C, groups, eps, relu, cl,
+                                    pix_per_cta));
+  avl_count_launch();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

@@ -14,6 +14,7 @@ _lib.register({
     "avl_conv2d_fwd": [P, I, I, I, I, P, I, I, I, I, I, P, P, P, L, I, P, L, P],
     "avl_groupnorm_fwd": [P, P, P, P, P, I, I, I, I, F, I, P],
     "avl_groupnorm_fwd_split": [P, P, P, P, P, I, I, I, I, F, I, P, P],
+    "avl_groupnorm_fwd_cluster": [P, P, P, P, P, I, I, I, I, F, I, P],
     "avl_resize_half": [P, P, I, I, I, I, I, F, P],
     "avl_pad_channels": [P, P, L, I, I, P],
     "avl_concat_rgbd": [P, P, P, L, I, I, F, P],
@@ -34,6 +35,7 @@ _lib.register({
     "avl_set_tensor_cores": [I],
     "avl_get_tensor_cores": [],
     "avl_set_tc_conv_l1": [I],
+    "avl_set_tc_conv_halo": [I, I],
     "avl_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "avl_conv2d_wgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "avl_relu_mask": [P, L, P, L, L, I, P],
@@ -44,12 +46,25 @@ _lib.register({
 }, {"avl_gru_workspace_bytes": c_longlong})
 
 _gn_scratch = {}
+_gn_cluster = [True]
+
+
+def set_groupnorm_cluster(on) -> bool:
+    """Single-pass cluster GroupNorm (csrc/gn_cluster.cu) on / off (off: the two-pass kernels)."""
+    old = _gn_cluster[0]
+    _gn_cluster[0] = bool(on)
+    return old
 
 
 def set_tensor_cores(level) -> int:
     """tcgen05 (TF32) level: 0/False = fp32 SIMT only, 1/True = encoder convs + FCs (default), 2 = also the SMT
     dense layers.  Returns the previous level."""
     return int(_lib.lib().avl_set_tensor_cores(int(level)))
+
+
+def set_conv_halo(on, rows=0) -> int:
+    """Halo-strip tensor-core kernel for stride-1 same-padded convolutions (csrc/conv_halo_tc.cu) on / off."""
+    return int(_lib.lib().avl_set_tc_conv_halo(int(on), int(rows)))
 
 
 def tensor_cores_level() -> int:
@@ -236,6 +251,14 @@ def _groupnorm_raw(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=Non
     N, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if _gn_cluster[0] and C % 4 == 0:
+        # one pass over HBM: a thread-block cluster per sample, statistics exchanged through distributed shared memory
+        rc = _lib.lib().avl_groupnorm_fwd_cluster(fptr(x), fptr(gamma), fptr(beta), fptr(residual), fptr(out), N, H * W,
+                                                  C, groups, float(eps), int(relu), stream())
+        if rc == 0:
+            return out
+        if rc != -2:  # -2: shape outside the cluster kernel -> two-pass kernels below
+            _lib.check(rc, "avl_groupnorm_fwd_cluster")
     if C % 4 == 0 and 256 % C == 0 and N * H * W * C >= (1 << 20):
         st = _gn_scratch.get(x.device)
         need = 2 * N * groups + N * C  # doubles: stats + (a, b) float2 per (n, c)

@@ -114,6 +114,10 @@ int avl_groupnorm_fwd(const float* x, const float* gamma, const float* beta, con
 int avl_groupnorm_fwd_split(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
                             int N, int HW, int C, int groups, float eps, int relu, double* stats_scratch,
                             void* stream);
+/* one pass over HBM: one thread-block cluster per sample, per-group statistics exchanged through distributed shared
+ * memory; AVL_ERR_UNSUPPORTED (-2, nothing launched) for shapes it does not cover                                   */
+int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                              int N, int HW, int C, int groups, float eps, int relu, void* stream);
 int avl_resize_half(const float* x, float* y, int N, int H, int W, int C, int C_out, float scale, void* stream);
 int avl_pad_channels(const float* x, float* y, long long rows, int C, int C_out, void* stream);
 int avl_concat_rgbd(const float* rgb, const float* depth, float* y, long long pixels, int c_rgb, int c_depth,
@@ -173,6 +177,7 @@ int avl_relu_mask(float* dy, long long ldd, const float* y, long long ldy, long 
 int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const float* gamma, float* dx, float* dres,
                       float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
                       void* stream);
+int avl_set_tc_conv_halo(int on, int rows_per_strip); /* halo-strip kernel for stride-1 same convs; returns old */
 int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
 
 /* ----------------------------------------------------------------------------- row H: GRU state encoder

@@ -83,6 +83,35 @@ def test_groupnorm_residual_relu(C, HW):
     assert rel(out, ref) < TOL
 
 
+@pytest.mark.parametrize("N,C,HW,res", [(3, 16, (64, 64), True), (70, 32, (32, 32), False), (5, 64, (16, 16), True),
+                                        (9, 128, (8, 8), True), (2, 128, (9, 4), False), (4, 16, (65, 26), True),
+                                        (3, 256, (5, 2), True), (2, 512, (3, 1), False), (2, 32, (33, 13), True)])
+def test_groupnorm_cluster_single_pass_matches_two_pass_and_torch(N, C, HW, res):
+    """csrc/gn_cluster.cu (one thread-block cluster per sample, DSMEM exchange of the group statistics) against
+    torch.nn.functional.group_norm and against the two-pass kernels, incl. ragged pixel splits across the cluster."""
+    from avlen_b200 import nn as K
+    g = torch.Generator().manual_seed(N * C)
+    x = torch.randn(N, *HW, C, generator=g) * 3 - 1.0
+    ga, be = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    r = torch.randn(N, *HW, C, generator=g) if res else None
+    ref = F.group_norm(x.permute(0, 3, 1, 2), 16, ga, be, 1e-5)
+    if res:
+        ref = ref + r.permute(0, 3, 1, 2)
+    ref = F.relu(ref).permute(0, 2, 3, 1)
+    xc, rc = x.cuda(), (r.cuda() if res else None)
+    old = K.set_groupnorm_cluster(True)
+    try:
+        n0 = K._lib.lib().avl_launch_count()
+        out = K.groupnorm(xc, ga.cuda(), be.cuda(), 16, 1e-5, relu=True, residual=rc)
+        assert K._lib.lib().avl_launch_count() - n0 == 1  # really the single-launch kernel
+        K.set_groupnorm_cluster(False)
+        two = K.groupnorm(xc, ga.cuda(), be.cuda(), 16, 1e-5, relu=True, residual=rc)
+    finally:
+        K.set_groupnorm_cluster(old)
+    assert rel(out.cpu(), ref) < TOL
+    assert rel(out, two) < 1e-5
+
+
 def test_resize_pool_concat():
     from avlen_b200 import nn as K
     g = torch.Generator().manual_seed(2)

@@ -72,6 +72,45 @@ def test_tc_conv_matches_fp32(shape):
     assert rel(out, tref) < TOL_TC
 
 
+@pytest.mark.parametrize("shape", [
+    (5, 64, 64, 16, 16, 3, 1), (3, 64, 64, 4, 16, 7, 3), (4, 32, 32, 32, 32, 3, 1), (2, 20, 24, 8, 48, 3, 1),
+    (3, 64, 64, 16, 16, 3, 1, "res"), (2, 37, 19, 16, 32, 5, 2), (1, 64, 64, 4, 16, 3, 1), (160, 64, 64, 16, 16, 3, 1),
+    (7, 30, 40, 24, 16, 3, 1, "res"), (2, 16, 16, 32, 128, 3, 1),
+])
+@pytest.mark.parametrize("rows", [8, 5, 16])
+def test_halo_strip_conv_matches_fp32(shape, rows):
+    """csrc/conv_halo_tc.cu (stride-1 same-padded conv computed on the padded grid, no im2col) against the fp32 SIMT
+    convolution and torch: ragged strips, 7x7 on 4 channels (adjacent-tap pairing), residual + ReLU epilogue,
+    strided destination rows."""
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, Kk, p = shape[:7]
+    res = len(shape) > 7
+    g = torch.Generator().manual_seed(sum(shape[:7]) + rows)
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    w = (torch.randn(Co, C, Kk, Kk, generator=g) / (C * Kk * Kk) ** 0.5).cuda()
+    b, sc = torch.randn(Co, generator=g).cuda(), (torch.rand(Co, generator=g) + 0.5).cuda()
+    r = torch.randn(N, H, W, Co, generator=g).cuda() if res else None
+    K.set_tensor_cores(False)
+    ref = K.conv2d(x, w, b, 1, p, relu=True, scale=sc, residual=r)
+    K.set_tensor_cores(True)
+    old = K.set_conv_halo(1, rows)
+    try:
+        out = K.conv2d(x, w, b, 1, p, relu=True, scale=sc, residual=r)
+        K.set_conv_halo(0)
+        gen = K.conv2d(x, w, b, 1, p, relu=True, scale=sc, residual=r)
+        K.set_conv_halo(1, rows)
+        wide = torch.full((N * H * W, Co + 5), 3.0, device="cuda")  # unaligned strided destination
+        K.conv2d(x, w, b, 1, p, relu=True, scale=sc, residual=r, out=wide[:, 1:1 + Co])
+    finally:
+        K.set_conv_halo(old, 8)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert rel(out, ref) < TOL_TC
+    assert rel(out, gen) < TOL_TC  # the im2col-gather tensor-core kernel computes the same TF32 products
+    assert torch.equal(wide[:, 1:1 + Co].reshape(out.shape), out)
+    assert bool((wide[:, 0] == 3.0).all()) and bool((wide[:, 1 + Co:] == 3.0).all())
+
+
 @pytest.mark.parametrize("level,min_cos", [(1, 0.9995), (2, 0.995)])
 def test_policy_with_tensor_cores_matches_oracle(level, min_cos):
     """Whole SAVi act + evaluate path with the tensor-core kernels on.  Level 1 (default): TF32 encoders, fp32 SMT.
