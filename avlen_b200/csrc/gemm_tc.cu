@@ -43,6 +43,8 @@ struct TcArgs {
   long long ldr;
   int relu;
   const int* m_dev;
+  int kt_per_split;  // k-tiles per blockIdx.z slice; splits > 1: raw partial sums are atomically added into C
+  int splits;
 };
 
 template <bool CONV, bool CA = false>
@@ -59,7 +61,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const int n0 = blockIdx.y * p.bn;
   const int bn = p.bn;
   const int K = p.K;
-  const int KT = (K + TC_BK - 1) / TC_BK;
+  const int kt0 = blockIdx.z * p.kt_per_split;  // split-K: this CTA reduces k-tiles [kt0, kt0 + KT)
+  const int KT = min((K + TC_BK - 1) / TC_BK - kt0, p.kt_per_split);
+  if (KT <= 0) return;
 
   const uint32_t a_plane = TC_BM * 16 + 16;          // bytes
   const uint32_t b_plane = (uint32_t)bn * 16 + 16;
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   for (int kt = 0; kt < KT; ++kt) {
     const int slot = kt % TC_STAGES;
     if (kt >= TC_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / TC_STAGES - 1) & 1));
-    load_tile(kt, slot);
+    load_tile(kt0 + kt, slot);
     cp_async_commit();
     if (kt >= TC_INFLIGHT) {
       cp_async_wait<TC_INFLIGHT>();
@@ -218,6 +222,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
         int n = n0 + c0 + j;
         if (n < p.N) {
           float x = __uint_as_float(v[j]);
+          if (p.splits > 1) {
+            atomicAdd(crow + j, x);
+            continue;
+          }
           if (p.scale) x *= __ldg(p.scale + n);
           if (p.bias) x += __ldg(p.bias + n);
           if (rrow) x += rrow[j];
@@ -232,6 +240,28 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
 }
 
 static int g_tc_ca = 1;
+static int g_tc_splitk = 1;
+
+__global__ void tc_zero_cols_kernel(float* y, long long ldy, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    y[(i / cols) * ldy + (i % cols)] = 0.f;
+}
+__global__ void tc_epilogue_cols_kernel(float* y, long long ldy, int rows, int cols, const float* __restrict__ scale,
+                                        const float* __restrict__ bias, const float* __restrict__ residual,
+                                        long long ldr, int relu) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long long r = i / cols;
+    float v = y[r * ldy + c];
+    if (scale) v *= scale[c];
+    if (bias) v += bias[c];
+    if (residual) v += residual[r * ldr + c];
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = v;
+  }
+}
 
 static int pick_bn(int N) {
   int n16 = (N + 15) / 16 * 16;
@@ -243,6 +273,24 @@ static int pick_bn(int N) {
 
 static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.bn = pick_bn(p.N);
+  const int sms = avl_num_sms();
+  const int mtiles = avl_div_up(p.M, TC_BM);
+  const int KT = avl_div_up(p.K, TC_BK);
+  p.splits = 1;
+  p.kt_per_split = KT;
+  if (g_tc_splitk && !p.m_dev && mtiles * avl_div_up(p.N, p.bn) * 2 <= sms && KT >= 8) {
+    // few output tiles, long reduction (rollout-batch convolutions on small maps, belief-predictor layers): a
+    // handful of CTAs would each stream the whole K extent through one SM's cp.async path.  Narrow the N tile and
+    // split K over blockIdx.z so that ~2 CTAs per SM share the operand traffic; partial sums meet in C by atomics.
+    if (p.bn > 64) p.bn = 64;
+    const int ctas = mtiles * avl_div_up(p.N, p.bn);
+    int splits = (2 * sms + ctas - 1) / ctas;
+    if (splits > KT / 4) splits = KT / 4;
+    if (splits > 1) {
+      p.kt_per_split = avl_div_up(KT, splits);
+      p.splits = avl_div_up(KT, p.kt_per_split);
+    }
+  }
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
@@ -254,15 +302,38 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
     AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     attr_set = true;
   }
-  dim3 grid(avl_div_up(p.M, TC_BM), avl_div_up(p.N, p.bn));
+  dim3 grid(mtiles, avl_div_up(p.N, p.bn), p.splits);
+  const float *scale = p.scale, *bias = p.bias, *residual = p.residual;
+  const int relu = p.relu;
+  if (p.splits > 1) {
+    long long tot = (long long)p.M * p.N;
+    int g = (int)((tot + 255) / 256 > (long long)sms * 16 ? (long long)sms * 16 : (tot + 255) / 256);
+    tc_zero_cols_kernel<<<g, 256, 0, s>>>(p.C, p.ldc, p.M, p.N);
+    AVL_LAUNCH_CHECK();
+    p.scale = p.bias = p.residual = nullptr;
+    p.relu = 0;
+  }
   if (conv && g_tc_ca) tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, s>>>(p);
   else if (conv) tc_gemm_kernel<true><<<grid, TC_THREADS, smem, s>>>(p);
   else tc_gemm_kernel<false><<<grid, TC_THREADS, smem, s>>>(p);
   AVL_LAUNCH_CHECK();
+  if (p.splits > 1 && (scale || bias || residual || relu)) {
+    long long tot = (long long)p.M * p.N;
+    int g = (int)((tot + 255) / 256 > (long long)sms * 16 ? (long long)sms * 16 : (tot + 255) / 256);
+    tc_epilogue_cols_kernel<<<g, 256, 0, s>>>(p.C, p.ldc, p.M, p.N, scale, bias, residual, p.ldr, relu);
+    AVL_LAUNCH_CHECK();
+  }
   return AVL_OK;
 }
 
 }  // namespace
+
+// 1 (default): small-M / long-K problems are split over K (atomic partial sums); 0: never.  Returns the old value.
+AVL_API int avl_set_tc_splitk(int on) {
+  int old = g_tc_splitk;
+  g_tc_splitk = on ? 1 : 0;
+  return old;
+}
 
 // 1 (default): im2col gathers go through L1 (cp.async.ca); 0: L2 only (cp.async.cg).  Returns the old value.
 AVL_API int avl_set_tc_conv_l1(int on) {

@@ -35,6 +35,7 @@ _lib.register({
     "avl_set_tensor_cores": [I],
     "avl_get_tensor_cores": [],
     "avl_set_tc_conv_l1": [I],
+    "avl_set_tc_splitk": [I],
     "avl_set_tc_conv_halo": [I, I],
     "avl_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "avl_conv2d_wgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
@@ -47,6 +48,7 @@ _lib.register({
 
 _gn_scratch = {}
 _gn_cluster = [True]
+_tc_min_rows = [64]
 
 
 def set_groupnorm_cluster(on) -> bool:
@@ -131,7 +133,8 @@ def _conv2d_raw(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residu
     Cout, Cw, KH, KW = w.shape
     assert Cw == C or (Cw < C and C % 4 == 0), (Cw, C)  # x may carry zero-padded channels (tensor-core path)
     OH, OW = conv_out(H, KH, stride, pad), conv_out(W, KW, stride, pad)
-    tc = N * OH * OW >= 512 and x.data_ptr() % 16 == 0 and tensor_cores_enabled()
+    # >= 64 output positions: below a full 128-row tile the tensor-core kernel still wins through split-K
+    tc = N * OH * OW >= _tc_min_rows[0] and x.data_ptr() % 16 == 0 and tensor_cores_enabled()
     if tc and C % 4 != 0:
         cp = (C + 3) // 4 * 4
         x, C = pad_channels(x, cp), cp

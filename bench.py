@@ -153,34 +153,45 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM convolution (tc_gemm_kernel<CONV>), timed on its
-    # most expensive shape (custom_resnet18 layer1 conv3x3 16->16 @64x64, update-minibatch batch).  Arithmetic
+    # ---- roofline of the dominant kernel.  The encoder convolutions dominate the device time of a cycle
+    # (profiles/r01_profile_step_*.txt); their most expensive single launch is custom_resnet18 layer1 (conv3x3
+    # 16->16 @64x64) at the update-minibatch batch, run by tc_conv_halo_kernel (csrc/conv_halo_tc.cu).  Arithmetic
     # intensity in fp32 = 2*144*16 / (2*16*4) = 36 FLOP/B < the TF32 ridge (~110 FLOP/B) => HBM-bound: algorithmic
-    # bytes = read x + write y (+ weights), DESIGN.md section 4.
+    # bytes = read x + write y (+ weights), DESIGN.md section 4.  Timed live here with CUDA events on the launch
+    # stream, L2 flushed between iterations.
     hbm, tf, how = _peaks()
     B = args.envs * args.rollout_steps // cfg.num_mini_batch
     B = min(B, 4800)
     x = torch.randn(B, 64, 64, 16, device=dev)
     w = torch.randn(16, 16, 3, 3, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(3):
         K.conv2d(x, w, None, 1, 1)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
+    ts = []
     for _ in range(10):
+        flush.zero_()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
         K.conv2d(x, w, None, 1, 1)
-    c1.record()
-    torch.cuda.synchronize()
-    k_ms = c0.elapsed_time(c1) / 10
+        c1.record()
+        torch.cuda.synchronize()
+        ts.append(c0.elapsed_time(c1))
+    k_ms = sum(ts) / len(ts)
     flops = 2.0 * B * 64 * 64 * 16 * 144
     nbytes = 2.0 * B * 64 * 64 * 16 * 4 + 16 * 144 * 4
     ach = nbytes / (k_ms * 1e-3) / 1e9
     tcl = K.tensor_cores_level()
-    roofline = {"kernel": ("tc_gemm_kernel<CONV> tcgen05 kind::tf32" if tcl >= 1 else "gemm_kernel<CONV> fp32 SIMT")
-                + " (custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d)" % B,
+    roofline = {"kernel": ("tc_conv_halo_kernel (tcgen05 kind::tf32, halo strips, no im2col)" if tcl >= 1
+                           else "gemm_kernel<CONV> fp32 SIMT")
+                + " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
                 "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(ach / hbm, 5), "traffic": None, "peak_source": how,
-                "launch_ms": round(k_ms, 4), "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2),
-                "note": "algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound"}
+                "frac": round(ach / hbm, 5),
+                "traffic": 2465679000 if (tcl >= 1 and B == 4800) else None,
+                "traffic_source": "profiles/r01_halo_conv_v2_layer1_ncu_full.txt (dram read + write of one launch)",
+                "peak_source": how, "launch_ms": round(k_ms, 4), "algorithmic_bytes": int(nbytes),
+                "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2),
+                "note": "algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound; "
+                        "limited by the tensor core's shared-memory operand fetch at N = 16 (DESIGN.md section 4)"}
     cpu = cpu_baseline_sample(1, quick=True) if not args.no_cpu else None
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",

@@ -43,7 +43,8 @@ def test_tc_gemm_matches_fp32(M, N, K_):
     mdev = torch.tensor([M // 2 + 3], dtype=torch.int32, device="cuda")
     _lib.call("avl_tc_gemm", x.data_ptr(), K_, w.data_ptr(), out2.data_ptr(), N, M, N, K_, None, b.data_ptr(),
               res.data_ptr(), N, 1, mdev.data_ptr(), _lib.stream())
-    assert torch.equal(out2[: M // 2 + 3], out[: M // 2 + 3])
+    # same TF32 products; the summation order may differ (the full-M call can take the split-K path)
+    assert float((out2[: M // 2 + 3] - out[: M // 2 + 3]).abs().max()) < 1e-5 * max(1.0, float(out.abs().max()))
     assert bool((out2[M // 2 + 3:] == 7.0).all())
     assert K.tensor_cores_enabled()
 
@@ -53,6 +54,9 @@ def test_tc_gemm_matches_fp32(M, N, K_):
     (40, 32, 32, 32, 32, 3, 3, 1, 1), (40, 16, 16, 64, 64, 3, 3, 1, 1), (40, 8, 8, 128, 128, 3, 3, 1, 1),
     (600, 8, 8, 128, 64, 8, 8, 1, 0), (64, 31, 11, 32, 64, 3, 3, 2, 0), (64, 15, 5, 64, 64, 3, 3, 1, 0),
     (600, 13, 3, 64, 128, 13, 3, 1, 0), (16, 17, 7, 64, 128, 3, 3, 2, 1), (16, 5, 2, 256, 512, 3, 3, 2, 1),
+    # rollout-batch shapes that take the split-K path (few output tiles, long reduction)
+    (64, 8, 8, 128, 128, 3, 3, 1, 1), (64, 5, 2, 256, 256, 3, 3, 1, 1), (64, 3, 1, 512, 512, 3, 3, 1, 1),
+    (64, 8, 8, 128, 64, 8, 8, 1, 0), (64, 9, 4, 128, 128, 3, 3, 1, 1), (5, 13, 3, 64, 512, 13, 3, 1, 0),
 ])
 def test_tc_conv_matches_fp32(shape):
     from avlen_b200 import nn as K
