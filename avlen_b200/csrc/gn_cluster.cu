@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __
                                                                  int pix_per_cta) {
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ float acc_s[512], acc_q[512];  // per channel (C <= 512)
+  __shared__ float red_s[1024], red_q[1024];  // per (slot, channel) partials, summed in a fixed order (deterministic)
   __shared__ double part[64][2];            // this CTA's per-group (sum, sumsq)
   __shared__ float g_mean[64], g_rstd[64];
   cg::cluster_group cluster = cg::this_cluster();
@@ -37,8 +38,6 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __
   const float4* xs = reinterpret_cast<const float4*>(x + ((size_t)n * HW + p0) * C);
   float4* tile = reinterpret_cast<float4*>(gsm);
 
-  for (int c = tid; c < C; c += GNC_THREADS) { acc_s[c] = 0.f; acc_q[c] = 0.f; }
-  __syncthreads();
   // ---- pass over HBM: stage + per-thread sums (a thread always sees the same 4 channels: nq divides the stride)
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   for (int i = tid; i < n4; i += GNC_THREADS) {
@@ -56,9 +55,24 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __
   }
   const int lane = tid & 31;
   const int c0 = (tid % nq) * 4;
+  // slot = warp (nq < 32: lanes < nq hold the warp's totals) or tid / nq (nq >= 32: every thread its own quad)
+  const int n_slots = nq < 32 ? GNC_THREADS / 32 : GNC_THREADS / nq;
   if (nq >= 32 || lane < nq) {
-    atomicAdd(&acc_s[c0], s0); atomicAdd(&acc_s[c0 + 1], s1); atomicAdd(&acc_s[c0 + 2], s2); atomicAdd(&acc_s[c0 + 3], s3);
-    atomicAdd(&acc_q[c0], q0); atomicAdd(&acc_q[c0 + 1], q1); atomicAdd(&acc_q[c0 + 2], q2); atomicAdd(&acc_q[c0 + 3], q3);
+    const int slot = nq < 32 ? (tid >> 5) : tid / nq;
+    float* ds = red_s + (slot * nq + (tid % nq)) * 4;
+    float* dq = red_q + (slot * nq + (tid % nq)) * 4;
+    ds[0] = s0; ds[1] = s1; ds[2] = s2; ds[3] = s3;
+    dq[0] = q0; dq[1] = q1; dq[2] = q2; dq[3] = q3;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += GNC_THREADS) {
+    float S = 0.f, Q = 0.f;
+    for (int k = 0; k < n_slots; ++k) {
+      S += red_s[(k * nq + (c >> 2)) * 4 + (c & 3)];
+      Q += red_q[(k * nq + (c >> 2)) * 4 + (c & 3)];
+    }
+    acc_s[c] = S;
+    acc_q[c] = Q;
   }
   __syncthreads();
   const int cpg = C / groups;

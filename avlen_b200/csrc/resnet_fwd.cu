@@ -1,0 +1,204 @@
+// Whole-network inference of the two ResNet-18 variants on the hot path in ONE C-ABI call:
+//   * custom_resnet18 (ss_baselines/savi/models/smt_resnet.py:56-164): 7x7 stride-1 stem, no max-pool, widths
+//     16/32/64/128, GroupNorm(16), FC over the flattened map — the SMTCNN rgb / depth encoders (smt_cnn.py:78-115)
+//     and the belief predictor's location head (belief_predictor.py:64-72);
+//   * torchvision resnet18 (belief_predictor.py:74-82): 7x7 stride-2 stem, max-pool, widths 64..512, eval-mode
+//     BatchNorm folded into the conv epilogue, global average pool + Linear.
+// A rollout step at 64 envs is a chain of ~230 small kernels; issued one ctypes call at a time from Python the host
+// (≈17 us per launch) was as slow as the device (tools/host_time.py: 4.0 ms issue vs 4.3 ms per step).  Here the
+// ~45 launches of one network are enqueued from C++ behind a single call, and two independent networks (rgb and
+// depth encoder; classifier and location predictor) can be enqueued on two streams that fork from / join into the
+// caller's stream with events, so their small grids share the GPU.
+#include "common.cuh"
+#include "../../include/avlen_b200.h"
+
+#ifndef AVL_HOST_EMUL
+namespace {
+
+struct Act {
+  float* p;
+  int H, W, C;
+};
+
+inline int out_dim(int size, int k, int stride, int pad) { return (size + 2 * pad - k) / stride + 1; }
+
+// params table layout (device pointers; host array):
+//   [0..2]   stem: weight, norm a, norm b            (GroupNorm: gamma, beta; folded BatchNorm: scale, bias)
+//   [3 + 9*i ..] block i = 2*layer + b: w1, a1, b1, w2, a2, b2, wd, ad, bd   (wd == NULL: identity shortcut)
+//   [75, 76] head: weight, bias
+// Conv weights: (Cout, KH, KW, Cin) when use_tc != 0 (tensor-core path), the reference's OIHW otherwise.
+constexpr int RN_STEM = 0, RN_BLOCK0 = 3, RN_PER_BLOCK = 9, RN_HEAD = RN_BLOCK0 + 8 * RN_PER_BLOCK, RN_COUNT = RN_HEAD + 2;
+
+int conv(const float* x, int N, int H, int W, int C, const float* w, int Cout, int K, int stride, int pad,
+         const float* scale, const float* bias, const float* residual, int relu, float* y, long long ldy, int use_tc,
+         void* s) {
+  const long long ldr = residual ? Cout : 0;
+  if (use_tc)
+    return avl_tc_conv2d_fwd(x, N, H, W, C, w, Cout, K, K, stride, pad, scale, bias, residual, ldr, relu, y, ldy, s);
+  return avl_conv2d_fwd(x, N, H, W, C, w, Cout, K, K, stride, pad, scale, bias, residual, ldr, relu, y, ldy, s);
+}
+
+int gnorm(float* x, const float* gamma, const float* beta, const float* residual, int N, int HW, int C, int groups,
+          float eps, int relu, void* s) {
+  int rc = avl_groupnorm_fwd_cluster(x, gamma, beta, residual, x, N, HW, C, groups, eps, relu, s);
+  if (rc == AVL_ERR_UNSUPPORTED) rc = avl_groupnorm_fwd(x, gamma, beta, residual, x, N, HW, C, groups, eps, relu, s);
+  return rc;
+}
+
+struct Net {
+  int N, H, W, Cin, norm_kind, stem_k, stem_stride, stem_pad, stem_maxpool, widths[4], groups, head_kind, out_dim;
+  float eps;
+};
+
+size_t max_act_floats(const Net& n) {
+  const int h1 = out_dim(n.H, n.stem_k, n.stem_stride, n.stem_pad), w1 = out_dim(n.W, n.stem_k, n.stem_stride, n.stem_pad);
+  return (size_t)n.N * h1 * w1 * n.widths[0];  // the stem output is the largest activation (later stages shrink 2x)
+}
+
+#define RN_TRY(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+int run(const Net& n, const float* x, const float* const* P, float* out, long long ldo, int use_tc, float* ws,
+        void* s) {
+  const size_t act = (max_act_floats(n) + 63) & ~(size_t)63;
+  float* buf[4] = {ws, ws + act, ws + 2 * act, ws + 3 * act};
+  const bool gn = n.norm_kind == 0;
+  // ---- stem
+  Act cur = {buf[0], out_dim(n.H, n.stem_k, n.stem_stride, n.stem_pad), out_dim(n.W, n.stem_k, n.stem_stride, n.stem_pad),
+             n.widths[0]};
+  if (gn) {
+    RN_TRY(conv(x, n.N, n.H, n.W, n.Cin, P[RN_STEM], cur.C, n.stem_k, n.stem_stride, n.stem_pad, nullptr, nullptr,
+                nullptr, 0, cur.p, cur.C, use_tc, s));
+    RN_TRY(gnorm(cur.p, P[RN_STEM + 1], P[RN_STEM + 2], nullptr, n.N, cur.H * cur.W, cur.C, n.groups, n.eps, 1, s));
+  } else {
+    RN_TRY(conv(x, n.N, n.H, n.W, n.Cin, P[RN_STEM], cur.C, n.stem_k, n.stem_stride, n.stem_pad, P[RN_STEM + 1],
+                P[RN_STEM + 2], nullptr, 1, cur.p, cur.C, use_tc, s));
+  }
+  int ci = 0;  // index of the buffer holding `cur`
+  if (n.stem_maxpool) {
+    Act nx = {buf[1], out_dim(cur.H, 3, 2, 1), out_dim(cur.W, 3, 2, 1), cur.C};
+    RN_TRY(avl_maxpool3x3s2(cur.p, nx.p, n.N, cur.H, cur.W, cur.C, s));
+    cur = nx;
+    ci = 1;
+  }
+  // ---- 4 stages x 2 BasicBlocks
+  for (int blk = 0; blk < 8; ++blk) {
+    const float* const* B = P + RN_BLOCK0 + blk * RN_PER_BLOCK;
+    const int planes = n.widths[blk >> 1];
+    const int stride = ((blk & 1) == 0 && blk > 0) ? 2 : 1;
+    float* t1 = buf[(ci + 1) & 3];
+    float* t2 = buf[(ci + 2) & 3];
+    float* idb = buf[(ci + 3) & 3];
+    const int oh = out_dim(cur.H, 3, stride, 1), ow = out_dim(cur.W, 3, stride, 1);
+    const float* identity = cur.p;
+    if (gn) {
+      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, cur.C, B[0], planes, 3, stride, 1, nullptr, nullptr, nullptr, 0, t1, planes,
+                  use_tc, s));
+      RN_TRY(gnorm(t1, B[1], B[2], nullptr, n.N, oh * ow, planes, n.groups, n.eps, 1, s));
+      RN_TRY(conv(t1, n.N, oh, ow, planes, B[3], planes, 3, 1, 1, nullptr, nullptr, nullptr, 0, t2, planes, use_tc, s));
+      if (B[6]) {
+        RN_TRY(conv(cur.p, n.N, cur.H, cur.W, cur.C, B[6], planes, 1, stride, 0, nullptr, nullptr, nullptr, 0, idb,
+                    planes, use_tc, s));
+        RN_TRY(gnorm(idb, B[7], B[8], nullptr, n.N, oh * ow, planes, n.groups, n.eps, 0, s));
+        identity = idb;
+      }
+      RN_TRY(gnorm(t2, B[4], B[5], identity, n.N, oh * ow, planes, n.groups, n.eps, 1, s));
+    } else {
+      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, cur.C, B[0], planes, 3, stride, 1, B[1], B[2], nullptr, 1, t1, planes,
+                  use_tc, s));
+      if (B[6]) {
+        RN_TRY(conv(cur.p, n.N, cur.H, cur.W, cur.C, B[6], planes, 1, stride, 0, B[7], B[8], nullptr, 0, idb, planes,
+                    use_tc, s));
+        identity = idb;
+      }
+      RN_TRY(conv(t1, n.N, oh, ow, planes, B[3], planes, 3, 1, 1, B[4], B[5], identity, 1, t2, planes, use_tc, s));
+    }
+    cur = {t2, oh, ow, planes};
+    ci = (ci + 2) & 3;
+  }
+  // ---- head
+  if (n.head_kind == 0) {  // Linear over the NCHW-flattened map == a conv whose kernel covers the whole map
+    if (cur.H != cur.W && use_tc == 0) {
+      // SIMT path takes KH, KW separately through avl_conv2d_fwd
+    }
+    const long long ldr = 0;
+    if (use_tc)
+      return avl_tc_conv2d_fwd(cur.p, n.N, cur.H, cur.W, cur.C, P[RN_HEAD], n.out_dim, cur.H, cur.W, 1, 0, nullptr,
+                               P[RN_HEAD + 1], nullptr, ldr, 0, out, ldo, s);
+    return avl_conv2d_fwd(cur.p, n.N, cur.H, cur.W, cur.C, P[RN_HEAD], n.out_dim, cur.H, cur.W, 1, 0, nullptr,
+                          P[RN_HEAD + 1], nullptr, ldr, 0, out, ldo, s);
+  }
+  float* pooled = buf[(ci + 1) & 3];
+  RN_TRY(avl_avgpool_global(cur.p, pooled, n.N, cur.H * cur.W, cur.C, s));
+  return avl_gemm(pooled, cur.C, 1, P[RN_HEAD], cur.C, 1, out, ldo, n.N, n.out_dim, cur.C, P[RN_HEAD + 1], 0, 0, 1, s);
+}
+
+bool fill(Net& n, int N, int H, int W, int Cin, const int* cfg) {
+  // cfg (host, 12 ints): norm_kind, stem_k, stem_stride, stem_pad, stem_maxpool, w0, w1, w2, w3, groups, head_kind, out_dim
+  n.N = N; n.H = H; n.W = W; n.Cin = Cin;
+  n.norm_kind = cfg[0]; n.stem_k = cfg[1]; n.stem_stride = cfg[2]; n.stem_pad = cfg[3]; n.stem_maxpool = cfg[4];
+  for (int i = 0; i < 4; ++i) n.widths[i] = cfg[5 + i];
+  n.groups = cfg[9]; n.head_kind = cfg[10]; n.out_dim = cfg[11];
+  if (N < 0 || H < 1 || W < 1 || Cin < 1 || n.stem_k < 1 || n.stem_stride < 1 || n.out_dim < 1) return false;
+  for (int i = 0; i < 4; ++i)
+    if (n.widths[i] < 1) return false;
+  return true;
+}
+
+cudaEvent_t g_fork = nullptr, g_join = nullptr;
+cudaStream_t g_side = nullptr;
+
+}  // namespace
+
+AVL_API int avl_resnet18_param_count(void) { return RN_COUNT; }
+
+// cfg: 12 host ints (see fill()).  Workspace for ONE network.
+AVL_API long long avl_resnet18_workspace_bytes(int N, int H, int W, const int* cfg) {
+  Net n;
+  if (!cfg || !fill(n, N, H, W, 4, cfg)) return -1;
+  return (long long)(4 * ((max_act_floats(n) + 63) & ~(size_t)63) * sizeof(float) + 256);
+}
+
+// x (N, H, W, Cin) NHWC (Cin % 4 == 0 on the tensor-core path); out (N, out_dim) rows of stride ldo.
+// eps: GroupNorm epsilon.  use_tc: weights are packed (Cout, KH, KW, Cin) and every conv runs on tcgen05.
+AVL_API int avl_resnet18_forward(const float* x, int N, int H, int W, int Cin, const int* cfg, float eps,
+                                 const float* const* params, float* out, long long ldo, int use_tc, void* workspace,
+                                 void* stream) {
+  Net n;
+  if (!cfg || !fill(n, N, H, W, Cin, cfg)) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !params || !out || !workspace) return AVL_ERR_ARG;
+  n.eps = eps;
+  return run(n, x, params, out, ldo, use_tc, static_cast<float*>(workspace), stream);
+}
+
+// Two independent networks (e.g. the rgb and the depth encoder) enqueued concurrently: network 0 on `stream`,
+// network 1 on an internal side stream that forks from `stream` and joins it again before the call returns control
+// to the stream order.  Arguments as avl_resnet18_forward, one per network.
+AVL_API int avl_resnet18_forward_pair(const float* x0, const float* x1, int N, int H, int W, int Cin0, int Cin1,
+                                      const int* cfg0, const int* cfg1, float eps, const float* const* params0,
+                                      const float* const* params1, float* out0, float* out1, long long ldo0,
+                                      long long ldo1, int use_tc, void* workspace0, void* workspace1, void* stream) {
+  Net a, b;
+  if (!cfg0 || !cfg1 || !fill(a, N, H, W, Cin0, cfg0) || !fill(b, N, H, W, Cin1, cfg1)) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x0 || !x1 || !params0 || !params1 || !out0 || !out1 || !workspace0 || !workspace1) return AVL_ERR_ARG;
+  a.eps = b.eps = eps;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_side) {
+    AVL_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+  }
+  AVL_CUDA_CHECK(cudaEventRecord(g_fork, s));
+  AVL_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
+  int rc1 = run(b, x1, params1, out1, ldo1, use_tc, static_cast<float*>(workspace1), g_side);
+  int rc0 = run(a, x0, params0, out0, ldo0, use_tc, static_cast<float*>(workspace0), s);
+  AVL_CUDA_CHECK(cudaEventRecord(g_join, g_side));
+  AVL_CUDA_CHECK(cudaStreamWaitEvent(s, g_join, 0));
+  return rc0 ? rc0 : rc1;
+}
+#endif  // AVL_HOST_EMUL

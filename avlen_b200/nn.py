@@ -36,6 +36,10 @@ _lib.register({
     "avl_get_tensor_cores": [],
     "avl_set_tc_conv_l1": [I],
     "avl_set_tc_splitk": [I],
+    "avl_resnet18_param_count": [],
+    "avl_resnet18_workspace_bytes": [I, I, I, P],
+    "avl_resnet18_forward": [P, I, I, I, I, P, F, P, P, L, I, P, P],
+    "avl_resnet18_forward_pair": [P, P, I, I, I, I, I, P, P, F, P, P, P, P, L, L, I, P, P, P],
     "avl_set_tc_conv_halo": [I, I],
     "avl_conv2d_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "avl_conv2d_wgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
@@ -44,7 +48,7 @@ _lib.register({
     "avl_gru_workspace_bytes": [I, I, I, I, I],
     "avl_gru_forward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
-}, {"avl_gru_workspace_bytes": c_longlong})
+}, {"avl_gru_workspace_bytes": c_longlong, "avl_resnet18_workspace_bytes": c_longlong})
 
 _gn_scratch = {}
 _gn_cluster = [True]
@@ -327,3 +331,72 @@ def copy_cols(src, dst):
     rows, cols = src.shape
     call("avl_copy_cols", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, stream())
     return dst
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole-network ResNet-18 inference behind one C-ABI call (csrc/resnet_fwd.cu)
+class ResNetPlan:
+    """Host-side plan of one network for ``avl_resnet18_forward``: the 12-int configuration, the device-pointer table
+    (rebuilt when a parameter changes or the tensor-core mode flips) and a private activation workspace."""
+
+    def __init__(self, cfg, tensors_fn):
+        import ctypes
+        self._ct = ctypes
+        self.cfg = (ctypes.c_int * 12)(*cfg)
+        self._tensors_fn = tensors_fn  # (use_tc) -> list of 77 tensors / None, plus a version key
+        self._key = None
+        self._keep = None
+        self._table = None
+        self._ws = None
+
+    def table(self, use_tc):
+        tensors, key = self._tensors_fn(use_tc)
+        key = (use_tc, key, tuple(0 if t is None else t.data_ptr() for t in tensors))
+        if key != self._key:
+            for t in tensors:
+                if t is not None and (t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()):
+                    raise _lib.AvlenError("ResNet parameters must be contiguous fp32 CUDA tensors")
+            self._table = (self._ct.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+            self._keep, self._key = tensors, key
+        return self._ct.cast(self._table, self._ct.c_void_p)
+
+    def workspace(self, N, H, W, device):
+        nbytes = int(_lib.lib().avl_resnet18_workspace_bytes(N, H, W, self._ct.cast(self.cfg, self._ct.c_void_p)))
+        if nbytes < 0:
+            raise _lib.AvlenError("invalid ResNet configuration")
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def cfg_ptr(self):
+        return self._ct.cast(self.cfg, self._ct.c_void_p)
+
+
+def _prep_net_input(x, use_tc):
+    x = x.contiguous()
+    if use_tc and x.shape[-1] % 4:
+        x = pad_channels(x, (x.shape[-1] + 3) // 4 * 4)
+    return x
+
+
+def resnet18_forward(plan, x, out, eps=1e-5):
+    """One network: x (N, H, W, C) NHWC -> out (N, out_dim) (a column slice is fine)."""
+    use_tc = int(tensor_cores_enabled())
+    x = _prep_net_input(x, use_tc)
+    N, H, W, C = x.shape
+    call("avl_resnet18_forward", fptr(x), N, H, W, C, plan.cfg_ptr(), float(eps), plan.table(use_tc), out.data_ptr(),
+         out.stride(0), use_tc, plan.workspace(N, H, W, x.device).data_ptr(), stream())
+    return out
+
+
+def resnet18_forward_pair(plan0, x0, out0, plan1, x1, out1, eps=1e-5):
+    """Two independent networks on two streams (fork / join around the caller's stream)."""
+    use_tc = int(tensor_cores_enabled())
+    x0, x1 = _prep_net_input(x0, use_tc), _prep_net_input(x1, use_tc)
+    N, H, W, C0 = x0.shape
+    assert x1.shape[:3] == x0.shape[:3]
+    call("avl_resnet18_forward_pair", fptr(x0), fptr(x1), N, H, W, C0, x1.shape[3], plan0.cfg_ptr(), plan1.cfg_ptr(),
+         float(eps), plan0.table(use_tc), plan1.table(use_tc), out0.data_ptr(), out1.data_ptr(), out0.stride(0),
+         out1.stride(0), use_tc, plan0.workspace(N, H, W, x0.device).data_ptr(),
+         plan1.workspace(N, H, W, x0.device).data_ptr(), stream())
+    return out0, out1

@@ -63,8 +63,40 @@ class ResNet18BN(nn.Module):
             self._folded = (key, d)
         return self._folded[1]
 
+    # ---- the whole network behind one C-ABI call (csrc/resnet_fwd.cu) -------------------------------------------
+    def _plan_tensors(self, use_tc):
+        f = self._fold()
+
+        def cw(conv, cin=None):
+            return K._packed_weight(conv.weight, cin) if use_tc else conv.weight.contiguous()
+
+        cin = self.conv1.weight.shape[1]
+        ts = [cw(self.conv1, (cin + 3) // 4 * 4 if use_tc else None), *f["bn1"]]
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                p = f"layer{li}.{bi}."
+                ts += [cw(blk.conv1), *f[p + "bn1"], cw(blk.conv2), *f[p + "bn2"]]
+                if blk.downsample is not None:
+                    ts += [cw(blk.downsample[0]), *f[p + "downsample.1"]]
+                else:
+                    ts += [None, None, None]
+        ts += [self.fc.weight, self.fc.bias]
+        return ts, self._folded[0]
+
+    def plan(self):
+        if getattr(self, "_plan", None) is None:
+            cfg = [1, 7, 2, 3, 1, 64, 128, 256, 512, 1, 1, self.fc.weight.shape[0]]
+            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors))
+        return self._plan
+
     @torch.no_grad()
-    def forward(self, x):  # x NHWC
+    def forward(self, x, out=None):  # x NHWC
+        if out is None:
+            out = torch.empty((x.shape[0], self.fc.weight.shape[0]), device=x.device, dtype=torch.float32)
+        return K.resnet18_forward(self.plan(), x, out)
+
+    @torch.no_grad()
+    def forward_layers(self, x):  # layer-by-layer path (kept as the cross-check of the fused call)
         f = self._fold()
         s, b = f["bn1"]
         x = K.conv2d(x, self.conv1.weight, b, 2, 3, relu=True, scale=s)
@@ -130,8 +162,16 @@ class BeliefPredictor(nn.Module):
         spec = observations[SPECTROGRAM].contiguous()
         n = spec.shape[0]
         st = self._ensure_state(n, spec.device)
-        pg = self.cnn_forward(observations) if self.predict_location else None
-        lab = self.classifier(spec) if self.predict_label else None
+        if self.predict_location and self.predict_label:
+            # classifier and location predictor are independent: one C-ABI call, two streams
+            xp = K.append_planes(spec, observations[CATEGORY]) if self.has_distractor_sound else spec
+            lab = torch.empty((n, self.classifier.fc.weight.shape[0]), device=spec.device, dtype=torch.float32)
+            pg = torch.empty((n, 2), device=spec.device, dtype=torch.float32)
+            K.resnet18_forward_pair(self.classifier.plan(), spec, lab, self.predictor.plan(), xp, pg,
+                                    self.predictor.bn1.eps)
+        else:
+            pg = self.cnn_forward(observations) if self.predict_location else None
+            lab = self.classifier(spec) if self.predict_label else None
         d = None
         if dones is not None:
             d = torch.as_tensor(dones, device=spec.device).reshape(n).to(torch.uint8).contiguous()

@@ -55,6 +55,14 @@ class SMTCNN(nn.Module):
         if out is None:
             out = torch.empty((n, self._feat_dims), device=observations[self.input_modalities[0]].device,
                               dtype=torch.float32)
+        if self.input_modalities == ["rgb", "depth"]:
+            # both encoders behind one C-ABI call, enqueued on two streams (csrc/resnet_fwd.cu)
+            pad = 4 if K.tensor_cores_enabled() else None
+            xr = K.resize_half(observations["rgb"].contiguous(), 1.0 / 255.0, pad)  # /255 then 2x2 area mean (:83-86)
+            xd = K.resize_half(observations["depth"].contiguous(), 1.0, pad)
+            K.resnet18_forward_pair(self.rgb_encoder.plan(), xr, out[:, 0:64], self.depth_encoder.plan(), xd,
+                                    out[:, 64:128], self.rgb_encoder.bn1.eps)
+            return out
         col = 0
         if "rgb" in self.input_modalities:
             pad = 4 if (K.tensor_cores_enabled() and n * 4096 >= 512) else None  # 16-byte channel rows for the TC loader

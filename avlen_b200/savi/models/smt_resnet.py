@@ -51,6 +51,7 @@ class CustomResNet(nn.Module):
         super().__init__()
         self.inplanes = 16
         self.groups = groups
+        self._fc_in_hw = tuple(fc_in_hw)
         self.conv1 = nn.Conv2d(num_input_channels, self.inplanes, kernel_size=7, stride=1, padding=3, bias=False)
         self.bn1 = nn.GroupNorm(groups, self.inplanes)
         self.relu = nn.ReLU(inplace=True)
@@ -77,10 +78,49 @@ class CustomResNet(nn.Module):
             layers.append(block(self.inplanes, planes, groups=self.groups))
         return nn.Sequential(*layers)
 
+    # ---- inference: the whole network behind one C-ABI call (csrc/resnet_fwd.cu) ---------------------------------
+    def _plan_tensors(self, use_tc):
+        def cw(conv, cin=None):  # conv weight in the layout of the selected path
+            return K._packed_weight(conv.weight, cin) if use_tc else conv.weight.contiguous()
+
+        cin = self.conv1.weight.shape[1]
+        ts = [cw(self.conv1, (cin + 3) // 4 * 4 if use_tc else None), self.bn1.weight, self.bn1.bias]
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                ts += [cw(blk.conv1), blk.bn1.weight, blk.bn1.bias, cw(blk.conv2), blk.bn2.weight, blk.bn2.bias]
+                if blk.downsample is not None:
+                    ts += [cw(blk.downsample[0]), blk.downsample[1].weight, blk.downsample[1].bias]
+                else:
+                    ts += [None, None, None]
+        O = self.fc.weight.shape[0]
+        C = self.layer4[-1].conv2.weight.shape[0]
+        hw = self.fc.weight.shape[1] // C
+        h, w = self._fc_in_hw if hw == self._fc_in_hw[0] * self._fc_in_hw[1] else (hw, 1)
+        fcw = self.fc.weight.view(O, C, h, w)
+        ts += [K._packed_weight(fcw) if use_tc else fcw.contiguous(), self.fc.bias]
+        key = tuple(p._version for p in self.parameters())
+        return ts, key
+
+    def plan(self):
+        if getattr(self, "_plan", None) is None:
+            widths = [self.layer1[0].conv1.weight.shape[0], self.layer2[0].conv1.weight.shape[0],
+                      self.layer3[0].conv1.weight.shape[0], self.layer4[0].conv1.weight.shape[0]]
+            cfg = [0, 7, 1, 3, 0, *widths, self.groups, 0, self.fc.weight.shape[0]]
+            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors))
+        return self._plan
+
     def forward(self, x, out=None):
         """x: (N, H, W, C) NHWC float32.  Returns (N, num_classes) (optionally written into ``out``)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            out = None  # differentiable path: K.conv2d / K.groupnorm switch to their autograd Functions
+        trainable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not trainable and not (torch.is_grad_enabled() and x.requires_grad):
+            if out is None:
+                out = torch.empty((x.shape[0], self.fc.weight.shape[0]), device=x.device, dtype=torch.float32)
+            return K.resnet18_forward(self.plan(), x, out, self.bn1.eps)
+        return self.forward_layers(x, None if trainable else out)
+
+    def forward_layers(self, x, out=None):
+        """Layer-by-layer path: the differentiable one (K.conv2d / K.groupnorm switch to their autograd Functions
+        when parameters require grad) and the cross-check of the fused call."""
         x = K.conv2d(x, self.conv1.weight, None, 1, 3)
         x = K.groupnorm(x, self.bn1.weight, self.bn1.bias, self.bn1.num_groups, self.bn1.eps, relu=True, out=x)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):

@@ -129,6 +129,24 @@ int avl_onehot_linear(const long long* actions, const float* W, const float* bia
                       int out_dim, int n_actions, void* stream);
 int avl_copy_cols(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, void* stream);
 
+/* ------------------------------------------------- rows E, M: whole ResNet-18 inference behind one call
+ * custom_resnet18 (ss_baselines/savi/models/smt_resnet.py:56-164; SMTCNN encoders smt_cnn.py:78-115, belief
+ * location head belief_predictor.py:64-72) and torchvision resnet18 with folded eval BatchNorm
+ * (belief_predictor.py:74-82).  cfg: 12 host ints {norm_kind (0 GroupNorm, 1 folded BN), stem_k, stem_stride,
+ * stem_pad, stem_maxpool, width0..3, groups, head_kind (0 Linear over the flattened map, 1 avg-pool + Linear),
+ * out_dim}.  params: avl_resnet18_param_count() device pointers {stem w, a, b; 8 x (w1, a1, b1, w2, a2, b2, wd,
+ * ad, bd); head w, b}; conv weights (Cout, KH, KW, Cin) when use_tc, OIHW otherwise.  _pair enqueues two
+ * independent networks on two streams that fork from / join into `stream`.                                       */
+int avl_resnet18_param_count(void);
+long long avl_resnet18_workspace_bytes(int N, int H, int W, const int* cfg /* host */);
+int avl_resnet18_forward(const float* x, int N, int H, int W, int Cin, const int* cfg /* host */, float eps,
+                         const float* const* params /* host array */, float* out, long long ldo, int use_tc,
+                         void* workspace, void* stream);
+int avl_resnet18_forward_pair(const float* x0, const float* x1, int N, int H, int W, int Cin0, int Cin1,
+                              const int* cfg0, const int* cfg1, float eps, const float* const* params0,
+                              const float* const* params1, float* out0, float* out1, long long ldo0, long long ldo1,
+                              int use_tc, void* workspace0, void* workspace1, void* stream);
+
 /* ----------------------------------------------------------------------------------- dense building blocks
  * C[M,N] (+)= sum_k A(m,k) B(n,k) with element strides; bias / ReLU / accumulate / split-K (atomic).           */
 int avl_gemm(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_n, long long sb_k, float* C,

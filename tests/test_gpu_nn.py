@@ -214,3 +214,67 @@ def test_varlen_attention_fwd_bwd():
     _lib.call("avl_attn_cross_bwd", qd.data_ptr(), kvd.data_ptr(), od.data_ptr(), probs.data_ptr(),
               d1.cuda().data_ptr(), len(lens), D, dq.data_ptr(), dkv.data_ptr(), _lib.stream())
     assert rel(out.cpu(), ref.detach()) < TOL and rel(dq.cpu(), q1.grad) < TOL and rel(dkv.cpu(), kv.grad) < TOL
+
+
+@pytest.mark.parametrize("tc", [1, 0])
+def test_fused_resnet_call_matches_layer_by_layer(tc):
+    """csrc/resnet_fwd.cu (whole custom_resnet18 / torchvision-resnet18 inference behind one C-ABI call, and two
+    networks on two streams) against the layer-by-layer Python path over the same kernels, and against the oracle."""
+    from avlen_b200 import nn as K
+    from avlen_b200.savi.models.belief_predictor import ResNet18BN
+    from avlen_b200.savi.models.smt_resnet import custom_resnet18
+    from oracle import models_torch as OM
+    old = K.set_tensor_cores(tc)
+    try:
+        g = torch.Generator().manual_seed(5)
+        for n in (2, 9):
+            # SMTCNN encoders: 3-channel and 1-channel 64x64 inputs
+            nets = []
+            for cin, seed in ((3, 1), (1, 2)):
+                net = custom_resnet18(num_input_channels=cin)
+                ref = OM.CustomResNet18(cin, 64)
+                sd = OM.seeded_state_dict(ref, seed)
+                ref.load_state_dict(sd); net.load_state_dict(sd)
+                net = net.cuda().eval()
+                x = torch.rand(n, 64, 64, cin, generator=g)
+                with torch.no_grad():
+                    want = ref(x.permute(0, 3, 1, 2))
+                    fused = net(x.cuda())
+                    layers = net.forward_layers(K._prep_net_input(x.cuda(), tc))
+                assert rel(fused, layers) < (2e-3 if tc else 1e-5)  # tiny-M layers: fused = tensor cores, layers = SIMT
+                assert rel(fused.cpu(), want) < (5e-3 if tc else TOL)
+                nets.append((net, x, fused))
+            big = torch.zeros(n, 130, device="cuda")
+            with torch.no_grad():
+                K.resnet18_forward_pair(nets[0][0].plan(), nets[0][1].cuda(), big[:, 1:65], nets[1][0].plan(),
+                                        nets[1][1].cuda(), big[:, 65:129])
+            # same kernels.  Split-K partial sums meet by fp32 atomics, so single ops differ by <= 1e-6 between runs
+            # (tools/check_determinism2.py); 20 layers of TF32 operand truncation turn a last-bit difference into a
+            # TF32-sized one, so on the tensor-core path two runs agree to the TF32 tolerance, not bitwise
+            tol_pair = 5e-3 if tc else 1e-5
+            assert rel(big[:, 1:65], nets[0][2]) < tol_pair and rel(big[:, 65:129], nets[1][2]) < tol_pair
+            assert float(big[:, 0].abs().max()) == 0 and float(big[:, 129].abs().max()) == 0
+            # belief predictor: location head (custom_resnet18 on the 65x26x2 spectrogram, FC over the 9x4 map) and
+            # classifier (torchvision resnet18, eval BatchNorm)
+            pred = custom_resnet18(num_input_channels=2, num_classes=2, fc_in_hw=(9, 4))
+            pref = OM.CustomResNet18(2, 2, fc_in=4608)
+            sd = OM.seeded_state_dict(pref, 7)
+            pref.load_state_dict(sd); pred.load_state_dict(sd)
+            pred = pred.cuda().eval()
+            cls = ResNet18BN(2, 21)
+            sd = OM.seeded_state_dict(cls, 8)
+            for k in sd:
+                if k.endswith("running_var"):
+                    sd[k] = sd[k].abs() + 0.5
+            cls.load_state_dict(sd)
+            cls = cls.cuda().eval()
+            sp = torch.rand(n, 65, 26, 2, generator=g)
+            with torch.no_grad():
+                want = pref(sp.permute(0, 3, 1, 2))
+                fused = pred(sp.cuda())
+                c_fused = cls(sp.cuda())
+                c_layers = cls.forward_layers(sp.cuda())
+            assert rel(fused.cpu(), want) < (5e-3 if tc else TOL)
+            assert rel(c_fused, c_layers) < (5e-3 if tc else 1e-5)
+    finally:
+        K.set_tensor_cores(old)
