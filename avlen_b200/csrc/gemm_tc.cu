@@ -43,6 +43,7 @@ struct TcArgs {
   long long ldr;
   int relu;
   const int* m_dev;
+  int swz;           // 1: SWIZZLE_128B K-major operand tiles (default); 0: SWIZZLE_NONE chunk planes
   int kt_per_split;  // k-tiles per blockIdx.z slice; splits > 1: raw partial sums are atomically added into C
   int splits;
 };
@@ -65,10 +66,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const int KT = min((K + TC_BK - 1) / TC_BK - kt0, p.kt_per_split);
   if (KT <= 0) return;
 
-  const uint32_t a_plane = TC_BM * 16 + 16;          // bytes
-  const uint32_t b_plane = (uint32_t)bn * 16 + 16;
-  const uint32_t a_stage = a_plane * TC_CHUNKS;
-  const uint32_t b_stage = b_plane * TC_CHUNKS;
+  // SWIZZLE_NONE: chunk c of row r at c * plane + r * 16 (plane = rows * 16 + 16).
+  // SWIZZLE_128B : one k-tile row is exactly one 128-byte swizzle row: chunk c of row r at r * 128 + ((c ^ (r & 7)) * 16),
+  //                8-row atoms 1024 bytes apart (SBO), tiles 1024-byte aligned; a K = 8 step advances the start by 32 B.
+  const bool swz = p.swz != 0;
+  const uint32_t a_plane = swz ? 0u : TC_BM * 16 + 16;  // bytes
+  const uint32_t b_plane = swz ? 0u : (uint32_t)bn * 16 + 16;
+  const uint32_t a_stage = swz ? TC_BM * 128u : a_plane * TC_CHUNKS;
+  const uint32_t b_stage = swz ? (uint32_t)bn * 128u : b_plane * TC_CHUNKS;
   const uint32_t stage_bytes = a_stage + b_stage;
   const uint32_t smem_base = smem_u32(smem);
 
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   auto load_tile = [&](int kt, int slot) {
     const int k = kt * TC_BK + 4 * c;  // first element of this thread's chunk
     const bool k_ok = k < K;
-    const uint32_t a_dst = smem_base + slot * stage_bytes + c * a_plane;
+    const uint32_t a_dst = smem_base + slot * stage_bytes + c * a_plane;  // SWIZZLE_NONE: plane base
     int r = 0, s = 0, ci = 0;
     if (CONV && k_ok) {
       int tap = k / p.g.C;
@@ -148,15 +153,16 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
           bytes = 16;
         }
       }
-      if (CA) cp_async16_ca(a_dst + row * 16, src, bytes);
-      else cp_async16(a_dst + row * 16, src, bytes);
+      const uint32_t dst = swz ? a_dst + row * 128 + ((uint32_t)(c ^ (row & 7)) << 4) : a_dst + row * 16;
+      if (CA) cp_async16_ca(dst, src, bytes);
+      else cp_async16(dst, src, bytes);
     }
     const uint32_t b_dst = smem_base + slot * stage_bytes + a_stage + c * b_plane;
     for (int row = r_first; row < bn; row += 16) {
       const int n = n0 + row;
       const bool ok = (n < p.N) && k_ok;
       const float* src = ok ? p.B + (long long)n * K + k : p.B;
-      cp_async16(b_dst + row * 16, src, ok ? 16u : 0u);
+      cp_async16(swz ? b_dst + row * 128 + ((uint32_t)(c ^ (row & 7)) << 4) : b_dst + row * 16, src, ok ? 16u : 0u);
     }
   };
 
@@ -169,12 +175,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
         mbar_wait(FULL(slot), (uint32_t)((kt / TC_STAGES) & 1));
         tc_fence_after();
         const uint32_t a_base = smem_base + slot * stage_bytes;
-        const uint64_t ad0 = umma_desc(a_base, a_plane, 128);
-        const uint64_t bd0 = umma_desc(a_base + a_stage, b_plane, 128);
+        const uint64_t ad0 = swz ? umma_desc_sw128(a_base) : umma_desc(a_base, a_plane, 128);
+        const uint64_t bd0 = swz ? umma_desc_sw128(a_base + a_stage) : umma_desc(a_base + a_stage, b_plane, 128);
+        const uint64_t ainc = swz ? 2u : (uint64_t)((2 * a_plane) >> 4);  // per K = 8 step, in 16-byte units
+        const uint64_t binc = swz ? 2u : (uint64_t)((2 * b_plane) >> 4);
 #pragma unroll
         for (int q = 0; q < TC_BK / 8; ++q)
-          umma_tf32(tmem_base, ad0 + (uint64_t)((2 * q * a_plane) >> 4), bd0 + (uint64_t)((2 * q * b_plane) >> 4), idesc,
-                    (kt > 0 || q > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, ad0 + q * ainc, bd0 + q * binc, idesc, (kt > 0 || q > 0) ? 1u : 0u);
         umma_commit(EMPTY(slot));  // the stage may be refilled once these MMAs have read it
       }
       umma_commit(DONE);
@@ -241,6 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
 
 static int g_tc_ca = 1;
 static int g_tc_splitk = 1;
+static int g_tc_swz = 1;
 
 __global__ void tc_zero_cols_kernel(float* y, long long ldy, int rows, int cols) {
   const long long total = (long long)rows * cols;
@@ -278,6 +286,7 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   const int KT = avl_div_up(p.K, TC_BK);
   p.splits = 1;
   p.kt_per_split = KT;
+  p.swz = g_tc_swz;
   if (g_tc_splitk && !p.m_dev && mtiles * avl_div_up(p.N, p.bn) * 2 <= sms && KT >= 8) {
     // few output tiles, long reduction (rollout-batch convolutions on small maps, belief-predictor layers): a
     // handful of CTAs would each stream the whole K extent through one SM's cp.async path.  Narrow the N tile and
@@ -294,7 +303,8 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = (size_t)TC_STAGES * TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
+  size_t smem = p.swz ? (size_t)TC_STAGES * (TC_BM + (size_t)p.bn) * 128
+                      : (size_t)TC_STAGES * TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
   static bool attr_set = false;
   if (!attr_set) {
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -327,6 +337,13 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
 }
 
 }  // namespace
+
+// Shared-memory operand layout of the generic kernel: 1 (default) SWIZZLE_128B K-major tiles, 0 SWIZZLE_NONE planes.
+AVL_API int avl_set_tc_swizzle(int on) {
+  int old = g_tc_swz;
+  g_tc_swz = on ? 1 : 0;
+  return old;
+}
 
 // 1 (default): small-M / long-K problems are split over K (atomic partial sums); 0: never.  Returns the old value.
 AVL_API int avl_set_tc_splitk(int on) {

@@ -54,6 +54,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= (uint64_t)1 << 46;
   return d;
 }
+// K-major SWIZZLE_128B tile (rows of exactly 128 bytes, 8-row atoms of 1024 bytes, tile 1024-byte aligned):
+// SBO = 1024, LBO unused, layout type 2 (cute::UMMA::LayoutType::SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B.
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   uint32_t d = 0;

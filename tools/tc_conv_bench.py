@@ -32,10 +32,11 @@ def main():
         OH, OW = K.conv_out(H, KH, s, p), K.conv_out(W, KW, s, p)
         flops = 2.0 * B * OH * OW * Co * C * KH * KW
         byts = 4.0 * (x.numel() + B * OH * OW * Co)
-        for level in (3, 2, 1, 0):  # 3: halo-strip kernel; 2: im2col gathers through L1; 1: L2 only; 0: fp32 SIMT
+        for level in (4, 3, 2, 1, 0):  # 4: im2col into SWIZZLE_NONE planes; 3: halo-strip kernel; 2: im2col cp.async.ca; 1: cp.async.cg; 0: fp32 SIMT
             K.set_tensor_cores(min(level, 1))
             K._lib.lib().avl_set_tc_conv_l1(1 if level >= 2 else 0)
             K.set_conv_halo(1 if level == 3 else 0, int(os.environ.get("HALO_ROWS", "8")))
+            K._lib.lib().avl_set_tc_swizzle(0 if level == 4 else 1)
             for _ in range(2):
                 K.conv2d(x, w, None, s, p)
             ts = []
@@ -48,11 +49,12 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = sorted(ts)[len(ts) // 2]
-            print(f"B={B} {name:28s} {('simt', 'tc.cg', 'tc.ca', 'tc.halo')[level]} {ms:8.3f} ms  {flops / ms / 1e9:8.2f} TFLOP/s  "
+            print(f"B={B} {name:28s} {('simt', 'tc.cg', 'tc.ca', 'tc.halo', 'tc.nosw')[level]} {ms:8.3f} ms  {flops / ms / 1e9:8.2f} TFLOP/s  "
                   f"{byts / ms / 1e6:8.1f} GB/s", flush=True)
     K.set_tensor_cores(1)
     K._lib.lib().avl_set_tc_conv_l1(1)
     K.set_conv_halo(1, 8)
+    K._lib.lib().avl_set_tc_swizzle(1)
 
 
 if __name__ == "__main__":
