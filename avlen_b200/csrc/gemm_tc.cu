@@ -22,7 +22,7 @@ namespace {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // floats per k-tile = 8 chunks of 16 B
 constexpr int TC_CHUNKS = TC_BK / 4;
-constexpr int TC_STAGES = 4;          // shared-memory ring
+constexpr int TC_MAX_STAGES = 4;      // shared-memory ring (p.stages <= 4, sized so that two CTAs fit one SM)
 constexpr int TC_INFLIGHT = 2;        // cp.async groups a loader thread keeps in flight before it signals a stage full
 constexpr int TC_LOAD_THREADS = 128;  // warps 0-3: loaders, then the epilogue (TMEM lane quadrant = warp index)
 constexpr int TC_THREADS = 160;       // warp 4: one elected thread issues every tcgen05.mma
@@ -43,6 +43,8 @@ struct TcArgs {
   long long ldr;
   int relu;
   const int* m_dev;
+  int stages;        // 3..4 ring slots
+  int vec_store;     // rows of C / residual and the scale / bias vectors are 16-byte aligned
   int swz;           // 1: SWIZZLE_128B K-major operand tiles (default); 0: SWIZZLE_NONE chunk planes
   int kt_per_split;  // k-tiles per blockIdx.z slice; splits > 1: raw partial sums are atomically added into C
   int splits;
@@ -51,7 +53,8 @@ struct TcArgs {
 template <bool CONV, bool CA = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   AVL_DYN_SMEM(smem);
-  __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 1];  // full[S], empty[S], done
+  __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_STAGES + 1];  // full[S], empty[S], done
+  const int TC_STAGES = p.stages;
   __shared__ uint32_t tmem_base_smem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,20 +227,43 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
     if (m < M) {
       float* crow = p.C + (long long)m * p.ldc + n0 + c0;
       const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
+      if (p.vec_store && p.splits == 1 && n0 + c0 + 16 <= p.N) {
+        // 16-byte stores: a 4-byte store per lane rewrites every 32-byte sector 8 times on its way to L2
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        int n = n0 + c0 + j;
-        if (n < p.N) {
-          float x = __uint_as_float(v[j]);
-          if (p.splits > 1) {
-            atomicAdd(crow + j, x);
-            continue;
+        for (int j = 0; j < 16; j += 4) {
+          float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (p.scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0 + j));
+            x.x *= sc.x; x.y *= sc.y; x.z *= sc.z; x.w *= sc.w;
           }
-          if (p.scale) x *= __ldg(p.scale + n);
-          if (p.bias) x += __ldg(p.bias + n);
-          if (rrow) x += rrow[j];
-          if (p.relu) x = fmaxf(x, 0.f);
-          crow[j] = x;
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          if (rrow) {
+            const float4 r = *reinterpret_cast<const float4*>(rrow + j);
+            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+          }
+          if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          *reinterpret_cast<float4*>(crow + j) = x;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int n = n0 + c0 + j;
+          if (n < p.N) {
+            float x = __uint_as_float(v[j]);
+            if (p.splits > 1) {
+              atomicAdd(crow + j, x);
+              continue;
+            }
+            if (p.scale) x *= __ldg(p.scale + n);
+            if (p.bias) x += __ldg(p.bias + n);
+            if (rrow) x += rrow[j];
+            if (p.relu) x = fmaxf(x, 0.f);
+            crow[j] = x;
+          }
         }
       }
     }
@@ -287,6 +313,9 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.splits = 1;
   p.kt_per_split = KT;
   p.swz = g_tc_swz;
+  p.vec_store = ((p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0 && (!p.bias || ((uintptr_t)p.bias & 15) == 0) &&
+                 (!p.scale || ((uintptr_t)p.scale & 15) == 0) &&
+                 (!p.residual || ((p.ldr & 3) == 0 && ((uintptr_t)p.residual & 15) == 0))) ? 1 : 0;
   if (g_tc_splitk && !p.m_dev && mtiles * avl_div_up(p.N, p.bn) * 2 <= sms && KT >= 8) {
     // few output tiles, long reduction (rollout-batch convolutions on small maps, belief-predictor layers): a
     // handful of CTAs would each stream the whole K extent through one SM's cp.async path.  Narrow the N tile and
@@ -303,8 +332,11 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = p.swz ? (size_t)TC_STAGES * (TC_BM + (size_t)p.bn) * 128
-                      : (size_t)TC_STAGES * TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
+  const size_t stage = p.swz ? (TC_BM + (size_t)p.bn) * 128 : (size_t)TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
+  p.stages = (int)((100 * 1024) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (p.stages < 3) p.stages = 3;  // the loaders keep TC_INFLIGHT = 2 tiles in flight
+  size_t smem = (size_t)p.stages * stage;
   static bool attr_set = false;
   if (!attr_set) {
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -359,6 +391,10 @@ AVL_API int avl_set_tc_conv_l1(int on) {
   return old;
 }
 
+int avl_tc_gemm_tma_try(const float* A, long long lda, const float* B, float* C, long long ldc, int M, int N, int K,
+                        const float* bias, const float* residual, long long ldr, int relu, const int* m_dev,
+                        cudaStream_t stream);  // gemm_tma.cu
+
 // Dense: C[M,N] = act(scale * A[M,K] B[N,K]^T + bias + residual).  A rows / B rows must be 16-byte aligned
 // (lda % 4 == 0, K % 4 == 0).  m_dev: optional device-side row count (packed SMT rows).
 AVL_API int avl_tc_gemm(const float* A, long long lda, const float* B, float* C, long long ldc, int M, int N, int K,
@@ -368,6 +404,12 @@ AVL_API int avl_tc_gemm(const float* A, long long lda, const float* B, float* C,
   if (M == 0) return AVL_OK;
   if (!A || !B || !C) return AVL_ERR_ARG;
   if ((K & 3) || (lda & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return AVL_ERR_UNSUPPORTED;
+  if (!scale && (m_dev || (long long)avl_div_up(M, TC_BM) * avl_div_up(N, 64) * 2 > avl_num_sms() ||
+                 avl_div_up(K, TC_BK) < 8)) {
+    // enough output tiles to fill the GPU without split-K (or split-K not applicable): the TMA-fed kernel
+    int rc = avl_tc_gemm_tma_try(A, lda, B, C, ldc, M, N, K, bias, residual, ldr, relu, m_dev, (cudaStream_t)stream);
+    if (rc != AVL_ERR_UNSUPPORTED) return rc;
+  }
   TcArgs p = {};
   p.A = A; p.lda = lda; p.B = B; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.scale = scale; p.residual = residual; p.ldr = ldr; p.relu = relu; p.m_dev = m_dev;
@@ -386,6 +428,11 @@ AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const 
   if (N == 0) return AVL_OK;
   if (!x || !w_packed || !y) return AVL_ERR_ARG;
   if ((C & 3) || ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15)) return AVL_ERR_UNSUPPORTED;
+  if (KH == H && KW == W && pad == 0) {
+    // kernel covers the whole map (Linear after a flatten): a dense GEMM over the NHWC-flattened rows, no im2col
+    return avl_tc_gemm(x, (long long)H * W * C, w_packed, y, ldy, N, Cout, H * W * C, scale, bias, residual, ldr, relu,
+                       nullptr, stream);
+  }
   {  // shallow stride-1 layers: halo-strip kernel (no im2col expansion); anything else falls through
     int rc = avl_tc_conv_halo_try(x, N, H, W, C, w_packed, Cout, KH, KW, stride, pad, scale, bias, residual, ldr, relu,
                                   y, ldy, (cudaStream_t)stream);

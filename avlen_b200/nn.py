@@ -37,6 +37,7 @@ _lib.register({
     "avl_set_tc_conv_l1": [I],
     "avl_set_tc_splitk": [I],
     "avl_set_tc_swizzle": [I],
+    "avl_set_tc_tma": [I],
     "avl_resnet18_param_count": [],
     "avl_resnet18_workspace_bytes": [I, I, I, P],
     "avl_resnet18_forward": [P, I, I, I, I, P, F, P, P, L, I, P, P],

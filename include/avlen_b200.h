@@ -196,6 +196,7 @@ int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const flo
                       float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
                       void* stream);
 int avl_set_tc_conv_halo(int on, int rows_per_strip); /* halo-strip kernel for stride-1 same convs; returns old */
+int avl_set_tc_tma(int on);      /* dense GEMMs: 1 TMA-fed kernel where it applies (default), 0 cp.async kernel; returns old */
 int avl_set_tc_swizzle(int on);  /* generic kernel operand tiles: 1 SWIZZLE_128B (default), 0 SWIZZLE_NONE; returns old */
 int avl_set_tc_splitk(int on);   /* split-K (atomic partial sums) for small-M / long-K tensor-core problems; returns old */
 int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
