@@ -23,6 +23,7 @@ namespace {
 
 constexpr int HL_TILE = 128;
 constexpr int HL_MAX_MMA = 256;   // MMAs per tile: KH * KW * C / 8 (C == 4: KH * ceil(KW / 2))
+constexpr int HL_PARAM_MMA = 96;  // descriptor increments of up to this many MMAs travel in kernel-parameter (constant) space
 constexpr int HL_EPI_WARPS = 4;    // warps 0-3: epilogue (TMEM lane quadrant = warp index)
 constexpr int HL_MMA_WARP = 4;     // warp 4: one elected thread issues every tcgen05.mma
 constexpr int HL_LOAD_WARPS = 4;   // warps 5-8: cp.async producers of the next strip
@@ -53,6 +54,7 @@ struct HaloArgs {
   int n_mma;           // MMAs per 128-output tile
   int ncols;           // TMEM columns per accumulator buffer (Cout)
   int tmem_cols;       // allocation (power of two >= 32)
+  uint32_t off_a[HL_PARAM_MMA], off_b[HL_PARAM_MMA];  // per-MMA descriptor increments (16-byte units), n_mma <= 96
 };
 
 // Warp-specialised, persistent over strips.  Three roles run their own loops over the same (strip, tile) sequence
@@ -61,7 +63,7 @@ struct HaloArgs {
 //   MMA      : wait in_full[b]; per tile: wait acc_empty[a] -> KH*KW*C/8 MMAs -> commit acc_full[a]; after the strip's
 //              last tile: commit in_empty[b]
 //   epilogue : wait acc_full[a] -> tcgen05.ld -> acc_empty[a] -> scale / bias / residual / ReLU -> NHWC store
-__global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(HaloArgs p) {
+__global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   AVL_DYN_SMEM(smem);
   __shared__ __align__(8) unsigned long long bars[8];  // in_full[2], in_empty[2], acc_full[2], acc_empty[2]
   __shared__ uint32_t tmem_base_smem;
@@ -173,7 +175,8 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(HaloArgs p) {
     }
   } else if (warp == HL_MMA_WARP) {
     // ================================================================================ MMA issuer
-    if (lane == 0) {
+    // (whole warp in the loop, one elected lane issues: see umma_tf32_elect)
+    {
       const uint32_t idesc = umma_idesc_tf32(HL_TILE, p.ncols);
       const uint64_t bd0 = umma_desc(w_base, p.w_plane, 128);
       int it_strip = 0, it_tile = 0;
@@ -188,14 +191,21 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(HaloArgs p) {
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(a * p.ncols);
           const uint64_t ad0 = umma_desc(in_base + (uint32_t)t * HL_TILE * 16, p.nc == 1 ? 16u : p.in_plane, 128);
+          if (p.n_mma <= HL_PARAM_MMA) {
+            // increments read from constant (parameter) space: uniform loads, no shared-memory latency
+#pragma unroll 6
+            for (int i = 0; i < p.n_mma; ++i)
+              umma_tf32_elect(d, ad0 + p.off_a[i], bd0 + p.off_b[i], idesc, i > 0 ? 1u : 0u);
+          } else {
 #pragma unroll 4
-          for (int i = 0; i < p.n_mma; ++i) {
-            const uint2 o = mma_off[i];
-            umma_tf32(d, ad0 + o.x, bd0 + o.y, idesc, i > 0 ? 1u : 0u);
+            for (int i = 0; i < p.n_mma; ++i) {
+              const uint2 o = mma_off[i];
+              umma_tf32_elect(d, ad0 + o.x, bd0 + o.y, idesc, i > 0 ? 1u : 0u);
+            }
           }
-          umma_commit(ACC_FULL(a));
+          umma_commit_elect(ACC_FULL(a));
         }
-        umma_commit(IN_EMPTY(b));  // arrives once every MMA that reads this strip buffer has completed
+        umma_commit_elect(IN_EMPTY(b));  // arrives once every MMA that reads this strip buffer has completed
       }
       // no commit may still be in flight towards this CTA's barriers when the CTA retires
       for (int b = 0; b < 2; ++b) {
@@ -302,6 +312,22 @@ int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float
   p.n_wplanes = (C == 4) ? KH * p.kwp : KH * KW * p.nc;
   p.n_mma = (C == 4) ? KH * (p.kwp / 2) : KH * KW * (p.nc / 2);
   if (p.n_mma > HL_MAX_MMA) return AVL_ERR_UNSUPPORTED;
+  if (p.n_mma <= HL_PARAM_MMA) {
+    for (int i = 0; i < p.n_mma; ++i) {
+      if (p.nc == 1) {
+        const int half = p.kwp >> 1;
+        const int r = i / half, s2 = (i - r * half) * 2;
+        p.off_a[i] = (uint32_t)(r * p.Wp + s2);
+        p.off_b[i] = (uint32_t)(r * p.kwp + s2) * (p.w_plane >> 4);
+      } else {
+        const int pairs = p.nc >> 1;
+        const int tap = i / pairs, j = (i - tap * pairs) * 2;
+        const int r = tap / KW, s2 = tap - r * KW;
+        p.off_a[i] = (uint32_t)(r * p.Wp + s2) + (uint32_t)j * (p.in_plane >> 4);
+        p.off_b[i] = (uint32_t)(tap * p.nc + j) * (p.w_plane >> 4);
+      }
+    }
+  }
   p.ncols = Cout;
   int cols = 32;
   while (cols < 2 * p.ncols) cols <<= 1;
