@@ -103,8 +103,21 @@ def _packed_weight(w, c_pad=None):
     if c_pad is not None and c_pad != w.shape[1]:
         pk = torch.nn.functional.pad(pk, (0, c_pad - w.shape[1]))
     pk = pk.contiguous()
+    if pk.data_ptr() == w.data_ptr():  # 1x1 kernels: the permuted view is already contiguous -> never round the parameter
+        pk = pk.clone()
+    pk = round_to_tf32(pk)
     cache[key] = (w._version, pk)
     return pk
+
+
+def round_to_tf32(t):
+    """Round-to-nearest-even onto the TF32 grid (10 explicit mantissa bits), in place on a contiguous fp32 tensor.
+    The tensor core TRUNCATES fp32 operands to TF32; weights that are already on the grid are consumed exactly, so the
+    weight side of every tensor-core product carries a round-to-nearest (unbiased, half the magnitude) error."""
+    bits = t.view(torch.int32)
+    lsb = (bits >> 13) & 1
+    bits.add_(0xFFF + lsb).bitwise_and_(~0x1FFF)  # Inf / NaN are not expected in weights
+    return t
 
 
 def pad_channels(x, c_out):

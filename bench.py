@@ -186,12 +186,13 @@ def run_ours(args):
                 + " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
                 "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(ach / hbm, 5),
-                "traffic": 2465679000 if (tcl >= 1 and B == 4800) else None,
-                "traffic_source": "profiles/r01_halo_conv_v2_layer1_ncu_full.txt (dram read + write of one launch)",
+                "traffic": 2469416000 if (tcl >= 1 and B == 4800) else None,
+                "traffic_source": "profiles/r01_halo_conv_v3_layer1_ncu_full.txt (dram read + write of one launch)",
                 "peak_source": how, "launch_ms": round(k_ms, 4), "algorithmic_bytes": int(nbytes),
                 "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2),
                 "note": "algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound; "
-                        "limited by the tensor core's shared-memory operand fetch at N = 16 (DESIGN.md section 4)"}
+                        "paced by the tensor core's shared-memory operand fetch (64 B/clk: ~73 cycles per M128xN16xK8 "
+                        "MMA), DESIGN.md section 4"}
     cpu = cpu_baseline_sample(1, quick=True) if not args.no_cpu else None
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
