@@ -1,0 +1,288 @@
+// fp32-ACCURATE dense GEMM on tcgen05 (3xTF32):  C[M, N] = act(A[M, K] B[N, K]^T + bias + residual).
+//
+// The scene-memory transformer's linears must stay fp32-faithful (the reference runs torch.matmul in fp32; stated
+// tolerance 1e-3), which kept them on the SIMT GEMM (~18 TFLOP/s) — by now 60 % of a PPO update.
+// Here every operand is split into two TF32 numbers, x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and
+//     A B^T  ~=  A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T          (dropped term: |A_lo B_lo| <= 2^-22 |A B|)
+// is accumulated in fp32 in TMEM: three tensor-core MMAs per K = 8 slice, fp32-level accuracy (measured ~1e-6).
+//   * B (the weights, <= 768 x 288) is split — and transposed when the backward pass needs W^T — by a tiny kernel
+//     into a library-owned scratch; both parts arrive by TMA.
+//   * A (activations, up to ~4e5 rows) arrives raw by TMA; four "splitter" warps rewrite the landed tile in shared
+//     memory as hi (in place) and lo (second buffer) — elementwise, so the SWIZZLE_128B placement is untouched —
+//     fence it towards the async proxy and hand it to the MMA warp.
+// Warps 0-3: splitters, then the epilogue; warp 4: MMA issue (elect.sync); warp 5: TMA producer.
+#include "tc_common.cuh"
+
+#ifndef AVL_HOST_EMUL
+#include <cuda.h>
+
+namespace {
+
+constexpr int X3_BM = 128, X3_BK = 32, X3_STAGES = 2, X3_THREADS = 192, X3_SPLITTERS = 128;
+
+struct X3Args {
+  float* C;
+  long long ldc;
+  int M, N, K, bn, tmem_cols;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  int relu;
+  int vec_store;
+  const int* m_dev;
+};
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmBhi,
+                                                                const __grid_constant__ CUtensorMap tmBlo, X3Args p) {
+  AVL_DYN_SMEM(smem);
+  __shared__ __align__(8) unsigned long long bars[3 * X3_STAGES + 1];  // full[S], split[S], empty[S], done
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = p.M;
+  if (p.m_dev) M = min(M, *p.m_dev);
+  const int m0 = blockIdx.x * X3_BM;
+  if (m0 >= M) return;
+  const int n0 = blockIdx.y * p.bn;
+  const int bn = p.bn;
+  const int KT = (p.K + X3_BK - 1) / X3_BK;
+  const uint32_t a_tile = X3_BM * 128u, b_tile = (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;  // [A hi | A lo | B hi | B lo]
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto SPLIT = [&](int s) { return bar0 + 8u * (X3_STAGES + s); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (2 * X3_STAGES + s); };
+  const uint32_t DONE = bar0 + 8u * (3 * X3_STAGES);
+  if (tid == 0) {
+    for (int i = 0; i < X3_STAGES; ++i) {
+      mbar_init(FULL(i), 1);
+      mbar_init(SPLIT(i), X3_SPLITTERS);
+      mbar_init(EMPTY(i), 1);
+    }
+    mbar_init(DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBhi);
+    tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 5) {
+    // ================================================================================ TMA producer
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % X3_STAGES;
+        if (kt >= X3_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / X3_STAGES - 1) & 1));
+        const uint32_t base = smem_base + slot * stage_bytes;
+        mbar_arrive_expect_tx(FULL(slot), a_tile + 2 * b_tile);
+        tma_load_2d(base, &tmA, kt * X3_BK, m0, FULL(slot));
+        tma_load_2d(base + 2 * a_tile, &tmBhi, kt * X3_BK, n0, FULL(slot));
+        tma_load_2d(base + 2 * a_tile + b_tile, &tmBlo, kt * X3_BK, n0, FULL(slot));
+      }
+    }
+    __syncthreads();  // matches the final barrier of the other roles
+    return;
+  }
+  if (warp == 4) {
+    // ================================================================================ MMA issuer
+    const uint32_t idesc = umma_idesc_tf32(X3_BM, bn);
+    for (int kt = 0; kt < KT; ++kt) {
+      const int slot = kt % X3_STAGES;
+      mbar_wait(SPLIT(slot), (uint32_t)((kt / X3_STAGES) & 1));
+      tc_fence_after();
+      const uint32_t base = smem_base + slot * stage_bytes;
+      const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + a_tile);
+      const uint64_t bhi = umma_desc_sw128(base + 2 * a_tile), blo = umma_desc_sw128(base + 2 * a_tile + b_tile);
+#pragma unroll
+      for (int q = 0; q < X3_BK / 8; ++q) {
+        umma_tf32_elect(tmem_base, alo + 2u * q, bhi + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);  // small terms first
+        umma_tf32_elect(tmem_base, ahi + 2u * q, blo + 2u * q, idesc, 1u);
+        umma_tf32_elect(tmem_base, ahi + 2u * q, bhi + 2u * q, idesc, 1u);
+      }
+      umma_commit_elect(EMPTY(slot));
+    }
+    umma_commit_elect(DONE);
+    for (int kt = max(0, KT - X3_STAGES); kt < KT; ++kt)
+      mbar_wait(EMPTY(kt % X3_STAGES), (uint32_t)((kt / X3_STAGES) & 1));
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    return;
+  }
+  // ==================================================================================== splitters (warps 0-3)
+  for (int kt = 0; kt < KT; ++kt) {
+    const int slot = kt % X3_STAGES;
+    mbar_wait(FULL(slot), (uint32_t)((kt / X3_STAGES) & 1));
+    float4* hi = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes);
+    float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes + a_tile);
+#pragma unroll
+    for (int i = 0; i < (int)(X3_BM * 128 / 16) / X3_SPLITTERS; ++i) {
+      const int idx = tid + i * X3_SPLITTERS;
+      const float4 v = hi[idx];
+      float4 h, l;
+      h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+      l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+      hi[idx] = h;
+      lo[idx] = l;
+    }
+    fence_proxy_async();
+    mbar_arrive(SPLIT(slot));
+  }
+  mbar_wait(DONE, 0);
+  tc_fence_after();
+  // ---- epilogue: thread = one output row (TMEM lane), 16 columns at a time
+  const int m = m0 + warp * 32 + lane;
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < bn; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c0, v);
+    if (m < M) {
+      float* crow = p.C + (long long)m * p.ldc + n0 + c0;
+      const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
+      if (p.vec_store && n0 + c0 + 16 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          if (rrow) {
+            const float4 r = *reinterpret_cast<const float4*>(rrow + j);
+            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+          }
+          if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          *reinterpret_cast<float4*>(crow + j) = x;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            float x = __uint_as_float(v[j]);
+            if (p.bias) x += __ldg(p.bias + n);
+            if (rrow) x += rrow[j];
+            if (p.relu) x = fmaxf(x, 0.f);
+            crow[j] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+// hi / lo TF32 parts of the (small) B operand; transpose != 0: B is given as [K][N] (ld = row stride) and the parts
+// are written as [N][K]
+__global__ void split_tf32_kernel(const float* __restrict__ src, long long ld, int N, int K, int transpose, float* hi,
+                                  float* lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i - n * K;
+  const float x = transpose ? src[(long long)k * ld + n] : src[(long long)n * ld + k];
+  const float h = rna_tf32(x);
+  hi[i] = h;
+  lo[i] = rna_tf32(x - h);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled3() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+bool make_map3(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled3();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)X3_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr size_t X3_SCRATCH_FLOATS = 1u << 20;  // hi + lo of the B operand: N * K <= 512 Ki elements
+float* g_scratch = nullptr;
+int g_x3_on = 1;
+
+}  // namespace
+
+AVL_API int avl_set_tc_3xtf32(int on) {
+  int old = g_x3_on;
+  g_x3_on = on ? 1 : 0;
+  return old;
+}
+
+// b_transposed != 0: B is stored [K][N] with row stride ldb (the weight of a Linear seen from its backward pass).
+// Returns AVL_ERR_UNSUPPORTED (nothing launched) when the shape / alignment is outside the kernel or the path is off.
+AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long long ldb, int b_transposed, float* C,
+                           long long ldc, int M, int N, int K, const float* bias, const float* residual, long long ldr,
+                           int relu, const int* m_dev, void* stream) {
+  if (!g_x3_on) return AVL_ERR_UNSUPPORTED;
+  if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return AVL_ERR_ARG;
+  if (((uintptr_t)A & 15) || (lda & 3) || (K & 3) || (size_t)N * K * 2 > X3_SCRATCH_FLOATS) return AVL_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_scratch) AVL_CUDA_CHECK(cudaMalloc(&g_scratch, X3_SCRATCH_FLOATS * sizeof(float)));
+  float* bhi = g_scratch;
+  float* blo = g_scratch + (size_t)N * K;
+  split_tf32_kernel<<<avl_div_up((long long)N * K, 256), 256, 0, s>>>(B, ldb, N, K, b_transposed, bhi, blo);
+  AVL_LAUNCH_CHECK();
+  X3Args p = {};
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
+  p.m_dev = m_dev;
+  const int n16 = (N + 15) / 16 * 16;
+  p.bn = n16 < 256 ? n16 : 256;
+  if (n16 > 256)
+    for (int bn = 256; bn >= 64; bn -= 16)
+      if (n16 % bn == 0) { p.bn = bn; break; }
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  p.vec_store = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
+                 (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
+  CUtensorMap ta, tbh, tbl;
+  if (!make_map3(&ta, A, M, K, lda, X3_BM) || !make_map3(&tbh, bhi, N, K, K, p.bn) || !make_map3(&tbl, blo, N, K, K, p.bn))
+    return AVL_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)X3_STAGES * (2 * X3_BM + 2 * (size_t)p.bn) * 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(avl_div_up(M, X3_BM), avl_div_up(N, p.bn));
+  tc_gemm_3x_kernel<<<grid, X3_THREADS, smem, s>>>(ta, tbh, tbl, p);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

@@ -205,8 +205,18 @@ AVL_API int avl_get_tensor_cores(void);
 static bool tc_ok(const float* X, long long ldx, const float* W, int rows, int K) {
   return avl_get_tensor_cores() >= 2 && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && (((uintptr_t)X | (uintptr_t)W) & 15) == 0;
 }
+// fp32-accurate tensor-core path (3xTF32, gemm_3xtf32.cu): level >= 1, enough rows to fill 128-row tiles
+AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long long ldb, int b_transposed, float* C,
+                           long long ldc, int M, int N, int K, const float* bias, const float* residual, long long ldr,
+                           int relu, const int* m_dev, void* stream);
+static bool x3_ok(const float* X, long long ldx, int rows, int K) {
+  return avl_get_tensor_cores() >= 1 && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0;
+}
 #else
 static bool tc_ok(const float*, long long, const float*, int, int) { return false; }
+static bool x3_ok(const float*, long long, int, int) { return false; }
+static int avl_tc_gemm_3x(const float*, long long, const float*, long long, int, float*, long long, int, int, int,
+                          const float*, const float*, long long, int, const int*, void*) { return AVL_ERR_UNSUPPORTED; }
 static int avl_tc_gemm(const float*, long long, const float*, float*, long long, int, int, int, const float*,
                        const float*, const float*, long long, int, const int*, void*) { return 0; }
 #endif
@@ -227,6 +237,11 @@ static void lin_fwd(Launcher& L, const float* X, long long ldx, const float* W, 
     if (rc && !L.err) L.err = rc;
     return;
   }
+  if (x3_ok(X, ldx, rows, K)) {
+    int rc = avl_tc_gemm_3x(X, ldx, W, K, 0, Y, ldy, rows, N, K, b, nullptr, 0, relu, rows_dev, L.s);
+    if (rc == AVL_OK) return;
+    if (rc != AVL_ERR_UNSUPPORTED && !L.err) { L.err = rc; return; }
+  }
   launch_gemm(L, {X, ldx, 1}, true, {W, (long long)K, 1}, true, Y, ldy, rows, N, K, make_ep(b, relu, rows_dev), 1);
 }
 // dX[rows, K] (+)= dY[rows, N] W[N, K]
@@ -241,6 +256,12 @@ static void lin_bwd_x(Launcher& L, const float* dY, long long ldy, const float* 
                          rows_dev, L.s);
     if (rc && !L.err) L.err = rc;
     return;
+  }
+  if (x3_ok(dY, ldy, rows, N)) {  // dX = dY . W with B = W^T taken from the [N][K] weight by the split kernel
+    int rc = avl_tc_gemm_3x(dY, ldy, W, ldw, 1, dX, ldx, rows, K, N, nullptr, accumulate ? dX : nullptr, ldx, 0, rows_dev,
+                            L.s);
+    if (rc == AVL_OK) return;
+    if (rc != AVL_ERR_UNSUPPORTED && !L.err) { L.err = rc; return; }
   }
   GemmEpilogue ep = make_ep(nullptr, 0, rows_dev);
   ep.accumulate = accumulate;

@@ -156,6 +156,13 @@ int avl_gemm(const float* A, long long sa_m, long long sa_k, const float* B, lon
 int avl_tc_gemm(const float* A, long long lda, const float* B, float* C, long long ldc, int M, int N, int K,
                 const float* scale, const float* bias, const float* residual, long long ldr, int relu,
                 const int* m_dev, void* stream);
+/* fp32-accurate (3xTF32: operands split into two TF32 numbers, three MMAs per K slice, fp32 accumulate) dense GEMM
+ * on tcgen05 fed by TMA — the scene-memory transformer's linears (reference: fp32 torch.matmul).  b_transposed: B is
+ * stored [K][N] with row stride ldb.  -2 when the shape / alignment is not covered (nothing launched).               */
+int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long long ldb, int b_transposed, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, const float* residual, long long ldr,
+                   int relu, const int* m_dev, void* stream);
+int avl_set_tc_3xtf32(int on);   /* returns old */
 int avl_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                       float* stats, int rows, int cols, void* stream);
 int avl_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy,

@@ -146,3 +146,39 @@ def test_policy_with_tensor_cores_matches_oracle(level, min_cos):
             cos = float(torch.nn.functional.cosine_similarity(q.grad.cpu().flatten(), og[k].grad.flatten(), dim=0))
             worst = min(worst, cos)
     assert worst > min_cos, worst  # gradient direction per parameter tensor
+
+
+# ------------------------------------------------------------------ 3xTF32: fp32-accurate tensor-core GEMM
+TOL_3X = 2e-5   # of the output's max magnitude; plain fp32 summation over K <= 768 lands at ~1e-6
+
+
+@pytest.mark.parametrize("M,N,K_,bt", [(4800, 256, 276, 0), (1000, 768, 256, 0), (513, 16, 64, 0), (9600, 512, 256, 1),
+                                       (777, 144, 256, 1), (2048, 256, 36, 0), (600, 4, 256, 0), (3000, 276, 256, 1),
+                                       (5000, 256, 512, 1), (128, 256, 256, 0)])
+def test_tc_gemm_3xtf32_is_fp32_accurate(M, N, K_, bt):
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401  (registers the argtypes)
+    g = torch.Generator().manual_seed(M + N + K_ + bt)
+    x = (torch.randn(M, K_, generator=g) * torch.exp(2 * torch.randn(M, 1, generator=g))).cuda()   # wide dynamic range
+    w = (torch.randn(N, K_, generator=g) / K_ ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    ref = F.relu(x.double() @ w.double().t() + b.double() + res.double()).float()
+    wb = w.t().contiguous() if bt else w          # b_transposed: stored [K][N]
+    ldb = N if bt else K_
+    out = torch.full((M, N), float("nan"), device="cuda")
+    rc = _lib.lib().avl_tc_gemm_3x(x.data_ptr(), K_, wb.data_ptr(), ldb, bt, out.data_ptr(), N, M, N, K_, b.data_ptr(),
+                                   res.data_ptr(), N, 1, None, _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert rel(out, ref) < TOL_3X
+    # in-place accumulate (residual aliases the output, as lin_bwd_x uses it) + device-side row count
+    out2 = res.clone()
+    mdev = torch.tensor([M // 2 + 3], dtype=torch.int32, device="cuda")
+    rc = _lib.lib().avl_tc_gemm_3x(x.data_ptr(), K_, wb.data_ptr(), ldb, bt, out2.data_ptr(), N, M, N, K_, None,
+                                   out2.data_ptr(), N, 0, mdev.data_ptr(), _lib.stream())
+    assert rc == 0
+    ref2 = (x.double() @ w.double().t() + res.double()).float()
+    assert rel(out2[: M // 2 + 3], ref2[: M // 2 + 3]) < TOL_3X
+    assert torch.equal(out2[M // 2 + 3:], res[M // 2 + 3:])
