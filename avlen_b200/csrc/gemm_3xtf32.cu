@@ -204,6 +204,208 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long long ld, i
   lo[i] = rna_tf32(x - h);
 }
 
+
+// =====================================================================================================================
+// Weight gradient on tensor cores:  dW[N, K] += dY[rows, N]^T X[rows, K]   (reduction over the rows — up to ~7e5)
+//
+// Both operands have the REDUCTION index as their slow (row) index, i.e. they are "MN-major" for the tensor core.
+// For 32-bit MN-major operands the tensor core accepts exactly one swizzled layout, SWIZZLE_128B with 32-byte atoms
+// (UMMA layout type 1 = cute's Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>: 128-byte line = 32 consecutive features of
+// one row, 32-byte chunk index XOR (row & 3), 4 rows = one 512-byte K atom) — which is what a TMA box of 32 rows x
+// 32 features lands with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  SBO = 512 bytes (next 4 rows), LBO = 4096 bytes (the
+// next 32 features = the next box), one K = 8 slice = 1024 bytes.  So no transposition is needed anywhere: the
+// instruction descriptor just flags A and B as MN-major.  The 3xTF32 split is elementwise and done in place like above; rows at
+// or beyond the device-side row count are zeroed by the splitters (their content is stale).  The grid's z dimension
+// splits the reduction; each CTA writes its partial tile to a workspace with plain stores and a second kernel sums
+// the partials in a fixed order into dW (deterministic, no atomics).
+constexpr int W3_BM = 128, W3_BK = 32, W3_STAGES = 2, W3_SPLIT_WARPS = 8, W3_THREADS = (W3_SPLIT_WARPS + 2) * 32;
+constexpr uint32_t W3_BOX = 32 * 128;  // bytes of one 32 x 32 fp32 box
+
+struct W3Args {
+  float* ws;
+  int rows, N, K, bn, tmem_cols;
+  const int* rows_dev;
+  uint32_t lbo, sbo;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// k-tile range of split z when the reduction has `rows` rows (shared by the GEMM and the reduction kernel)
+__device__ __forceinline__ void w3_range(int rows, int nsplit, int z, int& kt0, int& kt1, int& active) {
+  const int kt_total = (rows + W3_BK - 1) / W3_BK;
+  const int kps = max(1, (kt_total + nsplit - 1) / nsplit);
+  active = (kt_total + kps - 1) / kps;
+  kt0 = z * kps;
+  kt1 = min(kt_total, kt0 + kps);
+}
+
+__global__ void __launch_bounds__(W3_THREADS) tc_wgrad_3x_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, W3Args p) {
+  AVL_DYN_SMEM(smem);
+  __shared__ __align__(8) unsigned long long bars[3 * W3_STAGES + 1];  // full[S], split[S], empty[S], done
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int rows = p.rows;
+  if (p.rows_dev) rows = min(rows, *p.rows_dev);
+  int kt0, kt1, active;
+  w3_range(rows, (int)gridDim.z, (int)blockIdx.z, kt0, kt1, active);
+  if (kt0 >= kt1) return;  // the reduction kernel skips this split as well
+  const int m0 = blockIdx.x * W3_BM, n0 = blockIdx.y * p.bn, bn = p.bn;
+  const int boxes_a = min(W3_BM / 32, (p.N - m0 + 31) / 32);
+  const int boxes_b_cap = (bn + 31) / 32;
+  const int boxes_b = min(boxes_b_cap, (p.K - n0 + 31) / 32);
+  const uint32_t a_tile = (W3_BM / 32) * W3_BOX, b_tile = (uint32_t)boxes_b_cap * W3_BOX;
+  const uint32_t stage_bytes = 2 * a_tile + 2 * b_tile;  // [A hi | A lo | B hi | B lo]
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto SPLIT = [&](int s) { return bar0 + 8u * (W3_STAGES + s); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (2 * W3_STAGES + s); };
+  const uint32_t DONE = bar0 + 8u * (3 * W3_STAGES);
+  if (tid == 0) {
+    for (int i = 0; i < W3_STAGES; ++i) {
+      mbar_init(FULL(i), 1);
+      mbar_init(SPLIT(i), W3_SPLIT_WARPS * 32);
+      mbar_init(EMPTY(i), 1);
+    }
+    mbar_init(DONE, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  // boxes that lie entirely beyond the feature range are never loaded: they must read as zeros
+  for (uint32_t i = tid; i < W3_STAGES * stage_bytes / 16; i += W3_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  if (warp == W3_SPLIT_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int KT = kt1 - kt0;
+
+  if (warp == W3_SPLIT_WARPS + 1) {
+    // ================================================================================ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < KT; ++it) {
+        const int slot = it % W3_STAGES;
+        if (it >= W3_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((it / W3_STAGES - 1) & 1));
+        const uint32_t base = smem_base + slot * stage_bytes;
+        const int r0 = (kt0 + it) * W3_BK;
+        mbar_arrive_expect_tx(FULL(slot), (uint32_t)(boxes_a + boxes_b) * W3_BOX);
+        for (int i = 0; i < boxes_a; ++i) tma_load_2d(base + i * W3_BOX, &tmA, m0 + 32 * i, r0, FULL(slot));
+        for (int j = 0; j < boxes_b; ++j) tma_load_2d(base + 2 * a_tile + j * W3_BOX, &tmB, n0 + 32 * j, r0, FULL(slot));
+      }
+    }
+    __syncthreads();  // matches the final barrier of the other roles
+    return;
+  }
+  if (warp == W3_SPLIT_WARPS) {
+    // ================================================================================ MMA issuer
+    const uint32_t idesc = umma_idesc_tf32(W3_BM, bn) | (1u << 15) | (1u << 16);  // A and B MN-major
+    for (int it = 0; it < KT; ++it) {
+      const int slot = it % W3_STAGES;
+      mbar_wait(SPLIT(slot), (uint32_t)((it / W3_STAGES) & 1));
+      tc_fence_after();
+      const uint32_t base = smem_base + slot * stage_bytes;
+      const uint64_t ahi = umma_desc_mn_sw128_32b(base, p.lbo, p.sbo), alo = umma_desc_mn_sw128_32b(base + a_tile, p.lbo, p.sbo);
+      const uint64_t bhi = umma_desc_mn_sw128_32b(base + 2 * a_tile, p.lbo, p.sbo);
+      const uint64_t blo = umma_desc_mn_sw128_32b(base + 2 * a_tile + b_tile, p.lbo, p.sbo);
+#pragma unroll
+      for (int q = 0; q < W3_BK / 8; ++q) {  // one K = 8 slice = 8 rows = one 1024-byte atom per box
+        const uint32_t adv = (uint32_t)q * (1024u >> 4);
+        umma_tf32_elect(tmem_base, alo + adv, bhi + adv, idesc, (it > 0 || q > 0) ? 1u : 0u);  // small terms first
+        umma_tf32_elect(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+        umma_tf32_elect(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
+      }
+      umma_commit_elect(EMPTY(slot));
+    }
+    umma_commit_elect(DONE);
+    for (int it = max(0, KT - W3_STAGES); it < KT; ++it)
+      mbar_wait(EMPTY(it % W3_STAGES), (uint32_t)((it / W3_STAGES) & 1));
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    return;
+  }
+  // ==================================================================================== splitters (warps 0-7)
+  const int srow = tid >> 3;  // row of this thread's 16-byte chunk inside every box (256 chunks per box)
+  for (int it = 0; it < KT; ++it) {
+    const int slot = it % W3_STAGES;
+    mbar_wait(FULL(slot), (uint32_t)((it / W3_STAGES) & 1));
+    const bool live = (kt0 + it) * W3_BK + srow < rows;
+    unsigned char* st = smem + (size_t)slot * stage_bytes;
+    auto split_boxes = [&](unsigned char* hi_base, unsigned char* lo_base, int nbox) {
+      for (int i = 0; i < nbox; ++i) {
+        float4* hp = reinterpret_cast<float4*>(hi_base + (size_t)i * W3_BOX) + tid;
+        float4* lp = reinterpret_cast<float4*>(lo_base + (size_t)i * W3_BOX) + tid;
+        float4 v = *hp;
+        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+        *hp = h;
+        *lp = l;
+      }
+    };
+    split_boxes(st, st + a_tile, boxes_a);
+    split_boxes(st + 2 * a_tile, st + 2 * a_tile + b_tile, boxes_b);
+    fence_proxy_async();
+    mbar_arrive(SPLIT(slot));
+  }
+  if (warp < 4) {
+    mbar_wait(DONE, 0);
+    tc_fence_after();
+    // ---- epilogue: thread = one dW row (TMEM lane); the partial tile goes to ws[z][tile_m][tile_n][128][bn]
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* wrow = p.ws + ((((size_t)blockIdx.z * gridDim.x + blockIdx.x) * gridDim.y + blockIdx.y) * W3_BM + warp * 32 + lane) * bn;
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(wrow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+// dW[m][n] += sum over the active splits of the partial tiles, in split order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* dW, long long lddw, int N, int K, int bn,
+                                    int tiles_m, int tiles_n, int nsplit, int rows_cap, const int* rows_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  int rows = rows_cap;
+  if (rows_dev) rows = min(rows, *rows_dev);
+  int kt0, kt1, active;
+  w3_range(rows, nsplit, 0, kt0, kt1, active);
+  if (rows <= 0) return;
+  const int m = i / K, n = i - m * K;
+  const int bx = m / W3_BM, by = n / bn;
+  const size_t tile = (size_t)W3_BM * bn;
+  const float* src = ws + ((size_t)bx * tiles_n + by) * tile + (size_t)(m - bx * W3_BM) * bn + (n - by * bn);
+  const size_t zstride = (size_t)tiles_m * tiles_n * tile;
+  float acc = 0.f;
+  for (int z = 0; z < active; ++z) acc += src[(size_t)z * zstride];
+  dW[(long long)m * lddw + n] += acc;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -220,7 +422,8 @@ EncodeTiledFn encode_tiled3() {
   }
   return fn;
 }
-bool make_map3(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+bool make_map3(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+               CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_tiled3();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -228,7 +431,7 @@ bool make_map3(CUtensorMap* map, const float* base, long long rows, long long co
   cuuint32_t box[2] = {(cuuint32_t)X3_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -282,6 +485,64 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   }
   dim3 grid(avl_div_up(M, X3_BM), avl_div_up(N, p.bn));
   tc_gemm_3x_kernel<<<grid, X3_THREADS, smem, s>>>(ta, tbh, tbl, p);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+namespace {
+constexpr size_t W3_WS_FLOATS = 8u << 20;  // 32 MB of partial tiles
+float* g_w3_ws = nullptr;
+int g_w3_lbo = 4096, g_w3_sbo = 512;
+}  // namespace
+
+AVL_API int avl_set_wgrad_desc(int lbo_bytes, int sbo_bytes) {  // diagnostic: descriptor strides of the MN-major tiles
+  g_w3_lbo = lbo_bytes;
+  g_w3_sbo = sbo_bytes;
+  return AVL_OK;
+}
+
+// dW[N, K] += dY[rows, N]^T X[rows, K], fp32-accurate (3xTF32) on tcgen05; rows_dev = optional device row count.
+// Returns AVL_ERR_UNSUPPORTED (nothing launched) when the shape / alignment is outside the kernel or the path is off.
+AVL_API int avl_tc_wgrad_3x(const float* dY, long long ldy, const float* X, long long ldx, float* dW, long long lddw,
+                            int rows, int N, int K, const int* rows_dev, void* stream) {
+  if (!g_x3_on) return AVL_ERR_UNSUPPORTED;
+  if (rows < 1 || N < 1 || K < 1 || !dY || !X || !dW) return AVL_ERR_ARG;
+  if (((uintptr_t)dY & 15) || ((uintptr_t)X & 15) || (ldy & 3) || (ldx & 3)) return AVL_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_w3_ws) AVL_CUDA_CHECK(cudaMalloc(&g_w3_ws, W3_WS_FLOATS * sizeof(float)));
+  W3Args p = {};
+  p.ws = g_w3_ws; p.rows = rows; p.N = N; p.K = K; p.rows_dev = rows_dev;
+  p.lbo = (uint32_t)g_w3_lbo; p.sbo = (uint32_t)g_w3_sbo;
+  const int n16 = (K + 15) / 16 * 16;
+  p.bn = n16 < 256 ? n16 : 256;
+  if (n16 > 256)
+    for (int bn = 256; bn >= 64; bn -= 16)
+      if (n16 % bn == 0) { p.bn = bn; break; }
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const int tiles_m = avl_div_up(N, W3_BM), tiles_n = avl_div_up(K, p.bn);
+  const size_t tile_floats = (size_t)tiles_m * tiles_n * W3_BM * p.bn;
+  int splits = avl_num_sms() / (tiles_m * tiles_n);
+  const int max_by_rows = avl_div_up(rows, 8 * W3_BK);
+  if (splits > max_by_rows) splits = max_by_rows;
+  if ((size_t)splits * tile_floats > W3_WS_FLOATS) splits = (int)(W3_WS_FLOATS / tile_floats);
+  if (splits < 1) return AVL_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb;
+  if (!make_map3(&ta, dY, rows, N, ldy, W3_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map3(&tb, X, rows, K, ldx, W3_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return AVL_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)W3_STAGES * (2 * (W3_BM / 32) + 2 * (size_t)((p.bn + 31) / 32)) * W3_BOX;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(tiles_m, tiles_n, splits);
+  tc_wgrad_3x_kernel<<<grid, W3_THREADS, smem, s>>>(ta, tb, p);
+  AVL_LAUNCH_CHECK();
+  wgrad_reduce_kernel<<<avl_div_up((long long)N * K, 256), 256, 0, s>>>(g_w3_ws, dW, lddw, N, K, p.bn, tiles_m, tiles_n,
+                                                                       splits, rows, rows_dev);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

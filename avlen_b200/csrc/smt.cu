@@ -209,14 +209,20 @@ static bool tc_ok(const float* X, long long ldx, const float* W, int rows, int K
 AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long long ldb, int b_transposed, float* C,
                            long long ldc, int M, int N, int K, const float* bias, const float* residual, long long ldr,
                            int relu, const int* m_dev, void* stream);
+AVL_API int avl_tc_wgrad_3x(const float* dY, long long ldy, const float* X, long long ldx, float* dW, long long lddw,
+                            int rows, int N, int K, const int* rows_dev, void* stream);
 static bool x3_ok(const float* X, long long ldx, int rows, int K) {
   return avl_get_tensor_cores() >= 1 && rows >= 512 && (K & 3) == 0 && (ldx & 3) == 0 && ((uintptr_t)X & 15) == 0;
 }
+static int avl_get_tensor_cores_or0() { return avl_get_tensor_cores(); }
 #else
+static int avl_get_tensor_cores_or0() { return 0; }
 static bool tc_ok(const float*, long long, const float*, int, int) { return false; }
 static bool x3_ok(const float*, long long, int, int) { return false; }
 static int avl_tc_gemm_3x(const float*, long long, const float*, long long, int, float*, long long, int, int, int,
                           const float*, const float*, long long, int, const int*, void*) { return AVL_ERR_UNSUPPORTED; }
+static int avl_tc_wgrad_3x(const float*, long long, const float*, long long, float*, long long, int, int, int, const int*,
+                           void*) { return AVL_ERR_UNSUPPORTED; }
 static int avl_tc_gemm(const float*, long long, const float*, float*, long long, int, int, int, const float*,
                        const float*, const float*, long long, int, const int*, void*) { return 0; }
 #endif
@@ -270,7 +276,13 @@ static void lin_bwd_x(Launcher& L, const float* dY, long long ldy, const float* 
 // dW[N, K] += dY[rows, N]^T X[rows, K] ; db[N] += colsum(dY)
 static void lin_bwd_w(Launcher& L, const float* dY, long long ldy, const float* X, long long ldx, float* dW,
                       long long lddw, float* db, int rows, int N, int K, const int* rows_dev) {
-  if (dW) {
+  bool done_w = false;
+  if (dW && avl_get_tensor_cores_or0() >= 1 && rows >= 2048 && N >= 32) {  // tcgen05 3xTF32, MN-major operands straight from TMA
+    int rc = avl_tc_wgrad_3x(dY, ldy, X, ldx, dW, lddw, rows, N, K, rows_dev, L.s);
+    if (rc == AVL_OK) done_w = true;
+    else if (rc != AVL_ERR_UNSUPPORTED && !L.err) { L.err = rc; return; }
+  }
+  if (dW && !done_w) {
     GemmEpilogue ep = make_ep(nullptr, 0, nullptr);
     ep.accumulate = 1;
     ep.k_dev = rows_dev;

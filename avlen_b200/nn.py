@@ -40,6 +40,8 @@ _lib.register({
     "avl_set_tc_tma": [I],
     "avl_set_tc_3xtf32": [I],
     "avl_tc_gemm_3x": [P, L, P, L, I, P, L, I, I, I, P, P, L, I, P, P],
+    "avl_tc_wgrad_3x": [P, L, P, L, P, L, I, I, I, P, P],
+    "avl_set_wgrad_desc": [I, I],
     "avl_resnet18_param_count": [],
     "avl_resnet18_workspace_bytes": [I, I, I, P],
     "avl_resnet18_forward": [P, I, I, I, I, P, F, P, P, L, I, P, P],

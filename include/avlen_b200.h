@@ -163,6 +163,12 @@ int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long long ldb,
                    long long ldc, int M, int N, int K, const float* bias, const float* residual, long long ldr,
                    int relu, const int* m_dev, void* stream);
 int avl_set_tc_3xtf32(int on);   /* returns old */
+/* Weight gradient of a Linear, dW[N,K] += dY[rows,N]^T X[rows,K] (reference: autograd of F.linear, fp32), 3xTF32 on
+ * tcgen05 with both operands MN-major straight from TMA; the reduction over rows is split over the grid and summed in a
+ * fixed order (deterministic).  rows_dev = optional device-side row count.  -2: shape / alignment not covered.    */
+int avl_tc_wgrad_3x(const float* dY, long long ldy, const float* X, long long ldx, float* dW, long long lddw, int rows,
+                    int N, int K, const int* rows_dev, void* stream);
+int avl_set_wgrad_desc(int lbo_bytes, int sbo_bytes);   /* diagnostic */
 int avl_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                       float* stats, int rows, int cols, void* stream);
 int avl_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy,

@@ -182,3 +182,41 @@ def test_tc_gemm_3xtf32_is_fp32_accurate(M, N, K_, bt):
     ref2 = (x.double() @ w.double().t() + res.double()).float()
     assert rel(out2[: M // 2 + 3], ref2[: M // 2 + 3]) < TOL_3X
     assert torch.equal(out2[M // 2 + 3:], res[M // 2 + 3:])
+
+
+@pytest.mark.parametrize("R,N,K_", [(5000, 256, 276), (2048, 768, 256), (3001, 32, 256), (9000, 256, 8), (4097, 144, 100),
+                                    (20000, 512, 256)])
+def test_tc_wgrad_3xtf32_is_fp32_accurate(R, N, K_):
+    """dW += dY^T X on tcgen05 with MN-major operands (smt.cu lin_bwd_w): fp32-accurate, accumulates into dW, honours
+    the device-side row count (rows beyond it hold stale data, here NaN) and is run-to-run deterministic."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401
+    g = torch.Generator().manual_seed(R + N + K_)
+    dy = (torch.randn(R, N, generator=g) * torch.exp(torch.randn(R, 1, generator=g))).cuda()
+    ldx = (K_ + 3) // 4 * 4
+    xfull = torch.randn(R, ldx, generator=g).cuda()
+    x = xfull[:, :K_]
+    dw0 = torch.randn(N, K_, generator=g).cuda()
+    ref = (dw0.double() + dy.double().t() @ x.double()).float()
+    lib = _lib.lib()
+    dw = dw0.clone()
+    rc = lib.avl_tc_wgrad_3x(dy.data_ptr(), N, xfull.data_ptr(), ldx, dw.data_ptr(), K_, R, N, K_, None, _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert rel(dw, ref) < TOL_3X
+    live = R // 3 + 5
+    dy2, x2 = dy.clone(), xfull.clone()
+    dy2[live:] = float("nan")
+    x2[live:] = float("nan")
+    rd = torch.tensor([live], dtype=torch.int32, device="cuda")
+    ref2 = (dw0.double() + dy[:live].double().t() @ x[:live].double()).float()
+    outs = []
+    for _ in range(2):
+        dw2 = dw0.clone()
+        rc = lib.avl_tc_wgrad_3x(dy2.data_ptr(), N, x2.data_ptr(), ldx, dw2.data_ptr(), K_, R, N, K_, rd.data_ptr(),
+                                 _lib.stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert rel(dw2, ref2) < TOL_3X
+        outs.append(dw2)
+    assert torch.equal(outs[0], outs[1])
