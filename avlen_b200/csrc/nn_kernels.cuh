@@ -285,6 +285,43 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, const i
   atomicAdd(&out[c], s);
 }
 
+// Same for cols % 4 == 0 and 16-byte aligned rows: 16-byte loads, 4 independent rows in flight per thread, 8 row lanes
+// per CTA folded through shared memory (one atomic per column and CTA).  blockDim = (32, 8): 128 columns per CTA.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ x, long long ld, const int* rows_dev,
+                                                      int rows_max, int cols, float* out) {
+  __shared__ float4 red[8][32];
+  const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b2 = a, c2 = a, d2 = a;
+  if (c < cols) {
+    const int step = gridDim.y * 8;
+    int r = blockIdx.y * 8 + ty;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + (size_t)(r + step) * ld + c);
+      const float4 v2 = *reinterpret_cast<const float4*>(x + (size_t)(r + 2 * step) * ld + c);
+      const float4 v3 = *reinterpret_cast<const float4*>(x + (size_t)(r + 3 * step) * ld + c);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+      b2.x += v1.x; b2.y += v1.y; b2.z += v1.z; b2.w += v1.w;
+      c2.x += v2.x; c2.y += v2.y; c2.z += v2.z; c2.w += v2.w;
+      d2.x += v3.x; d2.y += v3.y; d2.z += v3.z; d2.w += v3.w;
+    }
+    for (; r < rows; r += step) {
+      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+    }
+    a.x += b2.x + c2.x + d2.x; a.y += b2.y + c2.y + d2.y; a.z += b2.z + c2.z + d2.z; a.w += b2.w + c2.w + d2.w;
+  }
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float4 t = red[0][tx];
+    for (int k = 1; k < 8; ++k) { t.x += red[k][tx].x; t.y += red[k][tx].y; t.z += red[k][tx].z; t.w += red[k][tx].w; }
+    atomicAdd(&out[c], t.x); atomicAdd(&out[c + 1], t.y); atomicAdd(&out[c + 2], t.z); atomicAdd(&out[c + 3], t.w);
+  }
+}
+
 // dx = dy * (y > 0) in place on dy (ReLU backward given the forward output)
 __global__ void relu_bwd_kernel(float* dy, const float* __restrict__ y, const int* rows_dev, long long rows_max,
                                 int cols) {
@@ -295,10 +332,20 @@ __global__ void relu_bwd_kernel(float* dy, const float* __restrict__ y, const in
 
 // --------------------------------------------------------------------------- varlen self-attention
 // qkv: [R, 3*D] packed rows (q | k | v), heads of 32; off[b]..off[b+1] are sample b's rows.
-// One CTA per (sample, head).  Scores never leave shared memory; lse is saved for the backward.
-constexpr int ATT_HD = 32;      // head dim
-constexpr int ATT_MAXV = 320;   // max tokens per sample
-constexpr int ATT_WARPS = 8;
+// One CTA per (sample, head).  Scores never leave registers; lse is saved for the backward.
+//
+// Register-tiled: the "owner" rows live in registers (forward: one query per lane; backward: one key / one query per
+// lane PAIR, each lane holding half of the 32 head channels), the other side is streamed from shared memory with
+// warp-broadcast 16-byte loads, so one LDS.128 feeds 4-16 FMAs (the first version did one 4-byte LDS per FMA and was
+// bound by the shared-memory pipe at ~1/8 of the FMA rate).  Rows are stored as 8 chunks of 16 bytes, chunk c of
+// row j at slot c ^ (j & 7): conflict-free both for the per-lane row loads and for the staging stores.
+constexpr int ATT_HD = 32;       // head dim
+constexpr int ATT_MAXV = 320;    // max tokens per sample
+constexpr int ATT_WARPS = 5;     // forward: 32 queries per warp
+constexpr int ATT_BWD_WARPS = 8; // backward: units of 16 keys / 16 queries, two lanes per owner row
+
+__device__ __forceinline__ int att_slot(int row, int c) { return row * ATT_HD + ((c ^ (row & 7)) << 2); }
+__device__ __forceinline__ float4 att_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, float* out, float* lse, int D,
@@ -307,127 +354,222 @@ attn_self_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off,
   AVL_DYN_SMEM(smem_raw);
   const int b = blockIdx.x, h = blockIdx.y;
   const int r0 = off[b], V = min(off[b + 1] - r0, vcap);
-  float* Ks = reinterpret_cast<float*>(smem_raw);   // [V][33]
-  float* Vs = Ks + vcap * 33;                       // [V][33]
-  float* Ps = Vs + vcap * 33;                       // [warps][vcap]
-  float* Qs = Ps + ATT_WARPS * vcap;                // [warps][32]
+  float* Ks = reinterpret_cast<float*>(smem_raw);   // [V][32] swizzled chunks
+  float* Vs = Ks + vcap * ATT_HD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = 3 * D;
-  for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
-    int j = i >> 5, d = i & 31;
-    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + d;
-    Ks[j * 33 + d] = row[D];
-    Vs[j * 33 + d] = row[2 * D];
+  for (int t = threadIdx.x; t < V * 8; t += blockDim.x) {
+    const int j = t >> 3, c = t & 7;
+    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + 4 * c;
+    *reinterpret_cast<float4*>(Ks + att_slot(j, c)) = att_ld4(row + D);
+    *reinterpret_cast<float4*>(Vs + att_slot(j, c)) = att_ld4(row + 2 * D);
   }
   __syncthreads();
-  float* ps = Ps + warp * vcap;
-  float* qs = Qs + warp * 32;
-  for (int i = warp; i < V; i += ATT_WARPS) {
-    qs[lane] = qkv[(size_t)(r0 + i) * ld + h * ATT_HD + lane] * scale;
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int j = lane; j < V; j += 32) {
-      float s = 0.f;
+  for (int qb = warp; qb * 32 < V; qb += ATT_WARPS) {
+    const int i = qb * 32 + lane;
+    const bool valid = i < V;
+    const float* qrow = qkv + (size_t)(r0 + (valid ? i : V - 1)) * ld + h * ATT_HD;
+    float q[ATT_HD], o[ATT_HD];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) s = fmaf(qs[d], Ks[j * 33 + d], s);
-      ps[j] = s;
-      mx = fmaxf(mx, s);
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = att_ld4(qrow + 4 * c);
+      q[4 * c] = v.x * scale; q[4 * c + 1] = v.y * scale; q[4 * c + 2] = v.z * scale; q[4 * c + 3] = v.w * scale;
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < V; j += 32) {
-      float p = __expf(ps[j] - mx);
-      ps[j] = p;
-      sum += p;
+#pragma unroll
+    for (int d = 0; d < ATT_HD; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j0 = 0; j0 < V; j0 += 8) {   // online softmax over chunks of 8 keys (one rescale of o per chunk)
+      const int nj = min(8, V - j0);
+      float s[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        s[jj] = -INFINITY;
+        if (jj < nj) {
+          const int j = j0 + jj, sw = j & 7;
+          const float* kr = Ks + j * ATT_HD;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 kv = att_ld4(kr + ((c ^ sw) << 2));
+            a0 = fmaf(q[4 * c], kv.x, a0); a1 = fmaf(q[4 * c + 1], kv.y, a1);
+            a2 = fmaf(q[4 * c + 2], kv.z, a2); a3 = fmaf(q[4 * c + 3], kv.w, a3);
+          }
+          s[jj] = (a0 + a1) + (a2 + a3);
+        }
+      }
+      float mn = m;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) mn = fmaxf(mn, s[jj]);
+      const float alpha = __expf(m - mn);   // 0 on the first chunk (m = -inf)
+      m = mn;
+      l *= alpha;
+#pragma unroll
+      for (int d = 0; d < ATT_HD; ++d) o[d] *= alpha;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (jj < nj) {
+          const int j = j0 + jj, sw = j & 7;
+          const float* vr = Vs + j * ATT_HD;
+          const float pj = __expf(s[jj] - mn);
+          l += pj;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 vv = att_ld4(vr + ((c ^ sw) << 2));
+            o[4 * c] = fmaf(pj, vv.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, vv.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(pj, vv.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, vv.w, o[4 * c + 3]);
+          }
+        }
+      }
     }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float o = 0.f;
-    for (int j = 0; j < V; ++j) o = fmaf(ps[j], Vs[j * 33 + lane], o);
-    out[(size_t)(r0 + i) * D + h * ATT_HD + lane] = o / sum;
-    if (lane == 0 && lse) lse[(size_t)(r0 + i) * (D / ATT_HD) + h] = mx + __logf(sum);
-    __syncwarp();
+    if (valid) {
+      const float inv = 1.f / l;
+      float* orow = out + (size_t)(r0 + i) * D + h * ATT_HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(orow + 4 * c) =
+            make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+      if (lse) lse[(size_t)(r0 + i) * (D / ATT_HD) + h] = m + __logf(l);
+    }
   }
 }
 
-// Backward with recomputation.  dqkv receives (dq | dk | dv) rows.
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+// Backward with recomputation.  dqkv receives (dq | dk | dv) rows.  Every output element is produced by exactly one
+// lane in a fixed summation order (deterministic).
+__global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
 attn_self_bwd_kernel(const float* __restrict__ qkv, const int* __restrict__ off, const float* __restrict__ out,
                      const float* __restrict__ lse, const float* __restrict__ dout, float* dqkv, int D, float scale,
                      int vcap) {
   AVL_DYN_SMEM(smem_raw);
   const int b = blockIdx.x, h = blockIdx.y;
   const int r0 = off[b], V = min(off[b + 1] - r0, vcap);
-  float* Qs = reinterpret_cast<float*>(smem_raw);  // [V][33] (pre-scaled)
-  float* Ks = Qs + vcap * 33;
-  float* Vs = Ks + vcap * 33;
-  float* Gs = Vs + vcap * 33;                      // dO
-  float* Ls = Gs + vcap * 33;                      // lse [V]
+  float* Qs = reinterpret_cast<float*>(smem_raw);  // [V][32] swizzled chunks, pre-scaled
+  float* Ks = Qs + vcap * ATT_HD;
+  float* Vs = Ks + vcap * ATT_HD;
+  float* Gs = Vs + vcap * ATT_HD;                  // dO
+  float* Ls = Gs + vcap * ATT_HD;                  // lse [V]
   float* Ds = Ls + vcap;                           // D_i = dO_i . O_i  [V]
-  float* Wa = Ds + vcap;                           // [warps][vcap]
-  float* Wb = Wa + ATT_WARPS * vcap;               // [warps][vcap]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = 3 * D, H = D / ATT_HD;
-  for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
-    int j = i >> 5, d = i & 31;
-    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + d;
-    Qs[j * 33 + d] = row[0] * scale;
-    Ks[j * 33 + d] = row[D];
-    Vs[j * 33 + d] = row[2 * D];
-    Gs[j * 33 + d] = dout[(size_t)(r0 + j) * D + h * ATT_HD + d];
-  }
-  for (int i = threadIdx.x; i < V; i += blockDim.x) Ls[i] = lse[(size_t)(r0 + i) * H + h];
-  __syncthreads();
-  // D_i
-  for (int i = warp; i < V; i += ATT_WARPS) {
-    float t = Gs[i * 33 + lane] * out[(size_t)(r0 + i) * D + h * ATT_HD + lane];
-    t = warp_sum(t);
-    if (lane == 0) Ds[i] = t;
-  }
-  __syncthreads();
-  float* wa = Wa + warp * vcap;
-  float* wb = Wb + warp * vcap;
-  // pass 1: dQ_i = scale * sum_j dS_ij K_j
-  for (int i = warp; i < V; i += ATT_WARPS) {
-    const float li = Ls[i], di = Ds[i];
-    for (int j = lane; j < V; j += 32) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        s = fmaf(Qs[i * 33 + d], Ks[j * 33 + d], s);
-        dp = fmaf(Gs[i * 33 + d], Vs[j * 33 + d], dp);
+  for (int t = threadIdx.x; t < ((V * 8 + 31) & ~31); t += blockDim.x) {   // warp-uniform trip count (shuffles below)
+    const int j = min(t >> 3, V - 1), c = t & 7;
+    const float* row = qkv + (size_t)(r0 + j) * ld + h * ATT_HD + 4 * c;
+    float4 qv = att_ld4(row);
+    qv.x *= scale; qv.y *= scale; qv.z *= scale; qv.w *= scale;
+    const float4 gv = att_ld4(dout + (size_t)(r0 + j) * D + h * ATT_HD + 4 * c);
+    const float4 ov = att_ld4(out + (size_t)(r0 + j) * D + h * ATT_HD + 4 * c);
+    float dsum = gv.x * ov.x + gv.y * ov.y + gv.z * ov.z + gv.w * ov.w;
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    if (t < V * 8) {
+      *reinterpret_cast<float4*>(Qs + att_slot(j, c)) = qv;
+      *reinterpret_cast<float4*>(Ks + att_slot(j, c)) = att_ld4(row + D);
+      *reinterpret_cast<float4*>(Vs + att_slot(j, c)) = att_ld4(row + 2 * D);
+      *reinterpret_cast<float4*>(Gs + att_slot(j, c)) = gv;
+      if (c == 0) {
+        Ds[j] = dsum;
+        Ls[j] = lse[(size_t)(r0 + j) * H + h];
       }
-      float p = __expf(s - li);
-      wa[j] = p * (dp - di);
     }
-    __syncwarp();
-    float dq = 0.f;
-    for (int j = 0; j < V; ++j) dq = fmaf(wa[j], Ks[j * 33 + lane], dq);
-    dqkv[(size_t)(r0 + i) * ld + h * ATT_HD + lane] = dq * scale;
-    __syncwarp();
   }
-  // pass 2: dK_j = sum_i dS_ij Qs_i (Qs already carries the scale), dV_j = sum_i P_ij dO_i
-  for (int j = warp; j < V; j += ATT_WARPS) {
-    for (int i = lane; i < V; i += 32) {
-      float s = 0.f, dp = 0.f;
+  __syncthreads();
+  const int nb = (V + 15) >> 4;            // units of 16 owner rows
+  const int half = lane & 1, c0 = half * 4;  // this lane's 16 head channels = chunks c0 .. c0+3
+  for (int u = warp; u < 2 * nb; u += ATT_BWD_WARPS) {
+    if (u < nb) {
+      // ---- owner = key j: dK_j = sum_i dS_ij Qs_i (Qs carries the scale), dV_j = sum_i P_ij dO_i
+      const int j = u * 16 + (lane >> 1);
+      const bool valid = j < V;
+      const int jr = valid ? j : V - 1;
+      float k[16], v[16], dk[16], dv[16];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        s = fmaf(Qs[i * 33 + d], Ks[j * 33 + d], s);
-        dp = fmaf(Gs[i * 33 + d], Vs[j * 33 + d], dp);
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 kv = att_ld4(Ks + att_slot(jr, c0 + cc)), vv = att_ld4(Vs + att_slot(jr, c0 + cc));
+        k[4 * cc] = kv.x; k[4 * cc + 1] = kv.y; k[4 * cc + 2] = kv.z; k[4 * cc + 3] = kv.w;
+        v[4 * cc] = vv.x; v[4 * cc + 1] = vv.y; v[4 * cc + 2] = vv.z; v[4 * cc + 3] = vv.w;
       }
-      float p = __expf(s - Ls[i]);
-      wa[i] = p;
-      wb[i] = p * (dp - Ds[i]);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+      for (int i = 0; i < V; ++i) {
+        const int sw = i & 7;
+        float qr[16], gr[16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 qv = att_ld4(Qs + i * ATT_HD + (((c0 + cc) ^ sw) << 2));
+          const float4 gv = att_ld4(Gs + i * ATT_HD + (((c0 + cc) ^ sw) << 2));
+          qr[4 * cc] = qv.x; qr[4 * cc + 1] = qv.y; qr[4 * cc + 2] = qv.z; qr[4 * cc + 3] = qv.w;
+          gr[4 * cc] = gv.x; gr[4 * cc + 1] = gv.y; gr[4 * cc + 2] = gv.z; gr[4 * cc + 3] = gv.w;
+        }
+        float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; d += 2) {
+          s0 = fmaf(qr[d], k[d], s0); s1 = fmaf(qr[d + 1], k[d + 1], s1);
+          p0 = fmaf(gr[d], v[d], p0); p1 = fmaf(gr[d + 1], v[d + 1], p1);
+        }
+        float sv = s0 + s1, dp = p0 + p1;
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+        dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+        const float p = __expf(sv - Ls[i]);
+        const float ds = p * (dp - Ds[i]);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          dv[d] = fmaf(p, gr[d], dv[d]);
+          dk[d] = fmaf(ds, qr[d], dk[d]);
+        }
+      }
+      if (valid) {
+        float* krow = dqkv + (size_t)(r0 + j) * ld + D + h * ATT_HD + half * 16;
+        float* vrow = krow + D;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          *reinterpret_cast<float4*>(krow + 4 * cc) = make_float4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
+          *reinterpret_cast<float4*>(vrow + 4 * cc) = make_float4(dv[4 * cc], dv[4 * cc + 1], dv[4 * cc + 2], dv[4 * cc + 3]);
+        }
+      }
+    } else {
+      // ---- owner = query i: dQ_i = scale * sum_j dS_ij K_j
+      const int i = (u - nb) * 16 + (lane >> 1);
+      const bool valid = i < V;
+      const int ir = valid ? i : V - 1;
+      float q[16], g[16], dq[16];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 qv = att_ld4(Qs + att_slot(ir, c0 + cc)), gv = att_ld4(Gs + att_slot(ir, c0 + cc));
+        q[4 * cc] = qv.x; q[4 * cc + 1] = qv.y; q[4 * cc + 2] = qv.z; q[4 * cc + 3] = qv.w;
+        g[4 * cc] = gv.x; g[4 * cc + 1] = gv.y; g[4 * cc + 2] = gv.z; g[4 * cc + 3] = gv.w;
+      }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) dq[d] = 0.f;
+      const float li = Ls[ir], di = Ds[ir];
+      for (int j = 0; j < V; ++j) {
+        const int sw = j & 7;
+        float kr[16];
+        float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 kv = att_ld4(Ks + j * ATT_HD + (((c0 + cc) ^ sw) << 2));
+          const float4 vv = att_ld4(Vs + j * ATT_HD + (((c0 + cc) ^ sw) << 2));
+          kr[4 * cc] = kv.x; kr[4 * cc + 1] = kv.y; kr[4 * cc + 2] = kv.z; kr[4 * cc + 3] = kv.w;
+          s0 = fmaf(q[4 * cc], kv.x, s0); s1 = fmaf(q[4 * cc + 1], kv.y, s1);
+          s0 = fmaf(q[4 * cc + 2], kv.z, s0); s1 = fmaf(q[4 * cc + 3], kv.w, s1);
+          p0 = fmaf(g[4 * cc], vv.x, p0); p1 = fmaf(g[4 * cc + 1], vv.y, p1);
+          p0 = fmaf(g[4 * cc + 2], vv.z, p0); p1 = fmaf(g[4 * cc + 3], vv.w, p1);
+        }
+        float sv = s0 + s1, dp = p0 + p1;
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+        dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+        const float ds = __expf(sv - li) * (dp - di);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) dq[d] = fmaf(ds, kr[d], dq[d]);
+      }
+      if (valid) {
+        float* qrow = dqkv + (size_t)(r0 + i) * ld + h * ATT_HD + half * 16;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          *reinterpret_cast<float4*>(qrow + 4 * cc) = make_float4(dq[4 * cc] * scale, dq[4 * cc + 1] * scale,
+                                                                  dq[4 * cc + 2] * scale, dq[4 * cc + 3] * scale);
+      }
     }
-    __syncwarp();
-    float dk = 0.f, dv = 0.f;
-    for (int i = 0; i < V; ++i) {
-      dk = fmaf(wb[i], Qs[i * 33 + lane], dk);
-      dv = fmaf(wa[i], Gs[i * 33 + lane], dv);
-    }
-    dqkv[(size_t)(r0 + j) * ld + D + h * ATT_HD + lane] = dk;
-    dqkv[(size_t)(r0 + j) * ld + 2 * D + h * ATT_HD + lane] = dv;
-    __syncwarp();
   }
 }
 

@@ -296,7 +296,11 @@ static void lin_bwd_w(Launcher& L, const float* dY, long long ldy, const float* 
     int gy = rows / 64;
     if (gy < 1) gy = 1;
     if (gy > 256) gy = 256;
-    AVL_LAUNCH(colsum_kernel, dim3(avl_div_up(N, 128), gy), 128, 0, L.s, dY, ldy, rows_dev, rows, N, db);
+    if ((N & 3) == 0 && (ldy & 3) == 0 && ((uintptr_t)dY & 15) == 0 && rows >= 512) {
+      AVL_LAUNCH(colsum4_kernel, dim3(avl_div_up(N, 128), gy), 256, 0, L.s, dY, ldy, rows_dev, rows, N, db);
+    } else {
+      AVL_LAUNCH(colsum_kernel, dim3(avl_div_up(N, 128), gy), 128, 0, L.s, dY, ldy, rows_dev, rows, N, db);
+    }
     L.check();
   }
 }
@@ -327,8 +331,8 @@ static void relu_bwd(Launcher& L, float* dy, const float* y, const int* rows_dev
   L.check();
 }
 
-static size_t attn_fwd_smem(int vcap) { return (size_t)(2 * vcap * 33 + ATT_WARPS * vcap + ATT_WARPS * 32) * sizeof(float); }
-static size_t attn_bwd_smem(int vcap) { return (size_t)(4 * vcap * 33 + 2 * vcap + 2 * ATT_WARPS * vcap) * sizeof(float); }
+static size_t attn_fwd_smem(int vcap) { return (size_t)(2 * vcap * ATT_HD) * sizeof(float); }
+static size_t attn_bwd_smem(int vcap) { return (size_t)(4 * vcap * ATT_HD + 2 * vcap) * sizeof(float); }
 static const size_t kAttnFwdSmem = attn_fwd_smem(ATT_MAXV);
 static const size_t kAttnBwdSmem = attn_bwd_smem(ATT_MAXV);
 static int attn_vcap(int rows_cap, int B) {  // per-sample token bound implied by the caller's row capacity
@@ -481,7 +485,7 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
   // GC = grad wrt (X0 + AO)
   lin_bwd_w(L, t.GC, D, t.ATT, D, gp(G, TP_ENC_OUT_W), D, gp(G, TP_ENC_OUT_B), Rcap, D, D, total);
   lin_bwd_x(L, t.GC, D, P[TP_ENC_OUT_W], D, t.GB, D, Rcap, D, D, 0, total, t.WT);  // GB = gATT
-  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_WARPS * 32, attn_bwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale, vcap);
+  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_BWD_WARPS * 32, attn_bwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale, vcap);
   L.check();
   lin_bwd_w(L, t.GQKV, 3 * D, X0, D, gp(G, TP_ENC_IN_W), D, gp(G, TP_ENC_IN_B), Rcap, 3 * D, D, total);
   lin_bwd_x(L, t.GQKV, 3 * D, P[TP_ENC_IN_W], D, t.GC, D, Rcap, 3 * D, D, 1, total, t.WT);  // GC = gX0
@@ -570,7 +574,7 @@ AVL_API int avl_attn_self_bwd(const float* qkv, const int* off, int B, int D, co
   if (!qkv || !off || !out || !lse || !dout || !dqkv) return AVL_ERR_ARG;
   int rc = ensure_attn_attrs();
   if (rc) return rc;
-  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, D / 32), ATT_WARPS * 32, kAttnBwdSmem, (cudaStream_t)stream, 
+  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, D / 32), ATT_BWD_WARPS * 32, kAttnBwdSmem, (cudaStream_t)stream, 
       qkv, off, out, lse, dout, dqkv, D, 1.0f / sqrtf(32.f), ATT_MAXV);
   AVL_LAUNCH_CHECK();
   return AVL_OK;

@@ -17,8 +17,12 @@ act = torch.randint(0, 4, (n, 1))
 v_r, lp_r, ent_r, _, _ = o.evaluate_actions(obs, h, pa, mk, act, mem, masks)
 (v_r.sum() + 2 * lp_r.sum() + 0.5 * ent_r).backward()
 og = dict(o.named_parameters())
-for tc in (False, True):
+from avlen_b200 import _lib
+cosf = lambda a, b: float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+for tc, x3 in ((False, 1), (True, 1), (True, 0)):
     K.set_tensor_cores(tc)
+    _lib.lib().avl_set_tc_3xtf32(x3)
+    print("=== 3xTF32 paths", x3)
     for q in p.parameters():
         q.grad = None
     v, lp, ent, _, _ = p.evaluate_actions(cu(obs), h.cuda(), pa.cuda(), mk.cuda(), act.cuda(), mem.cuda(), masks.cuda())
@@ -26,7 +30,7 @@ for tc in (False, True):
     print("TC", tc, "v rel", rel(v.detach().cpu(), v_r.detach()), "lp rel", rel(lp.detach().cpu(), lp_r.detach()))
     for k, q in p.named_parameters():
         if q.requires_grad and og[k].grad is not None:
-            print(f"  {k:70s} gmax={float(og[k].grad.abs().max()):.3e} rel={rel(q.grad.cpu(), og[k].grad):.3e}")
+            print(f"  {k:70s} gmax={float(og[k].grad.abs().max()):.3e} rel={rel(q.grad.cpu(), og[k].grad):.3e} cos={cosf(q.grad.cpu(), og[k].grad):.6f}")
 # raw GEMM error level
 g = torch.Generator().manual_seed(0)
 x = torch.randn(4096, 256, generator=g).cuda(); w = (torch.randn(256, 256, generator=g) / 16).cuda()
