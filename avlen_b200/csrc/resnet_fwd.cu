@@ -148,8 +148,32 @@ bool fill(Net& n, int N, int H, int W, int Cin, const int* cfg) {
   return true;
 }
 
-cudaEvent_t g_fork = nullptr, g_join = nullptr;
-cudaStream_t g_side = nullptr;
+// side stream + fork / join events PER CALLER STREAM: two pairs enqueued from two different streams (the visual
+// encoders of step s+1 on the main stream, the belief networks on the trainer's belief stream) must not serialise
+// on one shared side stream.
+struct Side {
+  cudaStream_t caller;
+  cudaStream_t side;
+  cudaEvent_t fork, join;
+};
+constexpr int MAX_SIDES = 8;
+Side g_sides[MAX_SIDES];
+int g_num_sides = 0;
+
+int side_for(cudaStream_t s, Side** out) {
+  for (int i = 0; i < g_num_sides; ++i)
+    if (g_sides[i].caller == s) { *out = &g_sides[i]; return AVL_OK; }
+  Side* sd = &g_sides[g_num_sides < MAX_SIDES ? g_num_sides : 0];  // more caller streams than slots: share slot 0
+  if (g_num_sides < MAX_SIDES) {
+    AVL_CUDA_CHECK(cudaStreamCreateWithFlags(&sd->side, cudaStreamNonBlocking));
+    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming));
+    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming));
+    sd->caller = s;
+    ++g_num_sides;
+  }
+  *out = sd;
+  return AVL_OK;
+}
 
 }  // namespace
 
@@ -188,17 +212,15 @@ AVL_API int avl_resnet18_forward_pair(const float* x0, const float* x1, int N, i
   if (!x0 || !x1 || !params0 || !params1 || !out0 || !out1 || !workspace0 || !workspace1) return AVL_ERR_ARG;
   a.eps = b.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!g_side) {
-    AVL_CUDA_CHECK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    AVL_CUDA_CHECK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-  }
-  AVL_CUDA_CHECK(cudaEventRecord(g_fork, s));
-  AVL_CUDA_CHECK(cudaStreamWaitEvent(g_side, g_fork, 0));
-  int rc1 = run(b, x1, params1, out1, ldo1, use_tc, static_cast<float*>(workspace1), g_side);
+  Side* sd = nullptr;
+  int rcs = side_for(s, &sd);
+  if (rcs) return rcs;
+  AVL_CUDA_CHECK(cudaEventRecord(sd->fork, s));
+  AVL_CUDA_CHECK(cudaStreamWaitEvent(sd->side, sd->fork, 0));
+  int rc1 = run(b, x1, params1, out1, ldo1, use_tc, static_cast<float*>(workspace1), sd->side);
   int rc0 = run(a, x0, params0, out0, ldo0, use_tc, static_cast<float*>(workspace0), s);
-  AVL_CUDA_CHECK(cudaEventRecord(g_join, g_side));
-  AVL_CUDA_CHECK(cudaStreamWaitEvent(s, g_join, 0));
+  AVL_CUDA_CHECK(cudaEventRecord(sd->join, sd->side));
+  AVL_CUDA_CHECK(cudaStreamWaitEvent(s, sd->join, 0));
   return rc0 ? rc0 : rc1;
 }
 #endif  // AVL_HOST_EMUL

@@ -16,6 +16,7 @@ import types
 import torch
 import torch.distributed as distrib
 
+from ... import nn as K
 from ...common import spaces
 from ...common.baseline_registry import baseline_registry
 from ...synth_env import SyntheticVectorEnv
@@ -35,7 +36,7 @@ def savi_config(**overrides):
                num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu", freeze_encoders=True,
                pretraining=False, use_label_belief=True, use_location_belief=True, online_training=True,
                sync_frac=0.6, distrib_backend="nccl", use_preemption=False, seed=1234, sampling_rate=16000,
-               host_buffers=False, has_distractor_sound=False)
+               host_buffers=False, has_distractor_sound=False, overlap_belief=True)
     cfg.update(overrides)
     return types.SimpleNamespace(**cfg)
 
@@ -125,6 +126,7 @@ class DDPPOTrainer(PPOTrainer):
                     break
         if store is not None:
             store.add("num_done", 1)
+        K.sync_pending()  # the last step's deferred belief update joins the main stream here
         return self.rollouts.step * self.envs.num_envs
 
     def train(self):

@@ -86,7 +86,7 @@ class ResNet18BN(nn.Module):
     def plan(self):
         if getattr(self, "_plan", None) is None:
             cfg = [1, 7, 2, 3, 1, 64, 128, 256, 512, 1, 1, self.fc.weight.shape[0]]
-            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors))
+            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors, self))
         return self._plan
 
     @torch.no_grad()

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import torch
 
+from ... import nn as K
 from ... import ops
 from .smt_state_encoder import IndexedMemory
 
@@ -169,6 +170,7 @@ class RolloutStorage:
         self.step = s + 1
 
     def after_update(self):
+        K.sync_pending()  # deferred belief update (ppo_trainer._belief_update_deferred)
         s = self.step
         for sensor in self.observations:
             self.observations[sensor][0].copy_(self.observations[sensor][s])
@@ -182,11 +184,13 @@ class RolloutStorage:
         self.step = 0
 
     def compute_returns(self, next_value, use_gae, gamma, tau):
+        K.sync_pending()  # deferred belief update (ppo_trainer._belief_update_deferred)
         ops.gae(self.rewards, self.value_preds, self.masks, next_value, self.returns, self.step, use_gae, gamma, tau)
 
     def recurrent_generator(self, advantages, num_mini_batch, perm=None):
         """Same 22-tuple as rollout_storage.py:784-810.  Observations and per-step tensors are gathered by env
         index; the external memories are ``IndexedMemory`` views (no copies)."""
+        K.sync_pending()  # deferred belief update (ppo_trainer._belief_update_deferred)
         num_processes = self.rewards.size(1)
         assert num_processes >= num_mini_batch, (
             "Trainer requires the number of processes ({}) to be greater than or equal to the number of trainer "

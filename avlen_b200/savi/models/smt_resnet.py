@@ -106,12 +106,12 @@ class CustomResNet(nn.Module):
             widths = [self.layer1[0].conv1.weight.shape[0], self.layer2[0].conv1.weight.shape[0],
                       self.layer3[0].conv1.weight.shape[0], self.layer4[0].conv1.weight.shape[0]]
             cfg = [0, 7, 1, 3, 0, *widths, self.groups, 0, self.fc.weight.shape[0]]
-            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors))
+            object.__setattr__(self, "_plan", K.ResNetPlan(cfg, self._plan_tensors, self))
         return self._plan
 
     def forward(self, x, out=None):
         """x: (N, H, W, C) NHWC float32.  Returns (N, num_classes) (optionally written into ``out``)."""
-        trainable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        trainable = torch.is_grad_enabled() and self.plan().any_requires_grad()
         if not trainable and not (torch.is_grad_enabled() and x.requires_grad):
             if out is None:
                 out = torch.empty((x.shape[0], self.fc.weight.shape[0]), device=x.device, dtype=torch.float32)

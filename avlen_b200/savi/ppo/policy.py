@@ -261,6 +261,7 @@ class AudioNavSMTNet(Net):
         return -1
 
     def _belief(self, observations, n, device):
+        K.sync_pending()  # the belief vectors may still be in flight on the trainer's belief stream (ppo_trainer.py)
         belief = torch.zeros((n, self._hidden_size), device=device)
         if self._use_label_belief:
             cb = observations[CATEGORY_BELIEF]

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import torch
 
+from ... import nn as K
+
 
 class PPOTrainer:
     def __init__(self, config=None):
@@ -36,11 +38,42 @@ class PPOTrainer:
                 running_episode_stats["count"] += 1 - masks
             current_episode_reward *= masks
         if self.belief_predictor is not None:  # :890-894: belief for the NEXT observation
-            self.belief_predictor.update(observations, dones)
+            if getattr(self.config, "overlap_belief", False):
+                observations = self._belief_update_deferred(rollouts, observations, dones)
+            else:
+                self.belief_predictor.update(observations, dones)
         rollouts.insert(observations, recurrent_hidden_states, actions, None, actions_log_probs, values, rewards, masks,
                         masks, external_memory_features, None, None, None, None, None, None, None, None, None, None,
                         None, None)
         return self.envs.num_envs
+
+    _BELIEF_KEYS = ("location_belief", "category_belief")
+
+    def _belief_update_deferred(self, rollouts, observations, dones):
+        """The two belief networks only feed the NEXT step's scene-memory transformer, and the next step's visual
+        encoders do not depend on them: enqueue the belief update (networks, belief filter, the copy of the two belief
+        vectors into storage slot step+1) on a side stream and let the consumer (``AudioNavSMTNet._belief``, storage
+        readers) wait for it with an event — four small-grid ResNet-18 chains share the GPU instead of two.  Same
+        kernels on the same data: results are identical to the in-order path.  Returns the observations the main
+        stream still has to insert."""
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_belief_stream", None)
+        if side is None:
+            side = self._belief_stream = torch.cuda.Stream()
+        side.wait_stream(main)
+        for v in observations.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(side)
+        if torch.is_tensor(dones) and dones.is_cuda:
+            dones.record_stream(side)
+        s = rollouts.step
+        with torch.cuda.stream(side):
+            self.belief_predictor.update(observations, dones)
+            for k in self._BELIEF_KEYS:
+                if k in observations and k in rollouts.observations:
+                    rollouts.observations[k][s + 1].copy_(observations[k])
+        K.defer_join(side)
+        return {k: v for k, v in observations.items() if k not in self._BELIEF_KEYS}
 
     def _update_agent(self, ppo_cfg, rollouts):
         """ppo_trainer.py:1045-1093: bootstrap value, GAE, PPO.update, after_update."""
