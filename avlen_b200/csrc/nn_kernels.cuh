@@ -274,6 +274,66 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------- skinny GEMM
+// C[M, N] (+)= act(A[M, K] B[N, K]^T + bias) for FEW rows (the decoder side of the scene-memory transformer and the
+// policy heads at rollout batch: M = number of envs).  The 128x64-tile kernel above runs such a problem on 4 CTAs
+// with a 16-step serial K loop (~30 us for 64 x 256 x 256); here a CTA owns 64 rows x SK_BN columns, so N / 4 CTAs
+// share the work, and the K loop moves 64-wide chunks through shared memory (A transposed, conflict-free).
+constexpr int SK_BM = 64, SK_BN = 4, SK_BK = 64, SK_THREADS = SK_BM * SK_BN;
+
+__global__ void __launch_bounds__(SK_THREADS)
+skinny_gemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* C,
+                   long long ldc, int M, int N, int K, const float* __restrict__ bias, int relu, int accumulate,
+                   const int* m_dev, int vec) {
+  __shared__ float xs[SK_BK][SK_BM + 1];
+  __shared__ float ws[SK_BN][SK_BK];
+  if (m_dev) M = min(M, *m_dev);
+  const int m0 = blockIdx.x * SK_BM, n0 = blockIdx.y * SK_BN;
+  if (m0 >= M) return;
+  const int tid = threadIdx.x;
+  const int ml = tid & (SK_BM - 1), nl = tid >> 6;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK_BK) {
+    if (vec) {  // rows 16-byte aligned, K % 4 == 0
+#pragma unroll
+      for (int i = 0; i < (SK_BM * SK_BK / 4) / SK_THREADS; ++i) {
+        const int idx = tid + i * SK_THREADS;
+        const int r = idx >> 4, k4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < M && k0 + 4 * k4 < K) v = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + 4 * k4);
+        xs[4 * k4][r] = v.x; xs[4 * k4 + 1][r] = v.y; xs[4 * k4 + 2][r] = v.z; xs[4 * k4 + 3][r] = v.w;
+      }
+    } else {
+      for (int idx = tid; idx < SK_BM * SK_BK; idx += SK_THREADS) {
+        const int r = idx >> 6, k = idx & 63;
+        xs[k][r] = (m0 + r < M && k0 + k < K) ? A[(long long)(m0 + r) * lda + k0 + k] : 0.f;
+      }
+    }
+    {
+      const int n = tid >> 6, k = tid & 63;  // SK_BN * SK_BK == SK_THREADS
+      ws[n][k] = (n0 + n < N && k0 + k < K) ? B[(long long)(n0 + n) * ldb + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < SK_BK; k += 4) {
+      a0 = fmaf(xs[k][ml], ws[nl][k], a0);
+      a1 = fmaf(xs[k + 1][ml], ws[nl][k + 1], a1);
+      a2 = fmaf(xs[k + 2][ml], ws[nl][k + 2], a2);
+      a3 = fmaf(xs[k + 3][ml], ws[nl][k + 3], a3);
+    }
+    acc += (a0 + a1) + (a2 + a3);
+    __syncthreads();
+  }
+  const int m = m0 + ml, n = n0 + nl;
+  if (m < M && n < N) {
+    if (bias) acc += bias[n];
+    if (relu) acc = fmaxf(acc, 0.f);
+    float* c = C + (long long)m * ldc + n;
+    *c = accumulate ? *c + acc : acc;
+  }
+}
+
 // column sums of a [rows, cols] matrix accumulated into out[cols] (bias gradients)
 __global__ void colsum_kernel(const float* __restrict__ x, long long ld, const int* rows_dev, int rows_max, int cols,
                               float* out) {
