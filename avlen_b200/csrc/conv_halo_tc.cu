@@ -16,6 +16,15 @@
 // input) pairs horizontally adjacent taps in one K = 8 MMA by setting LBO = 16 bytes (the next pixel).
 //
 // HBM traffic = read x once (+ (KH-1)/R halo rows, L2 hits) + write y once: the algorithmic bytes of DESIGN.md §4.
+//
+// fp16 activation storage (template IN16 / OUT16): the widest tensors of the encoders (stem output and layer1 of
+// custom_resnet18, 64x64x16 per frame) can be kept in HBM as fp16 — the same 10-bit mantissa the TF32 tensor core
+// keeps of an fp32 operand, rounded to nearest instead of truncated.  A chunk plane then holds 8 channels per
+// 16 bytes and one kind::f16 MMA covers K = 16 channels with the operand bytes of a K = 8 TF32 MMA: half the HBM
+// bytes and half the MMAs (this kernel is paced by the tensor core's shared-memory operand fetch).  Accumulation
+// stays fp32 in TMEM; weights are the TF32-rounded fp32 weights converted (exactly) to fp16.
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 #ifndef AVL_HOST_EMUL
@@ -31,9 +40,9 @@ constexpr int HL_THREADS = 32 * (HL_EPI_WARPS + 1 + HL_LOAD_WARPS);
 constexpr int HL_LOAD_THREADS = 32 * HL_LOAD_WARPS;
 
 struct HaloArgs {
-  const float* x;
-  const float* w;  // packed (Cout, KH, KW, C)
-  float* y;
+  const void* x;   // fp32, or fp16 when IN16
+  const void* w;   // packed (Cout, KH, KW, C), same element type as x
+  void* y;         // fp32, or fp16 when OUT16
   const float* bias;
   const float* scale;
   const float* residual;
@@ -46,7 +55,7 @@ struct HaloArgs {
   int tiles;           // ceil(R * Wp / 128)
   int strips_per_img;  // ceil(H / R)
   int total_strips;
-  int nc;              // C / 4 chunk planes of the input
+  int nc;              // 16-byte chunk planes of the input: C / 4 (fp32) or C / 8 (fp16)
   int kwp;             // C == 4: KW rounded up to even (weight planes per kernel row), else KW
   uint32_t in_plane;   // bytes per input chunk plane
   uint32_t w_plane;    // bytes per weight chunk plane (Cout * 16)
@@ -63,6 +72,30 @@ struct HaloArgs {
 //   MMA      : wait in_full[b]; per tile: wait acc_empty[a] -> KH*KW*C/8 MMAs -> commit acc_full[a]; after the strip's
 //              last tile: commit in_empty[b]
 //   epilogue : wait acc_full[a] -> tcgen05.ld -> acc_empty[a] -> scale / bias / residual / ReLU -> NHWC store
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {  // kind::f16, fp16 A / B (format 0), fp32 accumulate
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ void umma_halo_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_tf32_elect(tmem_d, a_desc, b_desc, idesc, accumulate);
+  }
+}
+
+template <bool IN16, bool OUT16>
 __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   AVL_DYN_SMEM(smem);
   __shared__ __align__(8) unsigned long long bars[8];  // in_full[2], in_empty[2], acc_full[2], acc_empty[2]
@@ -118,7 +151,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
         const int r = rest / p.KW;
         plane = r * p.kwp + (rest - r * p.KW);
       }
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w) + e);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w) + e);  // 16 bytes = 4 fp32 / 8 fp16 channels
       *reinterpret_cast<float4*>(smem + (size_t)plane * p.w_plane + (size_t)n * 16) = v;
     }
   }
@@ -156,7 +189,8 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
       mbar_wait(IN_EMPTY(b), (uint32_t)(((it_strip >> 1) & 1) ^ 1));  // first use of each buffer passes
       const int n = strip / p.strips_per_img;
       const int oh0 = (strip - n * p.strips_per_img) * p.R;
-      const float* xin = p.x + (long long)n * p.H * p.W * p.C;
+      constexpr int ESZ = IN16 ? 2 : 4;
+      const unsigned char* xin = reinterpret_cast<const unsigned char*>(p.x) + (long long)n * p.H * p.W * p.C * ESZ;
       const uint32_t dst0 = in_base0 + (uint32_t)b * in_bytes;
       for (int it = lt; it < items; it += HL_LOAD_THREADS) {
         const int ir = it / per_row;
@@ -165,7 +199,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
         const int c = rem - iw * p.nc;
         const int ih = oh0 - pad + ir;
         const bool ok = ih >= 0 && ih < p.H;
-        const float* src = ok ? xin + ((long long)ih * p.W) * p.C + (long long)rem * 4 : p.x;
+        const void* src = ok ? (const void*)(xin + ((long long)ih * p.W) * p.C * ESZ + (long long)rem * 16) : p.x;
         cp_async16(dst0 + (uint32_t)c * p.in_plane + (uint32_t)(ir * p.Wp + pad + iw) * 16, src, ok ? 16u : 0u);
       }
       cp_async_commit();
@@ -177,7 +211,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
     // ================================================================================ MMA issuer
     // (whole warp in the loop, one elected lane issues: see umma_tf32_elect)
     {
-      const uint32_t idesc = umma_idesc_tf32(HL_TILE, p.ncols);
+      const uint32_t idesc = IN16 ? umma_idesc_f16(HL_TILE, p.ncols) : umma_idesc_tf32(HL_TILE, p.ncols);
       const uint64_t bd0 = umma_desc(w_base, p.w_plane, 128);
       int it_strip = 0, it_tile = 0;
       for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
@@ -195,12 +229,12 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
             // increments read from constant (parameter) space: uniform loads, no shared-memory latency
 #pragma unroll 6
             for (int i = 0; i < p.n_mma; ++i)
-              umma_tf32_elect(d, ad0 + p.off_a[i], bd0 + p.off_b[i], idesc, i > 0 ? 1u : 0u);
+              umma_halo_elect<IN16>(d, ad0 + p.off_a[i], bd0 + p.off_b[i], idesc, i > 0 ? 1u : 0u);
           } else {
 #pragma unroll 4
             for (int i = 0; i < p.n_mma; ++i) {
               const uint2 o = mma_off[i];
-              umma_tf32_elect(d, ad0 + o.x, bd0 + o.y, idesc, i > 0 ? 1u : 0u);
+              umma_halo_elect<IN16>(d, ad0 + o.x, bd0 + o.y, idesc, i > 0 ? 1u : 0u);
             }
           }
           umma_commit_elect(ACC_FULL(a));
@@ -238,7 +272,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
             mbar_arrive(ACC_EMPTY(a));
           }
           if (valid) {
-            float* yrow = p.y + pix * p.ldy + c0;
+            float* yrow = reinterpret_cast<float*>(p.y) + pix * p.ldy + c0;  // (OUT16: recomputed below)
             const float* rrow = p.residual ? p.residual + pix * p.ldr + c0 : nullptr;
             float o[16];
 #pragma unroll
@@ -250,7 +284,14 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
               if (p.relu) acc = fmaxf(acc, 0.f);
               o[j] = acc;
             }
-            if (p.vec_store) {
+            if (OUT16) {  // 16 channels = 32 bytes of fp16 (rows are 16-byte aligned: checked by the host)
+              __half2 h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + pix * p.ldy + c0);
+              dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+              dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+            } else if (p.vec_store) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(yrow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -286,14 +327,21 @@ AVL_API int avl_set_tc_conv_halo(int on, int rows) {
 }
 
 // Returns AVL_ERR_UNSUPPORTED (without launching) when the shape is outside what this kernel is built for; the
-// caller (avl_tc_conv2d_fwd) then falls back to the im2col-gather kernel.
-int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
-                         int stride, int pad, const float* scale, const float* bias, const float* residual,
-                         long long ldr, int relu, float* y, long long ldy, cudaStream_t stream) {
+// caller (avl_tc_conv2d_fwd) then falls back to the im2col-gather kernel.  in16 / out16: x (and w) / y are fp16.
+int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
+                           int KW, int stride, int pad, const float* scale, const float* bias, const float* residual,
+                           long long ldr, int relu, void* y, int out16, long long ldy, cudaStream_t stream) {
   if (!g_halo_on) return AVL_ERR_UNSUPPORTED;
   if (stride != 1 || KH != KW || !(KH & 1) || pad != KH / 2 || KH < 3) return AVL_ERR_UNSUPPORTED;
-  if (!(C == 4 || (C % 8 == 0 && C <= 64)) || (Cout % 16) || Cout > 128) return AVL_ERR_UNSUPPORTED;
+  if (in16) {
+    if ((C % 16) || C > 128) return AVL_ERR_UNSUPPORTED;
+  } else if (!(C == 4 || (C % 8 == 0 && C <= 64))) {
+    return AVL_ERR_UNSUPPORTED;
+  }
+  if ((Cout % 16) || Cout > 128) return AVL_ERR_UNSUPPORTED;
   if (W < 16 || ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15)) return AVL_ERR_UNSUPPORTED;
+  if (out16 && (residual || (ldy & 7) || ((uintptr_t)y & 15))) return AVL_ERR_UNSUPPORTED;
+  const int cpc = in16 ? 8 : 4;  // channels per 16-byte chunk
   HaloArgs p = {};
   p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
   p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
@@ -304,13 +352,14 @@ int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float
   long long total = (long long)N * p.strips_per_img;
   if (total > 2147483647LL) return AVL_ERR_UNSUPPORTED;
   p.total_strips = (int)total;
-  p.nc = C / 4;
-  p.kwp = (C == 4) ? ((KW + 1) & ~1) : KW;
+  p.nc = C / cpc;
+  const bool c4 = !in16 && C == 4;
+  p.kwp = c4 ? ((KW + 1) & ~1) : KW;
   const int in_pixels = p.tiles * HL_TILE + (KH - 1) * p.Wp + KW + 8;
   p.in_plane = (uint32_t)in_pixels * 16;
   p.w_plane = (uint32_t)Cout * 16;
-  p.n_wplanes = (C == 4) ? KH * p.kwp : KH * KW * p.nc;
-  p.n_mma = (C == 4) ? KH * (p.kwp / 2) : KH * KW * (p.nc / 2);
+  p.n_wplanes = c4 ? KH * p.kwp : KH * KW * p.nc;
+  p.n_mma = c4 ? KH * (p.kwp / 2) : KH * KW * (p.nc / 2);
   if (p.n_mma > HL_MAX_MMA) return AVL_ERR_UNSUPPORTED;
   if (p.n_mma <= HL_PARAM_MMA) {
     for (int i = 0; i < p.n_mma; ++i) {
@@ -336,7 +385,10 @@ int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float
   if (smem > 200 * 1024 || smem + (1 << 14) > (1u << 18)) return AVL_ERR_UNSUPPORTED;  // descriptor addresses: 18 bits
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -345,8 +397,28 @@ int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float
   while (per_sm > 1 && per_sm * cols > 512) --per_sm;
   long long grid = (long long)avl_num_sms() * per_sm;
   if (grid > total) grid = total;
-  tc_conv_halo_kernel<<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  if (in16 && out16) tc_conv_halo_kernel<true, true><<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  else if (in16) tc_conv_halo_kernel<true, false><<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  else if (out16) tc_conv_halo_kernel<false, true><<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  else tc_conv_halo_kernel<false, false><<<(int)grid, HL_THREADS, smem, stream>>>(p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
+}
+
+int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
+                         int stride, int pad, const float* scale, const float* bias, const float* residual,
+                         long long ldr, int relu, float* y, long long ldy, cudaStream_t stream) {
+  return avl_tc_conv_halo_typed(x, 0, N, H, W, C, w_packed, Cout, KH, KW, stride, pad, scale, bias, residual, ldr, relu, y,
+                                0, ldy, stream);
+}
+
+// Test / bench entry of the fp16-storage variants (x / w fp16 when in16, y fp16 when out16); -2 when not covered.
+AVL_API int avl_tc_conv_halo_f16(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout,
+                                 int KH, int KW, int pad, int relu, void* y, int out16, void* stream) {
+  if (N < 0 || H < 1 || W < 1 || C < 1 || Cout < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !w_packed || !y) return AVL_ERR_ARG;
+  return avl_tc_conv_halo_typed(x, in16, N, H, W, C, w_packed, Cout, KH, KW, 1, pad, nullptr, nullptr, nullptr, 0, relu, y,
+                                out16, Cout, (cudaStream_t)stream);
 }
 #endif  // AVL_HOST_EMUL

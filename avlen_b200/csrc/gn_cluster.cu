@@ -5,10 +5,14 @@
 // (every CTA reads its peers' partials after a cluster barrier), and the slice is normalised straight from shared
 // memory.  x is read once and y written once — the two-pass kernels (statistics pass + apply pass, conv.cu) read x
 // twice and need three launches.  With 64 environments in a rollout step this also turns 64 CTAs into 64 * CL.
+//
+// IN16 / OUT16: x (and the residual) / y are stored as fp16 (the encoders' widest activations, see conv_halo_tc.cu);
+// statistics and the normalisation run in fp32 on the staged fp32 copy either way.
 #include "common.cuh"
 
 #ifndef AVL_HOST_EMUL
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -16,10 +20,34 @@ namespace {
 constexpr int GNC_THREADS = 256;
 constexpr int GNC_MAX_SLICE = 48 * 1024;  // bytes of one CTA's slice (dynamic shared memory)
 
-__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __restrict__ x,
+__device__ __forceinline__ float4 gn_cvt4(uint2 u) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <bool F16>
+__device__ __forceinline__ float4 gn_ld4(const void* base, size_t i) {  // 4 consecutive channels, element index 4 * i
+  if (F16) return gn_cvt4(__ldg(reinterpret_cast<const uint2*>(base) + i));
+  return __ldg(reinterpret_cast<const float4*>(base) + i);
+}
+template <bool F16>
+__device__ __forceinline__ void gn_st4(void* base, size_t i, float4 o) {
+  if (F16) {
+    const __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    reinterpret_cast<uint2*>(base)[i] = u;
+  } else {
+    reinterpret_cast<float4*>(base)[i] = o;
+  }
+}
+
+template <bool IN16, bool OUT16>
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const void* __restrict__ x,
                                                                  const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta,
-                                                                 const float* __restrict__ residual, float* y, int HW,
+                                                                 const void* __restrict__ residual, void* y, int HW,
                                                                  int C, int groups, float eps, int relu, int cl,
                                                                  int pix_per_cta) {
   extern __shared__ __align__(16) unsigned char gsm[];
@@ -35,14 +63,24 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __
   const int p0 = rank * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
   const int n4 = max(0, p1 - p0) * nq;
-  const float4* xs = reinterpret_cast<const float4*>(x + ((size_t)n * HW + p0) * C);
+  const size_t base4 = ((size_t)n * HW + p0) * nq;  // float4-sized element index of this CTA's slice
+  // the slice is staged in its storage type: an fp16 sample needs half the shared memory, i.e. half the cluster
+  // size (fewer barriers per sample) and twice the bytes in flight per CTA
   float4* tile = reinterpret_cast<float4*>(gsm);
+  uint2* tile16 = reinterpret_cast<uint2*>(gsm);
 
   // ---- pass over HBM: stage + per-thread sums (a thread always sees the same 4 channels: nq divides the stride)
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   for (int i = tid; i < n4; i += GNC_THREADS) {
-    const float4 v = __ldg(xs + i);
-    tile[i] = v;
+    float4 v;
+    if (IN16) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(x) + base4 + i);
+      tile16[i] = u;
+      v = gn_cvt4(u);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
+      tile[i] = v;
+    }
     s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1); q2 = fmaf(v.z, v.z, q2); q3 = fmaf(v.w, v.w, q3);
   }
@@ -106,41 +144,44 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const float* __
     a[j] = g_rstd[g] * __ldg(gamma + c);
     b[j] = __ldg(beta + c) - g_mean[g] * a[j];
   }
-  float4* ys = reinterpret_cast<float4*>(y + ((size_t)n * HW + p0) * C);
-  const float4* rs = residual ? reinterpret_cast<const float4*>(residual + ((size_t)n * HW + p0) * C) : nullptr;
   for (int i = tid; i < n4; i += GNC_THREADS) {
-    const float4 v = tile[i];
+    const float4 v = IN16 ? gn_cvt4(tile16[i]) : tile[i];
     float4 o = make_float4(fmaf(v.x, a[0], b[0]), fmaf(v.y, a[1], b[1]), fmaf(v.z, a[2], b[2]), fmaf(v.w, a[3], b[3]));
-    if (rs) {
-      const float4 r = __ldg(rs + i);
+    if (residual) {
+      const float4 r = gn_ld4<IN16>(residual, base4 + i);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    ys[i] = o;
+    gn_st4<OUT16>(y, base4 + i, o);
   }
 }
 
 }  // namespace
 
 // Returns AVL_ERR_UNSUPPORTED (nothing launched) for shapes outside this kernel: the caller falls back to the
-// two-pass kernels.  x, y, residual must be 16-byte aligned.
-AVL_API int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, const float* residual,
-                                      float* y, int N, int HW, int C, int groups, float eps, int relu, void* stream) {
+// two-pass kernels.  x, y, residual must be 16-byte aligned.  in16: x and residual are fp16; out16: y is fp16.
+int avl_groupnorm_cluster_typed(const void* x, int in16, const float* gamma, const float* beta, const void* residual,
+                                void* y, int out16, int N, int HW, int C, int groups, float eps, int relu,
+                                void* stream) {
   if (N < 0 || HW < 1 || C < 1 || groups < 1) return AVL_ERR_ARG;
   if (N == 0) return AVL_OK;
   if (!x || !gamma || !beta || !y) return AVL_ERR_ARG;
   if ((C & 3) || C > 512 || groups > 64 || C % groups || GNC_THREADS % (C >> 2)) return AVL_ERR_UNSUPPORTED;
   if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || ((uintptr_t)residual & 15)) return AVL_ERR_UNSUPPORTED;
-  const long long sample_bytes = (long long)HW * C * 4;
+  const int esz = in16 ? 2 : 4;
+  const long long sample_bytes = (long long)HW * C * esz;  // staged in shared memory in its storage type
   int cl = 1;
   while (cl < 8 && sample_bytes / cl > 32 * 1024) cl <<= 1;
   if (cl > HW) return AVL_ERR_UNSUPPORTED;
   const int pix_per_cta = avl_div_up(HW, cl);
-  const size_t smem = (size_t)pix_per_cta * C * 4;
+  const size_t smem = (size_t)pix_per_cta * C * esz;
   if (smem > (size_t)GNC_MAX_SLICE || (long long)N * cl > 2147483647LL) return AVL_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNC_MAX_SLICE));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -155,9 +196,22 @@ AVL_API int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, x, gamma, beta, residual, y, HW, C, groups, eps, relu, cl,
-                                    pix_per_cta));
+  auto kern = in16 ? (out16 ? gn_cluster_kernel<true, true> : gn_cluster_kernel<true, false>)
+                   : (out16 ? gn_cluster_kernel<false, true> : gn_cluster_kernel<false, false>);
+  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, residual, y, HW, C, groups, eps, relu, cl, pix_per_cta));
   avl_count_launch();
   return AVL_OK;
+}
+
+AVL_API int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, const float* residual,
+                                      float* y, int N, int HW, int C, int groups, float eps, int relu, void* stream) {
+  return avl_groupnorm_cluster_typed(x, 0, gamma, beta, residual, y, 0, N, HW, C, groups, eps, relu, stream);
+}
+
+// Test entry of the fp16-storage variants (x / residual fp16; y fp16 when out16).
+AVL_API int avl_groupnorm_fwd_cluster_f16(const void* x, const float* gamma, const float* beta, const void* residual,
+                                          void* y, int out16, int N, int HW, int C, int groups, float eps, int relu,
+                                          void* stream) {
+  return avl_groupnorm_cluster_typed(x, 1, gamma, beta, residual, y, out16, N, HW, C, groups, eps, relu, stream);
 }
 #endif  // AVL_HOST_EMUL

@@ -13,7 +13,32 @@
 #include "../../include/avlen_b200.h"
 
 #ifndef AVL_HOST_EMUL
+#include <cuda_fp16.h>
+
+// typed entries of the halo-strip convolution and the cluster GroupNorm (fp16 activation storage)
+int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
+                           int KW, int stride, int pad, const float* scale, const float* bias, const float* residual,
+                           long long ldr, int relu, void* y, int out16, long long ldy, cudaStream_t stream);
+int avl_groupnorm_cluster_typed(const void* x, int in16, const float* gamma, const float* beta, const void* residual,
+                                void* y, int out16, int N, int HW, int C, int groups, float eps, int relu,
+                                void* stream);
+
 namespace {
+
+int g_f16_act = 1;
+
+// 3x3 weights of stages 1 / 2 (already rounded to TF32, so the conversion is exact) as fp16, one launch
+struct HalfPack {
+  const float* src[8];
+  __half* dst[8];
+  int n[8];
+};
+__global__ void pack_half_kernel(HalfPack p) {
+  const float* s = p.src[blockIdx.y];
+  __half* d = p.dst[blockIdx.y];
+  const int n = p.n[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = __float2half_rn(s[i]);
+}
 
 struct Act {
   float* p;
@@ -69,7 +94,20 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
   // ---- stem
   Act cur = {buf[0], out_dim(n.H, n.stem_k, n.stem_stride, n.stem_pad), out_dim(n.W, n.stem_k, n.stem_stride, n.stem_pad),
              n.widths[0]};
-  if (gn) {
+  // fp16 activation storage for the stem output and stage 1 (the widest tensors): GroupNorm networks on the
+  // tensor-core path whose stem and stage-1 convolutions fit the halo-strip kernel and the cluster GroupNorm
+  bool f16_path = false;
+  if (gn && use_tc && g_f16_act && !n.stem_maxpool && n.stem_stride == 1 && n.stem_pad == n.stem_k / 2 &&
+      (n.widths[0] % 16) == 0 && n.widths[0] <= 64 && cur.W >= 16 && (long long)cur.H * cur.W * cur.C * 4 <= 8 * 32 * 1024 &&
+      cur.H * cur.W >= 8) {
+    int rc = avl_tc_conv_halo_typed(x, 0, n.N, n.H, n.W, n.Cin, P[RN_STEM], cur.C, n.stem_k, n.stem_k, 1, n.stem_pad, nullptr,
+                                    nullptr, nullptr, 0, 0, buf[0], 1, cur.C, (cudaStream_t)s);
+    if (rc == AVL_OK) f16_path = true;
+    else if (rc != AVL_ERR_UNSUPPORTED) return rc;
+  }
+  if (f16_path) {
+    // GroupNorm + stage 1 follow below (fp16 buffers)
+  } else if (gn) {
     RN_TRY(conv(x, n.N, n.H, n.W, n.Cin, P[RN_STEM], cur.C, n.stem_k, n.stem_stride, n.stem_pad, nullptr, nullptr,
                 nullptr, 0, cur.p, cur.C, use_tc, s));
     RN_TRY(gnorm(cur.p, P[RN_STEM + 1], P[RN_STEM + 2], nullptr, n.N, cur.H * cur.W, cur.C, n.groups, n.eps, 1, s));
@@ -78,6 +116,82 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
                 P[RN_STEM + 2], nullptr, 1, cur.p, cur.C, use_tc, s));
   }
   int ci = 0;  // index of the buffer holding `cur`
+  int first_blk = 0;
+  if (f16_path) {
+    // ---- stage 1 on fp16 activations: t(fp16) in buf[0..2], the stage's output leaves as fp32 in buf[3]
+    const int HW = cur.H * cur.W, C = cur.C;
+    const int oh2 = out_dim(cur.H, 3, 2, 1), ow2 = out_dim(cur.W, 3, 2, 1), C2 = n.widths[1];
+    const bool stage2 = ow2 >= 16 && (C2 % 16) == 0 && C2 <= 128 && C2 == 2 * C && (oh2 * ow2) >= 8 &&
+                        (long long)oh2 * ow2 * C2 <= (long long)HW * C / 2 + 0 && (cur.H % 2) == 0 && (cur.W % 2) == 0;
+    HalfPack hp = {};
+    __half* wh = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(ws + 4 * act) + 256);
+    const int n1 = C * 9 * C, n2 = C2 * 9 * C2;
+    for (int i = 0; i < 4; ++i) {
+      hp.src[i] = P[RN_BLOCK0 + (i >> 1) * RN_PER_BLOCK + (i & 1) * 3];
+      hp.dst[i] = wh + (size_t)i * n1;
+      hp.n[i] = n1;
+    }
+    const int pack_idx2[3] = {RN_BLOCK0 + 2 * RN_PER_BLOCK + 3, RN_BLOCK0 + 3 * RN_PER_BLOCK, RN_BLOCK0 + 3 * RN_PER_BLOCK + 3};
+    for (int i = 0; i < 3; ++i) {
+      hp.src[4 + i] = P[pack_idx2[i]];
+      hp.dst[4 + i] = wh + (size_t)4 * n1 + (size_t)i * n2;
+      hp.n[4 + i] = n2;
+    }
+    pack_half_kernel<<<dim3(avl_div_up(stage2 ? n2 : n1, 256), stage2 ? 7 : 4), 256, 0, (cudaStream_t)s>>>(hp);
+    AVL_LAUNCH_CHECK();
+    void* h0 = buf[0];
+    void* h1 = buf[1];
+    void* h2 = buf[2];
+    RN_TRY(avl_groupnorm_cluster_typed(h0, 1, P[RN_STEM + 1], P[RN_STEM + 2], nullptr, h0, 1, n.N, HW, C, n.groups, n.eps,
+                                       1, s));
+    for (int blk = 0; blk < 2; ++blk) {
+      const float* const* B = P + RN_BLOCK0 + blk * RN_PER_BLOCK;
+      RN_TRY(avl_tc_conv_halo_typed(h0, 1, n.N, cur.H, cur.W, C, hp.dst[2 * blk], C, 3, 3, 1, 1, nullptr, nullptr, nullptr,
+                                    0, 0, h1, 1, C, (cudaStream_t)s));
+      RN_TRY(avl_groupnorm_cluster_typed(h1, 1, B[1], B[2], nullptr, h1, 1, n.N, HW, C, n.groups, n.eps, 1, s));
+      RN_TRY(avl_tc_conv_halo_typed(h1, 1, n.N, cur.H, cur.W, C, hp.dst[2 * blk + 1], C, 3, 3, 1, 1, nullptr, nullptr,
+                                    nullptr, 0, 0, h2, 1, C, (cudaStream_t)s));
+      if (blk == 0) {
+        RN_TRY(avl_groupnorm_cluster_typed(h2, 1, B[4], B[5], h0, h2, 1, n.N, HW, C, n.groups, n.eps, 1, s));
+        void* t = h0; h0 = h2; h2 = t;  // block output becomes the next block's input / identity
+      } else {
+        RN_TRY(avl_groupnorm_cluster_typed(h2, 1, B[4], B[5], h0, buf[3], 0, n.N, HW, C, n.groups, n.eps, 1, s));
+      }
+    }
+    cur.p = buf[3];
+    ci = 3;
+    first_blk = 2;
+    if (stage2) {
+      // ---- stage 2: the two stride-2 convolutions read the fp32 stage-1 output through the im2col kernel and write
+      // fp32; everything between them and the stage's output is fp16.  An fp16 stage-2 tensor is a quarter of a
+      // buffer, an fp32 one half.
+      const int HW2 = oh2 * ow2;
+      const float* const* B2 = P + RN_BLOCK0 + 2 * RN_PER_BLOCK;
+      const float* const* B3 = P + RN_BLOCK0 + 3 * RN_PER_BLOCK;
+      float* f32a = buf[0];
+      float* f32b = buf[0] + act / 2;
+      void* q1 = buf[1];
+      void* q2 = buf[1] + act / 4;
+      void* q3 = buf[1] + act / 2;
+      void* q4 = buf[1] + 3 * (act / 4);
+      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[0], C2, 3, 2, 1, nullptr, nullptr, nullptr, 0, f32a, C2, use_tc, s));
+      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[6], C2, 1, 2, 0, nullptr, nullptr, nullptr, 0, f32b, C2, use_tc, s));
+      RN_TRY(avl_groupnorm_cluster_typed(f32a, 0, B2[1], B2[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+      RN_TRY(avl_groupnorm_cluster_typed(f32b, 0, B2[7], B2[8], nullptr, q2, 1, n.N, HW2, C2, n.groups, n.eps, 0, s));
+      RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh2, ow2, C2, hp.dst[4], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q3,
+                                    1, C2, (cudaStream_t)s));
+      RN_TRY(avl_groupnorm_cluster_typed(q3, 1, B2[4], B2[5], q2, q3, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+      RN_TRY(avl_tc_conv_halo_typed(q3, 1, n.N, oh2, ow2, C2, hp.dst[5], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q1,
+                                    1, C2, (cudaStream_t)s));
+      RN_TRY(avl_groupnorm_cluster_typed(q1, 1, B3[1], B3[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+      RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh2, ow2, C2, hp.dst[6], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q4,
+                                    1, C2, (cudaStream_t)s));
+      RN_TRY(avl_groupnorm_cluster_typed(q4, 1, B3[4], B3[5], q3, buf[2], 0, n.N, HW2, C2, n.groups, n.eps, 1, s));
+      cur = {buf[2], oh2, ow2, C2};
+      ci = 2;
+      first_blk = 4;
+    }
+  }
   if (n.stem_maxpool) {
     Act nx = {buf[1], out_dim(cur.H, 3, 2, 1), out_dim(cur.W, 3, 2, 1), cur.C};
     RN_TRY(avl_maxpool3x3s2(cur.p, nx.p, n.N, cur.H, cur.W, cur.C, s));
@@ -85,7 +199,7 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
     ci = 1;
   }
   // ---- 4 stages x 2 BasicBlocks
-  for (int blk = 0; blk < 8; ++blk) {
+  for (int blk = first_blk; blk < 8; ++blk) {
     const float* const* B = P + RN_BLOCK0 + blk * RN_PER_BLOCK;
     const int planes = n.widths[blk >> 1];
     const int stride = ((blk & 1) == 0 && blk > 0) ? 2 : 1;
@@ -179,11 +293,22 @@ int side_for(cudaStream_t s, Side** out) {
 
 AVL_API int avl_resnet18_param_count(void) { return RN_COUNT; }
 
+// 1 (default): the fused GroupNorm ResNet-18 keeps its stem output and stage 1 in HBM as fp16 (tensor-core path only);
+// 0: fp32 activations everywhere.  Returns the previous setting.
+AVL_API int avl_set_f16_activations(int on) {
+  int old = g_f16_act;
+  g_f16_act = on ? 1 : 0;
+  return old;
+}
+
 // cfg: 12 host ints (see fill()).  Workspace for ONE network.
 AVL_API long long avl_resnet18_workspace_bytes(int N, int H, int W, const int* cfg) {
   Net n;
   if (!cfg || !fill(n, N, H, W, 4, cfg)) return -1;
-  return (long long)(4 * ((max_act_floats(n) + 63) & ~(size_t)63) * sizeof(float) + 256);
+  // 4 activation buffers + the fp16 copies of stage 1's four 3x3 weights (fp16 activation path)
+  return (long long)(4 * ((max_act_floats(n) + 63) & ~(size_t)63) * sizeof(float) + 256 +
+                     (4 * (size_t)n.widths[0] * 9 * n.widths[0] + 3 * (size_t)n.widths[1] * 9 * n.widths[1]) * sizeof(__half) +
+                     256);
 }
 
 // x (N, H, W, Cin) NHWC (Cin % 4 == 0 on the tensor-core path); out (N, out_dim) rows of stride ldo.

@@ -41,6 +41,9 @@ _lib.register({
     "avl_set_tc_3xtf32": [I],
     "avl_tc_gemm_3x": [P, L, P, L, I, P, L, I, I, I, P, P, L, I, P, P],
     "avl_tc_wgrad_3x": [P, L, P, L, P, L, I, I, I, P, P],
+    "avl_set_f16_activations": [I],
+    "avl_tc_conv_halo_f16": [P, I, I, I, I, I, P, I, I, I, I, I, P, I, P],
+    "avl_groupnorm_fwd_cluster_f16": [P, P, P, P, P, I, I, I, I, I, F, I, P],
     "avl_set_wgrad_desc": [I, I],
     "avl_resnet18_param_count": [],
     "avl_resnet18_workspace_bytes": [I, I, I, P],
@@ -97,6 +100,12 @@ def sync_pending():
         for ev in _pending_events:
             cur.wait_event(ev)
         _pending_events.clear()
+
+
+def set_f16_activations(on: bool) -> bool:
+    """fp16 storage of the fused GroupNorm ResNet-18's stem output and stage 1 (tensor-core path).  Returns the old
+    setting."""
+    return bool(_lib.lib().avl_set_f16_activations(int(bool(on))))
 
 
 def tensor_cores_level() -> int:

@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "policy_env_steps_per_sec_rollout_plus_ppo_update"
 UNIT = "env-steps/s"
+HALO_F16_TRAFFIC = 1216954880  # dram read + write of one fp16 halo-conv launch (profiles/r01_halo_conv_f16_layer1_ncu_full.txt)
 WORKLOAD = "savi_smt_memory150_frozen_encoders_rollout150_ppo2x2"
 
 
@@ -162,37 +163,61 @@ def run_ours(args):
     hbm, tf, how = _peaks()
     B = args.envs * args.rollout_steps // cfg.num_mini_batch
     B = min(B, 4800)
-    x = torch.randn(B, 64, 64, 16, device=dev)
-    w = torch.randn(16, 16, 3, 3, device=dev)
+    tcl = K.tensor_cores_level()
+    f16 = tcl >= 1 and bool(_lib.lib().avl_set_f16_activations(1))  # (returns the previous setting; default on)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if f16:
+        # the fused ResNet keeps the stem output and stage 1 as fp16 in HBM: the launch that dominates is the
+        # kind::f16 halo-strip kernel reading and writing fp16 (half the bytes and half the MMAs of the TF32 variant)
+        x = torch.randn(B, 64, 64, 16, device=dev).half()
+        w = (torch.randn(16, 3, 3, 16, device=dev) / 12).half()
+        y = torch.empty(B, 64, 64, 16, device=dev, dtype=torch.float16)
+
+        def run_conv():
+            _lib.call("avl_tc_conv_halo_f16", x.data_ptr(), 1, B, 64, 64, 16, w.data_ptr(), 16, 3, 3, 1, 0, y.data_ptr(), 1,
+                      _lib.stream())
+        esz = 2
+    else:
+        _lib.lib().avl_set_f16_activations(0)
+        x = torch.randn(B, 64, 64, 16, device=dev)
+        w = torch.randn(16, 16, 3, 3, device=dev)
+
+        def run_conv():
+            K.conv2d(x, w, None, 1, 1)
+        esz = 4
     for _ in range(3):
-        K.conv2d(x, w, None, 1, 1)
+        run_conv()
     ts = []
     for _ in range(10):
         flush.zero_()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        K.conv2d(x, w, None, 1, 1)
+        run_conv()
         c1.record()
         torch.cuda.synchronize()
         ts.append(c0.elapsed_time(c1))
     k_ms = sum(ts) / len(ts)
     flops = 2.0 * B * 64 * 64 * 16 * 144
-    nbytes = 2.0 * B * 64 * 64 * 16 * 4 + 16 * 144 * 4
+    nbytes = 2.0 * B * 64 * 64 * 16 * esz + 16 * 144 * esz
     ach = nbytes / (k_ms * 1e-3) / 1e9
-    tcl = K.tensor_cores_level()
-    roofline = {"kernel": ("tc_conv_halo_kernel (tcgen05 kind::tf32, halo strips, no im2col)" if tcl >= 1
-                           else "gemm_kernel<CONV> fp32 SIMT")
-                + " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
+    if f16:
+        kname = "tc_conv_halo_kernel<fp16 in, fp16 out> (tcgen05 kind::f16, fp32 accumulate, halo strips, no im2col)"
+        traffic, tsrc = (HALO_F16_TRAFFIC if B == 4800 else None), "profiles/r01_halo_conv_f16_layer1_ncu_full.txt (dram read + write of one launch)"
+        note = ("algorithmic bytes = B*64*64*16*2 read + same written + weights (activations stored as fp16); 72 FLOP/B "
+                "< the fp16 ridge => HBM-bound; paced by the tensor core's shared-memory operand fetch (one M128xN16xK16 "
+                "MMA per 4.5 KB of operands), DESIGN.md section 4")
+    elif tcl >= 1:
+        kname = "tc_conv_halo_kernel (tcgen05 kind::tf32, halo strips, no im2col)"
+        traffic, tsrc = (2469416000 if B == 4800 else None), "profiles/r01_halo_conv_v3_layer1_ncu_full.txt (dram read + write of one launch)"
+        note = ("algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound; paced by the "
+                "tensor core's shared-memory operand fetch (64 B/clk: ~73 cycles per M128xN16xK8 MMA), DESIGN.md section 4")
+    else:
+        kname, traffic, tsrc, note = "gemm_kernel<CONV> fp32 SIMT", None, None, "fp32 SIMT build"
+    roofline = {"kernel": kname + " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
                 "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(ach / hbm, 5),
-                "traffic": 2469416000 if (tcl >= 1 and B == 4800) else None,
-                "traffic_source": "profiles/r01_halo_conv_v3_layer1_ncu_full.txt (dram read + write of one launch)",
+                "frac": round(ach / hbm, 5), "traffic": traffic, "traffic_source": tsrc,
                 "peak_source": how, "launch_ms": round(k_ms, 4), "algorithmic_bytes": int(nbytes),
-                "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2),
-                "note": "algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound; "
-                        "paced by the tensor core's shared-memory operand fetch (64 B/clk: ~73 cycles per M128xN16xK8 "
-                        "MMA), DESIGN.md section 4"}
+                "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2), "note": note}
     cpu = cpu_baseline_sample(1, quick=True) if not args.no_cpu else None
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",

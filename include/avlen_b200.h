@@ -169,6 +169,16 @@ int avl_set_tc_3xtf32(int on);   /* returns old */
 int avl_tc_wgrad_3x(const float* dY, long long ldy, const float* X, long long ldx, float* dW, long long lddw, int rows,
                     int N, int K, const int* rows_dev, void* stream);
 int avl_set_wgrad_desc(int lbo_bytes, int sbo_bytes);   /* diagnostic */
+/* fp16 ACTIVATION STORAGE for the widest encoder tensors (stem output + stage 1 of custom_resnet18, smt_resnet.py:56-164):
+ * avl_resnet18_forward keeps them in HBM as fp16 (10-bit mantissa = what the TF32 tensor core keeps of an fp32 operand),
+ * fp32 accumulation and fp32 GroupNorm arithmetic; avl_set_f16_activations(0) restores fp32 storage.  The two typed
+ * entries below expose the kernels for tests / benches: x (and w, packed (Cout,KH,KW,C)) fp16 when in16, y fp16 when
+ * out16; stride 1, pad = K/2.  -2: shape not covered.                                                             */
+int avl_set_f16_activations(int on);   /* returns old */
+int avl_tc_conv_halo_f16(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
+                         int KW, int pad, int relu, void* y, int out16, void* stream);
+int avl_groupnorm_fwd_cluster_f16(const void* x, const float* gamma, const float* beta, const void* residual, void* y,
+                                  int out16, int N, int HW, int C, int groups, float eps, int relu, void* stream);
 int avl_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
                       float* stats, int rows, int cols, void* stream);
 int avl_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy,

@@ -241,7 +241,9 @@ def test_fused_resnet_call_matches_layer_by_layer(tc):
                     want = ref(x.permute(0, 3, 1, 2))
                     fused = net(x.cuda())
                     layers = net.forward_layers(K._prep_net_input(x.cuda(), tc))
-                assert rel(fused, layers) < (2e-3 if tc else 1e-5)  # tiny-M layers: fused = tensor cores, layers = SIMT
+                # tiny-M layers: fused = tensor cores, layers = SIMT; the fused call also keeps the stem output and
+                # stage 1 as fp16 in HBM (one more 2^-11 rounding per tensor than the fp32-storage layer path)
+                assert rel(fused, layers) < (4e-3 if tc else 1e-5)
                 assert rel(fused.cpu(), want) < (5e-3 if tc else TOL)
                 nets.append((net, x, fused))
             big = torch.zeros(n, 130, device="cuda")

@@ -226,3 +226,91 @@ def test_tc_wgrad_3xtf32_is_fp32_accurate(R, N, K_):
         assert rel(dw2, ref2) < TOL_3X
         outs.append(dw2)
     assert torch.equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------ fp16 activation storage (stem + stage 1)
+@pytest.mark.parametrize("case", [
+    # N, H, W, C, Cout, K, in16, out16
+    (5, 64, 64, 4, 16, 7, 0, 1), (7, 64, 64, 16, 16, 3, 1, 1), (3, 65, 26, 16, 16, 3, 1, 0), (4, 32, 32, 32, 32, 3, 1, 1),
+    (2, 65, 26, 4, 16, 7, 0, 1), (300, 64, 64, 16, 16, 3, 1, 1),
+])
+def test_halo_conv_fp16_storage(case):
+    """Halo-strip convolution with fp16 operands / fp16 output against torch on the SAME rounded inputs: the products
+    are exact in fp32, so only the accumulation order and the output rounding (2^-11) differ."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, k, in16, out16 = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, H, W, C, generator=g)
+    w = K.round_to_tf32((torch.randn(Co, k, k, C, generator=g) / (C * k * k) ** 0.5).contiguous())   # packed layout
+    if in16:
+        x, w = x.half(), w.half()
+    xd, wd = x.cuda(), w.cuda()
+    y = torch.full((N, H, W, Co), float("nan"), dtype=torch.float16 if out16 else torch.float32, device="cuda")
+    rc = _lib.lib().avl_tc_conv_halo_f16(xd.data_ptr(), in16, N, H, W, C, wd.data_ptr(), Co, k, k, k // 2, 1, y.data_ptr(),
+                                         out16, _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    xr = x.float()
+    if not in16:   # the TF32 tensor core truncates fp32 activations to 10 mantissa bits
+        xr = (xr.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = F.relu(F.conv2d(xr.double().permute(0, 3, 1, 2), w.double().permute(0, 3, 1, 2), None, 1, k // 2)).permute(0, 2, 3, 1)
+    assert not torch.isnan(y.float()).any()
+    tol = 1.5e-3 if out16 else 2e-5
+    assert rel(y.float().cpu().double(), ref) < tol
+
+
+@pytest.mark.parametrize("case", [(6, 64 * 64, 16, 1, 1), (6, 64 * 64, 16, 0, 1), (5, 65 * 26, 16, 1, 0), (9, 32 * 32, 32, 1, 1)])
+def test_groupnorm_cluster_fp16_storage(case):
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401
+    N, HW, C, out16, with_res = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = (3 * torch.randn(N, HW, C, generator=g) + 1).half()
+    res = torch.randn(N, HW, C, generator=g).half() if with_res else None
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 16, gamma, beta, 1e-5).permute(0, 2, 1)
+    if res is not None:
+        ref = ref + res.float()
+    ref = F.relu(ref)
+    xd, gd, bd = x.cuda(), gamma.cuda(), beta.cuda()   # keep the device copies alive across the calls
+    rd = res.cuda() if with_res else None
+    rp = rd.data_ptr() if with_res else None
+    y = torch.empty(N, HW, C, dtype=torch.float16 if out16 else torch.float32, device="cuda")
+    rc = _lib.lib().avl_groupnorm_fwd_cluster_f16(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), rp, y.data_ptr(), out16, N, HW,
+                                                  C, 16, 1e-5, 1, _lib.stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert rel(y.float().cpu(), ref) < (1e-3 if out16 else 1e-5)
+    # in place (x == y), as the fused network runs it
+    if out16:
+        rc = _lib.lib().avl_groupnorm_fwd_cluster_f16(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), rp, xd.data_ptr(), 1, N,
+                                                      HW, C, 16, 1e-5, 1, _lib.stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(xd, y)
+
+
+@pytest.mark.parametrize("shape", [(6, 64, 64, 3, (8, 8)), (5, 65, 26, 2, (9, 4))])
+def test_fused_resnet_fp16_stage1_matches_fp32_storage(shape):
+    """custom_resnet18 through the fused call with fp16 storage of the stem output + stage 1 against fp32 storage (both
+    TF32 / fp16 tensor-core products): differences stay at the TF32 tolerance of the 20-layer network."""
+    from avlen_b200 import nn as K
+    from avlen_b200.savi.models import smt_resnet
+    N, H, W, C, hw = shape
+    torch.manual_seed(3)
+    net = smt_resnet.custom_resnet18(num_input_channels=C, num_classes=64, fc_in_hw=hw).cuda().eval()
+    for q in net.parameters():
+        q.requires_grad = False
+    x = torch.rand(N, H, W, C, device="cuda")
+    outs = []
+    for on in (False, True):
+        old = K.set_f16_activations(on)
+        try:
+            with torch.no_grad():
+                outs.append(net(x).clone())
+        finally:
+            K.set_f16_activations(old)
+    torch.cuda.synchronize()
+    assert rel(outs[1], outs[0]) < 5e-3
+    assert not torch.equal(outs[1], outs[0])   # the fp16 path really ran
