@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
     const int rows_in = p.R + p.KH - 1;
     const int per_row = p.W * p.nc;  // 16-byte chunks per input row
     const int items = rows_in * per_row;
+    const int nc_shift = (p.nc & (p.nc - 1)) == 0 ? __ffs(p.nc) - 1 : -1;
     int it_strip = 0;
     for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
       const int b = it_strip & 1;
@@ -192,15 +193,20 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
       constexpr int ESZ = IN16 ? 2 : 4;
       const unsigned char* xin = reinterpret_cast<const unsigned char*>(p.x) + (long long)n * p.H * p.W * p.C * ESZ;
       const uint32_t dst0 = in_base0 + (uint32_t)b * in_bytes;
+      // (row, chunk-in-row) advance incrementally: two integer divisions per 16-byte chunk were most of this
+      // kernel's issue slots once the fp16 variant halved its MMA count (profiles/r01_halo_conv_f16_layer1_ncu_full.txt)
+      int ir = lt / per_row;
+      int rem = lt - ir * per_row;  // iw * nc + c == 16-byte chunk index within the image row
+      const long long row_bytes = (long long)p.W * p.C * ESZ;
       for (int it = lt; it < items; it += HL_LOAD_THREADS) {
-        const int ir = it / per_row;
-        const int rem = it - ir * per_row;  // iw * nc + c == float4 index within the image row
-        const int iw = rem / p.nc;
+        const int iw = nc_shift >= 0 ? (rem >> nc_shift) : rem / p.nc;
         const int c = rem - iw * p.nc;
         const int ih = oh0 - pad + ir;
         const bool ok = ih >= 0 && ih < p.H;
-        const void* src = ok ? (const void*)(xin + ((long long)ih * p.W) * p.C * ESZ + (long long)rem * 16) : p.x;
+        const void* src = ok ? (const void*)(xin + ih * row_bytes + (long long)rem * 16) : p.x;
         cp_async16(dst0 + (uint32_t)c * p.in_plane + (uint32_t)(ir * p.Wp + pad + iw) * 16, src, ok ? 16u : 0u);
+        rem += HL_LOAD_THREADS;
+        while (rem >= per_row) { rem -= per_row; ++ir; }
       }
       cp_async_commit();
       cp_async_wait<0>();

@@ -29,9 +29,9 @@ int g_f16_act = 1;
 
 // 3x3 weights of stages 1 / 2 (already rounded to TF32, so the conversion is exact) as fp16, one launch
 struct HalfPack {
-  const float* src[8];
-  __half* dst[8];
-  int n[8];
+  const float* src[10];
+  __half* dst[10];
+  int n[10];
 };
 __global__ void pack_half_kernel(HalfPack p) {
   const float* s = p.src[blockIdx.y];
@@ -86,6 +86,42 @@ size_t max_act_floats(const Net& n) {
     if (_rc) return _rc;    \
   } while (0)
 
+// One stride-2 stage (BasicBlocks blk0, blk0 + 1) with fp16 storage of everything between the two stride-2
+// convolutions (fp32 in, fp32 out: they run on the im2col kernel) and the stage output (fp32).  `cur` (fp32) lives in
+// buf[ci]; the three other buffers are scratch; on return cur / ci describe the stage's fp32 output.  wh: the fp16
+// 3x3 weights (blk0.conv2, blk0+1.conv1, blk0+1.conv2).  Buffer `act` floats hold the stem output, so an fp32 tensor of
+// this stage is at most half of one and an fp16 tensor at most a quarter.
+int stage_f16(const Net& n, const float* const* P, int blk0, Act& cur, int& ci, float* const* buf, size_t act,
+              __half* const* wh, int use_tc, void* s) {
+  const int C = cur.C, C2 = 2 * C;
+  const int oh = out_dim(cur.H, 3, 2, 1), ow = out_dim(cur.W, 3, 2, 1), HW2 = oh * ow;
+  const float* const* B2 = P + RN_BLOCK0 + blk0 * RN_PER_BLOCK;
+  const float* const* B3 = B2 + RN_PER_BLOCK;
+  float* fb = buf[(ci + 1) & 3];
+  float* qb = buf[(ci + 2) & 3];
+  float* ob = buf[(ci + 3) & 3];
+  float* f32a = fb;
+  float* f32b = fb + act / 2;
+  void* q1 = qb;
+  void* q2 = qb + act / 4;
+  void* q3 = qb + act / 2;
+  void* q4 = qb + 3 * (act / 4);
+  cudaStream_t cs = (cudaStream_t)s;
+  RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[0], C2, 3, 2, 1, nullptr, nullptr, nullptr, 0, f32a, C2, use_tc, s));
+  RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[6], C2, 1, 2, 0, nullptr, nullptr, nullptr, 0, f32b, C2, use_tc, s));
+  RN_TRY(avl_groupnorm_cluster_typed(f32a, 0, B2[1], B2[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+  RN_TRY(avl_groupnorm_cluster_typed(f32b, 0, B2[7], B2[8], nullptr, q2, 1, n.N, HW2, C2, n.groups, n.eps, 0, s));
+  RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh, ow, C2, wh[0], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q3, 1, C2, cs));
+  RN_TRY(avl_groupnorm_cluster_typed(q3, 1, B2[4], B2[5], q2, q3, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+  RN_TRY(avl_tc_conv_halo_typed(q3, 1, n.N, oh, ow, C2, wh[1], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q1, 1, C2, cs));
+  RN_TRY(avl_groupnorm_cluster_typed(q1, 1, B3[1], B3[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
+  RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh, ow, C2, wh[2], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q4, 1, C2, cs));
+  RN_TRY(avl_groupnorm_cluster_typed(q4, 1, B3[4], B3[5], q3, ob, 0, n.N, HW2, C2, n.groups, n.eps, 1, s));
+  cur = {ob, oh, ow, C2};
+  ci = (ci + 3) & 3;
+  return AVL_OK;
+}
+
 int run(const Net& n, const float* x, const float* const* P, float* out, long long ldo, int use_tc, float* ws,
         void* s) {
   const size_t act = (max_act_floats(n) + 63) & ~(size_t)63;
@@ -123,9 +159,12 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
     const int oh2 = out_dim(cur.H, 3, 2, 1), ow2 = out_dim(cur.W, 3, 2, 1), C2 = n.widths[1];
     const bool stage2 = ow2 >= 16 && (C2 % 16) == 0 && C2 <= 128 && C2 == 2 * C && (oh2 * ow2) >= 8 &&
                         (long long)oh2 * ow2 * C2 <= (long long)HW * C / 2 + 0 && (cur.H % 2) == 0 && (cur.W % 2) == 0;
+    const int oh3 = out_dim(oh2, 3, 2, 1), ow3 = out_dim(ow2, 3, 2, 1), C3 = n.widths[2];
+    const bool stage3 = stage2 && ow3 >= 16 && (C3 % 16) == 0 && C3 <= 64 && C3 == 2 * C2 && (oh3 * ow3) >= 8 &&
+                        (oh2 % 2) == 0 && (ow2 % 2) == 0;
     HalfPack hp = {};
     __half* wh = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(ws + 4 * act) + 256);
-    const int n1 = C * 9 * C, n2 = C2 * 9 * C2;
+    const int n1 = C * 9 * C, n2 = C2 * 9 * C2, n3 = C3 * 9 * C3;
     for (int i = 0; i < 4; ++i) {
       hp.src[i] = P[RN_BLOCK0 + (i >> 1) * RN_PER_BLOCK + (i & 1) * 3];
       hp.dst[i] = wh + (size_t)i * n1;
@@ -137,7 +176,13 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
       hp.dst[4 + i] = wh + (size_t)4 * n1 + (size_t)i * n2;
       hp.n[4 + i] = n2;
     }
-    pack_half_kernel<<<dim3(avl_div_up(stage2 ? n2 : n1, 256), stage2 ? 7 : 4), 256, 0, (cudaStream_t)s>>>(hp);
+    for (int i = 0; i < 3; ++i) {
+      hp.src[7 + i] = P[pack_idx2[i] + 2 * RN_PER_BLOCK];
+      hp.dst[7 + i] = wh + (size_t)4 * n1 + (size_t)3 * n2 + (size_t)i * n3;
+      hp.n[7 + i] = n3;
+    }
+    pack_half_kernel<<<dim3(avl_div_up(stage3 ? n3 : (stage2 ? n2 : n1), 256), stage3 ? 10 : (stage2 ? 7 : 4)), 256, 0,
+                       (cudaStream_t)s>>>(hp);
     AVL_LAUNCH_CHECK();
     void* h0 = buf[0];
     void* h1 = buf[1];
@@ -161,35 +206,12 @@ int run(const Net& n, const float* x, const float* const* P, float* out, long lo
     cur.p = buf[3];
     ci = 3;
     first_blk = 2;
-    if (stage2) {
-      // ---- stage 2: the two stride-2 convolutions read the fp32 stage-1 output through the im2col kernel and write
-      // fp32; everything between them and the stage's output is fp16.  An fp16 stage-2 tensor is a quarter of a
-      // buffer, an fp32 one half.
-      const int HW2 = oh2 * ow2;
-      const float* const* B2 = P + RN_BLOCK0 + 2 * RN_PER_BLOCK;
-      const float* const* B3 = P + RN_BLOCK0 + 3 * RN_PER_BLOCK;
-      float* f32a = buf[0];
-      float* f32b = buf[0] + act / 2;
-      void* q1 = buf[1];
-      void* q2 = buf[1] + act / 4;
-      void* q3 = buf[1] + act / 2;
-      void* q4 = buf[1] + 3 * (act / 4);
-      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[0], C2, 3, 2, 1, nullptr, nullptr, nullptr, 0, f32a, C2, use_tc, s));
-      RN_TRY(conv(cur.p, n.N, cur.H, cur.W, C, B2[6], C2, 1, 2, 0, nullptr, nullptr, nullptr, 0, f32b, C2, use_tc, s));
-      RN_TRY(avl_groupnorm_cluster_typed(f32a, 0, B2[1], B2[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
-      RN_TRY(avl_groupnorm_cluster_typed(f32b, 0, B2[7], B2[8], nullptr, q2, 1, n.N, HW2, C2, n.groups, n.eps, 0, s));
-      RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh2, ow2, C2, hp.dst[4], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q3,
-                                    1, C2, (cudaStream_t)s));
-      RN_TRY(avl_groupnorm_cluster_typed(q3, 1, B2[4], B2[5], q2, q3, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
-      RN_TRY(avl_tc_conv_halo_typed(q3, 1, n.N, oh2, ow2, C2, hp.dst[5], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q1,
-                                    1, C2, (cudaStream_t)s));
-      RN_TRY(avl_groupnorm_cluster_typed(q1, 1, B3[1], B3[2], nullptr, q1, 1, n.N, HW2, C2, n.groups, n.eps, 1, s));
-      RN_TRY(avl_tc_conv_halo_typed(q1, 1, n.N, oh2, ow2, C2, hp.dst[6], C2, 3, 3, 1, 1, nullptr, nullptr, nullptr, 0, 0, q4,
-                                    1, C2, (cudaStream_t)s));
-      RN_TRY(avl_groupnorm_cluster_typed(q4, 1, B3[4], B3[5], q3, buf[2], 0, n.N, HW2, C2, n.groups, n.eps, 1, s));
-      cur = {buf[2], oh2, ow2, C2};
-      ci = 2;
-      first_blk = 4;
+    // ---- stages 2 and 3: the two stride-2 convolutions read the previous stage's fp32 output through the im2col
+    // kernel and write fp32; everything between them and the stage's output is fp16
+    for (int st = 1; st <= 2 && first_blk == 2 * st; ++st) {
+      if (!(st == 1 ? stage2 : stage3)) break;
+      RN_TRY(stage_f16(n, P, 2 * st, cur, ci, buf, act, hp.dst + (st == 1 ? 4 : 7), use_tc, s));
+      first_blk = 2 * st + 2;
     }
   }
   if (n.stem_maxpool) {
@@ -307,8 +329,8 @@ AVL_API long long avl_resnet18_workspace_bytes(int N, int H, int W, const int* c
   if (!cfg || !fill(n, N, H, W, 4, cfg)) return -1;
   // 4 activation buffers + the fp16 copies of stage 1's four 3x3 weights (fp16 activation path)
   return (long long)(4 * ((max_act_floats(n) + 63) & ~(size_t)63) * sizeof(float) + 256 +
-                     (4 * (size_t)n.widths[0] * 9 * n.widths[0] + 3 * (size_t)n.widths[1] * 9 * n.widths[1]) * sizeof(__half) +
-                     256);
+                     (4 * (size_t)n.widths[0] * 9 * n.widths[0] + 3 * (size_t)n.widths[1] * 9 * n.widths[1] +
+                      3 * (size_t)n.widths[2] * 9 * n.widths[2]) * sizeof(__half) + 256);
 }
 
 // x (N, H, W, Cin) NHWC (Cin % 4 == 0 on the tensor-core path); out (N, out_dim) rows of stride ldo.
