@@ -319,16 +319,17 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
 }
 
 static int g_halo_on = 1;
-static int g_halo_rows = 8;
+static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
 
 }  // namespace
 
 // 1 (default): stride-1 same-padded convolutions with few channels use the halo-strip kernel; 0: always the
-// im2col-gather kernel.  rows > 0 sets the strip height.  Returns the previous on/off state.
+// im2col-gather kernel.  rows > 0 sets the strip height, rows == 0 selects it per shape (default), rows < 0 keeps it.
+// Returns the previous on/off state.
 AVL_API int avl_set_tc_conv_halo(int on, int rows) {
   int old = g_halo_on;
   g_halo_on = on ? 1 : 0;
-  if (rows > 0) g_halo_rows = rows;
+  if (rows >= 0) g_halo_rows = rows;  // 0: automatic
   return old;
 }
 
@@ -351,8 +352,30 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   HaloArgs p = {};
   p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
   p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
-  p.R = g_halo_rows < H ? g_halo_rows : H;
   p.Wp = W + KW - 1;
+  if (g_halo_rows > 0) {
+    p.R = g_halo_rows < H ? g_halo_rows : H;
+  } else {
+    // strip height: outputs are computed on the padded grid in tiles of 128, so the useful fraction of the MMAs is
+    // H * W / (strips * tiles * 128); pick the height that maximises it among those whose double-buffered strip
+    // still leaves room for two CTAs per SM (one CTA alone cannot hide its own strip turnaround)
+    const int nc_ = C / cpc;
+    const bool c4_ = !in16 && C == 4;
+    const size_t w_bytes = (size_t)(c4_ ? KH * ((KW + 1) & ~1) : KH * KW * nc_) * Cout * 16;
+    int best = 0;
+    double best_eff = -1.0;
+    for (int pass = 0; pass < 2 && best == 0; ++pass) {
+      const size_t budget = pass == 0 ? 108 * 1024 : 200 * 1024;
+      for (int R = 1; R <= H; ++R) {
+        const int tiles = avl_div_up((long long)R * p.Wp, HL_TILE);
+        const size_t in_plane = (size_t)(tiles * HL_TILE + (KH - 1) * p.Wp + KW + 8) * 16;
+        if (w_bytes + 2 * nc_ * in_plane > budget) break;
+        const double eff = (double)H * W / ((double)avl_div_up(H, R) * tiles * HL_TILE);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = R; }
+      }
+    }
+    p.R = best > 0 ? best : (8 < H ? 8 : H);
+  }
   p.tiles = avl_div_up((long long)p.R * p.Wp, HL_TILE);
   p.strips_per_img = avl_div_up(H, p.R);
   long long total = (long long)N * p.strips_per_img;

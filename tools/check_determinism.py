@@ -32,4 +32,4 @@ for n in (2, 9, 64):
             torch.cuda.synchronize()
             print(f"n={n} splitk={sk} halo={halo}: single rerun {rel(a2, a1):.2e}  pair-vs-single {rel(p0, a1):.2e} {rel(p1, b1):.2e}  "
                   f"pair rerun {rel(o0, p0):.2e}  layers-vs-single {rel(lay, a1):.2e}", flush=True)
-K._lib.lib().avl_set_tc_splitk(1); K.set_conv_halo(1, 8)
+K._lib.lib().avl_set_tc_splitk(1); K.set_conv_halo(1, 0)

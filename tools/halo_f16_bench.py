@@ -27,9 +27,12 @@ def timeit(fn, flush, n=7):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 4800
     lib = _lib.lib()
+    if len(sys.argv) > 2:
+        K.set_conv_halo(1, int(sys.argv[2]))   # strip height (output rows per strip)
+        print("strip rows", sys.argv[2])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name, H, W, C, Co, k in (("layer1 3x3 16->16 @64", 64, 64, 16, 16, 3), ("layer2 3x3 32->32 @32", 32, 32, 32, 32, 3),
-                                 ("conv1 7x7 4->16 @64", 64, 64, 4, 16, 7)):
+                                 ("layer3 3x3 64->64 @16", 16, 16, 64, 64, 3), ("conv1 7x7 4->16 @64", 64, 64, 4, 16, 7)):
         x32 = torch.randn(B, H, W, C, device="cuda")
         w32 = K.round_to_tf32((torch.randn(Co, k, k, C, device="cuda") / (C * k * k) ** 0.5).contiguous())
         for in16, out16 in ((0, 0), (0, 1), (1, 1)):

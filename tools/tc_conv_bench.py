@@ -35,7 +35,7 @@ def main():
         for level in (4, 3, 2, 1, 0):  # 4: im2col into SWIZZLE_NONE planes; 3: halo-strip kernel; 2: im2col cp.async.ca; 1: cp.async.cg; 0: fp32 SIMT
             K.set_tensor_cores(min(level, 1))
             K._lib.lib().avl_set_tc_conv_l1(1 if level >= 2 else 0)
-            K.set_conv_halo(1 if level == 3 else 0, int(os.environ.get("HALO_ROWS", "8")))
+            K.set_conv_halo(1 if level == 3 else 0, int(os.environ.get("HALO_ROWS", "0")))
             K._lib.lib().avl_set_tc_swizzle(0 if level == 4 else 1)
             for _ in range(2):
                 K.conv2d(x, w, None, s, p)
@@ -53,7 +53,7 @@ def main():
                   f"{byts / ms / 1e6:8.1f} GB/s", flush=True)
     K.set_tensor_cores(1)
     K._lib.lib().avl_set_tc_conv_l1(1)
-    K.set_conv_halo(1, 8)
+    K.set_conv_halo(1, 0)
     K._lib.lib().avl_set_tc_swizzle(1)
 
 
