@@ -17,6 +17,17 @@
 //
 // HBM traffic = read x once (+ (KH-1)/R halo rows, L2 hits) + write y once: the algorithmic bytes of DESIGN.md §4.
 //
+// Pixel groups (G = 2 or 4, layers with Cout <= 32): an MMA with N = Cout = 16 costs as much as one with N = 64 —
+// it is paced by fetching its 4 KB A operand from shared memory, not by its math.  So G horizontally adjacent
+// output pixels are computed by ONE MMA row: row m of a tile is the pixel group g = q / G, the accumulator columns
+// are (dx, cout), and the weight matrix of tap (r, s') — s' in [0, KW + G - 1) — holds W[r, s' - dx] in the column
+// block dx (zero where s' - dx falls outside the kernel).  KH * (KW + G - 1) taps instead of G * KH * KW: 18 MMAs per
+// 512 outputs instead of 36 at 3x3, G = 4.  For the A operand of tap (r, s') to be rows 16 bytes apart again, the
+// padded strip is stored as G phase planes (pixel index P -> plane P % G, slot P / G) and the pitch Wp is a multiple of G.
+// MEASURED (B200, batch 4800, layer1 3x3 16->16 @64x64): fp16 429 -> 559 us, TF32 863 -> 1178 us with G = 4 — half the
+// MMAs but each N = 64 MMA costs ~2.6x an N = 16 one, so the premise (cost independent of N) does not hold; the path
+// is parity-tested and left OFF (avl_set_tc_conv_halo_group).
+//
 // fp16 activation storage (template IN16 / OUT16): the widest tensors of the encoders (stem output and layer1 of
 // custom_resnet18, 64x64x16 per frame) can be kept in HBM as fp16 — the same 10-bit mantissa the TF32 tensor core
 // keeps of an fp32 operand, rounded to nearest instead of truncated.  A chunk plane then holds 8 channels per
@@ -55,6 +66,10 @@ struct HaloArgs {
   int tiles;           // ceil(R * Wp / 128)
   int strips_per_img;  // ceil(H / R)
   int total_strips;
+  int G;               // pixels per MMA row (1, 2 or 4)
+  int g_shift;         // log2(G)
+  int kwe;             // taps per kernel row: KW + G - 1
+  uint32_t ppu;        // 16-byte slots per phase plane (in_plane = G * ppu * 16)
   int nc;              // 16-byte chunk planes of the input: C / 4 (fp32) or C / 8 (fp16)
   int kwp;             // C == 4: KW rounded up to even (weight planes per kernel row), else KW
   uint32_t in_plane;   // bytes per input chunk plane
@@ -146,12 +161,21 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
     for (int e = tid; e < total; e += HL_THREADS) {
       const int n = e / per_n;
       const int rest = e - n * per_n;  // tap * nc + c
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w) + e);  // 16 bytes = 4 fp32 / 8 fp16 channels
+      if (p.G > 1) {  // column block dx of tap (r, s + dx) holds W[r, s]
+        const int tap = rest / p.nc, c = rest - tap * p.nc;
+        const int r = tap / p.KW, sx = tap - r * p.KW;
+        for (int dx = 0; dx < p.G; ++dx) {
+          const int plane = (r * p.kwe + sx + dx) * p.nc + c;
+          *reinterpret_cast<float4*>(smem + (size_t)plane * p.w_plane + (size_t)(dx * p.Cout + n) * 16) = v;
+        }
+        continue;
+      }
       int plane = rest;
       if (p.nc == 1) {  // C == 4: planes indexed (r, s) with kwp planes per kernel row
         const int r = rest / p.KW;
         plane = r * p.kwp + (rest - r * p.KW);
       }
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w) + e);  // 16 bytes = 4 fp32 / 8 fp16 channels
       *reinterpret_cast<float4*>(smem + (size_t)plane * p.w_plane + (size_t)n * 16) = v;
     }
   }
@@ -204,7 +228,9 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
         const int ih = oh0 - pad + ir;
         const bool ok = ih >= 0 && ih < p.H;
         const void* src = ok ? (const void*)(xin + ih * row_bytes + (long long)rem * 16) : p.x;
-        cp_async16(dst0 + (uint32_t)c * p.in_plane + (uint32_t)(ir * p.Wp + pad + iw) * 16, src, ok ? 16u : 0u);
+        const uint32_t P = (uint32_t)(ir * p.Wp + pad + iw);  // padded pixel index -> (phase plane, slot)
+        const uint32_t slot = p.G > 1 ? (P & (uint32_t)(p.G - 1)) * p.ppu + (P >> p.g_shift) : P;
+        cp_async16(dst0 + (uint32_t)c * p.in_plane + slot * 16, src, ok ? 16u : 0u);
         rem += HL_LOAD_THREADS;
         while (rem >= per_row) { rem -= per_row; ++ir; }
       }
@@ -261,22 +287,26 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
       const int oh0 = (strip - n * p.strips_per_img) * p.R;
       for (int t = 0; t < p.tiles; ++t, ++it_tile) {
         const int a = it_tile & 1;
-        const int q = t * HL_TILE + warp * 32 + lane;
+        const int q = (t * HL_TILE + warp * 32 + lane) << p.g_shift;  // first pixel of this row's group
         const int ohl = q / p.Wp;
-        const int ow = q - ohl * p.Wp;
+        const int ow0 = q - ohl * p.Wp;
         const int oh = oh0 + ohl;
-        const bool valid = ow < p.W && ohl < p.R && oh < p.H;
-        const long long pix = ((long long)n * p.H + oh) * p.W + ow;
+        const bool row_ok = ohl < p.R && oh < p.H;
+        const long long pix0 = ((long long)n * p.H + oh) * p.W + ow0;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.ncols);
         mbar_wait(ACC_FULL(a), (uint32_t)((it_tile >> 1) & 1));
         tc_fence_after();
-        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        for (int cc = 0; cc < p.ncols; cc += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          if (c0 + 16 >= p.Cout) {  // accumulator fully read: hand the TMEM buffer back before the stores
+          tmem_ld16(taddr + cc, v);
+          if (cc + 16 >= p.ncols) {  // accumulator fully read: hand the TMEM buffer back before the stores
             tc_fence_before();
             mbar_arrive(ACC_EMPTY(a));
           }
+          const int dx = p.G > 1 ? cc / p.Cout : 0;  // accumulator columns are (dx, cout); Cout % 16 == 0
+          const int c0 = cc - dx * p.Cout;
+          const bool valid = row_ok && ow0 + dx < p.W;
+          const long long pix = pix0 + dx;
           if (valid) {
             float* yrow = reinterpret_cast<float*>(p.y) + pix * p.ldy + c0;  // (OUT16: recomputed below)
             const float* rrow = p.residual ? p.residual + pix * p.ldr + c0 : nullptr;
@@ -319,6 +349,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
 }
 
 static int g_halo_on = 1;
+static int g_halo_group = 0;  // pixel groups (G > 1): measured SLOWER on B200 (see header), kept as an opt-in
 static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
 
 }  // namespace
@@ -330,6 +361,13 @@ AVL_API int avl_set_tc_conv_halo(int on, int rows) {
   int old = g_halo_on;
   g_halo_on = on ? 1 : 0;
   if (rows >= 0) g_halo_rows = rows;  // 0: automatic
+  return old;
+}
+
+// 1: layers with Cout <= 32 compute 2 / 4 adjacent pixels per MMA row; 0 (default): one pixel per row.  Returns old.
+AVL_API int avl_set_tc_conv_halo_group(int on) {
+  int old = g_halo_group;
+  g_halo_group = on ? 1 : 0;
   return old;
 }
 
@@ -352,43 +390,57 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   HaloArgs p = {};
   p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
   p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
-  p.Wp = W + KW - 1;
+  const int nc_ = C / cpc;
+  const bool c4 = !in16 && C == 4;
+  // pixels per MMA row: fill N up to 64 accumulator columns when Cout is small (see the header); kept at 1 for the
+  // C == 4 stem path, for wide kernels whose descriptor table would not fit the parameter space, and when disabled
+  int G = 1;
+  if (g_halo_group && !c4 && KH == 3) {
+    if (Cout * 4 <= 64 && (W % 4) == 0) G = 4;
+    else if (Cout * 2 <= 64 && (W % 2) == 0) G = 2;
+    if (KH * (KW + G - 1) * (nc_ / 2) > HL_PARAM_MMA) G = 1;
+  }
+  p.G = G;
+  p.g_shift = G == 4 ? 2 : (G == 2 ? 1 : 0);
+  p.kwe = KW + G - 1;
+  p.Wp = (W + KW - 1 + G - 1) / G * G;
+  const int gpr = p.Wp / G;  // MMA rows (pixel groups) per padded image row
+  const size_t w_bytes = (size_t)(c4 ? KH * ((KW + 1) & ~1) : KH * p.kwe * nc_) * G * Cout * 16;
+  auto plane_units = [&](int tiles) {  // 16-byte slots of one phase plane
+    return (size_t)tiles * HL_TILE + (size_t)((KH - 1) * p.Wp) / G + (size_t)(KW - 1 + G - 1) / G + 8;
+  };
   if (g_halo_rows > 0) {
     p.R = g_halo_rows < H ? g_halo_rows : H;
   } else {
-    // strip height: outputs are computed on the padded grid in tiles of 128, so the useful fraction of the MMAs is
-    // H * W / (strips * tiles * 128); pick the height that maximises it among those whose double-buffered strip
-    // still leaves room for two CTAs per SM (one CTA alone cannot hide its own strip turnaround)
-    const int nc_ = C / cpc;
-    const bool c4_ = !in16 && C == 4;
-    const size_t w_bytes = (size_t)(c4_ ? KH * ((KW + 1) & ~1) : KH * KW * nc_) * Cout * 16;
+    // strip height: outputs are computed on the padded grid in tiles of 128 rows (x G pixels), so the useful
+    // fraction of the MMAs is H * W / (strips * tiles * 128 * G); pick the height that maximises it among those whose
+    // double-buffered strip still leaves room for two CTAs per SM (one CTA alone cannot hide its strip turnaround)
     int best = 0;
     double best_eff = -1.0;
     for (int pass = 0; pass < 2 && best == 0; ++pass) {
       const size_t budget = pass == 0 ? 108 * 1024 : 200 * 1024;
       for (int R = 1; R <= H; ++R) {
-        const int tiles = avl_div_up((long long)R * p.Wp, HL_TILE);
-        const size_t in_plane = (size_t)(tiles * HL_TILE + (KH - 1) * p.Wp + KW + 8) * 16;
+        const int tiles = avl_div_up((long long)R * gpr, HL_TILE);
+        const size_t in_plane = plane_units(tiles) * G * 16;
         if (w_bytes + 2 * nc_ * in_plane > budget) break;
-        const double eff = (double)H * W / ((double)avl_div_up(H, R) * tiles * HL_TILE);
+        const double eff = (double)H * W / ((double)avl_div_up(H, R) * tiles * HL_TILE * G);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = R; }
       }
     }
     p.R = best > 0 ? best : (8 < H ? 8 : H);
   }
-  p.tiles = avl_div_up((long long)p.R * p.Wp, HL_TILE);
+  p.tiles = avl_div_up((long long)p.R * gpr, HL_TILE);
   p.strips_per_img = avl_div_up(H, p.R);
   long long total = (long long)N * p.strips_per_img;
   if (total > 2147483647LL) return AVL_ERR_UNSUPPORTED;
   p.total_strips = (int)total;
-  p.nc = C / cpc;
-  const bool c4 = !in16 && C == 4;
+  p.nc = nc_;
   p.kwp = c4 ? ((KW + 1) & ~1) : KW;
-  const int in_pixels = p.tiles * HL_TILE + (KH - 1) * p.Wp + KW + 8;
-  p.in_plane = (uint32_t)in_pixels * 16;
-  p.w_plane = (uint32_t)Cout * 16;
-  p.n_wplanes = c4 ? KH * p.kwp : KH * KW * p.nc;
-  p.n_mma = c4 ? KH * (p.kwp / 2) : KH * KW * (p.nc / 2);
+  p.ppu = (uint32_t)plane_units(p.tiles);
+  p.in_plane = p.ppu * (uint32_t)G * 16;
+  p.w_plane = (uint32_t)(G * Cout) * 16;
+  p.n_wplanes = c4 ? KH * p.kwp : KH * p.kwe * p.nc;
+  p.n_mma = c4 ? KH * (p.kwp / 2) : KH * p.kwe * (p.nc / 2);
   if (p.n_mma > HL_MAX_MMA) return AVL_ERR_UNSUPPORTED;
   if (p.n_mma <= HL_PARAM_MMA) {
     for (int i = 0; i < p.n_mma; ++i) {
@@ -400,13 +452,14 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
       } else {
         const int pairs = p.nc >> 1;
         const int tap = i / pairs, j = (i - tap * pairs) * 2;
-        const int r = tap / KW, s2 = tap - r * KW;
-        p.off_a[i] = (uint32_t)(r * p.Wp + s2) + (uint32_t)j * (p.in_plane >> 4);
+        const int r = tap / p.kwe, s2 = tap - r * p.kwe;  // s2 in [0, KW + G - 1)
+        // padded pixel G * g + r * Wp + s2 of output group g lives in phase plane s2 % G at slot g + r * Wp / G + s2 / G
+        p.off_a[i] = (uint32_t)(s2 % G) * p.ppu + (uint32_t)((r * p.Wp) / G + s2 / G) + (uint32_t)j * (p.in_plane >> 4);
         p.off_b[i] = (uint32_t)(tap * p.nc + j) * (p.w_plane >> 4);
       }
     }
   }
-  p.ncols = Cout;
+  p.ncols = G * Cout;
   int cols = 32;
   while (cols < 2 * p.ncols) cols <<= 1;
   p.tmem_cols = cols;

@@ -42,6 +42,7 @@ _lib.register({
     "avl_tc_gemm_3x": [P, L, P, L, I, P, L, I, I, I, P, P, L, I, P, P],
     "avl_tc_wgrad_3x": [P, L, P, L, P, L, I, I, I, P, P],
     "avl_set_f16_activations": [I],
+    "avl_set_tc_conv_halo_group": [I],
     "avl_tc_conv_halo_f16": [P, I, I, I, I, I, P, I, I, I, I, I, P, I, P],
     "avl_groupnorm_fwd_cluster_f16": [P, P, P, P, P, I, I, I, I, I, F, I, P],
     "avl_set_wgrad_desc": [I, I],

@@ -234,7 +234,8 @@ def test_tc_wgrad_3xtf32_is_fp32_accurate(R, N, K_):
     (5, 64, 64, 4, 16, 7, 0, 1), (7, 64, 64, 16, 16, 3, 1, 1), (3, 65, 26, 16, 16, 3, 1, 0), (4, 32, 32, 32, 32, 3, 1, 1),
     (2, 65, 26, 4, 16, 7, 0, 1), (300, 64, 64, 16, 16, 3, 1, 1),
 ])
-def test_halo_conv_fp16_storage(case):
+@pytest.mark.parametrize("group", [0, 1])
+def test_halo_conv_fp16_storage(case, group):
     """Halo-strip convolution with fp16 operands / fp16 output against torch on the SAME rounded inputs: the products
     are exact in fp32, so only the accumulation order and the output rounding (2^-11) differ."""
     from avlen_b200 import _lib
@@ -247,8 +248,12 @@ def test_halo_conv_fp16_storage(case):
         x, w = x.half(), w.half()
     xd, wd = x.cuda(), w.cuda()
     y = torch.full((N, H, W, Co), float("nan"), dtype=torch.float16 if out16 else torch.float32, device="cuda")
-    rc = _lib.lib().avl_tc_conv_halo_f16(xd.data_ptr(), in16, N, H, W, C, wd.data_ptr(), Co, k, k, k // 2, 1, y.data_ptr(),
-                                         out16, _lib.stream())
+    old_group = _lib.lib().avl_set_tc_conv_halo_group(group)   # 1: 2 / 4 adjacent pixels per MMA row (opt-in path)
+    try:
+        rc = _lib.lib().avl_tc_conv_halo_f16(xd.data_ptr(), in16, N, H, W, C, wd.data_ptr(), Co, k, k, k // 2, 1,
+                                             y.data_ptr(), out16, _lib.stream())
+    finally:
+        _lib.lib().avl_set_tc_conv_halo_group(old_group)
     assert rc == 0
     torch.cuda.synchronize()
     xr = x.float()
