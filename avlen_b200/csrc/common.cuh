@@ -31,6 +31,9 @@ extern "C" int avl_set_cuda_error(int e);
   } while (0)
 
 extern "C" void avl_count_launch();
+extern "C" void avl_add_launches(long long n);
+extern "C" void avl_bump_config_epoch();
+extern "C" long long avl_config_epoch();
 #define AVL_LAUNCH_CHECK()                \
   do {                                    \
     avl_count_launch();                   \

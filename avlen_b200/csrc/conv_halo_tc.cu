@@ -358,6 +358,7 @@ static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
 // im2col-gather kernel.  rows > 0 sets the strip height, rows == 0 selects it per shape (default), rows < 0 keeps it.
 // Returns the previous on/off state.
 AVL_API int avl_set_tc_conv_halo(int on, int rows) {
+  avl_bump_config_epoch();
   int old = g_halo_on;
   g_halo_on = on ? 1 : 0;
   if (rows >= 0) g_halo_rows = rows;  // 0: automatic
@@ -366,6 +367,7 @@ AVL_API int avl_set_tc_conv_halo(int on, int rows) {
 
 // 1: layers with Cout <= 32 compute 2 / 4 adjacent pixels per MMA row; 0 (default): one pixel per row.  Returns old.
 AVL_API int avl_set_tc_conv_halo_group(int on) {
+  avl_bump_config_epoch();
   int old = g_halo_group;
   g_halo_group = on ? 1 : 0;
   return old;

@@ -6,7 +6,15 @@ static int g_num_sms = 0;
 static long long g_launches = 0;
 static int g_use_tc = 1;
 
+static long long g_config_epoch = 0;
+
 extern "C" void avl_count_launch() { ++g_launches; }
+extern "C" void avl_add_launches(long long n) { g_launches += n; }
+long long avl_launch_count_internal() { return g_launches; }
+// every avl_set_* toggle that changes WHICH kernels a call launches bumps the epoch: cached CUDA graphs of whole-network
+// calls (resnet_fwd.cu) are keyed by it
+extern "C" void avl_bump_config_epoch() { ++g_config_epoch; }
+extern "C" long long avl_config_epoch() { return g_config_epoch; }
 
 extern "C" int avl_set_cuda_error(int e) {
   g_last_cuda_error = e;
@@ -43,6 +51,7 @@ AVL_API long long avl_launch_count(void) { return g_launches; }
 AVL_API int avl_set_tensor_cores(int level) {
   int old = g_use_tc;
   g_use_tc = level < 0 ? 0 : (level > 2 ? 2 : level);
+  avl_bump_config_epoch();
   return old;
 }
 AVL_API int avl_get_tensor_cores(void) { return g_use_tc; }

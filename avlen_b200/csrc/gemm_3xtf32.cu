@@ -442,6 +442,7 @@ int g_x3_on = 1;
 }  // namespace
 
 AVL_API int avl_set_tc_3xtf32(int on) {
+  avl_bump_config_epoch();
   int old = g_x3_on;
   g_x3_on = on ? 1 : 0;
   return old;

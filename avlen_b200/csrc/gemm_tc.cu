@@ -372,6 +372,7 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
 
 // Shared-memory operand layout of the generic kernel: 1 (default) SWIZZLE_128B K-major tiles, 0 SWIZZLE_NONE planes.
 AVL_API int avl_set_tc_swizzle(int on) {
+  avl_bump_config_epoch();
   int old = g_tc_swz;
   g_tc_swz = on ? 1 : 0;
   return old;
@@ -379,6 +380,7 @@ AVL_API int avl_set_tc_swizzle(int on) {
 
 // 1 (default): small-M / long-K problems are split over K (atomic partial sums); 0: never.  Returns the old value.
 AVL_API int avl_set_tc_splitk(int on) {
+  avl_bump_config_epoch();
   int old = g_tc_splitk;
   g_tc_splitk = on ? 1 : 0;
   return old;
@@ -386,6 +388,7 @@ AVL_API int avl_set_tc_splitk(int on) {
 
 // 1 (default): im2col gathers go through L1 (cp.async.ca); 0: L2 only (cp.async.cg).  Returns the old value.
 AVL_API int avl_set_tc_conv_l1(int on) {
+  avl_bump_config_epoch();
   int old = g_tc_ca;
   g_tc_ca = on ? 1 : 0;
   return old;

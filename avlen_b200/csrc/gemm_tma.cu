@@ -187,6 +187,7 @@ int g_tma_on = 1;
 }  // namespace
 
 AVL_API int avl_set_tc_tma(int on) {
+  avl_bump_config_epoch();
   int old = g_tma_on;
   g_tma_on = on ? 1 : 0;
   return old;

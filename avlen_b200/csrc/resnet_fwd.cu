@@ -14,6 +14,7 @@
 
 #ifndef AVL_HOST_EMUL
 #include <cuda_fp16.h>
+#include <string.h>
 
 // typed entries of the halo-strip convolution and the cluster GroupNorm (fp16 activation storage)
 int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
@@ -22,6 +23,7 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
 int avl_groupnorm_cluster_typed(const void* x, int in16, const float* gamma, const float* beta, const void* residual,
                                 void* y, int out16, int N, int HW, int C, int groups, float eps, int relu,
                                 void* stream);
+long long avl_launch_count_internal();
 
 namespace {
 
@@ -311,6 +313,125 @@ int side_for(cudaStream_t s, Side** out) {
   return AVL_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- CUDA graphs
+// At rollout batch a network is a chain of ~50 small kernels: ~0.2 ms of host launch time per network and a launch
+// gap between every dependent pair.  A whole-network call whose arguments (pointers, shapes, parameter table,
+// library toggles) repeat is captured once into a CUDA graph — fork / join of the second network included — and
+// replayed with one cudaGraphLaunch.  A key is captured the SECOND time it is seen (the first, direct run is the
+// warm-up: lazy attribute / stream / driver-entry initialisation must not happen under capture, and one-off
+// argument sets are never captured).  Only small batches use this (large ones are not launch-bound).
+int g_graphs_on = 1;
+constexpr int GR_MAX_BATCH = 512;
+constexpr int GR_SLOTS = 48;
+
+struct GraphKey {
+  const void* x[2];
+  const void* out[2];
+  const void* ws[2];
+  long long ldo[2];
+  long long epoch;
+  int N, H, W, cin[2], use_tc, pair;
+  float eps;
+  int cfg[2][12];
+  const float* params[2][RN_COUNT];
+};
+struct GraphSlot {
+  GraphKey key;
+  cudaGraphExec_t exec;  // null: key seen once, not captured yet
+  long long launches;
+  unsigned long long last_use;
+  bool used;
+};
+GraphSlot g_slots[GR_SLOTS];
+unsigned long long g_graph_clock = 0;
+long long g_graph_hits = 0, g_graph_captures = 0;
+
+GraphSlot* graph_find(const GraphKey& k) {
+  for (int i = 0; i < GR_SLOTS; ++i)
+    if (g_slots[i].used && memcmp(&g_slots[i].key, &k, sizeof(GraphKey)) == 0) return &g_slots[i];
+  return nullptr;
+}
+GraphSlot* graph_new(const GraphKey& k) {
+  GraphSlot* v = &g_slots[0];
+  for (int i = 0; i < GR_SLOTS; ++i) {
+    if (!g_slots[i].used) { v = &g_slots[i]; break; }
+    if (g_slots[i].last_use < v->last_use) v = &g_slots[i];
+  }
+  if (v->used && v->exec) cudaGraphExecDestroy(v->exec);
+  v->key = k;
+  v->exec = nullptr;
+  v->launches = 0;
+  v->used = true;
+  return v;
+}
+// Returns true when the call was served (rc holds its status): replayed, or captured + launched.  false: the caller
+// launches directly (first sighting of the key, or capture unavailable).
+template <class F>
+bool graph_call(const GraphKey& k, cudaStream_t s, int& rc, F&& body) {
+  ++g_graph_clock;
+  GraphSlot* slot = graph_find(k);
+  if (!slot) {
+    slot = graph_new(k);
+    slot->last_use = g_graph_clock;
+    return false;  // first sighting: direct run (warm-up)
+  }
+  slot->last_use = g_graph_clock;
+  if (!slot->exec) {
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+    // instantiated graph is launched into the caller's stream
+    static cudaStream_t cap = nullptr;
+    if (!cap) {
+      if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); g_graphs_on = 0; return false; }
+      Side* warm = nullptr;
+      if (side_for(cap, &warm) != AVL_OK) { g_graphs_on = 0; return false; }  // fork / join resources exist before capture
+    }
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      g_graphs_on = 0;
+      return false;
+    }
+    const long long l0 = avl_launch_count_internal();
+    const int brc = body(cap);
+    const long long l1 = avl_launch_count_internal();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    if (brc != AVL_OK || e != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g_graphs_on = 0;  // something on this path cannot be captured: stay on direct launches for good
+      avl_add_launches(-(l1 - l0));
+      if (brc != AVL_OK) { rc = brc; return true; }
+      return false;
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess || !exec) {
+      cudaGetLastError();
+      cudaGraphDestroy(graph);
+      g_graphs_on = 0;
+      avl_add_launches(-(l1 - l0));
+      return false;
+    }
+    cudaGraphDestroy(graph);
+    slot->exec = exec;
+    slot->launches = l1 - l0;
+    avl_add_launches(-(l1 - l0));  // counted at capture, but nothing ran yet: the replay below counts them
+    ++g_graph_captures;
+  } else {
+    ++g_graph_hits;
+  }
+  if (cudaGraphLaunch(slot->exec, s) != cudaSuccess) {
+    avl_set_cuda_error((int)cudaGetLastError());
+    rc = AVL_ERR_CUDA;
+    return true;
+  }
+  avl_add_launches(slot->launches);
+  rc = AVL_OK;
+  return true;
+}
+
 }  // namespace
 
 AVL_API int avl_resnet18_param_count(void) { return RN_COUNT; }
@@ -318,6 +439,7 @@ AVL_API int avl_resnet18_param_count(void) { return RN_COUNT; }
 // 1 (default): the fused GroupNorm ResNet-18 keeps its stem output and stage 1 in HBM as fp16 (tensor-core path only);
 // 0: fp32 activations everywhere.  Returns the previous setting.
 AVL_API int avl_set_f16_activations(int on) {
+  avl_bump_config_epoch();
   int old = g_f16_act;
   g_f16_act = on ? 1 : 0;
   return old;
@@ -343,6 +465,19 @@ AVL_API int avl_resnet18_forward(const float* x, int N, int H, int W, int Cin, c
   if (N == 0) return AVL_OK;
   if (!x || !params || !out || !workspace) return AVL_ERR_ARG;
   n.eps = eps;
+  if (g_graphs_on && N <= GR_MAX_BATCH) {
+    GraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.x[0] = x; k.out[0] = out; k.ws[0] = workspace; k.ldo[0] = ldo; k.epoch = avl_config_epoch();
+    k.N = N; k.H = H; k.W = W; k.cin[0] = Cin; k.use_tc = use_tc; k.pair = 0; k.eps = eps;
+    memcpy(k.cfg[0], cfg, sizeof(k.cfg[0]));
+    memcpy(k.params[0], params, sizeof(k.params[0]));
+    int rc = AVL_OK;
+    if (graph_call(k, (cudaStream_t)stream, rc, [&](cudaStream_t cs) {
+          return run(n, x, params, out, ldo, use_tc, static_cast<float*>(workspace), cs);
+        }))
+      return rc;
+  }
   return run(n, x, params, out, ldo, use_tc, static_cast<float*>(workspace), stream);
 }
 
@@ -359,15 +494,40 @@ AVL_API int avl_resnet18_forward_pair(const float* x0, const float* x1, int N, i
   if (!x0 || !x1 || !params0 || !params1 || !out0 || !out1 || !workspace0 || !workspace1) return AVL_ERR_ARG;
   a.eps = b.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
-  Side* sd = nullptr;
-  int rcs = side_for(s, &sd);
-  if (rcs) return rcs;
-  AVL_CUDA_CHECK(cudaEventRecord(sd->fork, s));
-  AVL_CUDA_CHECK(cudaStreamWaitEvent(sd->side, sd->fork, 0));
-  int rc1 = run(b, x1, params1, out1, ldo1, use_tc, static_cast<float*>(workspace1), sd->side);
-  int rc0 = run(a, x0, params0, out0, ldo0, use_tc, static_cast<float*>(workspace0), s);
-  AVL_CUDA_CHECK(cudaEventRecord(sd->join, sd->side));
-  AVL_CUDA_CHECK(cudaStreamWaitEvent(s, sd->join, 0));
-  return rc0 ? rc0 : rc1;
+  auto body = [&](cudaStream_t cs) -> int {
+    Side* sd = nullptr;
+    int rcs = side_for(cs, &sd);
+    if (rcs) return rcs;
+    AVL_CUDA_CHECK(cudaEventRecord(sd->fork, cs));
+    AVL_CUDA_CHECK(cudaStreamWaitEvent(sd->side, sd->fork, 0));
+    int rc1 = run(b, x1, params1, out1, ldo1, use_tc, static_cast<float*>(workspace1), sd->side);
+    int rc0 = run(a, x0, params0, out0, ldo0, use_tc, static_cast<float*>(workspace0), cs);
+    AVL_CUDA_CHECK(cudaEventRecord(sd->join, sd->side));
+    AVL_CUDA_CHECK(cudaStreamWaitEvent(cs, sd->join, 0));
+    return rc0 ? rc0 : rc1;
+  };
+  if (g_graphs_on && N <= GR_MAX_BATCH) {
+    GraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.x[0] = x0; k.x[1] = x1; k.out[0] = out0; k.out[1] = out1; k.ws[0] = workspace0; k.ws[1] = workspace1;
+    k.ldo[0] = ldo0; k.ldo[1] = ldo1; k.epoch = avl_config_epoch();
+    k.N = N; k.H = H; k.W = W; k.cin[0] = Cin0; k.cin[1] = Cin1; k.use_tc = use_tc; k.pair = 1; k.eps = eps;
+    memcpy(k.cfg[0], cfg0, sizeof(k.cfg[0]));
+    memcpy(k.cfg[1], cfg1, sizeof(k.cfg[1]));
+    memcpy(k.params[0], params0, sizeof(k.params[0]));
+    memcpy(k.params[1], params1, sizeof(k.params[1]));
+    int rc = AVL_OK;
+    if (graph_call(k, s, rc, body)) return rc;
+  }
+  return body(s);
 }
+
+// 1 (default): whole-network calls at small batch replay a cached CUDA graph; 0: always launch kernel by kernel.
+AVL_API int avl_set_resnet_graphs(int on) {
+  int old = g_graphs_on;
+  g_graphs_on = on ? 1 : 0;
+  return old;
+}
+// hits (replays) and captures so far
+AVL_API long long avl_resnet_graph_stats(int what) { return what == 0 ? g_graph_hits : g_graph_captures; }
 #endif  // AVL_HOST_EMUL

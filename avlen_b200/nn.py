@@ -42,6 +42,7 @@ _lib.register({
     "avl_tc_gemm_3x": [P, L, P, L, I, P, L, I, I, I, P, P, L, I, P, P],
     "avl_tc_wgrad_3x": [P, L, P, L, P, L, I, I, I, P, P],
     "avl_set_f16_activations": [I],
+    "avl_set_resnet_graphs": [I],
     "avl_set_tc_conv_halo_group": [I],
     "avl_tc_conv_halo_f16": [P, I, I, I, I, I, P, I, I, I, I, I, P, I, P],
     "avl_groupnorm_fwd_cluster_f16": [P, P, P, P, P, I, I, I, I, I, F, I, P],
@@ -58,7 +59,9 @@ _lib.register({
     "avl_gru_workspace_bytes": [I, I, I, I, I],
     "avl_gru_forward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
-}, {"avl_gru_workspace_bytes": c_longlong, "avl_resnet18_workspace_bytes": c_longlong})
+    "avl_resnet_graph_stats": [I],
+}, {"avl_gru_workspace_bytes": c_longlong, "avl_resnet18_workspace_bytes": c_longlong,
+    "avl_resnet_graph_stats": c_longlong})
 
 _gn_scratch = {}
 _gn_cluster = [True]
@@ -101,6 +104,16 @@ def sync_pending():
         for ev in _pending_events:
             cur.wait_event(ev)
         _pending_events.clear()
+
+
+def set_resnet_graphs(on: bool) -> bool:
+    """CUDA-graph replay of repeated whole-network calls at small batch (csrc/resnet_fwd.cu).  Returns the old setting."""
+    return bool(_lib.lib().avl_set_resnet_graphs(int(bool(on))))
+
+
+def resnet_graph_stats():
+    """(replays, captures) of whole-network CUDA graphs so far."""
+    return int(_lib.lib().avl_resnet_graph_stats(0)), int(_lib.lib().avl_resnet_graph_stats(1))
 
 
 def set_f16_activations(on: bool) -> bool:

@@ -175,6 +175,10 @@ int avl_set_wgrad_desc(int lbo_bytes, int sbo_bytes);   /* diagnostic */
  * entries below expose the kernels for tests / benches: x (and w, packed (Cout,KH,KW,C)) fp16 when in16, y fp16 when
  * out16; stride 1, pad = K/2.  -2: shape not covered.                                                             */
 int avl_set_f16_activations(int on);   /* returns old */
+/* Whole-network calls (avl_resnet18_forward / _pair) at batch <= 512 whose arguments repeat are captured into a CUDA
+ * graph the second time they are seen and replayed afterwards (1 graph launch instead of ~50-100 kernel launches).  */
+int avl_set_resnet_graphs(int on);     /* returns old */
+long long avl_resnet_graph_stats(int what);   /* 0: replays, 1: captures */
 int avl_set_tc_conv_halo_group(int on); /* halo-strip conv: 2 / 4 adjacent pixels per MMA row when Cout <= 32; returns old */
 int avl_tc_conv_halo_f16(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
                          int KW, int pad, int relu, void* y, int out16, void* stream);

@@ -280,3 +280,48 @@ def test_fused_resnet_call_matches_layer_by_layer(tc):
             assert rel(c_fused, c_layers) < (5e-3 if tc else 1e-5)
     finally:
         K.set_tensor_cores(old)
+
+
+def test_resnet_graph_replay_matches_direct_launches():
+    """Whole-network calls whose arguments repeat are captured into a CUDA graph (second sighting) and replayed: the
+    replay must produce what the kernel-by-kernel launches produce, follow in-place weight updates (same pointers) and
+    re-capture when an argument changes."""
+    from avlen_b200 import nn as K
+    from avlen_b200.savi.models.smt_resnet import custom_resnet18
+    torch.manual_seed(11)
+    nets = [custom_resnet18(num_input_channels=c).cuda().eval() for c in (3, 1)]
+    for net in nets:
+        for q in net.parameters():
+            q.requires_grad = False
+    x0, x1 = torch.rand(7, 64, 64, 3, device="cuda"), torch.rand(7, 64, 64, 1, device="cuda")
+    xin0, xin1 = K._prep_net_input(x0, 1), K._prep_net_input(x1, 1)   # fixed addresses
+    out = torch.zeros(7, 128, device="cuda")
+
+    def call():
+        with torch.no_grad():
+            K.resnet18_forward_pair(nets[0].plan(), xin0, out[:, :64], nets[1].plan(), xin1, out[:, 64:])
+        torch.cuda.synchronize()
+        return out.clone()
+
+    old = K.set_resnet_graphs(False)
+    try:
+        want = call()
+        K.set_resnet_graphs(True)
+        h0, c0 = K.resnet_graph_stats()
+        a = call()   # first sighting: direct
+        b = call()   # captured + launched
+        c = call()   # replayed
+        h1, c1 = K.resnet_graph_stats()
+        assert c1 == c0 + 1 and h1 == h0 + 1
+        for got in (a, b, c):
+            assert rel(got, want) < 5e-3   # split-K atomics: run-to-run agreement at the TF32 tolerance
+        # in-place change of the input: the replay reads the new data
+        xin0.copy_(torch.rand_like(xin0))   # (a rescaling would be undone by the GroupNorms)
+        K.set_resnet_graphs(False)
+        want2 = call()
+        K.set_resnet_graphs(True)
+        got2 = call()
+        assert K.resnet_graph_stats()[0] == h1 + 1
+        assert rel(got2, want2) < 5e-3 and rel(got2, want) > 1e-2
+    finally:
+        K.set_resnet_graphs(old)

@@ -17,3 +17,5 @@ for rep in range(3):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print(f"20 steps: host issue {1e3 * (t1 - t0) / 20:.3f} ms/step, incl. drain {1e3 * (t2 - t0) / 20:.3f} ms/step", flush=True)
+from avlen_b200 import nn as K
+print("resnet graph (replays, captures):", K.resnet_graph_stats(), flush=True)
