@@ -10,7 +10,7 @@
 //   * A (activations, up to ~4e5 rows) arrives raw by TMA; four "splitter" warps rewrite the landed tile in shared
 //     memory as hi (in place) and lo (second buffer) — elementwise, so the SWIZZLE_128B placement is untouched —
 //     fence it towards the async proxy and hand it to the MMA warp.
-// Warps 0-3: splitters, then the epilogue; warp 4: MMA issue (elect.sync); warp 5: TMA producer.
+// Warps 0-3: splitters; warps 4-7: epilogue; warp 8: MMA issue (elect.sync); warp 9: TMA producer (persistent CTAs).
 #include "tc_common.cuh"
 
 #ifndef AVL_HOST_EMUL
@@ -18,12 +18,13 @@
 
 namespace {
 
-constexpr int X3_BM = 128, X3_BK = 32, X3_STAGES = 2, X3_THREADS = 192, X3_SPLITTERS = 128;
+constexpr int X3_BM = 128, X3_BK = 32, X3_STAGES = 2, X3_SPLITTERS = 128, X3_EPI = 128;
+constexpr int X3_THREADS = X3_SPLITTERS + X3_EPI + 64;  // warps 0-3 split, 4-7 epilogue, 8 MMA, 9 TMA
 
 struct X3Args {
   float* C;
   long long ldc;
-  int M, N, K, bn, tmem_cols;
+  int M, N, K, bn, n_tiles, tmem_cols;
   const float* bias;
   const float* residual;
   long long ldr;
@@ -38,18 +39,21 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// PERSISTENT: one CTA per SM walks the output tiles (tile = blockIdx.x, + gridDim.x, ...); the TMA -> split -> MMA
+// pipeline runs straight through tile boundaries and the accumulator is double-buffered in TMEM (2 x bn columns), so
+// the epilogue of tile i (tcgen05.ld, bias / residual / ReLU, 16-byte stores) overlaps the main loop of tile i + 1.
+// The first version (one tile per CTA, profiles/r01_gemm3x_ncu_full.txt) kept the tensor pipe 31 % busy: prologue,
+// pipeline fill and the 128 KB epilogue of every tile were serial.
 __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmBhi,
                                                                 const __grid_constant__ CUtensorMap tmBlo, X3Args p) {
   AVL_DYN_SMEM(smem);
-  __shared__ __align__(8) unsigned long long bars[3 * X3_STAGES + 1];  // full[S], split[S], empty[S], done
+  __shared__ __align__(8) unsigned long long bars[3 * X3_STAGES + 4];  // full[S], split[S], empty[S], acc_full[2], acc_empty[2]
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
-  const int m0 = blockIdx.x * X3_BM;
-  if (m0 >= M) return;
-  const int n0 = blockIdx.y * p.bn;
+  const int total_tiles = ((M + X3_BM - 1) / X3_BM) * p.n_tiles;
   const int bn = p.bn;
   const int KT = (p.K + X3_BK - 1) / X3_BK;
   const uint32_t a_tile = X3_BM * 128u, b_tile = (uint32_t)bn * 128u;
@@ -59,20 +63,24 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto SPLIT = [&](int s) { return bar0 + 8u * (X3_STAGES + s); };
   auto EMPTY = [&](int s) { return bar0 + 8u * (2 * X3_STAGES + s); };
-  const uint32_t DONE = bar0 + 8u * (3 * X3_STAGES);
+  auto ACC_FULL = [&](int a) { return bar0 + 8u * (3 * X3_STAGES + a); };
+  auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (3 * X3_STAGES + 2 + a); };
   if (tid == 0) {
     for (int i = 0; i < X3_STAGES; ++i) {
       mbar_init(FULL(i), 1);
       mbar_init(SPLIT(i), X3_SPLITTERS);
       mbar_init(EMPTY(i), 1);
     }
-    mbar_init(DONE, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(ACC_FULL(a), 1);
+      mbar_init(ACC_EMPTY(a), X3_EPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmBhi);
     tma_prefetch_desc(&tmBlo);
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -83,105 +91,125 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ================================================================================ TMA producer
     if (lane == 0) {
-      for (int kt = 0; kt < KT; ++kt) {
-        const int slot = kt % X3_STAGES;
-        if (kt >= X3_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / X3_STAGES - 1) & 1));
-        const uint32_t base = smem_base + slot * stage_bytes;
-        mbar_arrive_expect_tx(FULL(slot), a_tile + 2 * b_tile);
-        tma_load_2d(base, &tmA, kt * X3_BK, m0, FULL(slot));
-        tma_load_2d(base + 2 * a_tile, &tmBhi, kt * X3_BK, n0, FULL(slot));
-        tma_load_2d(base + 2 * a_tile + b_tile, &tmBlo, kt * X3_BK, n0, FULL(slot));
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * X3_BM, n0 = (tile % p.n_tiles) * bn;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const int slot = it % X3_STAGES;
+          if (it >= X3_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((it / X3_STAGES - 1) & 1));
+          const uint32_t base = smem_base + slot * stage_bytes;
+          mbar_arrive_expect_tx(FULL(slot), a_tile + 2 * b_tile);
+          tma_load_2d(base, &tmA, kt * X3_BK, m0, FULL(slot));
+          tma_load_2d(base + 2 * a_tile, &tmBhi, kt * X3_BK, n0, FULL(slot));
+          tma_load_2d(base + 2 * a_tile + b_tile, &tmBlo, kt * X3_BK, n0, FULL(slot));
+        }
       }
     }
-    __syncthreads();  // matches the final barrier of the other roles
-    return;
-  }
-  if (warp == 4) {
+  } else if (warp == 8) {
     // ================================================================================ MMA issuer
     const uint32_t idesc = umma_idesc_tf32(X3_BM, bn);
-    for (int kt = 0; kt < KT; ++kt) {
-      const int slot = kt % X3_STAGES;
-      mbar_wait(SPLIT(slot), (uint32_t)((kt / X3_STAGES) & 1));
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      mbar_wait(ACC_EMPTY(acc), (uint32_t)(((ti >> 1) & 1) ^ 1));  // first use of each accumulator passes
       tc_fence_after();
-      const uint32_t base = smem_base + slot * stage_bytes;
-      const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + a_tile);
-      const uint64_t bhi = umma_desc_sw128(base + 2 * a_tile), blo = umma_desc_sw128(base + 2 * a_tile + b_tile);
+      const uint32_t d = tmem_base + (uint32_t)(acc * bn);
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const int slot = it % X3_STAGES;
+        mbar_wait(SPLIT(slot), (uint32_t)((it / X3_STAGES) & 1));
+        tc_fence_after();
+        const uint32_t base = smem_base + slot * stage_bytes;
+        const uint64_t ahi = umma_desc_sw128(base), alo = umma_desc_sw128(base + a_tile);
+        const uint64_t bhi = umma_desc_sw128(base + 2 * a_tile), blo = umma_desc_sw128(base + 2 * a_tile + b_tile);
 #pragma unroll
-      for (int q = 0; q < X3_BK / 8; ++q) {
-        umma_tf32_elect(tmem_base, alo + 2u * q, bhi + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);  // small terms first
-        umma_tf32_elect(tmem_base, ahi + 2u * q, blo + 2u * q, idesc, 1u);
-        umma_tf32_elect(tmem_base, ahi + 2u * q, bhi + 2u * q, idesc, 1u);
-      }
-      umma_commit_elect(EMPTY(slot));
-    }
-    umma_commit_elect(DONE);
-    for (int kt = max(0, KT - X3_STAGES); kt < KT; ++kt)
-      mbar_wait(EMPTY(kt % X3_STAGES), (uint32_t)((kt / X3_STAGES) & 1));
-    tc_fence_before();
-    __syncthreads();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    return;
-  }
-  // ==================================================================================== splitters (warps 0-3)
-  for (int kt = 0; kt < KT; ++kt) {
-    const int slot = kt % X3_STAGES;
-    mbar_wait(FULL(slot), (uint32_t)((kt / X3_STAGES) & 1));
-    float4* hi = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes);
-    float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes + a_tile);
-#pragma unroll
-    for (int i = 0; i < (int)(X3_BM * 128 / 16) / X3_SPLITTERS; ++i) {
-      const int idx = tid + i * X3_SPLITTERS;
-      const float4 v = hi[idx];
-      float4 h, l;
-      h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-      l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-      hi[idx] = h;
-      lo[idx] = l;
-    }
-    fence_proxy_async();
-    mbar_arrive(SPLIT(slot));
-  }
-  mbar_wait(DONE, 0);
-  tc_fence_after();
-  // ---- epilogue: thread = one output row (TMEM lane), 16 columns at a time
-  const int m = m0 + warp * 32 + lane;
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < bn; c0 += 16) {
-    uint32_t v[16];
-    tmem_ld16(taddr + c0, v);
-    if (m < M) {
-      float* crow = p.C + (long long)m * p.ldc + n0 + c0;
-      const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
-      if (p.vec_store && n0 + c0 + 16 <= p.N) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-          }
-          if (rrow) {
-            const float4 r = *reinterpret_cast<const float4*>(rrow + j);
-            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-          }
-          if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-          *reinterpret_cast<float4*>(crow + j) = x;
+        for (int q = 0; q < X3_BK / 8; ++q) {
+          umma_tf32_elect(d, alo + 2u * q, bhi + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);  // small terms first
+          umma_tf32_elect(d, ahi + 2u * q, blo + 2u * q, idesc, 1u);
+          umma_tf32_elect(d, ahi + 2u * q, bhi + 2u * q, idesc, 1u);
         }
-      } else {
+        umma_commit_elect(EMPTY(slot));
+      }
+      umma_commit_elect(ACC_FULL(acc));
+    }
+    // no commit may still be in flight towards this CTA's barriers when the CTA retires
+    for (int j = max(0, it - X3_STAGES); j < it; ++j) mbar_wait(EMPTY(j % X3_STAGES), (uint32_t)((j / X3_STAGES) & 1));
+    for (int j = max(0, ti - 2); j < ti; ++j) mbar_wait(ACC_FULL(j & 1), (uint32_t)((j >> 1) & 1));
+  } else if (warp < 4) {
+    // ================================================================================ splitters (warps 0-3)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const int slot = it % X3_STAGES;
+        mbar_wait(FULL(slot), (uint32_t)((it / X3_STAGES) & 1));
+        float4* hi = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * stage_bytes + a_tile);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) {
-            float x = __uint_as_float(v[j]);
-            if (p.bias) x += __ldg(p.bias + n);
-            if (rrow) x += rrow[j];
-            if (p.relu) x = fmaxf(x, 0.f);
-            crow[j] = x;
+        for (int i = 0; i < (int)(X3_BM * 128 / 16) / X3_SPLITTERS; ++i) {
+          const int idx = tid + i * X3_SPLITTERS;
+          const float4 v = hi[idx];
+          float4 h, l;
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(SPLIT(slot));
+      }
+    }
+  } else {
+    // ================================================================================ epilogue (warps 4-7)
+    // thread = one output row (TMEM lane = 32 * (warp % 4) + lane), 16 columns at a time
+    const int ew = warp - 4;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      const int m0 = (tile / p.n_tiles) * X3_BM, n0 = (tile % p.n_tiles) * bn;
+      const int m = m0 + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * bn);
+      mbar_wait(ACC_FULL(acc), (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        if (c0 + 16 >= bn) {  // accumulator fully read: hand it back before the stores
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY(acc));
+        }
+        if (m < M) {
+          float* crow = p.C + (long long)m * p.ldc + n0 + c0;
+          const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
+          if (p.vec_store && n0 + c0 + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+              }
+              if (rrow) {
+                const float4 r = *reinterpret_cast<const float4*>(rrow + j);
+                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+              }
+              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              *reinterpret_cast<float4*>(crow + j) = x;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N) {
+                float x = __uint_as_float(v[j]);
+                if (p.bias) x += __ldg(p.bias + n);
+                if (rrow) x += rrow[j];
+                if (p.relu) x = fmaxf(x, 0.f);
+                crow[j] = x;
+              }
+            }
           }
         }
       }
@@ -189,6 +217,10 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
 }
 
 // hi / lo TF32 parts of the (small) B operand; transpose != 0: B is given as [K][N] (ld = row stride) and the parts
@@ -471,8 +503,9 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
     for (int bn = 256; bn >= 64; bn -= 16)
       if (n16 % bn == 0) { p.bn = bn; break; }
   int cols = 32;
-  while (cols < p.bn) cols <<= 1;
+  while (cols < 2 * p.bn) cols <<= 1;  // two accumulators
   p.tmem_cols = cols;
+  p.n_tiles = avl_div_up(N, p.bn);
   p.vec_store = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
                  (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
   CUtensorMap ta, tbh, tbl;
@@ -484,7 +517,8 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid(avl_div_up(M, X3_BM), avl_div_up(N, p.bn));
+  long long tiles = (long long)avl_div_up(M, X3_BM) * p.n_tiles;
+  const int grid = (int)(tiles < avl_num_sms() ? tiles : avl_num_sms());  // persistent: one CTA per SM
   tc_gemm_3x_kernel<<<grid, X3_THREADS, smem, s>>>(ta, tbh, tbl, p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
