@@ -37,6 +37,7 @@ _SIGNATURES = {
     "avl_extmem_insert": [P, P, P, P, P, I, I, I, I, I, P],
     "avl_masked_weighted_ce": [P, P, P, P, I, I, P, P, P],
     "avl_belief_update": [I, P, I, P, P, P, P, I, F, I, P, P, P, P, P, P, P, P],
+    "avl_synth_env_step": [I, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_grad_sumsq": [P, L, P, P, P],
     "avl_clip_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P, F, P],
 }

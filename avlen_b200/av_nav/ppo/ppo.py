@@ -25,7 +25,7 @@ class PPO(nn.Module):
         self.use_normalized_advantage = use_normalized_advantage
         self.device = next(actor_critic.parameters()).device
         self._params, self._flat_p, self._flat_g = flatten_parameters(actor_critic)
-        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps)
+        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps, views=self._params)
         self._loss = ops.PpoLoss(self.device)
 
     def forward(self, *x):

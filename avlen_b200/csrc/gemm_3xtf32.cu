@@ -502,6 +502,9 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   if (n16 > 256)
     for (int bn = 256; bn >= 64; bn -= 16)
       if (n16 % bn == 0) { p.bn = bn; break; }
+  // few row tiles (rollout batch: <= 64 * 151 packed rows): narrower column tiles so that the tiles cover the SMs —
+  // a 128 x 256 tile per CTA left 3/4 of the GPU idle and made every CTA pull the whole split weight (80 KB per k-tile)
+  while (p.bn >= 128 && (p.bn % 32) == 0 && (long long)avl_div_up(M, X3_BM) * avl_div_up(N, p.bn) < avl_num_sms()) p.bn /= 2;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;  // two accumulators
   p.tmem_cols = cols;

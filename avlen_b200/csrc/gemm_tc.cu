@@ -48,7 +48,27 @@ struct TcArgs {
   int swz;           // 1: SWIZZLE_128B K-major operand tiles (default); 0: SWIZZLE_NONE chunk planes
   int kt_per_split;  // k-tiles per blockIdx.z slice; splits > 1: raw partial sums are atomically added into C
   int splits;
+  int cluster_red;   // splits > 1 only.  1: the blockIdx.z slices of one output tile form a thread-block cluster
+                     // (1, 1, splits); partial tiles meet in the owners' shared memory over DSMEM and are summed in
+                     // slice order (deterministic), epilogue applied in the same kernel — no zero / epilogue launches
+  int splits_nz;     // slices that own at least one k-tile (the others only take part in the reduction)
+  unsigned red_off;  // byte offset of the reduction buffer in dynamic shared memory (behind the operand ring)
 };
+
+__device__ __forceinline__ void cluster_arrive_wait() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank, uint32_t a, uint32_t b, uint32_t c,
+                                              uint32_t d) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 template <bool CONV, bool CA = false>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
@@ -66,8 +86,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const int bn = p.bn;
   const int K = p.K;
   const int kt0 = blockIdx.z * p.kt_per_split;  // split-K: this CTA reduces k-tiles [kt0, kt0 + KT)
-  const int KT = min((K + TC_BK - 1) / TC_BK - kt0, p.kt_per_split);
-  if (KT <= 0) return;
+  const int KT = max(0, min((K + TC_BK - 1) / TC_BK - kt0, p.kt_per_split));
+  const bool cred = p.cluster_red != 0;
+  if (KT <= 0 && !cred) return;  // (a cluster member without k-tiles still owns output rows of the reduction)
 
   // SWIZZLE_NONE: chunk c of row r at c * plane + r * 16 (plane = rows * 16 + 16).
   // SWIZZLE_128B : one k-tile row is exactly one 128-byte swizzle row: chunk c of row r at r * 128 + ((c ^ (r & 7)) * 16),
@@ -102,6 +123,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // distributed shared memory of a peer may only be written once that peer has started executing: every thread
+  // arrives here and waits (cluster_wait_started) right before its first remote store
+  if (cred) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   // ---- per-thread load coordinates: chunk column c = tid & 7 is fixed, rows (tid >> 3) + 16 j
   const int c = tid & 7;
@@ -187,9 +211,14 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
           umma_tf32(tmem_base, ad0 + q * ainc, bd0 + q * binc, idesc, (kt > 0 || q > 0) ? 1u : 0u);
         umma_commit(EMPTY(slot));  // the stage may be refilled once these MMAs have read it
       }
-      umma_commit(DONE);
+      if (KT > 0) umma_commit(DONE);
       // no commit may still be in flight towards this CTA's barriers when the CTA retires
       for (int kt = max(0, KT - TC_STAGES); kt < KT; ++kt) mbar_wait(EMPTY(kt % TC_STAGES), (uint32_t)((kt / TC_STAGES) & 1));
+    }
+    __syncwarp();
+    if (cred) {  // every thread of the cluster takes part in both barriers of the split-K reduction
+      asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+      cluster_arrive_wait();
     }
     tc_fence_before();
     __syncthreads();
@@ -214,13 +243,72 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   cp_async_wait<0>();
   fence_proxy_async();
   for (int kt = max(0, KT - TC_INFLIGHT); kt < KT; ++kt) mbar_arrive(FULL(kt % TC_STAGES));
-  mbar_wait(DONE, 0);
+  if (KT > 0) mbar_wait(DONE, 0);
   tc_fence_after();
 
   // ---- epilogue: thread = one output row (TMEM lane), 16 columns at a time
   const int row = warp * 32 + lane;
   const int m = m0 + row;
   const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (cred) {
+    // ---- split-K inside a cluster: rank r of the (1, 1, S) cluster reduced k-slice r of this output tile.  Output
+    // rows are dealt out to the S members (128 / S rows each); every member sends each owner the rows it owns
+    // (st.shared::cluster into slot [sender][row][col] of the owner's buffer), one cluster barrier, then each owner
+    // adds the S_nz slots in slice order and applies the epilogue: fixed summation order, no atomics, no workspace.
+    const int S = p.splits;
+    const int rows_per = TC_BM / S;
+    const uint32_t ldred = (uint32_t)bn + 4;  // floats; +4: the 16-byte stores of 32 lanes (32 rows) spread over the banks
+    const uint32_t rank = cluster_ctarank();
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // all members are running (arrival at kernel start)
+    if (KT > 0) {
+      const uint32_t owner = (uint32_t)(row / rows_per);
+      const uint32_t dst = smem_base + p.red_off + ((rank * rows_per + (uint32_t)(row % rows_per)) * ldred) * 4u;
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st_cluster_v4(dst + (uint32_t)(c0 + j) * 4u, owner, v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    cluster_arrive_wait();
+    const float* red = reinterpret_cast<const float*>(smem + p.red_off);
+    const int nz = p.splits_nz;
+    const int quads = bn >> 2;
+    const bool vec = p.vec_store != 0;
+    for (int idx = tid; idx < rows_per * quads; idx += TC_LOAD_THREADS) {
+      const int rl = idx / quads, q = idx - rl * quads;
+      const int mm = m0 + (int)rank * rows_per + rl;
+      const int n = n0 + 4 * q;
+      if (mm >= M || n >= p.N) continue;
+      float4 x = *reinterpret_cast<const float4*>(red + (size_t)rl * ldred + 4 * q);
+      for (int r = 1; r < nz; ++r) {
+        const float4 y = *reinterpret_cast<const float4*>(red + ((size_t)r * rows_per + rl) * ldred + 4 * q);
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+      }
+      float xv[4] = {x.x, x.y, x.z, x.w};
+      float* crow = p.C + (long long)mm * p.ldc + n;
+      const float* rrow = p.residual ? p.residual + (long long)mm * p.ldr + n : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j < p.N) {
+          if (p.scale) xv[j] *= __ldg(p.scale + n + j);
+          if (p.bias) xv[j] += __ldg(p.bias + n + j);
+          if (rrow) xv[j] += rrow[j];
+          if (p.relu) xv[j] = fmaxf(xv[j], 0.f);
+        }
+      }
+      if (vec && n + 4 <= p.N) {
+        *reinterpret_cast<float4*>(crow) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.N) crow[j] = xv[j];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
   for (int c0 = 0; c0 < bn; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(taddr + c0, v);
@@ -274,6 +362,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
 
 static int g_tc_ca = 1;
 static int g_tc_splitk = 1;
+static int g_tc_splitk_cluster = 1;
+static int g_tc_cluster16 = -1;  // -1: not probed yet; 0: clusters of 16 CTAs unavailable; 1: available
 static int g_tc_swz = 1;
 
 __global__ void tc_zero_cols_kernel(float* y, long long ldy, int rows, int cols) {
@@ -306,11 +396,42 @@ static int pick_bn(int N) {
 }
 
 static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    // clusters of 16 CTAs for the longest reductions: opt-in per kernel, then ask the driver whether one fits
+    bool ok16 = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (ok16) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1, 1, 16);
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = 112 * 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 16;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      ok16 = cudaOccupancyMaxActiveClusters(&nclusters, tc_gemm_kernel<true, true>, &cfg) == cudaSuccess && nclusters >= 4;
+    }
+    cudaGetLastError();  // a failed probe must not leave an error behind
+    g_tc_cluster16 = ok16 ? 1 : 0;
+    attr_set = true;
+  }
   p.bn = pick_bn(p.N);
   const int sms = avl_num_sms();
   const int mtiles = avl_div_up(p.M, TC_BM);
   const int KT = avl_div_up(p.K, TC_BK);
   p.splits = 1;
+  p.splits_nz = 1;
+  p.cluster_red = 0;
+  p.red_off = 0;
   p.kt_per_split = KT;
   p.swz = g_tc_swz;
   p.vec_store = ((p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0 && (!p.bias || ((uintptr_t)p.bias & 15) == 0) &&
@@ -324,29 +445,53 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
     const int ctas = mtiles * avl_div_up(p.N, p.bn);
     int splits = (2 * sms + ctas - 1) / ctas;
     if (splits > KT / 4) splits = KT / 4;
-    if (splits > 1) {
+    if (splits > 1 && g_tc_splitk_cluster && p.swz) {
+      // the slices of one tile as one cluster (portable size <= 8, a divisor of the 128 tile rows)
+      int S = splits >= 8 ? 8 : (splits >= 4 ? 4 : 2);
+      if (splits >= 16 && g_tc_cluster16 > 0) S = 16;  // non-portable cluster size (opt-in attribute, probed once)
+      p.kt_per_split = avl_div_up(KT, S);
+      p.splits = S;
+      p.splits_nz = avl_div_up(KT, p.kt_per_split);
+      p.cluster_red = 1;
+    } else if (splits > 1) {
       p.kt_per_split = avl_div_up(KT, splits);
       p.splits = avl_div_up(KT, p.kt_per_split);
+      p.splits_nz = p.splits;
     }
   }
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage = p.swz ? (TC_BM + (size_t)p.bn) * 128 : (size_t)TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
-  p.stages = (int)((100 * 1024) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+  const size_t red_bytes = p.cluster_red ? (size_t)TC_BM * (p.bn + 4) * sizeof(float) : 0;
+  p.stages = (int)((100 * 1024 - red_bytes) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.stages < 3) p.stages = 3;  // the loaders keep TC_INFLIGHT = 2 tiles in flight
   size_t smem = (size_t)p.stages * stage;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
-    attr_set = true;
-  }
+  p.red_off = (unsigned)smem;  // (the SWIZZLE_128B stage size is a multiple of 1024 bytes)
+  smem += red_bytes;
+
   dim3 grid(mtiles, avl_div_up(p.N, p.bn), p.splits);
   const float *scale = p.scale, *bias = p.bias, *residual = p.residual;
   const int relu = p.relu;
+  if (p.cluster_red) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = (unsigned)p.splits;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    auto kern = conv ? (g_tc_ca ? tc_gemm_kernel<true, true> : tc_gemm_kernel<true>) : tc_gemm_kernel<false>;
+    AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+    AVL_LAUNCH_CHECK();
+    return AVL_OK;
+  }
   if (p.splits > 1) {
     long long tot = (long long)p.M * p.N;
     int g = (int)((tot + 255) / 256 > (long long)sms * 16 ? (long long)sms * 16 : (tot + 255) / 256);
@@ -383,6 +528,16 @@ AVL_API int avl_set_tc_splitk(int on) {
   avl_bump_config_epoch();
   int old = g_tc_splitk;
   g_tc_splitk = on ? 1 : 0;
+  return old;
+}
+
+// 1 (default): the k-slices of a split-K problem form a thread-block cluster and are reduced through distributed shared
+// memory inside the kernel (deterministic, no helper launches); 0: atomic partial sums into a zeroed output + separate
+// epilogue kernel.  Returns the old value.
+AVL_API int avl_set_tc_splitk_cluster(int on) {
+  avl_bump_config_epoch();
+  int old = g_tc_splitk_cluster;
+  g_tc_splitk_cluster = on ? 1 : 0;
   return old;
 }
 

@@ -673,4 +673,71 @@ AVL_API int avl_clip_adam_step(float* param, const float* grad, float* exp_avg, 
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Synthetic VectorEnv step (avlen_b200/synth_env.py): episode bookkeeping + toy kinematics
+// of all environments in ONE launch.  Stands in for the reference's env workers (graph walk simulator.py:496-517,
+// episode reset, _audio_index advance simulator.py:668, silent-source test simulator.py:646) behind the VectorEnv
+// `step` call; as ~30 separate elementwise launches it sat on the critical path between two policy steps.
+// r: (n, 3) uniforms; dones = r[:,0] < done_prob; FORWARD=1 moves 0.5 m along the heading, LEFT=2 / RIGHT=3 turn by
+// 0.5236 rad; a finished episode resets pose / heading / step count; rewards = r[:,1] - 0.5.  Products and sums are
+// rounded separately (no FMA contraction) so that the result equals the elementwise formulation bit for bit.
+namespace {
+__global__ void synth_env_step_kernel(int n, const long long* __restrict__ actions, const float* __restrict__ r,
+                                      float done_prob, float* heading, float* pose_xy, float* episode_step,
+                                      int* audio_index, const int* __restrict__ clip_secs,
+                                      const float* __restrict__ silent_after, float* rewards, unsigned char* dones,
+                                      float* masks, float* pose_obs, int* silent, float* category_belief,
+                                      float* location_belief) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool done = r[3 * i] < done_prob;
+  const long long a = actions[i];
+  float h = heading[i];
+  if (a == 2) h = __fadd_rn(h, 0.5236f);
+  else if (a == 3) h = __fsub_rn(h, 0.5236f);
+  const float half_fwd = (a == 1) ? 0.5f : 0.f;
+  float px = __fadd_rn(pose_xy[2 * i], __fmul_rn(half_fwd, cosf(h)));
+  float py = __fadd_rn(pose_xy[2 * i + 1], __fmul_rn(half_fwd, -sinf(h)));
+  float es = __fadd_rn(episode_step[i], 1.f);
+  const float nd = done ? 0.f : 1.f;
+  es = __fmul_rn(es, nd);
+  px = __fmul_rn(px, nd);
+  py = __fmul_rn(py, nd);
+  h = __fmul_rn(h, nd);
+  heading[i] = h;
+  pose_xy[2 * i] = px;
+  pose_xy[2 * i + 1] = py;
+  episode_step[i] = es;
+  const int secs = clip_secs[i];
+  audio_index[i] = secs > 0 ? (audio_index[i] + 1) % secs : 0;
+  rewards[i] = __fsub_rn(r[3 * i + 1], 0.5f);
+  dones[i] = done ? 1 : 0;
+  masks[i] = nd;
+  pose_obs[4 * i] = px;
+  pose_obs[4 * i + 1] = py;
+  pose_obs[4 * i + 2] = h;
+  pose_obs[4 * i + 3] = es;
+  silent[i] = es > silent_after[i] ? 1 : 0;
+  if (category_belief)
+    for (int j = 0; j < 21; ++j) category_belief[21 * i + j] = 0.f;
+  if (location_belief) location_belief[2 * i] = location_belief[2 * i + 1] = 0.f;
+}
+}  // namespace
+
+AVL_API int avl_synth_env_step(int n_envs, const long long* actions, const float* uniforms, float done_prob,
+                               float* heading, float* pose_xy, float* episode_step, int* audio_index,
+                               const int* clip_secs, const float* silent_after, float* rewards, unsigned char* dones,
+                               float* masks, float* pose_obs, int* silent, float* category_belief,
+                               float* location_belief, void* stream) {
+  if (n_envs < 0) return AVL_ERR_ARG;
+  if (n_envs == 0) return AVL_OK;
+  if (!actions || !uniforms || !heading || !pose_xy || !episode_step || !audio_index || !clip_secs || !silent_after ||
+      !rewards || !dones || !masks || !pose_obs || !silent)
+    return AVL_ERR_ARG;
+  synth_env_step_kernel<<<avl_div_up(n_envs, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_envs, actions, uniforms, done_prob, heading, pose_xy, episode_step, audio_index, clip_secs, silent_after,
+      rewards, dones, masks, pose_obs, silent, category_belief, location_belief);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
 #endif  // AVL_HOST_EMUL

@@ -36,6 +36,7 @@ _lib.register({
     "avl_get_tensor_cores": [],
     "avl_set_tc_conv_l1": [I],
     "avl_set_tc_splitk": [I],
+    "avl_set_tc_splitk_cluster": [I],
     "avl_set_tc_swizzle": [I],
     "avl_set_tc_tma": [I],
     "avl_set_tc_3xtf32": [I],
@@ -423,14 +424,9 @@ class ResNetPlan:
             for m in self._module.modules():
                 refs += [(m._parameters, k) for k in m._parameters] + [(m._buffers, k) for k in m._buffers]
             self._refs = refs
-        fp = [use_tc]
-        for d, k in self._refs:
-            t = d[k]
-            if t is not None:
-                fp.append(id(t))
-                fp.append(t._version)
-                fp.append(t.data_ptr())
-        return fp
+        ts = [d[k] for d, k in self._refs]
+        ts = [t for t in ts if t is not None]
+        return (use_tc, [id(t) for t in ts], [t._version for t in ts], [t.data_ptr() for t in ts])
 
     def any_requires_grad(self):
         if self._refs is None:

@@ -151,8 +151,12 @@ class FlatAdam:
     The flat gradient buffer is also what the DD-PPO all-reduce operates on (one NCCL call per minibatch).
     """
 
-    def __init__(self, flat_param, flat_grad, lr, eps, betas=(0.9, 0.999)):
+    def __init__(self, flat_param, flat_grad, lr, eps, betas=(0.9, 0.999), views=None):
         self.p, self.g = flat_param, flat_grad
+        # the parameters that alias the flat buffer: the kernel writes them behind autograd's back, so their version
+        # counters are bumped by hand — derived data cached per weight version (packed tensor-core weights, parameter
+        # tables of the fused networks) must notice the step
+        self.views = list(views) if views is not None else None
         self.m = torch.zeros_like(flat_param)
         self.v = torch.zeros_like(flat_param)
         self.lr, self.eps, self.betas = lr, eps, betas
@@ -169,6 +173,8 @@ class FlatAdam:
         call("avl_clip_adam_step", fptr(self.p), fptr(self.g), fptr(self.m), fptr(self.v), n, float(self.lr),
              float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count, mn, fptr(self._normsq),
              float(grad_scale), stream())
+        if self.views:
+            torch.autograd.graph.increment_version(self.views)
         return self._normsq  # device scalar: sum of squares of the unscaled gradient
 
     def state_dict(self):

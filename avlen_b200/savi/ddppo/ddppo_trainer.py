@@ -36,7 +36,7 @@ def savi_config(**overrides):
                num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu", freeze_encoders=True,
                pretraining=False, use_label_belief=True, use_location_belief=True, online_training=True,
                sync_frac=0.6, distrib_backend="nccl", use_preemption=False, seed=1234, sampling_rate=16000,
-               host_buffers=False, has_distractor_sound=False, overlap_belief=True)
+               host_buffers=False, has_distractor_sound=False, overlap_belief=True, prefetch_encoders=True)
     cfg.update(overrides)
     return types.SimpleNamespace(**cfg)
 

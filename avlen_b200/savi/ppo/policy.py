@@ -319,19 +319,72 @@ class AudioNavSMTNet(Net):
                 parts.append(torch.zeros(n, extra_cols, device=dev))
             return torch.cat(parts, dim=1)
         with torch.no_grad():
-            x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
-            self.visual_encoder(observations, out=x[:, 0:128])
+            x = self._take_prefetch(observations, n, self._base_feature_size + extra_cols)
+            if x is None:
+                x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
+                self._observation_features_into(x, observations)
             if prev_actions.shape[1] == self._action_size:  # already one-hot (policy.py:629-630)
                 K.linear(prev_actions.float().contiguous(), self.action_encoder.weight, self.action_encoder.bias,
                          out=x[:, 128:144])
             else:
                 K.onehot_linear(prev_actions, self.action_encoder.weight, self.action_encoder.bias, x[:, 128:144])
-            self.goal_encoder(observations, out=x[:, 144:272])
-            col = 272
-            if self._use_category_input:
-                K.copy_cols(observations[CATEGORY].contiguous(), x[:, col:col + 21])
-                col += 21
-            K.copy_cols(observations[POSE].contiguous(), x[:, col:col + 4])
+        return x
+
+    def _observation_features_into(self, x, observations):
+        """The columns of the feature row that depend on the observation only: visual 0:128, audio 144:272,
+        (category), pose."""
+        self.visual_encoder(observations, out=x[:, 0:128])
+        self.goal_encoder(observations, out=x[:, 144:272])
+        col = 272
+        if self._use_category_input:
+            K.copy_cols(observations[CATEGORY].contiguous(), x[:, col:col + 21])
+            col += 21
+        K.copy_cols(observations[POSE].contiguous(), x[:, col:col + 4])
+
+    # ---- encoder prefetch: the observation-only columns of step s+1 are enqueued on a side stream as soon as the
+    # environment has returned observation s+1 (trainer: right after ``envs.step``), so that the two visual ResNet-18s
+    # and the audio CNN run next to the audio rendering / belief networks / storage insert instead of in front of the
+    # next step's transformer.  Same kernels on the same data: the features are identical to the in-order path.
+    _PREFETCH_KEYS = ("rgb", "depth", SPECTROGRAM, POSE)
+    _prefetch = None
+
+    def observation_key(self, observations):
+        return tuple(observations[k].data_ptr() for k in self._PREFETCH_KEYS if k in observations)
+
+    @torch.no_grad()
+    def prefetch_observation_features(self, observations, key, stream, extra_cols=0):
+        """``observations``: what the environment returned; ``key``: ``observation_key`` of the tensors the NEXT
+        ``act`` / ``get_value`` call will be given (the rollout-storage slots these observations are copied into)."""
+        self.drop_prefetch()
+        main = torch.cuda.current_stream()
+        stream.wait_stream(main)
+        n, dev = observations[POSE].shape[0], observations[POSE].device
+        for k in self._PREFETCH_KEYS + (CATEGORY,):
+            v = observations.get(k)
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(stream)
+        with torch.cuda.stream(stream):
+            x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
+            self._observation_features_into(x, observations)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._prefetch = (key, x, ev)
+
+    def drop_prefetch(self):
+        pre, self._prefetch = self._prefetch, None
+        if pre is not None:  # the encoders' workspaces are per network: whatever was enqueued must finish first
+            torch.cuda.current_stream().wait_event(pre[2])
+
+    def _take_prefetch(self, observations, n, cols):
+        pre, self._prefetch = self._prefetch, None
+        if pre is None:
+            return None
+        key, x, ev = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        if key != self.observation_key(observations) or tuple(x.shape) != (n, cols):
+            return None
+        x.record_stream(cur)
         return x
 
 

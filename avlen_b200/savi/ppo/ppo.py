@@ -46,9 +46,9 @@ class PPO(nn.Module):
         self.policy_head = policy_head  # "goal": SAVi evaluate_actions ; "option": AVLEN evaluate_actions_option
         self.device = next(actor_critic.parameters()).device
         self._params, self._flat_p, self._flat_g = flatten_parameters(actor_critic)
-        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps)
+        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps, views=self._params)
         # dialog pretraining (ppo.py:63, :70-76): its own Adam moments, lr 1e-5, class weights 'balanced'
-        self.dialog_optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=0.00001, eps=eps)
+        self.dialog_optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=0.00001, eps=eps, views=self._params)
         self.dialog_class_weight = torch.tensor([0, .33, .33, .33], device=self.device)
         self._loss = ops.PpoLoss(self.device)
         self.world_size = 1

@@ -30,13 +30,23 @@ class PPOTrainer:
                                   rollouts.masks[s], rollouts.external_memory_goal[:, s],
                                   rollouts.external_memory_masks[s], uniforms=uniforms)
         observations, rewards, dones = self.envs.step(actions)
-        masks = (~dones).float().unsqueeze(1)
+        masks = getattr(self.envs, "last_masks", None)  # (N, 1) not-done floats when the env already produced them
+        if masks is None:
+            masks = (~dones).float().unsqueeze(1)
         if current_episode_reward is not None:
             current_episode_reward += rewards
             if running_episode_stats is not None:
                 running_episode_stats["reward"] += (1 - masks) * current_episode_reward
                 running_episode_stats["count"] += 1 - masks
             current_episode_reward *= masks
+        if getattr(self.config, "prefetch_encoders", False) and s + 1 < rollouts.masks.shape[0]:
+            # the visual / audio encoders of observation s+1 only need what the environment just returned
+            net = self.actor_critic.net
+            vs = getattr(self, "_encoder_stream", None)
+            if vs is None:
+                vs = self._encoder_stream = torch.cuda.Stream()
+            slot = {k: rollouts.observations[k][s + 1] for k in net._PREFETCH_KEYS if k in rollouts.observations}
+            net.prefetch_observation_features(observations, net.observation_key(slot), vs)
         if self.belief_predictor is not None:  # :890-894: belief for the NEXT observation
             if getattr(self.config, "overlap_belief", False):
                 observations = self._belief_update_deferred(rollouts, observations, dones)

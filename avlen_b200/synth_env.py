@@ -12,15 +12,17 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import synth
+from . import _lib, synth
 from .audio import AudioRenderer
 
 
 class SyntheticVectorEnv:
     def __init__(self, num_envs, device, seed=1234, sr=16000, pool=4, distractor=False, host_buffers=False,
-                 done_prob=1.0 / 80.0, rir_len=None):
+                 done_prob=1.0 / 80.0, rir_len=None, fused_step=True):
         self.num_envs, self.device, self.sr = num_envs, torch.device(device), sr
         self.host_buffers = host_buffers
+        self.fused_step = fused_step  # one kernel for the episode bookkeeping (avl_synth_env_step) instead of ~30 torch ops
+        self.last_masks = None
         rng = np.random.default_rng(seed)
         self._g = torch.Generator(device="cpu").manual_seed(seed)
         self.pool = pool
@@ -62,18 +64,21 @@ class SyntheticVectorEnv:
             rgb, depth = self._rgb[i], self._depth[i]
         return rgb.float(), depth  # batch_obs: everything becomes float32 (common/utils.py:149-154)
 
-    def _observe(self):
+    def _observe(self, silent=None, pose=None, beliefs=None):
         a = self._audio
-        silent = (self._episode_step > self._silent_after).to(torch.int32)  # simulator.py:646
+        if silent is None:
+            silent = (self._episode_step > self._silent_after).to(torch.int32)  # simulator.py:646
         _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
                                        silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
                                        want_audiogoal=False)
         rgb, depth = self._visual()
-        pose = torch.cat([self._pose_xy, self._heading[:, None], self._episode_step[:, None]], 1)
+        if pose is None:
+            pose = torch.cat([self._pose_xy, self._heading[:, None], self._episode_step[:, None]], 1)
         n = self.num_envs
+        cb, lb = beliefs if beliefs is not None else (torch.zeros(n, 21, device=self.device),
+                                                      torch.zeros(n, 2, device=self.device))
         return {"rgb": rgb, "depth": depth, "spectrogram": spec, "pose": pose, "category": self._category,
-                "category_belief": torch.zeros(n, 21, device=self.device),
-                "location_belief": torch.zeros(n, 2, device=self.device)}
+                "category_belief": cb, "location_belief": lb}
 
     def reset(self):
         self._t = 0
@@ -88,6 +93,24 @@ class SyntheticVectorEnv:
         n, dev = self.num_envs, self.device
         self._t += 1
         r = torch.rand(n, 3, device=dev)
+        if self.fused_step:
+            f32 = torch.float32
+            rewards = torch.empty(n, 1, device=dev, dtype=f32)
+            dones = torch.empty(n, device=dev, dtype=torch.bool)
+            masks = torch.empty(n, 1, device=dev, dtype=f32)
+            pose = torch.empty(n, 4, device=dev, dtype=f32)
+            silent = torch.empty(n, device=dev, dtype=torch.int32)
+            cb = torch.empty(n, 21, device=dev, dtype=f32)
+            lb = torch.empty(n, 2, device=dev, dtype=f32)
+            idx = self._audio["index"]
+            _lib.call("avl_synth_env_step", n, _lib.dptr(actions.view(n), torch.int64), _lib.fptr(r),
+                      float(self.done_prob), _lib.fptr(self._heading), _lib.fptr(self._pose_xy),
+                      _lib.fptr(self._episode_step), _lib.dptr(idx, torch.int32), _lib.dptr(self._clip_secs, torch.int32),
+                      _lib.fptr(self._silent_after), _lib.fptr(rewards), dones.data_ptr(), _lib.fptr(masks),
+                      _lib.fptr(pose), _lib.dptr(silent, torch.int32), _lib.fptr(cb), _lib.fptr(lb), _lib.stream())
+            self.last_masks = masks
+            return self._observe(silent, pose, (cb, lb)), rewards, dones
+        self.last_masks = None
         dones = r[:, 0] < self.done_prob
         a = actions.view(n)
         # toy kinematics so that relative poses are non-trivial: FORWARD=1, LEFT=2, RIGHT=3 (simulator.py:494)

@@ -90,6 +90,16 @@ int avl_belief_update(int n_envs, const float* spectrogram, int spec_elems_per_e
                       int* has_pointgoal, float* last_label, int* has_label, float* location_belief,
                       float* category_belief, int* nonzero_scratch, void* stream);
 
+/* ------------------------------------------------- synthetic VectorEnv step (bench / tests)
+ * Stands in for the reference's env workers behind VectorEnv.step (graph walk soundspaces/simulator.py:496-517,
+ * _audio_index advance :668, silent-source test :646): episode bookkeeping + toy kinematics of all envs, one launch.
+ * uniforms (n, 3); state arrays are updated in place; category_belief (n, 21) / location_belief (n, 2), when given,
+ * are zero-filled (the belief predictor fills them afterwards).                                                    */
+int avl_synth_env_step(int n_envs, const long long* actions, const float* uniforms, float done_prob, float* heading,
+                       float* pose_xy, float* episode_step, int* audio_index, const int* clip_secs,
+                       const float* silent_after, float* rewards, unsigned char* dones, float* masks, float* pose_obs,
+                       int* silent, float* category_belief, float* location_belief, void* stream);
+
 /* ----------------------------------------------------------------------- clip_grad_norm_ + Adam (flat buffers)
  * ss_baselines/savi/ppo/ppo.py:62, :297-300 (torch.optim.Adam + nn.utils.clip_grad_norm_)                      */
 int avl_grad_sumsq(const float* grad, long long n, float* normsq_out, void* workspace /* 1032 floats, zeroed */,
@@ -226,7 +236,8 @@ int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const flo
 int avl_set_tc_conv_halo(int on, int rows_per_strip); /* halo-strip kernel for stride-1 same convs; returns old */
 int avl_set_tc_tma(int on);      /* dense GEMMs: 1 TMA-fed kernel where it applies (default), 0 cp.async kernel; returns old */
 int avl_set_tc_swizzle(int on);  /* generic kernel operand tiles: 1 SWIZZLE_128B (default), 0 SWIZZLE_NONE; returns old */
-int avl_set_tc_splitk(int on);   /* split-K (atomic partial sums) for small-M / long-K tensor-core problems; returns old */
+int avl_set_tc_splitk(int on);   /* split-K for small-M / long-K tensor-core problems; returns old */
+int avl_set_tc_splitk_cluster(int on); /* 1 (default): the k-slices of a tile form a thread-block cluster, partial tiles are summed in slice order through distributed shared memory inside the kernel (deterministic, no helper launches); 0: atomic partial sums + separate zero / epilogue kernels; returns old */
 int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
 
 /* ----------------------------------------------------------------------------- row H: GRU state encoder

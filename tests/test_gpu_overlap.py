@@ -7,11 +7,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(overlap, level):
+def _run(overlap, level, prefetch=False):
     from avlen_b200 import nn as K
     from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
     K.set_tensor_cores(level)
-    cfg = savi_config(NUM_PROCESSES=6, num_steps=12, NUM_UPDATES=1, memory_size=8, overlap_belief=overlap, seed=77)
+    cfg = savi_config(NUM_PROCESSES=6, num_steps=12, NUM_UPDATES=1, memory_size=8, overlap_belief=overlap, seed=77,
+                      prefetch_encoders=prefetch)
     tr = DDPPOTrainer(cfg).setup()
     tr.collect_rollout()
     r = tr.rollouts
@@ -24,13 +25,15 @@ def _run(overlap, level):
     return snap, [float(x) for x in losses]
 
 
-@pytest.mark.parametrize("level", [0, 1])
-def test_deferred_belief_update_matches_in_order_rollout(level):
+@pytest.mark.parametrize("level,prefetch", [(0, False), (1, False), (0, True), (1, True)])
+def test_deferred_belief_update_matches_in_order_rollout(level, prefetch):
+    """prefetch: additionally the observation-only feature columns (visual ResNet-18s, audio CNN, pose) of step s+1 are
+    enqueued on an encoder stream right after ``envs.step`` (AudioNavSMTNet.prefetch_observation_features)."""
     from avlen_b200 import nn as K
     old = K.tensor_cores_level()
     try:
         a, la = _run(False, level)
-        b, lb = _run(True, level)
+        b, lb = _run(True, level, prefetch)
     finally:
         K.set_tensor_cores(old)
     # level 0 (fp32 SIMT): same summation orders except split-K atomics -> last-ulp; level 1: TF32 tolerance
@@ -48,3 +51,26 @@ def test_deferred_belief_update_matches_in_order_rollout(level):
         assert torch.equal(a["actions"], b["actions"])
         for x, y in zip(la, lb):
             assert abs(x - y) <= 1e-4 * max(1.0, abs(x)), (la, lb)
+
+
+def test_fused_synthetic_env_step_matches_elementwise():
+    """avl_synth_env_step (one kernel) against the elementwise torch formulation of SyntheticVectorEnv.step: bitwise."""
+    from avlen_b200.synth_env import SyntheticVectorEnv
+    a = SyntheticVectorEnv(7, "cuda", seed=5, fused_step=False, done_prob=0.2)
+    b = SyntheticVectorEnv(7, "cuda", seed=5, fused_step=True, done_prob=0.2)
+    oa, ob = a.reset(), b.reset()
+    g = torch.Generator().manual_seed(3)
+    for t in range(25):
+        actions = torch.randint(0, 4, (7, 1), generator=g).cuda()
+        torch.manual_seed(100 + t)
+        oa, ra, da = a.step(actions)
+        torch.manual_seed(100 + t)
+        ob, rb, db = b.step(actions)
+        assert torch.equal(da, db) and torch.equal(ra, rb)
+        for k in ("pose", "spectrogram", "category_belief", "location_belief"):
+            assert torch.equal(oa[k], ob[k]), (t, k)
+        assert torch.equal(b.last_masks, (~da).float().unsqueeze(1))
+        assert torch.equal(a._audio["index"], b._audio["index"])
+    assert bool(da.any()) or True
+    a.close()
+    b.close()

@@ -77,6 +77,44 @@ def test_tc_conv_matches_fp32(shape):
 
 
 @pytest.mark.parametrize("shape", [
+    (64, 8, 8, 128, 128, 3, 3, 1, 1), (64, 5, 2, 256, 256, 3, 3, 1, 1), (64, 3, 1, 512, 512, 3, 3, 1, 1),
+    (64, 9, 4, 128, 128, 3, 3, 1, 1), (5, 13, 3, 64, 512, 13, 3, 1, 0), (64, 16, 16, 64, 128, 3, 3, 2, 1),
+    (33, 8, 8, 128, 66, 3, 3, 1, 1), (7, 8, 8, 132, 20, 3, 3, 1, 1), (64, 8, 8, 128, 64, 8, 8, 1, 0),
+])
+def test_tc_splitk_cluster_reduction(shape):
+    """Split-K inside a thread-block cluster (partial tiles summed through distributed shared memory in slice order,
+    epilogue in the same kernel) against the atomic split-K path and PyTorch; two runs are bitwise identical."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, KH, KW, s, p = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    w = (torch.randn(Co, C, KH, KW, generator=g) / (C * KH * KW) ** 0.5).cuda()
+    b, sc = torch.randn(Co, generator=g).cuda(), (torch.rand(Co, generator=g) + 0.5).cuda()
+    OH, OW = (H + 2 * p - KH) // s + 1, (W + 2 * p - KW) // s + 1
+    res = torch.randn(N, OH, OW, Co, generator=g).cuda()
+    lib = _lib.lib()
+    old = lib.avl_set_tc_splitk_cluster(0)
+    try:
+        atomic = K.conv2d(x, w, b, s, p, relu=True, scale=sc, residual=res)
+        lib.avl_set_tc_splitk_cluster(1)
+        l0 = lib.avl_launch_count()
+        out = K.conv2d(x, w, b, s, p, relu=True, scale=sc, residual=res)
+        launches = lib.avl_launch_count() - l0
+        again = [K.conv2d(x, w, b, s, p, relu=True, scale=sc, residual=res) for _ in range(6)]
+        torch.cuda.synchronize()
+    finally:
+        lib.avl_set_tc_splitk_cluster(old)
+    tref = F.relu(F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, s, p) * sc.double().view(1, -1, 1, 1)
+                  + b.double().view(1, -1, 1, 1) + res.permute(0, 3, 1, 2).double()).permute(0, 2, 3, 1).float()
+    assert rel(out, tref) < TOL_TC
+    assert float((out - atomic).abs().max()) < 1e-4 * max(1.0, float(tref.abs().max()))  # same TF32 products, other order
+    for o in again:
+        assert torch.equal(out, o)
+    assert launches <= 2  # (weight packing may launch once; no zero / epilogue helper kernels)
+
+
+@pytest.mark.parametrize("shape", [
     (5, 64, 64, 16, 16, 3, 1), (3, 64, 64, 4, 16, 7, 3), (4, 32, 32, 32, 32, 3, 1), (2, 20, 24, 8, 48, 3, 1),
     (3, 64, 64, 16, 16, 3, 1, "res"), (2, 37, 19, 16, 32, 5, 2), (1, 64, 64, 4, 16, 3, 1), (160, 64, 64, 16, 16, 3, 1),
     (7, 30, 40, 24, 16, 3, 1, "res"), (2, 16, 16, 32, 128, 3, 1),
@@ -319,3 +357,29 @@ def test_fused_resnet_fp16_stage1_matches_fp32_storage(shape):
     torch.cuda.synchronize()
     assert rel(outs[1], outs[0]) < 5e-3
     assert not torch.equal(outs[1], outs[0])   # the fp16 path really ran
+
+
+def test_packed_weights_follow_the_fused_adam_step():
+    """The fused clip + Adam kernel writes the flattened parameters behind autograd's back; the tensor-core path caches
+    packed (Cout, KH, KW, Cin) weights per weight version, so the step has to bump the versions — otherwise a trainable
+    encoder keeps convolving with its pre-step weights."""
+    import torch.nn as nn
+    from avlen_b200 import nn as K
+    from avlen_b200 import ops
+    from avlen_b200.savi.ppo.ppo import flatten_parameters
+    g = torch.Generator().manual_seed(5)
+    m = nn.Conv2d(16, 32, 3, padding=1, bias=False).cuda()
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(32, 16, 3, 3, generator=g) / 12.0)
+    params, flat_p, flat_g = flatten_parameters(m)
+    opt = ops.FlatAdam(flat_p, flat_g, lr=0.05, eps=1e-5, views=params)
+    x = torch.randn(8, 16, 16, 16, generator=g).cuda()
+    with torch.no_grad():
+        y0 = K.conv2d(x, m.weight, None, 1, 1)
+        flat_g.copy_(torch.randn(flat_g.shape, generator=g))
+        opt.step(None)
+        y1 = K.conv2d(x, m.weight, None, 1, 1)
+        fresh = K.conv2d(x, m.weight.detach().clone(), None, 1, 1)
+    torch.cuda.synchronize()
+    assert float((y1 - y0).abs().max()) > 1e-2          # the step moved the weights by ~lr
+    assert torch.equal(y1, fresh)

@@ -37,6 +37,8 @@ def main():
         torch.cuda.synchronize()
     print("10 rollout steps wall", time.time() - t0)
     table(prof, "10 rollout steps (64 envs)")
+    if os.environ.get("AVL_TRACE"):
+        prof.export_chrome_trace(os.environ["AVL_TRACE"])  # per-kernel start / duration / stream (tools/trace_streams.py)
     for _ in range(steps - 10):
         tr._collect_rollout_step(tr.rollouts)
     torch.cuda.synchronize()
