@@ -27,6 +27,7 @@ _SIGNATURES = {
     "avl_audio_status": [P, ctypes.POINTER(c_int)],
     "avl_audio_render_spectrogram": [P, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_audio_spectrogram": [P, I, P, P, P],
+    "avl_set_audio_channel_split": [I],
     "avl_gae_f64": [P, P, P, P, P, I, I, I, D, D, P],
     "avl_advantages": [P, P, P, I, I, F, P],
     "avl_categorical_act": [P, P, I, I, P, P, P, P],

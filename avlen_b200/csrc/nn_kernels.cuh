@@ -646,10 +646,21 @@ __global__ void attn_cross_fwd_kernel(const float* __restrict__ q, const float* 
   float* ps = Ps + h * ATT_MAXV;
   const float qd = q[(size_t)b * D + h * ATT_HD + lane] * scale;
   float mx = -INFINITY;
-  for (int j = 0; j < V; ++j) {
-    float s = warp_sum(qd * kv[(size_t)(r0 + j) * 2 * D + h * ATT_HD + lane]);
-    if (lane == 0) ps[j] = s;
-    mx = fmaxf(mx, s);
+  // keys in batches of 8: the loads of a batch are issued together (one dependent load + reduction per key left the
+  // warp waiting a full memory round trip per key: 48 us for ~76 keys at rollout batch)
+  for (int j0 = 0; j0 < V; j0 += 8) {
+    float kk[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      kk[u] = (j0 + u < V) ? kv[(size_t)(r0 + j0 + u) * 2 * D + h * ATT_HD + lane] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float s = warp_sum(qd * kk[u]);
+      if (j0 + u < V) {
+        if (lane == 0) ps[j0 + u] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
   }
   __syncwarp();
   float sum = 0.f;
@@ -662,10 +673,19 @@ __global__ void attn_cross_fwd_kernel(const float* __restrict__ q, const float* 
   const float inv = 1.f / sum;
   __syncwarp();
   float o = 0.f;
-  for (int j = 0; j < V; ++j) {
-    float p = ps[j] * inv;
-    o = fmaf(p, kv[(size_t)(r0 + j) * 2 * D + D + h * ATT_HD + lane], o);
-    if (lane == 0 && probs) probs[(size_t)(r0 + j) * H + h] = p;
+  for (int j0 = 0; j0 < V; j0 += 8) {
+    float vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      vv[u] = (j0 + u < V) ? kv[(size_t)(r0 + j0 + u) * 2 * D + D + h * ATT_HD + lane] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < V) {
+        const float p = ps[j0 + u] * inv;
+        o = fmaf(p, vv[u], o);  // same order as the key-by-key loop: bitwise the same result
+        if (lane == 0 && probs) probs[(size_t)(r0 + j0 + u) * H + h] = p;
+      }
+    }
   }
   out[(size_t)b * D + h * ATT_HD + lane] = o;
 }

@@ -330,10 +330,13 @@ class AudioNavSMTNet(Net):
                 K.onehot_linear(prev_actions, self.action_encoder.weight, self.action_encoder.bias, x[:, 128:144])
         return x
 
-    def _observation_features_into(self, x, observations):
+    def _observation_features_into(self, x, observations, visual=True, rest=True):
         """The columns of the feature row that depend on the observation only: visual 0:128, audio 144:272,
         (category), pose."""
-        self.visual_encoder(observations, out=x[:, 0:128])
+        if visual:
+            self.visual_encoder(observations, out=x[:, 0:128])
+        if not rest:
+            return
         self.goal_encoder(observations, out=x[:, 144:272])
         col = 272
         if self._use_category_input:
@@ -345,19 +348,32 @@ class AudioNavSMTNet(Net):
     # environment has returned observation s+1 (trainer: right after ``envs.step``), so that the two visual ResNet-18s
     # and the audio CNN run next to the audio rendering / belief networks / storage insert instead of in front of the
     # next step's transformer.  Same kernels on the same data: the features are identical to the in-order path.
+    # PPO.update uses the same mechanism one minibatch ahead (frozen encoders only).
     _PREFETCH_KEYS = ("rgb", "depth", SPECTROGRAM, POSE)
-    _prefetch = None
 
     def observation_key(self, observations):
         return tuple(observations[k].data_ptr() for k in self._PREFETCH_KEYS if k in observations)
 
+    def _prefetched(self):
+        d = self.__dict__.get("_prefetch")
+        if d is None:
+            d = self.__dict__["_prefetch"] = {}
+        return d
+
     @torch.no_grad()
-    def prefetch_observation_features(self, observations, key, stream, extra_cols=0):
-        """``observations``: what the environment returned; ``key``: ``observation_key`` of the tensors the NEXT
-        ``act`` / ``get_value`` call will be given (the rollout-storage slots these observations are copied into)."""
-        self.drop_prefetch()
+    def prefetch_observation_features(self, observations, key, stream, extra_cols=0, visual_event=None):
+        """``observations``: what the environment returned (or the next minibatch of a PPO update); ``key``:
+        ``observation_key`` of the tensors the consuming ``act`` / ``get_value`` / ``evaluate_actions`` call will be
+        given (rollout: the storage slots these observations are copied into).  All prefetches must be enqueued on
+        the same ``stream`` (the encoders' workspaces are per network).
+        ``visual_event``: optional event after which the frames are complete (an environment that produces them on
+        its own stream): the visual encoders then start without waiting for the rest of the current stream (the audio
+        rendering); everything else waits for the current stream."""
         main = torch.cuda.current_stream()
-        stream.wait_stream(main)
+        if visual_event is not None:
+            stream.wait_event(visual_event)
+        else:
+            stream.wait_stream(main)
         n, dev = observations[POSE].shape[0], observations[POSE].device
         for k in self._PREFETCH_KEYS + (CATEGORY,):
             v = observations.get(k)
@@ -365,25 +381,36 @@ class AudioNavSMTNet(Net):
                 v.record_stream(stream)
         with torch.cuda.stream(stream):
             x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
-            self._observation_features_into(x, observations)
+            self._observation_features_into(x, observations, visual=True, rest=False)
+        if visual_event is not None:
+            stream.wait_stream(main)
+        with torch.cuda.stream(stream):
+            self._observation_features_into(x, observations, visual=False, rest=True)
             ev = torch.cuda.Event()
             ev.record(stream)
-        self._prefetch = (key, x, ev)
+        self._prefetched()[key] = (x, ev)
 
     def drop_prefetch(self):
-        pre, self._prefetch = self._prefetch, None
-        if pre is not None:  # the encoders' workspaces are per network: whatever was enqueued must finish first
-            torch.cuda.current_stream().wait_event(pre[2])
+        d = self._prefetched()
+        cur = torch.cuda.current_stream()
+        for _x, ev in d.values():  # the encoders' workspaces are per network: whatever was enqueued must finish first
+            cur.wait_event(ev)
+        d.clear()
 
     def _take_prefetch(self, observations, n, cols):
-        pre, self._prefetch = self._prefetch, None
-        if pre is None:
+        d = self.__dict__.get("_prefetch")
+        if not d:
             return None
-        key, x, ev = pre
+        hit = d.pop(self.observation_key(observations), None)
+        if hit is None or tuple(hit[0].shape) != (n, cols):
+            # the caller is about to run the encoders itself: nothing enqueued earlier may still be using them
+            if hit is not None:
+                torch.cuda.current_stream().wait_event(hit[1])
+            self.drop_prefetch()
+            return None
+        x, ev = hit
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
-        if key != self.observation_key(observations) or tuple(x.shape) != (n, cols):
-            return None
         x.record_stream(cur)
         return x
 

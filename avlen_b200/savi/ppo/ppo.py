@@ -69,9 +69,8 @@ class PPO(nn.Module):
         sums = torch.zeros(8, device=self.device)
         n_updates = 0
         option = self.policy_head == "option"
-        for _e in range(self.ppo_epoch):
-            perm = perm_fn(rollouts.rewards.size(1)) if perm_fn is not None else None
-            for sample in rollouts.recurrent_generator(advantages, self.num_mini_batch, perm=perm):
+        for sample in self._minibatches_with_encoder_prefetch(rollouts, advantages, perm_fn, option):
+            if True:
                 (obs_batch, hidden_batch, actions_batch, actions_option_batch, prev_actions_batch, value_preds_batch,
                  return_batch, masks_batch, old_lp_batch, adv_targ, rl_masks_batch, unct_gt_batch, em_goal, em_option,
                  _em_vln, _em_dialog, em_masks, _em_vln_masks, _all_dialog, query_state_batch, last_query_info,
@@ -107,6 +106,43 @@ class PPO(nn.Module):
         value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]
         # the reference returns the *sums* of the two debug means (ppo.py:279-280, :289)
         return value_loss, action_loss, entropy, s[5] * n_updates, s[6] * n_updates, unct_loss
+
+    prefetch_encoders = True
+
+    def _minibatches_with_encoder_prefetch(self, rollouts, advantages, perm_fn, option):
+        """All ``ppo_epoch x num_mini_batch`` minibatches in the reference's order (ppo.py:163-166), one ahead: while
+        minibatch k runs its scene-memory transformer forward / backward and the optimizer step on the current stream,
+        the FROZEN encoders of minibatch k+1 (observation-only feature columns: no gradient, independent of the step)
+        are already enqueued on a side stream — HBM-bound convolutions / GroupNorms next to FMA- and tensor-bound
+        transformer kernels.  Trainable encoders are never prefetched (their weights change with the step)."""
+        def minibatches():
+            for _e in range(self.ppo_epoch):
+                perm = perm_fn(rollouts.rewards.size(1)) if perm_fn is not None else None
+                yield from rollouts.recurrent_generator(advantages, self.num_mini_batch, perm=perm)
+
+        net = getattr(self.actor_critic, "net", None)
+        can = (self.prefetch_encoders and net is not None and hasattr(net, "prefetch_observation_features")
+               and advantages.is_cuda
+               and not any(p.requires_grad for enc in (net.goal_encoder, net.visual_encoder, net.action_encoder)
+                           for p in enc.parameters()))
+        if not can:
+            yield from minibatches()
+            return
+        stream = self.__dict__.get("_encoder_stream")
+        if stream is None:
+            stream = self.__dict__["_encoder_stream"] = torch.cuda.Stream()
+        extra = getattr(net, "_query_count_emb_size", 0) if option else 0
+        it = minibatches()
+        cur = next(it, None)
+        if cur is not None:  # the first minibatch goes through the same stream: one encoder run at a time, in order
+            net.prefetch_observation_features(cur[0], net.observation_key(cur[0]), stream, extra_cols=extra)
+        while cur is not None:
+            nxt = next(it, None)  # its gathers are enqueued on the current stream before minibatch k's kernels
+            if nxt is not None:
+                net.prefetch_observation_features(nxt[0], net.observation_key(nxt[0]), stream, extra_cols=extra)
+            yield cur
+            cur = nxt
+        net.drop_prefetch()
 
     def update_dialog(self, rollouts):
         """ppo.py:99-154: one full-batch ``evaluate_actions_dialog`` over the NUM_DIALOG_STEPS x N rows, weighted

@@ -46,7 +46,8 @@ class PPOTrainer:
             if vs is None:
                 vs = self._encoder_stream = torch.cuda.Stream()
             slot = {k: rollouts.observations[k][s + 1] for k in net._PREFETCH_KEYS if k in rollouts.observations}
-            net.prefetch_observation_features(observations, net.observation_key(slot), vs)
+            net.prefetch_observation_features(observations, net.observation_key(slot), vs,
+                                              visual_event=getattr(self.envs, "visual_ready_event", None))
         if self.belief_predictor is not None:  # :890-894: belief for the NEXT observation
             if getattr(self.config, "overlap_belief", False):
                 observations = self._belief_update_deferred(rollouts, observations, dones)

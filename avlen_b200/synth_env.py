@@ -23,6 +23,8 @@ class SyntheticVectorEnv:
         self.host_buffers = host_buffers
         self.fused_step = fused_step  # one kernel for the episode bookkeeping (avl_synth_env_step) instead of ~30 torch ops
         self.last_masks = None
+        self._visual_stream = None
+        self.visual_ready_event = None
         rng = np.random.default_rng(seed)
         self._g = torch.Generator(device="cpu").manual_seed(seed)
         self.pool = pool
@@ -56,22 +58,40 @@ class SyntheticVectorEnv:
         self._rand_pool = None
 
     def _visual(self):
+        """The frames of this step, produced on a side stream (host->device copies / uint8->float cast run next to the
+        audio rendering on the main stream).  ``visual_ready_event`` marks their completion: the main stream waits for
+        it in ``_observe``; a consumer that only needs the frames (the trainer's encoder prefetch) may wait for the
+        event instead of for the whole main stream."""
         i = self._t % self.pool
-        if self.host_buffers:
-            rgb = self._rgb[i].to(self.device, non_blocking=True)
-            depth = self._depth[i].to(self.device, non_blocking=True)
-        else:
-            rgb, depth = self._rgb[i], self._depth[i]
-        return rgb.float(), depth  # batch_obs: everything becomes float32 (common/utils.py:149-154)
+        main = torch.cuda.current_stream()
+        side = self._visual_stream
+        if side is None:
+            side = self._visual_stream = torch.cuda.Stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if self.host_buffers:
+                rgb = self._rgb[i].to(self.device, non_blocking=True)
+                depth = self._depth[i].to(self.device, non_blocking=True)
+            else:
+                rgb, depth = self._rgb[i], self._depth[i]
+            rgb = rgb.float()  # batch_obs: everything becomes float32 (common/utils.py:149-154)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self.visual_ready_event = ev
+        return rgb, depth
 
     def _observe(self, silent=None, pose=None, beliefs=None):
         a = self._audio
         if silent is None:
             silent = (self._episode_step > self._silent_after).to(torch.int32)  # simulator.py:646
+        rgb, depth = self._visual()
         _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
                                        silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
                                        want_audiogoal=False)
-        rgb, depth = self._visual()
+        main = torch.cuda.current_stream()
+        main.wait_event(self.visual_ready_event)
+        rgb.record_stream(main)
+        depth.record_stream(main)
         if pose is None:
             pose = torch.cat([self._pose_xy, self._heading[:, None], self._episode_step[:, None]], 1)
         n = self.num_envs

@@ -44,6 +44,9 @@ int avl_audio_render_spectrogram(void* handle, int n_envs, const float* sounds, 
                                  const int* d_rir_len, float* audiogoal_out, float* spectrogram_out, void* stream);
 int avl_audio_spectrogram(void* handle, int n, const float* audio /* (N,2,sr) */, float* spectrogram_out,
                           void* stream);
+/* 1 (default): batches of at most half the SM count render each ear in its own CTA (rollout latency); 0: one CTA per
+ * env always.  Returns the old setting. */
+int avl_set_audio_channel_split(int on);
 
 /* ------------------------------------------------------------------------- rows N, O: returns / advantages
  * ss_baselines/savi/models/rollout_storage.py:394-412, ss_baselines/common/rollout_storage.py:114-132 (bit-exact)

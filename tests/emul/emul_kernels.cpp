@@ -24,9 +24,12 @@ EMUL_API int emul_audio_render(int n_envs, int sr, const float* sounds, const lo
                                float* audiogoal, float* spectrogram, int grid) {
   std::vector<cf> tw(kM + 1);
   emul::launch(dim3((kM + 1 + 255) / 256), dim3(256), [&] { twiddle_init_kernel(tw.data()); });
+  const int split = grid < 0 ? 1 : 0;  // negative grid: one CTA per (env, ear) (RenderArgs::split)
+  if (grid < 0) grid = -grid;
   std::vector<cf> scratch((size_t)3 * (kM + 1) * grid);
   int status = 0;
   RenderArgs a;
+  a.split = split;
   a.n_envs = n_envs; a.sr = sr; a.sounds = sounds; a.clip_off = clip_off; a.index = index; a.rirs = rirs;
   a.rir_off = rir_off; a.rir_len = rir_len; a.silent = silent; a.d_clip_off = d_clip_off; a.d_rir_off = d_rir_off;
   a.d_rir_len = d_rir_len; a.audiogoal = audiogoal; a.spectrogram = spectrogram; a.tw = tw.data();

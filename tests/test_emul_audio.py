@@ -37,6 +37,15 @@ def test_emulated_render_matches_oracle(emul_lib, distractor):
     assert np.abs(sp - sp_ref).max() < 1e-4 * max(1.0, np.abs(sp_ref).max())
 
 
+def test_emulated_render_channel_split_matches_unsplit(emul_lib):
+    """One CTA per (env, ear) (small batches, RenderArgs::split) writes exactly what one CTA per env writes."""
+    b = synth.make_audio_batch(12, 3, max_seconds=6, distractor=False, silent_frac=0.0)
+    b["silent"][1] = 1
+    ag, sp = _run_emul(emul_lib, b, grid=2)
+    ag2, sp2 = _run_emul(emul_lib, b, grid=-3)
+    assert np.array_equal(ag, ag2) and np.array_equal(sp, sp2)
+
+
 def test_emulated_spectrogram_only(emul_lib):
     rng = np.random.default_rng(5)
     audio = (rng.standard_normal((3, 2, SR)) * 0.2).astype(np.float32)

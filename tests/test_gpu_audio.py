@@ -111,3 +111,23 @@ def test_argument_errors(renderer):
         renderer.compute_spectrogram(torch.zeros(2, 2, 100, device="cuda"))
     with pytest.raises(_lib.AvlenError):
         renderer.compute_spectrogram(torch.zeros(2, 2, SR))  # CPU tensor: no CPU fallback
+
+
+@pytest.mark.parametrize("distractor", [False, True])
+def test_channel_split_small_batches_bitwise(renderer, distractor):
+    """Rollout-sized batches (2 N <= SM count) render each ear in its own CTA; results equal the one-CTA-per-env path."""
+    from avlen_b200 import _lib
+    b = synth.make_audio_batch(23, 9, max_seconds=6, distractor=distractor, silent_frac=0.2)
+    b["silent"][2] = 1
+    b["rir_len"][4] = 0
+    lib = _lib.lib()
+    old = lib.avl_set_audio_channel_split(0)
+    try:
+        ag0, sp0 = _render(renderer, b)
+        lib.avl_set_audio_channel_split(1)
+        ag1, sp1 = _render(renderer, b)
+    finally:
+        lib.avl_set_audio_channel_split(old)
+    assert np.array_equal(ag0, ag1) and np.array_equal(sp0, sp1)
+    ag_ref, sp_ref = oracle_render(b)
+    assert rel_err(ag1, ag_ref) < TOL

@@ -78,7 +78,7 @@ def test_tc_conv_matches_fp32(shape):
 
 @pytest.mark.parametrize("shape", [
     (64, 8, 8, 128, 128, 3, 3, 1, 1), (64, 5, 2, 256, 256, 3, 3, 1, 1), (64, 3, 1, 512, 512, 3, 3, 1, 1),
-    (64, 9, 4, 128, 128, 3, 3, 1, 1), (5, 13, 3, 64, 512, 13, 3, 1, 0), (64, 16, 16, 64, 128, 3, 3, 2, 1),
+    (64, 9, 4, 128, 128, 3, 3, 1, 1), (70, 13, 3, 64, 512, 13, 3, 1, 0), (64, 16, 16, 64, 128, 3, 3, 2, 1),
     (33, 8, 8, 128, 66, 3, 3, 1, 1), (7, 8, 8, 132, 20, 3, 3, 1, 1), (64, 8, 8, 128, 64, 8, 8, 1, 0),
 ])
 def test_tc_splitk_cluster_reduction(shape):
