@@ -123,9 +123,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  // distributed shared memory of a peer may only be written once that peer has started executing: every thread
-  // arrives here and waits (cluster_wait_started) right before its first remote store
-  if (cred) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   // ---- per-thread load coordinates: chunk column c = tid & 7 is fixed, rows (tid >> 3) + 16 j
   const int c = tid & 7;
@@ -217,8 +214,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
     }
     __syncwarp();
     if (cred) {  // every thread of the cluster takes part in both barriers of the split-K reduction
-      asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
-      cluster_arrive_wait();
+      cluster_arrive_wait();  // (1) every member has finished its main loop
+      cluster_arrive_wait();  // (2) every partial tile has been delivered
     }
     tc_fence_before();
     __syncthreads();
@@ -259,7 +256,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
     const int rows_per = TC_BM / S;
     const uint32_t ldred = (uint32_t)bn + 4;  // floats; +4: the 16-byte stores of 32 lanes (32 rows) spread over the banks
     const uint32_t rank = cluster_ctarank();
-    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // all members are running (arrival at kernel start)
+    // The reduction buffer ALIASES the operand ring (one more CTA fits an SM): a peer may only write into it once this
+    // CTA's last MMA has read its operands — every thread arrives after the DONE wait above (MMA warp: after its own
+    // EMPTY waits), so once the barrier completes no ring of the cluster is in use any more.  The barrier also
+    // guarantees that every peer has started executing, which distributed shared memory accesses require.
+    cluster_arrive_wait();
     if (KT > 0) {
       const uint32_t owner = (uint32_t)(row / rows_per);
       const uint32_t dst = smem_base + p.red_off + ((rank * rows_per + (uint32_t)(row % rows_per)) * ldred) * 4u;
@@ -464,12 +465,13 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.tmem_cols = cols;
   const size_t stage = p.swz ? (TC_BM + (size_t)p.bn) * 128 : (size_t)TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
   const size_t red_bytes = p.cluster_red ? (size_t)TC_BM * (p.bn + 4) * sizeof(float) : 0;
-  p.stages = (int)((100 * 1024 - red_bytes) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+  p.stages = (int)((100 * 1024) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (p.cluster_red) p.stages = 3;  // short k-slices: a small footprint (3 CTAs per SM next to the other streams' kernels)
   if (p.stages < 3) p.stages = 3;  // the loaders keep TC_INFLIGHT = 2 tiles in flight
   size_t smem = (size_t)p.stages * stage;
-  p.red_off = (unsigned)smem;  // (the SWIZZLE_128B stage size is a multiple of 1024 bytes)
-  smem += red_bytes;
+  p.red_off = 0;  // the reduction buffer aliases the operand ring (see the kernel)
+  if (smem < red_bytes) smem = red_bytes;
 
   dim3 grid(mtiles, avl_div_up(p.N, p.bn), p.splits);
   const float *scale = p.scale, *bias = p.bias, *residual = p.residual;

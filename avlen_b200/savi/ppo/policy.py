@@ -361,14 +361,16 @@ class AudioNavSMTNet(Net):
         return d
 
     @torch.no_grad()
-    def prefetch_observation_features(self, observations, key, stream, extra_cols=0, visual_event=None):
+    def prefetch_observation_features(self, observations, key, stream, extra_cols=0, visual_event=None, between=None):
         """``observations``: what the environment returned (or the next minibatch of a PPO update); ``key``:
         ``observation_key`` of the tensors the consuming ``act`` / ``get_value`` / ``evaluate_actions`` call will be
         given (rollout: the storage slots these observations are copied into).  All prefetches must be enqueued on
         the same ``stream`` (the encoders' workspaces are per network).
         ``visual_event``: optional event after which the frames are complete (an environment that produces them on
         its own stream): the visual encoders then start without waiting for the rest of the current stream (the audio
-        rendering); everything else waits for the current stream."""
+        rendering); everything else waits for the current stream.  ``between``: optional callable run by the host
+        after the visual encoders have been enqueued and before the remaining columns are (the trainer enqueues the
+        belief networks there: they are the longer dependency chain of the next step)."""
         main = torch.cuda.current_stream()
         if visual_event is not None:
             stream.wait_event(visual_event)
@@ -382,6 +384,8 @@ class AudioNavSMTNet(Net):
         with torch.cuda.stream(stream):
             x = torch.empty((n, self._base_feature_size + extra_cols), device=dev, dtype=torch.float32)
             self._observation_features_into(x, observations, visual=True, rest=False)
+        if between is not None:
+            between()
         if visual_event is not None:
             stream.wait_stream(main)
         with torch.cuda.stream(stream):

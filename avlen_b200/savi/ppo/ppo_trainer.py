@@ -39,20 +39,29 @@ class PPOTrainer:
                 running_episode_stats["reward"] += (1 - masks) * current_episode_reward
                 running_episode_stats["count"] += 1 - masks
             current_episode_reward *= masks
+        box = [observations]
+
+        def belief():  # :890-894: belief for the NEXT observation
+            if self.belief_predictor is not None:
+                if getattr(self.config, "overlap_belief", False):
+                    box[0] = self._belief_update_deferred(rollouts, observations, dones)
+                else:
+                    self.belief_predictor.update(observations, dones)
+
         if getattr(self.config, "prefetch_encoders", False) and s + 1 < rollouts.masks.shape[0]:
-            # the visual / audio encoders of observation s+1 only need what the environment just returned
+            # the visual / audio encoders of observation s+1 only need what the environment just returned; the belief
+            # networks are enqueued right after the visual encoders (host order = start order of the chains)
             net = self.actor_critic.net
             vs = getattr(self, "_encoder_stream", None)
             if vs is None:
                 vs = self._encoder_stream = torch.cuda.Stream()
             slot = {k: rollouts.observations[k][s + 1] for k in net._PREFETCH_KEYS if k in rollouts.observations}
             net.prefetch_observation_features(observations, net.observation_key(slot), vs,
-                                              visual_event=getattr(self.envs, "visual_ready_event", None))
-        if self.belief_predictor is not None:  # :890-894: belief for the NEXT observation
-            if getattr(self.config, "overlap_belief", False):
-                observations = self._belief_update_deferred(rollouts, observations, dones)
-            else:
-                self.belief_predictor.update(observations, dones)
+                                              visual_event=getattr(self.envs, "visual_ready_event", None),
+                                              between=belief)
+        else:
+            belief()
+        observations = box[0]
         rollouts.insert(observations, recurrent_hidden_states, actions, None, actions_log_probs, values, rewards, masks,
                         masks, external_memory_features, None, None, None, None, None, None, None, None, None, None,
                         None, None)
