@@ -468,6 +468,9 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.stages = (int)((100 * 1024) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
   if (p.cluster_red) p.stages = 3;  // short k-slices: a small footprint (3 CTAs per SM next to the other streams' kernels)
+  if (conv && KT <= 6) p.stages = 3;  // shallow stride-2 layers (K = 144): the cost is per CTA (launch, barriers, TMEM
+                                      // allocation, a 5-tile pipeline), not per k-tile — a third resident CTA per SM hides
+                                      // more of it than a fourth ring slot (update batch: 1870 -> 1570 us)
   if (p.stages < 3) p.stages = 3;  // the loaders keep TC_INFLIGHT = 2 tiles in flight
   size_t smem = (size_t)p.stages * stage;
   p.red_off = 0;  // the reduction buffer aliases the operand ring (see the kernel)

@@ -47,6 +47,8 @@ def main():
         tr._update_agent(cfg, tr.rollouts)
         torch.cuda.synchronize()
     print("update wall", time.time() - t0)
+    if os.environ.get("AVL_TRACE_UPDATE"):
+        prof.export_chrome_trace(os.environ["AVL_TRACE_UPDATE"])
     table(prof, "PPO update (2 epochs x 2 minibatches)")
 
 
