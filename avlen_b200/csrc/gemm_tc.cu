@@ -366,6 +366,7 @@ static int g_tc_splitk = 1;
 static int g_tc_splitk_cluster = 1;
 static int g_tc_cluster16 = -1;  // -1: not probed yet; 0: clusters of 16 CTAs unavailable; 1: available
 static int g_tc_swz = 1;
+static int g_tc_stages = 0;  // 0: automatic; 3 / 4: forced ring depth (diagnostic)
 
 __global__ void tc_zero_cols_kernel(float* y, long long ldy, int rows, int cols) {
   const long long total = (long long)rows * cols;
@@ -465,12 +466,19 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.tmem_cols = cols;
   const size_t stage = p.swz ? (TC_BM + (size_t)p.bn) * 128 : (size_t)TC_CHUNKS * ((TC_BM * 16 + 16) + ((size_t)p.bn * 16 + 16));
   const size_t red_bytes = p.cluster_red ? (size_t)TC_BM * (p.bn + 4) * sizeof(float) : 0;
-  p.stages = (int)((100 * 1024) / stage);  // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
-  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
-  if (p.cluster_red) p.stages = 3;  // short k-slices: a small footprint (3 CTAs per SM next to the other streams' kernels)
-  if (conv && KT <= 6) p.stages = 3;  // shallow stride-2 layers (K = 144): the cost is per CTA (launch, barriers, TMEM
-                                      // allocation, a 5-tile pipeline), not per k-tile — a third resident CTA per SM hides
-                                      // more of it than a fourth ring slot (update batch: 1870 -> 1570 us)
+  // Ring depth: the loaders keep TC_INFLIGHT = 2 tiles in flight, so 3 slots suffice; a 4th slot never paid for itself
+  // (tools/tc_conv_bench.py at update batch, TC_STAGES=0/3/4: 3 slots equal or faster on every layer, e.g. the
+  // stride-2 entry convolutions 1.37 -> 1.06 ms, 0.59 -> 0.47 ms, 0.52 -> 0.34 ms) because the smaller footprint
+  // admits one more resident CTA per SM — which hides the per-CTA fixed cost at update batch and lets the kernels of
+  // the other streams co-reside at rollout batch.  Exception (measured on the rollout step, 40.4k vs 38.7k env-steps/s):
+  // a single wave of CTAs with a long reduction is latency-bound and prefers the deeper ring.
+  const long long n_ctas = (long long)mtiles * avl_div_up(p.N, p.bn) * p.splits;
+  p.stages = 3;
+  if (!p.cluster_red && KT > 6 && n_ctas < 2LL * sms) {
+    p.stages = (int)((100 * 1024) / stage);
+    if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  }
+  if (g_tc_stages >= 3 && g_tc_stages <= TC_MAX_STAGES && (size_t)g_tc_stages * stage <= 200 * 1024) p.stages = g_tc_stages;
   if (p.stages < 3) p.stages = 3;  // the loaders keep TC_INFLIGHT = 2 tiles in flight
   size_t smem = (size_t)p.stages * stage;
   p.red_off = 0;  // the reduction buffer aliases the operand ring (see the kernel)
@@ -533,6 +541,14 @@ AVL_API int avl_set_tc_splitk(int on) {
   avl_bump_config_epoch();
   int old = g_tc_splitk;
   g_tc_splitk = on ? 1 : 0;
+  return old;
+}
+
+// Ring depth of the generic kernel: 0 (default) automatic, 3 or 4 forced (diagnostic).  Returns the old value.
+AVL_API int avl_set_tc_stages(int stages) {
+  avl_bump_config_epoch();
+  int old = g_tc_stages;
+  g_tc_stages = stages;
   return old;
 }
 

@@ -37,6 +37,7 @@ _lib.register({
     "avl_set_tc_conv_l1": [I],
     "avl_set_tc_splitk": [I],
     "avl_set_tc_splitk_cluster": [I],
+    "avl_set_tc_stages": [I],
     "avl_set_tc_swizzle": [I],
     "avl_set_tc_tma": [I],
     "avl_set_tc_3xtf32": [I],

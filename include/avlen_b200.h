@@ -240,6 +240,7 @@ int avl_set_tc_conv_halo(int on, int rows_per_strip); /* halo-strip kernel for s
 int avl_set_tc_tma(int on);      /* dense GEMMs: 1 TMA-fed kernel where it applies (default), 0 cp.async kernel; returns old */
 int avl_set_tc_swizzle(int on);  /* generic kernel operand tiles: 1 SWIZZLE_128B (default), 0 SWIZZLE_NONE; returns old */
 int avl_set_tc_splitk(int on);   /* split-K for small-M / long-K tensor-core problems; returns old */
+int avl_set_tc_stages(int stages); /* ring depth of the generic tensor-core kernel: 0 (default) automatic, 3 / 4 forced (diagnostic); returns old */
 int avl_set_tc_splitk_cluster(int on); /* 1 (default): the k-slices of a tile form a thread-block cluster, partial tiles are summed in slice order through distributed shared memory inside the kernel (deterministic, no helper launches); 0: atomic partial sums + separate zero / epilogue kernels; returns old */
 int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
 

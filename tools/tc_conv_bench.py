@@ -13,6 +13,8 @@ SHAPES = [  # H, W, C, Cout, KH, KW, stride, pad
     ("layer1 3x3 16->16 @64", 64, 64, 16, 16, 3, 3, 1, 1),
     ("layer2 3x3 16->32 s2", 64, 64, 16, 32, 3, 3, 2, 1),
     ("layer2 3x3 32->32 @32", 32, 32, 32, 32, 3, 3, 1, 1),
+    ("layer3 3x3 32->64 s2", 32, 32, 32, 64, 3, 3, 2, 1),
+    ("layer4 3x3 64->128 s2", 16, 16, 64, 128, 3, 3, 2, 1),
     ("layer3 3x3 64->64 @16", 16, 16, 64, 64, 3, 3, 1, 1),
     ("layer4 3x3 128->128 @8", 8, 8, 128, 128, 3, 3, 1, 1),
     ("fc 8x8x128->64", 8, 8, 128, 64, 8, 8, 1, 0),
@@ -24,6 +26,8 @@ def main():
     only = sys.argv[2] if len(sys.argv) > 2 else None
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if os.environ.get("TC_STAGES"):
+        K._lib.lib().avl_set_tc_stages(int(os.environ["TC_STAGES"]))
     for name, H, W, C, Co, KH, KW, s, p in SHAPES:
         if only and only not in name:
             continue
