@@ -70,38 +70,37 @@ class PPO(nn.Module):
         n_updates = 0
         option = self.policy_head == "option"
         for sample in self._minibatches_with_encoder_prefetch(rollouts, advantages, perm_fn, option):
-            if True:
-                (obs_batch, hidden_batch, actions_batch, actions_option_batch, prev_actions_batch, value_preds_batch,
-                 return_batch, masks_batch, old_lp_batch, adv_targ, rl_masks_batch, unct_gt_batch, em_goal, em_option,
-                 _em_vln, _em_dialog, em_masks, _em_vln_masks, _all_dialog, query_state_batch, last_query_info,
-                 _agent_step) = sample
-                self._flat_g.zero_()
-                if option:
-                    logits, values, unct = self.actor_critic.evaluate_heads(
-                        "option", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_option, em_masks,
-                        query_state_batch, last_query_info)
-                    acts, rl_mask, ugt = actions_option_batch, rl_masks_batch.float(), unct_gt_batch
-                else:
-                    logits, values, unct = self.actor_critic.evaluate_heads(
-                        "goal", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_goal, em_masks)
-                    acts, rl_mask, ugt = actions_batch, None, None
-                out, dlogits, dvalues, dunct = self._loss(
-                    logits.detach(), acts, old_lp_batch, adv_targ, values.detach(), value_preds_batch, return_batch,
-                    rl_mask, None if unct is None else unct.detach(), ugt, self.clip_param, self.value_loss_coef,
-                    self.entropy_coef, self.unct_coef, self.use_clipped_value_loss)
-                self.before_backward(None)
-                heads, grads = [logits, values], [dlogits, dvalues]
-                if unct is not None:
-                    heads.append(unct)
-                    grads.append(dunct)
-                torch.autograd.backward(heads, grads)
-                self.after_backward(None)
-                scale = self._reduce_gradients()
-                self.before_step()
-                self.optimizer.step(self.max_grad_norm, grad_scale=scale)
-                self.after_step()
-                sums += out
-                n_updates += 1
+            (obs_batch, hidden_batch, actions_batch, actions_option_batch, prev_actions_batch, value_preds_batch,
+             return_batch, masks_batch, old_lp_batch, adv_targ, rl_masks_batch, unct_gt_batch, em_goal, em_option,
+             _em_vln, _em_dialog, em_masks, _em_vln_masks, _all_dialog, query_state_batch, last_query_info,
+             _agent_step) = sample
+            self._flat_g.zero_()
+            if option:
+                logits, values, unct = self.actor_critic.evaluate_heads(
+                    "option", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_option, em_masks,
+                    query_state_batch, last_query_info)
+                acts, rl_mask, ugt = actions_option_batch, rl_masks_batch.float(), unct_gt_batch
+            else:
+                logits, values, unct = self.actor_critic.evaluate_heads(
+                    "goal", obs_batch, hidden_batch, prev_actions_batch, masks_batch, em_goal, em_masks)
+                acts, rl_mask, ugt = actions_batch, None, None
+            out, dlogits, dvalues, dunct = self._loss(
+                logits.detach(), acts, old_lp_batch, adv_targ, values.detach(), value_preds_batch, return_batch,
+                rl_mask, None if unct is None else unct.detach(), ugt, self.clip_param, self.value_loss_coef,
+                self.entropy_coef, self.unct_coef, self.use_clipped_value_loss)
+            self.before_backward(None)
+            heads, grads = [logits, values], [dlogits, dvalues]
+            if unct is not None:
+                heads.append(unct)
+                grads.append(dunct)
+            torch.autograd.backward(heads, grads)
+            self.after_backward(None)
+            scale = self._reduce_gradients()
+            self.before_step()
+            self.optimizer.step(self.max_grad_norm, grad_scale=scale)
+            self.after_step()
+            sums += out
+            n_updates += 1
         s = (sums / max(1, n_updates)).tolist()  # the only host synchronisation of the update
         value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]
         # the reference returns the *sums* of the two debug means (ppo.py:279-280, :289)
