@@ -18,13 +18,14 @@
 
 namespace {
 
-constexpr int X3_BM = 128, X3_BK = 32, X3_STAGES = 2, X3_SPLITTERS = 128, X3_EPI = 128;
+constexpr int X3_BM = 128, X3_BK = 32, X3_MAX_STAGES = 3, X3_SPLITTERS = 128, X3_EPI = 128;
 constexpr int X3_THREADS = X3_SPLITTERS + X3_EPI + 64;  // warps 0-3 split, 4-7 epilogue, 8 MMA, 9 TMA
 
 struct X3Args {
   float* C;
   long long ldc;
   int M, N, K, bn, n_tiles, tmem_cols;
+  int stages;  // ring depth: 2 (column tiles of 256: 96 KB per slot) or 3 (narrower tiles)
   const float* bias;
   const float* residual;
   long long ldr;
@@ -48,9 +49,10 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmBhi,
                                                                 const __grid_constant__ CUtensorMap tmBlo, X3Args p) {
   AVL_DYN_SMEM(smem);
-  __shared__ __align__(8) unsigned long long bars[3 * X3_STAGES + 4];  // full[S], split[S], empty[S], acc_full[2], acc_empty[2]
+  __shared__ __align__(8) unsigned long long bars[3 * X3_MAX_STAGES + 4];  // full[S], split[S], empty[S], acc_full[2], acc_empty[2]
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int X3_STAGES = p.stages;
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
   const int total_tiles = ((M + X3_BM - 1) / X3_BM) * p.n_tiles;
@@ -514,7 +516,11 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   CUtensorMap ta, tbh, tbl;
   if (!make_map3(&ta, A, M, K, lda, X3_BM) || !make_map3(&tbh, bhi, N, K, K, p.bn) || !make_map3(&tbl, blo, N, K, K, p.bn))
     return AVL_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)X3_STAGES * (2 * X3_BM + 2 * (size_t)p.bn) * 128;
+  // 2 slots of 96 KB with 256-column tiles; narrower tiles (rollout batch) afford a third slot, which matters there:
+  // a tile is only 8-9 k-steps long, so the pipeline never reaches steady state with 2
+  const size_t slot_bytes = (2 * X3_BM + 2 * (size_t)p.bn) * 128;
+  p.stages = 3 * slot_bytes <= 200 * 1024 ? 3 : 2;
+  const size_t smem = (size_t)p.stages * slot_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -690,6 +690,84 @@ __global__ void attn_cross_fwd_kernel(const float* __restrict__ q, const float* 
   out[(size_t)b * D + h * ATT_HD + lane] = o;
 }
 
+// D = 256 (8 heads of 32) variant with more loads in flight: the kernel above walks the keys one warp-wide row per
+// step (a memory round trip per 8 keys and per head); at rollout batch (64 CTAs) that latency is the whole cost.
+//   phase 1: a warp takes WHOLE 256-wide key rows — lane l holds columns [8l, 8l + 8), i.e. a quarter of head l / 4 —
+//            four rows per iteration, two shuffles finish the eight head scores of a row;
+//   phase 2: warp h normalises head h (max, exp, sum);  phase 3: thread t accumulates output column t over all keys,
+//            eight value rows in flight.
+__global__ void __launch_bounds__(256) attn_cross_fwd256_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                                const int* __restrict__ off, float* out,
+                                                                float* probs /* [R, 8] */, float scale) {
+  AVL_DYN_SMEM(smem_raw);
+  float* Ps = reinterpret_cast<float*>(smem_raw);  // [8][ATT_MAXV]
+  constexpr int D = 256, H = 8;
+  const int b = blockIdx.x;
+  const int r0 = off[b], V = off[b + 1] - r0;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float qv[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q + (size_t)b * D + 8 * lane);
+    const float4 c = *reinterpret_cast<const float4*>(q + (size_t)b * D + 8 * lane + 4);
+    qv[0] = a.x * scale; qv[1] = a.y * scale; qv[2] = a.z * scale; qv[3] = a.w * scale;
+    qv[4] = c.x * scale; qv[5] = c.y * scale; qv[6] = c.z * scale; qv[7] = c.w * scale;
+  }
+  for (int j0 = w; j0 < V; j0 += 32) {  // rows j0, j0 + 8, j0 + 16, j0 + 24 of this warp
+    float4 ka[4], kb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < V) {
+        const float* row = kv + (size_t)(r0 + j) * 2 * D + 8 * lane;
+        ka[u] = *reinterpret_cast<const float4*>(row);
+        kb[u] = *reinterpret_cast<const float4*>(row + 4);
+      } else {
+        ka[u] = kb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = qv[0] * ka[u].x;
+      s = fmaf(qv[1], ka[u].y, s); s = fmaf(qv[2], ka[u].z, s); s = fmaf(qv[3], ka[u].w, s);
+      s = fmaf(qv[4], kb[u].x, s); s = fmaf(qv[5], kb[u].y, s); s = fmaf(qv[6], kb[u].z, s); s = fmaf(qv[7], kb[u].w, s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const int j = j0 + 8 * u;
+      if (j < V && (lane & 3) == 0) Ps[(lane >> 2) * ATT_MAXV + j] = s;
+    }
+  }
+  __syncthreads();
+  float* ps = Ps + w * ATT_MAXV;  // head w
+  float mx = -INFINITY;
+  for (int j = lane; j < V; j += 32) mx = fmaxf(mx, ps[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < V; j += 32) {
+    const float p = __expf(ps[j] - mx);
+    ps[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < V; j += 32) {
+    const float p = ps[j] * inv;
+    ps[j] = p;
+    if (probs) probs[(size_t)(r0 + j) * H + w] = p;
+  }
+  __syncwarp();
+  float o = 0.f;  // output column tid (head w): same key order as the generic kernel
+  for (int j0 = 0; j0 < V; j0 += 8) {
+    float vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) vv[u] = (j0 + u < V) ? kv[(size_t)(r0 + j0 + u) * 2 * D + D + tid] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (j0 + u < V) o = fmaf(ps[j0 + u], vv[u], o);
+  }
+  out[(size_t)b * D + tid] = o;
+}
+
 __global__ void attn_cross_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                       const int* __restrict__ off, const float* __restrict__ probs,
                                       const float* __restrict__ dout, float* dq, float* dkv, int D, float scale) {

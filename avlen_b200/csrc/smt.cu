@@ -432,7 +432,10 @@ static void tf_forward(Launcher& L, const float* const* P, const TfBufs& t, cons
   ln_fwd(L, tgt, t.SA, P[TP_DEC_N1_W], P[TP_DEC_N1_B], t.T1, t.STT1, nullptr, B, D);
   lin_fwd(L, t.T1, D, P[TP_DEC_CA_IN_W], P[TP_DEC_CA_IN_B], t.Q, D, B, D, D, 0, nullptr);
   lin_fwd(L, t.MEM, D, P[TP_DEC_CA_IN_W] + (size_t)D * D, P[TP_DEC_CA_IN_B] + D, t.KV, 2 * D, Rcap, 2 * D, D, 0, total);
-  AVL_LAUNCH(attn_cross_fwd_kernel, B, H * 32, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, D, scale);
+  if (D == 256)
+    AVL_LAUNCH(attn_cross_fwd256_kernel, B, 256, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, scale);
+  else
+    AVL_LAUNCH(attn_cross_fwd_kernel, B, H * 32, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, D, scale);
   L.check();
   lin_fwd(L, t.C, D, P[TP_DEC_CA_OUT_W], P[TP_DEC_CA_OUT_B], t.CO, D, B, D, D, 0, nullptr);
   ln_fwd(L, t.T1, t.CO, P[TP_DEC_N2_W], P[TP_DEC_N2_B], t.T2, t.STT2, nullptr, B, D);
@@ -594,8 +597,12 @@ AVL_API int avl_attn_cross_fwd(const float* q, const float* kv, const int* off, 
   if (B == 0) return AVL_OK;
   if (!q || !kv || !off || !out) return AVL_ERR_ARG;
   int H = D / 32;
-  AVL_LAUNCH(attn_cross_fwd_kernel, B, H * 32, H * ATT_MAXV * sizeof(float), (cudaStream_t)stream, q, kv, off, out, probs, D,
-                                                                                          1.0f / sqrtf(32.f));
+  if (D == 256 && (((uintptr_t)q | (uintptr_t)kv) & 15) == 0)
+    AVL_LAUNCH(attn_cross_fwd256_kernel, B, 256, H * ATT_MAXV * sizeof(float), (cudaStream_t)stream, q, kv, off, out, probs,
+               1.0f / sqrtf(32.f));
+  else
+    AVL_LAUNCH(attn_cross_fwd_kernel, B, H * 32, H * ATT_MAXV * sizeof(float), (cudaStream_t)stream, q, kv, off, out, probs, D,
+               1.0f / sqrtf(32.f));
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
