@@ -1,0 +1,219 @@
+"""Generates the golden vectors under tests/golden/ from the UNMODIFIED reference (merlresearch/avlen), loaded from
+/root/reference through the import shim oracle/ref_shim.py (no reference source is copied; only inputs and the outputs
+the reference computed are stored).  Run in the authoring container:
+
+    python tests/golden/make_golden.py
+
+The reference tree does not travel to the GPU box, so these files are what pins the oracle (tests/test_golden.py, CPU)
+and the CUDA path (tests/test_gpu_golden.py) to the reference there.  Weights are not stored: both sides rebuild them
+from a numpy PCG64 seed (oracle.models_torch.seeded_state_dict), which is platform independent.
+
+Cases (reference file:line of what is being recorded):
+  smt_policy.npz      AudioNavSMTPolicy.evaluate_actions / act(deterministic)      savi/ppo/policy.py:70-96,:183-205
+  option_policy.npz   AudioNavOptionPolicy.evaluate_actions_option / act_option     savi/ppo/policy.py:98-127,:207-235
+  dialog_policy.npz   AudioNavDialogPolicy.evaluate_actions_dialog / act_dialog     savi/ppo/policy.py:130-162,:238-276
+                      (the third-party CLIP package is absent: the shim gives the reference policy the oracle's
+                      restatement of the text tower with 2 layers — the POLICY code around it is the reference's)
+  extmem.npz          ExternalMemory.insert, 37 steps with episode ends             savi/models/rollout_storage.py:930-941
+  gae.npz             RolloutStorage.compute_returns (use_gae True / False)         common/rollout_storage.py:114-132
+  avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
+  rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import models_torch as OM  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+
+def obs(n, g):
+    return {"rgb": torch.randint(0, 256, (n, 128, 128, 3), generator=g).float(),
+            "depth": torch.rand(n, 128, 128, 1, generator=g),
+            "spectrogram": torch.rand(n, 65, 26, 2, generator=g),
+            "pose": torch.cat([torch.randn(n, 2, generator=g) * 5, torch.rand(n, 1, generator=g) * 6 - 3,
+                               torch.randint(0, 50, (n, 1), generator=g).float()], 1),
+            "category": torch.zeros(n, 21), "category_belief": torch.rand(n, 21, generator=g),
+            "location_belief": torch.randn(n, 2, generator=g)}
+
+
+def mem(M, n, dim, g, pose_at):
+    em = torch.randn(M, n, dim, generator=g)
+    em[..., pose_at:pose_at + 4] = torch.cat([torch.randn(M, n, 2, generator=g) * 5, torch.rand(M, n, 1, generator=g) * 6 - 3,
+                                              torch.randint(0, 50, (M, n, 1), generator=g).float()], -1)
+    return em
+
+
+def pack_obs(o):
+    d = {"obs_" + k: v.numpy() for k, v in o.items()}
+    d["obs_rgb"] = o["rgb"].numpy().astype(np.uint8)  # integer-valued 0..255: exact
+    return d
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KB")
+
+
+def policy_kwargs():
+    return dict(hidden_size=256, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
+                pretraining=False)
+
+
+def smt_policy():
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavSMTPolicy(ref_shim.observation_space(), sp.Discrete(4), **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=False), 5))
+    ref.eval()
+    g = torch.Generator().manual_seed(101)
+    n, M = 2, 24
+    o = obs(n, g)
+    em = mem(M, n, 276, g, 272)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    act = torch.randint(0, 4, (n, 1), generator=g)
+    with torch.no_grad():
+        v, lp, ent, _, x = ref.evaluate_actions(o, h, pa, mk, act, em, emm)
+        av, aa, alp, _, ax, apr = ref.act(o, h, pa, mk, em, emm, deterministic=True)
+    save("smt_policy.npz", seed=5, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
+         eval_value=v, eval_log_probs=lp, eval_entropy=ent, eval_em_feats=x,
+         act_value=av, act_action=aa, act_log_probs=alp, act_em_feats=ax, act_probs=apr)
+
+
+def option_policy():
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavOptionPolicy(ref_shim.observation_space(), sp.Discrete(4), **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavOptionPolicy(), 6))
+    ref.eval()
+    g = torch.Generator().manual_seed(102)
+    n, M = 2, 20
+    o = obs(n, g)
+    em = mem(M, n, 308, g, 272)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    qs, lq = torch.randn(n, 32, generator=g), torch.randn(n, 32, generator=g)
+    act = torch.randint(0, 2, (n, 1), generator=g)
+    with torch.no_grad():
+        r = ref.evaluate_actions_option(o, h, pa, mk, act, em, emm, qs, lq)
+        a = ref.act_option(o, h, pa, mk, em, emm, qs, lq, deterministic=True)
+    save("option_policy.npz", seed=6, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
+         query_state=qs, last_query_info=lq,
+         eval_value=r[0], eval_unct=r[1], eval_log_probs=r[2], eval_entropy=r[3], eval_em_feats=r[5], eval_probs=r[6],
+         act_value=a[0], act_unct=a[1], act_action=a[2], act_log_probs=a[3], act_em_feats=a[5], act_probs=a[6])
+
+
+def dialog_policy():
+    os.environ["AVLEN_SHIM_CLIP_LAYERS"] = "2"
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavDialogPolicy(ref_shim.observation_space(), sp.Discrete(4), **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavDialogPolicy(clip_layers=2), 7))
+    ref.eval()
+    g = torch.Generator().manual_seed(103)
+    n, M = 3, 3  # NUM_DIALOG_STEPS = 3 slots; one mask tensor serves both memories on this call path (policy.py:846,:862)
+    o = obs(n, g)
+    em = mem(M, n, 276, g, 272)
+    emd = torch.randn(M, n, 256, generator=g)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    dialog = torch.zeros(n, 77, dtype=torch.long)
+    for b, k in enumerate((6, 0, 12)):
+        if k:
+            dialog[b, 0] = 49406
+            dialog[b, 1:1 + k] = torch.randint(1, 49000, (k,), generator=g)
+            dialog[b, 1 + k] = 49407
+    step = torch.randint(0, 3, (n,), generator=g)
+    act = torch.randint(0, 4, (n, 1), generator=g)
+    with torch.no_grad():
+        r = ref.evaluate_actions_dialog(o, h, pa, mk, act, em, emd, emm, dialog, step, without_dialog=False)
+        a = ref.act_dialog(o, h, pa, mk, em, emd, emm, dialog, step, deterministic=True, without_dialog=False)
+    save("dialog_policy.npz", seed=7, clip_layers=2, **pack_obs(o), em=em, em_dialog=emd, em_masks=emm, prev_actions=pa,
+         masks=mk, action=act, dialog=dialog, agent_step=step,
+         eval_log_probs=r[1], eval_entropy=r[2], eval_em_feats=r[4], eval_em_dialog_feats=r[5], eval_logits=r[6],
+         act_value=a[0], act_action=a[1], act_log_probs=a[2], act_em_feats=a[4], act_em_dialog_feats=a[5], act_probs=a[6])
+
+
+def extmem():
+    rs = ref_shim.load("ss_baselines.savi.models.rollout_storage")
+    g = torch.Generator().manual_seed(104)
+    N, total, cap, dim, steps = 4, 10, 5, 6, 37
+    ref = rs.ExternalMemory(N, total, cap, dim, num_copies=3)
+    feats = torch.randn(steps, N, dim, generator=g)
+    not_done = (torch.rand(steps, N, 1, generator=g) > 0.1).float()
+    mask_trace = []
+    for t in range(steps):
+        ref.insert(feats[t], not_done[t])
+        mask_trace.append(ref.masks.clone())
+    save("extmem.npz", n_envs=N, total=total, capacity=cap, dim=dim, feats=feats, not_done=not_done,
+         masks_trace=torch.stack(mask_trace), final_memory=ref.memory[:, 0], final_idx=ref.idx)
+
+
+def gae():
+    rs = ref_shim.load("ss_baselines.common.rollout_storage")
+    sp = ref_shim.spaces()
+    g = torch.Generator().manual_seed(105)
+    T, N = 12, 5
+    out = {}
+
+    class ActionSpace:  # habitat's action space class name is what the reference's constructor tests for (:51)
+        n = 4
+
+    for use_gae in (True, False):
+        st = rs.RolloutStorage(T, N, ref_shim.observation_space(), ActionSpace(), 8)
+        st.rewards.copy_(torch.randn(T, N, 1, generator=g))
+        st.value_preds.copy_(torch.randn(T + 1, N, 1, generator=g))
+        st.masks.copy_((torch.rand(T + 1, N, 1, generator=g) > 0.2).float())
+        nv = torch.randn(N, 1, generator=g)
+        tag = "gae" if use_gae else "mc"
+        out[tag + "_rewards"], out[tag + "_value_preds"] = st.rewards.clone(), st.value_preds.clone()
+        out[tag + "_masks"], out[tag + "_next_value"] = st.masks.clone(), nv.clone()
+        st.compute_returns(nv, use_gae, 0.99, 0.95)
+        out[tag + "_returns"] = st.returns.clone()
+    save("gae.npz", gamma=0.99, tau=0.95, **out)
+
+
+def avnav_net():
+    pol = ref_shim.load("ss_baselines.av_nav.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavBaselinePolicy(ref_shim.observation_space(), sp.Discrete(4), "spectrogram", hidden_size=512)
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavBaselinePolicy(), 9))
+    ref.eval()
+    g = torch.Generator().manual_seed(106)
+    n = 2
+    o = obs(n, g)
+    h = torch.randn(1, n, 512, generator=g)
+    mk = torch.tensor([[1.0], [0.0]])
+    with torch.no_grad():
+        f, h2 = ref.net(o, h, None, mk)  # (the shipped Policy.act raises: SURVEY Appendix C)
+        value = ref.critic(f)
+    save("avnav_net.npz", seed=9, **pack_obs(o), hidden=h, masks=mk, features=f, hidden_out=h2, value=value)
+
+
+def rnn_seq():
+    rnn = ref_shim.load("ss_baselines.av_nav.models.rnn_state_encoder")
+    torch.manual_seed(107)
+    ref = rnn.RNNStateEncoder(32, 16)
+    g = torch.Generator().manual_seed(108)
+    T, N = 9, 3
+    x = torch.randn(T * N, 32, generator=g)
+    h = torch.randn(1, N, 16, generator=g)
+    m = (torch.rand(T * N, 1, generator=g) > 0.25).float()
+    with torch.no_grad():
+        o, h2 = ref(x, h, m)
+    save("rnn_seq.npz", T=T, N=N, x=x, hidden=h, masks=m, out=o, hidden_out=h2,
+         **{"w_" + k: v for k, v in ref.state_dict().items()})
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
+    torch.set_num_threads(1)
+    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq):
+        fn()

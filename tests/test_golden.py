@@ -1,0 +1,130 @@
+"""Pins the CPU oracle (oracle/*) against golden vectors recorded from the UNMODIFIED reference
+(tests/golden/make_golden.py, run in the authoring container where /root/reference exists).  Unlike
+tests/test_oracle_vs_reference.py these run everywhere, the GPU box included: the files carry the reference's outputs."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import models_torch as OM
+from oracle import rl_torch as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ATOL = 2e-5  # reference and oracle are both PyTorch fp32 on the CPU; thread counts / BLAS blocking may differ
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name)).items()}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def obs_of(g):
+    o = {k[4:]: t(v) for k, v in g.items() if k.startswith("obs_")}
+    o["rgb"] = o["rgb"].float()
+    return o
+
+
+def close(a, b, atol=ATOL):
+    b = t(b)
+    return float((a.detach().float() - b.float()).abs().max()) <= atol * max(1.0, float(b.abs().max()))
+
+
+def test_smt_policy_oracle_matches_reference_golden():
+    g = load("smt_policy.npz")
+    pol = OM.AudioNavSMTPolicy(pretraining=False)
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512)
+    with torch.no_grad():
+        v, lp, ent, _, x = pol.evaluate_actions(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["action"]), t(g["em"]),
+                                                t(g["em_masks"]))
+        av, aa, alp, _, ax, apr = pol.act(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["em"]), t(g["em_masks"]),
+                                          uniforms=None)
+    assert close(v, g["eval_value"]) and close(lp, g["eval_log_probs"]) and close(ent, g["eval_entropy"])
+    assert close(x, g["eval_em_feats"]) and close(av, g["act_value"]) and close(alp, g["act_log_probs"])
+    assert close(ax, g["act_em_feats"]) and close(apr, g["act_probs"])
+    assert torch.equal(aa, t(g["act_action"]))
+
+
+def test_option_policy_oracle_matches_reference_golden():
+    g = load("option_policy.npz")
+    pol = OM.AudioNavOptionPolicy()
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512)
+    args = (t(g["em"]), t(g["em_masks"]), t(g["query_state"]), t(g["last_query_info"]))
+    with torch.no_grad():
+        r = pol.evaluate_actions_option(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["action"]), *args)
+        a = pol.act_option(o, h, t(g["prev_actions"]), t(g["masks"]), *args, uniforms=None)
+    for i, k in ((0, "eval_value"), (1, "eval_unct"), (2, "eval_log_probs"), (3, "eval_entropy"), (5, "eval_em_feats"),
+                 (6, "eval_probs")):
+        assert close(r[i], g[k]), k
+    for i, k in ((0, "act_value"), (1, "act_unct"), (3, "act_log_probs"), (5, "act_em_feats"), (6, "act_probs")):
+        assert close(a[i], g[k]), k
+    assert torch.equal(a[2], t(g["act_action"]))
+
+
+def test_dialog_policy_oracle_matches_reference_golden():
+    g = load("dialog_policy.npz")
+    pol = OM.AudioNavDialogPolicy(clip_layers=int(g["clip_layers"]))
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512)
+    args = (t(g["em"]), t(g["em_dialog"]), t(g["em_masks"]), t(g["dialog"]), t(g["agent_step"]))
+    with torch.no_grad():
+        r = pol.evaluate_actions_dialog(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["action"]), *args,
+                                        without_dialog=False)
+        a = pol.act_dialog(o, h, t(g["prev_actions"]), t(g["masks"]), *args, uniforms=None, without_dialog=False)
+    assert r[0] is None
+    for i, k in ((1, "eval_log_probs"), (2, "eval_entropy"), (4, "eval_em_feats"), (5, "eval_em_dialog_feats"),
+                 (6, "eval_logits")):
+        assert close(r[i], g[k]), k
+    for i, k in ((0, "act_value"), (2, "act_log_probs"), (4, "act_em_feats"), (5, "act_em_dialog_feats"), (6, "act_probs")):
+        assert close(a[i], g[k]), k
+    assert torch.equal(a[1], t(g["act_action"]))
+
+
+def test_external_memory_oracle_matches_reference_golden():
+    g = load("extmem.npz")
+    N, total, cap, dim = int(g["n_envs"]), int(g["total"]), int(g["capacity"]), int(g["dim"])
+    em = R.ExternalMemory(N, total, cap, dim, num_copies=3)
+    for step in range(g["feats"].shape[0]):
+        em.insert(t(g["feats"][step]), t(g["not_done"][step]))
+        assert torch.equal(em.masks, t(g["masks_trace"][step])), step     # bit-exact mask logic
+    assert em.idx == int(g["final_idx"])
+    assert torch.equal(em.memory[:, 0], t(g["final_memory"]))
+
+
+def test_gae_oracle_matches_reference_golden():
+    g = load("gae.npz")
+    for tag, use_gae in (("gae", True), ("mc", False)):
+        rewards, vp, masks = t(g[tag + "_rewards"]), t(g[tag + "_value_preds"]).clone(), t(g[tag + "_masks"])
+        returns = R.compute_returns(rewards, vp, masks, t(g[tag + "_next_value"]), rewards.shape[0], use_gae,
+                                    float(g["gamma"]), float(g["tau"]))
+        assert torch.allclose(returns, t(g[tag + "_returns"]), atol=1e-6, rtol=1e-6), tag
+
+
+def test_av_nav_net_oracle_matches_reference_golden():
+    g = load("avnav_net.npz")
+    pol = OM.AudioNavBaselinePolicy()
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    with torch.no_grad():
+        f, h2 = pol._features(obs_of(g), t(g["hidden"]), t(g["masks"]))
+        value = pol.critic(f)
+    assert close(f, g["features"]) and close(h2, g["hidden_out"]) and close(value, g["value"])
+
+
+def test_rnn_seq_forward_oracle_matches_reference_golden():
+    g = load("rnn_seq.npz")
+    enc = OM.RNNStateEncoder(32, 16)
+    enc.load_state_dict({k[2:]: t(v) for k, v in g.items() if k.startswith("w_")})
+    with torch.no_grad():
+        o, h2 = enc(t(g["x"]), t(g["hidden"]), t(g["masks"]))
+    assert close(o, g["out"]) and close(h2, g["hidden_out"])

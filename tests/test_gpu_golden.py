@@ -1,0 +1,138 @@
+"""The CUDA path against golden vectors recorded from the UNMODIFIED reference (tests/golden/make_golden.py): the
+reference tree does not exist on the GPU box, the files carry its outputs.  fp32 kernels (tensor cores off): fp32
+outputs within 1e-3 relative (north_star), actions / masks / indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models_torch as OM
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+KW = dict(hidden_size=256, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
+          pretraining=False)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_path():
+    from avlen_b200 import nn as K
+    old = K.set_tensor_cores(False)
+    yield
+    K.set_tensor_cores(old)
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name)).items()}
+
+
+def d(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+def obs_of(g):
+    o = {k[4:]: d(v) for k, v in g.items() if k.startswith("obs_")}
+    o["rgb"] = o["rgb"].float()
+    return o
+
+
+def rel(a, b):
+    b = torch.from_numpy(np.asarray(b)).float()
+    return float((a.detach().float().cpu() - b).abs().max() / max(1e-12, float(b.abs().max())))
+
+
+def _load(policy, oracle_cls_instance, seed):
+    policy.load_state_dict(OM.seeded_state_dict(oracle_cls_instance, seed))
+    policy = policy.cuda()
+    policy.net.freeze_encoders()
+    policy.net.set_eval_encoders()
+    return policy
+
+
+def test_smt_policy_cuda_matches_reference_golden():
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.ppo.policy import AudioNavSMTPolicy
+    g = load("smt_policy.npz")
+    p = _load(AudioNavSMTPolicy(spaces.savi_observation_space(), spaces.Discrete(4), **KW),
+              OM.AudioNavSMTPolicy(pretraining=False), int(g["seed"]))
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512, device="cuda")
+    with torch.no_grad():
+        v, a, lp, _, x, pr = p.act(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["em"]), d(g["em_masks"]),
+                                   deterministic=True)
+    assert torch.equal(a.cpu(), torch.from_numpy(g["act_action"]))
+    assert rel(v, g["act_value"]) < TOL and rel(lp, g["act_log_probs"]) < TOL and rel(pr, g["act_probs"]) < TOL
+    assert rel(x, g["act_em_feats"]) < TOL
+    v, lp, ent, _, x = p.evaluate_actions(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), d(g["em"]),
+                                          d(g["em_masks"]))
+    assert rel(v, g["eval_value"]) < TOL and rel(lp, g["eval_log_probs"]) < TOL and rel(x, g["eval_em_feats"]) < TOL
+    assert abs(float(ent) - float(g["eval_entropy"])) < 1e-4
+
+
+def test_option_policy_cuda_matches_reference_golden():
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.ppo.policy import AudioNavOptionPolicy
+    g = load("option_policy.npz")
+    p = _load(AudioNavOptionPolicy(spaces.savi_observation_space(), spaces.Discrete(4), **KW), OM.AudioNavOptionPolicy(),
+              int(g["seed"]))
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512, device="cuda")
+    args = (d(g["em"]), d(g["em_masks"]), d(g["query_state"]), d(g["last_query_info"]))
+    with torch.no_grad():
+        a = p.act_option(o, h, d(g["prev_actions"]), d(g["masks"]), *args, deterministic=True)
+    assert torch.equal(a[2].cpu(), torch.from_numpy(g["act_action"]))
+    for i, k in ((0, "act_value"), (1, "act_unct"), (3, "act_log_probs"), (5, "act_em_feats"), (6, "act_probs")):
+        assert rel(a[i], g[k]) < TOL, k
+    r = p.evaluate_actions_option(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), *args)
+    for i, k in ((0, "eval_value"), (1, "eval_unct"), (2, "eval_log_probs"), (5, "eval_em_feats"), (6, "eval_probs")):
+        assert rel(r[i], g[k]) < TOL, k
+    assert abs(float(r[3]) - float(g["eval_entropy"])) < 1e-4
+
+
+def test_dialog_policy_cuda_matches_reference_golden():
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.ppo.policy import AudioNavDialogPolicy
+    g = load("dialog_policy.npz")
+    layers = int(g["clip_layers"])
+    p = _load(AudioNavDialogPolicy(spaces.savi_observation_space(), spaces.Discrete(4), clip_layers=layers, **KW),
+              OM.AudioNavDialogPolicy(clip_layers=layers), int(g["seed"]))
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512, device="cuda")
+    args = (d(g["em"]), d(g["em_dialog"]), d(g["em_masks"]), d(g["dialog"]), d(g["agent_step"]).float())
+    with torch.no_grad():
+        a = p.act_dialog(o, h, d(g["prev_actions"]), d(g["masks"]), *args, deterministic=True, without_dialog=False)
+    assert torch.equal(a[1].cpu(), torch.from_numpy(g["act_action"]))
+    for i, k in ((0, "act_value"), (2, "act_log_probs"), (4, "act_em_feats"), (5, "act_em_dialog_feats"), (6, "act_probs")):
+        assert rel(a[i], g[k]) < TOL, k
+    r = p.evaluate_actions_dialog(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), *args, without_dialog=False)
+    assert r[0] is None
+    for i, k in ((1, "eval_log_probs"), (4, "eval_em_feats"), (5, "eval_em_dialog_feats"), (6, "eval_logits")):
+        assert rel(r[i], g[k]) < TOL, k
+    assert abs(float(r[2]) - float(g["eval_entropy"])) < 1e-4
+
+
+def test_external_memory_cuda_matches_reference_golden():
+    from avlen_b200.savi.models.rollout_storage import ExternalMemory
+    g = load("extmem.npz")
+    em = ExternalMemory(int(g["n_envs"]), int(g["total"]), int(g["capacity"]), int(g["dim"]), num_copies=3)
+    em.to(torch.device("cuda"))
+    for step in range(g["feats"].shape[0]):
+        em.insert(d(g["feats"][step]), d(g["not_done"][step]))
+        assert torch.equal(em.masks.cpu(), torch.from_numpy(g["masks_trace"][step])), step   # bit-exact
+    assert em.idx == int(g["final_idx"])
+    assert torch.equal(em.memory.cpu(), torch.from_numpy(g["final_memory"]))
+
+
+def test_gae_cuda_matches_reference_golden():
+    from avlen_b200 import ops
+    g = load("gae.npz")
+    for tag, use_gae in (("gae", True), ("mc", False)):
+        rewards, vp, masks = d(g[tag + "_rewards"]), d(g[tag + "_value_preds"]).clone(), d(g[tag + "_masks"])
+        returns = torch.zeros_like(vp)
+        T = rewards.shape[0]
+        ops.gae(rewards, vp, masks, d(g[tag + "_next_value"]), returns, T, use_gae, float(g["gamma"]), float(g["tau"]))
+        want = torch.from_numpy(g[tag + "_returns"])
+        hi = T if use_gae else T + 1  # (the GAE branch leaves returns[T] untouched)
+        assert torch.allclose(returns.cpu()[:hi], want[:hi], atol=1e-5, rtol=1e-5), tag
