@@ -68,7 +68,7 @@ def test_smt_policy_cuda_matches_reference_golden():
     v, lp, ent, _, x = p.evaluate_actions(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), d(g["em"]),
                                           d(g["em_masks"]))
     assert rel(v, g["eval_value"]) < TOL and rel(lp, g["eval_log_probs"]) < TOL and rel(x, g["eval_em_feats"]) < TOL
-    assert abs(float(ent) - float(g["eval_entropy"])) < 1e-4
+    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < 1e-4
 
 
 def test_option_policy_cuda_matches_reference_golden():
@@ -88,7 +88,7 @@ def test_option_policy_cuda_matches_reference_golden():
     r = p.evaluate_actions_option(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), *args)
     for i, k in ((0, "eval_value"), (1, "eval_unct"), (2, "eval_log_probs"), (5, "eval_em_feats"), (6, "eval_probs")):
         assert rel(r[i], g[k]) < TOL, k
-    assert abs(float(r[3]) - float(g["eval_entropy"])) < 1e-4
+    assert abs(float(r[3].detach()) - float(g["eval_entropy"])) < 1e-4
 
 
 def test_dialog_policy_cuda_matches_reference_golden():
@@ -110,7 +110,7 @@ def test_dialog_policy_cuda_matches_reference_golden():
     assert r[0] is None
     for i, k in ((1, "eval_log_probs"), (4, "eval_em_feats"), (5, "eval_em_dialog_feats"), (6, "eval_logits")):
         assert rel(r[i], g[k]) < TOL, k
-    assert abs(float(r[2]) - float(g["eval_entropy"])) < 1e-4
+    assert abs(float(r[2].detach()) - float(g["eval_entropy"])) < 1e-4
 
 
 def test_external_memory_cuda_matches_reference_golden():
