@@ -18,6 +18,8 @@ Cases (reference file:line of what is being recorded):
   gae.npz             RolloutStorage.compute_returns (use_gae True / False)         common/rollout_storage.py:114-132
   avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
   rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
+  ppo_update.npz      RolloutStorage.insert x4 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
+                      one epoch / one minibatch: the six returned numbers            :591-810; savi/ppo/ppo.py:90-95,:157-289
 """
 import os
 import sys
@@ -212,8 +214,79 @@ def rnn_seq():
          **{"w_" + k: v for k, v in ref.state_dict().items()})
 
 
+def ppo_update():
+    """One full reference ``PPO.update`` (savi/ppo/ppo.py:157-289, interactive pi_q: evaluate_actions_option, rl_masks,
+    uncertainty loss) over a reference RolloutStorage filled through its own 22-argument ``insert`` — one epoch, one
+    minibatch, so the returned losses are those of the un-updated weights and do not depend on the env permutation."""
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    rs = ref_shim.load("ss_baselines.savi.models.rollout_storage")
+    ppo = ref_shim.load("ss_baselines.savi.ppo.ppo")
+    sp = ref_shim.spaces()
+
+    class ActionSpace:
+        n = 4
+
+    T, N, em_size, cap = 3, 2, 8, 4
+    ref = pol.AudioNavOptionPolicy(ref_shim.observation_space(), sp.Discrete(4), **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavOptionPolicy(), 6))
+    ref.eval()
+    st = rs.RolloutStorage(T, N, ref_shim.observation_space(), ActionSpace(), 512, True, em_size, cap, em_size, cap, 3, 3,
+                           276, 276, 308, 256, num_recurrent_layers=1, max_dialog_len=77)
+    g = torch.Generator().manual_seed(109)
+    def small_obs():  # depth quantised to k / 256 so that it is stored exactly as uint8 (keeps the fixture small)
+        o = obs(N, g)
+        o["depth"] = torch.floor(o["depth"] * 256.0) / 256.0
+        return o
+
+    def pack(o, prefix):
+        out = {}
+        for k, v in o.items():
+            if k == "rgb":
+                out[prefix + k] = v.numpy().astype(np.uint8)
+            elif k == "depth":
+                out[prefix + "depth_u8"] = (v * 256.0).numpy().astype(np.uint8)
+            else:
+                out[prefix + k] = v.numpy()
+        return out
+
+    o0 = small_obs()
+    for k in st.observations:
+        if k in o0:
+            st.observations[k][0].copy_(o0[k])
+    rec = pack(o0, "obs0_")
+    names = ("actions", "actions_option", "log_probs", "values", "rewards", "masks", "emf", "emf_option", "emf_vln",
+             "rl_masks", "ucnt_gt", "query_state", "last_query_info")
+    for t in range(T):
+        o = small_obs()
+        d = dict(actions=torch.randint(0, 4, (N, 1), generator=g), actions_option=torch.randint(0, 2, (N, 1), generator=g),
+                 log_probs=-torch.rand(N, 1, generator=g), values=torch.randn(N, 1, generator=g),
+                 rewards=torch.randn(N, 1, generator=g), masks=(torch.rand(N, 1, generator=g) > 0.2).float(),
+                 emf=mem(1, N, 276, g, 272)[0], emf_option=mem(1, N, 308, g, 272)[0], emf_vln=mem(1, N, 276, g, 272)[0],
+                 rl_masks=(torch.rand(N, generator=g) > 0.3).float(), ucnt_gt=torch.randint(0, 2, (N,), generator=g).float(),
+                 query_state=torch.randn(N, 32, generator=g), last_query_info=torch.randn(N, 32, generator=g))
+        if t == 0:
+            d["rl_masks"][0] = 1.0  # (sum of rl_masks is the denominator of the action loss)
+        st.insert(o, torch.zeros(1, N, 512), d["actions"], d["actions_option"], d["log_probs"], d["values"], d["rewards"],
+                  d["masks"], d["masks"], d["emf"], d["emf_option"], d["emf_vln"], None, torch.zeros(N, 77),
+                  torch.zeros(N), torch.zeros(N), d["rl_masks"], d["ucnt_gt"], torch.zeros(N, 4), d["query_state"],
+                  d["last_query_info"], torch.zeros(N))
+        for k in names:
+            rec[f"s{t}_{k}"] = d[k].numpy()
+        rec.update(pack(o, f"s{t}_obs_"))
+    nv = torch.randn(N, 1, generator=g)
+    st.compute_returns(nv, True, 0.99, 0.95)
+    agent = ppo.PPO(actor_critic=ref, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.05,
+                    lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+    adv = agent.get_advantages(st).clone()
+    out = agent.update(st)
+    save("ppo_update.npz", seed=6, T=T, N=N, em_size=em_size, capacity=cap, next_value=nv, returns=st.returns,
+         advantages=adv, em_option_memory=st.em_option.memory[:, 0], em_masks=st.em_masks,
+         value_loss=out[0], action_loss=out[1], dist_entropy=out[2], values_debug=out[3], return_batch_debug=out[4],
+         unct_loss=out[5], **rec)
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq):
+    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, ppo_update):
         fn()

@@ -128,3 +128,77 @@ def test_rnn_seq_forward_oracle_matches_reference_golden():
     with torch.no_grad():
         o, h2 = enc(t(g["x"]), t(g["hidden"]), t(g["masks"]))
     assert close(o, g["out"]) and close(h2, g["hidden_out"])
+
+
+def _ppo_update_batch(g):
+    """Rebuilds, from the recorded per-step inputs, the single minibatch the reference's recurrent_generator hands to
+    PPO.update (rows t * N + env; rollout_storage.py:591-810) — with the oracle's ExternalMemory doing the inserts."""
+    T, N, em_size, cap = int(g["T"]), int(g["N"]), int(g["em_size"]), int(g["capacity"])
+
+    def obs_at(prefix):
+        o = {}
+        for k, v in g.items():
+            if k.startswith(prefix):
+                name = k[len(prefix):]
+                if name == "rgb":
+                    o["rgb"] = t(v).float()
+                elif name == "depth_u8":
+                    o["depth"] = t(v).float() / 256.0
+                else:
+                    o[name] = t(v)
+        return o
+
+    obs_steps = [obs_at("obs0_")] + [obs_at(f"s{s}_obs_") for s in range(T)]
+    em_option = R.ExternalMemory(N, em_size, cap, 308, num_copies=1)
+    em_goal = R.ExternalMemory(N, em_size, cap, 276, num_copies=1)
+    em_masks = [torch.zeros(N, em_size)]
+    for s in range(T):
+        em_option.insert(t(g[f"s{s}_emf_option"]), t(g[f"s{s}_masks"]))
+        em_goal.insert(t(g[f"s{s}_emf"]), t(g[f"s{s}_masks"]))
+        em_masks.append(em_goal.masks.clone())
+    em_masks = torch.stack(em_masks)
+    rows = lambda fn: torch.cat([fn(s) for s in range(T)], 0)  # noqa: E731
+    batch = dict(
+        obs={k: rows(lambda s: obs_steps[s][k]) for k in obs_steps[0]},
+        prev_actions=rows(lambda s: torch.zeros(N, 1, dtype=torch.long) if s == 0 else t(g[f"s{s - 1}_actions"])),
+        masks=rows(lambda s: torch.ones(N, 1) if s == 0 else t(g[f"s{s - 1}_masks"])),
+        actions_option=rows(lambda s: t(g[f"s{s}_actions_option"])),
+        value_preds=rows(lambda s: t(g[f"s{s}_values"])), old_lp=rows(lambda s: t(g[f"s{s}_log_probs"])),
+        returns=rows(lambda s: t(g["returns"])[s]), adv=rows(lambda s: t(g["advantages"])[s]),
+        rl_masks=rows(lambda s: t(g[f"s{s}_rl_masks"])), ucnt_gt=rows(lambda s: t(g[f"s{s}_ucnt_gt"])),
+        query_state=rows(lambda s: t(g[f"s{s}_query_state"])), last_query_info=rows(lambda s: t(g[f"s{s}_last_query_info"])),
+        em_masks=rows(lambda s: em_masks[s]),
+        memory=em_option.memory[:, 0].repeat(1, T, 1),  # (em_size, T * N, dim): row t * N + j reads env j
+    )
+    return batch, em_option, em_masks
+
+
+def test_ppo_update_oracle_matches_reference_golden():
+    """insert x T -> compute_returns -> get_advantages -> recurrent_generator -> evaluate_actions_option -> the PPO
+    losses of savi/ppo/ppo.py:219-262, all through the oracle, against the six numbers the reference's PPO.update
+    returned for the same rollout."""
+    g = load("ppo_update.npz")
+    T, N = int(g["T"]), int(g["N"])
+    b, em_option, em_masks = _ppo_update_batch(g)
+    assert torch.equal(em_option.memory[:, 0], t(g["em_option_memory"]))
+    assert torch.equal(em_masks, t(g["em_masks"]))
+    # returns / advantages (rows N, O)
+    rewards = torch.stack([t(g[f"s{s}_rewards"]) for s in range(T)])
+    vp = torch.cat([torch.stack([t(g[f"s{s}_values"]) for s in range(T)]), torch.zeros(1, N, 1)])
+    masks = torch.cat([torch.ones(1, N, 1), torch.stack([t(g[f"s{s}_masks"]) for s in range(T)])])
+    returns = R.compute_returns(rewards, vp, masks, t(g["next_value"]), T, True, 0.99, 0.95)
+    assert torch.allclose(returns[:T], t(g["returns"])[:T], atol=1e-6)
+    assert torch.allclose(R.get_advantages(returns, vp, False), t(g["advantages"]), atol=1e-6)
+    pol = OM.AudioNavOptionPolicy()
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    with torch.no_grad():
+        r = pol.evaluate_actions_option(b["obs"], torch.zeros(1, T * N, 512), b["prev_actions"], b["masks"],
+                                        b["actions_option"], b["memory"], b["em_masks"], b["query_state"],
+                                        b["last_query_info"])
+    values, unct, probs = r[0], r[1], r[6]
+    out = R.ppo_loss(torch.log(probs), b["actions_option"], b["old_lp"], b["adv"], values, b["value_preds"], b["returns"],
+                     b["rl_masks"], unct, b["ucnt_gt"], 0.2, 0.5, 0.05, 0.5)
+    for k, ref_k in (("value_loss", "value_loss"), ("action_loss", "action_loss"), ("entropy", "dist_entropy"),
+                     ("unct_loss", "unct_loss"), ("values_mean", "values_debug"), ("returns_mean", "return_batch_debug")):
+        assert abs(out[k] - float(g[ref_k])) <= 2e-5 * max(1.0, abs(float(g[ref_k]))), (k, out[k], float(g[ref_k]))

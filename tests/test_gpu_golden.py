@@ -136,3 +136,58 @@ def test_gae_cuda_matches_reference_golden():
         want = torch.from_numpy(g[tag + "_returns"])
         hi = T if use_gae else T + 1  # (the GAE branch leaves returns[T] untouched)
         assert torch.allclose(returns.cpu()[:hi], want[:hi], atol=1e-5, rtol=1e-5), tag
+
+
+def test_ppo_update_cuda_matches_reference_golden():
+    """The recorded rollout goes through the product's RolloutStorage.insert / compute_returns / recurrent_generator and
+    PPO.update (option head: rl_masks, uncertainty loss); the six returned numbers are the reference's
+    (savi/ppo/ppo.py:157-289; one epoch, one minibatch: losses of the un-updated weights)."""
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.models.rollout_storage import RolloutStorage
+    from avlen_b200.savi.ppo.policy import AudioNavOptionPolicy
+    from avlen_b200.savi.ppo.ppo import PPO
+    g = load("ppo_update.npz")
+    T, N, em_size, cap = int(g["T"]), int(g["N"]), int(g["em_size"]), int(g["capacity"])
+    p = _load(AudioNavOptionPolicy(spaces.savi_observation_space(), spaces.Discrete(4), **KW), OM.AudioNavOptionPolicy(),
+              int(g["seed"]))
+
+    def obs_at(prefix):
+        o = {}
+        for k, v in g.items():
+            if k.startswith(prefix):
+                name = k[len(prefix):]
+                if name == "rgb":
+                    o["rgb"] = d(v).float()
+                elif name == "depth_u8":
+                    o["depth"] = d(v).float() / 256.0
+                else:
+                    o[name] = d(v)
+        return o
+
+    obs_space = spaces.savi_observation_space()
+    st = RolloutStorage(T, N, obs_space, spaces.Discrete(4), 512, True, em_size, cap, em_size, cap, 3, 3, 276, 276, 308, 256,
+                        num_recurrent_layers=1, max_dialog_len=77)
+    st.to(torch.device("cuda"))
+    o0 = obs_at("obs0_")
+    for k in st.observations:
+        if k in o0:
+            st.observations[k][0].copy_(o0[k])
+    z = lambda *shape: torch.zeros(*shape, device="cuda")  # noqa: E731
+    for s in range(T):
+        st.insert(obs_at(f"s{s}_obs_"), z(1, N, 512), d(g[f"s{s}_actions"]), d(g[f"s{s}_actions_option"]),
+                  d(g[f"s{s}_log_probs"]), d(g[f"s{s}_values"]), d(g[f"s{s}_rewards"]), d(g[f"s{s}_masks"]),
+                  d(g[f"s{s}_masks"]), d(g[f"s{s}_emf"]), d(g[f"s{s}_emf_option"]), d(g[f"s{s}_emf_vln"]), None,
+                  z(N, 77), z(N), z(N), d(g[f"s{s}_rl_masks"]), d(g[f"s{s}_ucnt_gt"]), z(N, 4), d(g[f"s{s}_query_state"]),
+                  d(g[f"s{s}_last_query_info"]), z(N))
+    assert torch.equal(st.em_masks.cpu(), torch.from_numpy(g["em_masks"]))           # bit-exact mask snapshots
+    assert torch.equal(st.em_option.memory.cpu(), torch.from_numpy(g["em_option_memory"]))
+    st.compute_returns(d(g["next_value"]), True, 0.99, 0.95)
+    assert torch.allclose(st.returns.cpu()[:T], torch.from_numpy(g["returns"])[:T], atol=1e-5)
+    agent = PPO(p, 0.2, 1, 1, 0.5, 0.05, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False,
+                policy_head="option")
+    adv = agent.get_advantages(st)
+    assert torch.allclose(adv.cpu(), torch.from_numpy(g["advantages"]), atol=1e-5)
+    out = agent.update(st)
+    for got, k in zip(out, ("value_loss", "action_loss", "dist_entropy", "values_debug", "return_batch_debug", "unct_loss")):
+        want = float(g[k])
+        assert abs(float(got) - want) <= TOL * max(1.0, abs(want)), (k, float(got), want)

@@ -1,6 +1,7 @@
 """Pins oracle/* against the UNMODIFIED reference modules (loaded through oracle/ref_shim.py).
 Only runs where /root/reference exists (the authoring container); elsewhere the committed golden
-vectors (tests/golden) carry the same pin."""
+vectors (tests/golden/*.npz, written by tests/golden/make_golden.py from the same unmodified reference) carry the pin:
+tests/test_golden.py for the oracle, tests/test_gpu_golden.py for the CUDA path."""
 import numpy as np
 import pytest
 import torch
