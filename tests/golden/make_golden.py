@@ -18,7 +18,8 @@ Cases (reference file:line of what is being recorded):
   gae.npz             RolloutStorage.compute_returns (use_gae True / False)         common/rollout_storage.py:114-132
   avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
   rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
-  ppo_update.npz      RolloutStorage.insert x4 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
+  belief_update.npz   BeliefPredictor.update x5 (silent frames, episode ends)      savi/models/belief_predictor.py:126-230
+  ppo_update.npz      RolloutStorage.insert x3 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
                       one epoch / one minibatch: the six returned numbers            :591-810; savi/ppo/ppo.py:90-95,:157-289
 """
 import os
@@ -214,6 +215,56 @@ def rnn_seq():
          **{"w_" + k: v for k, v in ref.state_dict().items()})
 
 
+def belief_update():
+    """The reference's BeliefPredictor.update / cnn_forward / base_to_odom / odom_to_base (belief_predictor.py:126-230),
+    unmodified, over 5 steps with silent spectrograms and episode ends.  Its constructor downloads torchvision weights
+    and reads a checkpoint file, so the object is assembled around it: same attributes, the reference's own
+    custom_resnet18 as location predictor, torchvision's resnet18 (2-channel stem, 21 classes) as classifier."""
+    import types
+    import torchvision
+    bp_mod = ref_shim.load("ss_baselines.savi.models.belief_predictor")
+    n, steps = 4, 5
+    bp = bp_mod.BeliefPredictor.__new__(bp_mod.BeliefPredictor)
+    torch.nn.Module.__init__(bp)
+    bp.config = types.SimpleNamespace(use_label_belief=True, use_location_belief=True, online_training=True,
+                                      weighting_factor=0.5, current_pred_only=False)
+    bp.device = torch.device("cpu")
+    bp.predict_label = bp.predict_location = True
+    bp.has_distractor_sound = False
+    bp.predictor = bp_mod.custom_resnet18(num_input_channels=2)
+    bp.predictor.fc = torch.nn.Linear(4608, 2)
+    bp.classifier = torchvision.models.resnet18()
+    bp.classifier.conv1 = torch.nn.Conv2d(2, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    bp.classifier.fc = torch.nn.Linear(512, 21)
+    bp.last_pointgoal, bp.last_label = [None] * n, [None] * n
+    sd_c = OM.seeded_state_dict(bp.classifier, 21)
+    for k in sd_c:
+        if k.endswith("running_var"):
+            sd_c[k] = sd_c[k].abs() + 0.5
+    bp.classifier.load_state_dict(sd_c)
+    bp.predictor.load_state_dict(OM.seeded_state_dict(OM.CustomResNet18(2, 2, fc_in=4608), 22))
+    bp.set_eval_encoders()
+    g = torch.Generator().manual_seed(110)
+    rec = {}
+    silent = [(), (1,), (0, 2), (), (3,)]
+    done = [None, (2,), (), (0, 3), (1,)]
+    for t in range(steps):
+        o = obs(n, g)
+        o["pose"][:, 3] = float(t)
+        for i in silent[t]:
+            o["spectrogram"][i] = 0
+        dones = None if done[t] is None else [i in done[t] for i in range(n)]
+        o["location_belief"].zero_()
+        o["category_belief"].zero_()
+        rec[f"s{t}_spectrogram"], rec[f"s{t}_pose"] = o["spectrogram"].numpy().copy(), o["pose"].numpy().copy()
+        rec[f"s{t}_dones"] = np.asarray([False] * n if dones is None else dones)
+        rec[f"s{t}_has_dones"] = dones is not None
+        bp.update(o, dones)
+        rec[f"s{t}_location_belief"] = o["location_belief"].numpy().copy()
+        rec[f"s{t}_category_belief"] = o["category_belief"].numpy().copy()
+    save("belief_update.npz", n=n, steps=steps, seed_classifier=21, seed_predictor=22, **rec)
+
+
 def ppo_update():
     """One full reference ``PPO.update`` (savi/ppo/ppo.py:157-289, interactive pi_q: evaluate_actions_option, rl_masks,
     uncertainty loss) over a reference RolloutStorage filled through its own 22-argument ``insert`` — one epoch, one
@@ -288,5 +339,5 @@ def ppo_update():
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, ppo_update):
+    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update):
         fn()

@@ -202,3 +202,37 @@ def test_ppo_update_oracle_matches_reference_golden():
     for k, ref_k in (("value_loss", "value_loss"), ("action_loss", "action_loss"), ("entropy", "dist_entropy"),
                      ("unct_loss", "unct_loss"), ("values_mean", "values_debug"), ("returns_mean", "return_batch_debug")):
         assert abs(out[k] - float(g[ref_k])) <= 2e-5 * max(1.0, abs(float(g[ref_k]))), (k, out[k], float(g[ref_k]))
+
+
+def _belief_nets(g):
+    import torchvision
+    cls = torchvision.models.resnet18()
+    cls.conv1 = torch.nn.Conv2d(2, 64, 7, 2, 3, bias=False)
+    cls.fc = torch.nn.Linear(512, 21)
+    pred = OM.CustomResNet18(2, 2, fc_in=4608)
+    sd_c, sd_p = OM.seeded_state_dict(cls, int(g["seed_classifier"])), OM.seeded_state_dict(pred, int(g["seed_predictor"]))
+    for k in sd_c:
+        if k.endswith("running_var"):
+            sd_c[k] = sd_c[k].abs() + 0.5
+    cls.load_state_dict(sd_c)
+    pred.load_state_dict(sd_p)
+    return cls.eval(), pred.eval(), sd_c, sd_p
+
+
+def test_belief_update_oracle_matches_reference_golden():
+    """Row M: the oracle's belief filter (EMA, odom <-> base transforms, silent frames, episode ends) and the two
+    networks against what the reference's own BeliefPredictor.update wrote into the observations."""
+    g = load("belief_update.npz")
+    n = int(g["n"])
+    cls, pred, _, _ = _belief_nets(g)
+    st = R.BeliefState(n)
+    for s in range(int(g["steps"])):
+        spec, pose = g[f"s{s}_spectrogram"], g[f"s{s}_pose"]
+        with torch.no_grad():
+            sp = t(spec).permute(0, 3, 1, 2)
+            pg, lab = pred(sp).numpy(), cls(sp)[:, :21].numpy()
+        dones = list(g[f"s{s}_dones"]) if bool(g[f"s{s}_has_dones"]) else None
+        loc, cat = st.update(spec, pose, dones, pg, lab)
+        want_l, want_c = g[f"s{s}_location_belief"], g[f"s{s}_category_belief"]
+        assert np.abs(loc - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max()), s
+        assert np.abs(cat - want_c).max() <= 1e-4 * max(1.0, np.abs(want_c).max()), s

@@ -191,3 +191,27 @@ def test_ppo_update_cuda_matches_reference_golden():
     for got, k in zip(out, ("value_loss", "action_loss", "dist_entropy", "values_debug", "return_batch_debug", "unct_loss")):
         want = float(g[k])
         assert abs(float(got) - want) <= TOL * max(1.0, abs(want)), (k, float(got), want)
+
+
+def test_belief_update_cuda_matches_reference_golden():
+    """Row M: BeliefPredictor.update on the GPU (both networks + the batched belief filter kernel) against the
+    observations the reference's own BeliefPredictor.update produced over 5 steps with silent frames / episode ends."""
+    import types
+    from avlen_b200.savi.models.belief_predictor import BeliefPredictor
+    from tests.test_golden import _belief_nets
+    g = load("belief_update.npz")
+    n = int(g["n"])
+    _, _, sd_c, sd_p = _belief_nets(g)
+    cfg = types.SimpleNamespace(use_label_belief=True, use_location_belief=True, online_training=True,
+                                weighting_factor=0.5, current_pred_only=False)
+    bp = BeliefPredictor(cfg, "cuda", None, None, None, n)
+    bp.classifier.load_state_dict(sd_c)
+    bp.predictor.load_state_dict(sd_p)
+    bp = bp.cuda()
+    for s in range(int(g["steps"])):
+        o = {"spectrogram": d(g[f"s{s}_spectrogram"]), "pose": d(g[f"s{s}_pose"]),
+             "location_belief": torch.zeros(n, 2, device="cuda"), "category_belief": torch.zeros(n, 21, device="cuda")}
+        dones = torch.from_numpy(g[f"s{s}_dones"]) if bool(g[f"s{s}_has_dones"]) else None
+        bp.update(o, dones)
+        assert rel(o["location_belief"], g[f"s{s}_location_belief"]) < TOL, s
+        assert rel(o["category_belief"], g[f"s{s}_category_belief"]) < TOL, s
