@@ -19,6 +19,8 @@ Cases (reference file:line of what is being recorded):
   avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
   rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
   belief_update.npz   BeliefPredictor.update x5 (silent frames, episode ends)      savi/models/belief_predictor.py:126-230
+  dialog_update.npz   RolloutStorage.insert x3 + dialog_batching + PPO.update_dialog  savi/models/rollout_storage.py:414-588;
+                      (pi_l, weighted CE on the o_mask rows)                         savi/ppo/ppo.py:99-154
   ppo_update.npz      RolloutStorage.insert x3 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
                       one epoch / one minibatch: the six returned numbers            :591-810; savi/ppo/ppo.py:90-95,:157-289
 """
@@ -336,8 +338,83 @@ def ppo_update():
          unct_loss=out[5], **rec)
 
 
+def dialog_update():
+    """One reference ``PPO.update_dialog`` (savi/ppo/ppo.py:99-154) over a reference RolloutStorage with the dialog
+    memories (use_state_memory), read back through its ``dialog_batching`` (rollout_storage.py:414-588): the weighted
+    cross-entropy of pi_l's logits against the oracle actions on the rows with o_mask != 0."""
+    os.environ["AVLEN_SHIM_CLIP_LAYERS"] = "2"
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    rs = ref_shim.load("ss_baselines.savi.models.rollout_storage")
+    ppo = ref_shim.load("ss_baselines.savi.ppo.ppo")
+    sp = ref_shim.spaces()
+
+    class ActionSpace:
+        n = 4
+
+    T, N = 3, 2
+    ref = pol.AudioNavDialogPolicy(ref_shim.observation_space(), sp.Discrete(4), **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavDialogPolicy(clip_layers=2), 7))
+    ref.eval()
+    st = rs.RolloutStorage(T, N, ref_shim.observation_space(), ActionSpace(), 512, True, 8, 4, 8, 4, 3, 3, 276, 276, 308, 256,
+                           num_recurrent_layers=1, max_dialog_len=77, use_state_memory=True)
+    g = torch.Generator().manual_seed(111)
+
+    def small_obs():
+        o = obs(N, g)
+        o["depth"] = torch.floor(o["depth"] * 256.0) / 256.0
+        return o
+
+    def pack(o, prefix):
+        out = {}
+        for k, v in o.items():
+            if k == "rgb":
+                out[prefix + k] = v.numpy().astype(np.uint8)
+            elif k == "depth":
+                out[prefix + "depth_u8"] = (v * 256.0).numpy().astype(np.uint8)
+            else:
+                out[prefix + k] = v.numpy()
+        return out
+
+    o0 = small_obs()
+    for k in st.observations:
+        if k in o0:
+            st.observations[k][0].copy_(o0[k])
+    rec = pack(o0, "obs0_")
+    for t in range(T):
+        o = small_obs()
+        dialog = torch.zeros(N, 77, dtype=torch.long)
+        for b in range(N):
+            k = int(torch.randint(0, 12, (1,), generator=g))
+            if k >= 3:
+                dialog[b, 0] = 49406
+                dialog[b, 1:1 + k] = torch.randint(1, 49000, (k,), generator=g)
+                dialog[b, 1 + k] = 49407
+        d = dict(actions=torch.randint(0, 4, (N, 1), generator=g), log_probs=-torch.rand(N, 1, generator=g),
+                 values=torch.randn(N, 1, generator=g), rewards=torch.randn(N, 1, generator=g),
+                 masks=(torch.rand(N, 1, generator=g) > 0.2).float(), emf=mem(1, N, 276, g, 272)[0],
+                 emf_option=mem(1, N, 308, g, 272)[0], emf_vln=mem(1, N, 276, g, 272)[0],
+                 emf_dialog=torch.randn(N, 256, generator=g), all_dialog=dialog,
+                 o_action=torch.randint(1, 4, (N,), generator=g).float(), o_mask=(torch.rand(N, generator=g) > 0.35).float(),
+                 agent_step=torch.full((N,), float(t)))
+        if t == 0:
+            d["o_mask"][0] = 1.0
+        st.insert(o, torch.zeros(1, N, 512), d["actions"], None, d["log_probs"], d["values"], d["rewards"], d["masks"],
+                  d["masks"], d["emf"], d["emf_option"], d["emf_vln"], d["emf_dialog"], d["all_dialog"], d["o_action"],
+                  d["o_mask"], torch.zeros(N), torch.zeros(N), torch.zeros(N, 4), torch.zeros(N, 32), torch.zeros(N, 32),
+                  d["agent_step"])
+        for k, v in d.items():
+            rec[f"s{t}_{k}"] = v.numpy()
+        rec.update(pack(o, f"s{t}_obs_"))
+    agent = ppo.PPO(actor_critic=ref, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.05,
+                    lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+    loss = agent.update_dialog(st)
+    save("dialog_update.npz", seed=7, clip_layers=2, T=T, N=N, dialog_loss=loss.detach(),
+         em_vln_memory=st.em_vln.memory[:, 0], em_vln_dialog_memory=st.em_vln_dialog.memory[:, 0],
+         em_vln_masks=st.em_vln_masks, **rec)
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update):
+    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
         fn()

@@ -236,3 +236,51 @@ def test_belief_update_oracle_matches_reference_golden():
         want_l, want_c = g[f"s{s}_location_belief"], g[f"s{s}_category_belief"]
         assert np.abs(loc - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max()), s
         assert np.abs(cat - want_c).max() <= 1e-4 * max(1.0, np.abs(want_c).max()), s
+
+
+def _obs_from(g, prefix):
+    o = {}
+    for k, v in g.items():
+        if k.startswith(prefix):
+            name = k[len(prefix):]
+            if name == "rgb":
+                o["rgb"] = t(v).float()
+            elif name == "depth_u8":
+                o["depth"] = t(v).float() / 256.0
+            else:
+                o[name] = t(v)
+    return o
+
+
+def test_update_dialog_oracle_matches_reference_golden():
+    """Row R: insert x T (dialog memories) -> dialog_batching -> evaluate_actions_dialog -> weighted cross-entropy on
+    the o_mask rows, through the oracle, against the loss the reference's PPO.update_dialog returned."""
+    g = load("dialog_update.npz")
+    T, N = int(g["T"]), int(g["N"])
+    em_vln = R.ExternalMemory(N, 3, 3, 276, num_copies=1)
+    em_dlg = R.ExternalMemory(N, 3, 3, 256, num_copies=1)
+    vln_masks = [torch.zeros(N, 3)]
+    for s in range(T):
+        em_vln.insert(t(g[f"s{s}_emf_vln"]), t(g[f"s{s}_masks"]))
+        em_dlg.insert(t(g[f"s{s}_emf_dialog"]), t(g[f"s{s}_masks"]))
+        vln_masks.append(em_vln.masks.clone())
+    assert torch.equal(em_vln.memory[:, 0], t(g["em_vln_memory"])) and torch.equal(em_dlg.memory[:, 0], t(g["em_vln_dialog_memory"]))
+    assert torch.equal(torch.stack(vln_masks), t(g["em_vln_masks"]))
+    obs_steps = [_obs_from(g, "obs0_")] + [_obs_from(g, f"s{s}_obs_") for s in range(T)]
+    rows = lambda fn: torch.cat([fn(s) for s in range(T)], 0)  # noqa: E731
+    pol = OM.AudioNavDialogPolicy(clip_layers=int(g["clip_layers"]))
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    with torch.no_grad():
+        r = pol.evaluate_actions_dialog(
+            {k: rows(lambda s: obs_steps[s][k]) for k in obs_steps[0]}, torch.zeros(1, T * N, 512),
+            rows(lambda s: torch.zeros(N, 1, dtype=torch.long) if s == 0 else t(g[f"s{s - 1}_actions"])),
+            rows(lambda s: torch.ones(N, 1) if s == 0 else t(g[f"s{s - 1}_masks"])),
+            rows(lambda s: t(g[f"s{s}_actions"])), em_vln.memory[:, 0].repeat(1, T, 1), em_dlg.memory[:, 0].repeat(1, T, 1),
+            rows(lambda s: vln_masks[s]), rows(lambda s: t(g[f"s{s}_all_dialog"])), rows(lambda s: t(g[f"s{s}_agent_step"])))
+    logits = r[6]
+    o_mask = rows(lambda s: t(g[f"s{s}_o_mask"]))
+    o_act = rows(lambda s: t(g[f"s{s}_o_action"])).long()
+    sel = torch.nonzero(o_mask).squeeze(-1)
+    loss = torch.nn.functional.cross_entropy(logits[sel], o_act[sel], weight=torch.tensor([0, .33, .33, .33]))
+    assert abs(float(loss) - float(g["dialog_loss"])) <= 2e-5 * max(1.0, abs(float(g["dialog_loss"])))

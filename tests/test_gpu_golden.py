@@ -215,3 +215,52 @@ def test_belief_update_cuda_matches_reference_golden():
         bp.update(o, dones)
         assert rel(o["location_belief"], g[f"s{s}_location_belief"]) < TOL, s
         assert rel(o["category_belief"], g[f"s{s}_category_belief"]) < TOL, s
+
+
+def test_update_dialog_cuda_matches_reference_golden():
+    """Row R: the recorded dialog rollout through the product's RolloutStorage.insert (dialog memories) /
+    dialog_batching / PPO.update_dialog against the loss the reference's own update_dialog returned
+    (savi/ppo/ppo.py:99-154)."""
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.models.rollout_storage import RolloutStorage
+    from avlen_b200.savi.ppo.policy import AudioNavDialogPolicy
+    from avlen_b200.savi.ppo.ppo import PPO
+    g = load("dialog_update.npz")
+    T, N, layers = int(g["T"]), int(g["N"]), int(g["clip_layers"])
+    p = _load(AudioNavDialogPolicy(spaces.savi_observation_space(), spaces.Discrete(4), clip_layers=layers, **KW),
+              OM.AudioNavDialogPolicy(clip_layers=layers), int(g["seed"]))
+
+    def obs_at(prefix):
+        o = {}
+        for k, v in g.items():
+            if k.startswith(prefix):
+                name = k[len(prefix):]
+                if name == "rgb":
+                    o["rgb"] = d(v).float()
+                elif name == "depth_u8":
+                    o["depth"] = d(v).float() / 256.0
+                else:
+                    o[name] = d(v)
+        return o
+
+    st = RolloutStorage(T, N, spaces.savi_observation_space(), spaces.Discrete(4), 512, True, 8, 4, 8, 4, 3, 3, 276, 276, 308,
+                        256, num_recurrent_layers=1, max_dialog_len=77, use_state_memory=True)
+    st.to(torch.device("cuda"))
+    o0 = obs_at("obs0_")
+    for k in st.observations:
+        if k in o0:
+            st.observations[k][0].copy_(o0[k])
+    z = lambda *shape: torch.zeros(*shape, device="cuda")  # noqa: E731
+    for s in range(T):
+        st.insert(obs_at(f"s{s}_obs_"), z(1, N, 512), d(g[f"s{s}_actions"]), None, d(g[f"s{s}_log_probs"]),
+                  d(g[f"s{s}_values"]), d(g[f"s{s}_rewards"]), d(g[f"s{s}_masks"]), d(g[f"s{s}_masks"]), d(g[f"s{s}_emf"]),
+                  d(g[f"s{s}_emf_option"]), d(g[f"s{s}_emf_vln"]), d(g[f"s{s}_emf_dialog"]), d(g[f"s{s}_all_dialog"]),
+                  d(g[f"s{s}_o_action"]), d(g[f"s{s}_o_mask"]), z(N), z(N), z(N, 4), z(N, 32), z(N, 32),
+                  d(g[f"s{s}_agent_step"]))
+    assert torch.equal(st.em_vln_masks.cpu(), torch.from_numpy(g["em_vln_masks"]))
+    assert torch.equal(st.em_vln.memory.cpu(), torch.from_numpy(g["em_vln_memory"]))
+    assert torch.equal(st.em_vln_dialog.memory.cpu(), torch.from_numpy(g["em_vln_dialog_memory"]))
+    agent = PPO(p, 0.2, 1, 1, 0.5, 0.05, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
+    loss = agent.update_dialog(st)
+    want = float(g["dialog_loss"])
+    assert abs(float(loss) - want) <= 2e-3 * max(1.0, abs(want)), (float(loss), want)
