@@ -264,3 +264,20 @@ def test_update_dialog_cuda_matches_reference_golden():
     loss = agent.update_dialog(st)
     want = float(g["dialog_loss"])
     assert abs(float(loss) - want) <= 2e-3 * max(1.0, abs(want)), (float(loss), want)
+
+
+def test_av_nav_net_cuda_matches_reference_golden():
+    """BASELINE config[0]: the av_nav net (VisualCNN + AudioCNN + GRU-512 with an episode-start mask) and the critic
+    against the unmodified reference's ``AudioNavBaselineNet`` / ``CriticHead`` outputs (av_nav/ppo/policy.py:85-160)."""
+    from avlen_b200.av_nav.ppo.policy import AudioNavBaselinePolicy
+    from avlen_b200.common import spaces
+    g = load("avnav_net.npz")
+    p = AudioNavBaselinePolicy(spaces.savi_observation_space(), spaces.Discrete(4), "spectrogram", 512)
+    p.load_state_dict(OM.seeded_state_dict(OM.AudioNavBaselinePolicy(), int(g["seed"])))
+    p = p.cuda()
+    o = obs_of(g)
+    n = o["pose"].shape[0]
+    with torch.no_grad():
+        feats, h2 = p.net(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
+        value = p.get_value(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
+    assert rel(feats, g["features"]) < TOL and rel(h2, g["hidden_out"]) < TOL and rel(value, g["value"]) < TOL
