@@ -10,6 +10,7 @@ from a numpy PCG64 seed (oracle.models_torch.seeded_state_dict), which is platfo
 
 Cases (reference file:line of what is being recorded):
   smt_policy.npz      AudioNavSMTPolicy.evaluate_actions / act(deterministic)      savi/ppo/policy.py:70-96,:183-205
+  smt_policy_distractor.npz  the same with use_category_input=True (memory_dim 297)  savi/ppo/policy.py:546,:667
   option_policy.npz   AudioNavOptionPolicy.evaluate_actions_option / act_option     savi/ppo/policy.py:98-127,:207-235
   dialog_policy.npz   AudioNavDialogPolicy.evaluate_actions_dialog / act_dialog     savi/ppo/policy.py:130-162,:238-276
                       (the third-party CLIP package is absent: the shim gives the reference policy the oracle's
@@ -88,6 +89,31 @@ def smt_policy():
         v, lp, ent, _, x = ref.evaluate_actions(o, h, pa, mk, act, em, emm)
         av, aa, alp, _, ax, apr = ref.act(o, h, pa, mk, em, emm, deterministic=True)
     save("smt_policy.npz", seed=5, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
+         eval_value=v, eval_log_probs=lp, eval_entropy=ent, eval_em_feats=x,
+         act_value=av, act_action=aa, act_log_probs=alp, act_em_feats=ax, act_probs=apr)
+
+
+def smt_policy_distractor():
+    """BASELINE configs 4 / 5 (semantic_audionav_distractor): pi_g with ``use_category_input=True`` — the one-hot goal
+    category joins the feature row (memory_dim 297, pose columns 293:297, fusion input 309; policy.py:546,:667)."""
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    ref = pol.AudioNavSMTPolicy(ref_shim.observation_space(), sp.Discrete(4), use_category_input=True, **policy_kwargs())
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=False, use_category_input=True), 15))
+    ref.eval()
+    g = torch.Generator().manual_seed(112)
+    n, M = 2, 16
+    o = obs(n, g)
+    o["category"] = torch.zeros(n, 21)
+    o["category"][torch.arange(n), torch.randint(0, 21, (n,), generator=g)] = 1.0
+    em = mem(M, n, 297, g, 293)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    act = torch.randint(0, 4, (n, 1), generator=g)
+    with torch.no_grad():
+        v, lp, ent, _, x = ref.evaluate_actions(o, h, pa, mk, act, em, emm)
+        av, aa, alp, _, ax, apr = ref.act(o, h, pa, mk, em, emm, deterministic=True)
+    save("smt_policy_distractor.npz", seed=15, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
          eval_value=v, eval_log_probs=lp, eval_entropy=ent, eval_em_feats=x,
          act_value=av, act_action=aa, act_log_probs=alp, act_em_feats=ax, act_probs=apr)
 
@@ -416,5 +442,5 @@ def dialog_update():
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
+    for fn in (smt_policy, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
         fn()
