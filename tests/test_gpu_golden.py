@@ -281,3 +281,25 @@ def test_av_nav_net_cuda_matches_reference_golden():
         feats, h2 = p.net(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
         value = p.get_value(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
     assert rel(feats, g["features"]) < TOL and rel(h2, g["hidden_out"]) < TOL and rel(value, g["value"]) < TOL
+
+
+def test_smt_policy_distractor_cuda_matches_reference_golden():
+    """BASELINE configs 4 / 5 (distractor sound): pi_g with ``use_category_input=True`` (memory_dim 297, pose columns
+    293:297) against the unmodified reference.  Measured on B200: actions equal, outputs within 3e-5 of the range."""
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.ppo.policy import AudioNavSMTPolicy
+    g = load("smt_policy_distractor.npz")
+    p = _load(AudioNavSMTPolicy(spaces.savi_observation_space(), spaces.Discrete(4), use_category_input=True, **KW),
+              OM.AudioNavSMTPolicy(pretraining=False, use_category_input=True), int(g["seed"]))
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512, device="cuda")
+    with torch.no_grad():
+        v, a, lp, _, x, pr = p.act(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["em"]), d(g["em_masks"]),
+                                   deterministic=True)
+    assert torch.equal(a.cpu(), torch.from_numpy(g["act_action"]))
+    assert rel(v, g["act_value"]) < TOL and rel(lp, g["act_log_probs"]) < TOL and rel(pr, g["act_probs"]) < TOL
+    assert rel(x, g["act_em_feats"]) < TOL and x.shape[1] == 297
+    v, lp, ent, _, x = p.evaluate_actions(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), d(g["em"]),
+                                          d(g["em_masks"]))
+    assert rel(v, g["eval_value"]) < TOL and rel(lp, g["eval_log_probs"]) < TOL and rel(x, g["eval_em_feats"]) < TOL
+    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < 1e-4
