@@ -52,7 +52,7 @@ struct TcArgs {
                      // (1, 1, splits); partial tiles meet in the owners' shared memory over DSMEM and are summed in
                      // slice order (deterministic), epilogue applied in the same kernel — no zero / epilogue launches
   int splits_nz;     // slices that own at least one k-tile (the others only take part in the reduction)
-  unsigned red_off;  // byte offset of the reduction buffer in dynamic shared memory (behind the operand ring)
+  unsigned red_off;  // byte offset of the reduction buffer in dynamic shared memory (0: it aliases the operand ring)
 };
 
 __device__ __forceinline__ void cluster_arrive_wait() {
