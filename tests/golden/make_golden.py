@@ -10,6 +10,7 @@ from a numpy PCG64 seed (oracle.models_torch.seeded_state_dict), which is platfo
 
 Cases (reference file:line of what is being recorded):
   smt_policy.npz      AudioNavSMTPolicy.evaluate_actions / act(deterministic)      savi/ppo/policy.py:70-96,:183-205
+  smt_policy_pretraining.npz the same with pretraining=True (memory masked out)       savi/models/smt_state_encoder.py:126-129
   smt_policy_distractor.npz  the same with use_category_input=True (memory_dim 297)  savi/ppo/policy.py:546,:667
   option_policy.npz   AudioNavOptionPolicy.evaluate_actions_option / act_option     savi/ppo/policy.py:98-127,:207-235
   dialog_policy.npz   AudioNavDialogPolicy.evaluate_actions_dialog / act_dialog     savi/ppo/policy.py:130-162,:238-276
@@ -89,6 +90,31 @@ def smt_policy():
         v, lp, ent, _, x = ref.evaluate_actions(o, h, pa, mk, act, em, emm)
         av, aa, alp, _, ax, apr = ref.act(o, h, pa, mk, em, emm, deterministic=True)
     save("smt_policy.npz", seed=5, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
+         eval_value=v, eval_log_probs=lp, eval_entropy=ent, eval_em_feats=x,
+         act_value=av, act_action=aa, act_log_probs=alp, act_em_feats=ax, act_probs=apr)
+
+
+def smt_policy_pretraining():
+    """pi_g with ``pretraining=True`` (savi_pretraining.yaml): only the current observation is attendable
+    (smt_state_encoder.py:126-129), whatever the memory masks say."""
+    pol = ref_shim.load("ss_baselines.savi.ppo.policy")
+    sp = ref_shim.spaces()
+    kw = policy_kwargs()
+    kw["pretraining"] = True
+    ref = pol.AudioNavSMTPolicy(ref_shim.observation_space(), sp.Discrete(4), **kw)
+    ref.load_state_dict(OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=True), 5))
+    ref.eval()
+    g = torch.Generator().manual_seed(113)
+    n, M = 2, 10
+    o = obs(n, g)
+    em = mem(M, n, 276, g, 272)
+    emm = (torch.rand(n, M, generator=g) > 0.5).float()
+    h, pa, mk = torch.zeros(1, n, 512), torch.randint(0, 4, (n, 1), generator=g), torch.ones(n, 1)
+    act = torch.randint(0, 4, (n, 1), generator=g)
+    with torch.no_grad():
+        v, lp, ent, _, x = ref.evaluate_actions(o, h, pa, mk, act, em, emm)
+        av, aa, alp, _, ax, apr = ref.act(o, h, pa, mk, em, emm, deterministic=True)
+    save("smt_policy_pretraining.npz", seed=5, **pack_obs(o), em=em, em_masks=emm, prev_actions=pa, masks=mk, action=act,
          eval_value=v, eval_log_probs=lp, eval_entropy=ent, eval_em_feats=x,
          act_value=av, act_action=aa, act_log_probs=alp, act_em_feats=ax, act_probs=apr)
 
@@ -442,5 +468,5 @@ def dialog_update():
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
+    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
         fn()

@@ -286,6 +286,24 @@ def test_update_dialog_oracle_matches_reference_golden():
     assert abs(float(loss) - float(g["dialog_loss"])) <= 2e-5 * max(1.0, abs(float(g["dialog_loss"])))
 
 
+def test_smt_policy_pretraining_oracle_matches_reference_golden():
+    """pretraining=True: only the current observation is attendable, the memory (and its masks) must not matter."""
+    g = load("smt_policy_pretraining.npz")
+    pol = OM.AudioNavSMTPolicy(pretraining=True)
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    o, n = obs_of(g), g["em"].shape[1]
+    h = torch.zeros(1, n, 512)
+    with torch.no_grad():
+        v, lp, ent, _, x = pol.evaluate_actions(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["action"]), t(g["em"]),
+                                                t(g["em_masks"]))
+        av, aa, alp, _, ax, apr = pol.act(o, h, t(g["prev_actions"]), t(g["masks"]), t(g["em"]), 1 - t(g["em_masks"]),
+                                          uniforms=None)   # (inverted masks: same result)
+    assert close(v, g["eval_value"]) and close(lp, g["eval_log_probs"]) and close(ent, g["eval_entropy"])
+    assert close(x, g["eval_em_feats"]) and close(av, g["act_value"]) and close(alp, g["act_log_probs"])
+    assert close(apr, g["act_probs"]) and torch.equal(aa, t(g["act_action"]))
+
+
 def test_smt_policy_distractor_oracle_matches_reference_golden():
     """BASELINE configs 4 / 5: pi_g with the one-hot category in the feature row (memory_dim 297)."""
     g = load("smt_policy_distractor.npz")
