@@ -1,0 +1,115 @@
+"""The CUDA source of the rollout kernels, run on the host (tests/emul), against golden vectors recorded from the
+UNMODIFIED reference (tests/golden/make_golden.py) — the CPU suite's own pin of the kernel code to the reference,
+independent of the oracle restatement."""
+import ctypes
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+f32, i32 = ctypes.c_float, ctypes.c_int
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name)).items()}
+
+
+def c(a, dtype=np.float32):
+    return np.ascontiguousarray(np.asarray(a, dtype=dtype))
+
+
+def test_gae_kernel_source_matches_reference_golden(emul_lib):
+    g = load("gae.npz")
+    emul_lib.emul_gae.argtypes = [ctypes.c_void_p] * 5 + [i32, i32, i32, ctypes.c_double, ctypes.c_double]
+    for tag, use_gae in (("gae", 1), ("mc", 0)):
+        rewards, vp, masks, nv = c(g[tag + "_rewards"]), c(g[tag + "_value_preds"]).copy(), c(g[tag + "_masks"]), c(g[tag + "_next_value"])
+        T, N = rewards.shape[0], rewards.shape[1]
+        ret = np.zeros((T + 1, N, 1), np.float32)
+        emul_lib.emul_gae(rewards.ctypes.data, vp.ctypes.data, masks.ctypes.data, nv.ctypes.data, ret.ctypes.data, T, N,
+                          use_gae, float(g["gamma"]), float(g["tau"]))
+        hi = T if use_gae else T + 1
+        assert np.allclose(ret[:hi], g[tag + "_returns"][:hi], atol=1e-6, rtol=1e-6), tag
+
+
+def test_extmem_insert_kernel_source_matches_reference_golden(emul_lib):
+    g = load("extmem.npz")
+    N, total, cap, dim = int(g["n_envs"]), int(g["total"]), int(g["capacity"]), int(g["dim"])
+    mem = np.zeros((total, N, dim), np.float32)
+    masks = np.zeros((N, total), np.float32)
+    snap = np.zeros((N, total), np.float32)
+    emul_lib.emul_extmem_insert.argtypes = [ctypes.c_void_p] * 5 + [i32] * 5
+    idx = 0
+    for step in range(g["feats"].shape[0]):
+        f, nd = c(g["feats"][step]), c(g["not_done"][step])
+        emul_lib.emul_extmem_insert(mem.ctypes.data, masks.ctypes.data, f.ctypes.data, nd.ctypes.data, snap.ctypes.data, N,
+                                    total, cap, dim, idx)
+        idx = (idx + 1) % total
+        assert np.array_equal(masks, g["masks_trace"][step]) and np.array_equal(snap, masks), step   # bit-exact
+    assert idx == int(g["final_idx"]) and np.array_equal(mem, g["final_memory"])
+
+
+def test_belief_filter_kernel_source_matches_reference_golden(emul_lib):
+    """The batched belief filter kernel (EMA, odom <-> base transforms, silent frames, episode ends) fed with the two
+    networks' outputs computed by PyTorch on the CPU, against what the reference's BeliefPredictor.update produced."""
+    import torch
+    from tests.test_golden import _belief_nets
+    g = load("belief_update.npz")
+    n = int(g["n"])
+    cls, pred, _, _ = _belief_nets(g)
+    lastpg, haspg = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+    lastlb, haslb = np.zeros((n, 21), np.float32), np.zeros(n, np.int32)
+    emul_lib.emul_belief_update.argtypes = ([i32, ctypes.c_void_p, i32] + [ctypes.c_void_p] * 4 + [i32, f32, i32] +
+                                            [ctypes.c_void_p] * 6)
+    for s in range(int(g["steps"])):
+        spec, pose = c(g[f"s{s}_spectrogram"]), c(g[f"s{s}_pose"])
+        with torch.no_grad():
+            sp = torch.from_numpy(spec).permute(0, 3, 1, 2)
+            pg, lab = c(pred(sp).numpy()), c(cls(sp)[:, :21].numpy())
+        dn = c(g[f"s{s}_dones"], np.uint8)
+        loc, cat = np.zeros((n, 2), np.float32), np.zeros((n, 21), np.float32)
+        emul_lib.emul_belief_update(n, spec.ctypes.data, 65 * 26 * 2, pose.ctypes.data,
+                                    dn.ctypes.data if bool(g[f"s{s}_has_dones"]) else None, pg.ctypes.data, lab.ctypes.data,
+                                    21, 0.5, 0, lastpg.ctypes.data, haspg.ctypes.data, lastlb.ctypes.data,
+                                    haslb.ctypes.data, loc.ctypes.data, cat.ctypes.data)
+        want_l, want_c = g[f"s{s}_location_belief"], g[f"s{s}_category_belief"]
+        assert np.abs(loc - want_l).max() <= 3e-4 * max(1.0, np.abs(want_l).max()), s
+        assert np.abs(cat - want_c).max() <= 1e-4 * max(1.0, np.abs(want_c).max()), s
+
+
+def test_smt_forward_kernel_source_matches_reference_golden(emul_lib):
+    """The scene-memory transformer's CUDA source (token compaction, relative-pose encoding, fusion MLP, encoder /
+    decoder layers, varlen attention) run on the host on the feature rows the REFERENCE computed, followed by the two
+    heads: value and action probabilities of the reference's ``AudioNavSMTPolicy.act`` (pi_g and its distractor variant)."""
+    import torch
+    from avlen_b200.savi.models.smt_state_encoder import SMT_PARAM_KEYS
+    from oracle import models_torch as OM
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    emul_lib.avl_smt_workspace_bytes.restype = ctypes.c_longlong
+    emul_lib.avl_smt_workspace_bytes.argtypes = [ci] * 6
+    emul_lib.avl_smt_forward.argtypes = [ci] * 7 + [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    for name, kw in (("smt_policy.npz", {}), ("smt_policy_distractor.npz", {"use_category_input": True})):
+        g = load(name)
+        sd = OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=False, **kw), int(g["seed"]))
+        x = c(g["act_em_feats"])
+        B, F = x.shape
+        mem, masks = c(g["em"]), c(g["em_masks"])
+        M, D = mem.shape[0], 256
+        goal = np.zeros((B, D), np.float32)
+        goal[:, :21] = g["obs_category_belief"]
+        goal[:, 21:23] = g["obs_location_belief"]
+        params = [c(sd["net.smt_state_encoder." + k].numpy()) for k in SMT_PARAM_KEYS]
+        ptab = (vp * len(params))(*[p.ctypes.data for p in params])
+        rows_cap = B * (M + 1)
+        ws = np.zeros(emul_lib.avl_smt_workspace_bytes(B, rows_cap, F, D, 0, 0), np.uint8)
+        out = np.zeros((B, D), np.float32)
+        rc = emul_lib.avl_smt_forward(B, M, F, D, F - 4, 0, rows_cap, x.ctypes.data, mem.ctypes.data, B, None,
+                                      masks.ctypes.data, goal.ctypes.data, ctypes.cast(ptab, vp), out.ctypes.data,
+                                      ws.ctypes.data, 0, 0, None)
+        assert rc == 0
+        h = torch.from_numpy(out)
+        value = h @ sd["critic_goal.fc.weight"].t() + sd["critic_goal.fc.bias"]
+        logits = h @ sd["action_distribution_goal.linear.weight"].t() + sd["action_distribution_goal.linear.bias"]
+        probs = torch.softmax(logits, -1)
+        assert np.abs(value.numpy() - g["act_value"]).max() <= 1e-4 * max(1.0, np.abs(g["act_value"]).max()), name
+        assert np.abs(probs.numpy() - g["act_probs"]).max() <= 1e-4, name
+        assert np.array_equal(probs.argmax(-1, keepdim=True).numpy(), g["act_action"]), name
