@@ -113,3 +113,79 @@ def test_smt_forward_kernel_source_matches_reference_golden(emul_lib):
         assert np.abs(value.numpy() - g["act_value"]).max() <= 1e-4 * max(1.0, np.abs(g["act_value"]).max()), name
         assert np.abs(probs.numpy() - g["act_probs"]).max() <= 1e-4, name
         assert np.array_equal(probs.argmax(-1, keepdim=True).numpy(), g["act_action"]), name
+
+
+def test_ppo_loss_kernel_source_matches_reference_golden(emul_lib):
+    """Row Q: the fused PPO loss kernel (clipped surrogate with rl_masks, clipped value loss, entropy, uncertainty
+    cross-entropy) on the minibatch of the recorded rollout — heads evaluated by the oracle policy — against the numbers
+    the reference's ``PPO.update`` returned."""
+    import torch
+    from oracle import models_torch as OM
+    from tests.test_golden import _ppo_update_batch
+    from tests.test_golden import load as tload
+    g = tload("ppo_update.npz")
+    T, N = int(g["T"]), int(g["N"])
+    b, _, _ = _ppo_update_batch(g)
+    pol = OM.AudioNavOptionPolicy()
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    with torch.no_grad():
+        r = pol.evaluate_actions_option(b["obs"], torch.zeros(1, T * N, 512), b["prev_actions"], b["masks"],
+                                        b["actions_option"], b["memory"], b["em_masks"], b["query_state"],
+                                        b["last_query_info"])
+    values, unct, logits = r[0], r[1], torch.log(r[6])
+    B, A = logits.shape
+    arrs = [c(logits.numpy()), c(b["actions_option"].numpy()[:, 0], np.int64), c(b["old_lp"].numpy()), c(b["adv"].numpy()),
+            c(values.numpy()), c(b["value_preds"].numpy()), c(b["returns"].numpy()), c(b["rl_masks"].numpy()),
+            c(unct.numpy()), c(b["ucnt_gt"].numpy(), np.int64)]
+    dl, dv, du, out = (np.zeros((B, A), np.float32), np.zeros(B, np.float32), np.zeros((B, 2), np.float32),
+                       np.zeros(8, np.float32))
+    emul_lib.emul_ppo_loss.argtypes = [i32, i32] + [ctypes.c_void_p] * 10 + [f32] * 4 + [i32] + [ctypes.c_void_p] * 4
+    emul_lib.emul_ppo_loss(B, A, *[a.ctypes.data for a in arrs], 0.2, 0.5, 0.05, 0.5, 1, dl.ctypes.data, dv.ctypes.data,
+                           du.ctypes.data, out.ctypes.data)
+    for k, name in ((0, "value_loss"), (1, "action_loss"), (2, "dist_entropy"), (3, "unct_loss"), (5, "values_debug"),
+                    (6, "return_batch_debug")):
+        want = float(g[name])
+        assert abs(float(out[k]) - want) <= 5e-5 * max(1.0, abs(want)), (name, float(out[k]), want)
+
+
+def test_masked_weighted_ce_kernel_source_matches_reference_golden(emul_lib):
+    """Row R: the masked, class-weighted cross-entropy kernel on pi_l's logits (oracle policy) for the recorded dialog
+    rollout, against the loss the reference's ``PPO.update_dialog`` returned."""
+    import torch
+    from oracle import models_torch as OM
+    from oracle import rl_torch as R
+    from tests.test_golden import _obs_from, t
+    from tests.test_golden import load as tload
+    g = tload("dialog_update.npz")
+    T, N = int(g["T"]), int(g["N"])
+    em_vln, em_dlg = R.ExternalMemory(N, 3, 3, 276, num_copies=1), R.ExternalMemory(N, 3, 3, 256, num_copies=1)
+    vln_masks = [torch.zeros(N, 3)]
+    for s in range(T):
+        em_vln.insert(t(g[f"s{s}_emf_vln"]), t(g[f"s{s}_masks"]))
+        em_dlg.insert(t(g[f"s{s}_emf_dialog"]), t(g[f"s{s}_masks"]))
+        vln_masks.append(em_vln.masks.clone())
+    obs_steps = [_obs_from(g, "obs0_")] + [_obs_from(g, f"s{s}_obs_") for s in range(T)]
+    rows = lambda fn: torch.cat([fn(s) for s in range(T)], 0)  # noqa: E731
+    pol = OM.AudioNavDialogPolicy(clip_layers=int(g["clip_layers"]))
+    pol.load_state_dict(OM.seeded_state_dict(pol, int(g["seed"])))
+    pol.eval()
+    with torch.no_grad():
+        r = pol.evaluate_actions_dialog(
+            {k: rows(lambda s: obs_steps[s][k]) for k in obs_steps[0]}, torch.zeros(1, T * N, 512),
+            rows(lambda s: torch.zeros(N, 1, dtype=torch.long) if s == 0 else t(g[f"s{s - 1}_actions"])),
+            rows(lambda s: torch.ones(N, 1) if s == 0 else t(g[f"s{s - 1}_masks"])),
+            rows(lambda s: t(g[f"s{s}_actions"])), em_vln.memory[:, 0].repeat(1, T, 1), em_dlg.memory[:, 0].repeat(1, T, 1),
+            rows(lambda s: vln_masks[s]), rows(lambda s: t(g[f"s{s}_all_dialog"])), rows(lambda s: t(g[f"s{s}_agent_step"])))
+    logits = c(r[6].numpy())
+    B, A = logits.shape
+    targets = c(rows(lambda s: t(g[f"s{s}_o_action"])).numpy())
+    mask = c(rows(lambda s: t(g[f"s{s}_o_mask"])).numpy(), np.int64)
+    w = c([0, .33, .33, .33])
+    dlog, out = np.zeros((B, A), np.float32), np.zeros(3, np.float32)
+    vp = ctypes.c_void_p
+    emul_lib.emul_masked_weighted_ce.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+    assert emul_lib.emul_masked_weighted_ce(logits.ctypes.data, targets.ctypes.data, mask.ctypes.data, w.ctypes.data, B, A,
+                                            dlog.ctypes.data, out.ctypes.data) == 0
+    want = float(g["dialog_loss"])
+    assert abs(float(out[0]) - want) <= 5e-5 * max(1.0, abs(want)) and int(out[2]) == int(mask.sum())
