@@ -20,6 +20,7 @@ Cases (reference file:line of what is being recorded):
   gae.npz             RolloutStorage.compute_returns (use_gae True / False)         common/rollout_storage.py:114-132
   avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
   rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
+  smt_backward.npz    SMTStateEncoder forward + autograd backward (all gradients)   savi/models/smt_state_encoder.py:23-280
   belief_update.npz   BeliefPredictor.update x5 (silent frames, episode ends)      savi/models/belief_predictor.py:126-230
   dialog_update.npz   RolloutStorage.insert x3 + dialog_batching + PPO.update_dialog  savi/models/rollout_storage.py:414-588;
                       (pi_l, weighted CE on the o_mask rows)                         savi/ppo/ppo.py:99-154
@@ -319,6 +320,35 @@ def belief_update():
     save("belief_update.npz", n=n, steps=steps, seed_classifier=21, seed_predictor=22, **rec)
 
 
+def smt_backward():
+    """The reference's SMTStateEncoder (smt_state_encoder.py:23-280, nn.Transformer inside) forward + autograd backward
+    of sum(out * gout): the output, the gradient wrt the current features and every parameter gradient (matrices
+    subsampled with stride 97 to keep the fixture small)."""
+    enc_mod = ref_shim.load("ss_baselines.savi.models.smt_state_encoder")
+    from avlen_b200.savi.models.smt_state_encoder import SMT_PARAM_KEYS
+    B, M, F, D = 3, 9, 276, 256
+    ref = enc_mod.SMTStateEncoder(F, dim_feedforward=D, pose_indices=(272, 276), nhead=8, num_encoder_layers=1,
+                                  num_decoder_layers=1, dropout=0.0, activation="relu", pretraining=False)
+    ref.load_state_dict(OM.seeded_state_dict(OM.SMTStateEncoder(F, dim_feedforward=D, pose_indices=(272, 276)), 3))
+    g = torch.Generator().manual_seed(114)
+    x = mem(1, B, F, g, 272)[0]
+    memory = mem(M, B, F, g, 272)
+    masks = (torch.rand(B, M, generator=g) > 0.4).float()
+    masks[1] = 0  # a sample with an empty memory
+    goal = torch.randn(B, D, generator=g)
+    gout = torch.randn(B, D, generator=g)
+    xr = x.clone().requires_grad_(True)
+    out = ref(xr, memory, masks, goal=goal)
+    (out * gout).sum().backward()
+    sd = dict(ref.named_parameters())
+    grads = {}
+    for k in SMT_PARAM_KEYS:
+        gk = sd[k].grad
+        gk = torch.zeros_like(sd[k]) if gk is None else gk
+        grads["g_" + k] = gk.reshape(-1)[::97].clone() if gk.numel() > 4096 else gk.clone()
+    save("smt_backward.npz", seed=3, x=x, memory=memory, masks=masks, goal=goal, gout=gout, out=out, dx=xr.grad, **grads)
+
+
 def ppo_update():
     """One full reference ``PPO.update`` (savi/ppo/ppo.py:157-289, interactive pi_q: evaluate_actions_option, rl_masks,
     uncertainty loss) over a reference RolloutStorage filled through its own 22-argument ``insert`` — one epoch, one
@@ -468,5 +498,5 @@ def dialog_update():
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, ppo_update, dialog_update):
+    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, ppo_update, dialog_update):
         fn()

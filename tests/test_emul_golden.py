@@ -189,3 +189,40 @@ def test_masked_weighted_ce_kernel_source_matches_reference_golden(emul_lib):
                                             dlog.ctypes.data, out.ctypes.data) == 0
     want = float(g["dialog_loss"])
     assert abs(float(out[0]) - want) <= 5e-5 * max(1.0, abs(want)) and int(out[2]) == int(mask.sum())
+
+
+def test_smt_backward_kernel_source_matches_reference_golden(emul_lib):
+    """Forward + backward of the scene-memory transformer's CUDA source against the reference SMTStateEncoder's output
+    and its AUTOGRAD gradients (every parameter — matrices subsampled with stride 97 — and the current features)."""
+    from avlen_b200.savi.models.smt_state_encoder import SMT_PARAM_KEYS
+    from oracle import models_torch as OM
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    emul_lib.avl_smt_workspace_bytes.restype = ctypes.c_longlong
+    emul_lib.avl_smt_workspace_bytes.argtypes = [ci] * 6
+    emul_lib.avl_smt_forward.argtypes = [ci] * 7 + [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, ci, vp]
+    emul_lib.avl_smt_backward.argtypes = [ci] * 6 + [vp] * 8
+    g = load("smt_backward.npz")
+    x, mem, masks, goal, gout = c(g["x"]), c(g["memory"]), c(g["masks"]), c(g["goal"]), c(g["gout"])
+    B, F = x.shape
+    M, D = mem.shape[0], goal.shape[1]
+    sd = OM.seeded_state_dict(OM.SMTStateEncoder(F, dim_feedforward=D, pose_indices=(272, 276)), int(g["seed"]))
+    params = [c(sd[k].numpy()) for k in SMT_PARAM_KEYS]
+    grads = [np.zeros_like(p) for p in params]
+    ptab = (vp * len(params))(*[p.ctypes.data for p in params])
+    gtab = (vp * len(params))(*[q.ctypes.data for q in grads])
+    rows_cap = B * (M + 1)
+    ws = np.zeros(emul_lib.avl_smt_workspace_bytes(B, rows_cap, F, D, 1, 1), np.uint8)
+    out = np.zeros((B, D), np.float32)
+    assert emul_lib.avl_smt_forward(B, M, F, D, 272, 0, rows_cap, x.ctypes.data, mem.ctypes.data, B, None, masks.ctypes.data,
+                                    goal.ctypes.data, ctypes.cast(ptab, vp), out.ctypes.data, ws.ctypes.data, 1, 1, None) == 0
+    assert np.abs(out - g["out"]).max() <= 1e-4 * max(1.0, np.abs(g["out"]).max())
+    dx, dgoal = np.zeros((B, F), np.float32), np.zeros((B, D), np.float32)
+    assert emul_lib.avl_smt_backward(B, M, F, D, 272, rows_cap, goal.ctypes.data, ctypes.cast(ptab, vp), ctypes.cast(gtab, vp),
+                                     gout.ctypes.data, dx.ctypes.data, dgoal.ctypes.data, ws.ctypes.data, None) == 0
+    for k, gk in zip(SMT_PARAM_KEYS, grads):
+        want = g["g_" + k]
+        got = gk.reshape(-1)[::97] if gk.size > 4096 else gk
+        assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), k
+    want_dx = g["dx"].copy()
+    want_dx[:, 272:] = 0  # pose columns of the current observation carry no gradient in the CUDA path (DESIGN section 6)
+    assert np.abs(dx - want_dx).max() <= 2e-4 * max(1.0, np.abs(want_dx).max())
