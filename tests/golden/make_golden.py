@@ -21,6 +21,7 @@ Cases (reference file:line of what is being recorded):
   avnav_net.npz       AudioNavBaselineNet forward (visual + audio CNN, GRU)         av_nav/ppo/policy.py:85-160
   rnn_seq.npz         RNNStateEncoder.seq_forward with episode boundaries           av_nav/models/rnn_state_encoder.py:80-149
   smt_backward.npz    SMTStateEncoder forward + autograd backward (all gradients)   savi/models/smt_state_encoder.py:23-280
+  dialog_encoder_backward.npz  DialogStateEncoder forward + autograd backward      savi/models/dialog_state_encoder.py:43-160
   belief_update.npz   BeliefPredictor.update x5 (silent frames, episode ends)      savi/models/belief_predictor.py:126-230
   dialog_update.npz   RolloutStorage.insert x3 + dialog_batching + PPO.update_dialog  savi/models/rollout_storage.py:414-588;
                       (pi_l, weighted CE on the o_mask rows)                         savi/ppo/ppo.py:99-154
@@ -349,6 +350,37 @@ def smt_backward():
     save("smt_backward.npz", seed=3, x=x, memory=memory, masks=masks, goal=goal, gout=gout, out=out, dx=xr.grad, **grads)
 
 
+def dialog_encoder_backward():
+    """The reference's DialogStateEncoder (dialog_state_encoder.py:43-160: fusion of the dialog embedding, sinusoidal
+    position by agent step, nn.Transformer) forward + autograd backward of sum(out * gout)."""
+    enc_mod = ref_shim.load("ss_baselines.savi.models.dialog_state_encoder")
+    from avlen_b200.savi.models.dialog_state_encoder import DIALOG_PARAM_KEYS
+    B, K, D = 4, 3, 256
+    ref = enc_mod.DialogStateEncoder(2 * D, dim_feedforward=D, nhead=8, num_encoder_layers=1, num_decoder_layers=1,
+                                     dropout=0.0, activation="relu")
+    ref.load_state_dict(OM.seeded_state_dict(OM.DialogStateEncoder(2 * D, dim_feedforward=D), 4))
+    g = torch.Generator().manual_seed(115)
+    x = torch.randn(B, D, generator=g)
+    memory = torch.randn(K, B, D, generator=g)
+    masks = (torch.rand(B, K, generator=g) > 0.4).float()
+    masks[1] = 0
+    d_emb = torch.randn(B, D, generator=g)
+    step = torch.tensor([0, 2, 1, 99])
+    goal = torch.randn(B, D, generator=g)
+    gout = torch.randn(B, D, generator=g)
+    xr, dr, gr = (v.clone().requires_grad_(True) for v in (x, d_emb, goal))
+    out = ref(xr, memory, masks, dr, step, goal=gr)
+    (out * gout).sum().backward()
+    sd = dict(ref.named_parameters())
+    grads = {}
+    for k in DIALOG_PARAM_KEYS:
+        gk = sd[k].grad
+        gk = torch.zeros_like(sd[k]) if gk is None else gk
+        grads["g_" + k] = gk.reshape(-1)[::97].clone() if gk.numel() > 4096 else gk.clone()
+    save("dialog_encoder_backward.npz", seed=4, x=x, memory=memory, masks=masks, d_emb=d_emb, step=step.int(), goal=goal,
+         gout=gout, out=out, dx=xr.grad, dd=dr.grad, dgoal=gr.grad, **grads)
+
+
 def ppo_update():
     """One full reference ``PPO.update`` (savi/ppo/ppo.py:157-289, interactive pi_q: evaluate_actions_option, rl_masks,
     uncertainty loss) over a reference RolloutStorage filled through its own 22-argument ``insert`` — one epoch, one
@@ -498,5 +530,5 @@ def dialog_update():
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, ppo_update, dialog_update):
+    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, dialog_encoder_backward, ppo_update, dialog_update):
         fn()

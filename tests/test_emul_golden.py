@@ -226,3 +226,44 @@ def test_smt_backward_kernel_source_matches_reference_golden(emul_lib):
     want_dx = g["dx"].copy()
     want_dx[:, 272:] = 0  # pose columns of the current observation carry no gradient in the CUDA path
     assert np.abs(dx - want_dx).max() <= 2e-4 * max(1.0, np.abs(want_dx).max())
+
+
+def test_dialog_encoder_kernel_source_matches_reference_golden(emul_lib):
+    """Row K: forward + backward of the dialog state encoder's CUDA source against the reference DialogStateEncoder's
+    output and autograd gradients (parameters — matrices subsampled with stride 97 — features, dialog embedding, goal)."""
+    from avlen_b200.savi.models.dialog_state_encoder import DIALOG_PARAM_KEYS
+    from oracle import models_torch as OM
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib = emul_lib
+    lib.avl_dialog_workspace_bytes.restype = ctypes.c_longlong
+    lib.avl_dialog_workspace_bytes.argtypes = [ci] * 4
+    lib.avl_dialog_forward.argtypes = [ci, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp]
+    lib.avl_dialog_backward.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    g = load("dialog_encoder_backward.npz")
+    x, mem, masks, d_emb, goal, gout = (c(g[k]) for k in ("x", "memory", "masks", "d_emb", "goal", "gout"))
+    step = c(g["step"], np.int32)
+    B, D = x.shape
+    K = mem.shape[0]
+    enc = OM.DialogStateEncoder(2 * D, dim_feedforward=D)
+    sd = OM.seeded_state_dict(enc, int(g["seed"]))
+    params = [c(sd[k].numpy()) for k in DIALOG_PARAM_KEYS]
+    grads = [np.zeros_like(p) for p in params]
+    pe = c(enc.pos_encode.pe[:, 0].numpy())
+    ws = np.zeros(lib.avl_dialog_workspace_bytes(B, K, D, 1), np.uint8)
+    out = np.zeros((B, D), np.float32)
+    ptab = (vp * len(params))(*[p.ctypes.data for p in params])
+    gtab = (vp * len(params))(*[q.ctypes.data for q in grads])
+    assert lib.avl_dialog_forward(B, K, D, x.ctypes.data, mem.ctypes.data, B, None, masks.ctypes.data, d_emb.ctypes.data,
+                                  step.ctypes.data, pe.ctypes.data, pe.shape[0], goal.ctypes.data, ctypes.cast(ptab, vp),
+                                  out.ctypes.data, ws.ctypes.data, 1, None) == 0
+    assert np.abs(out - g["out"]).max() <= 1e-4 * max(1.0, np.abs(g["out"]).max())
+    dx, dd, dgoal = (np.zeros((B, D), np.float32) for _ in range(3))
+    assert lib.avl_dialog_backward(B, K, D, 1, goal.ctypes.data, ctypes.cast(ptab, vp), ctypes.cast(gtab, vp),
+                                   gout.ctypes.data, dx.ctypes.data, dd.ctypes.data, dgoal.ctypes.data, ws.ctypes.data,
+                                   None) == 0
+    for k, gk in zip(DIALOG_PARAM_KEYS, grads):
+        want = g["g_" + k]
+        got = gk.reshape(-1)[::97] if gk.size > 4096 else gk
+        assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), k
+    for got, key in ((dx, "dx"), (dd, "dd"), (dgoal, "dgoal")):
+        assert np.abs(got - g[key]).max() <= 2e-4 * max(1.0, np.abs(g[key]).max()), key
