@@ -267,3 +267,23 @@ def test_dialog_encoder_kernel_source_matches_reference_golden(emul_lib):
         assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), k
     for got, key in ((dx, "dx"), (dd, "dd"), (dgoal, "dgoal")):
         assert np.abs(got - g[key]).max() <= 2e-4 * max(1.0, np.abs(g[key]).max()), key
+
+
+def test_gru_kernel_source_matches_reference_golden(emul_lib):
+    """Row H: the fused GRU kernels against the reference RNNStateEncoder's chunked ``seq_forward`` over a sequence with
+    episode boundaries (av_nav/models/rnn_state_encoder.py:80-149): outputs and final hidden state."""
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    g = load("rnn_seq.npz")
+    T, N = int(g["T"]), int(g["N"])
+    x, h0, masks = c(g["x"]), c(g["hidden"][0]), c(g["masks"][:, 0])
+    I, H = x.shape[1], h0.shape[1]
+    wih, whh, bih, bhh = (c(g["w_rnn." + k]) for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"))
+    emul_lib.avl_gru_workspace_bytes.restype = ctypes.c_longlong
+    emul_lib.avl_gru_workspace_bytes.argtypes = [ci] * 5
+    emul_lib.avl_gru_forward.argtypes = [ci] * 4 + [vp] * 10 + [ci, vp]
+    ws = np.zeros(int(emul_lib.avl_gru_workspace_bytes(T, N, I, H, 0)) // 4 + 64, np.float32)
+    o, hl = np.zeros((T * N, H), np.float32), np.zeros((N, H), np.float32)
+    assert emul_lib.avl_gru_forward(T, N, I, H, x.ctypes.data, h0.ctypes.data, masks.ctypes.data, wih.ctypes.data,
+                                    whh.ctypes.data, bih.ctypes.data, bhh.ctypes.data, o.ctypes.data, hl.ctypes.data,
+                                    ws.ctypes.data, 0, None) == 0
+    assert np.abs(o - g["out"]).max() < 2e-5 and np.abs(hl - g["hidden_out"][0]).max() < 2e-5
