@@ -287,3 +287,93 @@ def test_gru_kernel_source_matches_reference_golden(emul_lib):
                                     whh.ctypes.data, bih.ctypes.data, bhh.ctypes.data, o.ctypes.data, hl.ctypes.data,
                                     ws.ctypes.data, 0, None) == 0
     assert np.abs(o - g["out"]).max() < 2e-5 and np.abs(hl - g["hidden_out"][0]).max() < 2e-5
+
+
+def test_audio_cnn_kernel_source_matches_reference_golden(emul_lib):
+    """Row C: the convolution kernel source (im2col-gather GEMM, OIHW weights, fused bias / ReLU) chained as the AudioCNN
+    (savi/models/audio_cnn.py:136-151: 5x5 s2, 3x3 s2, 3x3, Linear over the NCHW-flattened map = a whole-map kernel) on
+    the golden spectrograms, against the audio columns 144:272 of the feature row the reference policy produced."""
+    from oracle import models_torch as OM
+    vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    emul_lib.avl_conv2d_fwd.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, ll, ci, vp, ll, vp]
+    g = load("smt_policy.npz")
+    sd = OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=False), int(g["seed"]))
+    x = c(g["obs_spectrogram"])
+    N = x.shape[0]
+
+    def conv(x, key, KH, KW, stride, relu, whole_map=None):
+        w = sd[f"net.goal_encoder.cnn.{key}.weight"].numpy()
+        b = c(sd[f"net.goal_encoder.cnn.{key}.bias"].numpy())
+        n, H, W, C = x.shape
+        if whole_map is not None:
+            w = w.reshape(w.shape[0], *whole_map)
+        w = c(w)
+        Co = w.shape[0]
+        OH, OW = (H - KH) // stride + 1, (W - KW) // stride + 1
+        y = np.zeros((n, OH, OW, Co), np.float32)
+        assert emul_lib.avl_conv2d_fwd(x.ctypes.data, n, H, W, C, w.ctypes.data, Co, KH, KW, stride, 0, None, b.ctypes.data,
+                                       None, 0, int(relu), y.ctypes.data, Co, None) == 0
+        return y
+
+    y = conv(x, 0, 5, 5, 2, True)
+    y = conv(y, 2, 3, 3, 2, True)
+    y = conv(y, 4, 3, 3, 1, False)
+    assert y.shape == (N, 13, 3, 64)
+    y = conv(y, 6, 13, 3, 1, True, whole_map=(64, 13, 3)).reshape(N, 128)
+    want = g["act_em_feats"][:, 144:272]
+    assert np.abs(y - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
+
+
+def test_av_nav_net_kernel_source_matches_reference_golden(emul_lib):
+    """BASELINE config[0] on the kernel source: AudioCNN-512 and VisualCNN (rows C, D: av_nav/models/audio_cnn.py:79-89,
+    visual_cnn.py:137-154) as chains of the convolution kernel, then the fused GRU step with an episode-start mask
+    (row H), against the reference ``AudioNavBaselineNet`` features / hidden state and the critic's value."""
+    import torch
+    from oracle import models_torch as OM
+    vp, ci, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    emul_lib.avl_conv2d_fwd.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, ll, ci, vp, ll, vp]
+    g = load("avnav_net.npz")
+    sd = OM.seeded_state_dict(OM.AudioNavBaselinePolicy(), int(g["seed"]))
+
+    def conv(x, prefix, key, KH, KW, stride, relu, whole_map=None):
+        w = sd[f"{prefix}.cnn.{key}.weight"].numpy()
+        b = c(sd[f"{prefix}.cnn.{key}.bias"].numpy())
+        n, H, W, C = x.shape
+        if whole_map is not None:
+            w = w.reshape(w.shape[0], *whole_map)
+        w = c(w)
+        Co = w.shape[0]
+        OH, OW = (H - KH) // stride + 1, (W - KW) // stride + 1
+        y = np.zeros((n, OH, OW, Co), np.float32)
+        assert emul_lib.avl_conv2d_fwd(x.ctypes.data, n, H, W, C, w.ctypes.data, Co, KH, KW, stride, 0, None, b.ctypes.data,
+                                       None, 0, int(relu), y.ctypes.data, Co, None) == 0
+        return y
+
+    n = g["obs_pose"].shape[0]
+    a = conv(c(g["obs_spectrogram"]), "net.audio_encoder", 0, 5, 5, 2, True)
+    a = conv(a, "net.audio_encoder", 2, 3, 3, 2, True)
+    a = conv(a, "net.audio_encoder", 4, 3, 3, 1, False)
+    a = conv(a, "net.audio_encoder", 6, 13, 3, 1, True, whole_map=(64, 13, 3)).reshape(n, 512)
+    rgbd = c(np.concatenate([g["obs_rgb"].astype(np.float32) / np.float32(255.0), g["obs_depth"]], -1))
+    v = conv(rgbd, "net.visual_encoder", 0, 8, 8, 4, True)
+    v = conv(v, "net.visual_encoder", 2, 4, 4, 2, True)
+    v = conv(v, "net.visual_encoder", 4, 3, 3, 2, False)
+    assert v.shape == (n, 6, 6, 64)
+    v = conv(v, "net.visual_encoder", 6, 6, 6, 1, True, whole_map=(64, 6, 6)).reshape(n, 512)
+    x = c(np.concatenate([a, v], 1))
+    h0, masks = c(g["hidden"][0]), c(g["masks"][:, 0])
+    wih, whh, bih, bhh = (c(sd["net.state_encoder.rnn." + k].numpy())
+                          for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"))
+    emul_lib.avl_gru_workspace_bytes.restype = ll
+    emul_lib.avl_gru_workspace_bytes.argtypes = [ci] * 5
+    emul_lib.avl_gru_forward.argtypes = [ci] * 4 + [vp] * 10 + [ci, vp]
+    I, H = x.shape[1], h0.shape[1]
+    ws = np.zeros(int(emul_lib.avl_gru_workspace_bytes(1, n, I, H, 0)) // 4 + 64, np.float32)
+    o, hl = np.zeros((n, H), np.float32), np.zeros((n, H), np.float32)
+    assert emul_lib.avl_gru_forward(1, n, I, H, x.ctypes.data, h0.ctypes.data, masks.ctypes.data, wih.ctypes.data,
+                                    whh.ctypes.data, bih.ctypes.data, bhh.ctypes.data, o.ctypes.data, hl.ctypes.data,
+                                    ws.ctypes.data, 0, None) == 0
+    assert np.abs(o - g["features"]).max() <= 1e-4 * max(1.0, np.abs(g["features"]).max())
+    assert np.abs(hl - g["hidden_out"][0]).max() <= 1e-4
+    value = torch.from_numpy(o) @ sd["critic.fc.weight"].t() + sd["critic.fc.bias"]
+    assert np.abs(value.numpy() - g["value"]).max() <= 1e-4 * max(1.0, np.abs(g["value"]).max())
