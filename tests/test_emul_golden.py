@@ -377,3 +377,58 @@ def test_av_nav_net_kernel_source_matches_reference_golden(emul_lib):
     assert np.abs(hl - g["hidden_out"][0]).max() <= 1e-4
     value = torch.from_numpy(o) @ sd["critic.fc.weight"].t() + sd["critic.fc.bias"]
     assert np.abs(value.numpy() - g["value"]).max() <= 1e-4 * max(1.0, np.abs(g["value"]).max())
+
+
+def test_custom_resnet18_kernel_source_matches_reference_golden(emul_lib):
+    """Row E: the reference's SMTCNN rgb branch (smt_cnn.py:78-115: /255, 2x2 area mean to 64x64, custom_resnet18 with
+    GroupNorm(16), FC over the NCHW-flattened 8x8 map) as a chain of the convolution and GroupNorm kernel SOURCE on the
+    first golden sample, against the visual columns 0:64 of the feature row the reference policy produced."""
+    from oracle import models_torch as OM
+    vp, ci, ll, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    emul_lib.avl_conv2d_fwd.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, ll, ci, vp, ll, vp]
+    emul_lib.avl_groupnorm_fwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp]
+    g = load("smt_policy.npz")
+    sd = OM.seeded_state_dict(OM.AudioNavSMTPolicy(pretraining=False), int(g["seed"]))
+    P = "net.visual_encoder.rgb_encoder."
+
+    def conv(x, key, K, stride, pad, whole_map=None, bias=None):
+        w = sd[P + key].numpy()
+        if whole_map is not None:
+            w = w.reshape(w.shape[0], *whole_map)
+        w = c(w)
+        n, H, W, C = x.shape
+        Co = w.shape[0]
+        KH, KW = w.shape[2], w.shape[3]
+        OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+        y = np.zeros((n, OH, OW, Co), np.float32)
+        b = None if bias is None else c(sd[P + bias].numpy())
+        assert emul_lib.avl_conv2d_fwd(x.ctypes.data, n, H, W, C, w.ctypes.data, Co, KH, KW, stride, pad, None,
+                                       None if b is None else b.ctypes.data, None, 0, 0, y.ctypes.data, Co, None) == 0
+        return y
+
+    def gn(x, key, residual=None, relu=True):
+        n, H, W, C = x.shape
+        ga, be = c(sd[P + key + ".weight"].numpy()), c(sd[P + key + ".bias"].numpy())
+        y = np.zeros_like(x)
+        assert emul_lib.avl_groupnorm_fwd(x.ctypes.data, ga.ctypes.data, be.ctypes.data,
+                                          None if residual is None else residual.ctypes.data, y.ctypes.data, n, H * W, C, 16,
+                                          1e-5, int(relu), None) == 0
+        return y
+
+    rgb = g["obs_rgb"][:1].astype(np.float32) / np.float32(255.0)
+    x = c(rgb.reshape(1, 64, 2, 64, 2, 3).mean(axis=(2, 4)))  # F.interpolate(mode="area") 128 -> 64
+    x = gn(conv(x, "conv1.weight", 7, 1, 3), "bn1")
+    for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+        for bi in (0, 1):
+            s = stride if bi == 0 else 1
+            p = f"layer{li}.{bi}."
+            out = gn(conv(x, p + "conv1.weight", 3, s, 1), p + "bn1")
+            out = conv(out, p + "conv2.weight", 3, 1, 1)
+            identity = x
+            if (p + "downsample.0.weight") in {k[len(P):] for k in sd if k.startswith(P)}:
+                identity = gn(conv(x, p + "downsample.0.weight", 1, s, 0), p + "downsample.1", relu=False)
+            x = gn(out, p + "bn2", residual=c(identity), relu=True)
+    assert x.shape == (1, 8, 8, 128)
+    feat = conv(x, "fc.weight", 8, 1, 0, whole_map=(128, 8, 8), bias="fc.bias").reshape(1, 64)
+    want = g["act_em_feats"][:1, 0:64]
+    assert np.abs(feat - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
