@@ -432,3 +432,24 @@ def test_custom_resnet18_kernel_source_matches_reference_golden(emul_lib):
     feat = conv(x, "fc.weight", 8, 1, 0, whole_map=(128, 8, 8), bias="fc.bias").reshape(1, 64)
     want = g["act_em_feats"][:1, 0:64]
     assert np.abs(feat - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+
+
+def test_returns_and_advantages_kernel_source_match_reference_ppo_update(emul_lib):
+    """Rows N + O on the recorded PPO.update rollout: the GAE kernel reproduces ``rollouts.returns`` and the advantages
+    kernel ``PPO.get_advantages`` (savi/ppo/ppo.py:90-95, un-normalised) of the reference."""
+    from tests.test_golden import load as tload
+    g = tload("ppo_update.npz")
+    T, N = int(g["T"]), int(g["N"])
+    rewards = c(np.stack([g[f"s{s}_rewards"] for s in range(T)]))
+    vp = c(np.concatenate([np.stack([g[f"s{s}_values"] for s in range(T)]), np.zeros((1, N, 1), np.float32)]))
+    masks = c(np.concatenate([np.ones((1, N, 1), np.float32), np.stack([g[f"s{s}_masks"] for s in range(T)])]))
+    nv = c(g["next_value"])
+    ret = np.zeros((T + 1, N, 1), np.float32)
+    emul_lib.emul_gae.argtypes = [ctypes.c_void_p] * 5 + [i32, i32, i32, ctypes.c_double, ctypes.c_double]
+    emul_lib.emul_gae(rewards.ctypes.data, vp.ctypes.data, masks.ctypes.data, nv.ctypes.data, ret.ctypes.data, T, N, 1, 0.99,
+                      0.95)
+    assert np.allclose(ret[:T], g["returns"][:T], atol=1e-6, rtol=1e-6)
+    adv = np.zeros((T, N, 1), np.float32)
+    emul_lib.emul_advantages.argtypes = [ctypes.c_void_p] * 3 + [i32, i32, f32]
+    emul_lib.emul_advantages(ret.ctypes.data, vp.ctypes.data, adv.ctypes.data, T * N, 0, 1e-5)
+    assert np.allclose(adv, g["advantages"], atol=1e-6, rtol=1e-6)
