@@ -187,3 +187,21 @@ def test_dialog_policy_matches_reference(without_dialog, monkeypatch):
     assert torch.equal(r[1], m[1])
     for i in (0, 2, 4, 5, 6):
         assert torch.allclose(r[i], m[i], atol=2e-6), i
+
+
+def test_batch_obs_matches_reference():
+    """Row T (common/utils.py:129-156): list of per-env numpy observation dicts -> dict of stacked float32 tensors; the
+    product's staging (source dtype stacked once, converted after the copy) yields the reference's tensors bit for bit,
+    including the float64 silent audiogoal frame (simulator.py:648) and the uint8 images."""
+    u = ref_shim.load("ss_baselines.common.utils")
+    from avlen_b200.common.utils import batch_obs
+    rng = np.random.default_rng(6)
+    obs = [{"rgb": rng.integers(0, 256, (16, 16, 3), dtype=np.uint8), "depth": rng.random((16, 16, 1), dtype=np.float32),
+            "audiogoal": np.zeros((2, 40)) if i == 1 else rng.standard_normal((2, 40)).astype(np.float32),
+            "spectrogram": rng.random((65, 26, 2), dtype=np.float32), "pose": rng.standard_normal(4)}
+           for i in range(3)]
+    ref = u.batch_obs(obs)
+    mine = batch_obs(obs)
+    assert set(ref) == set(mine)
+    for k in ref:
+        assert mine[k].dtype == torch.float32 and torch.equal(ref[k], mine[k]), k
