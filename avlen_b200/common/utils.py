@@ -117,20 +117,40 @@ def linear_decay(epoch: int, total_num_updates: int) -> float:
     return 1 - (epoch / float(total_num_updates))
 
 
-def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, pinned: Optional[Dict] = None):
-    """common/utils.py:129-156: list of per-env observation dicts -> dict of stacked float32 tensors on ``device``.
+def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, pinned: Optional[Dict] = None,
+              keep_dtypes: Optional[Dict] = None):
+    """common/utils.py:129-156: list of per-env observation dicts -> dict of stacked tensors on ``device``.
 
-    The reference inflates uint8 images to fp32 on the host before the copy; here each sensor is stacked once into
-    pinned staging memory in its source dtype and converted on the device after an asynchronous copy."""
+    The reference inflates every sensor to fp32 on the host before a pageable copy; here each sensor is stacked ONCE,
+    in its source dtype, straight into pinned staging memory (``pinned``: a dict the caller keeps between steps; two
+    buffers per sensor alternate so that the copy of step s may still be in flight while step s+1 is staged), copied
+    asynchronously and converted on the device.  ``keep_dtypes``: sensors listed there stay in the
+    given dtype on the device (``{"rgb": torch.uint8, "depth": torch.float16}`` for the compact rollout storage);
+    everything else becomes float32 as in the reference."""
     out = {}
-    for sensor in observations[0]:
-        arr = np.stack([np.asarray(o[sensor]) for o in observations])
-        t = torch.from_numpy(arr)
+    first = observations[0]
+    n = len(observations)
+    for sensor in first:
+        a0 = np.asarray(first[sensor])
         if pinned is not None:
-            buf = pinned.get(sensor)
-            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                buf = pinned[sensor] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            buf.copy_(t)
-            t = buf
-        out[sensor] = t.to(device=device, non_blocking=True).to(dtype=torch.float32)
+            slot = pinned.get(sensor)
+            if slot is None or slot[0][0].shape != (n,) + a0.shape or slot[0][0].numpy().dtype != a0.dtype:
+                bufs = [torch.empty((n,) + a0.shape, dtype=torch.from_numpy(np.empty(0, a0.dtype)).dtype).pin_memory()
+                        for _ in range(2)]
+                slot = pinned[sensor] = [bufs, 0, [None, None]]
+            bufs, k, evs = slot
+            if evs[k] is not None:
+                evs[k].synchronize()  # the H2D copy that last read this buffer (two steps ago) must have finished
+            np.stack([np.asarray(o[sensor]) for o in observations], out=bufs[k].numpy())
+            t = bufs[k]
+        else:
+            t = torch.from_numpy(np.stack([np.asarray(o[sensor]) for o in observations]))
+        d = t.to(device=device, non_blocking=True)
+        if pinned is not None and d.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            slot[2][k] = ev
+            slot[1] = 1 - k
+        want = (keep_dtypes or {}).get(sensor, torch.float32)
+        out[sensor] = d if d.dtype == want else d.to(dtype=want)
     return out

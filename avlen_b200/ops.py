@@ -16,7 +16,8 @@ i64 = torch.int64
 def gae(rewards, value_preds, masks, next_value, returns, steps, use_gae, gamma, tau):
     """RolloutStorage.compute_returns (savi/models/rollout_storage.py:394-412). In place on value_preds/returns."""
     n = rewards.shape[1]
-    call("avl_gae_f64", fptr(rewards), fptr(value_preds), fptr(masks), fptr(next_value.contiguous()), fptr(returns),
+    nv = next_value.contiguous()  # held until the launch is enqueued (see PpoLoss.__call__)
+    call("avl_gae_f64", fptr(rewards), fptr(value_preds), fptr(masks), fptr(nv), fptr(returns),
          int(steps), int(n), int(bool(use_gae)), float(gamma), float(tau), stream())
     return returns
 
@@ -92,12 +93,17 @@ class PpoLoss:
         dv = torch.empty((B, 1), device=logits.device, dtype=torch.float32)
         du = torch.empty((B, 2), device=logits.device, dtype=torch.float32) if unct is not None else None
         out = torch.empty(8, device=logits.device, dtype=torch.float32)
-        c = lambda t: None if t is None else t.contiguous()
-        call("avl_ppo_loss_fwd_bwd", B, A, fptr(c(logits)), dptr(c(actions.reshape(B)), i64), fptr(c(old_lp)),
-             fptr(c(adv)), fptr(c(values)), fptr(c(value_preds)), fptr(c(returns)), fptr(c(rl_mask)), fptr(c(unct)),
-             dptr(c(unct_gt), i64) if unct_gt is not None else None, float(clip), float(value_coef), float(ent_coef),
-             float(unct_coef), int(bool(use_clipped_value)), fptr(dl), fptr(dv), fptr(du), fptr(out),
+        # contiguous copies are held in locals until the launch is enqueued: a temporary released right after
+        # data_ptr() could be handed by the caching allocator to the NEXT temporary, whose copy kernel would then
+        # overwrite the first argument before the loss kernel reads it
+        keep = [None if t is None else t.contiguous() for t in
+                (logits, actions.reshape(B), old_lp, adv, values, value_preds, returns, rl_mask, unct, unct_gt)]
+        lg, ac, ol, ad, va, vp, rt, rm, un, ug = keep
+        call("avl_ppo_loss_fwd_bwd", B, A, fptr(lg), dptr(ac, i64), fptr(ol), fptr(ad), fptr(va), fptr(vp), fptr(rt),
+             fptr(rm), fptr(un), dptr(ug, i64) if ug is not None else None, float(clip), float(value_coef),
+             float(ent_coef), float(unct_coef), int(bool(use_clipped_value)), fptr(dl), fptr(dv), fptr(du), fptr(out),
              self._ws.data_ptr(), stream())
+        del keep
         return out, dl, dv, du
 
 
@@ -108,8 +114,9 @@ class _MaskedWeightedCE(torch.autograd.Function):
         logits = logits.contiguous()
         d = torch.empty_like(logits)
         out = torch.empty(3, device=logits.device, dtype=torch.float32)
-        call("avl_masked_weighted_ce", fptr(logits), fptr(targets.reshape(B).float().contiguous()),
-             dptr(mask.reshape(B).contiguous(), i64), fptr(weight), B, A, fptr(d), fptr(out), stream())
+        tg, mk = targets.reshape(B).float().contiguous(), mask.reshape(B).contiguous()
+        call("avl_masked_weighted_ce", fptr(logits), fptr(tg), dptr(mk, i64), fptr(weight), B, A, fptr(d), fptr(out),
+             stream())
         ctx.save_for_backward(d)
         ctx.mark_non_differentiable(out)
         return out[0], out
@@ -129,7 +136,8 @@ def masked_weighted_ce(logits, targets, mask, weight=None):
 def extmem_insert(memory, masks, feats, not_done, snapshot, capacity, idx):
     """ExternalMemory.insert on the single-copy layout (total, N, dim) (rollout_storage.py:930-941)."""
     total, n, dim = memory.shape
-    call("avl_extmem_insert", fptr(memory), fptr(masks), fptr(feats.contiguous()), fptr(not_done.contiguous()),
+    feats, not_done = feats.contiguous(), not_done.contiguous()  # both alive until the launch is enqueued
+    call("avl_extmem_insert", fptr(memory), fptr(masks), fptr(feats), fptr(not_done),
          fptr(snapshot), n, total, int(capacity), dim, int(idx), stream())
 
 

@@ -41,7 +41,18 @@ class DecentralizedDistributedMixin:
         gradient reduction on."""
         assert distrib.is_initialized()
         self.world_size = distrib.get_world_size()
+        # DistributedDataParallel's constructor syncs EVERY parameter and buffer of the wrapped module from rank 0
+        # (ddppo.py:76-88), frozen encoders included: ranks are seeded differently (seed + rank), so without this a
+        # rank-0 checkpoint would only describe rank 0's rollouts.  Trainable parameters alias the flat buffer.
         distrib.broadcast(self._flat_p, src=0)
+        ac = getattr(self, "actor_critic", None)
+        if ac is not None:
+            flat_ptrs = {p.data_ptr() for p in self._params}
+            for t in ac.state_dict().values():
+                if torch.is_tensor(t) and t.data_ptr() not in flat_ptrs and t.numel() > 0:
+                    distrib.broadcast(t, src=0)
+            # packed tensor-core copies / parameter tables are keyed by the parameters' version counters
+            torch.autograd.graph.increment_version([p for p in ac.parameters() if p.data_ptr() not in flat_ptrs])
         self.get_advantages = self._get_advantages_distributed
         self._distributed = True
 

@@ -129,6 +129,14 @@ class DDPPOTrainer(PPOTrainer):
         K.sync_pending()  # the last step's deferred belief update joins the main stream here
         return self.rollouts.step * self.envs.num_envs
 
+    def reset_preemption_counter(self):
+        """ddppo_trainer.py:1005 / :1071: rank 0 zeroes ``num_done`` after every update; the barrier keeps a fast rank
+        from starting (and finishing a quarter of) the next rollout against the stale count."""
+        if self.world_size > 1 and self.config.use_preemption:
+            if self.world_rank == 0:
+                distrib.distributed_c10d._get_default_store().set("num_done", "0")
+            distrib.barrier()
+
     def train(self):
         if self.rollouts is None:
             self.setup()
@@ -139,6 +147,7 @@ class DDPPOTrainer(PPOTrainer):
         for _update in range(cfg.NUM_UPDATES):
             count_steps += self.collect_rollout()
             stats = self._update_agent(cfg, self.rollouts)
+            self.reset_preemption_counter()
         torch.cuda.synchronize()
         fps = count_steps * self.world_size / max(1e-9, time.time() - t0)
         return {"fps": fps, "value_loss": stats[0], "action_loss": stats[1], "dist_entropy": stats[2]}

@@ -61,6 +61,8 @@ class _DialogFunction(torch.autograd.Function):
                   _lib.dptr(agent_step, torch.int32), _lib.fptr(pe), pe.shape[0], _lib.fptr(goal),
                   ctypes.cast(enc._ptab.get(params), _p), _lib.fptr(out), ws.data_ptr(), int(need_grad), _lib.stream())
         if need_grad:
+            # single training workspace per module: refuse a backward whose activations were overwritten
+            enc._train_generation = ctx.generation = getattr(enc, "_train_generation", 0) + 1
             ctx.enc, ctx.dims, ctx.ws, ctx.params, ctx.goal = enc, (B, K, D), ws, params, goal
             ctx.has_dialog = d_emb is not None
             ctx.need = (x.requires_grad, d_emb is not None and d_emb.requires_grad, goal.requires_grad)
@@ -69,6 +71,9 @@ class _DialogFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         enc = ctx.enc
+        if enc._train_generation != ctx.generation:
+            raise _lib.AvlenError("DialogStateEncoder: another grad-enabled forward of this module ran before this "
+                                  "backward (the saved activations share one workspace); run backward per forward")
         B, K, D = ctx.dims
         params = ctx.params
         grads = []

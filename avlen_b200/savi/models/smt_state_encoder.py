@@ -105,6 +105,9 @@ class _SMTFunction(torch.autograd.Function):
                   ctypes.cast(ptab, ctypes.c_void_p), _lib.fptr(out), ws.data_ptr(), int(need_grad), int(need_dx),
                   _lib.stream())
         if need_grad:
+            # the activations live in the module's single training workspace: a second grad-enabled forward before
+            # this one's backward would overwrite them -> stamp a generation and refuse a stale backward
+            enc._train_generation = ctx.generation = getattr(enc, "_train_generation", 0) + 1
             ctx.enc, ctx.dims, ctx.ws, ctx.params, ctx.goal = enc, (B, M, F, D, pi, rows_cap), ws, params, goal
             ctx.need_dx, ctx.need_dgoal = need_dx, goal.requires_grad
         return out
@@ -112,6 +115,9 @@ class _SMTFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         enc = ctx.enc
+        if enc._train_generation != ctx.generation:
+            raise _lib.AvlenError("SMTStateEncoder: another grad-enabled forward of this module ran before this "
+                                  "backward (the saved activations share one workspace); run backward per forward")
         B, M, F, D, pi, rows_cap = ctx.dims
         params = ctx.params
         grads = []

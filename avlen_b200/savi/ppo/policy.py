@@ -443,13 +443,13 @@ class AudioNavOptionNet(AudioNavSMTNet):
     def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_masks, query_state,
                 last_query_info):
         e = self._query_count_emb_size
-        x = self.get_features(observations, prev_actions, extra_cols=e)  # [x (276) | query_state (32)]
         base = self._base_feature_size
-        if x.requires_grad:  # encoders are training: keep the autograd graph intact (no in-place column writes)
-            x = torch.cat([x[:, :base], query_state.float()], dim=1)
-        else:
-            with torch.no_grad():
-                K.copy_cols(query_state.contiguous(), x[:, base:base + e])
+        # the reference builds x_query = cat([x, query_state]) under torch.no_grad() (policy.py:1034-1036): pi_q never
+        # back-propagates into its encoders, whatever freeze_encoders says -> the features are computed without a graph
+        # (and therefore by the fused inference path), only the scene-memory transformer and the heads train
+        with torch.no_grad():
+            x = self.get_features(observations, prev_actions, extra_cols=e)  # [x (276) | query_state (32)]
+            K.copy_cols(query_state.contiguous(), x[:, base:base + e])
         belief = self._belief(observations, x.shape[0], x.device)
         x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
         with torch.no_grad():  # memory rows: [x | last_query_info] (policy.py:1062-1063)

@@ -46,7 +46,16 @@ class PPO(nn.Module):
         self.policy_head = policy_head  # "goal": SAVi evaluate_actions ; "option": AVLEN evaluate_actions_option
         self.device = next(actor_critic.parameters()).device
         self._params, self._flat_p, self._flat_g = flatten_parameters(actor_critic)
-        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps, views=self._params)
+        # pi_q builds its feature row under no_grad (policy.py:1034-1036): its encoders never see a gradient, so Adam
+        # leaves them bit-identical (zero moments) and nothing derived from them has to be refreshed after a step
+        net = getattr(actor_critic, "net", None)
+        self._encoders_never_trained = policy_head == "option" and net is not None
+        untouched = set()
+        if self._encoders_never_trained:
+            for enc in (net.goal_encoder, net.visual_encoder, net.action_encoder):
+                untouched.update(id(p) for p in enc.parameters())
+        views = [p for p in self._params if id(p) not in untouched]
+        self.optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=lr, eps=eps, views=views)
         # dialog pretraining (ppo.py:63, :70-76): its own Adam moments, lr 1e-5, class weights 'balanced'
         self.dialog_optimizer = ops.FlatAdam(self._flat_p, self._flat_g, lr=0.00001, eps=eps, views=self._params)
         self.dialog_class_weight = torch.tensor([0, .33, .33, .33], device=self.device)
@@ -122,8 +131,9 @@ class PPO(nn.Module):
         net = getattr(self.actor_critic, "net", None)
         can = (self.prefetch_encoders and net is not None and hasattr(net, "prefetch_observation_features")
                and advantages.is_cuda
-               and not any(p.requires_grad for enc in (net.goal_encoder, net.visual_encoder, net.action_encoder)
-                           for p in enc.parameters()))
+               and (self._encoders_never_trained or
+                    not any(p.requires_grad for enc in (net.goal_encoder, net.visual_encoder, net.action_encoder)
+                            for p in enc.parameters())))
         if not can:
             yield from minibatches()
             return

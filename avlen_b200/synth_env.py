@@ -14,6 +14,7 @@ import torch
 
 from . import _lib, synth
 from .audio import AudioRenderer
+from .common.utils import batch_obs
 
 
 class SyntheticVectorEnv:
@@ -33,7 +34,9 @@ class SyntheticVectorEnv:
         rgb = torch.from_numpy(rng.integers(0, 256, size=(pool, n, 128, 128, 3), dtype=np.uint8))
         depth = torch.from_numpy(rng.random((pool, n, 128, 128, 1), dtype=np.float32))
         if host_buffers:
-            self._rgb, self._depth = rgb.pin_memory(), depth.pin_memory()
+            # pageable host frames, as an env worker produces them; batch_obs owns the pinned staging buffers
+            self._rgb_np, self._depth_np = rgb.numpy(), depth.numpy()
+            self._staging = {}
             self._actions_host = torch.zeros(n, 1, dtype=torch.int64).pin_memory()
         else:
             self._rgb, self._depth = rgb.to(self.device), depth.to(self.device)
@@ -70,11 +73,14 @@ class SyntheticVectorEnv:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             if self.host_buffers:
-                rgb = self._rgb[i].to(self.device, non_blocking=True)
-                depth = self._depth[i].to(self.device, non_blocking=True)
+                # what a VectorEnv hands the trainer: one observation dict per env (numpy frames on the host) ->
+                # the product's batch_obs (common/utils.py:129-156): stack into pinned staging, async H2D, cast
+                per_env = [{"rgb": self._rgb_np[i][e], "depth": self._depth_np[i][e]} for e in range(self.num_envs)]
+                batch = batch_obs(per_env, device=self.device, pinned=self._staging)
+                rgb, depth = batch["rgb"], batch["depth"]
             else:
                 rgb, depth = self._rgb[i], self._depth[i]
-            rgb = rgb.float()  # batch_obs: everything becomes float32 (common/utils.py:149-154)
+                rgb = rgb.float()  # batch_obs: everything becomes float32 (common/utils.py:149-154)
             ev = torch.cuda.Event()
             ev.record(side)
         self.visual_ready_event = ev

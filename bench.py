@@ -1,15 +1,20 @@
-"""bench.py — BASELINE.json metric on BASELINE config[1]: SAVi semantic_audionav SMT policy (memory 150), rollout +
-PPO update, 64 envs per B200.
-
-A *step* is one full PPO iteration on synthetic Habitat-shaped observations: 150 rollout steps for all envs
-(audio render A+B, belief update M, policy act E/C/F/I, ring-memory insert G) followed by the update (bootstrap
-value, GAE N, 2 epochs x 2 minibatches of evaluate -> fused loss O/Q -> backward -> [all-reduce] -> clip + Adam).
-``value`` = env-steps/s of that whole cycle over all GPUs (the reference's ``fps``, ddppo_trainer.py:1161-1168).
+"""bench.py — BASELINE.json metric: policy env-steps/s (rollout + PPO update) on synthetic Habitat-shaped observations.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config savi|interactive|distractor|audio_sweep|avnav] [--regime both|frozen|trainable]
+
+Default (the driver's contract line) = BASELINE config[1]: SAVi semantic_audionav SMT policy (memory 150), 64 envs per
+B200.  A *step* is one full PPO iteration: 150 rollout steps for all envs (audio render A+B, belief update M, policy act
+E/C/F/I, ring-memory insert G) followed by the update (bootstrap value, GAE N, 2 epochs x 2 minibatches of evaluate ->
+fused loss O/Q -> backward -> [all-reduce] -> clip + Adam).  ``value`` = env-steps/s of that whole cycle over all GPUs
+(the reference's ``fps``, ddppo_trainer.py:1161-1168) in the FROZEN-encoder regime (savi.yaml, 2nd stage); the same
+line carries the TRAINABLE-encoder regime (savi_pretraining.yaml:53 ``freeze_encoders: False``, ``pretraining: True``)
+under ``"trainable"``, the reference modules as PyTorch-eager on the same GPU under ``"gpu_eager_baseline"`` and the
+reference algorithm on the host cores under ``"cpu_baseline"``.
 
 N>1 is launched by torchrun (one rank per GPU, NCCL); environments shard across ranks (weak scaling), the only
-data-path collective is the flat gradient all-reduce of the update.
+data-path collective is the flat gradient all-reduce of the update.  After the timed cycles every rank's flat
+parameter buffer is compared bit for bit (``ranks_params_equal``).
 """
 from __future__ import annotations
 
@@ -26,8 +31,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "policy_env_steps_per_sec_rollout_plus_ppo_update"
 UNIT = "env-steps/s"
-HALO_F16_TRAFFIC = 1216954880  # dram read + write of one fp16 halo-conv launch (profiles/r01_halo_conv_f16_layer1_ncu_full.txt)
-WORKLOAD = "savi_smt_memory150_frozen_encoders_rollout150_ppo2x2"
+DTYPE = "tf32 conv (tcgen05) / fp16 activation storage / 3xTF32 matmul / fp32 elsewhere"
+# bounded CPU sample of the reference arm / cpu_baseline: ONE fixed size (the throughput of the port depends on it)
+CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 8, 4
 
 
 def _peaks():
@@ -73,249 +79,348 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-# ------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def _world():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+
+
+def _barrier():
     import torch
     import torch.distributed as distrib
+    if _world()[0] > 1:
+        distrib.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(ms, dev):
+    import torch
+    import torch.distributed as distrib
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if _world()[0] > 1:
+        distrib.all_reduce(t, op=distrib.ReduceOp.MAX)
+    return float(t)
+
+
+def time_cycles(tr, cfg, steps, warmup):
+    """W untimed + K timed rollout+update cycles; device-timed, max over ranks.  Returns (ms/cycle, rollout ms total,
+    total ms, launches)."""
+    import torch
+    from avlen_b200 import _lib
+    for _ in range(warmup):
+        tr.collect_rollout()
+        tr._update_agent(cfg, tr.rollouts)
+    _barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    em = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    n0 = int(_lib.lib().avl_launch_count())
+    e0.record()
+    for i in range(steps):
+        es[i].record()
+        tr.collect_rollout()
+        em[i].record()
+        stats = tr._update_agent(cfg, tr.rollouts)
+    e1.record()
+    _barrier()
+    launches = int(_lib.lib().avl_launch_count()) - n0
+    ms_total = e0.elapsed_time(e1)
+    roll_ms = sum(es[i].elapsed_time(em[i]) for i in range(steps))
+    return _max_over_ranks(ms_total, tr.device) / steps, roll_ms, ms_total, launches, stats
+
+
+def ranks_params_equal(tr):
+    """Bit-compares the flat parameter buffer of every rank with rank 0's (DD-PPO keeps replicas identical)."""
+    import torch
+    import torch.distributed as distrib
+    world, _ = _world()
+    if world == 1:
+        return None
+    p = tr.agent._flat_p
+    ref = p.clone()
+    distrib.broadcast(ref, src=0)
+    same = torch.tensor([int(torch.equal(ref.view(torch.int32), p.view(torch.int32)))], device=p.device)
+    distrib.all_reduce(same, op=distrib.ReduceOp.MIN)
+    return bool(int(same))
+
+
+# ------------------------------------------------------------------------------------------ roofline legs
+def _time_kernel(fn, flush, iters=10):
+    import torch
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()  # 256 MB > the 126 MB L2
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        fn()
+        c1.record()
+        torch.cuda.synchronize()
+        ts.append(c0.elapsed_time(c1))
+    return sum(ts) / len(ts)
+
+
+def roofline_halo_conv(dev, B, flush, hbm, how):
+    """custom_resnet18 layer1 conv3x3 16->16 @64x64 at the update-minibatch batch: tc_conv_halo_kernel<fp16,fp16>.
+    36-72 FLOP/B << the tensor ridge => HBM-bound; algorithmic bytes = read x + write y (+ weights), DESIGN.md §4."""
+    import torch
+    from avlen_b200 import _lib
+    x = torch.randn(B, 64, 64, 16, device=dev).half()
+    w = (torch.randn(16, 3, 3, 16, device=dev) / 12).half()
+    y = torch.empty(B, 64, 64, 16, device=dev, dtype=torch.float16)
+
+    def run():
+        _lib.call("avl_tc_conv_halo_f16", x.data_ptr(), 1, B, 64, 64, 16, w.data_ptr(), 16, 3, 3, 1, 0, y.data_ptr(), 1,
+                  _lib.stream())
+    ms = _time_kernel(run, flush)
+    nbytes = 2.0 * B * 64 * 64 * 16 * 2 + 16 * 144 * 2
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "tc_conv_halo_kernel<fp16 in, fp16 out> (tcgen05 kind::f16, fp32 accumulate, halo strips, no im2col)"
+                      " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
+            "match": "tc_conv_halo_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+            "frac": round(ach / hbm, 5), "traffic": 1216954880 if B == 4800 else None,
+            "traffic_source": "profiles/r01_halo_conv_f16_layer1_ncu_full.txt (dram read + write of one launch)",
+            "peak_source": how, "launch_ms": round(ms, 4), "algorithmic_bytes": int(nbytes),
+            "tflops": round(2.0 * B * 64 * 64 * 16 * 144 / (ms * 1e-3) / 1e12, 2)}
+
+
+def roofline_im2col_conv(dev, B, flush, hbm, how):
+    """custom_resnet18 layer4 conv3x3 128->128 @8x8 at the update-minibatch batch through the generic tensor-core
+    convolution (tc_gemm_kernel<CONV>): 2*1152*128/(2*128*4) = 288 FLOP/B -> above the TF32 ridge only nominally;
+    measured against HBM (algorithmic bytes = read x + write y + weights, fp32)."""
+    import torch
+    from avlen_b200 import nn as K
+    x = torch.randn(B, 8, 8, 128, device=dev)
+    w = torch.randn(128, 128, 3, 3, device=dev) / 34
+
+    def run():
+        K._conv2d_raw(x, w, None, 1, 1)
+    ms = _time_kernel(run, flush)
+    nbytes = 2.0 * B * 8 * 8 * 128 * 4 + 128 * 1152 * 4
+    flops = 2.0 * B * 64 * 128 * 1152
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "tc_gemm_kernel<CONV> (tcgen05 kind::tf32, im2col gather) on custom_resnet18 layer4 conv3x3 "
+                      "128->128 @8x8, batch %d" % B, "match": "tc_gemm_kernel<true", "bound": "hbm",
+            "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 5), "traffic": None,
+            "peak_source": how, "launch_ms": round(ms, 4), "algorithmic_bytes": int(nbytes),
+            "tflops": round(flops / (ms * 1e-3) / 1e12, 2)}
+
+
+def kernel_shares(tr, cfg, rollout_steps):
+    """Per-kernel share of the device time of one cycle, via CUPTI (torch.profiler) OUTSIDE the timed region: 10 rollout
+    steps (scaled to the rollout length) + one full update.  Returns {kernel name prefix: share}."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    def collect(fn):
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        d = {}
+        for e in prof.key_averages():
+            if e.device_time_total > 0 and not e.key.startswith(("autograd::", "_SMT", "_Dialog", "aten::", "_Conv", "_Group", "_Gru", "_ResNet")):
+                d[e.key] = d.get(e.key, 0.0) + e.device_time_total
+        return d
+
+    k = min(10, rollout_steps)
+
+    def roll():
+        for _ in range(k):
+            tr._collect_rollout_step(tr.rollouts)
+    tr.rollouts.step = 0
+    a = collect(roll)
+    for _ in range(rollout_steps - k):
+        tr._collect_rollout_step(tr.rollouts)
+    from avlen_b200 import nn as K
+    K.sync_pending()
+    b = collect(lambda: tr._update_agent(cfg, tr.rollouts))
+    tot = {}
+    for name, us in a.items():
+        tot[name] = tot.get(name, 0.0) + us * rollout_steps / k
+    for name, us in b.items():
+        tot[name] = tot.get(name, 0.0) + us
+    s = sum(tot.values())
+    return {n: v / s for n, v in sorted(tot.items(), key=lambda kv: -kv[1])}
+
+
+# ------------------------------------------------------------------------------------------ our arm (config savi)
+def run_savi(args):
+    import torch
 
     from avlen_b200 import _lib
     from avlen_b200 import nn as K
     from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    world, rank = _world()
     if args.tc_level is not None:
         K.set_tensor_cores(args.tc_level)
-    cfg = savi_config(NUM_PROCESSES=args.envs, num_steps=args.rollout_steps)
-    tr = DDPPOTrainer(cfg).setup()
-    dev = tr.device
-    launches = {"n": 0}
-
-    def one_cycle(trainer):
-        trainer.collect_rollout()
-        return trainer._update_agent(cfg, trainer.rollouts)
-
-    def barrier():
-        if world > 1:
-            distrib.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        one_cycle(tr)
-    barrier()
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    em = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    n_launch0 = int(_lib.lib().avl_launch_count())
-    e0.record()
-    for i in range(args.steps):
-        es[i].record()
-        tr.collect_rollout()
-        em[i].record()
-        tr._update_agent(cfg, tr.rollouts)
-    e1.record()
-    barrier()
-    n_launch = int(_lib.lib().avl_launch_count()) - n_launch0
-    ms_total = e0.elapsed_time(e1)
-    roll_ms = sum(es[i].elapsed_time(em[i]) for i in range(args.steps))
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        distrib.all_reduce(t, op=distrib.ReduceOp.MAX)
-    ms_step = float(t) / args.steps
+    distractor = args.config == "distractor_smt"
+    base = dict(NUM_PROCESSES=args.envs, num_steps=args.rollout_steps, has_distractor_sound=distractor)
     env_steps = args.envs * args.rollout_steps * world
-    value = env_steps / (ms_step * 1e-3)
+    out = {}
+    line_stats = None
+    regimes = ["frozen", "trainable"] if args.regime == "both" else [args.regime]
+    sampler = None
+    tr_frozen = None
+    for regime in regimes:
+        over = dict(base)
+        if regime == "trainable":  # savi_pretraining.yaml:52-54
+            over.update(freeze_encoders=False, pretraining=not args.trainable_full_memory)
+        cfg = savi_config(**over)
+        tr = DDPPOTrainer(cfg).setup()
+        headline = regime == regimes[0]
+        if headline and rank == 0:
+            sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+            sampler.start()
+        steps = args.steps if headline else max(1, min(args.steps, 3))
+        ms_step, roll_ms, ms_total, launches, stats = time_cycles(tr, cfg, steps, args.warmup)
+        clocks = sampler.stop() if (headline and sampler) else None
+        k = args.envs * args.rollout_steps * steps
+        rec = {"env_steps_per_s": round(env_steps / (ms_step * 1e-3), 2), "ms_per_step": round(ms_step, 3), "steps": steps,
+               "rollout_env_steps_per_s": round(k / (roll_ms * 1e-3), 1),
+               "update_samples_per_s": round(k / ((ms_total - roll_ms) * 1e-3), 1), "gpu_launches": launches,
+               "losses": [round(float(x), 5) for x in stats[:3]], "ranks_params_equal": ranks_params_equal(tr),
+               "config": {"freeze_encoders": cfg.freeze_encoders, "pretraining": cfg.pretraining}}
+        if rec["ranks_params_equal"] is False:
+            raise SystemExit("DD-PPO replicas diverged: flat parameter buffers differ between ranks")
+        if headline:
+            rec["clocks"] = clocks
+            line_stats = rec
+        out[regime] = rec
+        if regime == "frozen":
+            tr_frozen, cfg_frozen = tr, cfg
+        else:
+            del tr
+        torch.cuda.empty_cache()
 
-    # ---- e2e: same cycle through the public API with HOST visual buffers (H2D every step, actions D2H every step)
+    # ---- e2e: the same cycle through the public API with HOST observations: every step the env hands over a list of
+    # per-env numpy observation dicts, batch_obs (common/utils.py) stages them in pinned memory and copies them to the
+    # device, the actions are read back to the host (D2H) for the env workers
     e2e = None
     if not args.no_e2e:
-        cfg2 = savi_config(NUM_PROCESSES=args.envs, num_steps=args.rollout_steps, host_buffers=True)
-        tr2 = DDPPOTrainer(cfg2)
-        tr2.setup()
-        one_cycle(tr2)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
+        over = dict(base, host_buffers=True)
+        if regimes[0] == "trainable":
+            over.update(freeze_encoders=False, pretraining=not args.trainable_full_memory)
+        cfg2 = savi_config(**over)
+        tr2 = DDPPOTrainer(cfg2).setup()
         k2 = max(1, min(2, args.steps))
-        for _ in range(k2):
-            stats = one_cycle(tr2)  # returns python floats (loss read back = D2H of the step result)
-        a1.record()
-        barrier()
-        t2 = torch.tensor([a0.elapsed_time(a1)], device=dev)
-        if world > 1:
-            distrib.all_reduce(t2, op=distrib.ReduceOp.MAX)
-        e2e = {"value": env_steps / (float(t2) / k2 * 1e-3), "unit": UNIT,
+        ms2, _, _, _, stats = time_cycles(tr2, cfg2, k2, 1)
+        e2e = {"value": round(env_steps / (ms2 * 1e-3), 2), "unit": UNIT,
                "h2d_bytes_per_step": int(tr2.envs.h2d_bytes_per_step * args.rollout_steps),
-               "d2h_bytes_per_step": int(tr2.envs.d2h_bytes_per_step * args.rollout_steps + 8 * 4)}
+               "d2h_bytes_per_step": int(tr2.envs.d2h_bytes_per_step * args.rollout_steps + 8 * 4),
+               "path": "SyntheticVectorEnv(host_buffers) -> list of per-env numpy dicts -> common.utils.batch_obs "
+                       "(pinned staging, async H2D, device-side cast) -> policy; actions D2H every step; losses D2H "
+                       "every update"}
         del tr2
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel.  The encoder convolutions dominate the device time of a cycle
-    # (profiles/r01_profile_step_*.txt); their most expensive single launch is custom_resnet18 layer1 (conv3x3
-    # 16->16 @64x64) at the update-minibatch batch, run by tc_conv_halo_kernel (csrc/conv_halo_tc.cu).  Arithmetic
-    # intensity in fp32 = 2*144*16 / (2*16*4) = 36 FLOP/B < the TF32 ridge (~110 FLOP/B) => HBM-bound: algorithmic
-    # bytes = read x + write y (+ weights), DESIGN.md section 4.  Timed live here with CUDA events on the launch
-    # stream, L2 flushed between iterations.
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     hbm, tf, how = _peaks()
-    B = args.envs * args.rollout_steps // cfg.num_mini_batch
-    B = min(B, 4800)
-    tcl = K.tensor_cores_level()
-    f16 = tcl >= 1 and bool(_lib.lib().avl_set_f16_activations(1))  # (returns the previous setting; default on)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    if f16:
-        # the fused ResNet keeps the stem output and stage 1 as fp16 in HBM: the launch that dominates is the
-        # kind::f16 halo-strip kernel reading and writing fp16 (half the bytes and half the MMAs of the TF32 variant)
-        x = torch.randn(B, 64, 64, 16, device=dev).half()
-        w = (torch.randn(16, 3, 3, 16, device=dev) / 12).half()
-        y = torch.empty(B, 64, 64, 16, device=dev, dtype=torch.float16)
+    B = min(args.envs * args.rollout_steps // 2, 4800)
+    cands = [roofline_halo_conv(dev, B, flush, hbm, how), roofline_im2col_conv(dev, B, flush, hbm, how)]
+    shares = {}
+    if tr_frozen is not None and not args.no_shares:
+        try:
+            shares = kernel_shares(tr_frozen, cfg_frozen, args.rollout_steps)
+        except Exception as e:  # the profiler is evidence, not the measurement
+            shares = {"error": str(e)[:200]}
+    top = [(n[:110], round(v, 4)) for n, v in list(shares.items())[:8] if isinstance(v, float)]
+    for c in cands:
+        c["share_of_step"] = round(sum(v for n, v in shares.items() if isinstance(v, float) and c["match"] in n), 4) \
+            if shares else None
+    cands.sort(key=lambda c: -(c["share_of_step"] or 0))
+    roofline = dict(cands[0])
+    roofline["others"] = cands[1:]
+    roofline["share_source"] = ("CUPTI (torch.profiler) after the timed region: 10 rollout steps scaled to the rollout "
+                                "length + one full update, frozen regime; share of the summed kernel device time")
+    roofline["top_kernels_by_device_time"] = top
+    del flush
 
-        def run_conv():
-            _lib.call("avl_tc_conv_halo_f16", x.data_ptr(), 1, B, 64, 64, 16, w.data_ptr(), 16, 3, 3, 1, 0, y.data_ptr(), 1,
-                      _lib.stream())
-        esz = 2
-    else:
-        _lib.lib().avl_set_f16_activations(0)
-        x = torch.randn(B, 64, 64, 16, device=dev)
-        w = torch.randn(16, 16, 3, 3, device=dev)
-
-        def run_conv():
-            K.conv2d(x, w, None, 1, 1)
-        esz = 4
-    for _ in range(3):
-        run_conv()
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        run_conv()
-        c1.record()
-        torch.cuda.synchronize()
-        ts.append(c0.elapsed_time(c1))
-    k_ms = sum(ts) / len(ts)
-    flops = 2.0 * B * 64 * 64 * 16 * 144
-    nbytes = 2.0 * B * 64 * 64 * 16 * esz + 16 * 144 * esz
-    ach = nbytes / (k_ms * 1e-3) / 1e9
-    if f16:
-        kname = "tc_conv_halo_kernel<fp16 in, fp16 out> (tcgen05 kind::f16, fp32 accumulate, halo strips, no im2col)"
-        traffic, tsrc = (HALO_F16_TRAFFIC if B == 4800 else None), "profiles/r01_halo_conv_f16_layer1_ncu_full.txt (dram read + write of one launch)"
-        note = ("algorithmic bytes = B*64*64*16*2 read + same written + weights (activations stored as fp16); 72 FLOP/B "
-                "< the fp16 ridge => HBM-bound; paced by the tensor core's shared-memory operand fetch (one M128xN16xK16 "
-                "MMA per 4.5 KB of operands), DESIGN.md section 4")
-    elif tcl >= 1:
-        kname = "tc_conv_halo_kernel (tcgen05 kind::tf32, halo strips, no im2col)"
-        traffic, tsrc = (2469416000 if B == 4800 else None), "profiles/r01_halo_conv_v3_layer1_ncu_full.txt (dram read + write of one launch)"
-        note = ("algorithmic bytes = B*64*64*16*4 read + same written + weights; 36 FLOP/B => HBM-bound; paced by the "
-                "tensor core's shared-memory operand fetch (64 B/clk: ~73 cycles per M128xN16xK8 MMA), DESIGN.md section 4")
-    else:
-        kname, traffic, tsrc, note = "gemm_kernel<CONV> fp32 SIMT", None, None, "fp32 SIMT build"
-    roofline = {"kernel": kname + " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
-                "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(ach / hbm, 5), "traffic": traffic, "traffic_source": tsrc,
-                "peak_source": how, "launch_ms": round(k_ms, 4), "algorithmic_bytes": int(nbytes),
-                "tflops": round(flops / (k_ms * 1e-3) / 1e12, 2), "note": note}
-    cpu = cpu_baseline_sample(1, quick=True) if not args.no_cpu else None
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps,
-                       "memory_size": 150, "ppo_epoch": 2, "num_mini_batch": 2, "parallelism": f"dp{world}",
-                       "l2": "inputs larger than L2 (rollout storage 2.6 GB, minibatch obs 1.3 GB)"},
-            "rollout_env_steps_per_s": round(args.envs * args.rollout_steps * args.steps / (roll_ms * 1e-3), 1),
-            "update_samples_per_s": round(args.envs * args.rollout_steps * args.steps / ((ms_total - roll_ms) * 1e-3), 1),
-            "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    gpu_eager = None
+    if not args.no_eager:
+        gpu_eager = gpu_eager_baseline(args, regimes)
+    cpu = cpu_baseline_sample(steps=3, warmup=1, one_thread=True) if not args.no_cpu else None
+    r0 = line_stats
+    wl = ("savi_smt_memory150_%s_encoders_rollout150_ppo2x2" % regimes[0]) + ("_distractor" if distractor else "")
+    line = {"metric": METRIC, "value": r0["env_steps_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r0["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": wl, "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps, "memory_size": 150,
+                       "ppo_epoch": 2, "num_mini_batch": 2, "parallelism": f"dp{world}", "regime": regimes[0],
+                       "l2": "inputs larger than L2 (rollout storage > 1 GB, minibatch obs > 0.3 GB)"},
+            "rollout_env_steps_per_s": r0["rollout_env_steps_per_s"], "update_samples_per_s": r0["update_samples_per_s"],
+            "ranks_params_equal": r0["ranks_params_equal"], "e2e": e2e, "gpu_launches": r0["gpu_launches"],
+            "clocks": r0["clocks"], "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager}
+    if "trainable" in out and regimes[0] != "trainable":
+        t = out["trainable"]
+        line["trainable"] = t
+        line["trainable_env_steps_per_s"] = t["env_steps_per_s"]
+        line["trainable_update_samples_per_s"] = t["update_samples_per_s"]
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------ reference arm
-def cpu_baseline_sample(steps, quick=False):
-    """The reference algorithm (oracle port of the reference's PyTorch modules + scipy/numpy audio) on the host
-    cores: n_cpu envs x t_cpu rollout steps + the PPO update over those rows, 301-token dense memory as the
-    reference executes it.  Returns the cpu_baseline dict (value in env-steps/s)."""
-    import numpy as np
+def gpu_eager_baseline(args, regimes):
+    """The reference modules (oracle port, state_dict-identical) as PyTorch-eager on cuda:0, the SAME 64 x 150 workload,
+    actually executed (one warm-up cycle of 10 steps, one full timed cycle per regime): cuDNN TF32 convolutions, fp32
+    matmuls, dense 301-token memory, T+1 memory copies, materialised minibatch memory.  No audio rendering (a CPU job of
+    the env workers in the reference) — which favours this baseline."""
     import torch
+    from oracle import baseline_workload as BW
+    res = {"what": "oracle port of the reference modules, PyTorch-eager on the same GPU, same envs x rollout x ppo 2x2, "
+                   "executed in full; audio rendering excluded (favours the baseline)", "unit": UNIT}
+    for regime in regimes:
+        kw = dict(freeze_encoders=regime == "frozen", pretraining=(regime == "trainable" and not args.trainable_full_memory),
+                  with_audio=False)
+        try:
+            BW.measure(args.envs, min(10, args.rollout_steps), "cuda", 1, 0, **kw)  # warm-up (cuDNN autotune, allocator)
+            torch.cuda.empty_cache()
+            m = BW.measure(args.envs, args.rollout_steps, "cuda", 1, 0, **kw)
+            res[regime] = {k: round(v, 2) for k, v in m.items()}
+        except Exception as e:
+            res[regime] = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
+    return res
 
-    from avlen_b200 import synth
-    from oracle import audio_np, models_torch as OM, rl_torch as R
 
+# ------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_baseline_sample(steps, warmup=1, one_thread=False):
+    """The reference algorithm (oracle/baseline_workload.py: oracle port of the reference's PyTorch modules + scipy/numpy
+    audio, dense memory with T+1 copies, GAE loop, real PPO loss) on the host cores, on ONE fixed bounded sample per
+    step.  Returns the cpu_baseline dict (value in env-steps/s at all host cores; ``value_1thread`` = the reference's
+    own ``torch.set_num_threads(1)`` setting, run.py:113)."""
+    from oracle import baseline_workload as BW
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n, T = (4, 2) if quick else (8, 4)
-    pol = OM.AudioNavSMTPolicy()
-    pol.load_state_dict(OM.seeded_state_dict(pol, 5))
-    for q in list(pol.net.goal_encoder.parameters()) + list(pol.net.visual_encoder.parameters()) + \
-            list(pol.net.action_encoder.parameters()):
-        q.requires_grad = False
-    pred = OM.CustomResNet18(2, 2, fc_in=4608)
-    import torchvision
-    cls = torchvision.models.resnet18()
-    cls.conv1 = torch.nn.Conv2d(2, 64, 7, 2, 3, bias=False)
-    cls.fc = torch.nn.Linear(512, 21)
-    cls.eval()
-    opt = torch.optim.Adam([q for q in pol.parameters() if q.requires_grad], lr=2.5e-4, eps=1e-5)
-    rng = np.random.default_rng(0)
-    b = synth.make_audio_batch(3, n, max_seconds=6)
-    sounds = [b["sounds"][o:o + l] for o, l in zip(b["clip_off_all"], b["clip_len_all"])]
-    rirs = [b["rirs"][o:o + l] for o, l in zip(b["rir_off"], b["rir_len"])]
-    mem = torch.randn(300, n, 276)
-    masks = (torch.rand(n, 300) < 0.25).float()
-    total = 0.0
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        store = []
-        for t in range(T):
-            _, sp = audio_np.render_batch(sounds, b["clip_id"], b["index"], rirs, b["silent"], 16000)
-            o = synth.make_observations(rng, n, t)
-            obs = {k: torch.from_numpy(v) for k, v in o.items()}
-            obs["spectrogram"] = torch.from_numpy(sp)
-            with torch.no_grad():
-                s4 = obs["spectrogram"].permute(0, 3, 1, 2)
-                obs["location_belief"], obs["category_belief"] = pred(s4), cls(s4)
-                v, a, lp, _, x, _ = pol.act(obs, None, torch.zeros(n, 1).long(), None, mem, masks,
-                                            uniforms=torch.rand(n))
-            store.append((obs, a, lp, v))
-        for _ep in range(2):
-            for _mb in range(2):
-                half = n // 2
-                sl = slice(_mb * half, (_mb + 1) * half)
-                ob = {k: torch.cat([s[0][k][sl] for s in store]) for k in store[0][0]}
-                acts = torch.cat([s[1][sl] for s in store])
-                v, lp, ent, _, _ = pol.evaluate_actions(ob, None, torch.zeros(T * half, 1).long(), None, acts,
-                                                        mem[:, sl].repeat(1, T, 1), masks[sl].repeat(T, 1))
-                old = torch.cat([s[2][sl] for s in store])
-                ratio = torch.exp(lp - old)
-                adv = torch.ones_like(ratio)
-                loss = -torch.min(ratio * adv, ratio.clamp(0.8, 1.2) * adv).mean() + 0.5 * (v - 1).pow(2).mean() - 0.05 * ent
-                opt.zero_grad()
-                loss.backward()
-                torch.nn.utils.clip_grad_norm_(pol.parameters(), 0.2)
-                opt.step()
-        total += time.perf_counter() - t0
-    val = steps * n * T / total
-    return {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} envs x {T} rollout steps (scipy/numpy audio + oracle belief + SMT policy act, dense 301-token "
-                      f"memory) + PPO update 2 epochs x 2 minibatches over those rows, torch CPU fp32, {cores} threads"}
+    n, T = CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS
+    m = BW.measure(n, T, "cpu", steps, warmup, threads=cores)
+    d = {"value": round(m["value"], 3), "unit": UNIT, "cores": cores, "kind": "port",
+         "rollout_env_steps_per_s": round(m["rollout_env_steps_per_s"], 2),
+         "update_samples_per_s": round(m["update_samples_per_s"], 2), "steps_timed": steps,
+         "sample": f"{n} envs x {T} rollout steps per step (scipy/numpy audio + belief nets + SMT policy act on the dense "
+                   f"{150 + T}-token memory with {T + 1} copies + storage insert) + GAE + PPO update 2 epochs x 2 "
+                   f"minibatches over those rows (real clipped loss, backward, clip, Adam), torch CPU fp32"}
+    if one_thread:
+        m1 = BW.measure(n, T, "cpu", 1, 0, threads=1)
+        d["value_1thread"] = round(m1["value"], 3)
+        import torch
+        torch.set_num_threads(cores)
+    return d
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
+    world, rank = _world()
     if rank != 0:
         return
-    # warm-up
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline_sample(1, quick=True)
     t0 = time.perf_counter()
-    cpu = cpu_baseline_sample(max(1, min(args.steps, 3)))
-    dt = time.perf_counter() - t0
-    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
-            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dt / max(1, min(args.steps, 3)) * 1e3, 2), "higher_is_better": True,
+    cpu = cpu_baseline_sample(steps=args.steps, warmup=args.warmup)  # executes exactly the steps it prints
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(CPU_SAMPLE_ENVS * CPU_SAMPLE_STEPS / cpu["value"] * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm on host cores, bounded sample per step"},
+            "config": {"workload": "savi_smt_memory150_frozen_encoders_rollout150_ppo2x2",
+                       "note": "reference algorithm on host cores, bounded sample per step", "wall_s": round(wall, 1)},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -327,16 +432,25 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--envs", type=int, default=64)
+    ap.add_argument("--config", default="savi")
+    ap.add_argument("--regime", default="both", choices=["both", "frozen", "trainable"])
+    ap.add_argument("--trainable-full-memory", action="store_true",
+                    help="trainable regime with pretraining=False (150-slot memory) instead of savi_pretraining.yaml")
+    ap.add_argument("--envs", type=int, default=None)
     ap.add_argument("--rollout-steps", type=int, default=150)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-shares", action="store_true")
     ap.add_argument("--tc-level", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 encoders (default), 2 + SMT")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+        return run_reference(args)
+    if args.config in ("savi", "distractor_smt"):
+        args.envs = args.envs or 64
+        return run_savi(args)
+    import bench_configs  # the other BASELINE configs (interactive / distractor / audio_sweep / avnav)
+    return bench_configs.run(args)
 
 
 if __name__ == "__main__":

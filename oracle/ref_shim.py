@@ -138,6 +138,49 @@ def load(modname: str):
     return mod
 
 
+def load_simulator():
+    """The UNMODIFIED ``soundspaces/simulator.py`` as a module (for ``SoundSpacesSim._compute_audiogoal`` /
+    ``get_current_audiogoal_observation``, simulator.py:644-721).  Its imports that are absent here (librosa,
+    habitat, habitat_sim, networkx when missing, soundspaces.utils / mp3d_utils) are stubbed; the methods under test
+    only use numpy, ``scipy.io.wavfile`` and ``scipy.signal.fftconvolve``, which are the real packages."""
+    install()
+    name = "soundspaces.simulator"
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None):
+        return sys.modules[name]
+    _stub("librosa")
+    try:
+        import networkx  # noqa: F401
+    except Exception:
+        _stub("networkx")
+
+    class _Registry:
+        def register_simulator(self, *a, **k):
+            return lambda cls: cls
+
+        def __getattr__(self, item):
+            return lambda *a, **k: (lambda cls: cls)
+
+    _stub("habitat.core")
+    _stub("habitat.core.registry", registry=_Registry())
+    _stub("habitat.sims")
+    _stub("habitat.sims.habitat_simulator")
+    _stub("habitat.sims.habitat_simulator.actions", HabitatSimActions=_Anything())
+    base = type("Simulator", (), {})
+    _stub("habitat.core.simulator", AgentState=_Anything, Config=_Anything, Observations=_Anything,
+          SensorSuite=_Anything, ShortestPathPoint=_Anything, Simulator=base)
+    hs = sys.modules["habitat_sim"]
+    for attr in ("AgentState", "Simulator", "SimulatorConfiguration", "AgentConfiguration", "Configuration"):
+        setattr(hs, attr, _Anything)
+    _stub("soundspaces.utils", load_metadata=_Anything())
+    _stub("soundspaces.mp3d_utils", HouseReader=_Anything)
+    path = os.path.join(REF_ROOT, "soundspaces", "simulator.py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def spaces():
     install()
     return sys.modules["gym.spaces"]

@@ -25,6 +25,8 @@ Cases (reference file:line of what is being recorded):
   belief_update.npz   BeliefPredictor.update x5 (silent frames, episode ends)      savi/models/belief_predictor.py:126-230
   dialog_update.npz   RolloutStorage.insert x3 + dialog_batching + PPO.update_dialog  savi/models/rollout_storage.py:414-588;
                       (pi_l, weighted CE on the o_mask rows)                         savi/ppo/ppo.py:99-154
+  audiogoal.npz       SoundSpacesSim._compute_audiogoal (three branches, distractor,    soundspaces/simulator.py:644-699,
+                      empty / unreadable RIR, silent) + the audiogoal cache sequence  :711-721
   ppo_update.npz      RolloutStorage.insert x3 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
                       one epoch / one minibatch: the six returned numbers            :591-810; savi/ppo/ppo.py:90-95,:157-289
 """
@@ -527,8 +529,90 @@ def dialog_update():
          em_vln_masks=st.em_vln_masks, **rec)
 
 
+def audiogoal():
+    """The reference's own ``SoundSpacesSim._compute_audiogoal`` (simulator.py:644-699), unmodified, executed on a plain
+    attribute holder as ``self`` with the RIRs written as float32 wav files (what ``wavfile.read`` expects): the three
+    source-clip branches, the distractor sum, an empty RIR file, an unreadable one, the silent frame; then
+    ``get_current_audiogoal_observation`` (:711-721) over a sequence of revisited (source, receiver, azimuth) keys —
+    the clip index advances only on cache misses (:668).  Inputs are regenerated from seeds by
+    tests/_audio_helpers.golden_audio_inputs; only the reference's outputs are stored."""
+    import tempfile
+    import types
+
+    from scipy.io import wavfile
+
+    from tests._audio_helpers import GOLDEN_AUDIO_CASES, GOLDEN_AUDIO_SR, golden_audio_inputs
+
+    sim = ref_shim.load_simulator()
+    fn = sim.SoundSpacesSim._compute_audiogoal
+    sr = GOLDEN_AUDIO_SR
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "0"))
+
+        def holder(src, index, distractor=None):
+            h = types.SimpleNamespace()
+            h.config = types.SimpleNamespace(AUDIO=types.SimpleNamespace(RIR_SAMPLING_RATE=sr,
+                                                                         HAS_DISTRACTOR_SOUND=distractor is not None))
+            h._episode_step_count, h._duration = 0, 500
+            h.binaural_rir_dir, h.azimuth_angle = tmp, 0
+            h._receiver_position_index, h._source_position_index, h._distractor_position_index = 1, 2, 3
+            h.current_source_sound = src
+            h._audio_index, h._audio_length = index, src.shape[0] // sr
+            h._source_sound_dict = {"d": distractor}
+            h._current_distractor_sound = "d"
+            return h
+
+        for ci, (name, secs, index, L, Ld) in enumerate(GOLDEN_AUDIO_CASES):
+            src, rir, d_src, d_rir = golden_audio_inputs(ci)
+            wavfile.write(os.path.join(tmp, "0", "1_2.wav"), sr, rir)
+            if d_rir is not None:
+                wavfile.write(os.path.join(tmp, "0", "1_3.wav"), sr, d_rir)
+            h = holder(src, index, d_src)
+            ag = fn(h)
+            assert ag.shape == (2, sr), ag.shape
+            out[name] = np.asarray(ag, dtype=np.float32)
+            out[name + "_next_index"] = np.int64(h._audio_index)
+        # empty RIR file (:657-659), unreadable file (:654-656), silent frame (:646-648)
+        src, rir, _, _ = golden_audio_inputs(1)
+        wavfile.write(os.path.join(tmp, "0", "1_2.wav"), sr, np.zeros((0, 2), np.float32))
+        ag = fn(holder(src, 1))
+        out["empty_rir_absmax"] = np.float64(np.abs(ag).max())
+        out["empty_rir_shape"] = np.array(ag.shape)
+        with open(os.path.join(tmp, "0", "1_2.wav"), "wb") as f:
+            f.write(b"this is not a wav file")
+        ag = fn(holder(src, 1))
+        out["unreadable_rir_absmax"] = np.float64(np.abs(ag).max())
+        h = holder(src, 1)
+        h._episode_step_count = 501
+        ag = fn(h)
+        out["silent_absmax"] = np.float64(np.abs(ag).max())
+        out["silent_dtype"] = np.array(str(ag.dtype))
+        # cache sequence: keys (source, receiver, azimuth); the clip index only advances when the key misses
+        src, rir, _, _ = golden_audio_inputs(2)
+        keys = [(2, 1, 0), (2, 4, 0), (2, 1, 0), (2, 5, 0), (2, 4, 0), (2, 6, 0), (2, 1, 0)]
+        for (_s, r, a) in set(keys):
+            os.makedirs(os.path.join(tmp, str(a)), exist_ok=True)
+            wavfile.write(os.path.join(tmp, str(a), f"{r}_2.wav"), sr, np.roll(rir, 37 * r, axis=0))
+        h = holder(src, 0)
+        h._audiogoal_cache = {}
+        h._compute_audiogoal = lambda: fn(h)
+        seq_idx, seq_head = [], []
+        for (_s, r, a) in keys:
+            h._receiver_position_index, h.azimuth_angle = r, a
+            before = h._audio_index
+            ag = sim.SoundSpacesSim.get_current_audiogoal_observation(h)
+            seq_idx.append(before if h._audio_index != before else -1)  # index consumed by this step (-1: cache hit)
+            seq_head.append(np.asarray(ag[:, :256], dtype=np.float32))
+        out["cache_keys"] = np.array(keys)
+        out["cache_index_used"] = np.array(seq_idx)
+        out["cache_heads"] = np.stack(seq_head)
+    np.savez_compressed(os.path.join(HERE, "audiogoal.npz"), **out)
+    print("audiogoal.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, dialog_encoder_backward, ppo_update, dialog_update):
+    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, dialog_encoder_backward, ppo_update, dialog_update, audiogoal):
         fn()

@@ -322,3 +322,50 @@ def test_smt_policy_distractor_oracle_matches_reference_golden():
     assert close(x, g["eval_em_feats"]) and close(av, g["act_value"]) and close(alp, g["act_log_probs"])
     assert close(ax, g["act_em_feats"]) and close(apr, g["act_probs"])
     assert torch.equal(aa, t(g["act_action"]))
+
+
+def test_audiogoal_oracle_matches_reference_golden():
+    """Row A: oracle/audio_np.compute_audiogoal against the outputs of the UNMODIFIED ``SoundSpacesSim._compute_audiogoal``
+    (soundspaces/simulator.py:644-699) executed under the shim on wav files (tests/golden/make_golden.py:audiogoal): the
+    three clip branches, the distractor sum, the clip-index advance, empty / unreadable RIR files, the silent frame."""
+    from oracle import audio_np as A
+    from tests._audio_helpers import GOLDEN_AUDIO_CASES, GOLDEN_AUDIO_SR, golden_audio_inputs
+    g = load("audiogoal.npz")
+    sr = GOLDEN_AUDIO_SR
+    for ci, (name, secs, index, L, Ld) in enumerate(GOLDEN_AUDIO_CASES):
+        src, rir, d_src, d_rir = golden_audio_inputs(ci)
+        ag, nxt = A.compute_audiogoal(src, rir, index, sr, False, d_src, d_rir)
+        want = g[name]
+        assert ag.shape == (2, sr)
+        assert np.abs(ag.astype(np.float32) - want).max() <= 1e-6 * np.abs(want).max(), name
+        assert nxt == int(g[name + "_next_index"]), name
+        fir = A.fir_definition(src, rir, index, sr)  # the unified causal-FIR statement the CUDA kernel implements
+        if d_src is not None:
+            fir = fir + A.fir_definition(d_src, d_rir, 0, sr)
+        assert np.abs(fir - want).max() <= 2e-5 * np.abs(want).max(), name
+    src, rir, _, _ = golden_audio_inputs(1)
+    ag, _ = A.compute_audiogoal(src, np.zeros((0, 2), np.float32), 1, sr)
+    assert float(g["empty_rir_absmax"]) == 0.0 and np.abs(ag).max() == 0.0 and tuple(g["empty_rir_shape"]) == ag.shape
+    assert float(g["unreadable_rir_absmax"]) == 0.0  # an unreadable file is replaced by a zero RIR (:654-656)
+    ag, nxt = A.compute_audiogoal(src, rir, 1, sr, silent=True)
+    assert float(g["silent_absmax"]) == 0.0 and np.abs(ag).max() == 0.0 and nxt == 1
+    assert str(g["silent_dtype"]) == str(ag.dtype) == "float64"
+
+
+def test_audiogoal_cache_sequence_matches_reference_golden():
+    """simulator.py:711-721 + :668: ``get_current_audiogoal_observation`` caches by (source, receiver, azimuth) and the
+    clip index only advances on a miss.  Replays the recorded key sequence through the oracle with a dict cache."""
+    from oracle import audio_np as A
+    from tests._audio_helpers import GOLDEN_AUDIO_SR, golden_audio_inputs
+    g = load("audiogoal.npz")
+    sr = GOLDEN_AUDIO_SR
+    src, rir, _, _ = golden_audio_inputs(2)
+    cache, index = {}, 0
+    for step, key in enumerate(map(tuple, g["cache_keys"])):
+        used = -1
+        if key not in cache:
+            used = index
+            cache[key], index = A.compute_audiogoal(src, np.roll(rir, 37 * key[1], axis=0), index, sr)
+        assert used == int(g["cache_index_used"][step]), step
+        want = g["cache_heads"][step]
+        assert np.abs(cache[key][:, :256].astype(np.float32) - want).max() <= 1e-6 * max(1e-9, np.abs(want).max())

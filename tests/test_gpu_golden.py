@@ -1,6 +1,11 @@
 """The CUDA path against golden vectors recorded from the UNMODIFIED reference (tests/golden/make_golden.py): the
-reference tree does not exist on the GPU box, the files carry its outputs.  fp32 kernels (tensor cores off): fp32
-outputs within 1e-3 relative (north_star), actions / masks / indices bit-exact."""
+reference tree does not exist on the GPU box, the files carry its outputs.  Every case runs in BOTH numeric modes:
+
+* ``fp32``    — tensor cores off: fp32 outputs within 1e-3 relative (north_star), actions / masks / indices bit-exact;
+* ``default`` — what bench.py times: tcgen05 TF32 convolutions, fp16 activation STORAGE inside the fused ResNet-18,
+  3xTF32 transformer linears: fp32 outputs within the stated reduced-precision tolerance 2e-2 of the output range
+  (north_star: "bf16 encoders within a stated tolerance"); mask / index work stays bit-exact; a deterministic action
+  must equal the reference's wherever the reference's top-2 probability gap exceeds that tolerance."""
 import os
 
 import numpy as np
@@ -11,17 +16,38 @@ from oracle import models_torch as OM
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = 1e-3
+TOL = [1e-3]      # set per mode by the fixture below
+ENT_TOL = [1e-4]
+MODE = ["fp32"]
 KW = dict(hidden_size=256, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
           pretraining=False)
 
 
-@pytest.fixture(autouse=True)
-def _fp32_path():
+@pytest.fixture(autouse=True, params=["fp32", "default"])
+def _numeric_mode(request):
     from avlen_b200 import nn as K
-    old = K.set_tensor_cores(False)
+    MODE[0] = request.param
+    if request.param == "fp32":
+        old = K.set_tensor_cores(False)
+        TOL[0], ENT_TOL[0] = 1e-3, 1e-4
+    else:
+        old = K.set_tensor_cores(1)
+        K.set_f16_activations(True)
+        TOL[0], ENT_TOL[0] = 2e-2, 5e-3
     yield
     K.set_tensor_cores(old)
+    TOL[0], ENT_TOL[0], MODE[0] = 1e-3, 1e-4, "fp32"
+
+
+def same_action(a, want, probs):
+    """Deterministic actions: bit-equal in fp32 mode; in the reduced-precision mode a row may only differ where the
+    reference's own top-2 probabilities are closer than the mode's tolerance."""
+    a, want = a.cpu().view(-1), torch.from_numpy(np.asarray(want)).view(-1)
+    if MODE[0] == "fp32":
+        return torch.equal(a, want)
+    top2 = torch.from_numpy(np.asarray(probs)).float().topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * TOL[0]
+    return torch.equal(a[decided], want[decided])
 
 
 def load(name):
@@ -62,13 +88,13 @@ def test_smt_policy_cuda_matches_reference_golden():
     with torch.no_grad():
         v, a, lp, _, x, pr = p.act(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["em"]), d(g["em_masks"]),
                                    deterministic=True)
-    assert torch.equal(a.cpu(), torch.from_numpy(g["act_action"]))
-    assert rel(v, g["act_value"]) < TOL and rel(lp, g["act_log_probs"]) < TOL and rel(pr, g["act_probs"]) < TOL
-    assert rel(x, g["act_em_feats"]) < TOL
+    assert same_action(a, g["act_action"], g["act_probs"])
+    assert rel(v, g["act_value"]) < TOL[0] and rel(lp, g["act_log_probs"]) < TOL[0] and rel(pr, g["act_probs"]) < TOL[0]
+    assert rel(x, g["act_em_feats"]) < TOL[0]
     v, lp, ent, _, x = p.evaluate_actions(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), d(g["em"]),
                                           d(g["em_masks"]))
-    assert rel(v, g["eval_value"]) < TOL and rel(lp, g["eval_log_probs"]) < TOL and rel(x, g["eval_em_feats"]) < TOL
-    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < 1e-4
+    assert rel(v, g["eval_value"]) < TOL[0] and rel(lp, g["eval_log_probs"]) < TOL[0] and rel(x, g["eval_em_feats"]) < TOL[0]
+    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < ENT_TOL[0]
 
 
 def test_option_policy_cuda_matches_reference_golden():
@@ -82,13 +108,13 @@ def test_option_policy_cuda_matches_reference_golden():
     args = (d(g["em"]), d(g["em_masks"]), d(g["query_state"]), d(g["last_query_info"]))
     with torch.no_grad():
         a = p.act_option(o, h, d(g["prev_actions"]), d(g["masks"]), *args, deterministic=True)
-    assert torch.equal(a[2].cpu(), torch.from_numpy(g["act_action"]))
+    assert same_action(a[2], g["act_action"], g["act_probs"])
     for i, k in ((0, "act_value"), (1, "act_unct"), (3, "act_log_probs"), (5, "act_em_feats"), (6, "act_probs")):
-        assert rel(a[i], g[k]) < TOL, k
+        assert rel(a[i], g[k]) < TOL[0], k
     r = p.evaluate_actions_option(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), *args)
     for i, k in ((0, "eval_value"), (1, "eval_unct"), (2, "eval_log_probs"), (5, "eval_em_feats"), (6, "eval_probs")):
-        assert rel(r[i], g[k]) < TOL, k
-    assert abs(float(r[3].detach()) - float(g["eval_entropy"])) < 1e-4
+        assert rel(r[i], g[k]) < TOL[0], k
+    assert abs(float(r[3].detach()) - float(g["eval_entropy"])) < ENT_TOL[0]
 
 
 def test_dialog_policy_cuda_matches_reference_golden():
@@ -103,14 +129,14 @@ def test_dialog_policy_cuda_matches_reference_golden():
     args = (d(g["em"]), d(g["em_dialog"]), d(g["em_masks"]), d(g["dialog"]), d(g["agent_step"]).float())
     with torch.no_grad():
         a = p.act_dialog(o, h, d(g["prev_actions"]), d(g["masks"]), *args, deterministic=True, without_dialog=False)
-    assert torch.equal(a[1].cpu(), torch.from_numpy(g["act_action"]))
+    assert same_action(a[1], g["act_action"], g["act_probs"])
     for i, k in ((0, "act_value"), (2, "act_log_probs"), (4, "act_em_feats"), (5, "act_em_dialog_feats"), (6, "act_probs")):
-        assert rel(a[i], g[k]) < TOL, k
+        assert rel(a[i], g[k]) < TOL[0], k
     r = p.evaluate_actions_dialog(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), *args, without_dialog=False)
     assert r[0] is None
     for i, k in ((1, "eval_log_probs"), (4, "eval_em_feats"), (5, "eval_em_dialog_feats"), (6, "eval_logits")):
-        assert rel(r[i], g[k]) < TOL, k
-    assert abs(float(r[2].detach()) - float(g["eval_entropy"])) < 1e-4
+        assert rel(r[i], g[k]) < TOL[0], k
+    assert abs(float(r[2].detach()) - float(g["eval_entropy"])) < ENT_TOL[0]
 
 
 def test_external_memory_cuda_matches_reference_golden():
@@ -190,7 +216,7 @@ def test_ppo_update_cuda_matches_reference_golden():
     out = agent.update(st)
     for got, k in zip(out, ("value_loss", "action_loss", "dist_entropy", "values_debug", "return_batch_debug", "unct_loss")):
         want = float(g[k])
-        assert abs(float(got) - want) <= TOL * max(1.0, abs(want)), (k, float(got), want)
+        assert abs(float(got) - want) <= TOL[0] * max(1.0, abs(want)), (k, float(got), want)
 
 
 def test_belief_update_cuda_matches_reference_golden():
@@ -213,8 +239,8 @@ def test_belief_update_cuda_matches_reference_golden():
              "location_belief": torch.zeros(n, 2, device="cuda"), "category_belief": torch.zeros(n, 21, device="cuda")}
         dones = torch.from_numpy(g[f"s{s}_dones"]) if bool(g[f"s{s}_has_dones"]) else None
         bp.update(o, dones)
-        assert rel(o["location_belief"], g[f"s{s}_location_belief"]) < TOL, s
-        assert rel(o["category_belief"], g[f"s{s}_category_belief"]) < TOL, s
+        assert rel(o["location_belief"], g[f"s{s}_location_belief"]) < TOL[0], s
+        assert rel(o["category_belief"], g[f"s{s}_category_belief"]) < TOL[0], s
 
 
 def test_update_dialog_cuda_matches_reference_golden():
@@ -263,7 +289,7 @@ def test_update_dialog_cuda_matches_reference_golden():
     agent = PPO(p, 0.2, 1, 1, 0.5, 0.05, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_normalized_advantage=False)
     loss = agent.update_dialog(st)
     want = float(g["dialog_loss"])
-    assert abs(float(loss) - want) <= 2e-3 * max(1.0, abs(want)), (float(loss), want)
+    assert abs(float(loss) - want) <= max(2e-3, TOL[0]) * max(1.0, abs(want)), (float(loss), want)
 
 
 def test_av_nav_net_cuda_matches_reference_golden():
@@ -280,7 +306,7 @@ def test_av_nav_net_cuda_matches_reference_golden():
     with torch.no_grad():
         feats, h2 = p.net(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
         value = p.get_value(o, d(g["hidden"]), torch.zeros(n, 1, dtype=torch.long, device="cuda"), d(g["masks"]))
-    assert rel(feats, g["features"]) < TOL and rel(h2, g["hidden_out"]) < TOL and rel(value, g["value"]) < TOL
+    assert rel(feats, g["features"]) < TOL[0] and rel(h2, g["hidden_out"]) < TOL[0] and rel(value, g["value"]) < TOL[0]
 
 
 def test_smt_policy_distractor_cuda_matches_reference_golden():
@@ -296,10 +322,65 @@ def test_smt_policy_distractor_cuda_matches_reference_golden():
     with torch.no_grad():
         v, a, lp, _, x, pr = p.act(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["em"]), d(g["em_masks"]),
                                    deterministic=True)
-    assert torch.equal(a.cpu(), torch.from_numpy(g["act_action"]))
-    assert rel(v, g["act_value"]) < TOL and rel(lp, g["act_log_probs"]) < TOL and rel(pr, g["act_probs"]) < TOL
-    assert rel(x, g["act_em_feats"]) < TOL and x.shape[1] == 297
+    assert same_action(a, g["act_action"], g["act_probs"])
+    assert rel(v, g["act_value"]) < TOL[0] and rel(lp, g["act_log_probs"]) < TOL[0] and rel(pr, g["act_probs"]) < TOL[0]
+    assert rel(x, g["act_em_feats"]) < TOL[0] and x.shape[1] == 297
     v, lp, ent, _, x = p.evaluate_actions(o, h, d(g["prev_actions"]), d(g["masks"]), d(g["action"]), d(g["em"]),
                                           d(g["em_masks"]))
-    assert rel(v, g["eval_value"]) < TOL and rel(lp, g["eval_log_probs"]) < TOL and rel(x, g["eval_em_feats"]) < TOL
-    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < 1e-4
+    assert rel(v, g["eval_value"]) < TOL[0] and rel(lp, g["eval_log_probs"]) < TOL[0] and rel(x, g["eval_em_feats"]) < TOL[0]
+    assert abs(float(ent.detach()) - float(g["eval_entropy"])) < ENT_TOL[0]
+
+
+def test_audiogoal_cuda_matches_reference_golden():
+    """Row A: the batched CUDA renderer against the outputs of the UNMODIFIED ``SoundSpacesSim._compute_audiogoal``
+    (soundspaces/simulator.py:644-699; tests/golden/make_golden.py:audiogoal): all three clip branches, the distractor
+    sum, an empty RIR file and the silent frame in ONE launch.  fp32 FFT convolution: 1e-3 of the output range
+    (north_star); silent / empty-RIR rows must be exact zeros (Appendix B.13)."""
+    from avlen_b200.audio import AudioRenderer
+    from oracle import audio_np as A
+    from tests._audio_helpers import GOLDEN_AUDIO_CASES, GOLDEN_AUDIO_SR, golden_audio_inputs
+    g = load("audiogoal.npz")
+    sr = GOLDEN_AUDIO_SR
+    sounds, rirs, clip_off, index, rir_off, rir_len, silent, d_clip_off, d_rir_off, d_rir_len = [], [], [], [], [], [], [], [], [], []
+    s_at = r_at = 0
+
+    def add_sound(x):
+        nonlocal s_at
+        sounds.append(x)
+        s_at += len(x)
+        return s_at - len(x)
+
+    def add_rir(h):
+        nonlocal r_at
+        rirs.append(h)
+        r_at += len(h)
+        return r_at - len(h)
+
+    silence = add_sound(np.zeros(sr, np.float32))
+    for ci, (name, secs, idx, L, Ld) in enumerate(GOLDEN_AUDIO_CASES):
+        src, rir, d_src, d_rir = golden_audio_inputs(ci)
+        clip_off.append(add_sound(src)); index.append(idx); rir_off.append(add_rir(rir)); rir_len.append(L); silent.append(0)
+        d_clip_off.append(add_sound(d_src) if d_src is not None else silence)
+        d_rir_off.append(add_rir(d_rir) if d_rir is not None else 0)
+        d_rir_len.append(Ld)
+    src, rir, _, _ = golden_audio_inputs(1)
+    base = add_sound(src)
+    for sil, L in ((0, 0), (1, len(rir))):  # empty RIR file ; silent frame
+        clip_off.append(base); index.append(1); rir_off.append(add_rir(rir)); rir_len.append(L); silent.append(sil)
+        d_clip_off.append(silence); d_rir_off.append(0); d_rir_len.append(0)
+    r = AudioRenderer(sr)
+    i64, i32 = torch.int64, torch.int32
+    ag, sp = r.render(d(np.concatenate(sounds)), torch.tensor(clip_off, dtype=i64).cuda(), torch.tensor(index, dtype=i32).cuda(),
+                      d(np.concatenate(rirs, 0)), torch.tensor(rir_off, dtype=i64).cuda(), torch.tensor(rir_len, dtype=i32).cuda(),
+                      torch.tensor(silent, dtype=i32).cuda(), torch.tensor(d_clip_off, dtype=i64).cuda(),
+                      torch.tensor(d_rir_off, dtype=i64).cuda(), torch.tensor(d_rir_len, dtype=i32).cuda())
+    torch.cuda.synchronize()
+    ag, sp = ag.cpu().numpy(), sp.cpu().numpy()
+    for ci, (name, *_rest) in enumerate(GOLDEN_AUDIO_CASES):
+        want = g[name]
+        assert np.abs(ag[ci] - want).max() <= 1e-3 * np.abs(want).max(), name
+        sp_want = A.compute_spectrogram(want)  # restated librosa / skimage (parity unpinned at that boundary)
+        assert np.abs(sp[ci] - sp_want).max() <= 1e-3 * max(1.0, np.abs(sp_want).max()), name
+    n = len(GOLDEN_AUDIO_CASES)
+    assert np.all(ag[n:] == 0.0) and np.all(sp[n:] == 0.0)
+    r.close()

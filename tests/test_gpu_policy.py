@@ -202,3 +202,38 @@ def test_rollout_and_ppo_update_match_oracle():
         assert float((d_mine - d_ref).abs().max()) < 0.15 * 2.5e-4 * 2 + 1e-7, k
     rs.after_update()
     assert rs.step == 0
+
+
+def test_option_policy_never_trains_its_encoders():
+    """ADVICE r1 / policy.py:1034-1036: pi_q concatenates its feature row under no_grad, so with freeze_encoders False
+    (all savi_interactive yamls) its encoders still receive no gradient, PPO.update leaves them bit-identical, and the
+    outputs equal the frozen policy's."""
+    from avlen_b200.common import spaces
+    from avlen_b200.savi.ppo.policy import AudioNavOptionPolicy
+    kw = dict(hidden_size=256, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu",
+              pretraining=False)
+    o = OM.AudioNavOptionPolicy()
+    sd = OM.seeded_state_dict(o, 6)
+    p = AudioNavOptionPolicy(spaces.savi_observation_space(), spaces.Discrete(4), **kw)
+    p.load_state_dict(sd)
+    p = p.cuda()  # encoders NOT frozen
+    n, M = 4, 40
+    obs = cu(make_obs(n, 21))
+    mem, masks = make_memory(M, n, 308, 22)
+    mem[..., 272:276] = mem[..., 304:308]
+    g = torch.Generator().manual_seed(3)
+    qs, lq = torch.randn(n, 32, generator=g).cuda(), torch.randn(n, 32, generator=g).cuda()
+    pa = torch.randint(0, 4, (n, 1), generator=g).cuda()
+    h = torch.zeros(1, n, 512, device="cuda")
+    logits, value, unct = p.evaluate_heads("option", obs, h, pa, None, mem.cuda(), masks.cuda(), qs, lq)
+    (logits.sum() + value.sum() + unct.sum()).backward()
+    for enc in (p.net.visual_encoder, p.net.goal_encoder, p.net.action_encoder):
+        for q in enc.parameters():
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0
+    assert float(p.net.smt_state_encoder.fusion_encoder[0].weight.grad.abs().max()) > 0
+    o.load_state_dict(sd)
+    o.eval()
+    with torch.no_grad():
+        want = o.evaluate_actions_option({k: v.cpu() for k, v in obs.items()}, h.cpu(), pa.cpu(), None,
+                                         torch.zeros(n, 1).long(), mem, masks, qs.cpu(), lq.cpu())
+    assert rel(value.detach().cpu(), want[0]) < TOL and rel(unct.detach().cpu(), want[1]) < TOL

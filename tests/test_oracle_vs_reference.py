@@ -134,6 +134,14 @@ def test_option_policy_matches_reference():
     m = mine.evaluate_actions_option(obs, h, pa, mk, act, em, emm, qs, lq)
     for i in (0, 1, 2, 3, 5, 6):  # value, unct, log_probs, entropy, em_feats, probs
         assert torch.allclose(r[i], m[i], atol=1e-6), i
+    # policy.py:1034-1036 builds x_query under no_grad: pi_q's encoders receive NO gradient even with freeze_encoders
+    # False (every savi_interactive yaml) — in the reference and in the port alike
+    for pol_ in (ref, mine):
+        out = pol_.evaluate_actions_option(obs, h, pa, mk, act, em, emm, qs, lq)
+        (out[0].sum() + out[1].sum() + out[2].sum() + out[3]).backward()
+        for enc in (pol_.net.visual_encoder, pol_.net.goal_encoder, pol_.net.action_encoder):
+            assert all(q.grad is None for q in enc.parameters())
+        assert pol_.net.smt_state_encoder.fusion_encoder[0].weight.grad is not None
     with torch.no_grad():
         r = ref.act_option(obs, h, pa, mk, em, emm, qs, lq, deterministic=True)
         m = mine.act_option(obs, h, pa, mk, em, emm, qs, lq, uniforms=None)
