@@ -41,6 +41,15 @@
 #ifndef AVL_HOST_EMUL
 namespace {
 
+// Round-to-nearest conversion that SATURATES to +-65504 instead of producing inf (fp16 has a 5-bit exponent; the
+// GroupNorm that consumes the tensor flags saturated values, gn_cluster.cu g_f16_overflow).
+__device__ __forceinline__ __half2 floats2half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+
+
 constexpr int HL_TILE = 128;
 constexpr int HL_MAX_MMA = 256;   // MMAs per tile: KH * KW * C / 8 (C == 4: KH * ceil(KW / 2))
 constexpr int HL_PARAM_MMA = 96;  // descriptor increments of up to this many MMAs travel in kernel-parameter (constant) space
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
             if (OUT16) {  // 16 channels = 32 bytes of fp16 (rows are 16-byte aligned: checked by the host)
               __half2 h[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+              for (int j = 0; j < 8; ++j) h[j] = floats2half2_sat(o[2 * j], o[2 * j + 1]);
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + pix * p.ldy + c0);
               dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
               dst[1] = *reinterpret_cast<const uint4*>(&h[4]);

@@ -17,6 +17,11 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// fp16 storage guard: the convolution that produced an fp16 tensor SATURATES to +-65504 instead of overflowing to inf
+// (conv_halo_tc.cu); this kernel reads every element of such a tensor anyway and raises a sticky flag when it meets a
+// saturated value, so that the host can fall back to fp32 storage (avl_f16_overflow, nn.check_f16_overflow).
+__device__ int g_f16_overflow = 0;
+
 constexpr int GNC_THREADS = 256;
 constexpr int GNC_MAX_SLICE = 48 * 1024;  // bytes of one CTA's slice (dynamic shared memory)
 
@@ -71,11 +76,14 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const void* __r
 
   // ---- pass over HBM: stage + per-thread sums (a thread always sees the same 4 channels: nq divides the stride)
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  unsigned sat = 0u;
   for (int i = tid; i < n4; i += GNC_THREADS) {
     float4 v;
     if (IN16) {
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(x) + base4 + i);
       tile16[i] = u;
+      // |h| >= 65504 (0x7BFF): a saturated (or non-finite) fp16 value
+      sat |= __vcmpgeu2(u.x & 0x7fff7fffu, 0x7bff7bffu) | __vcmpgeu2(u.y & 0x7fff7fffu, 0x7bff7bffu);
       v = gn_cvt4(u);
     } else {
       v = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
@@ -84,6 +92,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const void* __r
     s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1); q2 = fmaf(v.z, v.z, q2); q3 = fmaf(v.w, v.w, q3);
   }
+  if (IN16 && sat) atomicOr(&g_f16_overflow, 1);
   // lanes that share a channel quad inside the warp (nq < 32) combine first
   for (int o = 16; o >= nq && o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -201,6 +210,17 @@ int avl_groupnorm_cluster_typed(const void* x, int in16, const float* gamma, con
   AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, residual, y, HW, C, groups, eps, relu, cl, pix_per_cta));
   avl_count_launch();
   return AVL_OK;
+}
+
+// 1 if an fp16-stored activation tensor saturated since the last reset (synchronises the device).
+AVL_API int avl_f16_overflow(int reset) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_f16_overflow, sizeof(int)) != cudaSuccess) return AVL_ERR_CUDA;
+  if (reset && v) {
+    const int z = 0;
+    if (cudaMemcpyToSymbol(g_f16_overflow, &z, sizeof(int)) != cudaSuccess) return AVL_ERR_CUDA;
+  }
+  return v;
 }
 
 AVL_API int avl_groupnorm_fwd_cluster(const float* x, const float* gamma, const float* beta, const float* residual,

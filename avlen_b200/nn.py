@@ -62,6 +62,7 @@ _lib.register({
     "avl_gru_forward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_resnet_graph_stats": [I],
+    "avl_f16_overflow": [I],
 }, {"avl_gru_workspace_bytes": c_longlong, "avl_resnet18_workspace_bytes": c_longlong,
     "avl_resnet_graph_stats": c_longlong})
 
@@ -122,6 +123,26 @@ def set_f16_activations(on: bool) -> bool:
     """fp16 storage of the fused GroupNorm ResNet-18's stem output and stage 1 (tensor-core path).  Returns the old
     setting."""
     return bool(_lib.lib().avl_set_f16_activations(int(bool(on))))
+
+
+def f16_overflow(reset: bool = False) -> bool:
+    """True if an fp16-stored activation saturated (|v| >= 65504) since the last reset.  Synchronises the device."""
+    v = int(_lib.lib().avl_f16_overflow(int(bool(reset))))
+    if v < 0:
+        _lib.check(v, "avl_f16_overflow")
+    return bool(v)
+
+
+def check_f16_overflow() -> bool:
+    """Call at a point where the host synchronises anyway (end of a PPO update): if an fp16-stored activation of the
+    fused ResNet-18s saturated, switch the activation storage back to fp32 for the rest of the run and say so."""
+    if not f16_overflow(reset=True):
+        return False
+    set_f16_activations(False)
+    import warnings
+    warnings.warn("avlen_b200: an fp16-stored encoder activation saturated (|v| >= 65504); activation storage falls "
+                  "back to fp32 from here on (results since the last check used clamped values)", RuntimeWarning)
+    return True
 
 
 def tensor_cores_level() -> int:

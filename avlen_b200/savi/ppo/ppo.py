@@ -9,6 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ... import nn as K
 from ... import ops
 
 EPS_PPO = 1e-5
@@ -111,6 +112,7 @@ class PPO(nn.Module):
             sums += out
             n_updates += 1
         s = (sums / max(1, n_updates)).tolist()  # the only host synchronisation of the update
+        K.check_f16_overflow()  # (device already idle) fp16 activation storage guard, nn.check_f16_overflow
         value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]
         # the reference returns the *sums* of the two debug means (ppo.py:279-280, :289)
         return value_loss, action_loss, entropy, s[5] * n_updates, s[6] * n_updates, unct_loss

@@ -188,6 +188,10 @@ int avl_set_wgrad_desc(int lbo_bytes, int sbo_bytes);   /* diagnostic */
  * entries below expose the kernels for tests / benches: x (and w, packed (Cout,KH,KW,C)) fp16 when in16, y fp16 when
  * out16; stride 1, pad = K/2.  -2: shape not covered.                                                             */
 int avl_set_f16_activations(int on);   /* returns old */
+/* fp16 has a 5-bit exponent: the convolutions that write fp16 saturate to +-65504 (never inf) and the GroupNorm that
+ * reads the tensor raises a sticky flag when it meets a saturated value.  Returns 1 if that happened since the last
+ * reset (synchronises the device; the host then falls back to fp32 storage).                                       */
+int avl_f16_overflow(int reset);
 /* Whole-network calls (avl_resnet18_forward / _pair) at batch <= 512 whose arguments repeat are captured into a CUDA
  * graph the second time they are seen and replayed afterwards (1 graph launch instead of ~50-100 kernel launches).  */
 int avl_set_resnet_graphs(int on);     /* returns old */

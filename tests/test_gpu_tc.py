@@ -359,6 +359,49 @@ def test_fused_resnet_fp16_stage1_matches_fp32_storage(shape):
     assert not torch.equal(outs[1], outs[0])   # the fp16 path really ran
 
 
+@pytest.mark.parametrize("scale", [100.0, 3000.0])
+def test_fused_resnet_fp16_storage_does_not_saturate(scale):
+    """fp16 has a 5-bit exponent: pre-GroupNorm convolution outputs of a checkpoint whose weights are much larger than
+    the seeded initialisation (here: every conv weight x ``scale``, which GroupNorm cancels exactly in real arithmetic)
+    must neither overflow to inf / NaN nor lose the result — the fp16-storage path has to agree with fp32 storage."""
+    from avlen_b200 import nn as K
+    from avlen_b200.savi.models import smt_resnet
+    torch.manual_seed(4)
+    net = smt_resnet.custom_resnet18(num_input_channels=3, num_classes=64).cuda().eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data.mul_(scale)
+    for q in net.parameters():
+        q.requires_grad = False
+    x = torch.rand(6, 64, 64, 3, device="cuda") * 100.0
+    outs = []
+    K.f16_overflow(reset=True)
+    for on in (False, True):
+        old = K.set_f16_activations(on)
+        try:
+            with torch.no_grad():
+                outs.append(net(x).clone())
+        finally:
+            K.set_f16_activations(old)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1]).all()     # the conv epilogue saturates, never inf / NaN
+    if K.f16_overflow(reset=False):
+        # saturation is DETECTED (sticky flag raised by the GroupNorm that read the tensor) and the guard falls back to
+        # fp32 storage, after which the result is the fp32-storage one again
+        with pytest.warns(RuntimeWarning):
+            assert K.check_f16_overflow()
+        try:
+            with torch.no_grad():
+                again = net(x).clone()
+            assert torch.equal(again, outs[0])
+        finally:
+            K.set_f16_activations(True)
+    else:
+        assert rel(outs[1], outs[0]) < 5e-3
+    if scale >= 3000.0:
+        pass  # (whether this scale saturates depends on the seeded weights; both branches are legal)
+
+
 def test_packed_weights_follow_the_fused_adam_step():
     """The fused clip + Adam kernel writes the flattened parameters behind autograd's back; the tensor-core path caches
     packed (Cout, KH, KW, Cin) weights per weight version, so the step has to bump the versions — otherwise a trainable

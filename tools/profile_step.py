@@ -24,7 +24,10 @@ def main():
     if len(sys.argv) > 2:
         from avlen_b200 import nn as K
         K.set_tensor_cores(int(sys.argv[2]))
-    cfg = savi_config(NUM_PROCESSES=64, num_steps=steps)
+    over = {}
+    if os.environ.get("AVL_REGIME") == "trainable":  # savi_pretraining.yaml: freeze_encoders False, pretraining True
+        over = dict(freeze_encoders=False, pretraining=os.environ.get("AVL_FULL_MEMORY") != "1")
+    cfg = savi_config(NUM_PROCESSES=64, num_steps=steps, **over)
     tr = DDPPOTrainer(cfg).setup()
     tr.collect_rollout()
     tr._update_agent(cfg, tr.rollouts)
