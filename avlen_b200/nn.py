@@ -63,8 +63,12 @@ _lib.register({
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_resnet_graph_stats": [I],
     "avl_f16_overflow": [I],
+    "avl_pack_conv_weight": [P, I, I, I, I, I, I, P, P],
+    "avl_zero_upsample2": [P, P, I, I, I, I, I, I, P],
+    "avl_tc_conv2d_wgrad_workspace": [I, I, I, I, I, I, I, I, I],
+    "avl_tc_conv2d_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, P, L, P],
 }, {"avl_gru_workspace_bytes": c_longlong, "avl_resnet18_workspace_bytes": c_longlong,
-    "avl_resnet_graph_stats": c_longlong})
+    "avl_resnet_graph_stats": c_longlong, "avl_tc_conv2d_wgrad_workspace": c_longlong})
 
 _gn_scratch = {}
 _gn_cluster = [True]
@@ -153,10 +157,13 @@ def tensor_cores_enabled() -> bool:
     return tensor_cores_level() >= 1
 
 
-def _packed_weight(w, c_pad=None):
+def _packed_weight(w, c_pad=None, dgrad=False):
     """(Cout, C, KH, KW) -> (Cout, KH, KW, Cp) K-contiguous copy for the tensor-core path (input channels zero-padded
-    to ``c_pad``), cached ON the owning parameter object per weight version (a cache keyed by address would hand a
-    new module, allocated where a freed one lived, the old module's weights)."""
+    to ``c_pad``), rounded to nearest onto the TF32 grid, written by ONE kernel (csrc/conv_bwd_tc.cu
+    ``avl_pack_conv_weight``; no ATen permute / pad / bit-twiddling launches).  ``dgrad=True``: the weight of the
+    data-gradient convolution instead, (C, KH, KW, Coutp) with both kernel axes flipped and the channel roles swapped
+    (``c_pad`` then pads Cout).  Cached ON the owning parameter object per weight version (a cache keyed by address
+    would hand a new module, allocated where a freed one lived, the old module's weights)."""
     owner = w._base if w._base is not None else w
     cache = getattr(owner, "_avl_packed", None)
     if cache is None:
@@ -165,17 +172,21 @@ def _packed_weight(w, c_pad=None):
             owner._avl_packed = cache
         except AttributeError:
             pass
-    key = (tuple(w.shape), c_pad, w.data_ptr())
+    key = (tuple(w.shape), c_pad, w.data_ptr(), bool(dgrad))
     hit = cache.get(key)
     if hit is not None and hit[0] == w._version:
         return hit[1]
-    pk = w.detach().permute(0, 2, 3, 1)
-    if c_pad is not None and c_pad != w.shape[1]:
-        pk = torch.nn.functional.pad(pk, (0, c_pad - w.shape[1]))
-    pk = pk.contiguous()
-    if pk.data_ptr() == w.data_ptr():  # 1x1 kernels: the permuted view is already contiguous -> never round the parameter
-        pk = pk.clone()
-    pk = round_to_tf32(pk)
+    Cout, C, KH, KW = w.shape
+    wc = w.detach()
+    if not wc.is_contiguous():
+        wc = wc.contiguous()
+    if dgrad:
+        cp = Cout if c_pad is None else c_pad
+        pk = torch.empty((C, KH, KW, cp), device=w.device, dtype=torch.float32)
+    else:
+        cp = C if c_pad is None else c_pad
+        pk = torch.empty((Cout, KH, KW, cp), device=w.device, dtype=torch.float32)
+    call("avl_pack_conv_weight", fptr(wc), Cout, C, KH, KW, cp, int(bool(dgrad)), fptr(pk), stream())
     cache[key] = (w._version, pk)
     return pk
 
@@ -245,12 +256,89 @@ def _conv2d_raw(x, w, bias=None, stride=1, pad=0, relu=False, scale=None, residu
     return out
 
 
+def _conv2d_packed(x, pk, KH, KW, stride, pad, out=None):
+    """Tensor-core convolution with an already packed (Cout, KH, KW, C) weight (no bias / activation)."""
+    N, H, W, C = x.shape
+    Cout = pk.shape[0]
+    OH, OW = conv_out(H, KH, stride, pad), conv_out(W, KW, stride, pad)
+    if out is None:
+        out = torch.empty((N, OH, OW, Cout), device=x.device, dtype=torch.float32)
+    call("avl_tc_conv2d_fwd", fptr(x), N, H, W, C, fptr(pk), Cout, KH, KW, stride, pad, None, None, None, 0, 0,
+         out.data_ptr(), Cout, stream())
+    return out
+
+
+_wgrad_ws = {}
+_tc_backward = [True]
+
+
+def set_tc_backward(on) -> bool:
+    """Tensor-core data / weight gradients of the convolutions (csrc/conv_bwd_tc.cu) on / off (off: fp32 SIMT kernels
+    of csrc/nn_bwd.cu).  Returns the previous setting."""
+    old = _tc_backward[0]
+    _tc_backward[0] = bool(on)
+    return old
+
+
+def zero_upsample2(gy, H, W):
+    """(N, OH, OW, C) -> (N, H, W, C) with gy at the even positions and zeros elsewhere (stride-2 data gradients)."""
+    N, OH, OW, C = gy.shape
+    up = torch.empty((N, H, W, C), device=gy.device, dtype=torch.float32)
+    call("avl_zero_upsample2", fptr(gy), fptr(up), N, OH, OW, C, H, W, stream())
+    return up
+
+
+def conv2d_dgrad_tc(gy, w, H, W, stride, pad):
+    """dx (N, H, W, C) of y = conv(x, w, stride, pad) on the forward tensor-core kernels: a stride-1 convolution of gy
+    (zero-upsampled when the forward stride was 2) with the flipped, channel-transposed weight.  Returns None when
+    the shape is not covered."""
+    Cout, C, KH, KW = w.shape
+    if stride not in (1, 2) or Cout % 4 or pad > KH - 1 or pad > KW - 1:
+        return None
+    cp = (C + 3) // 4 * 4
+    pk = _packed_weight(w, Cout, dgrad=True)  # (C, KH, KW, Cout)
+    if cp != C:  # the result is cropped below; pad the packed rows instead of the activations
+        pk = torch.nn.functional.pad(pk, (0, 0, 0, 0, 0, 0, 0, cp - C))
+    if stride == 1:
+        gx = _conv2d_packed(gy, pk, KH, KW, 1, KH - 1 - pad)
+    elif KH == 1 and KW == 1:
+        gx = zero_upsample2(_conv2d_packed(gy, pk, 1, 1, 1, 0), H, W)
+    else:
+        up = zero_upsample2(gy, H - KH + 1 + 2 * pad, W - KW + 1 + 2 * pad)
+        gx = _conv2d_packed(up, pk, KH, KW, 1, KH - 1 - pad)
+    assert gx.shape[1] == H and gx.shape[2] == W, (gx.shape, H, W)
+    return gx if cp == C else gx[..., :C].contiguous()
+
+
+def conv2d_wgrad_tc(x, gy, w_shape, stride, pad):
+    """dw (Cout, Cw, KH, KW) on the tensor cores (csrc/conv_bwd_tc.cu); None when the shape is not covered."""
+    N, H, W, Cx = x.shape
+    Cout, Cw, KH, KW = w_shape
+    need = int(_lib.lib().avl_tc_conv2d_wgrad_workspace(N, H, W, Cx, Cout, KH, KW, stride, pad))
+    if need < 0:
+        return None
+    ws = _wgrad_ws.get(x.device)
+    if ws is None or ws.numel() < need:
+        ws = _wgrad_ws[x.device] = torch.empty(max(need, 1 << 20), device=x.device, dtype=torch.float32)
+    gw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().avl_tc_conv2d_wgrad(fptr(x), fptr(gy), fptr(gw), N, H, W, Cx, Cw, Cout, KH, KW, stride, pad,
+                                        ws.data_ptr(), ws.numel(), stream())
+    if rc == -2:
+        return None
+    _lib.check(rc, "avl_tc_conv2d_wgrad")
+    return gw
+
+
 class _ConvFn(torch.autograd.Function):
-    """conv2d (+bias, +ReLU) with dgrad / wgrad on the hand-written kernels (csrc/nn_bwd.cu)."""
+    """conv2d (+bias, +ReLU).  Backward: data gradient = a forward tensor-core convolution with the flipped weight,
+    weight gradient = the strip-staged TF32 kernel of csrc/conv_bwd_tc.cu; shapes they do not cover (and
+    ``set_tensor_cores(0)``) use the fp32 SIMT kernels of csrc/nn_bwd.cu."""
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, pad, relu):
         x = x.contiguous()
+        if tensor_cores_enabled() and x.shape[-1] % 4:  # save the channel-padded input: the weight gradient reads it
+            x = pad_channels(x, (x.shape[-1] + 3) // 4 * 4)
         y = _conv2d_raw(x, w, bias, stride, pad, relu)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.cfg = (stride, pad, relu, bias is not None)
@@ -266,18 +354,85 @@ class _ConvFn(torch.autograd.Function):
         if relu:
             gy = gy.clone()
             call("avl_relu_mask", fptr(gy), Cout, fptr(y), Cout, gy.numel() // Cout, Cout, stream())
+        tc = _tc_backward[0] and tensor_cores_enabled() and gy.data_ptr() % 16 == 0
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            call("avl_conv2d_dgrad", fptr(gy), fptr(w.contiguous()), fptr(gx), N, H, W, C, Cout, KH, KW, stride, pad, 0,
-                 stream())
+            if tc and C == Cw and N * H * W >= _tc_min_rows[0]:
+                gx = conv2d_dgrad_tc(gy, w, H, W, stride, pad)
+            if gx is None:  # (a channel-padded input gets the gradient of its Cw real channels)
+                gx = torch.empty((N, H, W, Cw), device=x.device, dtype=torch.float32)
+                call("avl_conv2d_dgrad", fptr(gy), fptr(w.contiguous()), fptr(gx), N, H, W, Cw, Cout, KH, KW, stride, pad,
+                     0, stream())
         need_w, need_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
-        if need_w or need_b:
-            gw = torch.zeros_like(w, memory_format=torch.contiguous_format) if need_w else None
-            gb = torch.zeros(Cout, device=x.device, dtype=torch.float32) if need_b else None
-            call("avl_conv2d_wgrad", fptr(x), fptr(gy), fptr(gw), fptr(gb), N, H, W, C, Cout, KH, KW, stride, pad,
-                 stream())
+        if need_w and tc:
+            gw = conv2d_wgrad_tc(x, gy, tuple(w.shape), stride, pad)
+            if gw is not None and need_b:
+                gb = gy.reshape(-1, Cout).sum(0)
+                need_b = False
+        if (need_w and gw is None) or need_b:
+            xs = x if C == Cw else x[..., :Cw].contiguous()
+            gw_ = torch.zeros_like(w, memory_format=torch.contiguous_format) if (need_w and gw is None) else None
+            gb = torch.zeros(Cout, device=x.device, dtype=torch.float32) if need_b else gb
+            call("avl_conv2d_wgrad", fptr(xs), fptr(gy), fptr(gw_), fptr(gb) if need_b else None, N, H, W, Cw, Cout, KH,
+                 KW, stride, pad, stream())
+            if gw is None:
+                gw = gw_
         return gx, gw, gb, None, None, None
+
+
+class _LinearFlatFn(torch.autograd.Function):
+    """nn.Linear over the NCHW-flattened map, computed from the NHWC tensor (forward: a convolution whose kernel covers
+    the whole map).  Backward as two dense products on the (O, H, W, C)-ordered weight: dx = dy @ Wp (3xTF32 tcgen05
+    GEMM), dWp = dy^T @ x_flat (``avl_tc_wgrad_3x``), permuted back to the reference's (O, C*H*W) order."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        O = w.shape[0]
+        y = _conv2d_raw(x, w.view(O, C, H, W), bias, 1, 0, relu).view(N, O)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.cfg = (relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        relu, has_bias = ctx.cfg
+        N, H, W, C = x.shape
+        O, K = w.shape[0], H * W * C
+        gy = gy.contiguous()
+        if relu:
+            gy = gy.clone()
+            call("avl_relu_mask", fptr(gy), O, fptr(y), O, N, O, stream())
+        gx = gw = gb = None
+        wp = None
+        if ctx.needs_input_grad[0]:
+            wp = w.detach().view(O, C, H, W).permute(0, 2, 3, 1).contiguous().view(O, K)  # (O, HWC), exact fp32
+            gx = torch.empty((N, K), device=x.device, dtype=torch.float32)
+            rc = -2
+            if tensor_cores_enabled() and N >= 512:
+                rc = _lib.lib().avl_tc_gemm_3x(fptr(gy), O, fptr(wp), K, 1, fptr(gx), K, N, K, O, None, None, 0, 0, None,
+                                               stream())
+                if rc not in (0, -2):
+                    _lib.check(rc, "avl_tc_gemm_3x")
+            if rc == -2:
+                call("avl_gemm", fptr(gy), O, 1, fptr(wp), 1, K, fptr(gx), K, N, K, O, None, 0, 0, 1, stream())
+            gx = gx.view(N, H, W, C)
+        if ctx.needs_input_grad[1]:
+            gwp = torch.zeros((O, K), device=x.device, dtype=torch.float32)
+            xf = x.view(N, K)
+            rc = -2
+            if tensor_cores_enabled() and N >= 512:
+                rc = _lib.lib().avl_tc_wgrad_3x(fptr(gy), O, fptr(xf), K, fptr(gwp), K, N, O, K, None, stream())
+                if rc not in (0, -2):
+                    _lib.check(rc, "avl_tc_wgrad_3x")
+            if rc == -2:
+                call("avl_gemm", fptr(gy), 1, O, fptr(xf), 1, K, fptr(gwp), K, O, K, N, None, 0, 0, 1, stream())
+            gw = gwp.view(O, H, W, C).permute(0, 3, 1, 2).reshape(O, K)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb, None
 
 
 class _GroupNormFn(torch.autograd.Function):
@@ -310,7 +465,7 @@ def linear_flat(x_nhwc, w, bias=None, relu=False, out=None):
     N, H, W, C = x_nhwc.shape
     O = w.shape[0]
     if _needs_grad(x_nhwc, w, bias):
-        return conv2d(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu).view(N, O)
+        return _LinearFlatFn.apply(x_nhwc, w, bias, bool(relu))
     y = _conv2d_raw(x_nhwc, w.view(O, C, H, W), bias, 1, 0, relu, out=out)
     return y.view(N, O) if out is None else out
 

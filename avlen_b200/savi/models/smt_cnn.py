@@ -48,8 +48,9 @@ class SMTCNN(nn.Module):
         n = observations[self.input_modalities[0]].shape[0]
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             feats = []
+            pad = 4 if K.tensor_cores_enabled() else None  # 16-byte channel rows for the tensor-core loaders
             for name in self.input_modalities:
-                x = K.resize_half(observations[name].contiguous(), 1.0 / 255.0 if name == "rgb" else 1.0, None)
+                x = K.resize_half(observations[name].contiguous(), 1.0 / 255.0 if name == "rgb" else 1.0, pad)
                 feats.append(getattr(self, name + "_encoder")(x))
             return torch.cat(feats, dim=1)
         if out is None:

@@ -236,6 +236,21 @@ int avl_conv2d_dgrad(const float* dy, const float* w_oihw, float* dx, int N, int
                      int KW, int stride, int pad, int accumulate, void* stream);
 int avl_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, int N, int H, int W, int C, int Cout,
                      int KH, int KW, int stride, int pad, void* stream);
+/* Tensor-core backward of the convolutions (csrc/conv_bwd_tc.cu; replaces autograd of nn.Conv2d in the trainable-encoder
+ * regime: smt_resnet.py:132-149 under savi_pretraining.yaml:53).
+ *   avl_pack_conv_weight : OIHW weight -> (Cout, KH, KW, pad_to) [mode 0, forward] or the flipped / channel-transposed
+ *                          (C, KH, KW, pad_to) weight of the data-gradient convolution [mode 1], TF32-rounded, one launch;
+ *   avl_zero_upsample2   : (N, OH, OW, C) -> (N, H, W, C), values at the even positions (stride-2 data gradients: dx is
+ *                          then a stride-1 avl_tc_conv2d_fwd with the mode-1 weight);
+ *   avl_tc_conv2d_wgrad  : dw (Cout, Cw, KH, KW) = sum_{n,oh,ow} dy x x, x (N, H, W, Cx) with Cx == 4 or Cx % 8 == 0 and
+ *                          Cx >= Cw, Cout % 16 == 0, stride 1 or 2; TF32 mma, fp32 accumulate, deterministic;
+ *                          workspace floats from avl_tc_conv2d_wgrad_workspace (-2: shape not covered).                 */
+int avl_pack_conv_weight(const float* w_oihw, int Cout, int C, int KH, int KW, int pad_to, int mode, float* out,
+                         void* stream);
+int avl_zero_upsample2(const float* dy, float* up, int N, int OH, int OW, int C, int H, int W, void* stream);
+long long avl_tc_conv2d_wgrad_workspace(int N, int H, int W, int Cx, int Cout, int KH, int KW, int stride, int pad);
+int avl_tc_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cx, int Cw, int Cout, int KH,
+                        int KW, int stride, int pad, float* workspace, long long ws_floats, void* stream);
 int avl_relu_mask(float* dy, long long ldd, const float* y, long long ldy, long long rows, int cols, void* stream);
 int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const float* gamma, float* dx, float* dres,
                       float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
