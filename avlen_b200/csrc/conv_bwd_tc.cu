@@ -143,8 +143,13 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   const int xc4 = p.Cx >> 2, dc4 = p.Cout >> 2;
   const int strip_px = p.R * p.OW;
   const int nsteps = (strip_px + 7) >> 3;
-  const int x_chunks = p.in_rows * p.Wp * xc4;
+  int xc4_shift = -1;  // log2(Cx / 4) when it is a power of two (every ResNet width), else divide
+  for (int k = 0; k < 10; ++k)
+    if ((1 << k) == xc4) xc4_shift = k;
   const int d_chunks = nsteps * 8 * dc4;
+  int dc4_shift = -1;
+  for (int k = 0; k < 10; ++k)
+    if ((1 << k) == dc4) dc4_shift = k;
   const uint32_t sx_u = smem_u32(Sx), sd_u = smem_u32(Sd);
 
   for (long long item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -152,16 +157,22 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
     const int oh0 = (int)(item - (long long)n * p.strips_per_img) * p.R;
     // ---- stage the x strip (zero halo) and the dy strip (zero rows beyond the image / the last k-step)
     const int ih0 = oh0 * p.stride - p.pad;
-    for (int c = tid; c < x_chunks; c += blockDim.x) {
-      const int pix = c / xc4, k4 = c - pix * xc4;
-      const int row = pix / p.Wp, col = pix - row * p.Wp;
-      const int ih = ih0 + row, iw = col - p.pad;
-      const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-      const float* src = ok ? p.x + (((long long)n * p.H + ih) * p.W + iw) * p.Cx + k4 * 4 : p.x;
-      cp_async16(sx_u + (uint32_t)(pix * p.xpitch + k4 * 4) * 4u, src, ok ? 16u : 0u);
+    const int row_chunks = p.Wp * xc4;  // 16-byte chunks of one staged row (halo pixels included)
+    for (int row = 0; row < p.in_rows; ++row) {
+      const int ih = ih0 + row;
+      const bool row_ok = ih >= 0 && ih < p.H;
+      const float* grow = p.x + (((long long)n * p.H + (row_ok ? ih : 0)) * p.W - p.pad) * p.Cx;  // pixel col -> iw = col - pad
+      const uint32_t srow = sx_u + (uint32_t)(row * p.Wp * p.xpitch) * 4u;
+      for (int c = tid; c < row_chunks; c += blockDim.x) {
+        const int col = xc4_shift >= 0 ? (c >> xc4_shift) : c / xc4, k4 = c - col * xc4;
+        const int iw = col - p.pad;
+        const bool ok = row_ok && iw >= 0 && iw < p.W;
+        cp_async16(srow + (uint32_t)(col * p.xpitch + k4 * 4) * 4u, ok ? grow + (long long)col * p.Cx + k4 * 4 : p.x,
+                   ok ? 16u : 0u);
+      }
     }
     for (int c = tid; c < d_chunks; c += blockDim.x) {
-      const int pix = c / dc4, k4 = c - pix * dc4;
+      const int pix = dc4_shift >= 0 ? (c >> dc4_shift) : c / dc4, k4 = c - pix * dc4;
       const int ohl = p.ow_shift >= 0 ? (pix >> p.ow_shift) : pix / p.OW;
       const bool ok = pix < strip_px && oh0 + ohl < p.OH;
       const float* src = ok ? p.dy + (((long long)n * p.OH + oh0) * p.OW + pix) * p.Cout + k4 * 4 : p.dy;
@@ -198,10 +209,32 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
     }
     __syncthreads();  // the strip buffers are rewritten by the next item
   }
-  if (!active) return;
-  // ---- partial sums of this warp: part[slice][co][tap][ci], slice = blockIdx.x * ps + q  (plain stores)
+  // ---- the ps warps of a group hold partial sums of the same tiles: add them through shared memory in warp order
+  // (fixed order: deterministic), then ONE slice per CTA goes to the workspace with plain stores
+  float* red = reinterpret_cast<float*>(smem_raw);  // [warp][tile][lane][4]; the strip buffers are free now
+  if (p.ps > 1) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < WG_MAX_TILES; ++i)
+        if (i < p.tpw)
+          *reinterpret_cast<float4*>(red + (((size_t)warp * p.tpw + i) * 32 + lane) * 4) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    __syncthreads();
+    if (active && q == 0) {
+#pragma unroll
+      for (int i = 0; i < WG_MAX_TILES; ++i) {
+        if (i >= p.tpw) continue;
+        for (int k = 1; k < p.ps; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(red + (((size_t)(warp + k) * p.tpw + i) * 32 + lane) * 4);
+          acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+        }
+      }
+    }
+  }
+  if (!active || q != 0) return;
   const int taps = p.KH * p.KW;
-  float* dst = p.part + ((long long)blockIdx.x * p.ps + q) * p.Cout * taps * p.Cx;
+  float* dst = p.part + (long long)blockIdx.x * p.Cout * taps * p.Cx;
 #pragma unroll
   for (int i = 0; i < WG_MAX_TILES; ++i) {
     if (i >= p.tpw) continue;
@@ -225,18 +258,25 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   }
 }
 
-// dw[co][ci][tap] (OIHW) = sum over slices, in slice order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int taps, int Cx, int Cw, float* dw) {
-  const int n = Cout * Cw * taps;
+// dw[co][ci][tap] (OIHW) = sum over slices.  A block owns 64 consecutive elements of the partial layout
+// [co][tap][Cx] (coalesced reads), its 8 thread rows take every 8th slice and the rows are added in row order:
+// the summation order is fixed by the launch shape alone (deterministic).
+__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int taps,
+                                                          int Cx, int Cw, float* dw) {
+  __shared__ float sm[8][64];
   const long long per = (long long)Cout * taps * Cx;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int tap = i % taps;
-    const int ci = (i / taps) % Cw;
-    const int co = i / (taps * Cw);
-    const float* src = part + ((long long)co * taps + tap) * Cx + ci;
-    float s = 0.f;
-    for (int k = 0; k < slices; ++k) s += src[k * per];
-    dw[i] = s;
+  const long long e = (long long)blockIdx.x * 64 + threadIdx.x;
+  float s = 0.f;
+  if (e < per)
+    for (int k = threadIdx.y; k < slices; k += 8) s += part[k * per + e];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < per) {
+    for (int k = 1; k < 8; ++k) s += sm[k][threadIdx.x];
+    const int ci = (int)(e % Cx);
+    const int tap = (int)((e / Cx) % taps);
+    const int co = (int)(e / ((long long)Cx * taps));
+    if (ci < Cw) dw[((long long)co * Cw + ci) * taps + tap] = s;
   }
 }
 
@@ -308,7 +348,9 @@ int plan_wgrad(int N, int H, int W, int Cx, int Cout, int KH, int KW, int stride
   if (gx < 1) gx = 1;
   if (gx > a.total_items) gx = a.total_items;
   pl.grid_x = (int)gx;
-  pl.ws_floats = (size_t)pl.grid_x * a.ps * Cout * KH * KW * Cx;
+  pl.ws_floats = (size_t)pl.grid_x * Cout * KH * KW * Cx;
+  const size_t red_bytes = a.ps > 1 ? (size_t)(pl.threads / 32) * a.tpw * 32 * 4 * sizeof(float) : 0;
+  if (pl.smem < red_bytes) pl.smem = red_bytes;
   return AVL_OK;
 }
 
@@ -369,9 +411,9 @@ AVL_API int avl_tc_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   pl.a.part = workspace;
   tc_conv_wgrad_kernel<<<dim3(pl.grid_x, pl.grid_y), pl.threads, pl.smem, (cudaStream_t)stream>>>(pl.a);
   AVL_LAUNCH_CHECK();
-  const int n = Cout * Cw * KH * KW;
-  wgrad_reduce_kernel<<<avl_div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(workspace, pl.grid_x * pl.a.ps, Cout, KH * KW, Cx,
-                                                                           Cw, dw);
+  const long long per = (long long)Cout * KH * KW * Cx;
+  wgrad_reduce_kernel<<<avl_div_up(per, 64), dim3(64, 8), 0, (cudaStream_t)stream>>>(workspace, pl.grid_x, Cout, KH * KW, Cx,
+                                                                                    Cw, dw);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -165,6 +165,160 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const void* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- backward, one pass
+// Forward was y = act(gn(x) * gamma + beta (+ residual)).  With g = dy * (y > 0) (ReLU) — also the gradient of the
+// residual branch — dx = rstd * (g*gamma - mean_grp(g*gamma) - xhat * mean_grp(g*gamma*xhat)).
+// Same decomposition as the forward kernel: a cluster per sample, every CTA stages its slice of x AND of g in shared
+// memory while accumulating the per-channel sums (x, x^2, g, g*x), the per-group sums cross CTAs through distributed
+// shared memory in rank order, and dx is produced from shared memory: x, dy, y are read ONCE and dx (+ dres) written
+// once (the two-pass kernel of nn_bwd.cu reads the three tensors twice).  dgamma / dbeta: per-sample partial rows
+// (plain stores), summed over samples in order by gn_param_reduce_kernel — deterministic, no atomics.
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                     const float* __restrict__ dy,
+                                                                     const float* __restrict__ gamma, float* dx, float* dres,
+                                                                     float* pgamma, float* pbeta, int HW, int C, int groups,
+                                                                     float eps, int relu, int cl, int pix_per_cta) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  __shared__ float ch[4][512];      // per-channel totals of this CTA: sum x, sum x^2, sum g, sum g*x
+  __shared__ float red[4][1024];    // per (slot, channel) partials, summed in a fixed order
+  __shared__ double part[64][4];    // per group: S, Q, sum gamma*G, sum gamma*GX   (this CTA)
+  __shared__ float g_mean[64], g_rstd[64], g_m1[64], g_m2[64];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / cl;
+  const int nq = C >> 2;
+  const int p0 = rank * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int n4 = max(0, p1 - p0) * nq;
+  const size_t base4 = ((size_t)n * HW + p0) * nq;
+  float4* tx = reinterpret_cast<float4*>(gsm);
+  float4* tg = tx + (size_t)pix_per_cta * nq;
+  float a[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[k][j] = 0.f;
+  for (int i = tid; i < n4; i += GNC_THREADS) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
+    float4 gv = __ldg(reinterpret_cast<const float4*>(dy) + base4 + i);
+    if (relu) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + base4 + i);
+      if (!(yv.x > 0.f)) gv.x = 0.f;
+      if (!(yv.y > 0.f)) gv.y = 0.f;
+      if (!(yv.z > 0.f)) gv.z = 0.f;
+      if (!(yv.w > 0.f)) gv.w = 0.f;
+    }
+    tx[i] = xv;
+    tg[i] = gv;
+    if (dres) reinterpret_cast<float4*>(dres)[base4 + i] = gv;
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[0][j] += xs[j];
+      a[1][j] = fmaf(xs[j], xs[j], a[1][j]);
+      a[2][j] += gs[j];
+      a[3][j] = fmaf(gs[j], xs[j], a[3][j]);
+    }
+  }
+  for (int o = 16; o >= nq && o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[k][j] += __shfl_xor_sync(0xffffffffu, a[k][j], o);
+  const int lane = tid & 31;
+  const int c0 = (tid % nq) * 4;
+  const int n_slots = nq < 32 ? GNC_THREADS / 32 : GNC_THREADS / nq;
+  if (nq >= 32 || lane < nq) {
+    const int slot = nq < 32 ? (tid >> 5) : tid / nq;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[k][(slot * nq + (tid % nq)) * 4 + j] = a[k][j];
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += GNC_THREADS) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float S = 0.f;
+      for (int sl = 0; sl < n_slots; ++sl) S += red[k][(sl * nq + (c >> 2)) * 4 + (c & 3)];
+      ch[k][c] = S;
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0, P1 = 0.0, P2 = 0.0;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+      const double ga = (double)__ldg(gamma + c);
+      S += (double)ch[0][c];
+      Q += (double)ch[1][c];
+      P1 += ga * (double)ch[2][c];
+      P2 += ga * (double)ch[3][c];
+    }
+    part[tid][0] = S; part[tid][1] = Q; part[tid][2] = P1; part[tid][3] = P2;
+  }
+  cluster.sync();
+  if (tid < groups) {
+    double S = 0.0, Q = 0.0, P1 = 0.0, P2 = 0.0;
+    for (int r = 0; r < cl; ++r) {
+      const double* rp = cluster.map_shared_rank(&part[0][0], r);
+      S += rp[tid * 4]; Q += rp[tid * 4 + 1]; P1 += rp[tid * 4 + 2]; P2 += rp[tid * 4 + 3];
+    }
+    const double cnt = (double)HW * cpg;
+    const double m = S / cnt;
+    double var = Q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    const double rs = 1.0 / sqrt(var + (double)eps);
+    g_mean[tid] = (float)m;
+    g_rstd[tid] = (float)rs;
+    g_m1[tid] = (float)(P1 / cnt);
+    g_m2[tid] = (float)(rs * (P2 - m * P1) / cnt);
+  }
+  __syncthreads();
+  if (rank == 0 && (pgamma || pbeta)) {  // per-sample parameter-gradient rows: channel sums over the whole cluster
+    for (int c = tid; c < C; c += GNC_THREADS) {
+      float G = 0.f, GX = 0.f;
+      for (int r = 0; r < cl; ++r) {
+        const float* rc = cluster.map_shared_rank(&ch[0][0], r);
+        G += rc[2 * 512 + c];
+        GX += rc[3 * 512 + c];
+      }
+      const int g = c / cpg;
+      if (pgamma) pgamma[(size_t)n * C + c] = g_rstd[g] * (GX - g_mean[g] * G);
+      if (pbeta) pbeta[(size_t)n * C + c] = G;
+    }
+  }
+  cluster.sync();  // no CTA may retire (or overwrite ch / part) while a peer still reads them
+  if (!dx) return;
+  float ga[4], mu[4], rs[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j, g = c / cpg;
+    ga[j] = __ldg(gamma + c);
+    mu[j] = g_mean[g]; rs[j] = g_rstd[g]; m1[j] = g_m1[g]; m2[j] = g_m2[g];
+  }
+  for (int i = tid; i < n4; i += GNC_THREADS) {
+    const float4 xv = tx[i], gv = tg[i];
+    float4 o;
+    o.x = rs[0] * (gv.x * ga[0] - m1[0] - (xv.x - mu[0]) * rs[0] * m2[0]);
+    o.y = rs[1] * (gv.y * ga[1] - m1[1] - (xv.y - mu[1]) * rs[1] * m2[1]);
+    o.z = rs[2] * (gv.z * ga[2] - m1[2] - (xv.z - mu[2]) * rs[2] * m2[2]);
+    o.w = rs[3] * (gv.w * ga[3] - m1[3] - (xv.w - mu[3]) * rs[3] * m2[3]);
+    reinterpret_cast<float4*>(dx)[base4 + i] = o;
+  }
+}
+
+// out[c] (+)= sum over the N per-sample rows, in row order (deterministic)
+__global__ void gn_param_reduce_kernel(const float* __restrict__ rows, int N, int C, float* out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += rows[(size_t)n * C + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
 }  // namespace
 
 // Returns AVL_ERR_UNSUPPORTED (nothing launched) for shapes outside this kernel: the caller falls back to the
@@ -233,5 +387,56 @@ AVL_API int avl_groupnorm_fwd_cluster_f16(const void* x, const float* gamma, con
                                           void* y, int out16, int N, int HW, int C, int groups, float eps, int relu,
                                           void* stream) {
   return avl_groupnorm_cluster_typed(x, 1, gamma, beta, residual, y, out16, N, HW, C, groups, eps, relu, stream);
+}
+
+// One-pass cluster GroupNorm backward (see gn_cluster_bwd_kernel).  dgamma / dbeta are ACCUMULATED INTO (+=), like
+// avl_groupnorm_bwd; scratch: 2 * N * C floats.  -2 (nothing launched): shape not covered -> avl_groupnorm_bwd.
+AVL_API int avl_groupnorm_bwd_cluster(const float* x, const float* y, const float* dy, const float* gamma, float* dx,
+                                      float* dres, float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps,
+                                      int relu, float* scratch, void* stream) {
+  if (N < 0 || HW < 1 || C < 1 || groups < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !dy || !gamma || (relu && !y) || ((dgamma || dbeta) && !scratch)) return AVL_ERR_ARG;
+  if ((C & 3) || C > 512 || groups > 64 || C % groups || GNC_THREADS % (C >> 2)) return AVL_ERR_UNSUPPORTED;
+  if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)y & 15) || ((uintptr_t)dx & 15) || ((uintptr_t)dres & 15))
+    return AVL_ERR_UNSUPPORTED;
+  const long long sample_bytes = (long long)HW * C * 4;
+  int cl = 1;
+  while (cl < 8 && sample_bytes / cl > 32 * 1024) cl <<= 1;
+  if (cl > HW) return AVL_ERR_UNSUPPORTED;
+  const int pix_per_cta = avl_div_up(HW, cl);
+  const size_t smem = (size_t)pix_per_cta * C * 4 * 2;  // x slice + g slice
+  if (smem > 2 * (size_t)GNC_MAX_SLICE || (long long)N * cl > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GNC_MAX_SLICE));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(N * cl));
+  cfg.blockDim = dim3(GNC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  float* pg = dgamma ? scratch : nullptr;
+  float* pb = dbeta ? scratch + (size_t)N * C : nullptr;
+  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_bwd_kernel, x, y, dy, gamma, dx, dres, pg, pb, HW, C, groups, eps, relu,
+                                    cl, pix_per_cta));
+  avl_count_launch();
+  if (dgamma) {
+    gn_param_reduce_kernel<<<avl_div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(pg, N, C, dgamma, 1);
+    AVL_LAUNCH_CHECK();
+  }
+  if (dbeta) {
+    gn_param_reduce_kernel<<<avl_div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(pb, N, C, dbeta, 1);
+    AVL_LAUNCH_CHECK();
+  }
+  return AVL_OK;
 }
 #endif  // AVL_HOST_EMUL

@@ -58,6 +58,7 @@ _lib.register({
     "avl_conv2d_wgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "avl_relu_mask": [P, L, P, L, L, I, P],
     "avl_groupnorm_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
+    "avl_groupnorm_bwd_cluster": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P, P],
     "avl_gru_workspace_bytes": [I, I, I, I, I],
     "avl_gru_forward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, I, P],
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
@@ -71,6 +72,7 @@ _lib.register({
     "avl_resnet_graph_stats": c_longlong, "avl_tc_conv2d_wgrad_workspace": c_longlong})
 
 _gn_scratch = {}
+_gn_bwd_scratch = {}
 _gn_cluster = [True]
 _tc_min_rows = [64]
 
@@ -454,8 +456,20 @@ class _GroupNormFn(torch.autograd.Function):
         gres = torch.empty_like(x) if (has_res and ctx.needs_input_grad[3]) else None
         gg = torch.zeros_like(gamma) if ctx.needs_input_grad[1] else None
         gb = torch.zeros_like(gamma) if ctx.needs_input_grad[2] else None
-        call("avl_groupnorm_bwd", fptr(x), fptr(y), fptr(gy), fptr(gamma), fptr(gx), fptr(gres), fptr(gg), fptr(gb), N,
-             H * W, C, groups, eps, int(relu), stream())
+        rc = -2
+        if _gn_cluster[0] and C % 4 == 0:
+            # one pass over HBM, deterministic parameter gradients (csrc/gn_cluster.cu gn_cluster_bwd_kernel)
+            sc = _gn_bwd_scratch.get(x.device)
+            if sc is None or sc.numel() < 2 * N * C:
+                sc = _gn_bwd_scratch[x.device] = torch.empty(max(2 * N * C, 1 << 16), device=x.device, dtype=torch.float32)
+            rc = _lib.lib().avl_groupnorm_bwd_cluster(fptr(x), fptr(y), fptr(gy), fptr(gamma), fptr(gx), fptr(gres),
+                                                      fptr(gg), fptr(gb), N, H * W, C, groups, eps, int(relu),
+                                                      sc.data_ptr(), stream())
+            if rc not in (0, -2):
+                _lib.check(rc, "avl_groupnorm_bwd_cluster")
+        if rc == -2:
+            call("avl_groupnorm_bwd", fptr(x), fptr(y), fptr(gy), fptr(gamma), fptr(gx), fptr(gres), fptr(gg), fptr(gb), N,
+                 H * W, C, groups, eps, int(relu), stream())
         return gx, gg, gb, gres, None, None, None
 
 

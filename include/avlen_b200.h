@@ -255,6 +255,12 @@ int avl_relu_mask(float* dy, long long ldd, const float* y, long long ldy, long 
 int avl_groupnorm_bwd(const float* x, const float* y, const float* dy, const float* gamma, float* dx, float* dres,
                       float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
                       void* stream);
+/* The same in ONE pass over HBM (thread-block cluster per sample, x and the masked dy staged in shared memory, group sums
+ * through distributed shared memory; per-sample parameter-gradient rows summed in order: deterministic).  dgamma / dbeta
+ * are accumulated into; scratch: 2 * N * C floats.  -2: shape not covered (use avl_groupnorm_bwd).               */
+int avl_groupnorm_bwd_cluster(const float* x, const float* y, const float* dy, const float* gamma, float* dx, float* dres,
+                              float* dgamma, float* dbeta, int N, int HW, int C, int groups, float eps, int relu,
+                              float* scratch, void* stream);
 int avl_set_tc_conv_halo(int on, int rows_per_strip); /* halo-strip kernel for stride-1 same convs; returns old */
 int avl_set_tc_tma(int on);      /* dense GEMMs: 1 TMA-fed kernel where it applies (default), 0 cp.async kernel; returns old */
 int avl_set_tc_swizzle(int on);  /* generic kernel operand tiles: 1 SWIZZLE_128B (default), 0 SWIZZLE_NONE; returns old */

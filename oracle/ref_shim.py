@@ -181,6 +181,37 @@ def load_simulator():
     return mod
 
 
+def load_trainer():
+    """The UNMODIFIED ``ss_baselines/savi/ppo/ppo_trainer.py`` as a module (for ``PPOTrainer._collect_rollout_step``,
+    :323-897, executed on a scripted stand-in for ``self`` by tests/golden/make_golden.py).  Everything it imports
+    that is absent here (matplotlib, habitat task / geometry helpers, env construction, slurm helpers, tensorboard)
+    is stubbed; ``batch_obs``, ``RolloutStorage`` and the policies it touches are the reference's own."""
+    install()
+    name = "ss_baselines.savi.ppo.ppo_trainer"
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None):
+        return sys.modules[name]
+    for mod in ("matplotlib", "matplotlib.pyplot"):
+        try:
+            importlib.import_module(mod)
+        except Exception:
+            _stub(mod)
+    _stub("habitat.tasks")
+    _stub("habitat.tasks.nav")
+    _stub("habitat.tasks.nav.nav", IntegratedPointGoalGPSAndCompassSensor=_Anything)
+    _stub("habitat.tasks.utils", cartesian_to_polar=_Anything())
+    _stub("habitat.utils.geometry_utils", quaternion_from_coeff=_Anything(), quaternion_rotate_vector=_Anything())
+    base = type("BaseRLTrainer", (), {"__init__": lambda self, config=None: setattr(self, "config", config)})
+    _stub("ss_baselines.common.base_trainer", BaseRLTrainer=base, BaseTrainer=base)
+    _stub("ss_baselines.common.env_utils", construct_envs=_Anything())
+    _stub("ss_baselines.common.environments", get_env_class=_Anything())
+    _stub("ss_baselines.savi.ppo.slurm_utils", EXIT=_Anything(), REQUEUE=_Anything(), load_interrupted_state=_Anything(),
+          requeue_job=_Anything(), save_interrupted_state=_Anything())
+    _stub("ss_baselines.savi.models.belief_predictor", BeliefPredictor=_Anything, BeliefPredictorDDP=_Anything)
+    sys.modules["habitat"].Config = _Anything
+    load("ss_baselines.common.baseline_registry")
+    return load(name)
+
+
 def spaces():
     install()
     return sys.modules["gym.spaces"]
