@@ -92,18 +92,20 @@ struct WgArgs {
   int ow_shift;      // log2(OW) or -1
 };
 
-__device__ __forceinline__ uint32_t f2tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
+// fp32 -> TF32 operand, rounded to nearest (ties away): add half an ulp of the 10-bit mantissa and let the tensor core
+// drop the low 13 bits.  One integer add per value (cvt.rna.tf32.f32 expands to a 5-instruction sequence with
+// Inf / NaN handling on sm_100a; activations and gradients are finite here).
+__device__ __forceinline__ uint32_t f2tf32(float v) { return __float_as_uint(v) + 0x1000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// NT: compile-time tile slots per warp (>= p.tpw; surplus slots recompute tile 0 into accumulators nobody stores, so
+// that the MMA loop has no per-tile branches)
+template <int NT>
 __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   AVL_DYN_SMEM(smem_raw);
   float* Sx = reinterpret_cast<float*>(smem_raw);
@@ -119,9 +121,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   const int tile0 = active ? (grp % groups_per_ct) * p.tpw : 0;
   const int co0 = ct * 16;
   const bool c4 = p.Cx == 4;
-  int toff[WG_MAX_TILES];  // float offset of tile i inside the staged x strip (tap shift + channel chunk)
+  int toff[NT];  // float offset of tile i inside the staged x strip (tap shift + channel chunk)
 #pragma unroll
-  for (int i = 0; i < WG_MAX_TILES; ++i) {
+  for (int i = 0; i < NT; ++i) {
     const int id = tile0 + (i < p.tpw ? i : 0);
     int r, s, cc;
     if (c4) {
@@ -136,9 +138,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
     }
     toff[i] = (r * p.Wp + s) * p.xpitch + cc * 8;
   }
-  float acc[WG_MAX_TILES][4];
+  float acc[NT][4];
 #pragma unroll
-  for (int i = 0; i < WG_MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
   const int xc4 = p.Cx >> 2, dc4 = p.Cout >> 2;
   const int strip_px = p.R * p.OW;
@@ -201,9 +203,18 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
         a[1] = f2tf32(da[8]);
         a[2] = f2tf32(db[0]);
         a[3] = f2tf32(db[8]);
+        // operand loads are issued in batches (2 * BT shared-memory loads in flight) ahead of their MMAs
+        constexpr int BT = (NT % 6 == 0) ? 6 : ((NT % 4 == 0) ? 4 : 2);
 #pragma unroll
-        for (int i = 0; i < WG_MAX_TILES; ++i) {
-          if (i < p.tpw) mma_tf32(acc[i], a, f2tf32(xa[toff[i]]), f2tf32(xb[toff[i]]));
+        for (int i0 = 0; i0 < NT; i0 += BT) {
+          float b0[BT], b1[BT];
+#pragma unroll
+          for (int j = 0; j < BT; ++j) {
+            b0[j] = xa[toff[i0 + j]];
+            b1[j] = xb[toff[i0 + j]];
+          }
+#pragma unroll
+          for (int j = 0; j < BT; ++j) mma_tf32(acc[i0 + j], a, f2tf32(b0[j]), f2tf32(b1[j]));
         }
       }
     }
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   if (p.ps > 1) {
     if (active) {
 #pragma unroll
-      for (int i = 0; i < WG_MAX_TILES; ++i)
+      for (int i = 0; i < NT; ++i)
         if (i < p.tpw)
           *reinterpret_cast<float4*>(red + (((size_t)warp * p.tpw + i) * 32 + lane) * 4) =
               make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
     __syncthreads();
     if (active && q == 0) {
 #pragma unroll
-      for (int i = 0; i < WG_MAX_TILES; ++i) {
+      for (int i = 0; i < NT; ++i) {
         if (i >= p.tpw) continue;
         for (int k = 1; k < p.ps; ++k) {
           const float4 v = *reinterpret_cast<const float4*>(red + (((size_t)(warp + k) * p.tpw + i) * 32 + lane) * 4);
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   const int taps = p.KH * p.KW;
   float* dst = p.part + (long long)blockIdx.x * p.Cout * taps * p.Cx;
 #pragma unroll
-  for (int i = 0; i < WG_MAX_TILES; ++i) {
+  for (int i = 0; i < NT; ++i) {
     if (i >= p.tpw) continue;
     const int id = tile0 + i;
 #pragma unroll
@@ -403,13 +414,25 @@ AVL_API int avl_tc_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256));
+    const int mx = 200 * 1024 + 256;
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_set = true;
   }
   pl.a.x = x;
   pl.a.dy = dy;
   pl.a.part = workspace;
-  tc_conv_wgrad_kernel<<<dim3(pl.grid_x, pl.grid_y), pl.threads, pl.smem, (cudaStream_t)stream>>>(pl.a);
+  const dim3 grid(pl.grid_x, pl.grid_y);
+  const cudaStream_t cs = (cudaStream_t)stream;
+  const int tpw = pl.a.tpw;
+  if (tpw > 16) tc_conv_wgrad_kernel<18><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+  else if (tpw > 8) tc_conv_wgrad_kernel<16><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+  else if (tpw > 4) tc_conv_wgrad_kernel<8><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+  else if (tpw > 2) tc_conv_wgrad_kernel<4><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+  else tc_conv_wgrad_kernel<2><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
   AVL_LAUNCH_CHECK();
   const long long per = (long long)Cout * KH * KW * Cx;
   wgrad_reduce_kernel<<<avl_div_up(per, 64), dim3(64, 8), 0, (cudaStream_t)stream>>>(workspace, pl.grid_x, Cout, KH * KW, Cx,

@@ -310,13 +310,22 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
   }
 }
 
-// out[c] (+)= sum over the N per-sample rows, in row order (deterministic)
-__global__ void gn_param_reduce_kernel(const float* __restrict__ rows, int N, int C, float* out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out[c] (+)= sum over the N per-sample rows.  Block = 32 channels x 32 row lanes: lane j adds rows j, j + 32, ... and
+// the 32 partial sums are added in lane order — the order depends on the launch shape only (deterministic).
+__global__ void __launch_bounds__(1024) gn_param_reduce_kernel(const float* __restrict__ rows, int N, int C, float* out,
+                                                                int accumulate) {
+  __shared__ float sm[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int n = 0; n < N; ++n) s += rows[(size_t)n * C + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < C)
+    for (int n = threadIdx.y; n < N; n += 32) s += rows[(size_t)n * C + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 }  // namespace
@@ -430,11 +439,11 @@ AVL_API int avl_groupnorm_bwd_cluster(const float* x, const float* y, const floa
                                     cl, pix_per_cta));
   avl_count_launch();
   if (dgamma) {
-    gn_param_reduce_kernel<<<avl_div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(pg, N, C, dgamma, 1);
+    gn_param_reduce_kernel<<<avl_div_up(C, 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(pg, N, C, dgamma, 1);
     AVL_LAUNCH_CHECK();
   }
   if (dbeta) {
-    gn_param_reduce_kernel<<<avl_div_up(C, 64), 64, 0, (cudaStream_t)stream>>>(pb, N, C, dbeta, 1);
+    gn_param_reduce_kernel<<<avl_div_up(C, 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(pb, N, C, dbeta, 1);
     AVL_LAUNCH_CHECK();
   }
   return AVL_OK;

@@ -22,8 +22,9 @@ from ...common.baseline_registry import baseline_registry
 from ...synth_env import SyntheticVectorEnv
 from ..models.belief_predictor import BeliefPredictor
 from ..models.rollout_storage import RolloutStorage
-from ..ppo.policy import AudioNavSMTPolicy
+from ..ppo.policy import AudioNavDialogPolicy, AudioNavOptionPolicy, AudioNavSMTPolicy
 from ..ppo.ppo_trainer import PPOTrainer
+from ..ppo.query_state import QueryBookkeeper
 from .ddppo import DDPPO
 
 
@@ -36,7 +37,10 @@ def savi_config(**overrides):
                num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, activation="relu", freeze_encoders=True,
                pretraining=False, use_label_belief=True, use_location_belief=True, online_training=True,
                sync_frac=0.6, distrib_backend="nccl", use_preemption=False, seed=1234, sampling_rate=16000,
-               host_buffers=False, has_distractor_sound=False, overlap_belief=True, prefetch_encoders=True)
+               host_buffers=False, has_distractor_sound=False, overlap_belief=True, prefetch_encoders=True,
+               # AVLEN interactive stages (savi_interactive_2nd_stage.yaml:19-23,:30-41; config/default.py:183-186)
+               NUM_DIALOG_STEPS=3, ORACLE_WHEN_QUERIED=True, QUERY_WITHIN_RADIUS=True, ALLOW_STOP=False,
+               CONSECUTIVE_REWARD=-0.5, NUM_TOTAL_QUERY=3, QUERY_COUNT_EMB_SIZE=32, clip_layers=12, graph_env=None)
     cfg.update(overrides)
     return types.SimpleNamespace(**cfg)
 
@@ -62,20 +66,12 @@ class DDPPOTrainer(PPOTrainer):
         self.rollouts = None
         self.world_size, self.world_rank = 1, 0
 
-    def _setup_actor_critic_agent(self, ppo_cfg, observation_space=None):
-        cfg = ppo_cfg
-        obs_space = observation_space or spaces.savi_observation_space(cfg.sampling_rate)
-        self.obs_space = obs_space
-        self.actor_critic = AudioNavSMTPolicy(
-            observation_space=obs_space, action_space=spaces.Discrete(4), hidden_size=cfg.smt_hidden_size,
-            nhead=cfg.nhead, num_encoder_layers=cfg.num_encoder_layers, num_decoder_layers=cfg.num_decoder_layers,
-            dropout=cfg.dropout, activation=cfg.activation, pretraining=cfg.pretraining,
-            use_category_input=cfg.has_distractor_sound)
-        self.actor_critic.to(self.device)
-        if cfg.freeze_encoders:
-            self.actor_critic.net.freeze_encoders()
-            self.actor_critic.net.set_eval_encoders()
-        self.actor_critic.net.smt_state_encoder.rows_per_sample_cap = cfg.memory_size + 1
+    def _policy_kwargs(self, cfg):
+        return dict(hidden_size=cfg.smt_hidden_size, nhead=cfg.nhead, num_encoder_layers=cfg.num_encoder_layers,
+                    num_decoder_layers=cfg.num_decoder_layers, dropout=cfg.dropout, activation=cfg.activation,
+                    pretraining=cfg.pretraining)
+
+    def _setup_belief_predictor(self, cfg):
         if cfg.use_belief_predictor:
             bcfg = types.SimpleNamespace(use_label_belief=cfg.use_label_belief, online_training=cfg.online_training,
                                          use_location_belief=cfg.use_location_belief, weighting_factor=0.5,
@@ -84,10 +80,61 @@ class DDPPOTrainer(PPOTrainer):
                                                     cfg.NUM_PROCESSES, cfg.has_distractor_sound).to(self.device)
             self.belief_predictor.freeze_encoders()
             self.belief_predictor.set_eval_encoders()
+
+    def _setup_actor_critic_agent(self, ppo_cfg, observation_space=None):
+        cfg = ppo_cfg
+        obs_space = observation_space or spaces.savi_observation_space(cfg.sampling_rate)
+        self.obs_space = obs_space
+        if cfg.policy_type == "interactive":
+            return self._setup_interactive(cfg, obs_space)
+        self.actor_critic = AudioNavSMTPolicy(
+            observation_space=obs_space, action_space=spaces.Discrete(4), use_category_input=cfg.has_distractor_sound,
+            **self._policy_kwargs(cfg))
+        self.actor_critic.to(self.device)
+        if cfg.freeze_encoders:
+            self.actor_critic.net.freeze_encoders()
+            self.actor_critic.net.set_eval_encoders()
+        self.actor_critic.net.smt_state_encoder.rows_per_sample_cap = cfg.memory_size + 1
+        self._setup_belief_predictor(cfg)
         self.agent = DDPPO(actor_critic=self.actor_critic, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,
                            num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
                            entropy_coef=cfg.entropy_coef, lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm,
                            use_normalized_advantage=cfg.use_normalized_advantage)
+
+    def _setup_interactive(self, cfg, obs_space):
+        """ddppo_trainer.py:301-512, ``policy_type: "interactive"``: pi_g (goal policy, every parameter frozen, :413-414),
+        pi_l (dialog policy, CLIP frozen, :400-403) and pi_q (option policy) — ``self.agent`` trains pi_q, ``agent_vln``
+        wraps pi_l for the replay / dialog updates; the sinusoidal query-count table ``pe`` (:506-512)."""
+        kw = self._policy_kwargs(cfg)
+        act = spaces.Discrete(4)
+        dis = cfg.has_distractor_sound
+        self.actor_critic_goal = AudioNavSMTPolicy(obs_space, act, use_category_input=dis, **kw).to(self.device)
+        self.actor_critic_vln = AudioNavDialogPolicy(obs_space, act, clip_layers=cfg.clip_layers, **kw).to(self.device)
+        self.actor_critic_option = AudioNavOptionPolicy(obs_space, act, use_category_input=dis, **kw).to(self.device)
+        for p in self.actor_critic_goal.parameters():
+            p.requires_grad = False
+        for name, p in self.actor_critic_vln.named_parameters():
+            if "net.clip" in name:
+                p.requires_grad = False
+        for pol in (self.actor_critic_goal, self.actor_critic_vln, self.actor_critic_option):
+            if cfg.freeze_encoders:
+                pol.net.freeze_encoders()
+            pol.net.set_eval_encoders()
+            pol.net.smt_state_encoder.rows_per_sample_cap = cfg.memory_size + 1
+        self.actor_critic = self.actor_critic_option
+        self._setup_belief_predictor(cfg)
+        mk = lambda ac, head: DDPPO(actor_critic=ac, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,  # noqa: E731
+                                    num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
+                                    entropy_coef=cfg.entropy_coef, lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm,
+                                    use_normalized_advantage=cfg.use_normalized_advantage, policy_head=head)
+        self.agent = mk(self.actor_critic_option, "option")
+        self.agent_vln = mk(self.actor_critic_vln, "goal")
+        self.query_book = QueryBookkeeper(cfg.NUM_PROCESSES, self.device, num_dialog_steps=cfg.NUM_DIALOG_STEPS,
+                                          consecutive_reward=cfg.CONSECUTIVE_REWARD,
+                                          query_within_radius=cfg.QUERY_WITHIN_RADIUS,
+                                          oracle_when_queried=cfg.ORACLE_WHEN_QUERIED, allow_stop=cfg.ALLOW_STOP,
+                                          max_dialog_len=77, emb_size=cfg.QUERY_COUNT_EMB_SIZE)
+        self.pe = self.query_book.pe
 
     def setup(self, envs=None):
         cfg = self.config
@@ -95,18 +142,39 @@ class DDPPOTrainer(PPOTrainer):
         self.device = torch.device("cuda", local_rank)
         torch.cuda.set_device(self.device)
         torch.manual_seed(cfg.seed + self.world_rank)
-        self.envs = envs or SyntheticVectorEnv(cfg.NUM_PROCESSES, self.device, seed=cfg.seed + self.world_rank,
-                                               sr=cfg.sampling_rate, host_buffers=cfg.host_buffers,
-                                               distractor=cfg.has_distractor_sound)
+        interactive = cfg.policy_type == "interactive"
+        if envs is None:
+            kw = dict(seed=cfg.seed + self.world_rank, sr=cfg.sampling_rate, host_buffers=cfg.host_buffers,
+                      distractor=cfg.has_distractor_sound)
+            if interactive or cfg.graph_env:
+                # the interactive step needs what only a navigation graph provides: oracle actions, target distance,
+                # episode boundaries, query-aware rewards (ppo_trainer.py:336-345,:642,:706-710)
+                from ...graph_env import GraphVectorEnv
+                envs = GraphVectorEnv(cfg.NUM_PROCESSES, self.device,
+                                      reward=dict(NUM_TOTAL_QUERY=cfg.NUM_TOTAL_QUERY), **kw)
+            else:
+                envs = SyntheticVectorEnv(cfg.NUM_PROCESSES, self.device, **kw)
+        self.envs = envs
         self._setup_actor_critic_agent(cfg)
         if self.world_size > 1:
             self.agent.init_distributed(find_unused_params=True)
+            if interactive:
+                self.agent_vln.init_distributed(find_unused_params=True)
         em_size = cfg.memory_size + cfg.num_steps  # ddppo_trainer.py:656-657
-        dim = self.actor_critic.net.memory_dim
-        self.rollouts = RolloutStorage(cfg.num_steps, self.envs.num_envs, self.obs_space, spaces.Discrete(4),
-                                       cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
-                                       cfg.memory_size, 3, 3, dim, dim, dim + 32, 256, num_recurrent_layers=1,
-                                       max_dialog_len=77)
+        if interactive:  # ddppo_trainer.py:640-676: goal / vln / option / dialog memories
+            dg, dl = self.actor_critic_goal.net.memory_dim, self.actor_critic_vln.net.memory_dim
+            dq = self.actor_critic_option.net.memory_dim
+            self.rollouts = RolloutStorage(cfg.num_steps, self.envs.num_envs, self.obs_space, spaces.Discrete(4),
+                                           cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
+                                           cfg.memory_size, cfg.NUM_DIALOG_STEPS, cfg.NUM_DIALOG_STEPS, dg, dl, dq,
+                                           cfg.smt_hidden_size, num_recurrent_layers=1, max_dialog_len=77,
+                                           query_count_emb_size=cfg.QUERY_COUNT_EMB_SIZE, use_state_memory=True)
+        else:
+            dim = self.actor_critic.net.memory_dim
+            self.rollouts = RolloutStorage(cfg.num_steps, self.envs.num_envs, self.obs_space, spaces.Discrete(4),
+                                           cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
+                                           cfg.memory_size, 3, 3, dim, dim, dim + 32, 256, num_recurrent_layers=1,
+                                           max_dialog_len=77)
         self.rollouts.to(self.device)
         observations = self.envs.reset()
         if self.belief_predictor is not None:

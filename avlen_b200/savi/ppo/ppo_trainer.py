@@ -23,6 +23,8 @@ class PPOTrainer:
     @torch.no_grad()
     def _collect_rollout_step(self, rollouts, current_episode_reward=None, running_episode_stats=None, uniforms=None):
         """One environment step for all envs (ppo_trainer.py:323-897, smt policy path :606-623, :714-894)."""
+        if getattr(self.config, "policy_type", "smt") == "interactive":
+            return self._collect_rollout_step_interactive(rollouts)
         s = rollouts.step
         step_observation = {k: v[s] for k, v in rollouts.observations.items()}
         values, actions, actions_log_probs, recurrent_hidden_states, external_memory_features, _probs = \
@@ -67,6 +69,45 @@ class PPOTrainer:
                         None, None)
         return self.envs.num_envs
 
+    @torch.no_grad()
+    def _collect_rollout_step_interactive(self, rollouts):
+        """The AVLEN interactive step (ppo_trainer.py:323-897, ``DIALOG_TRAINING`` False): pi_q decides whether to query
+        (``act_option``), the query bookkeeping runs on the device (``QueryBookkeeper``: :394-416, :449-460, :487-588),
+        pi_g (``act``) and pi_l (``act_dialog`` with the CLIP-embedded instruction) both act, the arbitration picks
+        the executed action and builds ``o_mask`` / ``ucnt_gt`` (:639-694), the env receives the query flags that shape
+        its reward (:706-710), and the four memories are written (:864-888).  No ``.item()`` / ``.cpu()`` anywhere.
+        Deviation: pi_q sees THIS step's query-count rows; the reference reads
+        ``rollouts.query_state[step]`` before writing it (:440-442 vs :588-590), i.e. the rows of the previous rollout."""
+        s = rollouts.step
+        envs, book = self.envs, self.query_book
+        obs = {k: v[s] for k, v in rollouts.observations.items()}
+        h = rollouts.recurrent_hidden_states[s]
+        prev = rollouts.prev_actions[s]
+        qs, lq = book.pre(envs.is_new_episode())
+        vq, unct, aq, lpq, h_out, xq, _pq = self.actor_critic_option.act_option(
+            obs, h, prev, rollouts.masks[s], rollouts.external_memory_option[:, s], rollouts.external_memory_masks[s], qs, lq)
+        is_q, qnum, cons, rl_mask, dialog, agent_step = book.after_option(aq, envs.target_distance(), envs.pending_dialog())
+        _vg, ag, _lpg, _, xg, pg = self.actor_critic_goal.act(
+            obs, h, prev, rollouts.masks[s], rollouts.external_memory_goal[:, s], rollouts.external_memory_masks[s])
+        _vl, al, _lpl, _, xl, xd, pl = self.actor_critic_vln.act_dialog(
+            obs, h, prev, rollouts.masks_vln[s], rollouts.external_memory_vln[:, s],
+            rollouts.external_memory_vln_dialog[:, s], rollouts.external_memory_vln_masks[s], dialog, agent_step)
+        oracle = envs.compute_oracle_actions()
+        o_action = oracle.float()
+        actions, o_mask, ucnt_gt, masks_vln = book.arbitrate(ag, al, pg, oracle)
+        envs.set_is_queried(is_q)
+        envs.set_query_num(qnum)
+        envs.set_constraint_reward(cons)
+        observations, rewards, dones = envs.step(actions)
+        masks = getattr(envs, "last_masks", None)
+        if masks is None:
+            masks = (~dones).float().unsqueeze(1)
+        if self.belief_predictor is not None:
+            self.belief_predictor.update(observations, dones)
+        rollouts.insert(observations, h_out, actions, aq, lpq, vq, rewards, masks, masks_vln, xg, xq, xl, xd, dialog,
+                        o_action, o_mask, rl_mask, ucnt_gt, pl, qs, lq, agent_step)
+        return envs.num_envs
+
     _BELIEF_KEYS = ("location_belief", "category_belief")
 
     def _belief_update_deferred(self, rollouts, observations, dones):
@@ -100,10 +141,16 @@ class PPOTrainer:
         with torch.no_grad():
             s = rollouts.step
             last_observation = {k: v[s] for k, v in rollouts.observations.items()}
-            next_value = self.actor_critic.get_value(last_observation, rollouts.recurrent_hidden_states[s],
-                                                     rollouts.prev_actions[s], rollouts.masks[s],
-                                                     rollouts.external_memory_goal[:, s],
-                                                     rollouts.external_memory_masks[s])
+            if getattr(ppo_cfg, "policy_type", "smt") == "interactive":  # ppo_trainer.py:1058-1068
+                next_value = self.actor_critic.get_value_option(
+                    last_observation, rollouts.recurrent_hidden_states[s], rollouts.prev_actions[s], rollouts.masks[s],
+                    rollouts.external_memory_option[:, s], rollouts.external_memory_masks[s],
+                    rollouts.query_state[s - 1], rollouts.last_query_info[s - 1])
+            else:
+                next_value = self.actor_critic.get_value(last_observation, rollouts.recurrent_hidden_states[s],
+                                                         rollouts.prev_actions[s], rollouts.masks[s],
+                                                         rollouts.external_memory_goal[:, s],
+                                                         rollouts.external_memory_masks[s])
         rollouts.compute_returns(next_value, ppo_cfg.use_gae, ppo_cfg.gamma, ppo_cfg.tau)
         value_loss, action_loss, dist_entropy, _vd, _rd, _ul = self.agent.update(rollouts)
         rollouts.after_update()

@@ -253,18 +253,27 @@ def run_savi(args):
     world, rank = _world()
     if args.tc_level is not None:
         K.set_tensor_cores(args.tc_level)
-    distractor = args.config == "distractor_smt"
+    distractor = args.config in ("distractor_smt", "distractor")
+    interactive = args.config in ("interactive", "distractor")
     base = dict(NUM_PROCESSES=args.envs, num_steps=args.rollout_steps, has_distractor_sound=distractor)
+    if interactive:
+        # BASELINE configs[2] / [4]: savi_interactive_2nd_stage.yaml — pi_q + pi_g + pi_l (CLIP) per step, PPO on pi_q;
+        # ``freeze_encoders: False`` (:75) but pi_q never back-propagates into its encoders (policy.py:1034-1036)
+        base.update(policy_type="interactive", freeze_encoders=False)
     env_steps = args.envs * args.rollout_steps * world
     out = {}
     line_stats = None
     regimes = ["frozen", "trainable"] if args.regime == "both" else [args.regime]
+    if interactive:
+        regimes = ["interactive"]
     sampler = None
     tr_frozen = None
     for regime in regimes:
         over = dict(base)
         if regime == "trainable":  # savi_pretraining.yaml:52-54
             over.update(freeze_encoders=False, pretraining=not args.trainable_full_memory)
+        if regime == "interactive" and args.clip_layers is not None:
+            over.update(clip_layers=args.clip_layers)
         cfg = savi_config(**over)
         tr = DDPPOTrainer(cfg).setup()
         headline = regime == regimes[0]
@@ -286,7 +295,7 @@ def run_savi(args):
             rec["clocks"] = clocks
             line_stats = rec
         out[regime] = rec
-        if regime == "frozen":
+        if regime in ("frozen", "interactive"):
             tr_frozen, cfg_frozen = tr, cfg
         else:
             del tr
@@ -300,6 +309,8 @@ def run_savi(args):
         over = dict(base, host_buffers=True)
         if regimes[0] == "trainable":
             over.update(freeze_encoders=False, pretraining=not args.trainable_full_memory)
+        if interactive and args.clip_layers is not None:
+            over.update(clip_layers=args.clip_layers)
         cfg2 = savi_config(**over)
         tr2 = DDPPOTrainer(cfg2).setup()
         k2 = max(1, min(2, args.steps))
@@ -339,11 +350,14 @@ def run_savi(args):
     del flush
 
     gpu_eager = None
-    if not args.no_eager:
+    if not args.no_eager and not interactive:
         gpu_eager = gpu_eager_baseline(args, regimes)
     cpu = cpu_baseline_sample(steps=3, warmup=1, one_thread=True) if not args.no_cpu else None
     r0 = line_stats
     wl = ("savi_smt_memory150_%s_encoders_rollout150_ppo2x2" % regimes[0]) + ("_distractor" if distractor else "")
+    if interactive:
+        wl = ("avlen_interactive_2nd_stage_piq_pig_pil_clip_memory150_rollout150_ppo2x2_graphwalk_env"
+              + ("_distractor" if distractor else ""))
     line = {"metric": METRIC, "value": r0["env_steps_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r0["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
@@ -443,11 +457,13 @@ def main():
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-shares", action="store_true")
     ap.add_argument("--tc-level", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 encoders (default), 2 + SMT")
+    ap.add_argument("--clip-layers", type=int, default=None, help="interactive configs: CLIP text tower depth (default 12)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.config in ("savi", "distractor_smt"):
-        args.envs = args.envs or 64
+    if args.config in ("savi", "distractor_smt", "interactive", "distractor"):
+        # BASELINE configs [1] (64 envs / GPU), [2] (256 envs over 8 GPUs = 32 / GPU), [4] (512 over 8 = 64 / GPU)
+        args.envs = args.envs or (32 if args.config == "interactive" else 64)
         return run_savi(args)
     import bench_configs  # the other BASELINE configs (interactive / distractor / audio_sweep / avnav)
     return bench_configs.run(args)

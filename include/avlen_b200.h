@@ -93,6 +93,34 @@ int avl_belief_update(int n_envs, const float* spectrogram, int spec_elems_per_e
                       int* has_pointgoal, float* last_label, int* has_label, float* location_belief,
                       float* category_belief, int* nonzero_scratch, void* stream);
 
+/* ------------------------------------------------------------------- graph-walk environment step
+ * One launch for all envs: graph walk (soundspaces/simulator.py:496-517), first oracle action of the shortest path
+ * (:758-787), reward (ss_baselines/common/environments.py:98-135), PoseSensor (soundspaces/tasks/nav.py:745-775), episode
+ * end + VectorEnv auto-reset from a per-env episode table.  Scene tables: nbr (V,4) int32, hops (V,V) int16, next_dir
+ * (V,V) int8 [target][node], points (V,2).  iargs: V, E, with_time_penalty, with_distance_reward, with_query_constraint,
+ * consecutive_constraint, soft_query_reward, num_total_query, max_steps; fargs: grid_size, slack_reward, distance_scale,
+ * success_reward, query_reward.  state: int32 [7][n] node, rot, source, ep_step, ep_cursor, start_node, start_rot.        */
+int avl_graph_env_step(int n, const int* iargs, const float* fargs, const int* nbr, const short* hops,
+                       const signed char* next_dir, const float* points, const int* ep_start, const int* ep_rot,
+                       const int* ep_source, int* state, float* prev_dist, const long long* actions,
+                       const unsigned char* is_queried, const long long* query_num, const float* cons_reward, float* rewards,
+                       unsigned char* dones, float* masks, float* pose, long long* oracle, float* target_distance,
+                       unsigned char* new_episode, int* azimuth, void* stream);
+/* ------------------------------------------------------------------- AVLEN interactive step: query bookkeeping
+ * Replaces the per-env Python loops of PPOTrainer._collect_rollout_step (ss_baselines/savi/ppo/ppo_trainer.py:394-416,
+ * :449-460, :487-588, :639-694, :769-787).  state: int32 [5][n] = queried, dialog step, episode step, last query step,
+ * query count; dialog_store: (n, L) int64 tokens of each env's current dialog.  Bit-exact vs the reference trace.      */
+int avl_query_pre(int n, const unsigned char* new_episode, int* state, const float* pe, int pe_rows, int emb,
+                  float* query_state, float* last_query_info, void* stream);
+int avl_query_after_option(int n, const long long* actions_option, const float* target_distance,
+                           const long long* pending_dialog, int L, int num_dialog_steps, float consecutive_reward,
+                           int query_within_radius, int* state, long long* dialog_store, unsigned char* is_queried,
+                           long long* query_num, float* cons_reward, long long* rl_mask, long long* cur_dialog,
+                           float* agent_step, void* stream);
+int avl_option_arbitrate(int n, const long long* actions_goal, const long long* actions_vln, const float* probs_goal, int A,
+                         const long long* oracle, int oracle_when_queried, int allow_stop, int num_dialog_steps, int* state,
+                         long long* dialog_store, int L, long long* actions, long long* o_mask, long long* ucnt_gt,
+                         float* masks_vln, void* stream);
 /* ------------------------------------------------- synthetic VectorEnv step (bench / tests)
  * Stands in for the reference's env workers behind VectorEnv.step (graph walk soundspaces/simulator.py:496-517,
  * _audio_index advance :668, silent-source test :646): episode bookkeeping + toy kinematics of all envs, one launch.

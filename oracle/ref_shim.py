@@ -208,6 +208,25 @@ def load_trainer():
           requeue_job=_Anything(), save_interrupted_state=_Anything())
     _stub("ss_baselines.savi.models.belief_predictor", BeliefPredictor=_Anything, BeliefPredictorDDP=_Anything)
     sys.modules["habitat"].Config = _Anything
+
+    class _Reg:  # habitat.core.registry.Registry: only the decorator plumbing the reference's BaselineRegistry uses
+        mapping = {}
+
+        @classmethod
+        def _register_impl(cls, _type, to_register, name, assert_type=None):
+            def wrap(to_register):
+                cls.mapping.setdefault(_type, {})[name or to_register.__name__] = to_register
+                return to_register
+            return wrap if to_register is None else wrap(to_register)
+
+        @classmethod
+        def _get_impl(cls, _type, name):
+            return cls.mapping.get(_type, {}).get(name)
+
+    core = _stub("habitat.core")
+    reg = _stub("habitat.core.registry", Registry=_Reg)
+    if not hasattr(reg, "registry"):
+        reg.registry = _Reg()
     load("ss_baselines.common.baseline_registry")
     return load(name)
 

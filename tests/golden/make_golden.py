@@ -27,6 +27,8 @@ Cases (reference file:line of what is being recorded):
                       (pi_l, weighted CE on the o_mask rows)                         savi/ppo/ppo.py:99-154
   audiogoal.npz       SoundSpacesSim._compute_audiogoal (three branches, distractor,    soundspaces/simulator.py:644-699,
                       empty / unreadable RIR, silent) + the audiogoal cache sequence  :711-721
+  interactive_step.npz PPOTrainer._collect_rollout_step, interactive branch, 40 steps x 6 envs  savi/ppo/ppo_trainer.py:323-897
+                      with scripted policies / env: query bookkeeping, arbitration, what reaches the storage and the env
   ppo_update.npz      RolloutStorage.insert x3 + compute_returns + PPO.update (pi_q)  savi/models/rollout_storage.py:214-412,
                       one epoch / one minibatch: the six returned numbers            :591-810; savi/ppo/ppo.py:90-95,:157-289
 """
@@ -611,8 +613,197 @@ def audiogoal():
     print("audiogoal.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def interactive_tokens(env, step):
+    """Token row the scripted 'speaker' + 'clip.tokenize' produce for env ``env`` at trainer step ``step`` (77 ids)."""
+    row = np.zeros(77, np.int64)
+    k = 5 + (env * 7 + step * 3) % 12
+    row[0] = 49406
+    row[1:1 + k] = 1000 + (np.arange(k) * 37 + env * 101 + step * 13) % 40000
+    row[1 + k] = 49407
+    return row
+
+
+def interactive_step():
+    """The reference's own ``PPOTrainer._collect_rollout_step`` (savi/ppo/ppo_trainer.py:323-897), unmodified, in the
+    interactive (not DIALOG_TRAINING) branch with the savi_interactive_2nd_stage.yaml switches, driven for 40 steps x 6
+    envs by scripted stand-ins: policies whose outputs are seeded random draws (recorded), an env whose oracle actions /
+    target distances / dones are seeded random draws (recorded), a 'speaker' + tokenizer producing a known token row per
+    (env, step).  Recorded outputs: what the trainer hands the env (actions, is_queried, query_num, constraint reward)
+    and what it inserts into the reference RolloutStorage (actions, actions_option, rl_masks, o_masks, ucnt_gt,
+    o_actions, all_dialog, agent_step, query_state, last_query_info, masks_vln)."""
+    import types
+
+    tr = ref_shim.load_trainer()
+    rs_mod = ref_shim.load("ss_baselines.savi.models.rollout_storage")
+    sp = ref_shim.spaces()
+    N, T, steps = 6, 20, 40
+    g = torch.Generator().manual_seed(4242)
+    rng = np.random.default_rng(4242)
+    cfg = types.SimpleNamespace(
+        DIALOG_TRAINING=False, DIALOG_TRAINING_WITHOUT_DIALOG=False, QUERY_COUNT_EMB_SIZE=32, QUERY_WITHIN_RADIUS=True,
+        REPLAY_STORE=False, NUM_DIALOG_STEPS=3, ORACLE_WHEN_QUERIED=True, ALLOW_STOP=False,
+        RL=types.SimpleNamespace(CONSECUTIVE_REWARD=-0.5, NUM_TOTAL_QUERY=3,
+                                 PPO=types.SimpleNamespace(num_steps=T, use_external_memory=True, use_state_memory=True,
+                                                           use_belief_predictor=False)))
+    obs_space = sp.Dict({"pose": sp.Box(-1e9, 1e9, (4,), np.float32), "spectrogram": sp.Box(-1e9, 1e9, (3, 2, 2), np.float32)})
+    em = 6 + T
+
+    class ActionSpace:  # habitat's action space class name is what the reference's constructor tests for (:90)
+        n = 4
+
+    rollouts = rs_mod.RolloutStorage(T, N, obs_space, ActionSpace(), 8, True, em, 6, em, 6, 3, 3, 5, 5, 7, 4,
+                                     num_recurrent_layers=1, max_dialog_len=77, query_count_emb_size=32,
+                                     use_state_memory=True)
+    rec = {"N": np.int64(N), "T": np.int64(T), "steps": np.int64(steps)}
+    state = {"t": 0, "done_prev": np.ones(N, bool), "to_env": {}}
+
+    class Envs:
+        num_envs = N
+
+        def agent_state(self):
+            d = rng.uniform(0, 8, N).astype(np.float32)
+            rec[f"s{state['t']}_target_distance"] = d
+            return [([0, 0, 0], [0, 0, 0, 1], "scene", 1, "v0", ["v1", "v2", "v3"], "go", float(d[i])) for i in range(N)]
+
+        def is_new_episode(self):
+            rec[f"s{state['t']}_new_episode"] = state["done_prev"].copy()
+            return list(state["done_prev"])
+
+        def compute_oracle_actions(self):
+            o = rng.integers(0, 4, N)
+            rec[f"s{state['t']}_oracle"] = o.astype(np.int64)
+            return [[int(v), 1, 0] for v in o]
+
+        def set_is_queried(self, v):
+            state["to_env"]["is_queried"] = np.array(v, bool)
+
+        def set_query_num(self, v):
+            state["to_env"]["query_num"] = np.array(v, np.int64)
+
+        def set_constraint_reward(self, v):
+            state["to_env"]["cons_reward"] = np.array(v, np.float32)
+
+        def step(self, actions):
+            t = state["t"]
+            rec[f"s{t}_env_actions"] = np.array(actions, np.int64)
+            for k, v in state["to_env"].items():
+                rec[f"s{t}_env_{k}"] = v
+            dones = rng.random(N) < 0.08
+            rew = rng.standard_normal(N).astype(np.float32)
+            rec[f"s{t}_dones"], rec[f"s{t}_rewards"] = dones, rew
+            state["done_prev"] = dones
+            return [({"pose": rng.standard_normal(4).astype(np.float32),
+                      "spectrogram": rng.random((3, 2, 2)).astype(np.float32)}, float(rew[i]), bool(dones[i]), {})
+                    for i in range(N)]
+
+    def rand_act(n_act, extra):
+        probs = torch.softmax(torch.randn(N, n_act, generator=g) * 2, 1)
+        a = torch.multinomial(probs, 1, generator=g)
+        return probs, a, extra
+
+    def act_option(*a, **k):
+        probs, act, _ = rand_act(2, None)
+        rec[f"s{state['t']}_actions_option"] = act.numpy()
+        return (torch.randn(N, 1, generator=g), torch.randn(N, 2, generator=g), act, torch.randn(N, 1, generator=g),
+                torch.zeros(1, N, 8), torch.randn(N, 7, generator=g), probs)
+
+    def act_goal(*a, **k):
+        probs, act, _ = rand_act(4, None)
+        if state["t"] % 5 == 0:
+            probs[0] = torch.tensor([0.3, 0.3, 0.2, 0.2])  # a tie in the top-2 probabilities (ucnt_gt edge)
+        rec[f"s{state['t']}_actions_goal"], rec[f"s{state['t']}_probs_goal"] = act.numpy(), probs.numpy()
+        return torch.randn(N, 1, generator=g), act, torch.randn(N, 1, generator=g), torch.zeros(1, N, 8), torch.randn(N, 5, generator=g), probs
+
+    def act_dialog(*a, **k):
+        probs, act, _ = rand_act(4, None)
+        rec[f"s{state['t']}_actions_vln"] = act.numpy()
+        rec[f"s{state['t']}_dialog_seen_by_pi_l"] = a[7].numpy().copy()
+        rec[f"s{state['t']}_agent_step_seen_by_pi_l"] = a[8].numpy().copy()
+        return (torch.randn(N, 1, generator=g), act, torch.randn(N, 1, generator=g), torch.zeros(1, N, 8),
+                torch.randn(N, 5, generator=g), torch.randn(N, 4, generator=g), probs)
+
+    class Speaker:
+        def generate_instr(self, entry):
+            return [{"words": ["t%d" % state["t"], "e%d" % state["cur_env"]]}]
+
+    def tokenize(text):
+        t_, e_ = text.split()
+        return torch.from_numpy(interactive_tokens(int(e_[1:]), int(t_[1:])))[None]
+
+    tr.clip.tokenize = tokenize
+    me = types.SimpleNamespace()
+    me.envs, me.config, me.max_dialog_len, me.device = Envs(), cfg, 77, torch.device("cpu")
+    me.agent = types.SimpleNamespace(actor_critic=types.SimpleNamespace(act_option=act_option))
+    me.actor_critic_goal = types.SimpleNamespace(act=act_goal)
+    me.agent_vln = types.SimpleNamespace(actor_critic=types.SimpleNamespace(act_dialog=act_dialog))
+    me.speaker = Speaker()
+    me._extract_scalars_from_infos = lambda infos: {}
+    position = torch.arange(1000).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, 32, 2) * (-np.log(10000.0) / 32))
+    me.pe = torch.zeros(1000, 32)
+    me.pe[:, 0::2] = torch.sin(position * div_term)
+    me.pe[:, 1::2] = torch.cos(position * div_term)
+    rec["pe"] = me.pe.numpy()
+
+    # the speaker needs to know which env is being processed: the reference passes the heading through this hook right
+    # before it calls the speaker for env idx (ppo_trainer.py:537), in env order
+    order = {"i": 0}
+
+    def quat_hook(rot):
+        return 0.0
+    me._quat_to_xy_heading = quat_hook
+    z = lambda *s_: torch.zeros(*s_)  # noqa: E731
+    info = {k: z(N, 1) for k in ("current_episode_reward", "current_episode_reward_goal", "current_episode_reward_vln",
+                                 "current_episode_step_goal", "current_episode_step_vln",
+                                 "current_episode_query_cnt_thresh", "current_episode_query_cnt_radius",
+                                 "current_episode_1st_query", "current_episode_4th_query")}
+    info["current_episode_step_stat_goal"], info["current_episode_step_stat_vln"] = z(N, 4), z(N, 4)
+    stats = {k: z(N, 1) for k in ("count", "reward", "reward_goal", "reward_vln", "query_count", "step_count",
+                                  "step_count_goal", "step_count_vln", "forward_step_goal", "left_step_goal",
+                                  "right_step_goal", "forward_step_vln", "left_step_vln", "right_step_vln",
+                                  "query_count_thresh", "query_count_radius", "query_step_1st", "query_step_4th")}
+    track_query = [dict(queried=False, step=0, total_step=0, last_query_step=0, cons_reward=0, all_step=[], all_reward=[],
+                        dialog=[]) for _ in range(N)]
+    track_count = [0] * N
+
+    # which env the speaker is generating for: envs whose query fires at this step are visited in index order and
+    # each calls the speaker exactly once -> wrap generate_instr to read the index from the call sequence
+    fn = tr.PPOTrainer._collect_rollout_step
+    for t in range(steps):
+        state["t"] = t
+        fired = []
+
+        def gen(entry, _t=t):
+            # the i-th speaker call of this step belongs to the i-th env (in index order) whose query fired now
+            fired.append(1)
+            return [{"words": ["t%d" % _t, "e%d" % state["fire_order"][len(fired) - 1]]}]
+
+        # the envs whose query fires at step t are those with queried==False before and option action 1 (within
+        # radius): computed inside the reference; we only need their ORDER, which is the env index order, so the
+        # scripted speaker derives the env from the reference's own track_query state right before the call
+        def gen2(entry, _t=t):
+            cand = [i for i in range(N) if track_query[i]["queried"] and track_query[i]["step"] == 0
+                    and not isinstance(track_query[i]["dialog"], torch.Tensor)]
+            # envs already served in this step carry a tensor dialog; the first unserved one is being processed
+            return [{"words": ["t%d" % _t, "e%d" % cand[0]]}]
+        me.speaker.generate_instr = gen2
+        s_before = rollouts.step
+        fn(me, rollouts, info, stats, track_query, track_count)
+        s = s_before
+        for name in ("actions", "actions_option", "rl_masks", "o_masks", "ucnt_gt", "o_actions", "all_dialog",
+                     "agent_step", "query_state", "last_query_info"):
+            rec[f"s{t}_st_{name}"] = getattr(rollouts, name)[s].numpy().copy()
+        rec[f"s{t}_st_masks_vln"] = rollouts.masks_vln[s + 1].numpy().copy()
+        rec[f"s{t}_st_masks"] = rollouts.masks[s + 1].numpy().copy()
+        if rollouts.step == T:
+            rollouts.after_update()
+    np.savez_compressed(os.path.join(HERE, "interactive_step.npz"), **rec)
+    print("interactive_step.npz", len(rec), "arrays; queries fired:",
+          int(sum(rec[f"s{t}_env_is_queried"].sum() for t in range(steps))))
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the reference tree (/root/reference) is needed to generate golden vectors"
     torch.set_num_threads(1)
-    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, dialog_encoder_backward, ppo_update, dialog_update, audiogoal):
+    for fn in (smt_policy, smt_policy_pretraining, smt_policy_distractor, option_policy, dialog_policy, extmem, gae, avnav_net, rnn_seq, belief_update, smt_backward, dialog_encoder_backward, ppo_update, dialog_update, audiogoal, interactive_step):
         fn()

@@ -369,3 +369,44 @@ def test_audiogoal_cache_sequence_matches_reference_golden():
         assert used == int(g["cache_index_used"][step]), step
         want = g["cache_heads"][step]
         assert np.abs(cache[key][:, :256].astype(np.float32) - want).max() <= 1e-6 * max(1e-9, np.abs(want).max())
+
+
+def replay_interactive_golden(make_book, to_np=lambda a: np.asarray(a)):
+    """Drives a query-bookkeeping implementation through the recorded 40-step trace of the reference trainer and
+    compares everything the reference handed to its env and wrote into its storage.  ``make_book(n, pe)`` returns an
+    object with ``pre / after_option / arbitrate`` (oracle restatement or the CUDA product class)."""
+    from tests.golden.make_golden import interactive_tokens
+    g = load("interactive_step.npz")
+    N, S = int(g["N"]), int(g["steps"])
+    book = make_book(N, g["pe"])
+    for t in range(S):
+        qs, lq = book.pre(g[f"s{t}_new_episode"])
+        assert np.array_equal(to_np(qs), g[f"s{t}_st_query_state"]), t
+        assert np.array_equal(to_np(lq), g[f"s{t}_st_last_query_info"]), t
+        pending = np.stack([interactive_tokens(e, t) for e in range(N)])
+        is_q, qnum, cons, rl, dialog, astep = book.after_option(g[f"s{t}_actions_option"].reshape(-1),
+                                                                g[f"s{t}_target_distance"], pending)
+        assert np.array_equal(to_np(is_q).astype(bool), g[f"s{t}_env_is_queried"]), t
+        assert np.array_equal(to_np(qnum), g[f"s{t}_env_query_num"]), t
+        assert np.array_equal(to_np(cons), g[f"s{t}_env_cons_reward"]), t
+        assert np.array_equal(to_np(rl), g[f"s{t}_st_rl_masks"]), t
+        assert np.array_equal(to_np(dialog), g[f"s{t}_st_all_dialog"]), t
+        assert np.array_equal(to_np(dialog), g[f"s{t}_dialog_seen_by_pi_l"]), t
+        assert np.array_equal(to_np(astep), g[f"s{t}_st_agent_step"]), t
+        act, o_mask, ucnt, masks_vln = book.arbitrate(g[f"s{t}_actions_goal"].reshape(-1), g[f"s{t}_actions_vln"].reshape(-1),
+                                                      g[f"s{t}_probs_goal"], g[f"s{t}_oracle"])
+        assert np.array_equal(to_np(act).reshape(-1), g[f"s{t}_env_actions"]), t
+        assert np.array_equal(to_np(act).reshape(-1), g[f"s{t}_st_actions"].reshape(-1)), t
+        assert np.array_equal(to_np(o_mask), g[f"s{t}_st_o_masks"]), t
+        assert np.array_equal(to_np(ucnt), g[f"s{t}_st_ucnt_gt"]), t
+        assert np.array_equal(to_np(masks_vln).reshape(-1), g[f"s{t}_st_masks_vln"].reshape(-1)), t
+        assert np.array_equal(g[f"s{t}_oracle"].astype(np.float32), g[f"s{t}_st_o_actions"]), t
+
+
+def test_interactive_bookkeeping_oracle_matches_reference_trainer_golden():
+    """the per-env query / option / arbitration logic of ``_collect_rollout_step``
+    (savi/ppo/ppo_trainer.py:394-416, :449-460, :487-588, :639-694, :769-787) against a 40-step x 6-env trace of the
+    UNMODIFIED reference trainer method (scripted policies / env; tests/golden/make_golden.py:interactive_step) —
+    bit-exact: integer / index / mask work."""
+    from oracle.interactive_py import QueryBookkeeping
+    replay_interactive_golden(lambda n, pe: QueryBookkeeping(n, pe))

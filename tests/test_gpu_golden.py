@@ -384,3 +384,13 @@ def test_audiogoal_cuda_matches_reference_golden():
     n = len(GOLDEN_AUDIO_CASES)
     assert np.all(ag[n:] == 0.0) and np.all(sp[n:] == 0.0)
     r.close()
+
+
+def test_interactive_bookkeeping_cuda_matches_reference_trainer_golden():
+    """the three query-bookkeeping kernels (csrc/interactive.cu) driven through the recorded 40-step
+    trace of the UNMODIFIED ``PPOTrainer._collect_rollout_step`` — everything the reference handed to its env and wrote
+    into its storage, bit-exact (integer / index / mask work)."""
+    from avlen_b200.savi.ppo.query_state import QueryBookkeeper
+    from tests.test_golden import replay_interactive_golden
+    replay_interactive_golden(lambda n, pe: QueryBookkeeper(n, "cuda", pe=pe),
+                              to_np=lambda a: a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a))
