@@ -1,0 +1,68 @@
+// Observation ingest for the compact rollout storage: RolloutStorage keeps rgb as uint8 and depth
+// as fp16 (the reference stores fp32, ss_baselines/savi/models/rollout_storage.py:58-63, after inflating uint8 frames on
+// the host, common/utils.py:149-154), and the encoders' first op — x / 255 then the exact 2x2 area mean
+// (smt_cnn.py:83-95, common/utils.py:515-517) — reads those types directly.  A minibatch of the PPO update is addressed
+// by a per-row sample index into the time-major storage, so the (T*N_mb, 128, 128, C) copies the reference's generator
+// stacks (rollout_storage.py:716-760) never exist.
+#include "common.cuh"
+
+#ifndef AVL_HOST_EMUL
+#include <cuda_fp16.h>
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float ld_as_float<unsigned char>(const unsigned char* p) { return (float)__ldg(p); }
+
+// one thread per output pixel: reads the 2 x 2 x C source block (two contiguous runs of 2 C elements), writes Cp floats
+template <typename T>
+__global__ void resize_half_typed_kernel(const T* __restrict__ x, const long long* __restrict__ sample_index, float* y, int N,
+                                         int H, int W, int C, int Cp, float scale) {
+  const int OH = H >> 1, OW = W >> 1;
+  const long long total = (long long)N * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % OW);
+    long long t = i / OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    const long long src = sample_index ? sample_index[n] : n;
+    const T* p = x + ((src * H + 2 * oh) * W + 2 * ow) * C;
+    const T* q = p + (long long)W * C;
+    float* o = y + i * Cp;
+    for (int c = 0; c < C; ++c) {
+      // the reference divides by 255 first, then averages (smt_cnn.py:83-86): same operation order as resize_half_kernel
+      const float a = ld_as_float(p + c) * scale, b = ld_as_float(p + C + c) * scale;
+      const float d = ld_as_float(q + c) * scale, e = ld_as_float(q + C + c) * scale;
+      o[c] = (a + b + d + e) * 0.25f;
+    }
+    for (int c = C; c < Cp; ++c) o[c] = 0.f;
+  }
+}
+
+}  // namespace
+
+// dtype: 0 fp32, 1 fp16, 2 uint8.  sample_index (optional, device int64 [N]): row n reads source sample sample_index[n].
+AVL_API int avl_resize_half_typed(const void* x, int dtype, const long long* sample_index, float* y, int N, int H, int W,
+                                  int C, int C_out, float scale, void* stream) {
+  if (N < 0 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1 || C_out < C || dtype < 0 || dtype > 2) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!x || !y) return AVL_ERR_ARG;
+  const long long total = (long long)N * (H / 2) * (W / 2);
+  const int blocks = avl_div_up(total, 256) > 148 * 32 ? 148 * 32 : avl_div_up(total, 256);
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (dtype == 0)
+    resize_half_typed_kernel<float><<<blocks, 256, 0, cs>>>((const float*)x, sample_index, y, N, H, W, C, C_out, scale);
+  else if (dtype == 1)
+    resize_half_typed_kernel<__half><<<blocks, 256, 0, cs>>>((const __half*)x, sample_index, y, N, H, W, C, C_out, scale);
+  else
+    resize_half_typed_kernel<unsigned char><<<blocks, 256, 0, cs>>>((const unsigned char*)x, sample_index, y, N, H, W, C,
+                                                                    C_out, scale);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

@@ -64,6 +64,7 @@ _lib.register({
     "avl_gru_backward": [I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_resnet_graph_stats": [I],
     "avl_f16_overflow": [I],
+    "avl_resize_half_typed": [P, I, P, P, I, I, I, I, I, F, P],
     "avl_pack_conv_weight": [P, I, I, I, I, I, I, P, P],
     "avl_zero_upsample2": [P, P, I, I, I, I, I, I, P],
     "avl_tc_conv2d_wgrad_workspace": [I, I, I, I, I, I, I, I, I],
@@ -533,12 +534,61 @@ def _groupnorm_raw(x, gamma, beta, groups=16, eps=1e-5, relu=False, residual=Non
     return out
 
 
+class IndexedObservation:
+    """Rows of a time-major observation store ``(T + 1, N, H, W, C)`` addressed by a flat sample index, WITHOUT
+    materialising them: what ``RolloutStorage.recurrent_generator`` hands the policy for the image
+    sensors instead of the reference's stacked ``(T * N_mb, H, W, C)`` copies (rollout_storage.py:716-760).  The
+    encoders' first kernel (``resize_half``) gathers through the index."""
+
+    def __init__(self, storage, index):
+        self.storage = storage.reshape(-1, *storage.shape[2:])  # a view: the store is contiguous
+        self.index = index.to(torch.int64).contiguous()
+
+    @property
+    def shape(self):
+        return (self.index.shape[0],) + tuple(self.storage.shape[1:])
+
+    @property
+    def dtype(self):
+        return self.storage.dtype
+
+    @property
+    def device(self):
+        return self.storage.device
+
+    is_cuda = True
+
+    def contiguous(self):
+        return self
+
+    def data_ptr(self):
+        return self.index.data_ptr()
+
+    def materialize(self):
+        return self.storage.index_select(0, self.index)
+
+
+_RESIZE_DTYPES = {torch.float32: 0, torch.float16: 1, torch.uint8: 2}
+
+
 def resize_half(x, scale=1.0, c_out=None):
-    """Exact 2x2 area mean (x * scale first); ``c_out`` > C appends zero channels (tensor-core conv loader)."""
+    """Exact 2x2 area mean (x * scale first); ``c_out`` > C appends zero channels (tensor-core conv loader).  ``x``:
+    fp32 / fp16 / uint8 NHWC tensor, or an ``IndexedObservation`` (rows gathered through its sample index)."""
+    index = None
+    if isinstance(x, IndexedObservation):
+        index, x = x.index, x.storage
     N, H, W, C = x.shape
+    rows = N if index is None else index.shape[0]
     c_out = C if c_out is None else c_out
-    y = torch.empty((N, H // 2, W // 2, c_out), device=x.device, dtype=torch.float32)
-    call("avl_resize_half", fptr(x), fptr(y), N, H, W, C, c_out, float(scale), stream())
+    y = torch.empty((rows, H // 2, W // 2, c_out), device=x.device, dtype=torch.float32)
+    if index is None and x.dtype == torch.float32:
+        call("avl_resize_half", fptr(x), fptr(y), N, H, W, C, c_out, float(scale), stream())
+        return y
+    code = _RESIZE_DTYPES.get(x.dtype)
+    if code is None:
+        raise _lib.AvlenError(f"resize_half: unsupported observation dtype {x.dtype}")
+    call("avl_resize_half_typed", dptr(x), code, dptr(index, torch.int64), fptr(y), rows, H, W, C, c_out, float(scale),
+         stream())
     return y
 
 

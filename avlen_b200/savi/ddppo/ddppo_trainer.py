@@ -40,7 +40,9 @@ def savi_config(**overrides):
                host_buffers=False, has_distractor_sound=False, overlap_belief=True, prefetch_encoders=True,
                # AVLEN interactive stages (savi_interactive_2nd_stage.yaml:19-23,:30-41; config/default.py:183-186)
                NUM_DIALOG_STEPS=3, ORACLE_WHEN_QUERIED=True, QUERY_WITHIN_RADIUS=True, ALLOW_STOP=False,
-               CONSECUTIVE_REWARD=-0.5, NUM_TOTAL_QUERY=3, QUERY_COUNT_EMB_SIZE=32, clip_layers=12, graph_env=None)
+               CONSECUTIVE_REWARD=-0.5, NUM_TOTAL_QUERY=3, QUERY_COUNT_EMB_SIZE=32, clip_layers=12, graph_env=None,
+               # rgb uint8 / depth fp16 in the rollout storage and on the H2D path
+               compact_observations=True)
     cfg.update(overrides)
     return types.SimpleNamespace(**cfg)
 
@@ -145,7 +147,7 @@ class DDPPOTrainer(PPOTrainer):
         interactive = cfg.policy_type == "interactive"
         if envs is None:
             kw = dict(seed=cfg.seed + self.world_rank, sr=cfg.sampling_rate, host_buffers=cfg.host_buffers,
-                      distractor=cfg.has_distractor_sound)
+                      distractor=cfg.has_distractor_sound, compact=cfg.compact_observations)
             if interactive or cfg.graph_env:
                 # the interactive step needs what only a navigation graph provides: oracle actions, target distance,
                 # episode boundaries, query-aware rewards (ppo_trainer.py:336-345,:642,:706-710)
@@ -168,13 +170,14 @@ class DDPPOTrainer(PPOTrainer):
                                            cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
                                            cfg.memory_size, cfg.NUM_DIALOG_STEPS, cfg.NUM_DIALOG_STEPS, dg, dl, dq,
                                            cfg.smt_hidden_size, num_recurrent_layers=1, max_dialog_len=77,
-                                           query_count_emb_size=cfg.QUERY_COUNT_EMB_SIZE, use_state_memory=True)
+                                           query_count_emb_size=cfg.QUERY_COUNT_EMB_SIZE, use_state_memory=True,
+                                           compact_observations=cfg.compact_observations)
         else:
             dim = self.actor_critic.net.memory_dim
             self.rollouts = RolloutStorage(cfg.num_steps, self.envs.num_envs, self.obs_space, spaces.Discrete(4),
                                            cfg.hidden_size, cfg.use_external_memory, em_size, cfg.memory_size, em_size,
                                            cfg.memory_size, 3, 3, dim, dim, dim + 32, 256, num_recurrent_layers=1,
-                                           max_dialog_len=77)
+                                           max_dialog_len=77, compact_observations=cfg.compact_observations)
         self.rollouts.to(self.device)
         observations = self.envs.reset()
         if self.belief_predictor is not None:

@@ -50,7 +50,7 @@ class SMTCNN(nn.Module):
             feats = []
             pad = 4 if K.tensor_cores_enabled() else None  # 16-byte channel rows for the tensor-core loaders
             for name in self.input_modalities:
-                x = K.resize_half(observations[name].contiguous(), 1.0 / 255.0 if name == "rgb" else 1.0, pad)
+                x = K.resize_half(observations[name], 1.0 / 255.0 if name == "rgb" else 1.0, pad)
                 feats.append(getattr(self, name + "_encoder")(x))
             return torch.cat(feats, dim=1)
         if out is None:

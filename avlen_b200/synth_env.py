@@ -19,9 +19,13 @@ from .common.utils import batch_obs
 
 class SyntheticVectorEnv:
     def __init__(self, num_envs, device, seed=1234, sr=16000, pool=4, distractor=False, host_buffers=False,
-                 done_prob=1.0 / 80.0, rir_len=None, fused_step=True):
+                 done_prob=1.0 / 80.0, rir_len=None, fused_step=True, compact=False):
         self.num_envs, self.device, self.sr = num_envs, torch.device(device), sr
         self.host_buffers = host_buffers
+        # compact: frames are handed over as uint8 rgb / fp16 depth (what the compact rollout storage keeps,
+        # SURVEY §8f item 2) instead of the reference's fp32 (common/utils.py:149-154)
+        self.compact = bool(compact)
+        self._keep = {"rgb": torch.uint8, "depth": torch.float16} if self.compact else None
         self.fused_step = fused_step  # one kernel for the episode bookkeeping (avl_synth_env_step) instead of ~30 torch ops
         self.last_masks = None
         self._visual_stream = None
@@ -40,6 +44,8 @@ class SyntheticVectorEnv:
             self._actions_host = torch.zeros(n, 1, dtype=torch.int64).pin_memory()
         else:
             self._rgb, self._depth = rgb.to(self.device), depth.to(self.device)
+            if self.compact:
+                self._depth16 = self._depth.half()
         self.h2d_bytes_per_step = (rgb[0].numel() + depth[0].numel() * 4) if host_buffers else 0
         self.d2h_bytes_per_step = n * 8 if host_buffers else 0
         # audio assets resident on the device (RIR bank + sound bank), per-env descriptors
@@ -76,8 +82,10 @@ class SyntheticVectorEnv:
                 # what a VectorEnv hands the trainer: one observation dict per env (numpy frames on the host) ->
                 # the product's batch_obs (common/utils.py:129-156): stack into pinned staging, async H2D, cast
                 per_env = [{"rgb": self._rgb_np[i][e], "depth": self._depth_np[i][e]} for e in range(self.num_envs)]
-                batch = batch_obs(per_env, device=self.device, pinned=self._staging)
+                batch = batch_obs(per_env, device=self.device, pinned=self._staging, keep_dtypes=self._keep)
                 rgb, depth = batch["rgb"], batch["depth"]
+            elif self.compact:
+                rgb, depth = self._rgb[i], self._depth16[i]
             else:
                 rgb, depth = self._rgb[i], self._depth[i]
                 rgb = rgb.float()  # batch_obs: everything becomes float32 (common/utils.py:149-154)

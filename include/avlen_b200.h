@@ -93,6 +93,12 @@ int avl_belief_update(int n_envs, const float* spectrogram, int spec_elems_per_e
                       int* has_pointgoal, float* last_label, int* has_label, float* location_belief,
                       float* category_belief, int* nonzero_scratch, void* stream);
 
+/* ------------------------------------------------------------------- compact observation storage
+ * x / 255 + exact 2x2 area mean (smt_cnn.py:83-95) reading the storage dtype directly (0 fp32, 1 fp16 depth, 2 uint8 rgb);
+ * sample_index (optional, int64 [N]): output row n reads source sample sample_index[n] of the time-major storage — the
+ * minibatch copies of rollout_storage.py:716-760 are never made.  y: (N, H/2, W/2, C_out) fp32, channels >= C zero.     */
+int avl_resize_half_typed(const void* x, int dtype, const long long* sample_index, float* y, int N, int H, int W, int C,
+                          int C_out, float scale, void* stream);
 /* ------------------------------------------------------------------- graph-walk environment step
  * One launch for all envs: graph walk (soundspaces/simulator.py:496-517), first oracle action of the shortest path
  * (:758-787), reward (ss_baselines/common/environments.py:98-135), PoseSensor (soundspaces/tasks/nav.py:745-775), episode
