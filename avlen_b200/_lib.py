@@ -112,3 +112,26 @@ def fptr(t):
 def stream():
     # raw cudaStream_t of torch's current stream (the Python Stream object costs ~15 us to build per call)
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+# ---- NVTX ranges around the phases of the hot path (SURVEY §5 tracing): AVL_NVTX=1 turns them on; they show up in
+# Nsight Systems / ncu --nvtx captures as rollout_step / update / minibatch / encoder ranges.  Off by default: a range
+# push / pop pair costs ~1 us of host time per call.
+_NVTX = os.environ.get("AVL_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False

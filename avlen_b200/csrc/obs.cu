@@ -66,3 +66,87 @@ AVL_API int avl_resize_half_typed(const void* x, int dtype, const long long* sam
   return AVL_OK;
 }
 #endif  // AVL_HOST_EMUL
+
+// ------------------------------------------------------------------------------------------ fused storage insert
+// RolloutStorage.insert (ss_baselines/savi/models/rollout_storage.py:214-295) writes ~20-35 small tensors into slot
+// ``step`` of the time-major stores: as torch ``copy_`` calls that is one launch (and ~8 us of host time) EACH, every
+// rollout step.  Here all of them are one launch: a table of (dst, src, bytes, kind) segments travels in the kernel
+// parameters, one CTA column per segment.  kind 0: byte copy; 1: fp32 -> uint8 (rgb into the compact store);
+// 2: fp32 -> fp16 (depth); 3: int64 -> fp32; 4: fp32 -> int64.
+#ifndef AVL_HOST_EMUL
+namespace {
+
+constexpr int MC_MAX = 48;
+struct MultiCopy {
+  void* dst[MC_MAX];
+  const void* src[MC_MAX];
+  long long n[MC_MAX];      // bytes (kind 0) or elements
+  unsigned char kind[MC_MAX];
+  int count;
+};
+
+__global__ void multi_copy_kernel(MultiCopy m) {
+  const int s = blockIdx.y;
+  if (s >= m.count) return;
+  const long long n = m.n[s];
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const int kind = m.kind[s];
+  if (kind == 0) {
+    const uintptr_t a = (uintptr_t)m.dst[s] | (uintptr_t)m.src[s];
+    if (!(a & 15) && !(n & 15)) {
+      const uint4* src = (const uint4*)m.src[s];
+      uint4* dst = (uint4*)m.dst[s];
+      for (long long i = i0; i < (n >> 4); i += stride) dst[i] = src[i];
+    } else if (!(a & 3) && !(n & 3)) {
+      const uint32_t* src = (const uint32_t*)m.src[s];
+      uint32_t* dst = (uint32_t*)m.dst[s];
+      for (long long i = i0; i < (n >> 2); i += stride) dst[i] = src[i];
+    } else {
+      const unsigned char* src = (const unsigned char*)m.src[s];
+      unsigned char* dst = (unsigned char*)m.dst[s];
+      for (long long i = i0; i < n; i += stride) dst[i] = src[i];
+    }
+  } else if (kind == 1) {
+    const float* src = (const float*)m.src[s];
+    unsigned char* dst = (unsigned char*)m.dst[s];
+    for (long long i = i0; i < n; i += stride) dst[i] = (unsigned char)src[i];  // torch copy_: truncation toward zero
+  } else if (kind == 2) {
+    const float* src = (const float*)m.src[s];
+    __half* dst = (__half*)m.dst[s];
+    for (long long i = i0; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+  } else if (kind == 3) {
+    const long long* src = (const long long*)m.src[s];
+    float* dst = (float*)m.dst[s];
+    for (long long i = i0; i < n; i += stride) dst[i] = (float)src[i];
+  } else {
+    const float* src = (const float*)m.src[s];
+    long long* dst = (long long*)m.dst[s];
+    for (long long i = i0; i < n; i += stride) dst[i] = (long long)src[i];
+  }
+}
+
+}  // namespace
+
+// dst / src: host arrays of ``count`` device pointers; n: bytes (kind 0) or elements; kind as above.  count <= 48.
+AVL_API int avl_multi_copy(int count, void* const* dst, const void* const* src, const long long* n, const unsigned char* kind,
+                           void* stream) {
+  if (count < 0 || count > MC_MAX) return AVL_ERR_ARG;
+  if (count == 0) return AVL_OK;
+  if (!dst || !src || !n || !kind) return AVL_ERR_ARG;
+  MultiCopy m;
+  m.count = count;
+  long long biggest = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!dst[i] || !src[i] || n[i] < 0 || kind[i] > 4) return AVL_ERR_ARG;
+    m.dst[i] = dst[i]; m.src[i] = src[i]; m.n[i] = n[i]; m.kind[i] = kind[i];
+    const long long units = kind[i] == 0 ? (n[i] + 15) / 16 : n[i];
+    if (units > biggest) biggest = units;
+  }
+  int bx = avl_div_up(biggest, 256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 512) bx = 512;
+  multi_copy_kernel<<<dim3(bx, count), 256, 0, (cudaStream_t)stream>>>(m);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

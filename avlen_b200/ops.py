@@ -193,3 +193,57 @@ class FlatAdam:
         self.v.copy_(sd["exp_avg_sq"])
         self.step_count = int(sd["step"])
         self.lr = sd.get("lr", self.lr)
+
+
+# ---- fused storage insert: all the small copies of one rollout step in ONE launch (csrc/obs.cu avl_multi_copy) ----------
+import ctypes as _ct
+
+_lib.register({"avl_multi_copy": [_ct.c_int, _ct.c_void_p, _ct.c_void_p, _ct.c_void_p, _ct.c_void_p, _ct.c_void_p]})
+_MC_KIND = {(torch.float32, torch.uint8): 1, (torch.float32, torch.float16): 2, (torch.int64, torch.float32): 3,
+            (torch.float32, torch.int64): 4}
+
+
+class MultiCopy:
+    """Collects ``dst.copy_(src)`` pairs and issues them as one kernel.  Pairs it cannot express (non-contiguous views,
+    other dtype conversions, broadcasting) fall back to ``copy_`` immediately."""
+
+    MAX = 48
+
+    def __init__(self):
+        self._dst = (_ct.c_void_p * self.MAX)()
+        self._src = (_ct.c_void_p * self.MAX)()
+        self._n = (_ct.c_longlong * self.MAX)()
+        self._kind = (_ct.c_ubyte * self.MAX)()
+        self._count = 0
+        self._keep = []
+
+    def add(self, dst, src):
+        # same element count, both contiguous (a (N,) source into an (N, 1) slot is a flat copy); anything else —
+        # broadcasting, strided views, host tensors — keeps torch's copy_ semantics
+        if not (torch.is_tensor(src) and src.is_cuda and dst.is_cuda and dst.is_contiguous() and src.is_contiguous()
+                and dst.numel() == src.numel()):
+            dst.copy_(src)
+            return
+        if dst.dtype == src.dtype:
+            kind, n = 0, dst.numel() * dst.element_size()
+        else:
+            kind = _MC_KIND.get((src.dtype, dst.dtype))
+            if kind is None:
+                dst.copy_(src)
+                return
+            n = dst.numel()
+        if n == 0:
+            return
+        if self._count == self.MAX:
+            self.flush()
+        i = self._count
+        self._dst[i], self._src[i], self._n[i], self._kind[i] = dst.data_ptr(), src.data_ptr(), n, kind
+        self._keep.append(src)
+        self._count = i + 1
+
+    def flush(self):
+        if self._count:
+            call("avl_multi_copy", self._count, _ct.cast(self._dst, _ct.c_void_p), _ct.cast(self._src, _ct.c_void_p),
+                 _ct.cast(self._n, _ct.c_void_p), _ct.cast(self._kind, _ct.c_void_p), stream())
+            self._count = 0
+            self._keep.clear()

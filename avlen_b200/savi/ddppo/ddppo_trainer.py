@@ -16,6 +16,7 @@ import types
 import torch
 import torch.distributed as distrib
 
+from ... import _lib
 from ... import nn as K
 from ...common import spaces
 from ...common.baseline_registry import baseline_registry
@@ -191,7 +192,8 @@ class DDPPOTrainer(PPOTrainer):
         cfg = self.config
         store = distrib.distributed_c10d._get_default_store() if (self.world_size > 1 and cfg.use_preemption) else None
         for step in range(cfg.num_steps):
-            self._collect_rollout_step(self.rollouts)
+            with _lib.nvtx_range("rollout_step"):
+                self._collect_rollout_step(self.rollouts)
             if store is not None and step >= cfg.num_steps * self.SHORT_ROLLOUT_THRESHOLD:
                 if int(store.add("num_done", 0)) > cfg.sync_frac * self.world_size:
                     break

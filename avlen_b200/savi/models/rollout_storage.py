@@ -119,6 +119,7 @@ class RolloutStorage:
                               if use_state_memory else None)
         self.step = 0
         self.env_id = 0
+        self._mc = ops.MultiCopy()
 
     COMPACT_DTYPES = {"rgb": torch.uint8, "depth": torch.float16}
     LAZY_SENSORS = ("rgb", "depth")  # image sensors: gathered by the encoders' first kernel, never copied per minibatch
@@ -142,33 +143,39 @@ class RolloutStorage:
                em_features_dialog, all_dialog, o_action, o_mask, rl_masks, ucnt_gt, action_prob, query_state,
                last_query_info, agent_step):
         s = self.step
+        # every plain copy of this step goes into ONE launch (ops.MultiCopy -> avl_multi_copy) instead of ~20-35 torch
+        # copy_ kernels; dtype conversions into the compact store (fp32 -> uint8 / fp16) are done by the same kernel
+        mc = self._mc if self.rewards.is_cuda else None
+        put = mc.add if mc is not None else (lambda dst, src: dst.copy_(src))
         for sensor in observations:
             if sensor in self.observations:
-                self.observations[sensor][s + 1].copy_(observations[sensor])
-        self.recurrent_hidden_states[s + 1].copy_(recurrent_hidden_states)
+                put(self.observations[sensor][s + 1], observations[sensor])
+        put(self.recurrent_hidden_states[s + 1], recurrent_hidden_states)
         if all_dialog is not None:
-            self.all_dialog[s].copy_(all_dialog)
+            put(self.all_dialog[s], all_dialog)
         if query_state is not None:
-            self.query_state[s].copy_(query_state)
+            put(self.query_state[s], query_state)
         if last_query_info is not None:
-            self.last_query_info[s].copy_(last_query_info)
+            put(self.last_query_info[s], last_query_info)
         if agent_step is not None:
-            self.agent_step[s].copy_(agent_step)
+            put(self.agent_step[s], agent_step)
         if o_action is not None:
-            self.o_masks[s].copy_(o_mask)
-            self.ucnt_gt[s].copy_(ucnt_gt)
-            self.rl_masks[s].copy_(rl_masks)
-            self.o_actions[s].copy_(o_action)
-            self.action_probs[s].copy_(action_prob)
-        self.actions[s].copy_(actions)
+            put(self.o_masks[s], o_mask)
+            put(self.ucnt_gt[s], ucnt_gt)
+            put(self.rl_masks[s], rl_masks)
+            put(self.o_actions[s], o_action)
+            put(self.action_probs[s], action_prob)
+        put(self.actions[s], actions)
         if actions_option is not None:
-            self.actions_option[s].copy_(actions_option)
-        self.prev_actions[s + 1].copy_(actions)
-        self.action_log_probs[s].copy_(action_log_probs)
-        self.value_preds[s].copy_(value_preds)
-        self.rewards[s].copy_(rewards)
-        self.masks[s + 1].copy_(not_done_masks)
-        self.masks_vln[s + 1].copy_(not_done_masks_vln)
+            put(self.actions_option[s], actions_option)
+        put(self.prev_actions[s + 1], actions)
+        put(self.action_log_probs[s], action_log_probs)
+        put(self.value_preds[s], value_preds)
+        put(self.rewards[s], rewards)
+        put(self.masks[s + 1], not_done_masks)
+        put(self.masks_vln[s + 1], not_done_masks_vln)
+        if mc is not None:
+            mc.flush()
         if self.use_external_memory:
             self.em.insert(em_features, not_done_masks, snapshot=self.em_masks[s + 1])  # :284-286 fused
             if em_features_option is not None:

@@ -9,6 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ... import _lib
 from ... import nn as K
 from ... import ops
 
@@ -84,6 +85,8 @@ class PPO(nn.Module):
              return_batch, masks_batch, old_lp_batch, adv_targ, rl_masks_batch, unct_gt_batch, em_goal, em_option,
              _em_vln, _em_dialog, em_masks, _em_vln_masks, _all_dialog, query_state_batch, last_query_info,
              _agent_step) = sample
+            _nvtx = _lib.nvtx_range("ppo_minibatch")
+            _nvtx.__enter__()
             self._flat_g.zero_()
             if option:
                 logits, values, unct = self.actor_critic.evaluate_heads(
@@ -111,6 +114,7 @@ class PPO(nn.Module):
             self.after_step()
             sums += out
             n_updates += 1
+            _nvtx.__exit__()
         s = (sums / max(1, n_updates)).tolist()  # the only host synchronisation of the update
         K.check_f16_overflow()  # (device already idle) fp16 activation storage guard, nn.check_f16_overflow
         value_loss, action_loss, entropy, unct_loss = s[0], s[1], s[2], s[3]

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import torch
 
+from ... import _lib
 from ... import nn as K
 
 
@@ -152,6 +153,7 @@ class PPOTrainer:
                                                          rollouts.external_memory_goal[:, s],
                                                          rollouts.external_memory_masks[s])
         rollouts.compute_returns(next_value, ppo_cfg.use_gae, ppo_cfg.gamma, ppo_cfg.tau)
-        value_loss, action_loss, dist_entropy, _vd, _rd, _ul = self.agent.update(rollouts)
+        with _lib.nvtx_range("ppo_update"):
+            value_loss, action_loss, dist_entropy, _vd, _rd, _ul = self.agent.update(rollouts)
         rollouts.after_update()
         return value_loss, action_loss, dist_entropy

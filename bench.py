@@ -456,6 +456,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-shares", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="audio_sweep: headline point only")
     ap.add_argument("--tc-level", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 encoders (default), 2 + SMT")
     ap.add_argument("--clip-layers", type=int, default=None, help="interactive configs: CLIP text tower depth (default 12)")
     args = ap.parse_args()

@@ -99,6 +99,11 @@ int avl_belief_update(int n_envs, const float* spectrogram, int spec_elems_per_e
  * minibatch copies of rollout_storage.py:716-760 are never made.  y: (N, H/2, W/2, C_out) fp32, channels >= C zero.     */
 int avl_resize_half_typed(const void* x, int dtype, const long long* sample_index, float* y, int N, int H, int W, int C,
                           int C_out, float scale, void* stream);
+/* RolloutStorage.insert (savi/models/rollout_storage.py:214-295) as ONE launch: up to 48 (dst, src, n, kind) segments
+ * (host arrays of device pointers); kind 0 byte copy (n bytes), 1 fp32 -> uint8, 2 fp32 -> fp16, 3 int64 -> fp32,
+ * 4 fp32 -> int64 (n elements).                                                                                        */
+int avl_multi_copy(int count, void* const* dst, const void* const* src, const long long* n, const unsigned char* kind,
+                   void* stream);
 /* ------------------------------------------------------------------- graph-walk environment step
  * One launch for all envs: graph walk (soundspaces/simulator.py:496-517), first oracle action of the shortest path
  * (:758-787), reward (ss_baselines/common/environments.py:98-135), PoseSensor (soundspaces/tasks/nav.py:745-775), episode
