@@ -70,6 +70,7 @@ struct HaloArgs {
   int relu;
   int vec_store;       // y rows are 16-byte aligned
   int N, H, W, C, Cout, KH, KW;
+  int os, OH, OW;      // output stride (1, or 2: only the even positions of the stride-1 grid are stored) / output map
   int R;               // output rows per strip
   int Wp;              // padded pitch W + KW - 1
   int tiles;           // ceil(R * Wp / 128)
@@ -300,8 +301,11 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
         const int ohl = q / p.Wp;
         const int ow0 = q - ohl * p.Wp;
         const int oh = oh0 + ohl;
-        const bool row_ok = ohl < p.R && oh < p.H;
-        const long long pix0 = ((long long)n * p.H + oh) * p.W + ow0;
+        // stride 2 (pad = K / 2): output (oh2, ow2) is the stride-1 output at (2 oh2, 2 ow2) — the strip is convolved at
+        // stride 1 on the tensor cores (which this HBM-bound kernel has to spare) and only the even positions leave
+        const bool row_ok = ohl < p.R && oh < p.H && (p.os == 1 || !(oh & 1));
+        const long long pix0 = p.os == 1 ? ((long long)n * p.H + oh) * p.W + ow0
+                                         : ((long long)n * p.OH + (oh >> 1)) * p.OW + (ow0 >> 1);
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.ncols);
         mbar_wait(ACC_FULL(a), (uint32_t)((it_tile >> 1) & 1));
         tc_fence_after();
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
           }
           const int dx = p.G > 1 ? cc / p.Cout : 0;  // accumulator columns are (dx, cout); Cout % 16 == 0
           const int c0 = cc - dx * p.Cout;
-          const bool valid = row_ok && ow0 + dx < p.W;
+          const bool valid = row_ok && ow0 + dx < p.W && (p.os == 1 || !(ow0 & 1));
           const long long pix = pix0 + dx;
           if (valid) {
             float* yrow = reinterpret_cast<float*>(p.y) + pix * p.ldy + c0;  // (OUT16: recomputed below)
@@ -360,8 +364,18 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
 static int g_halo_on = 1;
 static int g_halo_group = 0;  // pixel groups (G > 1): measured SLOWER on B200 (see header), kept as an opt-in
 static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
+static int g_halo_stride2 = 1;  // stride-2 same-padded convolutions: stride-1 strip convolution, even positions stored
 
 }  // namespace
+
+// 1 (default): stride-2 odd-kernel convolutions with pad = K / 2 (the stage-entry convolutions of the ResNet-18s) run
+// on the halo-strip kernel too (computed at stride 1, only the even positions are stored); 0: im2col kernel.  Returns old.
+AVL_API int avl_set_tc_conv_halo_stride2(int on) {
+  avl_bump_config_epoch();
+  int old = g_halo_stride2;
+  g_halo_stride2 = on ? 1 : 0;
+  return old;
+}
 
 // 1 (default): stride-1 same-padded convolutions with few channels use the halo-strip kernel; 0: always the
 // im2col-gather kernel.  rows > 0 sets the strip height, rows == 0 selects it per shape (default), rows < 0 keeps it.
@@ -388,7 +402,8 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
                            int KW, int stride, int pad, const float* scale, const float* bias, const float* residual,
                            long long ldr, int relu, void* y, int out16, long long ldy, cudaStream_t stream) {
   if (!g_halo_on) return AVL_ERR_UNSUPPORTED;
-  if (stride != 1 || KH != KW || !(KH & 1) || pad != KH / 2 || KH < 3) return AVL_ERR_UNSUPPORTED;
+  if ((stride != 1 && stride != 2) || KH != KW || !(KH & 1) || pad != KH / 2 || KH < 3) return AVL_ERR_UNSUPPORTED;
+  if (stride == 2 && !g_halo_stride2) return AVL_ERR_UNSUPPORTED;
   if (in16) {
     if ((C % 16) || C > 128) return AVL_ERR_UNSUPPORTED;
   } else if (!(C == 4 || (C % 8 == 0 && C <= 64))) {
@@ -401,12 +416,13 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   HaloArgs p = {};
   p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
   p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
+  p.os = stride; p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KW) / stride + 1;
   const int nc_ = C / cpc;
   const bool c4 = !in16 && C == 4;
   // pixels per MMA row: fill N up to 64 accumulator columns when Cout is small (see the header); kept at 1 for the
   // C == 4 stem path, for wide kernels whose descriptor table would not fit the parameter space, and when disabled
   int G = 1;
-  if (g_halo_group && !c4 && KH == 3) {
+  if (g_halo_group && !c4 && KH == 3 && stride == 1) {
     if (Cout * 4 <= 64 && (W % 4) == 0) G = 4;
     else if (Cout * 2 <= 64 && (W % 2) == 0) G = 2;
     if (KH * (KW + G - 1) * (nc_ / 2) > HL_PARAM_MMA) G = 1;

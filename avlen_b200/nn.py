@@ -46,6 +46,7 @@ _lib.register({
     "avl_set_f16_activations": [I],
     "avl_set_resnet_graphs": [I],
     "avl_set_tc_conv_halo_group": [I],
+    "avl_set_tc_conv_halo_stride2": [I],
     "avl_tc_conv_halo_f16": [P, I, I, I, I, I, P, I, I, I, I, I, P, I, P],
     "avl_groupnorm_fwd_cluster_f16": [P, P, P, P, P, I, I, I, I, I, F, I, P],
     "avl_set_wgrad_desc": [I, I],

@@ -235,6 +235,7 @@ int avl_f16_overflow(int reset);
  * graph the second time they are seen and replayed afterwards (1 graph launch instead of ~50-100 kernel launches).  */
 int avl_set_resnet_graphs(int on);     /* returns old */
 long long avl_resnet_graph_stats(int what);   /* 0: replays, 1: captures */
+int avl_set_tc_conv_halo_stride2(int on); /* stride-2 same-padded convs on the halo-strip kernel (stride-1 strip, even positions stored); returns old */
 int avl_set_tc_conv_halo_group(int on); /* halo-strip conv: 2 / 4 adjacent pixels per MMA row when Cout <= 32; returns old */
 int avl_tc_conv_halo_f16(const void* x, int in16, int N, int H, int W, int C, const void* w_packed, int Cout, int KH,
                          int KW, int pad, int relu, void* y, int out16, void* stream);
