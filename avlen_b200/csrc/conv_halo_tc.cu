@@ -404,6 +404,9 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   if (!g_halo_on) return AVL_ERR_UNSUPPORTED;
   if ((stride != 1 && stride != 2) || KH != KW || !(KH & 1) || pad != KH / 2 || KH < 3) return AVL_ERR_UNSUPPORTED;
   if (stride == 2 && !g_halo_stride2) return AVL_ERR_UNSUPPORTED;
+  // measured (profiles/r02_halo_stride2_bench.txt, fp32 / TF32 operands): the stride-1 strip wins for the stage-2 entry
+  // (16 -> 32 @64x64: 1.06 -> 0.88 ms at batch 4800) and loses from 32 input channels on (0.47 -> 0.59 ms): 4x the MMAs
+  if (stride == 2 && !in16 && C > 16) return AVL_ERR_UNSUPPORTED;
   if (in16) {
     if ((C % 16) || C > 128) return AVL_ERR_UNSUPPORTED;
   } else if (!(C == 4 || (C % 8 == 0 && C <= 64))) {
