@@ -22,6 +22,7 @@ _SIGNATURES = {
     "avl_last_cuda_error": [],
     "avl_device_sm_count": [],
     "avl_launch_count": [],
+    "avl_launch_count_add": [c_longlong],
     "avl_audio_create": [I, ctypes.POINTER(c_void_p)],
     "avl_audio_destroy": [P],
     "avl_audio_status": [P, ctypes.POINTER(c_int)],
@@ -36,13 +37,14 @@ _SIGNATURES = {
     "avl_ppo_loss_workspace": [I],
     "avl_ppo_loss_fwd_bwd": [I, I, P, P, P, P, P, P, P, P, P, P, F, F, F, F, I, P, P, P, P, P, P],
     "avl_extmem_insert": [P, P, P, P, P, I, I, I, I, I, P],
+    "avl_extmem_insert_dev": [P, P, P, P, P, I, I, I, I, P, P],
     "avl_masked_weighted_ce": [P, P, P, P, I, I, P, P, P],
     "avl_belief_update": [I, P, I, P, P, P, P, I, F, I, P, P, P, P, P, P, P, P],
     "avl_synth_env_step": [I, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_grad_sumsq": [P, L, P, P, P],
     "avl_clip_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P, F, P],
 }
-_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_launch_count": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
+_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_launch_count": c_longlong, "avl_launch_count_add": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
 
 _lib = None
 

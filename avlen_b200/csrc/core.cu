@@ -43,6 +43,12 @@ AVL_API int avl_device_sm_count(void) { return avl_num_sms(); }
 
 // Number of kernels this library has launched so far in this process (bench.py's gpu_launches).
 AVL_API long long avl_launch_count(void) { return g_launches; }
+// A caller that replays kernels of this library through a CUDA graph of its own (the trainer's whole-step graphs)
+// reports the launches of each replay here, so that the count stays the number of kernels that actually ran.
+AVL_API long long avl_launch_count_add(long long n) {
+  g_launches += n;
+  return g_launches;
+}
 
 // Tensor-core (tcgen05, TF32 operands) level: 0 = fp32 SIMT kernels only; 1 (default) = encoder convolutions /
 // fully-connected layers (stated tolerance 2e-3 of the output range; the reference's cuDNN convolutions also run

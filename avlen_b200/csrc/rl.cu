@@ -304,6 +304,35 @@ __global__ void extmem_insert_kernel(float* memory, float* masks, const float* _
   }
 }
 
+// The same with the ring position read from device memory (a rollout step captured into a CUDA graph must not bake the
+// position into its kernel arguments); counter_advance_kernel moves it afterwards.
+__global__ void extmem_insert_dev_kernel(float* memory, float* masks, const float* __restrict__ feats,
+                                         const float* __restrict__ not_done, float* snapshot, int n, int total,
+                                         int capacity, int dim, const int* __restrict__ idx_dev) {
+  __shared__ float red[33];
+  const int idx = *idx_dev;
+  const int e = blockIdx.x;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x)
+    memory[((size_t)idx * n + e) * dim + i] = feats[(size_t)e * dim + i];
+  float* mrow = masks + (size_t)e * total;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) s += mrow[i];
+  s = block_sum(s, red);
+  const bool overflow = (s == (float)capacity);
+  int evict = idx - capacity;
+  if (evict < 0) evict += total;
+  const float nd = not_done[e];
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    float m = mrow[i];
+    if (overflow && i == evict) m = 0.f;
+    if (i == idx) m = 1.f;
+    m *= nd;
+    mrow[i] = m;
+    if (snapshot) snapshot[(size_t)e * total + i] = m;
+  }
+}
+__global__ void counter_advance_kernel(int* c, int mod) { *c = (*c + 1) % mod; }
+
 // ------------------------------------------------ belief EMA update (row M)
 // belief_predictor.py:139-230 batched: odom<->base transforms and EMA per env.
 __device__ __forceinline__ void odom_to_base(float gx, float gy, const float* pose, float& bx, float& by) {
@@ -616,6 +645,20 @@ AVL_API int avl_extmem_insert(float* memory, float* masks, const float* feats, c
   if (!memory || !masks || !feats || !not_done) return AVL_ERR_ARG;
   extmem_insert_kernel<<<n_envs, 128, 0, (cudaStream_t)stream>>>(memory, masks, feats, not_done, mask_snapshot,
                                                                 n_envs, total_size, capacity, dim, idx);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_extmem_insert_dev(float* memory, float* masks, const float* feats, const float* not_done,
+                                  float* mask_snapshot, int n_envs, int total_size, int capacity, int dim, int* idx_dev,
+                                  void* stream) {
+  if (n_envs < 0 || total_size < 1 || capacity < 0 || dim < 1) return AVL_ERR_ARG;
+  if (n_envs == 0) return AVL_OK;
+  if (!memory || !masks || !feats || !not_done || !idx_dev) return AVL_ERR_ARG;
+  extmem_insert_dev_kernel<<<n_envs, 128, 0, (cudaStream_t)stream>>>(memory, masks, feats, not_done, mask_snapshot,
+                                                                    n_envs, total_size, capacity, dim, idx_dev);
+  AVL_LAUNCH_CHECK();
+  counter_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(idx_dev, total_size);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

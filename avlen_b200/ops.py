@@ -141,6 +141,14 @@ def extmem_insert(memory, masks, feats, not_done, snapshot, capacity, idx):
          fptr(snapshot), n, total, int(capacity), dim, int(idx), stream())
 
 
+def extmem_insert_dev(memory, masks, feats, not_done, snapshot, capacity, idx_dev):
+    """``extmem_insert`` with the ring position in device memory (advanced by the call): CUDA-graph safe."""
+    total, n, dim = memory.shape
+    feats, not_done = feats.contiguous(), not_done.contiguous()
+    call("avl_extmem_insert_dev", fptr(memory), fptr(masks), fptr(feats), fptr(not_done), fptr(snapshot), n, total,
+         int(capacity), dim, dptr(idx_dev, torch.int32), stream())
+
+
 def belief_update(spectrogram, pose, dones, pointgoal_pred, label_pred, w, current_pred_only, last_pointgoal,
                   has_pointgoal, last_label, has_label, location_belief, category_belief, scratch):
     """BeliefPredictor.update scalar part, batched (belief_predictor.py:139-230)."""

@@ -43,7 +43,10 @@ def savi_config(**overrides):
                NUM_DIALOG_STEPS=3, ORACLE_WHEN_QUERIED=True, QUERY_WITHIN_RADIUS=True, ALLOW_STOP=False,
                CONSECUTIVE_REWARD=-0.5, NUM_TOTAL_QUERY=3, QUERY_COUNT_EMB_SIZE=32, clip_layers=12, graph_env=None,
                # rgb uint8 / depth fp16 in the rollout storage and on the H2D path
-               compact_observations=True)
+               compact_observations=True,
+               # whole-rollout-step CUDA graphs (frozen encoders, device-resident env): the ~230 launches of a step
+               # replay as ONE graph launch per step from the third rollout on
+               step_graphs=True)
     cfg.update(overrides)
     return types.SimpleNamespace(**cfg)
 
@@ -148,7 +151,8 @@ class DDPPOTrainer(PPOTrainer):
         interactive = cfg.policy_type == "interactive"
         if envs is None:
             kw = dict(seed=cfg.seed + self.world_rank, sr=cfg.sampling_rate, host_buffers=cfg.host_buffers,
-                      distractor=cfg.has_distractor_sound, compact=cfg.compact_observations)
+                      distractor=cfg.has_distractor_sound, compact=cfg.compact_observations,
+                      pool=5)  # (a frame pool whose size divides the 150-step rollout: step s always serves frame s % 5)
             if interactive or cfg.graph_env:
                 # the interactive step needs what only a navigation graph provides: oracle actions, target distance,
                 # episode boundaries, query-aware rewards (ppo_trainer.py:336-345,:642,:706-710)
@@ -187,9 +191,56 @@ class DDPPOTrainer(PPOTrainer):
             self.rollouts.observations[sensor][0].copy_(observations[sensor])
         return self
 
+    # ---- whole-step CUDA graphs -----------------------------------------------------------------------------------
+    # A rollout step at 64 envs is ~230 small kernels on five streams, issued by ~25 ctypes / torch calls: the host
+    # needs ~1.2 ms per step to issue them and its pauses stagger the four ResNet-18 chains by 150-470 us
+    # (profiles/r02_trace_rollout_step_timeline.txt).  Every device address a step touches is fixed by its position
+    # ``s`` in the rollout (storage slot s / s + 1, persistent env / belief / memory state, the ring position lives in
+    # device memory), so step ``s`` is captured ONCE (during the second rollout, after an eager warm-up rollout) and
+    # replayed afterwards: one graph launch per step, every dependency resolved on the device.
+    # Conditions: plain SMT policy, frozen encoders (a trained encoder re-packs its weights into new buffers),
+    # device-resident env (host frames are staged by the host every step), no preemption.
+    def _step_graphs_possible(self):
+        cfg = self.config
+        return (getattr(cfg, "step_graphs", False) and cfg.policy_type == "smt" and cfg.freeze_encoders
+                and not cfg.host_buffers and not cfg.use_preemption and getattr(self.envs, "fused_step", False)
+                and getattr(self, "_step_graphs_ok", True))
+
+    def _capture_step(self, s):
+        # (capture_begin / capture_end directly: the torch.cuda.graph context synchronises the device, runs the garbage
+        # collector and empties the allocator cache on every entry — 150 times per rollout)
+        net = self.actor_critic.net
+        g = torch.cuda.CUDAGraph()
+        n0 = int(_lib.lib().avl_launch_count())
+        kw = {"pool": self._graph_pool} if self._graph_pool is not None else {}
+        g.capture_begin(capture_error_mode="relaxed", **kw)
+        try:
+            self._collect_rollout_step(self.rollouts)
+            K.sync_pending()      # deferred belief update: joined inside the captured step
+            net.join_prefetch()   # encoder prefetch of slot s + 1: complete when the step's graph completes
+        finally:
+            g.capture_end()
+        if self._graph_pool is None:
+            self._graph_pool = g.pool()
+        n1 = int(_lib.lib().avl_launch_count())
+        g._avl_launches = n1 - n0
+        _lib.lib().avl_launch_count_add(-(n1 - n0))  # counted at capture, but nothing ran yet
+        return g
+
+    def _replay_step(self, g):
+        g.replay()
+        _lib.lib().avl_launch_count_add(g._avl_launches)
+        # the host-side counters the eager step advances
+        r = self.rollouts
+        r.step += 1
+        r.em.advance_host_index()
+        self.envs._t += 1
+
     def collect_rollout(self):
         """The 150-step rollout loop (ddppo_trainer.py:894-959)."""
         cfg = self.config
+        if self._step_graphs_possible():
+            return self._collect_rollout_graphed()
         store = distrib.distributed_c10d._get_default_store() if (self.world_size > 1 and cfg.use_preemption) else None
         for step in range(cfg.num_steps):
             with _lib.nvtx_range("rollout_step"):
@@ -200,6 +251,50 @@ class DDPPOTrainer(PPOTrainer):
         if store is not None:
             store.add("num_done", 1)
         K.sync_pending()  # the last step's deferred belief update joins the main stream here
+        return self.rollouts.step * self.envs.num_envs
+
+    def _collect_rollout_graphed(self):
+        cfg = self.config
+        main = torch.cuda.current_stream()
+        if getattr(self, "_rollout_stream", None) is None:
+            self._rollout_stream = torch.cuda.Stream()
+            self._graph_pool = None
+            self._step_graphs = None
+            self._rollouts_seen = 0
+        rs = self._rollout_stream
+        rs.wait_stream(main)
+        net = self.actor_critic.net
+        try:
+            with torch.cuda.stream(rs):
+                if self._step_graphs is not None:
+                    for g in self._step_graphs:
+                        self._replay_step(g)
+                elif self._rollouts_seen == 0:
+                    # warm-up rollout on the rollout stream: allocator, lazy library state, per-stream resources
+                    for _ in range(cfg.num_steps):
+                        self._collect_rollout_step(self.rollouts)
+                    K.sync_pending()
+                else:
+                    net.drop_prefetch()
+                    torch.cuda.synchronize()
+                    graphs = []
+                    for s in range(cfg.num_steps):
+                        g = self._capture_step(s)
+                        g.replay()
+                        _lib.lib().avl_launch_count_add(g._avl_launches)
+                        graphs.append(g)
+                    self._step_graphs = graphs
+                    # the prefetch entry the last captured step left behind is owned by its graph: drop the host handle
+                    net._prefetched().clear()
+            self._rollouts_seen += 1
+        except Exception as e:  # capture not possible in this environment: stay eager for good
+            import warnings
+            warnings.warn(f"avlen_b200: whole-step CUDA graphs disabled ({type(e).__name__}: {e})", RuntimeWarning)
+            self._step_graphs_ok = False
+            self._step_graphs = None
+            torch.cuda.synchronize()
+            raise
+        main.wait_stream(rs)
         return self.rollouts.step * self.envs.num_envs
 
     def reset_preemption_counter(self):

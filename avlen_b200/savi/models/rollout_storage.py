@@ -45,15 +45,26 @@ class ExternalMemory:
         self.masks = torch.zeros(num_envs, total_size)
         self.memory = torch.zeros(total_size, num_envs, dim)  # single copy (see module docstring)
         self.idx = 0
+        self.idx_dev = None  # device mirror of ``idx`` (int32[1]): what the insert kernel reads (CUDA-graph safe)
         self.num_steps = num_steps
 
     def insert(self, em_features, not_done_masks, snapshot=None):
-        ops.extmem_insert(self.memory, self.masks, em_features, not_done_masks, snapshot, self.capacity, self.idx)
+        if self.idx_dev is not None:
+            ops.extmem_insert_dev(self.memory, self.masks, em_features, not_done_masks, snapshot, self.capacity,
+                                  self.idx_dev)
+        else:
+            ops.extmem_insert(self.memory, self.masks, em_features, not_done_masks, snapshot, self.capacity, self.idx)
+        self.advance_host_index()
+
+    def advance_host_index(self):
+        """The host copy of the ring position (the device copy is advanced by the insert kernel)."""
         self.idx = (self.idx + 1) % self.total_size
 
     def to(self, device):
         self.masks = self.masks.to(device)
         self.memory = self.memory.to(device)
+        if self.memory.is_cuda:
+            self.idx_dev = torch.full((1,), self.idx, dtype=torch.int32, device=device)
 
 
 class RolloutStorage:

@@ -394,11 +394,23 @@ class AudioNavSMTNet(Net):
             ev.record(stream)
         self._prefetched()[key] = (x, ev)
 
+    def join_prefetch(self):
+        """Make the current stream wait for every enqueued prefetch WITHOUT consuming it (a rollout step captured into
+        a CUDA graph must have all its side-stream work joined before the capture ends; the next step's ``act`` then
+        finds the features complete)."""
+        cur = torch.cuda.current_stream()
+        d = self._prefetched()
+        for k, (x, ev) in list(d.items()):
+            if ev is not None:
+                cur.wait_event(ev)
+                d[k] = (x, None)  # joined: the consumer must not wait on an event that belongs to an ended capture
+
     def drop_prefetch(self):
         d = self._prefetched()
         cur = torch.cuda.current_stream()
         for _x, ev in d.values():  # the encoders' workspaces are per network: whatever was enqueued must finish first
-            cur.wait_event(ev)
+            if ev is not None:
+                cur.wait_event(ev)
         d.clear()
 
     def _take_prefetch(self, observations, n, cols):
@@ -408,13 +420,14 @@ class AudioNavSMTNet(Net):
         hit = d.pop(self.observation_key(observations), None)
         if hit is None or tuple(hit[0].shape) != (n, cols):
             # the caller is about to run the encoders itself: nothing enqueued earlier may still be using them
-            if hit is not None:
+            if hit is not None and hit[1] is not None:
                 torch.cuda.current_stream().wait_event(hit[1])
             self.drop_prefetch()
             return None
         x, ev = hit
         cur = torch.cuda.current_stream()
-        cur.wait_event(ev)
+        if ev is not None:
+            cur.wait_event(ev)
         x.record_stream(cur)
         return x
 

@@ -22,7 +22,8 @@ int avl_version(void);
 int avl_last_cuda_error(void);                 /* cudaError_t of the last failed runtime call (0 = none)  */
 const char* avl_last_cuda_error_string(void);
 int avl_device_sm_count(void);
-long long avl_launch_count(void);              /* kernels launched by this library so far in this process */
+long long avl_launch_count(void);
+long long avl_launch_count_add(long long n); /* kernels of this library replayed through a caller-owned CUDA graph */              /* kernels launched by this library so far in this process */
 int avl_set_tensor_cores(int level);           /* tcgen05 TF32: 0 off, 1 (default) encoder convs/FCs, 2 also SMT dense; returns old */
 int avl_get_tensor_cores(void);
 
@@ -84,6 +85,10 @@ int avl_ppo_loss_fwd_bwd(int B, int A, const float* logits, const long long* act
  * memory (total, N, dim), masks (N, total); bit-exact.                                                         */
 int avl_extmem_insert(float* memory, float* masks, const float* feats, const float* not_done, float* mask_snapshot,
                       int n_envs, int total_size, int capacity, int dim, int idx, void* stream);
+/* The same with the ring position in DEVICE memory (read by the kernel, advanced modulo total_size afterwards): a rollout
+ * step captured into a CUDA graph replays with the right slot.                                                          */
+int avl_extmem_insert_dev(float* memory, float* masks, const float* feats, const float* not_done, float* mask_snapshot,
+                          int n_envs, int total_size, int capacity, int dim, int* idx_dev, void* stream);
 
 /* --------------------------------------------------------------------- row M (scalar part): belief update
  * ss_baselines/savi/models/belief_predictor.py:139-230 (EMA + odom<->base transforms), batched.                */

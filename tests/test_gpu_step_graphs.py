@@ -1,0 +1,77 @@
+"""Whole-rollout-step CUDA graphs (DDPPOTrainer._collect_rollout_graphed): the replayed steps must leave the rollout
+storage in exactly the state an eager rollout leaves it in — checked through the quantities PPO relies on: re-evaluating
+the stored rollout with the (unchanged) policy reproduces the stored values / log-probs, the ring-memory masks follow
+ExternalMemory.insert (rollout_storage.py:930-941) across rollouts (the ring position lives in device memory), the
+env's episode counters advance every step."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_rollout(tr, cfg, masks0, idx0):
+    rs = tr.rollouts
+    T, N = rs.step, tr.envs.num_envs
+    assert T == cfg.num_steps
+    # 1. ring memory masks follow the reference rule from the state before the rollout
+    total, cap = rs.em.total_size, rs.em.capacity
+    m = masks0.clone()
+    idx = idx0
+    nd = rs.masks.cpu()
+    snaps = rs.em_masks.cpu()
+    for s in range(T):
+        over = m.sum(1) == cap
+        m[over, idx - cap] = 0.0
+        m[:, idx] = 1.0
+        m *= nd[s + 1]
+        idx = (idx + 1) % total
+        assert torch.equal(snaps[s + 1], m), s
+    assert rs.em.idx == idx and int(rs.em.idx_dev.cpu()) == idx
+    # 2. the env ran every step: the pose's episode-time column is 0 after a done, else previous + 1
+    t = rs.observations["pose"][:T + 1, :, 3].cpu()
+    for s in range(T):
+        want = torch.where(nd[s + 1, :, 0] > 0, t[s] + 1, torch.zeros(N))
+        assert torch.equal(t[s + 1], want), s
+    # 3. the stored values / log-probs are what the policy computes on the stored observations and memory
+    adv = torch.zeros(T, N, 1, device="cuda")
+    worst = 0.0
+    for sample in rs.recurrent_generator(adv, 1, perm=torch.arange(N)):
+        obs, h, acts, _, prev, vp, _, masks, old_lp = sample[:9]
+        em, em_masks = sample[12], sample[16]
+        with torch.no_grad():
+            v, lp, _, _, _ = tr.actor_critic.evaluate_actions(obs, h, prev, masks, acts, em, em_masks)
+        worst = max(worst, float((lp - old_lp).abs().max()), float((v - vp).abs().max()))
+    return worst, m, idx
+
+
+def test_graphed_rollouts_equal_eager_semantics():
+    from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
+    # memory 12 >= the 10 steps of a rollout: every memory row a stored step attended to is still in the ring afterwards
+    cfg = savi_config(NUM_PROCESSES=6, num_steps=10, memory_size=12, step_graphs=True)
+    tr = DDPPOTrainer(cfg).setup()
+    assert tr._step_graphs_possible()
+    masks0, idx0 = tr.rollouts.em.masks.cpu().clone(), tr.rollouts.em.idx
+    for r in range(5):  # eager warm-up, capture, three replays
+        tr.collect_rollout()
+        if r >= 1:
+            assert tr._step_graphs is not None and len(tr._step_graphs) == cfg.num_steps
+        worst, masks0, idx0 = _check_rollout(tr, cfg, masks0, idx0)
+        assert worst < 2e-3, (r, worst)
+        tr.rollouts.after_update()  # (no optimizer step: the policy stays the one that acted)
+    # and the full cycle with updates keeps running on the graphs
+    for _ in range(2):
+        tr.collect_rollout()
+        stats = tr._update_agent(cfg, tr.rollouts)
+        assert all(np.isfinite(v) for v in stats)
+    tr.envs.close()
+
+
+def test_step_graphs_are_skipped_where_they_do_not_apply():
+    from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
+    for over in (dict(freeze_encoders=False, pretraining=True), dict(host_buffers=True)):
+        tr = DDPPOTrainer(savi_config(NUM_PROCESSES=4, num_steps=4, memory_size=4, **over)).setup()
+        assert not tr._step_graphs_possible()
+        tr.collect_rollout()
+        tr.collect_rollout() if False else None
+        tr.envs.close()
