@@ -117,19 +117,49 @@ def linear_decay(epoch: int, total_num_updates: int) -> float:
     return 1 - (epoch / float(total_num_updates))
 
 
+_STACK_POOL = None
+_STACK_WORKERS = 4
+
+
+def _stack_pool():
+    global _STACK_POOL
+    if _STACK_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _STACK_POOL = ThreadPoolExecutor(max_workers=_STACK_WORKERS, thread_name_prefix="avl_batch_obs")
+    return _STACK_POOL
+
+
+def _stack_into(observations, sensor, out):
+    """np.stack of one sensor into ``out`` (pinned staging).  Large sensors (frames) are copied by a few threads, each
+    taking a contiguous range of envs — numpy's copy loops release the GIL, and at 64 envs the 7 MB of rgb + depth
+    otherwise cost the host thread more than a whole policy step costs the GPU."""
+    n = len(observations)
+    if out.nbytes < (1 << 20) or n < 2 * _STACK_WORKERS:
+        np.stack([np.asarray(o[sensor]) for o in observations], out=out)
+        return []
+    per = (n + _STACK_WORKERS - 1) // _STACK_WORKERS
+
+    def job(lo, hi):
+        for i in range(lo, hi):
+            out[i] = observations[i][sensor]
+
+    return [_stack_pool().submit(job, lo, min(n, lo + per)) for lo in range(0, n, per)]
+
+
 def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, pinned: Optional[Dict] = None,
               keep_dtypes: Optional[Dict] = None):
     """common/utils.py:129-156: list of per-env observation dicts -> dict of stacked tensors on ``device``.
 
     The reference inflates every sensor to fp32 on the host before a pageable copy; here each sensor is stacked ONCE,
     in its source dtype, straight into pinned staging memory (``pinned``: a dict the caller keeps between steps; two
-    buffers per sensor alternate so that the copy of step s may still be in flight while step s+1 is staged), copied
-    asynchronously and converted on the device.  ``keep_dtypes``: sensors listed there stay in the
-    given dtype on the device (``{"rgb": torch.uint8, "depth": torch.float16}`` for the compact rollout storage);
-    everything else becomes float32 as in the reference."""
+    buffers per sensor alternate so that the copy of step s may still be in flight while step s+1 is staged; frames
+    are stacked by a small thread pool), copied asynchronously and converted on the device.  ``keep_dtypes`` (SURVEY
+    §8f item 2): sensors listed there stay in the given dtype on the device (``{"rgb": torch.uint8, "depth":
+    torch.float16}`` for the compact rollout storage); everything else becomes float32 as in the reference."""
     out = {}
     first = observations[0]
     n = len(observations)
+    staged = []
     for sensor in first:
         a0 = np.asarray(first[sensor])
         if pinned is not None:
@@ -141,12 +171,14 @@ def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, p
             bufs, k, evs = slot
             if evs[k] is not None:
                 evs[k].synchronize()  # the H2D copy that last read this buffer (two steps ago) must have finished
-            np.stack([np.asarray(o[sensor]) for o in observations], out=bufs[k].numpy())
-            t = bufs[k]
+            staged.append((sensor, bufs[k], slot, k, _stack_into(observations, sensor, bufs[k].numpy())))
         else:
-            t = torch.from_numpy(np.stack([np.asarray(o[sensor]) for o in observations]))
+            staged.append((sensor, torch.from_numpy(np.stack([np.asarray(o[sensor]) for o in observations])), None, 0, []))
+    for sensor, t, slot, k, jobs in staged:
+        for j in jobs:
+            j.result()
         d = t.to(device=device, non_blocking=True)
-        if pinned is not None and d.is_cuda:
+        if slot is not None and d.is_cuda:
             ev = torch.cuda.Event()
             ev.record()
             slot[2][k] = ev

@@ -470,5 +470,18 @@ def main():
     return bench_configs.run(args)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as distrib
+        if distrib.is_available() and distrib.is_initialized():
+            distrib.barrier()
+            distrib.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

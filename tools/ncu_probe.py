@@ -1,0 +1,44 @@
+"""Launches ONE kernel of interest a few times (for `ncu -k regex:<name> -s 2 -c 1`); diagnostic.
+    python tools/ncu_probe.py wgrad_l1 | wgrad_l3 | gn_bwd_l1 | halo_s2 | resize_u8 | multi_copy"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avlen_b200 import nn as K
+
+
+def main():
+    what = sys.argv[1]
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 4800
+    K.set_tensor_cores(1)
+    if what.startswith("wgrad"):
+        H, C, Co = {"wgrad_l1": (64, 16, 16), "wgrad_l2": (32, 32, 32), "wgrad_l3": (16, 64, 64), "wgrad_l4": (8, 128, 128)}[what]
+        x = torch.randn(B, H, H, C, device="cuda")
+        gy = torch.randn(B, H, H, Co, device="cuda")
+        for _ in range(4):
+            K.conv2d_wgrad_tc(x, gy, (Co, C, 3, 3), 1, 1)
+    elif what == "gn_bwd_l1":
+        x = torch.randn(B, 64, 64, 16, device="cuda", requires_grad=True)
+        g = torch.ones(16, device="cuda", requires_grad=True)
+        b = torch.zeros(16, device="cuda", requires_grad=True)
+        gy = torch.randn(B, 64, 64, 16, device="cuda")
+        y = K.groupnorm(x, g, b, 16, 1e-5, relu=True)
+        for _ in range(4):
+            y.backward(gy, retain_graph=True)
+    elif what == "halo_s2":
+        x = torch.randn(B, 64, 64, 16, device="cuda")
+        w = torch.randn(32, 16, 3, 3, device="cuda") / 12
+        for _ in range(4):
+            K._conv2d_raw(x, w, None, 2, 1)
+    elif what == "resize_u8":
+        x = torch.randint(0, 256, (B, 128, 128, 3), dtype=torch.uint8, device="cuda")
+        for _ in range(4):
+            K.resize_half(x, 1 / 255.0, 4)
+    torch.cuda.synchronize()
+    print("ok")
+
+
+if __name__ == "__main__":
+    main()
