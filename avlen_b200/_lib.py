@@ -23,6 +23,8 @@ _SIGNATURES = {
     "avl_device_sm_count": [],
     "avl_launch_count": [],
     "avl_launch_count_add": [c_longlong],
+    "avl_spec_cache_lookup": [I, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "avl_spec_cache_commit": [I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "avl_audio_create": [I, ctypes.POINTER(c_void_p)],
     "avl_audio_destroy": [P],
     "avl_audio_status": [P, ctypes.POINTER(c_int)],

@@ -123,6 +123,90 @@ class AudioRenderer:
         return (ag.cpu().numpy() if ag is not None else None), spec.cpu().numpy()
 
 
+class RirBank:
+    """A scene's binaural RIRs as ONE packed tensor in HBM + a dense ``(azimuth, receiver, source) -> (offset, length)``
+    table.  The reference opens ``{binaural_rir_dir}/{azimuth}/{receiver}_{source}.wav`` on every
+    audiogoal miss (soundspaces/simulator.py:650-659); ``from_wav_dir`` reads that layout once, ``save`` / ``load`` keep
+    the packed form (``.npz``: ``rirs`` (sum L, 2) float32 [or float16 with ``half=True``], ``off``, ``len``)."""
+
+    AZIMUTHS = (0, 90, 180, 270)
+
+    def __init__(self, rirs, off, length, device="cuda"):
+        self.device = torch.device(device)
+        rirs = np.ascontiguousarray(rirs)
+        self.rirs = torch.from_numpy(rirs.astype(np.float32, copy=False)).to(self.device)
+        self.off = torch.from_numpy(np.ascontiguousarray(off, dtype=np.int64)).to(self.device)     # (4, V, V) frames
+        self.len = torch.from_numpy(np.ascontiguousarray(length, dtype=np.int32)).to(self.device)  # 0: empty / unreadable
+        self.V = int(self.off.shape[1])
+
+    @classmethod
+    def from_wav_dir(cls, rir_dir, num_nodes, device="cuda"):
+        """simulator.py:650-659: float32 wav per (azimuth, receiver, source); unreadable or empty files -> length 0."""
+        from scipy.io import wavfile
+        import os
+        chunks, off, ln, at = [], np.zeros((4, num_nodes, num_nodes), np.int64), np.zeros((4, num_nodes, num_nodes), np.int32), 0
+        for a, az in enumerate(cls.AZIMUTHS):
+            for r in range(num_nodes):
+                for s in range(num_nodes):
+                    f = os.path.join(rir_dir, str(az), f"{r}_{s}.wav")
+                    try:
+                        _, h = wavfile.read(f)
+                    except (ValueError, FileNotFoundError):
+                        h = np.zeros((0, 2), np.float32)
+                    h = np.asarray(h, np.float32).reshape(-1, 2)
+                    off[a, r, s], ln[a, r, s] = at, len(h)
+                    chunks.append(h)
+                    at += len(h)
+        rirs = np.concatenate(chunks, 0) if at else np.zeros((1, 2), np.float32)
+        return cls(rirs, off, ln, device)
+
+    def save(self, path, half=False):
+        np.savez_compressed(path, rirs=self.rirs.cpu().numpy().astype(np.float16 if half else np.float32),
+                            off=self.off.cpu().numpy(), len=self.len.cpu().numpy())
+
+    @classmethod
+    def load(cls, path, device="cuda"):
+        z = np.load(path)
+        return cls(z["rirs"].astype(np.float32), z["off"], z["len"], device)
+
+
+class SpectrogramCache:
+    """Per-env device mirror of ``_spectrogram_cache`` (simulator.py:723-734): dense over (source, receiver, azimuth).
+
+    ``render`` = ``get_current_spectrogram_observation`` for all envs: hits return the cached spectrogram and skip the
+    FFT work, misses are rendered by the batched kernel, stored, and advance the env's clip position (:668).  The
+    reference never evicts, so the cache covers the whole key space: ``n * V*V*4 * 13.5 KB`` of HBM (42 MB per env at
+    V = 28).  ``clear`` (N,) bool marks envs whose scene or sound changed (:393-395)."""
+
+    def __init__(self, num_envs, bank: RirBank, renderer: AudioRenderer):
+        self.n, self.bank, self.r = num_envs, bank, renderer
+        dev, V = bank.device, bank.V
+        self.E = int(np.prod(spectrogram_shape(renderer.sr)))
+        self.valid = torch.zeros(num_envs, V * V * 4, dtype=torch.uint8, device=dev)
+        self.cache = torch.empty(num_envs, V * V * 4, self.E, device=dev)
+
+    def render(self, sounds, clip_off, index, clip_secs, src, recv, az, silent, clear=None):
+        """sounds / clip_off / index as in ``AudioRenderer.render``; clip_secs (N,) int32 clip lengths in seconds; src /
+        recv / az (N,) int32 (az in quarter turns); silent (N,) int32.  ``index`` is advanced IN PLACE on misses.
+        Returns (spectrogram (N, 65, 26, 2), hit (N,) bool)."""
+        n, dev, V = self.n, self.bank.device, self.bank.V
+        i32, i64 = torch.int32, torch.int64
+        rir_off = torch.empty(n, dtype=i64, device=dev)
+        rir_len = torch.empty(n, dtype=i32, device=dev)
+        silent_eff = torch.empty(n, dtype=i32, device=dev)
+        hit = torch.empty(n, dtype=torch.uint8, device=dev)
+        cl = None if clear is None else clear.to(torch.uint8).contiguous()
+        _lib.call("avl_spec_cache_lookup", n, V, _lib.dptr(src, i32), _lib.dptr(recv, i32), _lib.dptr(az, i32),
+                  _lib.dptr(self.bank.off, i64), _lib.dptr(self.bank.len, i32), None if cl is None else cl.data_ptr(),
+                  self.valid.data_ptr(), _lib.dptr(silent, i32), _lib.dptr(rir_off, i64), _lib.dptr(rir_len, i32),
+                  _lib.dptr(silent_eff, i32), hit.data_ptr(), _lib.stream())
+        _, spec = self.r.render(sounds, clip_off, index, self.bank.rirs, rir_off, rir_len, silent_eff, want_audiogoal=False)
+        _lib.call("avl_spec_cache_commit", n, V, self.E, _lib.dptr(src, i32), _lib.dptr(recv, i32), _lib.dptr(az, i32),
+                  hit.data_ptr(), _lib.dptr(silent, i32), _lib.fptr(self.cache), self.valid.data_ptr(), _lib.fptr(spec),
+                  _lib.dptr(index, i32), _lib.dptr(clip_secs, i32), _lib.stream())
+        return spec, hit.view(torch.bool)
+
+
 class SpectrogramSensor:
     """Drop-in for the static method the task sensors call (nav.py:87): one (2, sr) waveform -> (65, 26, 2)."""
 

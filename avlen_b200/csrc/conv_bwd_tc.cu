@@ -105,7 +105,12 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 
 // NT: compile-time tile slots per warp (>= p.tpw; surplus slots recompute tile 0 into accumulators nobody stores, so
 // that the MMA loop has no per-tile branches)
-template <int NT>
+// PAIR (Cx % 16 == 0): two adjacent column tiles of a tap share their operand loads — tile 2j takes the even and tile
+// 2j + 1 the odd channels of a 16-channel block, so that one 8-byte shared-memory load feeds both MMAs (the K and N
+// index spaces of an MMA may be permuted freely as long as the result is stored through the same permutation).  The
+// rows of the dy^T fragment are permuted the same way for every shape: row g <-> output channel co0 + 2 g, row g + 8 <->
+// co0 + 2 g + 1 (one 8-byte load per pixel instead of two 4-byte loads).
+template <int NT, bool PAIR>
 __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
   AVL_DYN_SMEM(smem_raw);
   float* Sx = reinterpret_cast<float*>(smem_raw);
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
       r = tap / p.KW;
       s = tap - r * p.KW;
     }
-    toff[i] = (r * p.Wp + s) * p.xpitch + cc * 8;
+    toff[i] = (r * p.Wp + s) * p.xpitch + (PAIR ? (cc >> 1) * 16 : cc * 8);
   }
   float acc[NT][4];
 #pragma unroll
@@ -194,27 +199,47 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
           oa = pa / p.OW; wa = pa - oa * p.OW;
           ob = pb / p.OW; wb = pb - ob * p.OW;
         }
-        const float* xa = Sx + ((oa * p.stride) * p.Wp + wa * p.stride) * p.xpitch + g;
-        const float* xb = Sx + ((ob * p.stride) * p.Wp + wb * p.stride) * p.xpitch + g;
-        const float* da = Sd + pa * p.dpitch + co0 + g;
-        const float* db = Sd + pb * p.dpitch + co0 + g;
+        const int gx = PAIR ? 2 * g : g;
+        const float* xa = Sx + ((oa * p.stride) * p.Wp + wa * p.stride) * p.xpitch + gx;
+        const float* xb = Sx + ((ob * p.stride) * p.Wp + wb * p.stride) * p.xpitch + gx;
+        const float2 a01 = *reinterpret_cast<const float2*>(Sd + pa * p.dpitch + co0 + 2 * g);
+        const float2 a23 = *reinterpret_cast<const float2*>(Sd + pb * p.dpitch + co0 + 2 * g);
         uint32_t a[4];
-        a[0] = f2tf32(da[0]);
-        a[1] = f2tf32(da[8]);
-        a[2] = f2tf32(db[0]);
-        a[3] = f2tf32(db[8]);
-        // operand loads are issued in batches (2 * BT shared-memory loads in flight) ahead of their MMAs
-        constexpr int BT = (NT % 6 == 0) ? 6 : ((NT % 4 == 0) ? 4 : 2);
+        a[0] = f2tf32(a01.x);
+        a[1] = f2tf32(a01.y);
+        a[2] = f2tf32(a23.x);
+        a[3] = f2tf32(a23.y);
+        // operand loads are issued in batches ahead of their MMAs
+        if (PAIR) {
+          constexpr int NP = NT / 2;
+          constexpr int BP = (NP % 3 == 0) ? 3 : ((NP % 2 == 0) ? 2 : 1);
 #pragma unroll
-        for (int i0 = 0; i0 < NT; i0 += BT) {
-          float b0[BT], b1[BT];
+          for (int j0 = 0; j0 < NP; j0 += BP) {
+            float2 b0[BP], b1[BP];
 #pragma unroll
-          for (int j = 0; j < BT; ++j) {
-            b0[j] = xa[toff[i0 + j]];
-            b1[j] = xb[toff[i0 + j]];
+            for (int j = 0; j < BP; ++j) {
+              b0[j] = *reinterpret_cast<const float2*>(xa + toff[2 * (j0 + j)]);
+              b1[j] = *reinterpret_cast<const float2*>(xb + toff[2 * (j0 + j)]);
+            }
+#pragma unroll
+            for (int j = 0; j < BP; ++j) {
+              mma_tf32(acc[2 * (j0 + j)], a, f2tf32(b0[j].x), f2tf32(b1[j].x));
+              mma_tf32(acc[2 * (j0 + j) + 1], a, f2tf32(b0[j].y), f2tf32(b1[j].y));
+            }
           }
+        } else {
+          constexpr int BT = (NT % 6 == 0) ? 6 : ((NT % 4 == 0) ? 4 : 2);
 #pragma unroll
-          for (int j = 0; j < BT; ++j) mma_tf32(acc[i0 + j], a, f2tf32(b0[j]), f2tf32(b1[j]));
+          for (int i0 = 0; i0 < NT; i0 += BT) {
+            float b0[BT], b1[BT];
+#pragma unroll
+            for (int j = 0; j < BT; ++j) {
+              b0[j] = xa[toff[i0 + j]];
+              b1[j] = xb[toff[i0 + j]];
+            }
+#pragma unroll
+            for (int j = 0; j < BT; ++j) mma_tf32(acc[i0 + j], a, f2tf32(b0[j]), f2tf32(b1[j]));
+          }
         }
       }
     }
@@ -252,7 +277,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
     const int id = tile0 + i;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int co = co0 + g + ((e >> 1) << 3);
+      const int co = co0 + 2 * g + (e >> 1);  // (row permutation of the dy^T fragment, see the kernel header)
       const int nn = 2 * t + (e & 1);
       int tap, ci;
       if (c4) {
@@ -262,7 +287,8 @@ __global__ void __launch_bounds__(512, 1) tc_conv_wgrad_kernel(WgArgs p) {
         ci = nn & 3;
       } else {
         tap = id / p.ncc;
-        ci = (id - tap * p.ncc) * 8 + nn;
+        const int cc = id - tap * p.ncc;
+        ci = PAIR ? (cc >> 1) * 16 + 2 * nn + (cc & 1) : cc * 8 + nn;
       }
       dst[((long long)co * taps + tap) * p.Cx + ci] = acc[i][e];
     }
@@ -412,27 +438,33 @@ AVL_API int avl_tc_conv2d_wgrad(const float* x, const float* dy, float* dw, int 
     AVL_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(float) * Cout * Cw * KH * KW, (cudaStream_t)stream));
     return AVL_OK;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    const int mx = 200 * 1024 + 256;
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    attr_set = true;
-  }
-  pl.a.x = x;
-  pl.a.dy = dy;
-  pl.a.part = workspace;
   const dim3 grid(pl.grid_x, pl.grid_y);
   const cudaStream_t cs = (cudaStream_t)stream;
   const int tpw = pl.a.tpw;
-  if (tpw > 16) tc_conv_wgrad_kernel<18><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
-  else if (tpw > 8) tc_conv_wgrad_kernel<16><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
-  else if (tpw > 4) tc_conv_wgrad_kernel<8><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
-  else if (tpw > 2) tc_conv_wgrad_kernel<4><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
-  else tc_conv_wgrad_kernel<2><<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+  const bool pair = Cx != 4 && (pl.a.ncc % 2) == 0 && (tpw % 2) == 0;
+  pl.a.x = x;
+  pl.a.dy = dy;
+  pl.a.part = workspace;
+  auto launch = [&](auto kern) -> int {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 256));
+    kern<<<grid, pl.threads, pl.smem, cs>>>(pl.a);
+    return AVL_OK;
+  };
+  int lrc;
+  if (pair) {
+    if (tpw > 16) lrc = launch(tc_conv_wgrad_kernel<18, true>);
+    else if (tpw > 8) lrc = launch(tc_conv_wgrad_kernel<16, true>);
+    else if (tpw > 4) lrc = launch(tc_conv_wgrad_kernel<8, true>);
+    else if (tpw > 2) lrc = launch(tc_conv_wgrad_kernel<4, true>);
+    else lrc = launch(tc_conv_wgrad_kernel<2, true>);
+  } else {
+    if (tpw > 16) lrc = launch(tc_conv_wgrad_kernel<18, false>);
+    else if (tpw > 8) lrc = launch(tc_conv_wgrad_kernel<16, false>);
+    else if (tpw > 4) lrc = launch(tc_conv_wgrad_kernel<8, false>);
+    else if (tpw > 2) lrc = launch(tc_conv_wgrad_kernel<4, false>);
+    else lrc = launch(tc_conv_wgrad_kernel<2, false>);
+  }
+  if (lrc) return lrc;
   AVL_LAUNCH_CHECK();
   const long long per = (long long)Cout * KH * KW * Cx;
   wgrad_reduce_kernel<<<avl_div_up(per, 64), dim3(64, 8), 0, (cudaStream_t)stream>>>(workspace, pl.grid_x, Cout, KH * KW, Cx,

@@ -200,11 +200,10 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[k][j] = 0.f;
-  for (int i = tid; i < n4; i += GNC_THREADS) {
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
-    float4 gv = __ldg(reinterpret_cast<const float4*>(dy) + base4 + i);
+  // two iterations per trip, all six 16-byte loads issued before the first use: the kernel is latency-bound at 16
+  // warps per SM (profiles/r02_gn_bwd_l1_ncu_full.txt: long-scoreboard stalls 9.2 per issue with one iteration in flight)
+  auto absorb = [&](int i, const float4& xv, float4 gv, const float4& yv) {
     if (relu) {
-      const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + base4 + i);
       if (!(yv.x > 0.f)) gv.x = 0.f;
       if (!(yv.y > 0.f)) gv.y = 0.f;
       if (!(yv.z > 0.f)) gv.z = 0.f;
@@ -221,6 +220,25 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
       a[2][j] += gs[j];
       a[3][j] = fmaf(gs[j], xs[j], a[3][j]);
     }
+  };
+  const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  int i = tid;
+  for (; i + GNC_THREADS < n4; i += 2 * GNC_THREADS) {
+    const int i2 = i + GNC_THREADS;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x) + base4 + i2);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy) + base4 + i);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(dy) + base4 + i2);
+    const float4 y0 = relu ? __ldg(reinterpret_cast<const float4*>(y) + base4 + i) : one4;
+    const float4 y1 = relu ? __ldg(reinterpret_cast<const float4*>(y) + base4 + i2) : one4;
+    absorb(i, x0, g0, y0);
+    absorb(i2, x1, g1, y1);
+  }
+  for (; i < n4; i += GNC_THREADS) {
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x) + base4 + i);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy) + base4 + i);
+    const float4 y0 = relu ? __ldg(reinterpret_cast<const float4*>(y) + base4 + i) : one4;
+    absorb(i, x0, g0, y0);
   }
   for (int o = 16; o >= nq && o > 0; o >>= 1)
 #pragma unroll

@@ -150,3 +150,85 @@ AVL_API int avl_multi_copy(int count, void* const* dst, const void* const* src, 
   return AVL_OK;
 }
 #endif  // AVL_HOST_EMUL
+
+// ------------------------------------------------------------------ RIR bank lookup + spectrogram cache
+// The reference reads `{azimuth}/{receiver}_{source}.wav` from disk on every audio miss (soundspaces/simulator.py:650-659)
+// and keeps per-simulator dicts `_audiogoal_cache` / `_spectrogram_cache` keyed by (source, receiver, azimuth)
+// (:711-734), cleared when the scene or the sound changes (:393-395); the clip position `_audio_index` advances only
+// when the audiogoal is actually computed (:668).  Here a scene's RIRs are ONE packed tensor in HBM with a dense
+// (azimuth, receiver, source) -> (offset, length) table, and every env owns a dense spectrogram cache over the same
+// key space:  lookup  -> RIR descriptors of the step + hit flags (a hit is rendered as "silent": the render kernel skips it)
+//             commit  -> hits copy their cached spectrogram out, misses store theirs and advance the clip position.
+#ifndef AVL_HOST_EMUL
+namespace {
+
+__global__ void spec_cache_lookup_kernel(int n, int V, const int* __restrict__ src, const int* __restrict__ recv,
+                                         const int* __restrict__ az, const long long* __restrict__ tab_off,
+                                         const int* __restrict__ tab_len, const unsigned char* __restrict__ clear,
+                                         unsigned char* valid, const int* __restrict__ silent_in, long long* rir_off,
+                                         int* rir_len, int* silent_out, unsigned char* hit) {
+  const int i = blockIdx.x;
+  const int S = V * V * 4;
+  unsigned char* vrow = valid + (size_t)i * S;
+  const bool clr = clear && clear[i];
+  if (clr)
+    for (int k = threadIdx.x; k < S; k += blockDim.x) vrow[k] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int key = (src[i] * V + recv[i]) * 4 + az[i];
+    const int t = (az[i] * V + recv[i]) * V + src[i];
+    rir_off[i] = tab_off[t];
+    rir_len[i] = tab_len[t];
+    const unsigned char h = clr ? 0 : vrow[key];
+    hit[i] = h;
+    silent_out[i] = h ? 1 : silent_in[i];
+  }
+}
+
+__global__ void spec_cache_commit_kernel(int n, int V, int E, const int* __restrict__ src, const int* __restrict__ recv,
+                                         const int* __restrict__ az, const unsigned char* __restrict__ hit,
+                                         const int* __restrict__ silent_in, float* cache, unsigned char* valid, float* spec,
+                                         int* index, const int* __restrict__ clip_secs) {
+  const int i = blockIdx.x;
+  const int S = V * V * 4;
+  const int key = (src[i] * V + recv[i]) * 4 + az[i];
+  float* c = cache + ((size_t)i * S + key) * E;
+  float* s = spec + (size_t)i * E;
+  if (hit[i]) {
+    for (int k = threadIdx.x; k < E; k += blockDim.x) s[k] = c[k];
+  } else {
+    for (int k = threadIdx.x; k < E; k += blockDim.x) c[k] = s[k];
+    if (threadIdx.x == 0) {
+      valid[(size_t)i * S + key] = 1;
+      if (!silent_in[i]) index[i] = (index[i] + 1) % clip_secs[i];  // simulator.py:668 (inside the non-silent branch)
+    }
+  }
+}
+
+}  // namespace
+
+AVL_API int avl_spec_cache_lookup(int n, int V, const int* src, const int* recv, const int* az, const long long* tab_off,
+                                  const int* tab_len, const unsigned char* clear, unsigned char* valid, const int* silent_in,
+                                  long long* rir_off, int* rir_len, int* silent_out, unsigned char* hit, void* stream) {
+  if (n < 0 || V < 1) return AVL_ERR_ARG;
+  if (n == 0) return AVL_OK;
+  if (!src || !recv || !az || !tab_off || !tab_len || !valid || !silent_in || !rir_off || !rir_len || !silent_out || !hit)
+    return AVL_ERR_ARG;
+  spec_cache_lookup_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, V, src, recv, az, tab_off, tab_len, clear, valid,
+                                                               silent_in, rir_off, rir_len, silent_out, hit);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+AVL_API int avl_spec_cache_commit(int n, int V, int E, const int* src, const int* recv, const int* az,
+                                  const unsigned char* hit, const int* silent_in, float* cache, unsigned char* valid,
+                                  float* spec, int* index, const int* clip_secs, void* stream) {
+  if (n < 0 || V < 1 || E < 1) return AVL_ERR_ARG;
+  if (n == 0) return AVL_OK;
+  if (!src || !recv || !az || !hit || !silent_in || !cache || !valid || !spec || !index || !clip_secs) return AVL_ERR_ARG;
+  spec_cache_commit_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(n, V, E, src, recv, az, hit, silent_in, cache, valid, spec,
+                                                               index, clip_secs);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+#endif  // AVL_HOST_EMUL

@@ -117,6 +117,32 @@ class CLIPTextTower(nn.Module):
             self._last = (n, L)
         return out
 
+    @torch.no_grad()
+    def encode_text_cached(self, text):
+        """``encode_text`` for the rollout, where row i is env i at every call: a dialog changes only when a query
+        fires (ppo_trainer.py:548-553) and stays for NUM_DIALOG_STEPS steps, yet the reference runs the whole tower on
+        all N rows every step (:625-637).  Rows whose 77 tokens equal the previous call's reuse that call's embedding;
+        the others are encoded (unchanged rows are presented to the kernel as all-zero rows, which its device-side
+        compaction folds into one shared sequence — no host synchronisation, no data-dependent launch shapes).
+        Identical to ``encode_text`` as long as the (frozen) CLIP parameters do not change; ``reset_cache()`` after
+        loading new ones."""
+        text = text.to(torch.int64).contiguous()
+        c = self.__dict__.get("_row_cache")
+        key = (tuple(text.shape), text.device, self._ptr_key)
+        if c is None or c[0] != key:
+            emb = self.encode_text(text)
+            self.__dict__["_row_cache"] = ((tuple(text.shape), text.device, self._ptr_key), text.clone(), emb)
+            return emb
+        _, old_text, old_emb = c
+        changed = (text != old_text).any(dim=1, keepdim=True)
+        emb_new = self.encode_text(torch.where(changed, text, torch.zeros_like(text)))
+        emb = torch.where(changed, emb_new, old_emb)
+        self.__dict__["_row_cache"] = (key, text.clone(), emb)
+        return emb
+
+    def reset_cache(self):
+        self.__dict__.pop("_row_cache", None)
+
     def last_counts(self):
         """(synchronising) distinct sequences / token rows processed by the last chunk."""
         a, b = ctypes.c_int(0), ctypes.c_int(0)

@@ -494,7 +494,10 @@ class AudioNavDialogNet(AudioNavSMTNet):
         belief = self._belief(observations, x.shape[0], x.device)
         x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
         if all_dialog is not None:
-            dialog_emb = self.clip.encode_text(all_dialog)  # no_grad, fp32 (policy.py:847-849)
+            if torch.is_grad_enabled():
+                dialog_emb = self.clip.encode_text(all_dialog)  # no_grad, fp32 (policy.py:847-849)
+            else:  # rollout: per-env embedding cache, only rows whose dialog changed are encoded
+                dialog_emb = self.clip.encode_text_cached(all_dialog)
             dialog_emb = cuda_linear(dialog_emb, self.dialog_layer.weight, self.dialog_layer.bias)
         else:
             dialog_emb = None

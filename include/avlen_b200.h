@@ -109,6 +109,18 @@ int avl_resize_half_typed(const void* x, int dtype, const long long* sample_inde
  * 4 fp32 -> int64 (n elements).                                                                                        */
 int avl_multi_copy(int count, void* const* dst, const void* const* src, const long long* n, const unsigned char* kind,
                    void* stream);
+/* ------------------------------------------------------------------- RIR bank + spectrogram cache
+ * Replaces the per-miss wav read (soundspaces/simulator.py:650-659) and the per-simulator dict caches keyed by
+ * (source, receiver, azimuth) (:711-734; cleared on scene / sound change :393-395; `_audio_index` advances on a miss only,
+ * :668).  tab_off / tab_len: dense (4, V, V) [azimuth][receiver][source] table into the packed RIR bank; valid: (n, V*V*4)
+ * bytes; cache: (n, V*V*4, E) fp32.  lookup: RIR descriptors + hit flags, hits are marked silent for the render;
+ * commit: hits read their cached spectrogram, misses store theirs and advance the clip position.                        */
+int avl_spec_cache_lookup(int n, int V, const int* src, const int* recv, const int* az, const long long* tab_off,
+                          const int* tab_len, const unsigned char* clear, unsigned char* valid, const int* silent_in,
+                          long long* rir_off, int* rir_len, int* silent_out, unsigned char* hit, void* stream);
+int avl_spec_cache_commit(int n, int V, int E, const int* src, const int* recv, const int* az, const unsigned char* hit,
+                          const int* silent_in, float* cache, unsigned char* valid, float* spec, int* index,
+                          const int* clip_secs, void* stream);
 /* ------------------------------------------------------------------- graph-walk environment step
  * One launch for all envs: graph walk (soundspaces/simulator.py:496-517), first oracle action of the shortest path
  * (:758-787), reward (ss_baselines/common/environments.py:98-135), PoseSensor (soundspaces/tasks/nav.py:745-775), episode

@@ -238,3 +238,31 @@ def test_update_dialog_matches_oracle():
         assert float((d_mine - d_ref).abs().max()) < 0.15 * 1e-5 * 2 + 1e-8, k
         moved += int(float(d_ref.abs().max()) > 0)
     assert moved >= 40
+
+
+def test_clip_row_cache_equals_full_encode():
+    """The rollout's per-env CLIP embedding cache (only rows whose dialog changed are encoded) returns exactly what a
+    full ``encode_text`` of every row returns, over a sequence of steps where dialogs appear, persist and end."""
+    from avlen_b200.savi.models.clip_text import CLIPTextTower
+    torch.manual_seed(0)
+    clip = CLIPTextTower(layers=2).cuda()
+    g = torch.Generator().manual_seed(3)
+    n = 12
+    cur = torch.zeros(n, 77, dtype=torch.long)
+    for step in range(8):
+        for i in range(n):
+            r = float(torch.rand(1, generator=g))
+            if r < 0.25:  # a query fires: new dialog
+                k = int(torch.randint(5, 20, (1,), generator=g))
+                cur[i] = 0
+                cur[i, 0] = 49406
+                cur[i, 1:1 + k] = torch.randint(1, 49000, (k,), generator=g)
+                cur[i, 1 + k] = 49407
+            elif r < 0.4:  # the dialog ends
+                cur[i] = 0
+        t = cur.cuda()
+        got = clip.encode_text_cached(t)
+        want = clip.encode_text(t)
+        assert float((got - want).abs().max()) <= 1e-6, step  # (rows are independent of the batch they are encoded in)
+    clip.reset_cache()
+    assert float((clip.encode_text_cached(t) - want).abs().max()) <= 1e-6

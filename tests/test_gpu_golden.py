@@ -394,3 +394,55 @@ def test_interactive_bookkeeping_cuda_matches_reference_trainer_golden():
     from tests.test_golden import replay_interactive_golden
     replay_interactive_golden(lambda n, pe: QueryBookkeeper(n, "cuda", pe=pe),
                               to_np=lambda a: a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a))
+
+
+def test_spectrogram_cache_follows_reference_cache_sequence(tmp_path):
+    """``RirBank.from_wav_dir`` (the reference's ``{azimuth}/{receiver}_{source}.wav`` layout) +
+    ``SpectrogramCache.render`` against the recorded behaviour of the UNMODIFIED ``get_current_audiogoal_observation``
+    (soundspaces/simulator.py:711-721, :668; tests/golden/make_golden.py:audiogoal): which visits are cache hits, which
+    clip second each miss consumes, and the cached result returned on a hit."""
+    from scipy.io import wavfile
+    from avlen_b200.audio import AudioRenderer, RirBank, SpectrogramCache
+    from oracle import audio_np as A
+    from tests._audio_helpers import GOLDEN_AUDIO_SR, golden_audio_inputs
+    g = load("audiogoal.npz")
+    sr, V = GOLDEN_AUDIO_SR, 7
+    src, rir, _, _ = golden_audio_inputs(2)
+    keys = [tuple(k) for k in g["cache_keys"]]           # (source, receiver, azimuth)
+    for a in (0, 90, 180, 270):
+        (tmp_path / str(a)).mkdir()
+    for (_s, r, a) in set(keys):
+        wavfile.write(str(tmp_path / str(a) / f"{r}_2.wav"), sr, np.roll(rir, 37 * r, axis=0))
+    (tmp_path / "0" / "3_2.wav").write_bytes(b"not a wav file")  # an unreadable file is a zero-length entry
+    bank = RirBank.from_wav_dir(str(tmp_path), V)
+    assert int(bank.len[0, 1, 2]) == len(rir) and int(bank.len[0, 3, 2]) == 0 and int(bank.len[0, 0, 0]) == 0
+    r_ = AudioRenderer(sr)
+    cache = SpectrogramCache(1, bank, r_)
+    sounds = d(src)
+    i32 = torch.int32
+    clip_off = torch.zeros(1, dtype=torch.int64, device="cuda")
+    index = torch.zeros(1, dtype=i32, device="cuda")
+    secs = torch.full((1,), len(src) // sr, dtype=i32, device="cuda")
+    silent = torch.zeros(1, dtype=i32, device="cuda")
+    seen = {}
+    for step, (s_, rcv, az) in enumerate(keys):
+        before = int(index.cpu())
+        spec, hit = cache.render(sounds, clip_off, index, secs, torch.tensor([s_], dtype=i32).cuda(),
+                                 torch.tensor([rcv], dtype=i32).cuda(), torch.tensor([az // 90], dtype=i32).cuda(), silent)
+        used = int(g["cache_index_used"][step])
+        assert bool(hit[0]) == (used < 0), step
+        if used >= 0:
+            assert before == used and int(index.cpu()) == (used + 1) % int(secs[0]), step
+            ag, _ = A.compute_audiogoal(src, np.roll(rir, 37 * rcv, axis=0), used, sr)
+            assert np.abs(ag[:, :256].astype(np.float32) - g["cache_heads"][step]).max() <= 1e-5 * np.abs(g["cache_heads"][step]).max()
+            want = A.compute_spectrogram(ag.astype(np.float32))
+            assert np.abs(spec[0].cpu().numpy() - want).max() <= 1e-3 * max(1.0, np.abs(want).max()), step
+            seen[(s_, rcv, az)] = spec[0].clone()
+        else:
+            assert int(index.cpu()) == before
+            assert torch.equal(spec[0], seen[(s_, rcv, az)]), step   # the cached spectrogram, bit for bit
+    # a scene / sound change clears the env's cache (simulator.py:393-395)
+    spec, hit = cache.render(sounds, clip_off, index, secs, torch.tensor([2], dtype=i32).cuda(), torch.tensor([1], dtype=i32).cuda(),
+                             torch.tensor([0], dtype=i32).cuda(), silent, clear=torch.ones(1, dtype=torch.bool, device="cuda"))
+    assert not bool(hit[0])
+    r_.close()
