@@ -470,8 +470,29 @@ bool make_map3(CUtensorMap* map, const float* base, long long rows, long long co
 }
 
 constexpr size_t X3_SCRATCH_FLOATS = 1u << 20;  // hi + lo of the B operand: N * K <= 512 Ki elements
-float* g_scratch = nullptr;
+// one scratch per caller stream: two scene-memory transformers (pi_q and pi_g of the AVLEN interactive step) may run
+// concurrently on two streams, each splitting its own weights
+struct StreamScratch {
+  cudaStream_t stream;
+  float* buf;
+};
+constexpr int X3_MAX_STREAMS = 8;
+StreamScratch g_scratches[X3_MAX_STREAMS];
+int g_num_scratches = 0;
 int g_x3_on = 1;
+
+int scratch_for(cudaStream_t s, float** out) {
+  for (int i = 0; i < g_num_scratches; ++i)
+    if (g_scratches[i].stream == s) { *out = g_scratches[i].buf; return AVL_OK; }
+  if (g_num_scratches == X3_MAX_STREAMS) { *out = nullptr; return AVL_ERR_UNSUPPORTED; }  // caller falls back (fp32 SIMT)
+  float* b = nullptr;
+  AVL_CUDA_CHECK(cudaMalloc(&b, X3_SCRATCH_FLOATS * sizeof(float)));
+  g_scratches[g_num_scratches].stream = s;
+  g_scratches[g_num_scratches].buf = b;
+  ++g_num_scratches;
+  *out = b;
+  return AVL_OK;
+}
 
 }  // namespace
 
@@ -491,9 +512,13 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return AVL_ERR_ARG;
   if (((uintptr_t)A & 15) || (lda & 3) || (K & 3) || (size_t)N * K * 2 > X3_SCRATCH_FLOATS) return AVL_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!g_scratch) AVL_CUDA_CHECK(cudaMalloc(&g_scratch, X3_SCRATCH_FLOATS * sizeof(float)));
-  float* bhi = g_scratch;
-  float* blo = g_scratch + (size_t)N * K;
+  float* scratch = nullptr;
+  {
+    const int src = scratch_for(s, &scratch);
+    if (src) return src;
+  }
+  float* bhi = scratch;
+  float* blo = scratch + (size_t)N * K;
   split_tf32_kernel<<<avl_div_up((long long)N * K, 256), 256, 0, s>>>(B, ldb, N, K, b_transposed, bhi, blo);
   AVL_LAUNCH_CHECK();
   X3Args p = {};

@@ -84,15 +84,28 @@ class PPOTrainer:
         obs = {k: v[s] for k, v in rollouts.observations.items()}
         h = rollouts.recurrent_hidden_states[s]
         prev = rollouts.prev_actions[s]
+        # pi_g needs nothing from pi_q or pi_l: its whole act() (two ResNet-18s, audio CNN, scene-memory transformer,
+        # heads) runs on a side stream next to pi_q's and pi_l's, joined where the arbitration reads its outputs
+        main = torch.cuda.current_stream()
+        gs = getattr(self, "_goal_stream", None)
+        if gs is None:
+            gs = self._goal_stream = torch.cuda.Stream()
+        gs.wait_stream(main)
+        with torch.cuda.stream(gs):
+            _vg, ag, _lpg, _, xg, pg = self.actor_critic_goal.act(
+                obs, h, prev, rollouts.masks[s], rollouts.external_memory_goal[:, s], rollouts.external_memory_masks[s])
+            goal_done = torch.cuda.Event()
+            goal_done.record(gs)
         qs, lq = book.pre(envs.is_new_episode())
         vq, unct, aq, lpq, h_out, xq, _pq = self.actor_critic_option.act_option(
             obs, h, prev, rollouts.masks[s], rollouts.external_memory_option[:, s], rollouts.external_memory_masks[s], qs, lq)
         is_q, qnum, cons, rl_mask, dialog, agent_step = book.after_option(aq, envs.target_distance(), envs.pending_dialog())
-        _vg, ag, _lpg, _, xg, pg = self.actor_critic_goal.act(
-            obs, h, prev, rollouts.masks[s], rollouts.external_memory_goal[:, s], rollouts.external_memory_masks[s])
         _vl, al, _lpl, _, xl, xd, pl = self.actor_critic_vln.act_dialog(
             obs, h, prev, rollouts.masks_vln[s], rollouts.external_memory_vln[:, s],
             rollouts.external_memory_vln_dialog[:, s], rollouts.external_memory_vln_masks[s], dialog, agent_step)
+        main.wait_event(goal_done)
+        for t_ in (ag, xg, pg):
+            t_.record_stream(main)
         oracle = envs.compute_oracle_actions()
         o_action = oracle.float()
         actions, o_mask, ucnt_gt, masks_vln = book.arbitrate(ag, al, pg, oracle)
