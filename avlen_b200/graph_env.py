@@ -236,7 +236,7 @@ class GraphVectorEnv(SyntheticVectorEnv):
         self.last_masks = masks
         ep_step = self._gstate[3].float()
         silent = (ep_step > self._silent_after).to(torch.int32)  # simulator.py:646
-        self._audio["index"] = ((self._audio["index"] + 1) % self._clip_secs).to(torch.int32)  # simulator.py:668
+        self._audio["index"].copy_((self._audio["index"] + 1) % self._clip_secs)  # simulator.py:668 (in place: graph-safe)
         n = self.num_envs
         beliefs = (torch.zeros(n, 21, device=self.device), torch.zeros(n, 2, device=self.device))
         return self._observe(silent, pose, beliefs), rewards, dones

@@ -202,9 +202,14 @@ class DDPPOTrainer(PPOTrainer):
     # device-resident env (host frames are staged by the host every step), no preemption.
     def _step_graphs_possible(self):
         cfg = self.config
-        return (getattr(cfg, "step_graphs", False) and cfg.policy_type == "smt" and cfg.freeze_encoders
-                and not cfg.host_buffers and not cfg.use_preemption and getattr(self.envs, "fused_step", False)
-                and getattr(self, "_step_graphs_ok", True))
+        if not (getattr(cfg, "step_graphs", False) and not cfg.host_buffers and not cfg.use_preemption
+                and getattr(self, "_step_graphs_ok", True)):
+            return False
+        if cfg.policy_type == "interactive":
+            # pi_g / pi_l are frozen, pi_q never trains its encoders (policy.py:1034-1036): no packed weight changes
+            # between rollouts; env / bookkeeping / memory / CLIP-cache state lives in persistent device buffers
+            return hasattr(self.envs, "_gstate")
+        return cfg.policy_type == "smt" and cfg.freeze_encoders and getattr(self.envs, "fused_step", False)
 
     def _capture_step(self, s):
         # (capture_begin / capture_end directly: the torch.cuda.graph context synchronises the device, runs the garbage
@@ -217,7 +222,8 @@ class DDPPOTrainer(PPOTrainer):
         try:
             self._collect_rollout_step(self.rollouts)
             K.sync_pending()      # deferred belief update: joined inside the captured step
-            net.join_prefetch()   # encoder prefetch of slot s + 1: complete when the step's graph completes
+            if hasattr(net, "join_prefetch"):
+                net.join_prefetch()   # encoder prefetch of slot s + 1: complete when the step's graph completes
         finally:
             g.capture_end()
         if self._graph_pool is None:
@@ -234,6 +240,9 @@ class DDPPOTrainer(PPOTrainer):
         r = self.rollouts
         r.step += 1
         r.em.advance_host_index()
+        if self.config.policy_type == "interactive":
+            for em in (r.em_option, r.em_vln, r.em_vln_dialog):
+                em.advance_host_index()
         self.envs._t += 1
 
     def collect_rollout(self):

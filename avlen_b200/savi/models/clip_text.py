@@ -131,13 +131,15 @@ class CLIPTextTower(nn.Module):
         key = (tuple(text.shape), text.device, self._ptr_key)
         if c is None or c[0] != key:
             emb = self.encode_text(text)
-            self.__dict__["_row_cache"] = ((tuple(text.shape), text.device, self._ptr_key), text.clone(), emb)
+            # persistent buffers, updated in place: a rollout step captured into a CUDA graph keeps reading / writing them
+            self.__dict__["_row_cache"] = (key, text.clone(), emb.clone())
             return emb
         _, old_text, old_emb = c
         changed = (text != old_text).any(dim=1, keepdim=True)
         emb_new = self.encode_text(torch.where(changed, text, torch.zeros_like(text)))
         emb = torch.where(changed, emb_new, old_emb)
-        self.__dict__["_row_cache"] = (key, text.clone(), emb)
+        old_text.copy_(text)
+        old_emb.copy_(emb)
         return emb
 
     def reset_cache(self):

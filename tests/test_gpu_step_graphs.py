@@ -75,3 +75,44 @@ def test_step_graphs_are_skipped_where_they_do_not_apply():
         tr.collect_rollout()
         tr.collect_rollout() if False else None
         tr.envs.close()
+
+
+def test_graphed_interactive_rollouts_keep_the_step_semantics():
+    """The AVLEN interactive step (three policies, query bookkeeping, graph-walk env, four memories, CLIP cache) replayed
+    from per-step CUDA graphs: the stored pi_q values / log-probs are what pi_q computes on the stored data, the executed
+    action inside a dialog is the oracle's, the env's episode clock follows the done flags."""
+    from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
+    cfg = savi_config(NUM_PROCESSES=6, num_steps=10, memory_size=12, policy_type="interactive", freeze_encoders=False,
+                      clip_layers=2, step_graphs=True)
+    tr = DDPPOTrainer(cfg).setup()
+    assert tr._step_graphs_possible()
+    for r in range(4):  # eager warm-up, capture, two replays
+        tr.collect_rollout()
+        rs = tr.rollouts
+        T, N = rs.step, 6
+        assert T == 10
+        if r >= 1:
+            assert tr._step_graphs is not None
+        nd = rs.masks.cpu()
+        t = rs.observations["pose"][:T + 1, :, 3].cpu()
+        for s in range(T):
+            assert torch.equal(t[s + 1], torch.where(nd[s + 1, :, 0] > 0, t[s] + 1, torch.zeros(N))), (r, s)
+        acts, o_act = rs.actions[:T, :, 0].cpu(), rs.o_actions[:T].cpu()
+        has_dialog = (rs.all_dialog[:T] != 0).any(-1).cpu()
+        inside = has_dialog & (o_act != 0)
+        assert bool((acts[inside].float() == o_act[inside]).all())
+        for em in (rs.em, rs.em_option, rs.em_vln, rs.em_vln_dialog):
+            assert int(em.idx_dev.cpu()) == em.idx
+        adv = torch.zeros(T, N, 1, device="cuda")
+        for sample in rs.recurrent_generator(adv, 1, perm=torch.arange(N)):
+            obs, h, _a, a_opt, prev, vp, _ret, masks, old_lp = sample[:9]
+            em_option, em_masks, qs, lq = sample[13], sample[16], sample[19], sample[20]
+            with torch.no_grad():
+                v, _u, lp, _e, _h, _x, _p = tr.actor_critic.evaluate_actions_option(obs, h, prev, masks, a_opt, em_option,
+                                                                                      em_masks, qs, lq)
+            assert float((lp - old_lp).abs().max()) < 2e-3 and float((v - vp).abs().max()) < 2e-3, r
+        rs.after_update()
+    tr.collect_rollout()
+    stats = tr._update_agent(cfg, tr.rollouts)
+    assert all(np.isfinite(v) for v in stats)
+    tr.envs.close()
