@@ -294,7 +294,7 @@ struct Side {
   cudaStream_t side;
   cudaEvent_t fork, join;
 };
-constexpr int MAX_SIDES = 8;
+constexpr int MAX_SIDES = 16;
 Side g_sides[MAX_SIDES];
 int g_num_sides = 0;
 

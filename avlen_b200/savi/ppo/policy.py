@@ -89,13 +89,15 @@ class Policy(nn.Module):
         return value, unct, action, action_log_probs, rnn_hidden_states, ext_memory_feats, distribution.probs
 
     def act_dialog(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog,
-                   ext_memory_masks, all_dialog, agent_step, deterministic=False, without_dialog=False, uniforms=None):
-        """policy.py:130-162 (pi_l)."""
+                   ext_memory_masks, all_dialog, agent_step, deterministic=False, without_dialog=False, uniforms=None,
+                   scene=None):
+        """policy.py:130-162 (pi_l).  ``scene``: optional result of ``net.encode_scene`` computed ahead (side stream)."""
         if without_dialog:
             all_dialog = None
+        kw = {} if scene is None else {"scene": scene}
         features, rnn_hidden_states, ext_memory_feats, ext_memory_dialog_feats = self.net(
             observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog, ext_memory_masks,
-            all_dialog, agent_step)
+            all_dialog, agent_step, **kw)
         distribution, _ = self.action_distribution_vln(features)
         value = self.critic_vln(features)
         action = distribution.mode() if deterministic else distribution.sample(uniforms=uniforms)
@@ -488,11 +490,19 @@ class AudioNavDialogNet(AudioNavSMTNet):
         self.dialog_state_encoder = DialogStateEncoder(self._hidden_size + self._hidden_size,
                                                        dim_feedforward=self._hidden_size, **kwargs)
 
-    def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog,
-                ext_memory_masks, all_dialog, agent_step):
+    def encode_scene(self, observations, prev_actions, ext_memory, ext_memory_masks):
+        """The part of pi_l that does not depend on the dialog: features, belief vector, scene-memory transformer.  The
+        interactive trainer runs it on a side stream while pi_q decides whether a query fires."""
         x = self.get_features(observations, prev_actions)
         belief = self._belief(observations, x.shape[0], x.device)
         x_att = self.smt_state_encoder(x, ext_memory, ext_memory_masks, goal=belief)
+        return x, x_att, belief
+
+    def forward(self, observations, rnn_hidden_states, prev_actions, masks, ext_memory, ext_memory_dialog,
+                ext_memory_masks, all_dialog, agent_step, scene=None):
+        if scene is None:
+            scene = self.encode_scene(observations, prev_actions, ext_memory, ext_memory_masks)
+        x, x_att, belief = scene
         if all_dialog is not None:
             if torch.is_grad_enabled():
                 dialog_emb = self.clip.encode_text(all_dialog)  # no_grad, fp32 (policy.py:847-849)

@@ -96,13 +96,27 @@ class PPOTrainer:
                 obs, h, prev, rollouts.masks[s], rollouts.external_memory_goal[:, s], rollouts.external_memory_masks[s])
             goal_done = torch.cuda.Event()
             goal_done.record(gs)
+        # ... and so does the dialog-independent part of pi_l (features + scene-memory transformer)
+        ls = getattr(self, "_vln_stream", None)
+        if ls is None:
+            ls = self._vln_stream = torch.cuda.Stream()
+        ls.wait_stream(main)
+        with torch.cuda.stream(ls):
+            scene = self.actor_critic_vln.net.encode_scene(obs, prev, rollouts.external_memory_vln[:, s],
+                                                           rollouts.external_memory_vln_masks[s])
+            scene_done = torch.cuda.Event()
+            scene_done.record(ls)
         qs, lq = book.pre(envs.is_new_episode())
         vq, unct, aq, lpq, h_out, xq, _pq = self.actor_critic_option.act_option(
             obs, h, prev, rollouts.masks[s], rollouts.external_memory_option[:, s], rollouts.external_memory_masks[s], qs, lq)
         is_q, qnum, cons, rl_mask, dialog, agent_step = book.after_option(aq, envs.target_distance(), envs.pending_dialog())
+        main.wait_event(scene_done)
+        for t_ in scene:
+            t_.record_stream(main)
         _vl, al, _lpl, _, xl, xd, pl = self.actor_critic_vln.act_dialog(
             obs, h, prev, rollouts.masks_vln[s], rollouts.external_memory_vln[:, s],
-            rollouts.external_memory_vln_dialog[:, s], rollouts.external_memory_vln_masks[s], dialog, agent_step)
+            rollouts.external_memory_vln_dialog[:, s], rollouts.external_memory_vln_masks[s], dialog, agent_step,
+            scene=scene)
         main.wait_event(goal_done)
         for t_ in (ag, xg, pg):
             t_.record_stream(main)
