@@ -53,7 +53,9 @@ def _worker(rank, world, port, q):
     r.returns = torch.randn(6, 3, 1, generator=g)
     r.value_preds = torch.randn(6, 3, 1, generator=g)
     adv = a.get_advantages(r)
-    q.put((rank, params_after_broadcast, a._flat_g * scale, local_grad, vals, mean, var, adv.mean().item()))
+    # numpy arrays travel by value: a tensor in a torch mp queue is a shared file descriptor that dies with this worker
+    q.put((rank,) + tuple(t.detach().numpy().copy() for t in (params_after_broadcast, a._flat_g * scale, local_grad, vals,
+                                                                mean, var)) + (adv.mean().item(),))
     distrib.barrier()
     distrib.destroy_process_group()
 
@@ -70,6 +72,7 @@ def test_world_size_2_gloo():
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
+    res = [tuple(torch.from_numpy(x) if hasattr(x, "dtype") else x for x in r) for r in res]
     (_, p0, g0, l0, v0, m0, var0, a0), (_, p1, g1, l1, v1, m1, var1, a1) = res
     assert torch.equal(p0, p1)                                  # broadcast from rank 0
     assert torch.allclose(g0, g1) and torch.allclose(g0, (l0 + l1) / 2)   # averaged gradient on every rank
@@ -101,7 +104,7 @@ def _worker_full_state(rank, world, port, q):
                   entropy_coef=0.05, lr=1e-3, eps=1e-5, max_grad_norm=0.2)
     v0 = ac.encoder.weight._version
     agent.init_distributed(find_unused_params=True)
-    q.put((rank, {k: v.clone() for k, v in ac.state_dict().items()}, ac.encoder.weight._version > v0))
+    q.put((rank, {k: v.detach().numpy().copy() for k, v in ac.state_dict().items()}, ac.encoder.weight._version > v0))
     distrib.barrier()
     distrib.destroy_process_group()
 
@@ -123,7 +126,7 @@ def test_init_distributed_broadcasts_frozen_parameters_and_buffers():
     (_, sd0, bumped0), (_, sd1, bumped1) = res
     assert set(sd0) == {"head.weight", "head.bias", "encoder.weight", "encoder.bias", "running"}
     for k in sd0:
-        assert torch.equal(sd0[k], sd1[k]), k
+        assert (sd0[k] == sd1[k]).all(), k
     assert bumped0 and bumped1  # caches keyed by the parameter version (packed tensor-core weights) see the change
 
 
