@@ -349,6 +349,31 @@ static int attn_vcap(int rows_cap, int B) {  // per-sample token bound implied b
   if (v < 1) v = 1;
   return v;
 }
+// Tensor-core self-attention (attn_tc.cu, 3xTF32 warp MMAs) when the tensor-core level allows it; false = not taken.
+#ifndef AVL_HOST_EMUL
+extern "C" int avl_attn_self_fwd_tc_try(const float* qkv, const int* off, int B, int D, float* out, float* lse, float scale,
+                                        int vcap, cudaStream_t stream);
+extern "C" int avl_attn_self_bwd_tc_try(const float* qkv, const int* off, int B, int D, const float* out, const float* lse,
+                             const float* dout, float* dqkv, float scale, int vcap, cudaStream_t stream);
+static bool attn_fwd_tc(Launcher& L, const float* qkv, const int* off, int B, int D, float* out, float* lse, float scale,
+                        int vcap) {
+  int rc = avl_attn_self_fwd_tc_try(qkv, off, B, D, out, lse, scale, vcap, L.s);
+  if (rc == AVL_ERR_UNSUPPORTED) return false;
+  if (rc && !L.err) L.err = rc;
+  return true;
+}
+static bool attn_bwd_tc(Launcher& L, const float* qkv, const int* off, int B, int D, const float* out, const float* lse,
+                        const float* dout, float* dqkv, float scale, int vcap) {
+  int rc = avl_attn_self_bwd_tc_try(qkv, off, B, D, out, lse, dout, dqkv, scale, vcap, L.s);
+  if (rc == AVL_ERR_UNSUPPORTED) return false;
+  if (rc && !L.err) L.err = rc;
+  return true;
+}
+#else
+static bool attn_fwd_tc(Launcher&, const float*, const int*, int, int, float*, float*, float, int) { return false; }
+static bool attn_bwd_tc(Launcher&, const float*, const int*, int, int, const float*, const float*, const float*, float*,
+                        float, int) { return false; }
+#endif
 static bool g_attn_attr_set = false;
 static int ensure_attn_attrs() {
   if (g_attn_attr_set) return AVL_OK;
@@ -418,8 +443,10 @@ static void tf_forward(Launcher& L, const float* const* P, const TfBufs& t, cons
   const float scale = 1.0f / sqrtf((float)ATT_HD);
   const int vcap = attn_vcap(Rcap, B);
   lin_fwd(L, X0, D, P[TP_ENC_IN_W], P[TP_ENC_IN_B], t.QKV, 3 * D, Rcap, 3 * D, D, 0, total);
-  AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, H), ATT_WARPS * 32, attn_fwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, D, scale, vcap);
-  L.check();
+  if (!attn_fwd_tc(L, t.QKV, off, B, D, t.ATT, t.LSE, scale, vcap)) {
+    AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, H), ATT_WARPS * 32, attn_fwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, D, scale, vcap);
+    L.check();
+  }
   lin_fwd(L, t.ATT, D, P[TP_ENC_OUT_W], P[TP_ENC_OUT_B], t.AO, D, Rcap, D, D, 0, total);
   ln_fwd(L, X0, t.AO, P[TP_ENC_N1_W], P[TP_ENC_N1_B], t.X1, t.ST1, total, Rcap, D);
   lin_fwd(L, t.X1, D, P[TP_ENC_L1_W], P[TP_ENC_L1_B], t.FF1, D, Rcap, D, D, 1, total);
@@ -496,8 +523,10 @@ static void tf_backward(Launcher& L, const float* const* P, float* const* G, con
   // GC = grad wrt (X0 + AO)
   lin_bwd_w(L, t.GC, D, t.ATT, D, gp(G, TP_ENC_OUT_W), D, gp(G, TP_ENC_OUT_B), Rcap, D, D, total);
   lin_bwd_x(L, t.GC, D, P[TP_ENC_OUT_W], D, t.GB, D, Rcap, D, D, 0, total, t.WT);  // GB = gATT
-  AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_BWD_WARPS * 32, attn_bwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale, vcap);
-  L.check();
+  if (!attn_bwd_tc(L, t.QKV, off, B, D, t.ATT, t.LSE, t.GB, t.GQKV, scale, vcap)) {
+    AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, H), ATT_BWD_WARPS * 32, attn_bwd_smem(vcap), L.s, t.QKV, off, t.ATT, t.LSE, t.GB, t.GQKV, D, scale, vcap);
+    L.check();
+  }
   lin_bwd_w(L, t.GQKV, 3 * D, X0, D, gp(G, TP_ENC_IN_W), D, gp(G, TP_ENC_IN_B), Rcap, 3 * D, D, total);
   lin_bwd_x(L, t.GQKV, 3 * D, P[TP_ENC_IN_W], D, t.GC, D, Rcap, 3 * D, D, 1, total, t.WT);  // GC = gX0
 }
@@ -572,6 +601,10 @@ AVL_API int avl_attn_self_fwd(const float* qkv, const int* off, int B, int D, fl
   if (!qkv || !off || !out) return AVL_ERR_ARG;
   int rc = ensure_attn_attrs();
   if (rc) return rc;
+  {
+    Launcher L{(cudaStream_t)stream};
+    if (attn_fwd_tc(L, qkv, off, B, D, out, lse, 1.0f / sqrtf(32.f), ATT_MAXV)) return L.err;
+  }
   AVL_LAUNCH(attn_self_fwd_kernel, dim3(B, D / 32), ATT_WARPS * 32, kAttnFwdSmem, (cudaStream_t)stream, 
       qkv, off, out, lse, D, 1.0f / sqrtf(32.f), ATT_MAXV);
   AVL_LAUNCH_CHECK();
@@ -585,6 +618,10 @@ AVL_API int avl_attn_self_bwd(const float* qkv, const int* off, int B, int D, co
   if (!qkv || !off || !out || !lse || !dout || !dqkv) return AVL_ERR_ARG;
   int rc = ensure_attn_attrs();
   if (rc) return rc;
+  {
+    Launcher L{(cudaStream_t)stream};
+    if (attn_bwd_tc(L, qkv, off, B, D, out, lse, dout, dqkv, 1.0f / sqrtf(32.f), ATT_MAXV)) return L.err;
+  }
   AVL_LAUNCH(attn_self_bwd_kernel, dim3(B, D / 32), ATT_BWD_WARPS * 32, kAttnBwdSmem, (cudaStream_t)stream, 
       qkv, off, out, lse, dout, dqkv, D, 1.0f / sqrtf(32.f), ATT_MAXV);
   AVL_LAUNCH_CHECK();

@@ -426,3 +426,55 @@ def test_packed_weights_follow_the_fused_adam_step():
     torch.cuda.synchronize()
     assert float((y1 - y0).abs().max()) > 1e-2          # the step moved the weights by ~lr
     assert torch.equal(y1, fresh)
+
+
+TOL_ATTN = 2e-5  # 3xTF32 products, fp32 accumulate: of the output's / gradient's max magnitude
+
+
+@pytest.mark.parametrize("lens", [[1, 37, 301, 150, 2], [16, 15, 17, 31, 32, 33, 151, 8, 9, 64, 320], [95] * 7])
+def test_self_attention_tensor_cores_is_fp32_accurate(lens):
+    """Row F (smt_state_encoder.py:160-166): varlen multi-head self-attention as 3xTF32 warp MMAs against float64 torch,
+    ragged lengths around the 8 / 16 / 32-row tile edges, forward and backward; and against the fp32 SIMT kernels."""
+    import numpy as np
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K  # noqa: F401
+    g = torch.Generator().manual_seed(len(lens))
+    off = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+    R, D, H = int(off[-1]), 256, 8
+    qkv = (torch.randn(R, 3 * D, generator=g) * torch.exp(0.5 * torch.randn(R, 1, generator=g))).double().requires_grad_(True)
+    dout = torch.randn(R, D, generator=g).double()
+    outs = []
+    for b, L in enumerate(lens):
+        s = int(off[b])
+        q, k, v = (qkv[s:s + L, i * D:(i + 1) * D].view(L, H, 32).transpose(0, 1) for i in range(3))
+        a = torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v
+        outs.append(a.transpose(0, 1).reshape(L, D))
+    ref = torch.cat(outs)
+    (ref * dout).sum().backward()
+    qd, od, dd = qkv.detach().float().cuda(), off.cuda(), dout.float().cuda()
+    res = {}
+    for mode in (1, 0):
+        old = _lib.lib().avl_set_attn_tc(mode)
+        try:
+            out = torch.full((R, D), float("nan"), device="cuda")
+            lse = torch.full((R, H), float("nan"), device="cuda")
+            dq = torch.full((R, 3 * D), float("nan"), device="cuda")
+            _lib.call("avl_attn_self_fwd", qd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(), lse.data_ptr(), _lib.stream())
+            _lib.call("avl_attn_self_bwd", qd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(), lse.data_ptr(),
+                      dd.data_ptr(), dq.data_ptr(), _lib.stream())
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib().avl_set_attn_tc(old)
+        assert not torch.isnan(out).any() and not torch.isnan(lse).any() and not torch.isnan(dq).any()
+        res[mode] = (out.cpu().double(), lse.cpu().double(), dq.cpu().double())
+    for mode in (1, 0):
+        assert rel(res[mode][0], ref.detach()) < TOL_ATTN, mode
+        assert rel(res[mode][2], qkv.grad) < TOL_ATTN, mode
+    assert rel(res[1][1], res[0][1]) < 1e-5   # log-sum-exp of the two kernels
+    # deterministic: a second run reproduces the gradient bit for bit
+    dq2 = torch.empty(R, 3 * D, device="cuda")
+    out, lse = res[1][0].float().cuda(), res[1][1].float().cuda()
+    _lib.call("avl_attn_self_bwd", qd.data_ptr(), od.data_ptr(), len(lens), D, out.data_ptr(), lse.data_ptr(), dd.data_ptr(),
+              dq2.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dq2.cpu().double(), res[1][2])

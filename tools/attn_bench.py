@@ -32,6 +32,9 @@ def main():
         _lib.call("avl_attn_self_bwd", qkv.data_ptr(), off.data_ptr(), B, D, out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
                   dqkv.data_ptr(), _lib.stream())
 
+    mode = int(os.environ.get("AVL_ATTN_TC", "1"))
+    _lib.lib().avl_set_attn_tc(mode)
+    print(f"-- attn_tc={mode} (1: 3xTF32 warp MMAs, 0: register-tiled fp32)")
     fwd()
     # reference check on a few samples (fp64)
     for b in (0, B // 2, B - 1):

@@ -10,7 +10,7 @@ from torch.profiler import ProfilerActivity, profile
 from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
 
 
-def table(prof, title, n=18):
+def table(prof, title, n=40):
     ev = [e for e in prof.key_averages() if e.device_time_total > 0]
     tot = sum(e.device_time_total for e in ev)
     print(f"== {title}: total device {tot / 1000:.2f} ms")
