@@ -60,8 +60,34 @@ def _compile_one(src: str, verbose: bool) -> str:
     return obj
 
 
+PYHOST_SRC = os.path.join(CSRC, "py", "pyhost.c")
+PYHOST_PATH = os.path.join(HERE, "_pyhost.so")
+
+
+def build_pyhost(force: bool = False):
+    """The CPython glue of batch_obs (csrc/py/pyhost.c -> avlen_b200/_pyhost.so), compiled with the host C compiler
+    against this interpreter's headers.  Optional: without Python.h the pure-Python pointer loop is used instead."""
+    import sysconfig
+    inc = sysconfig.get_paths()["include"]
+    if not os.path.exists(os.path.join(inc, "Python.h")):
+        return None
+    stamp = PYHOST_PATH + ".sha"
+    with open(PYHOST_SRC, "rb") as f:
+        dig = hashlib.sha256(f.read() + sys.version.encode()).hexdigest()
+    if not force and os.path.exists(PYHOST_PATH) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return PYHOST_PATH
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-fvisibility=hidden", "-I", inc, PYHOST_SRC, "-o", PYHOST_PATH]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("pyhost build failed:\n" + res.stdout + res.stderr)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return PYHOST_PATH
+
+
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
+    build_pyhost(force)
     if force:
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))

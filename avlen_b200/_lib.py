@@ -23,6 +23,9 @@ _SIGNATURES = {
     "avl_device_sm_count": [],
     "avl_launch_count": [],
     "avl_launch_count_add": [c_longlong],
+    "avl_host_gather": [P, P, P, I],
+    "avl_set_host_gather_threads": [I],
+    "avl_set_host_gather_streaming": [I],
     "avl_spec_cache_lookup": [I, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_spec_cache_commit": [I, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "avl_audio_create": [I, ctypes.POINTER(c_void_p)],
@@ -81,6 +84,30 @@ def lib():
         _lib.avl_last_cuda_error_string.restype = ctypes.c_char_p
         _apply(_lib, _SIGNATURES)
     return _lib
+
+
+_pyhost = False
+
+
+def pyhost():
+    """The CPython glue module of batch_obs (csrc/py/pyhost.c), or None when it was not built (no Python.h at build
+    time): the caller then extracts the buffer addresses in Python."""
+    global _pyhost
+    if _pyhost is False:
+        path = os.path.join(os.path.dirname(LIB_PATH), "_pyhost.so")
+        _pyhost = None
+        if os.path.exists(path):
+            import importlib.machinery
+            import importlib.util
+            try:
+                loader = importlib.machinery.ExtensionFileLoader("_pyhost", path)
+                spec = importlib.util.spec_from_loader("_pyhost", loader)
+                mod = importlib.util.module_from_spec(spec)
+                loader.exec_module(mod)
+                _pyhost = mod
+            except ImportError:
+                _pyhost = None
+    return _pyhost
 
 
 def check(status: int, what: str = ""):

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import nn as K
-from .. import ops
+from .. import _lib, ops
 
 
 class _LinearFn(torch.autograd.Function):
@@ -117,51 +117,57 @@ def linear_decay(epoch: int, total_num_updates: int) -> float:
     return 1 - (epoch / float(total_num_updates))
 
 
-_STACK_POOL = None
-_STACK_WORKERS = 4
-
-
-def _stack_pool():
-    global _STACK_POOL
-    if _STACK_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _STACK_POOL = ThreadPoolExecutor(max_workers=_STACK_WORKERS, thread_name_prefix="avl_batch_obs")
-    return _STACK_POOL
+_NATIVE_MIN_BYTES = 1 << 18
+_GATHER_ADDR = None
 
 
 def _stack_into(observations, sensor, out):
-    """np.stack of one sensor into ``out`` (pinned staging).  Large sensors (frames) are copied by a few threads, each
-    taking a contiguous range of envs — numpy's copy loops release the GIL, and at 64 envs the 7 MB of rgb + depth
-    otherwise cost the host thread more than a whole policy step costs the GPU."""
+    """np.stack of one sensor into ``out`` (pinned staging).  Large sensors (frames) go through the library's native
+    gather (``avl_host_gather``: a persistent pool of copy threads, the GIL released for the whole call) — at 64 envs the
+    7 MB of rgb + depth copied piece by piece from Python cost the host thread more than a whole policy step costs the
+    GPU.  Pieces that are not C-contiguous arrays of the staging dtype take the numpy path."""
+    global _GATHER_ADDR
     n = len(observations)
-    if out.nbytes < (1 << 20) or n < 2 * _STACK_WORKERS:
-        np.stack([np.asarray(o[sensor]) for o in observations], out=out)
-        return []
-    per = (n + _STACK_WORKERS - 1) // _STACK_WORKERS
-
-    def job(lo, hi):
-        for i in range(lo, hi):
-            out[i] = observations[i][sensor]
-
-    return [_stack_pool().submit(job, lo, min(n, lo + per)) for lo in range(0, n, per)]
+    if out.nbytes >= _NATIVE_MIN_BYTES:
+        arrs = [o[sensor] for o in observations]
+        per = out.nbytes // n
+        ph = _lib.pyhost()
+        if ph is not None:
+            # buffer addresses, checks and the gather itself in C (csrc/py/pyhost.c); False = some piece does not fit
+            if _GATHER_ADDR is None:
+                import ctypes
+                _GATHER_ADDR = ctypes.cast(_lib.lib().avl_host_gather, ctypes.c_void_p).value
+            if ph.gather(_GATHER_ADDR, arrs, out.ctypes.data, per, out.dtype.char):
+                return
+        elif all(isinstance(a, np.ndarray) and a.dtype == out.dtype and a.flags.c_contiguous and a.nbytes == per for a in arrs):
+            import ctypes
+            src = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+            base = out.ctypes.data
+            dst = (ctypes.c_void_p * n)(*[base + i * per for i in range(n)])
+            nb = (ctypes.c_longlong * n)(*([per] * n))
+            _lib.call("avl_host_gather", src, dst, nb, n)
+            return
+    np.stack([np.asarray(o[sensor]) for o in observations], out=out)
 
 
 def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, pinned: Optional[Dict] = None,
-              keep_dtypes: Optional[Dict] = None):
+              keep_dtypes: Optional[Dict] = None, device_out: Optional[Dict] = None):
     """common/utils.py:129-156: list of per-env observation dicts -> dict of stacked tensors on ``device``.
 
     The reference inflates every sensor to fp32 on the host before a pageable copy; here each sensor is stacked ONCE,
     in its source dtype, straight into pinned staging memory (``pinned``: a dict the caller keeps between steps; two
     buffers per sensor alternate so that the copy of step s may still be in flight while step s+1 is staged; frames
-    are stacked by a small thread pool), copied asynchronously and converted on the device.  ``keep_dtypes`` (SURVEY
+    are gathered by the library's native copy threads with streaming stores), copied asynchronously and converted on the device.  ``keep_dtypes`` (SURVEY
     §8f item 2): sensors listed there stay in the given dtype on the device (``{"rgb": torch.uint8, "depth":
-    torch.float16}`` for the compact rollout storage); everything else becomes float32 as in the reference."""
+    torch.float16}`` for the compact rollout storage); everything else becomes float32 as in the reference.
+    ``device_out``: sensors listed there are copied into the given preallocated device tensors (source dtype and shape)
+    and returned as they are — fixed device addresses, which is what a rollout step replayed from CUDA graphs reads."""
     out = {}
     first = observations[0]
     n = len(observations)
-    staged = []
     for sensor in first:
         a0 = np.asarray(first[sensor])
+        slot, k = None, 0
         if pinned is not None:
             slot = pinned.get(sensor)
             if slot is None or slot[0][0].shape != (n,) + a0.shape or slot[0][0].numpy().dtype != a0.dtype:
@@ -171,18 +177,22 @@ def batch_obs(observations: List[Dict], device: Optional[torch.device] = None, p
             bufs, k, evs = slot
             if evs[k] is not None:
                 evs[k].synchronize()  # the H2D copy that last read this buffer (two steps ago) must have finished
-            staged.append((sensor, bufs[k], slot, k, _stack_into(observations, sensor, bufs[k].numpy())))
+            _stack_into(observations, sensor, bufs[k].numpy())
+            t = bufs[k]
         else:
-            staged.append((sensor, torch.from_numpy(np.stack([np.asarray(o[sensor]) for o in observations])), None, 0, []))
-    for sensor, t, slot, k, jobs in staged:
-        for j in jobs:
-            j.result()
-        d = t.to(device=device, non_blocking=True)
+            t = torch.from_numpy(np.stack([np.asarray(o[sensor]) for o in observations]))
+        # the copy of this sensor is enqueued before the next one is stacked: DMA and host gather overlap
+        fixed = device_out is not None and sensor in device_out
+        if fixed:
+            d = device_out[sensor]
+            d.copy_(t, non_blocking=True)
+        else:
+            d = t.to(device=device, non_blocking=True)
         if slot is not None and d.is_cuda:
             ev = torch.cuda.Event()
             ev.record()
             slot[2][k] = ev
             slot[1] = 1 - k
-        want = (keep_dtypes or {}).get(sensor, torch.float32)
+        want = d.dtype if fixed else (keep_dtypes or {}).get(sensor, torch.float32)
         out[sensor] = d if d.dtype == want else d.to(dtype=want)
     return out

@@ -96,7 +96,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // qkv: [R, 3 D] packed rows (q | k | v), heads of 32; off[b] .. off[b + 1] are sample b's rows.
-__global__ void __launch_bounds__(AT_WARPS * 32)
+__global__ void __launch_bounds__(AT_WARPS * 32, 3)
 attn_self_fwd_tc_kernel(const float* __restrict__ qkv, const int* __restrict__ off, float* out, float* lse, int D,
                         float scale, int vcap) {
   AVL_DYN_SMEM(smem_raw);
@@ -189,7 +189,7 @@ attn_self_fwd_tc_kernel(const float* __restrict__ qkv, const int* __restrict__ o
 }
 
 // Backward with recomputation.  dqkv receives (dq | dk | dv) rows.
-__global__ void __launch_bounds__(AT_WARPS * 32)
+__global__ void __launch_bounds__(AT_WARPS * 32, 2)
 attn_self_bwd_tc_kernel(const float* __restrict__ qkv, const int* __restrict__ off, const float* __restrict__ out,
                         const float* __restrict__ lse, const float* __restrict__ dout, float* dqkv, int D, float scale,
                         int vcap) {

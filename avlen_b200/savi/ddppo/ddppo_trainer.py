@@ -202,9 +202,13 @@ class DDPPOTrainer(PPOTrainer):
     # device-resident env (host frames are staged by the host every step), no preemption.
     def _step_graphs_possible(self):
         cfg = self.config
-        if not (getattr(cfg, "step_graphs", False) and not cfg.host_buffers and not cfg.use_preemption
-                and getattr(self, "_step_graphs_ok", True)):
+        if not (getattr(cfg, "step_graphs", False) and not cfg.use_preemption and getattr(self, "_step_graphs_ok", True)):
             return False
+        if cfg.host_buffers:
+            # host frames: a step is TWO graphs around the point where the env worker needs the actions on the host
+            # (``_capture_step_split``); plain SMT policy with frozen encoders on the synthetic env only
+            return (cfg.policy_type == "smt" and cfg.freeze_encoders and getattr(self.envs, "fused_step", False)
+                    and getattr(self.envs, "host_buffers", False) and hasattr(self.envs, "stage_frames"))
         if cfg.policy_type == "interactive":
             # pi_g / pi_l are frozen, pi_q never trains its encoders (policy.py:1034-1036): no packed weight changes
             # between rollouts; env / bookkeeping / memory / CLIP-cache state lives in persistent device buffers
@@ -233,7 +237,64 @@ class DDPPOTrainer(PPOTrainer):
         _lib.lib().avl_launch_count_add(-(n1 - n0))  # counted at capture, but nothing ran yet
         return g
 
+    # Host frames (``host_buffers``: the e2e path): the env worker needs the step's actions on the host and hands back
+    # frames that the host has to stage, so a step cannot be one graph.  It is two: A = policy act + D2H of the actions;
+    # [host: wait for A, env workers step, batch_obs stages the frames into pinned memory and copies them into FIXED
+    # device buffers]; B = device side of the env step (episode bookkeeping, audio rendering), belief networks, encoder
+    # prefetch of the next observation, storage insert.  The split is made from inside ``envs.step`` through the env's
+    # ``graph_split`` hook, so ``_collect_rollout_step`` is captured unchanged.
+    def _capture_step_split(self, s):
+        net = self.actor_critic.net
+        env = self.envs
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = int(_lib.lib().avl_launch_count())
+        kw = lambda: ({"pool": self._graph_pool} if self._graph_pool is not None else {})  # noqa: E731
+        state = {"in_b": False}
+
+        def split():
+            K.sync_pending()
+            ga.capture_end()
+            if self._graph_pool is None:
+                self._graph_pool = ga.pool()
+            ga.replay()                                  # the step really runs while it is being captured
+            torch.cuda.current_stream().synchronize()    # actions are on the host
+            env.stage_frames()
+            gb.capture_begin(capture_error_mode="relaxed", **kw())
+            state["in_b"] = True
+
+        env.graph_split = split
+        env.static_frames = True
+        ga.capture_begin(capture_error_mode="relaxed", **kw())
+        try:
+            self._collect_rollout_step(self.rollouts)
+            K.sync_pending()
+            if hasattr(net, "join_prefetch"):
+                net.join_prefetch()
+        finally:
+            env.graph_split = None
+            (gb if state["in_b"] else ga).capture_end()
+        n1 = int(_lib.lib().avl_launch_count())
+        gb._avl_launches = n1 - n0   # kernels of A + B; both run exactly once here (A above, B below): the count stands
+        ga._avl_launches = 0
+        gb.replay()
+        return (ga, gb)
+
+    def _replay_step_split(self, pair):
+        ga, gb = pair
+        env = self.envs
+        ga.replay()
+        torch.cuda.current_stream().synchronize()
+        env._t += 1
+        env.stage_frames()
+        gb.replay()
+        _lib.lib().avl_launch_count_add(gb._avl_launches)
+        r = self.rollouts
+        r.step += 1
+        r.em.advance_host_index()
+
     def _replay_step(self, g):
+        if isinstance(g, tuple):
+            return self._replay_step_split(g)
         g.replay()
         _lib.lib().avl_launch_count_add(g._avl_launches)
         # the host-side counters the eager step advances
@@ -288,6 +349,9 @@ class DDPPOTrainer(PPOTrainer):
                     torch.cuda.synchronize()
                     graphs = []
                     for s in range(cfg.num_steps):
+                        if cfg.host_buffers:
+                            graphs.append(self._capture_step_split(s))  # (runs the step while capturing it)
+                            continue
                         g = self._capture_step(s)
                         g.replay()
                         _lib.lib().avl_launch_count_add(g._avl_launches)

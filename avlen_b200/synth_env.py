@@ -42,6 +42,12 @@ class SyntheticVectorEnv:
             self._rgb_np, self._depth_np = rgb.numpy(), depth.numpy()
             self._staging = {}
             self._actions_host = torch.zeros(n, 1, dtype=torch.int64).pin_memory()
+            # split-step CUDA graphs (DDPPOTrainer): the frames of a step land in FIXED device buffers (``stage_frames``,
+            # run by the host between the two graphs of a step); ``graph_split`` is the trainer's hook at the point where
+            # the env worker needs the actions on the host
+            self._frames_dev = None
+            self.static_frames = False
+            self.graph_split = None
         else:
             self._rgb, self._depth = rgb.to(self.device), depth.to(self.device)
             if self.compact:
@@ -73,6 +79,11 @@ class SyntheticVectorEnv:
         event instead of for the whole main stream."""
         i = self._t % self.pool
         main = torch.cuda.current_stream()
+        if self.host_buffers and self.static_frames:
+            # the host has already staged this step's frames (``stage_frames``); only the device-side casts remain
+            rgb, depth = self._frames_dev["rgb"], self._frames_dev["depth"]
+            self.visual_ready_event = None
+            return (rgb, depth.half()) if self.compact else (rgb.float(), depth)
         side = self._visual_stream
         if side is None:
             side = self._visual_stream = torch.cuda.Stream()
@@ -94,6 +105,16 @@ class SyntheticVectorEnv:
         self.visual_ready_event = ev
         return rgb, depth
 
+    def stage_frames(self):
+        """Host side of a step under split-step graphs: what the VectorEnv hands over for the CURRENT step (one observation
+        dict per env, numpy frames) goes through ``batch_obs`` into the fixed device buffers, on the current stream."""
+        i = self._t % self.pool
+        if self._frames_dev is None:
+            self._frames_dev = {"rgb": torch.empty((self.num_envs, 128, 128, 3), dtype=torch.uint8, device=self.device),
+                                "depth": torch.empty((self.num_envs, 128, 128, 1), dtype=torch.float32, device=self.device)}
+        per_env = [{"rgb": self._rgb_np[i][e], "depth": self._depth_np[i][e]} for e in range(self.num_envs)]
+        batch_obs(per_env, device=self.device, pinned=self._staging, device_out=self._frames_dev)
+
     def _observe(self, silent=None, pose=None, beliefs=None):
         a = self._audio
         if silent is None:
@@ -102,10 +123,11 @@ class SyntheticVectorEnv:
         _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
                                        silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
                                        want_audiogoal=False)
-        main = torch.cuda.current_stream()
-        main.wait_event(self.visual_ready_event)
-        rgb.record_stream(main)
-        depth.record_stream(main)
+        if self.visual_ready_event is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(self.visual_ready_event)
+            rgb.record_stream(main)
+            depth.record_stream(main)
         if pose is None:
             pose = torch.cat([self._pose_xy, self._heading[:, None], self._episode_step[:, None]], 1)
         n = self.num_envs
@@ -121,11 +143,14 @@ class SyntheticVectorEnv:
 
     def step(self, actions):
         """actions: (N, 1) int64 device tensor.  Returns (obs dict, rewards (N,1), dones (N,) bool)."""
+        self._t += 1
         if self.host_buffers:  # the env worker needs the actions on the host (ppo_trainer.py:698-714)
             self._actions_host.copy_(actions, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if self.graph_split is not None:
+                self.graph_split()  # (trainer: ends the first graph of the step, waits, stages the frames, begins the second)
+            else:
+                torch.cuda.current_stream().synchronize()
         n, dev = self.num_envs, self.device
-        self._t += 1
         r = torch.rand(n, 3, device=dev)
         if self.fused_step:
             f32 = torch.float32

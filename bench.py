@@ -319,14 +319,17 @@ def run_savi(args):
             over.update(clip_layers=args.clip_layers)
         cfg2 = savi_config(**over)
         tr2 = DDPPOTrainer(cfg2).setup()
-        k2 = max(1, min(2, args.steps))
-        ms2, _, _, _, stats = time_cycles(tr2, cfg2, k2, 1)
+        k2 = max(1, min(3, args.steps))
+        # (>= 3 warm-up cycles: the split-step graphs are captured during the second rollout and replayed from the third)
+        ms2, roll2, tot2, _, stats = time_cycles(tr2, cfg2, k2, max(3, min(args.warmup, 3)))
         e2e = {"value": round(env_steps / (ms2 * 1e-3), 2), "unit": UNIT,
                "h2d_bytes_per_step": int(tr2.envs.h2d_bytes_per_step * args.rollout_steps),
                "d2h_bytes_per_step": int(tr2.envs.d2h_bytes_per_step * args.rollout_steps + 8 * 4),
+               "rollout_env_steps_per_s": round(args.envs * args.rollout_steps * k2 / (roll2 * 1e-3), 1),
                "path": "SyntheticVectorEnv(host_buffers) -> list of per-env numpy dicts -> common.utils.batch_obs "
-                       "(pinned staging, async H2D, device-side cast) -> policy; actions D2H every step; losses D2H "
-                       "every update"}
+                       "(native gather into pinned staging, async H2D into fixed device buffers, device-side cast) -> "
+                       "policy; actions D2H + stream sync every step; losses D2H every update; each step replays as two "
+                       "CUDA graphs around the host's part (frozen SMT regime)"}
         del tr2
         torch.cuda.empty_cache()
 

@@ -109,6 +109,14 @@ int avl_resize_half_typed(const void* x, int dtype, const long long* sample_inde
  * 4 fp32 -> int64 (n elements).                                                                                        */
 int avl_multi_copy(int count, void* const* dst, const void* const* src, const long long* n, const unsigned char* kind,
                    void* stream);
+/* ------------------------------------------------------------------- row T: batch_obs, host side
+ * ss_baselines/common/utils.py:129-156 stacks the per-env observation arrays with np.stack / torch.tensor on the host.
+ * avl_host_gather copies n pieces of HOST memory (dst[i][0..bytes[i]) = src[i][0..bytes[i])) with a small persistent
+ * pool of native threads — the per-env frames land in one pinned staging buffer per sensor; no CUDA call is made.
+ * avl_set_host_gather_threads: copy threads including the caller (0 = automatic); returns the old setting.             */
+int avl_host_gather(const void* const* src, void* const* dst, const long long* bytes, int n);
+int avl_set_host_gather_threads(int threads);
+int avl_set_host_gather_streaming(int on); /* 1 (default): non-temporal stores into the staging buffer (the copy engine reads it next; dirty cache lines made the H2D copy 5x slower); 0: memcpy; returns old */
 /* ------------------------------------------------------------------- RIR bank + spectrogram cache
  * Replaces the per-miss wav read (soundspaces/simulator.py:650-659) and the per-simulator dict caches keyed by
  * (source, receiver, azimuth) (:711-734; cleared on scene / sound change :393-395; `_audio_index` advances on a miss only,

@@ -67,9 +67,42 @@ def test_graphed_rollouts_equal_eager_semantics():
     tr.envs.close()
 
 
+def test_split_step_graphs_with_host_frames():
+    """The e2e path (``host_buffers``: per-env numpy frames -> batch_obs -> device, actions read back every step) as two
+    graphs per step around the host's part: same storage semantics as the eager rollout, and the frames that reach the
+    rollout storage are exactly the ones the env handed over."""
+    from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
+    cfg = savi_config(NUM_PROCESSES=6, num_steps=10, memory_size=12, step_graphs=True, host_buffers=True)
+    tr = DDPPOTrainer(cfg).setup()
+    assert tr._step_graphs_possible()
+    env = tr.envs
+    masks0, idx0 = tr.rollouts.em.masks.cpu().clone(), tr.rollouts.em.idx
+    for r in range(5):  # eager warm-up, capture, three replays
+        tr.collect_rollout()
+        if r >= 1:
+            assert tr._step_graphs is not None and isinstance(tr._step_graphs[0], tuple)
+        worst, masks0, idx0 = _check_rollout(tr, cfg, masks0, idx0)
+        assert worst < 2e-3, (r, worst)
+        rgb = tr.rollouts.observations["rgb"].cpu()
+        depth = tr.rollouts.observations["depth"].float().cpu()
+        for s in range(cfg.num_steps + 1):
+            i = (r * cfg.num_steps + s) % env.pool
+            assert torch.equal(rgb[s], torch.from_numpy(env._rgb_np[i]).to(rgb.dtype)), (r, s)
+            assert float((depth[s] - torch.from_numpy(env._depth_np[i])).abs().max()) < 5e-4, (r, s)
+        acts = tr.rollouts.actions[cfg.num_steps - 1].cpu()
+        assert torch.equal(env._actions_host, acts)   # the last step's actions reached the host
+        tr.rollouts.after_update()
+    for _ in range(2):
+        tr.collect_rollout()
+        stats = tr._update_agent(cfg, tr.rollouts)
+        assert all(np.isfinite(v) for v in stats)
+    tr.envs.close()
+
+
 def test_step_graphs_are_skipped_where_they_do_not_apply():
     from avlen_b200.savi.ddppo.ddppo_trainer import DDPPOTrainer, savi_config
-    for over in (dict(freeze_encoders=False, pretraining=True), dict(host_buffers=True)):
+    for over in (dict(freeze_encoders=False, pretraining=True), dict(use_preemption=True),
+                 dict(host_buffers=True, freeze_encoders=False, pretraining=True)):
         tr = DDPPOTrainer(savi_config(NUM_PROCESSES=4, num_steps=4, memory_size=4, **over)).setup()
         assert not tr._step_graphs_possible()
         tr.collect_rollout()
