@@ -49,7 +49,7 @@ _SIGNATURES = {
     "avl_grad_sumsq": [P, L, P, P, P],
     "avl_clip_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P, F, P],
 }
-_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_launch_count": c_longlong, "avl_launch_count_add": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
+_RESTYPES = {"avl_ppo_loss_workspace": c_longlong, "avl_launch_count": c_longlong, "avl_tc_conv_tma_count": c_longlong, "avl_launch_count_add": c_longlong, "avl_last_cuda_error_string": ctypes.c_char_p}
 
 _lib = None
 

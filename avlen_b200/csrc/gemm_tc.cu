@@ -15,6 +15,9 @@
 // plane_stride = rows*16 + 16 so that a warp's 16-byte cp.async writes spread over all banks.
 // One MMA consumes K = 8 fp32 (two chunks).  M tile = 128 (one TMEM lane per row), N tile <= 256.
 #include "tc_common.cuh"
+#ifndef AVL_HOST_EMUL
+#include <cuda.h>
+#endif
 
 #ifndef AVL_HOST_EMUL
 namespace {
@@ -53,7 +56,20 @@ struct TcArgs {
                      // slice order (deterministic), epilogue applied in the same kernel — no zero / epilogue launches
   int splits_nz;     // slices that own at least one k-tile (the others only take part in the reduction)
   unsigned red_off;  // byte offset of the reduction buffer in dynamic shared memory (0: it aliases the operand ring)
+  // TMA mode (template parameter TMA): operands arrive by cp.async.bulk.tensor — A through an im2col-mode tensor map
+  // (one box = 128 output pixels x 32 channels of one filter tap), B through a tiled map of the packed weights; k-tile
+  // kt = tap * cblocks + channel block; one elected thread issues both loads of a stage
+  int kt_total, cblocks;
 };
+
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, int c, int w, int h, int n,
+                                                   unsigned short off_w, unsigned short off_h, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 
 __device__ __forceinline__ void cluster_arrive_wait() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -70,8 +86,8 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t local_addr, uint32_t rank
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <bool CONV, bool CA = false>
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
+template <bool CONV, bool CA, bool TMA>
+__device__ __forceinline__ void tc_gemm_body(const TcArgs& p, const CUtensorMap* tmA, const CUtensorMap* tmB) {
   AVL_DYN_SMEM(smem);
   __shared__ __align__(8) unsigned long long bars[2 * TC_MAX_STAGES + 1];  // full[S], empty[S], done
   const int TC_STAGES = p.stages;
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const int bn = p.bn;
   const int K = p.K;
   const int kt0 = blockIdx.z * p.kt_per_split;  // split-K: this CTA reduces k-tiles [kt0, kt0 + KT)
-  const int KT = max(0, min((K + TC_BK - 1) / TC_BK - kt0, p.kt_per_split));
+  const int KT = max(0, min((TMA ? p.kt_total : (K + TC_BK - 1) / TC_BK) - kt0, p.kt_per_split));
   const bool cred = p.cluster_red != 0;
   if (KT <= 0 && !cred) return;  // (a cluster member without k-tiles still owns output rows of the reduction)
 
@@ -107,8 +123,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   const uint32_t DONE = bar0 + 8u * (2 * TC_STAGES);
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(FULL(i), TC_LOAD_THREADS);
+      mbar_init(FULL(i), TMA ? 1 : TC_LOAD_THREADS);
       mbar_init(EMPTY(i), 1);
+    }
+    if (TMA) {
+      tma_prefetch_desc(tmA);
+      tma_prefetch_desc(tmB);
     }
     mbar_init(DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,6 +246,24 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   // ==================================================================================== loaders (warps 0-3)
   // Each thread keeps TC_INFLIGHT groups of cp.async in flight; a stage is signalled full by all 128 threads once
   // their own copies for it have landed (wait_group) and been fenced towards the async proxy.
+  if (TMA) {
+    if (tid == 0) {  // one thread keeps the whole ring in flight: loads are fire-and-forget
+      const int ow = m0 % p.g.OW, t = m0 / p.g.OW;
+      const int cw = ow * p.g.stride - p.g.pad, ch = (t % p.g.OH) * p.g.stride - p.g.pad, cn = t / p.g.OH;
+      int tap = kt0 / p.cblocks, cb = kt0 - tap * p.cblocks;
+      for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % TC_STAGES;
+        if (kt >= TC_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / TC_STAGES - 1) & 1));
+        const uint32_t a_dst = smem_base + slot * stage_bytes;
+        mbar_arrive_expect_tx(FULL(slot), stage_bytes);
+        const int r = tap / p.g.KW, sx = tap - r * p.g.KW;
+        tma_load_im2col_4d(a_dst, tmA, cb * TC_BK, cw, ch, cn, (unsigned short)sx, (unsigned short)r, FULL(slot));
+        tma_load_2d(a_dst + a_stage, tmB, tap * p.g.C + cb * TC_BK, n0, FULL(slot));
+        if (++cb == p.cblocks) { cb = 0; ++tap; }
+      }
+    }
+    __syncwarp();
+  } else {
   for (int kt = 0; kt < KT; ++kt) {
     const int slot = kt % TC_STAGES;
     if (kt >= TC_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / TC_STAGES - 1) & 1));
@@ -240,6 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   cp_async_wait<0>();
   fence_proxy_async();
   for (int kt = max(0, KT - TC_INFLIGHT); kt < KT; ++kt) mbar_arrive(FULL(kt % TC_STAGES));
+  }
   if (KT > 0) mbar_wait(DONE, 0);
   tc_fence_after();
 
@@ -361,6 +400,16 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
   __syncthreads();  // warp 4 deallocates TMEM after every epilogue warp has drained it
 }
 
+template <bool CONV, bool CA = false>
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs p) {
+  tc_gemm_body<CONV, CA, false>(p, nullptr, nullptr);
+}
+// the same kernel fed by TMA (im2col-mode map for the activations, tiled map for the packed weights)
+__global__ void __launch_bounds__(TC_THREADS) tc_conv_tma_splitk_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                        const __grid_constant__ CUtensorMap tmB, TcArgs p) {
+  tc_gemm_body<true, false, true>(p, &tmA, &tmB);
+}
+
 static int g_tc_ca = 1;
 static int g_tc_splitk = 1;
 static int g_tc_splitk_cluster = 1;
@@ -397,12 +446,19 @@ static int pick_bn(int N) {
   return 256;
 }
 
-static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
+extern "C" bool avl_conv_tma_maps(CUtensorMap* ta, CUtensorMap* tb, const float* x, int N, int H, int W, int C,
+                                  const float* w_packed, int Cout, int KH, int KW, int stride, int pad, int bn);  // gemm_tma.cu
+extern "C" void avl_tc_conv_tma_count_add();
+
+// want_tma: a convolution whose operands may come by TMA (im2col-mode map); decided here once the N tile is known
+static int tc_launch(bool conv, TcArgs& p, cudaStream_t s, bool want_tma = false) {
   static bool attr_set = false;
   if (!attr_set) {
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_tma_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaFuncSetAttribute(tc_conv_tma_splitk_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     // clusters of 16 CTAs for the longest reductions: opt-in per kernel, then ask the driver whether one fits
     bool ok16 = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                 cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
@@ -429,7 +485,10 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   p.bn = pick_bn(p.N);
   const int sms = avl_num_sms();
   const int mtiles = avl_div_up(p.M, TC_BM);
-  const int KT = avl_div_up(p.K, TC_BK);
+  want_tma = want_tma && conv && g_tc_swz && p.g.C >= 32 && p.g.KH == p.g.KW;
+  p.cblocks = avl_div_up(p.g.C, TC_BK);
+  p.kt_total = p.g.KH * p.g.KW * p.cblocks;
+  const int KT = want_tma ? p.kt_total : avl_div_up(p.K, TC_BK);
   p.splits = 1;
   p.splits_nz = 1;
   p.cluster_red = 0;
@@ -487,6 +546,33 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s) {
   dim3 grid(mtiles, avl_div_up(p.N, p.bn), p.splits);
   const float *scale = p.scale, *bias = p.bias, *residual = p.residual;
   const int relu = p.relu;
+  CUtensorMap ta, tb;
+  // (TMA mode serves the single-launch forms: no split, or the in-cluster reduction; the atomic split-K fallback keeps
+  // its helper kernels and the cp.async loaders)
+  const bool tma = want_tma && (p.splits == 1 || p.cluster_red) &&
+                   avl_conv_tma_maps(&ta, &tb, p.A, p.g.N, p.g.H, p.g.W, p.g.C, p.B, p.N, p.g.KH, p.g.KW, p.g.stride, p.g.pad, p.bn);
+  if (want_tma && !tma && KT != avl_div_up(p.K, TC_BK)) {
+    // the split was planned on per-tap k-tiles (channels not a multiple of 32): re-plan for the cp.async k-tiles
+    return tc_launch(conv, p, s, false);
+  }
+  if (tma) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = (unsigned)(p.cluster_red ? p.splits : 1);
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_conv_tma_splitk_kernel, ta, tb, p));
+    AVL_LAUNCH_CHECK();
+    avl_tc_conv_tma_count_add();
+    return AVL_OK;
+  }
   if (p.cluster_red) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -599,6 +685,10 @@ int avl_tc_conv_halo_try(const float* x, int N, int H, int W, int C, const float
                          int stride, int pad, const float* scale, const float* bias, const float* residual,
                          long long ldr, int relu, float* y, long long ldy, cudaStream_t stream);  // conv_halo_tc.cu
 
+int avl_tc_conv_tma_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
+                        int stride, int pad, const float* scale, const float* bias, const float* residual, long long ldr,
+                        int relu, float* y, long long ldy, cudaStream_t stream);  // gemm_tma.cu
+
 // NHWC convolution on the tensor cores.  w_packed: (Cout, KH, KW, C) (k = (r*KW + s)*C + ci), C % 4 == 0.
 AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH,
                               int KW, int stride, int pad, const float* scale, const float* bias,
@@ -617,6 +707,11 @@ AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const 
                                   y, ldy, (cudaStream_t)stream);
     if (rc != AVL_ERR_UNSUPPORTED) return rc;
   }
+  {  // deep layers with enough output tiles: TMA in im2col mode (gemm_tma.cu)
+    int rc = avl_tc_conv_tma_try(x, N, H, W, C, w_packed, Cout, KH, KW, stride, pad, scale, bias, residual, ldr, relu, y, ldy,
+                                 (cudaStream_t)stream);
+    if (rc != AVL_ERR_UNSUPPORTED) return rc;
+  }
   TcArgs p = {};
   p.g.N = N; p.g.H = H; p.g.W = W; p.g.C = C; p.g.KH = KH; p.g.KW = KW; p.g.stride = stride; p.g.pad = pad;
   p.g.OH = (H + 2 * pad - KH) / stride + 1;
@@ -626,6 +721,6 @@ AVL_API int avl_tc_conv2d_fwd(const float* x, int N, int H, int W, int C, const 
   if (M > 2147483647LL) return AVL_ERR_UNSUPPORTED;
   p.A = x; p.B = w_packed; p.C = y; p.ldc = ldy; p.M = (int)M; p.N = Cout; p.K = KH * KW * C;
   p.bias = bias; p.scale = scale; p.residual = residual; p.ldr = ldr; p.relu = relu; p.m_dev = nullptr;
-  return tc_launch(true, p, (cudaStream_t)stream);
+  return tc_launch(true, p, (cudaStream_t)stream, true);
 }
 #endif  // AVL_HOST_EMUL

@@ -23,12 +23,30 @@ struct TmaArgs {
   int stages;     // 2..4: sized so that two CTAs fit one SM (one CTA's epilogue overlaps the other's main loop)
   int vec_store;  // rows of C (and of the residual) are 16-byte aligned
   const float* bias;
+  const float* scale;
   const float* residual;
   long long ldr;
   int relu;
   const int* m_dev;
+  // CONV: A is the im2col view of an NHWC tensor, loaded by TMA in im2col mode (one box = 128 output pixels x 32 channels
+  // of one filter tap); k-tile kt = tap * cblocks + channel block
+  int OH, OW, Cin, KW, conv_stride, pad, cblocks;
 };
 
+// cp.async.bulk.tensor im2col mode: {c, w, h, n} = channel offset and the input coordinates of the FIRST output pixel of
+// the tile's tap (0, 0) (ow * stride - pad, oh * stride - pad: inside the map's pixel bounding box); the unit walks 128
+// output pixels from there (W, then H, then N, stepping by the traversal strides of the map), adds the tap offsets and
+// zero-fills whatever falls outside the tensor.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, int c, int w, int h, int n,
+                                                   unsigned short off_w, unsigned short off_h, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+template <bool CONV>
 __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TmaArgs p) {
   AVL_DYN_SMEM(smem);
@@ -42,7 +60,7 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
   if (m0 >= M) return;
   const int n0 = blockIdx.y * p.bn;
   const int bn = p.bn;
-  const int KT = (p.K + TM_BK - 1) / TM_BK;
+  const int KT = CONV ? p.K : (p.K + TM_BK - 1) / TM_BK;  // (CONV: the host passes the number of k-tiles)
   const uint32_t a_stage = TM_BM * 128u, b_stage = (uint32_t)bn * 128u, stage_bytes = a_stage + b_stage;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -94,13 +112,28 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
     return;
   }
   if (tid == 0) {  // TMA producer
+    int cw = 0, ch = 0, cn = 0;
+    if (CONV) {
+      const int ow = m0 % p.OW, t = m0 / p.OW;
+      cw = ow * p.conv_stride - p.pad;
+      ch = (t % p.OH) * p.conv_stride - p.pad;
+      cn = t / p.OH;
+    }
+    int tap = 0, cb = 0;
     for (int kt = 0; kt < KT; ++kt) {
       const int slot = kt % TM_STAGES;
       if (kt >= TM_STAGES) mbar_wait(EMPTY(slot), (uint32_t)((kt / TM_STAGES - 1) & 1));
       const uint32_t a_dst = smem_base + slot * stage_bytes;
       mbar_arrive_expect_tx(FULL(slot), stage_bytes);
-      tma_load_2d(a_dst, &tmA, kt * TM_BK, m0, FULL(slot));
-      tma_load_2d(a_dst + a_stage, &tmB, kt * TM_BK, n0, FULL(slot));
+      if (CONV) {
+        const int r = tap / p.KW, sx = tap - r * p.KW;
+        tma_load_im2col_4d(a_dst, &tmA, cb * TM_BK, cw, ch, cn, (unsigned short)sx, (unsigned short)r, FULL(slot));
+        tma_load_2d(a_dst + a_stage, &tmB, tap * p.Cin + cb * TM_BK, n0, FULL(slot));
+        if (++cb == p.cblocks) { cb = 0; ++tap; }
+      } else {
+        tma_load_2d(a_dst, &tmA, kt * TM_BK, m0, FULL(slot));
+        tma_load_2d(a_dst + a_stage, &tmB, kt * TM_BK, n0, FULL(slot));
+      }
     }
   }
   __syncwarp();
@@ -120,6 +153,10 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
         for (int j = 0; j < 16; j += 4) {
           float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                  __uint_as_float(v[j + 3]));
+          if (p.scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c0 + j));
+            x.x *= sc.x; x.y *= sc.y; x.z *= sc.z; x.w *= sc.w;
+          }
           if (p.bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
             x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
@@ -137,6 +174,7 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
           const int n = n0 + c0 + j;
           if (n < p.N) {
             float x = __uint_as_float(v[j]);
+            if (p.scale) x *= __ldg(p.scale + n);
             if (p.bias) x += __ldg(p.bias + n);
             if (rrow) x += rrow[j];
             if (p.relu) x = fmaxf(x, 0.f);
@@ -182,9 +220,120 @@ bool make_map(CUtensorMap* map, const float* base, long long rows, long long col
   return r == CUDA_SUCCESS;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  return fn;
+}
+
+// NHWC fp32 activations as a rank-4 im2col map (C, W, H, N): the pixel bounding box holds the input coordinates of tap
+// (0, 0) of every output pixel — [-pad, size + pad - (K - 1)) per spatial dimension — traversed with the convolution's
+// stride; one load = 128 pixels x 32 channels, SWIZZLE_128B (= the K-major UMMA operand tile).
+bool make_im2col_map(CUtensorMap* map, const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad) {
+  EncodeIm2colFn enc = encode_im2col();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)W * C * sizeof(float), (cuuint64_t)H * W * C * sizeof(float)};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (KW - 1), pad - (KH - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower, upper,
+                   (cuuint32_t)TM_BK, (cuuint32_t)TM_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int g_tma_on = 1;
+int g_tma_conv_on = 1;
+long long g_tma_conv_launches = 0;
 
 }  // namespace
+
+// 1 (default): convolutions with >= 32 input channels and enough output tiles to fill the GPU are fed by TMA in im2col
+// mode (no per-16-byte gather instructions); 0: the cp.async im2col kernel everywhere.  Returns the old value.
+AVL_API int avl_set_tc_conv_tma(int on) {
+  avl_bump_config_epoch();
+  int old = g_tma_conv_on;
+  g_tma_conv_on = on ? 1 : 0;
+  return old;
+}
+
+// The two tensor maps of a TMA-fed convolution (gemm_tc.cu builds them for its split-K kernel): im2col-mode map of the
+// NHWC activations, tiled map of the packed weights with `bn` rows per box.  False: the driver entry point is missing or
+// the shape is outside the maps' limits.
+extern "C" bool avl_conv_tma_maps(CUtensorMap* ta, CUtensorMap* tb, const float* x, int N, int H, int W, int C,
+                                  const float* w_packed, int Cout, int KH, int KW, int stride, int pad, int bn) {
+  if (!g_tma_conv_on || KH != KW || C < 32 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
+      ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15) || H + 2 * pad - (KH - 1) < 1 || W + 2 * pad - (KW - 1) < 1)
+    return false;
+  return make_im2col_map(ta, x, N, H, W, C, KH, KW, stride, pad) && make_map(tb, w_packed, Cout, (long long)KH * KW * C,
+                                                                             (long long)KH * KW * C, bn);
+}
+
+// Number of convolutions this process has launched on the TMA im2col kernel (tests assert that the path is taken).
+AVL_API long long avl_tc_conv_tma_count(void) { return g_tma_conv_launches; }
+extern "C" void avl_tc_conv_tma_count_add() { ++g_tma_conv_launches; }
+
+// Implicit-GEMM convolution fed by TMA (im2col mode).  AVL_ERR_UNSUPPORTED = not taken (avl_tc_conv2d_fwd falls through
+// to the cp.async kernel): switched off, shape outside the map's limits, or too few output tiles (those go split-K).
+int avl_tc_conv_tma_try(const float* x, int N, int H, int W, int C, const float* w_packed, int Cout, int KH, int KW,
+                        int stride, int pad, const float* scale, const float* bias, const float* residual, long long ldr,
+                        int relu, float* y, long long ldy, cudaStream_t stream) {
+  if (!g_tma_conv_on) return AVL_ERR_UNSUPPORTED;
+  if (KH != KW || C < 32 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
+      ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15))
+    return AVL_ERR_UNSUPPORTED;
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  if (OH < 1 || OW < 1 || H + 2 * pad - (KH - 1) < 1 || W + 2 * pad - (KW - 1) < 1) return AVL_ERR_UNSUPPORTED;
+  const long long M = (long long)N * OH * OW;
+  if (M > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  const int K = KH * KW * C;
+  TmaArgs p = {};
+  p.C = y; p.ldc = ldy; p.M = (int)M; p.N = Cout; p.bias = bias; p.scale = scale; p.residual = residual; p.ldr = ldr;
+  p.relu = relu; p.m_dev = nullptr;
+  p.OH = OH; p.OW = OW; p.Cin = C; p.KW = KW; p.conv_stride = stride; p.pad = pad;
+  const int n16 = (Cout + 15) / 16 * 16;
+  const int mtiles = avl_div_up(M, TM_BM), sms = avl_num_sms();
+  p.bn = n16 < 128 ? n16 : 128;
+  if ((long long)mtiles * avl_div_up(Cout, p.bn) < 2LL * sms) return AVL_ERR_UNSUPPORTED;  // small grids: split-K kernel
+  p.cblocks = avl_div_up(C, TM_BK);
+  p.K = KH * KW * p.cblocks;  // number of k-tiles (the kernel's CONV loop bound)
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap ta, tb;
+  if (!make_im2col_map(&ta, x, N, H, W, C, KH, KW, stride, pad) || !make_map(&tb, w_packed, Cout, K, K, p.bn))
+    return AVL_ERR_UNSUPPORTED;
+  const size_t stage = (TM_BM + (size_t)p.bn) * 128;
+  p.stages = (int)((100 * 1024) / stage);
+  if (p.stages > TM_MAX_STAGES) p.stages = TM_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
+                 (!scale || ((uintptr_t)scale & 15) == 0) &&
+                 (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
+  const size_t smem = (size_t)p.stages * stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(mtiles, avl_div_up(Cout, p.bn));
+  tc_gemm_tma_kernel<true><<<grid, TM_THREADS, smem, stream>>>(ta, tb, p);
+  AVL_LAUNCH_CHECK();
+  ++g_tma_conv_launches;
+  return AVL_OK;
+}
 
 AVL_API int avl_set_tc_tma(int on) {
   avl_bump_config_epoch();
@@ -224,11 +373,11 @@ int avl_tc_gemm_tma_try(const float* A, long long lda, const float* B, float* C,
   const size_t smem = (size_t)p.stages * stage;
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid(avl_div_up(M, TM_BM), avl_div_up(N, p.bn));
-  tc_gemm_tma_kernel<<<grid, TM_THREADS, smem, stream>>>(ta, tb, p);
+  tc_gemm_tma_kernel<false><<<grid, TM_THREADS, smem, stream>>>(ta, tb, p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -36,6 +36,8 @@ _lib.register({
     "avl_get_tensor_cores": [],
     "avl_set_tc_conv_l1": [I],
     "avl_set_attn_tc": [I],
+    "avl_set_tc_conv_tma": [I],
+    "avl_tc_conv_tma_count": [],
     "avl_set_tc_splitk": [I],
     "avl_set_tc_splitk_cluster": [I],
     "avl_set_tc_stages": [I],

@@ -82,8 +82,11 @@ class SyntheticVectorEnv:
         if self.host_buffers and self.static_frames:
             # the host has already staged this step's frames (``stage_frames``); only the device-side casts remain
             rgb, depth = self._frames_dev["rgb"], self._frames_dev["depth"]
-            self.visual_ready_event = None
-            return (rgb, depth.half()) if self.compact else (rgb.float(), depth)
+            rgb, depth = (rgb, depth.half()) if self.compact else (rgb.float(), depth)
+            ev = torch.cuda.Event()   # the frames are complete HERE: the encoders need not wait for the audio rendering
+            ev.record(main)
+            self.visual_ready_event = ev
+            return rgb, depth
         side = self._visual_stream
         if side is None:
             side = self._visual_stream = torch.cuda.Stream()

@@ -478,3 +478,46 @@ def test_self_attention_tensor_cores_is_fp32_accurate(lens):
               dq2.data_ptr(), _lib.stream())
     torch.cuda.synchronize()
     assert torch.equal(dq2.cpu().double(), res[1][2])
+
+
+@pytest.mark.parametrize("shape", [
+    # N, H, W, C, Cout, K, stride, pad   (>= 2 x 148 output tiles: the TMA im2col path is taken)
+    (600, 8, 8, 128, 128, 3, 1, 1),     # custom_resnet18 layer4 at update batch
+    (601, 16, 16, 64, 128, 3, 2, 1),    # stage-4 entry, stride 2, ragged last tile
+    (600, 16, 16, 64, 128, 1, 2, 0),    # 1x1 stride-2 shortcut
+    (640, 32, 32, 32, 64, 3, 2, 1),     # stage-3 entry
+    (2400, 17, 7, 64, 64, 3, 1, 1),     # belief resnet18 layer1 on the 17x7 map (rows wrap inside a tile)
+    (1100, 9, 4, 48, 80, 3, 1, 1),      # channels not a multiple of the 32-channel box, Cout not a multiple of 16
+    (1200, 9, 9, 32, 32, 5, 1, 2),      # 5x5 taps
+    (1000, 12, 10, 64, 256, 3, 2, 0),   # no padding, Cout = 2 N tiles
+    (64, 8, 8, 128, 128, 3, 1, 1),      # rollout batch: split-K inside a cluster, operands by TMA
+    (64, 3, 1, 512, 512, 3, 1, 1),      # belief resnet18 layer4 at rollout batch (16-way split)
+    (64, 17, 7, 64, 128, 3, 2, 1),      # belief layer2 entry at rollout batch
+    (7, 8, 8, 132, 20, 3, 1, 1),        # channel tail of 4 in the last box
+])
+def test_tma_im2col_conv_matches_the_cp_async_kernel_and_torch(shape):
+    """Rows C / E / M: implicit-GEMM convolution fed by TMA in im2col mode (gemm_tma.cu) against the cp.async gather kernel
+    (same TF32 MMAs, same k order: equal up to the accumulation order of the tensor core) and against torch."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    N, H, W, C, Co, k, s, p = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    w = (torch.randn(Co, C, k, k, generator=g) / (C * k * k) ** 0.5).cuda()
+    b, sc = torch.randn(Co, generator=g).cuda(), (torch.rand(Co, generator=g) + 0.5).cuda()
+    OH, OW = K.conv_out(H, k, s, p), K.conv_out(W, k, s, p)
+    res = torch.randn(N, OH, OW, Co, generator=g).cuda()
+    outs = {}
+    for tma in (0, 1):
+        old = _lib.lib().avl_set_tc_conv_tma(tma)
+        try:
+            n0 = int(_lib.lib().avl_tc_conv_tma_count())
+            outs[tma] = K.conv2d(x, w, b, s, p, relu=True, scale=sc, residual=res)
+            torch.cuda.synchronize()
+            assert int(_lib.lib().avl_tc_conv_tma_count()) - n0 == tma   # the path under test is the one that ran
+        finally:
+            _lib.lib().avl_set_tc_conv_tma(old)
+    tref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, None, s, p) * sc.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+                  + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    assert rel(outs[1], tref) < TOL_TC
+    assert rel(outs[1], outs[0]) < 1e-5

@@ -35,7 +35,9 @@ def main():
         x = torch.randn(B, H, W, C, device="cuda")
         w = torch.randn(Co, C, k, k, device="cuda") / (C * k * k) ** 0.5
         row = [f"B={B} {name:30s}"]
-        for label, stages, splitk, cluster in (("default", 0, 1, 1), ("ring4", 4, 1, 1), ("atomic", 0, 1, 0), ("nosplit", 0, 0, 1)):
+        for label, stages, splitk, cluster, tma in (("tma", 0, 1, 1, 1), ("tma ring4", 4, 1, 1, 1), ("cp.async", 0, 1, 1, 0),
+                                                    ("cp.async ring4", 4, 1, 1, 0)):
+            lib.avl_set_tc_conv_tma(tma)
             lib.avl_set_tc_stages(stages)
             lib.avl_set_tc_splitk(splitk)
             lib.avl_set_tc_splitk_cluster(cluster)
@@ -56,6 +58,7 @@ def main():
             torch.cuda.synchronize()
             row.append(f"{label} {e0.elapsed_time(e1) / 40 * 1e3:6.1f} us")
         print("  ".join(row), flush=True)
+    lib.avl_set_tc_conv_tma(1)
     lib.avl_set_tc_stages(0)
     lib.avl_set_tc_splitk(1)
     lib.avl_set_tc_splitk_cluster(1)
