@@ -485,7 +485,7 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s, bool want_tma = false
   p.bn = pick_bn(p.N);
   const int sms = avl_num_sms();
   const int mtiles = avl_div_up(p.M, TC_BM);
-  want_tma = want_tma && conv && g_tc_swz && p.g.C >= 32 && p.g.KH == p.g.KW;
+  want_tma = want_tma && conv && g_tc_swz && p.g.C >= 16 && p.g.KH == p.g.KW;
   p.cblocks = avl_div_up(p.g.C, TC_BK);
   p.kt_total = p.g.KH * p.g.KW * p.cblocks;
   const int KT = want_tma ? p.kt_total : avl_div_up(p.K, TC_BK);

@@ -260,7 +260,7 @@ long long g_tma_conv_launches = 0;
 
 }  // namespace
 
-// 1 (default): convolutions with >= 32 input channels and enough output tiles to fill the GPU are fed by TMA in im2col
+// 1 (default): convolutions with >= 16 input channels and enough output tiles to fill the GPU are fed by TMA in im2col
 // mode (no per-16-byte gather instructions); 0: the cp.async im2col kernel everywhere.  Returns the old value.
 AVL_API int avl_set_tc_conv_tma(int on) {
   avl_bump_config_epoch();
@@ -274,7 +274,7 @@ AVL_API int avl_set_tc_conv_tma(int on) {
 // the shape is outside the maps' limits.
 extern "C" bool avl_conv_tma_maps(CUtensorMap* ta, CUtensorMap* tb, const float* x, int N, int H, int W, int C,
                                   const float* w_packed, int Cout, int KH, int KW, int stride, int pad, int bn) {
-  if (!g_tma_conv_on || KH != KW || C < 32 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
+  if (!g_tma_conv_on || KH != KW || C < 16 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
       ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15) || H + 2 * pad - (KH - 1) < 1 || W + 2 * pad - (KW - 1) < 1)
     return false;
   return make_im2col_map(ta, x, N, H, W, C, KH, KW, stride, pad) && make_map(tb, w_packed, Cout, (long long)KH * KW * C,
@@ -291,7 +291,7 @@ int avl_tc_conv_tma_try(const float* x, int N, int H, int W, int C, const float*
                         int stride, int pad, const float* scale, const float* bias, const float* residual, long long ldr,
                         int relu, float* y, long long ldy, cudaStream_t stream) {
   if (!g_tma_conv_on) return AVL_ERR_UNSUPPORTED;
-  if (KH != KW || C < 32 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
+  if (KH != KW || C < 16 || (C & 3) || stride < 1 || stride > 8 || pad > 127 || KW - 1 - pad > 127 ||
       ((uintptr_t)x & 15) || ((uintptr_t)w_packed & 15))
     return AVL_ERR_UNSUPPORTED;
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;

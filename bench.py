@@ -184,31 +184,72 @@ def roofline_halo_conv(dev, B, flush, hbm, how):
 
 
 def roofline_im2col_conv(dev, B, flush, hbm, how, tf=None):
-    """custom_resnet18 layer4 conv3x3 128->128 @8x8 at the update-minibatch batch through the generic tensor-core
-    convolution (tc_gemm_kernel<CONV>, kind::tf32): 2*1152*128 / (2*128*4) = 288 FLOP/B, above the TF32 ridge
-    (~110 FLOP/B) => the TENSOR roofline is the binding one.  Peak: MEASURED_PEAKS.json carries the dense bf16 cuBLAS
-    throughput only; TF32 runs at half the bf16 rate on this tensor core (B200_PROFILING.md: 2.25 vs 1.1 PFLOP/s
-    nominal), so peak = bf16_tflops_sustained / 2."""
+    """custom_resnet18 layer4 conv3x3 128->128 @8x8 at the update-minibatch batch through the TMA-fed implicit-GEMM
+    convolution (tc_gemm_tma_kernel<CONV>: cp.async.bulk.tensor im2col mode, tcgen05 kind::tf32): 2*1152*128 / (2*128*4) =
+    288 FLOP/B, above the TF32 ridge (~110 FLOP/B) => the TENSOR roofline is the binding one.  Peak: MEASURED_PEAKS.json
+    carries the dense bf16 cuBLAS throughput only; TF32 runs at half the bf16 rate on this tensor core
+    (B200_PROFILING.md: 2.25 vs 1.1 PFLOP/s nominal), so peak = bf16_tflops_sustained / 2."""
     import torch
     from avlen_b200 import nn as K
     x = torch.randn(B, 8, 8, 128, device=dev)
     w = torch.randn(128, 128, 3, 3, device=dev) / 34
+    n0 = int(K._lib.lib().avl_tc_conv_tma_count())
 
     def run():
         K._conv2d_raw(x, w, None, 1, 1)
     ms = _time_kernel(run, flush)
+    took_tma = int(K._lib.lib().avl_tc_conv_tma_count()) > n0
     nbytes = 2.0 * B * 8 * 8 * 128 * 4 + 128 * 1152 * 4
     flops = 2.0 * B * 64 * 128 * 1152
     tfl = flops / (ms * 1e-3) / 1e12
     peak = (tf or 1400.0) / 2.0
-    return {"kernel": "tc_gemm_kernel<CONV> (tcgen05 kind::tf32, im2col gather) on custom_resnet18 layer4 conv3x3 "
-                      "128->128 @8x8, batch %d" % B, "match": "tc_gemm_kernel<true", "bound": "tensor",
+    name = ("tc_gemm_tma_kernel<CONV> (TMA im2col-mode loads, tcgen05 kind::tf32)" if took_tma else
+            "tc_gemm_kernel<CONV> (cp.async im2col gather, tcgen05 kind::tf32)")
+    return {"kernel": name + " on custom_resnet18 layer4 conv3x3 128->128 @8x8, batch %d" % B,
+            "match": ("tc_gemm_tma_kernel<true",) if took_tma else ("tc_gemm_kernel<true",), "bound": "tensor",
             "achieved": round(tfl, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(tfl / peak, 5),
             "traffic": None, "peak_source": how + " bf16_tflops_sustained / 2 (TF32 = half the bf16 rate)",
             "launch_ms": round(ms, 4), "algorithmic_bytes": int(nbytes), "algorithmic_flops": int(flops),
-            "hbm_view": {"achieved_GBps": round(nbytes / (ms * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / hbm, 5)},
-            "note": "at rollout batch (64) the same kernel is a 5-32-CTA latency-bound launch (~25 us); most of its "
-                    "share_of_step comes from those launches, for which no roofline applies"}
+            "hbm_view": {"achieved_GBps": round(nbytes / (ms * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / hbm, 5)}}
+
+
+def roofline_splitk_conv(dev, envs, hbm, how, tf=None):
+    """The same convolution at ROLLOUT batch (64 samples: 32 output tiles): tc_conv_tma_splitk_kernel — k-slices of a tile as
+    a thread-block cluster, operands by TMA, partial tiles reduced over DSMEM.  75 MFLOP and 4.7 MB per launch: a
+    latency-bound launch (fixed cost: TMEM allocation, barrier set-up, two cluster barriers), reported against the same
+    tensor roofline for completeness.  Timed as 40 dependent launches replayed from a CUDA graph (no L2 flush: in a
+    rollout step the weights stay resident)."""
+    import torch
+    from avlen_b200 import nn as K
+    x = torch.randn(envs, 8, 8, 128, device=dev)
+    w = torch.randn(128, 128, 3, 3, device=dev) / 34
+    out = torch.empty(envs, 8, 8, 128, device=dev)
+    for _ in range(3):
+        K._conv2d_raw(x, w, None, 1, 1, out=out.view(-1, 128))
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(40):
+            K._conv2d_raw(x, w, None, 1, 1, out=out.view(-1, 128))
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 40
+    flops = 2.0 * envs * 64 * 128 * 1152
+    nbytes = 2.0 * envs * 64 * 128 * 4 + 128 * 1152 * 4
+    tfl = flops / (ms * 1e-3) / 1e12
+    peak = (tf or 1400.0) / 2.0
+    return {"kernel": "tc_conv_tma_splitk_kernel (TMA im2col-mode loads, tcgen05 kind::tf32, split-K inside a cluster) on "
+                      "custom_resnet18 layer4 conv3x3 128->128 @8x8, batch %d (rollout)" % envs,
+            "match": ("tc_conv_tma_splitk_kernel", "tc_gemm_kernel<true"), "bound": "tensor", "achieved": round(tfl, 2),
+            "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(tfl / peak, 5), "traffic": None,
+            "peak_source": how + " bf16_tflops_sustained / 2 (TF32 = half the bf16 rate)", "launch_ms": round(ms, 4),
+            "algorithmic_bytes": int(nbytes), "algorithmic_flops": int(flops),
+            "note": "latency-bound: 32 output tiles x 8 k-slices of 75 MFLOP in total; no roofline is binding at this size"}
 
 
 def kernel_shares(tr, cfg, rollout_steps):
@@ -339,7 +380,8 @@ def run_savi(args):
     hbm, tf, how = _peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     B = min(args.envs * args.rollout_steps // 2, 4800)
-    cands = [roofline_halo_conv(dev, B, flush, hbm, how), roofline_im2col_conv(dev, B, flush, hbm, how, tf)]
+    cands = [roofline_halo_conv(dev, B, flush, hbm, how), roofline_im2col_conv(dev, B, flush, hbm, how, tf),
+             roofline_splitk_conv(dev, args.envs, hbm, how, tf)]
     shares = {}
     if tr_frozen is not None and not args.no_shares:
         try:
@@ -348,7 +390,9 @@ def run_savi(args):
             shares = {"error": str(e)[:200]}
     top = [(n[:110], round(v, 4)) for n, v in list(shares.items())[:8] if isinstance(v, float)]
     for c in cands:
-        c["share_of_step"] = round(sum(v for n, v in shares.items() if isinstance(v, float) and c["match"] in n), 4) \
+        m = c["match"] if isinstance(c["match"], (tuple, list)) else (c["match"],)
+        c["match"] = list(m)
+        c["share_of_step"] = round(sum(v for n, v in shares.items() if isinstance(v, float) and any(k in n for k in m)), 4) \
             if shares else None
     cands.sort(key=lambda c: -(c["share_of_step"] or 0))
     roofline = dict(cands[0])

@@ -494,6 +494,8 @@ def test_self_attention_tensor_cores_is_fp32_accurate(lens):
     (64, 3, 1, 512, 512, 3, 1, 1),      # belief resnet18 layer4 at rollout batch (16-way split)
     (64, 17, 7, 64, 128, 3, 2, 1),      # belief layer2 entry at rollout batch
     (7, 8, 8, 132, 20, 3, 1, 1),        # channel tail of 4 in the last box
+    (600, 64, 64, 16, 32, 1, 2, 0),     # stage-2 shortcut: 16 channels = half a box (the rest is zero-filled)
+    (64, 64, 64, 16, 32, 1, 2, 0),
 ])
 def test_tma_im2col_conv_matches_the_cp_async_kernel_and_torch(shape):
     """Rows C / E / M: implicit-GEMM convolution fed by TMA in im2col mode (gemm_tma.cu) against the cp.async gather kernel

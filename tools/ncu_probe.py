@@ -36,6 +36,26 @@ def main():
         x = torch.randint(0, 256, (B, 128, 128, 3), dtype=torch.uint8, device="cuda")
         for _ in range(4):
             K.resize_half(x, 1 / 255.0, 4)
+    elif what in ("tma_conv_l4", "tma_conv_l4_b64"):
+        b = 64 if what.endswith("b64") else B
+        x = torch.randn(b, 8, 8, 128, device="cuda")
+        w = torch.randn(128, 128, 3, 3, device="cuda") / 34
+        for _ in range(4):
+            K._conv2d_raw(x, w, None, 1, 1)
+    elif what in ("attn_tc_fwd", "attn_tc_bwd"):
+        from avlen_b200 import _lib
+        g = torch.Generator().manual_seed(0)
+        lens = torch.randint(40, 152, (B,), generator=g)
+        off = torch.zeros(B + 1, dtype=torch.int32)
+        off[1:] = torch.cumsum(lens, 0)
+        R, D = int(off[-1]), 256
+        qkv, dout = torch.randn(R, 3 * D, generator=g).cuda(), torch.randn(R, D, generator=g).cuda()
+        off = off.cuda()
+        out, lse, dqkv = torch.empty(R, D, device="cuda"), torch.empty(R, 8, device="cuda"), torch.empty(R, 3 * D, device="cuda")
+        for _ in range(4):
+            _lib.call("avl_attn_self_fwd", qkv.data_ptr(), off.data_ptr(), B, D, out.data_ptr(), lse.data_ptr(), _lib.stream())
+            _lib.call("avl_attn_self_bwd", qkv.data_ptr(), off.data_ptr(), B, D, out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
+                      dqkv.data_ptr(), _lib.stream())
     torch.cuda.synchronize()
     print("ok")
 

@@ -9,6 +9,7 @@ import torch
 from avlen_b200 import nn as K
 
 SHAPES = [  # name, H, W, C, Cout, k, stride, pad
+    ("layer2 1x1 s2 16->32 @64", 64, 64, 16, 32, 1, 2, 0),
     ("layer3 3x3 s2 32->64 @32", 32, 32, 32, 64, 3, 2, 1),
     ("layer3 1x1 s2 32->64 @32", 32, 32, 32, 64, 1, 2, 0),
     ("layer3 3x3 64->64 @16", 16, 16, 64, 64, 3, 1, 1),
