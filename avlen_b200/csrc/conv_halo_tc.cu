@@ -39,7 +39,21 @@
 #include "tc_common.cuh"
 
 #ifndef AVL_HOST_EMUL
+#include <cuda.h>
+#include <string.h>
 namespace {
+
+// TMA variant of the strip loader: the NHWC tensor as a rank-5 tiled map (chunk elements, chunk, W, H, N); one load per
+// 16-byte chunk plane brings the whole padded strip of that plane — box (16 bytes, 1, Wp, R + KH - 1, 1) starting at
+// (w, h) = (-pad, oh0 - pad) — and the unit zero-fills the halo columns and the rows outside the image.  The landed box
+// is exactly the plane layout the MMAs read (pixel (ir, ic) at (ir * Wp + ic) * 16 bytes).
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 
 // Round-to-nearest conversion that SATURATES to +-65504 instead of producing inf (fp16 has a 5-bit exponent; the
 // GroupNorm that consumes the tensor flags saturated values, gn_cluster.cu g_f16_overflow).
@@ -86,6 +100,7 @@ struct HaloArgs {
   uint32_t w_plane;    // bytes per weight chunk plane (Cout * 16)
   int n_wplanes;
   int n_mma;           // MMAs per 128-output tile
+  int tma;             // strips arrive by TMA (one thread, one load per chunk plane) instead of cp.async gathers
   int ncols;           // TMEM columns per accumulator buffer (Cout)
   int tmem_cols;       // allocation (power of two >= 32)
   uint32_t off_a[HL_PARAM_MMA], off_b[HL_PARAM_MMA];  // per-MMA descriptor increments (16-byte units), n_mma <= 96
@@ -121,7 +136,8 @@ __device__ __forceinline__ void umma_halo_elect(uint32_t tmem_d, uint64_t a_desc
 }
 
 template <bool IN16, bool OUT16>
-__global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_constant__ HaloArgs p) {
+__global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_constant__ HaloArgs p,
+                                                                  const __grid_constant__ CUtensorMap tmX) {
   AVL_DYN_SMEM(smem);
   __shared__ __align__(8) unsigned long long bars[8];  // in_full[2], in_empty[2], acc_full[2], acc_empty[2]
   __shared__ uint32_t tmem_base_smem;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(IN_FULL(b), HL_LOAD_THREADS);
+      mbar_init(IN_FULL(b), p.tma ? 1 : HL_LOAD_THREADS);
       mbar_init(IN_EMPTY(b), 1);
       mbar_init(ACC_FULL(b), 1);
       mbar_init(ACC_EMPTY(b), 32 * HL_EPI_WARPS);
@@ -219,6 +235,21 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
     const int items = rows_in * per_row;
     const int nc_shift = (p.nc & (p.nc - 1)) == 0 ? __ffs(p.nc) - 1 : -1;
     int it_strip = 0;
+    if (p.tma) {
+      if (lt == 0) {
+        tma_prefetch_desc(&tmX);
+        const uint32_t plane_bytes = (uint32_t)(rows_in * p.Wp) * 16u;
+        for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
+          const int b = it_strip & 1;
+          mbar_wait(IN_EMPTY(b), (uint32_t)(((it_strip >> 1) & 1) ^ 1));
+          const int n = strip / p.strips_per_img;
+          const int oh0 = (strip - n * p.strips_per_img) * p.R;
+          const uint32_t dst0 = in_base0 + (uint32_t)b * in_bytes;
+          mbar_arrive_expect_tx(IN_FULL(b), plane_bytes * (uint32_t)p.nc);
+          for (int c = 0; c < p.nc; ++c) tma_load_5d(dst0 + (uint32_t)c * p.in_plane, &tmX, 0, c, -pad, oh0 - pad, n, IN_FULL(b));
+        }
+      }
+    } else
     for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x, ++it_strip) {
       const int b = it_strip & 1;
       mbar_wait(IN_EMPTY(b), (uint32_t)(((it_strip >> 1) & 1) ^ 1));  // first use of each buffer passes
@@ -361,7 +392,40 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
   }
 }
 
+typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn5 halo_encode_tiled() {
+  static EncodeTiledFn5 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn5>(ptr);
+  }
+  return fn;
+}
+// x: (N, H, W, C) with `cpc` channels per 16-byte chunk -> dims (cpc, C / cpc, W, H, N), box (cpc, 1, Wp, rows_in, 1)
+static bool halo_make_map(CUtensorMap* map, const void* x, bool in16, int N, int H, int W, int C, int Wp, int rows_in) {
+  EncodeTiledFn5 enc = halo_encode_tiled();
+  if (!enc || Wp > 256 || rows_in > 256) return false;
+  const int cpc = in16 ? 8 : 4;
+  const cuuint64_t esz = in16 ? 2 : 4;
+  cuuint64_t dims[5] = {(cuuint64_t)cpc, (cuuint64_t)(C / cpc), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[4] = {16, (cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
+  cuuint32_t box[5] = {(cuuint32_t)cpc, 1, (cuuint32_t)Wp, (cuuint32_t)rows_in, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, in16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(x), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static int g_halo_on = 1;
+static int g_halo_tma = 1;
 static int g_halo_group = 0;  // pixel groups (G > 1): measured SLOWER on B200 (see header), kept as an opt-in
 static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
 static int g_halo_stride2 = 1;  // stride-2 same-padded convolutions: stride-1 strip convolution, even positions stored
@@ -385,6 +449,15 @@ AVL_API int avl_set_tc_conv_halo(int on, int rows) {
   int old = g_halo_on;
   g_halo_on = on ? 1 : 0;
   if (rows >= 0) g_halo_rows = rows;  // 0: automatic
+  return old;
+}
+
+// 1 (default): the halo-strip kernel's input strips arrive by TMA (rank-5 tiled map, zero-filled halo); 0: cp.async
+// gathers by four loader warps.  Returns old.
+AVL_API int avl_set_tc_conv_halo_tma(int on) {
+  avl_bump_config_epoch();
+  int old = g_halo_tma;
+  g_halo_tma = on ? 1 : 0;
   return old;
 }
 
@@ -468,6 +541,7 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   p.kwp = c4 ? ((KW + 1) & ~1) : KW;
   p.ppu = (uint32_t)plane_units(p.tiles);
   p.in_plane = p.ppu * (uint32_t)G * 16;
+  if (G == 1) p.in_plane = (p.in_plane + 127u) & ~127u;  // TMA destinations are 128-byte aligned
   p.w_plane = (uint32_t)(G * Cout) * 16;
   p.n_wplanes = c4 ? KH * p.kwp : KH * p.kwe * p.nc;
   p.n_mma = c4 ? KH * (p.kwp / 2) : KH * p.kwe * (p.nc / 2);
@@ -509,10 +583,16 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   while (per_sm > 1 && per_sm * cols > 512) --per_sm;
   long long grid = (long long)avl_num_sms() * per_sm;
   if (grid > total) grid = total;
-  if (in16 && out16) tc_conv_halo_kernel<true, true><<<(int)grid, HL_THREADS, smem, stream>>>(p);
-  else if (in16) tc_conv_halo_kernel<true, false><<<(int)grid, HL_THREADS, smem, stream>>>(p);
-  else if (out16) tc_conv_halo_kernel<false, true><<<(int)grid, HL_THREADS, smem, stream>>>(p);
-  else tc_conv_halo_kernel<false, false><<<(int)grid, HL_THREADS, smem, stream>>>(p);
+  CUtensorMap tmx;
+  memset(&tmx, 0, sizeof(tmx));
+  p.tma = 0;
+  if (g_halo_tma && G == 1 && ((p.n_wplanes * p.w_plane) & 127u) == 0 &&
+      halo_make_map(&tmx, x, in16 != 0, N, H, W, C, p.Wp, p.R + KH - 1))
+    p.tma = 1;
+  if (in16 && out16) tc_conv_halo_kernel<true, true><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
+  else if (in16) tc_conv_halo_kernel<true, false><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
+  else if (out16) tc_conv_halo_kernel<false, true><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
+  else tc_conv_halo_kernel<false, false><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }
