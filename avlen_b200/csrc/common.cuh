@@ -73,3 +73,23 @@ __device__ __forceinline__ float block_sum(float v, float* red /* >=33 floats sm
 }
 
 int avl_num_sms();
+
+// ---- programmatic dependent launch (PDL): a kernel that calls avl_pdl_wait() before its first access to global memory
+// written by earlier kernels may be LAUNCHED while its predecessor in the stream still runs (launch attribute added by
+// avl_pdl_attr): its prologue (barrier / TMEM set-up, weight staging, the launch latency itself) overlaps the predecessor's
+// tail.  Every such kernel triggers its own dependents only AFTER its wait, so completion is transitive along the chain.
+#ifndef AVL_HOST_EMUL
+__device__ __forceinline__ void avl_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void avl_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern "C" int avl_pdl_enabled();
+static inline void avl_pdl_attr(cudaLaunchAttribute* at, unsigned* n) {
+  if (avl_pdl_enabled()) {
+    at[*n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[*n].val.programmaticStreamSerializationAllowed = 1;
+    ++*n;
+  }
+}
+#else
+static inline void avl_pdl_wait() {}
+static inline void avl_pdl_trigger() {}
+#endif

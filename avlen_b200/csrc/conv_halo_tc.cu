@@ -226,6 +226,10 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above touched only shared memory, TMEM and the (static) weights: under programmatic dependent launch it
+  // overlaps the previous kernel; activations / residual / output are touched below this line only
+  avl_pdl_wait();
+  avl_pdl_trigger();
 
   if (warp >= HL_MMA_WARP + 1) {
     // ================================================================================ loaders
@@ -589,10 +593,19 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   if (g_halo_tma && G == 1 && ((p.n_wplanes * p.w_plane) & 127u) == 0 &&
       halo_make_map(&tmx, x, in16 != 0, N, H, W, C, p.Wp, p.R + KH - 1))
     p.tma = 1;
-  if (in16 && out16) tc_conv_halo_kernel<true, true><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
-  else if (in16) tc_conv_halo_kernel<true, false><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
-  else if (out16) tc_conv_halo_kernel<false, true><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
-  else tc_conv_halo_kernel<false, false><<<(int)grid, HL_THREADS, smem, stream>>>(p, tmx);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(HL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  unsigned nat = 0;
+  avl_pdl_attr(at, &nat);
+  cfg.attrs = at;
+  cfg.numAttrs = nat;
+  auto kern = in16 ? (out16 ? tc_conv_halo_kernel<true, true> : tc_conv_halo_kernel<true, false>)
+                   : (out16 ? tc_conv_halo_kernel<false, true> : tc_conv_halo_kernel<false, false>);
+  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p, tmx));
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -61,3 +61,14 @@ AVL_API int avl_set_tensor_cores(int level) {
   return old;
 }
 AVL_API int avl_get_tensor_cores(void) { return g_use_tc; }
+
+// Programmatic dependent launch between the kernels of the encoder chains (convolutions, GroupNorm): 1 (default) on, 0 off.
+// Returns the old value.
+static int g_pdl = 1;
+extern "C" int avl_pdl_enabled() { return g_pdl; }
+AVL_API int avl_set_pdl(int on) {
+  int old = g_pdl;
+  g_pdl = on ? 1 : 0;
+  avl_bump_config_epoch();
+  return old;
+}

@@ -143,6 +143,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcArgs& p, const CUtensorMap*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  avl_pdl_wait();     // barriers / TMEM / descriptor prefetch above overlap the previous kernel under programmatic launch
+  avl_pdl_trigger();
 
   // ---- per-thread load coordinates: chunk column c = tid & 7 is fixed, rows (tid >> 3) + 16 j
   const int c = tid & 7;
@@ -561,13 +563,15 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s, bool want_tma = false
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = (unsigned)(p.cluster_red ? p.splits : 1);
+    unsigned nat = 1;
+    avl_pdl_attr(at, &nat);
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = nat;
     AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_conv_tma_splitk_kernel, ta, tb, p));
     AVL_LAUNCH_CHECK();
     avl_tc_conv_tma_count_add();

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  avl_pdl_wait();
+  avl_pdl_trigger();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -329,7 +331,17 @@ int avl_tc_conv_tma_try(const float* x, int N, int H, int W, int C, const float*
     attr_set = true;
   }
   dim3 grid(mtiles, avl_div_up(Cout, p.bn));
-  tc_gemm_tma_kernel<true><<<grid, TM_THREADS, smem, stream>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  unsigned nat = 0;
+  avl_pdl_attr(at, &nat);
+  cfg.attrs = at;
+  cfg.numAttrs = nat;
+  AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_tma_kernel<true>, ta, tb, p));
   AVL_LAUNCH_CHECK();
   ++g_tma_conv_launches;
   return AVL_OK;

@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_kernel(const void* __r
   // size (fewer barriers per sample) and twice the bytes in flight per CTA
   float4* tile = reinterpret_cast<float4*>(gsm);
   uint2* tile16 = reinterpret_cast<uint2*>(gsm);
+  avl_pdl_wait();     // (programmatic dependent launch: this grid may have been launched before its producer finished)
+  avl_pdl_trigger();  // the next convolution's prologue may start now
 
   // ---- pass over HBM: stage + per-thread sums (a thread always sees the same 4 channels: nq divides the stride)
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
@@ -379,13 +381,15 @@ int avl_groupnorm_cluster_typed(const void* x, int in16, const float* gamma, con
   cfg.blockDim = dim3(GNC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)cl;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  unsigned nat = 1;
+  avl_pdl_attr(at, &nat);
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = nat;
   auto kern = in16 ? (out16 ? gn_cluster_kernel<true, true> : gn_cluster_kernel<true, false>)
                    : (out16 ? gn_cluster_kernel<false, true> : gn_cluster_kernel<false, false>);
   AVL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, x, gamma, beta, residual, y, HW, C, groups, eps, relu, cl, pix_per_cta));

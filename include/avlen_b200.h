@@ -336,6 +336,7 @@ int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, def
 int avl_set_tc_conv_tma(int on);  /* 1 (default): convolutions with >= 16 input channels and enough output tiles are fed by TMA in im2col mode (cuTensorMapEncodeIm2col, cp.async.bulk.tensor...im2col); 0: the cp.async gather everywhere; returns old */
 long long avl_tc_conv_tma_count(void); /* convolutions launched on the TMA im2col kernel so far (diagnostic) */
 int avl_set_tc_conv_halo_tma(int on); /* 1 (default): the halo-strip kernel's input strips arrive by TMA (rank-5 tiled map, halo zero-filled by the unit); 0: cp.async gathers; returns old */
+int avl_set_pdl(int on);          /* 1 (default): the convolution / GroupNorm kernels of the encoder chains are launched with programmatic stream serialization (their prologues overlap the previous kernel; every kernel waits with griddepcontrol.wait before touching activations); 0: plain launches; returns old */
 int avl_set_attn_tc(int on);      /* 1 (default): varlen self-attention (row F, smt_state_encoder.py:160-166) as 3xTF32 warp MMAs whenever the tensor-core level is >= 1; 0: register-tiled fp32 kernels; returns old */
 
 /* ----------------------------------------------------------------------------- row H: GRU state encoder
