@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(AT_WARPS * 32, 3)
 attn_self_fwd_tc_kernel(const float* __restrict__ qkv, const int* __restrict__ off, float* out, float* lse, int D,
                         float scale, int vcap) {
   AVL_DYN_SMEM(smem_raw);
+  avl_pdl_wait();
+  avl_pdl_trigger();
   const int b = blockIdx.x, h = blockIdx.y;
   const int r0 = off[b], V = min(off[b + 1] - r0, vcap);
   if (V <= 0) return;
@@ -350,7 +352,8 @@ extern "C" int avl_attn_self_fwd_tc_try(const float* qkv, const int* off, int B,
     return AVL_ERR_UNSUPPORTED;
   int rc = ensure_attrs();
   if (rc) return rc;
-  attn_self_fwd_tc_kernel<<<dim3(B, D / AT_HD), AT_WARPS * 32, fwd_smem(vcap), stream>>>(qkv, off, out, lse, D, scale, vcap);
+  AVL_LAUNCH_PDL(attn_self_fwd_tc_kernel, dim3(B, D / AT_HD), AT_WARPS * 32, fwd_smem(vcap), stream, qkv, off, out, lse, D, scale,
+                 vcap);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -89,7 +89,24 @@ static inline void avl_pdl_attr(cudaLaunchAttribute* at, unsigned* n) {
     ++*n;
   }
 }
+// <<<>>>-style launch with the programmatic-serialization attribute (for kernels that call avl_pdl_wait())
+template <typename... KArgs, typename... Args>
+static inline void avl_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  unsigned n = 0;
+  avl_pdl_attr(at, &n);
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError at the caller
+}
+#define AVL_LAUNCH_PDL(kern, grid, block, smem, stream, ...) avl_launch_pdl(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
 #else
 static inline void avl_pdl_wait() {}
 static inline void avl_pdl_trigger() {}
+#define AVL_LAUNCH_PDL(kern, grid, block, smem, stream, ...) AVL_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__)
 #endif

@@ -53,9 +53,6 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int X3_STAGES = p.stages;
-  int M = p.M;
-  if (p.m_dev) M = min(M, *p.m_dev);
-  const int total_tiles = ((M + X3_BM - 1) / X3_BM) * p.n_tiles;
   const int bn = p.bn;
   const int KT = (p.K + X3_BK - 1) / X3_BK;
   const uint32_t a_tile = X3_BM * 128u, b_tile = (uint32_t)bn * 128u;
@@ -92,6 +89,13 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // barriers, TMEM and descriptor prefetch above overlap the previous kernel under programmatic dependent launch; the
+  // device-side row count and every operand are read below this line only
+  avl_pdl_wait();
+  avl_pdl_trigger();
+  int M = p.M;
+  if (p.m_dev) M = min(M, *p.m_dev);
+  const int total_tiles = ((M + X3_BM - 1) / X3_BM) * p.n_tiles;
 
   if (warp == 9) {
     // ================================================================================ TMA producer
@@ -229,6 +233,8 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
 // are written as [N][K]
 __global__ void split_tf32_kernel(const float* __restrict__ src, long long ld, int N, int K, int transpose, float* hi,
                                   float* lo) {
+  avl_pdl_wait();     // (the scratch this kernel overwrites may still be read by the previous GEMM)
+  avl_pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const int n = i / K, k = i - n * K;
@@ -519,7 +525,7 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   }
   float* bhi = scratch;
   float* blo = scratch + (size_t)N * K;
-  split_tf32_kernel<<<avl_div_up((long long)N * K, 256), 256, 0, s>>>(B, ldb, N, K, b_transposed, bhi, blo);
+  AVL_LAUNCH_PDL(split_tf32_kernel, avl_div_up((long long)N * K, 256), 256, 0, s, B, ldb, N, K, b_transposed, bhi, blo);
   AVL_LAUNCH_CHECK();
   X3Args p = {};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
@@ -553,7 +559,7 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   }
   long long tiles = (long long)avl_div_up(M, X3_BM) * p.n_tiles;
   const int grid = (int)(tiles < avl_num_sms() ? tiles : avl_num_sms());  // persistent: one CTA per SM
-  tc_gemm_3x_kernel<<<grid, X3_THREADS, smem, s>>>(ta, tbh, tbl, p);
+  AVL_LAUNCH_PDL(tc_gemm_3x_kernel, grid, X3_THREADS, smem, s, ta, tbh, tbl, p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -171,6 +171,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* y,
                                      float* mean_out, float* rstd_out, const int* rows_dev, int rows_max, int cols,
                                      float eps) {
+  avl_pdl_wait();
+  avl_pdl_trigger();
   const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -287,6 +289,8 @@ skinny_gemm_kernel(const float* __restrict__ A, long long lda, const float* __re
                    const int* m_dev, int vec) {
   __shared__ float xs[SK_BK][SK_BM + 1];
   __shared__ float ws[SK_BN][SK_BK];
+  avl_pdl_wait();
+  avl_pdl_trigger();
   if (m_dev) M = min(M, *m_dev);
   const int m0 = blockIdx.x * SK_BM, n0 = blockIdx.y * SK_BN;
   if (m0 >= M) return;
@@ -702,6 +706,8 @@ __global__ void __launch_bounds__(256) attn_cross_fwd256_kernel(const float* __r
   AVL_DYN_SMEM(smem_raw);
   float* Ps = reinterpret_cast<float*>(smem_raw);  // [8][ATT_MAXV]
   constexpr int D = 256, H = 8;
+  avl_pdl_wait();
+  avl_pdl_trigger();
   const int b = blockIdx.x;
   const int r0 = off[b], V = off[b + 1] - r0;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;

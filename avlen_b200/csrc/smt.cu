@@ -184,7 +184,7 @@ static void launch_gemm(Launcher& L, GemmOperand A, bool a_kc, GemmOperand B, bo
   if (a_kc && b_kc && splits <= 1 && M <= 4 * SK_BM && !ep.scale && !ep.residual && !ep.k_dev) {
     // few rows (rollout batch): many small CTAs instead of 1-2 tiles of the 128 x 64 kernel
     const int vec = ((A.s_row & 3) == 0 && (K & 3) == 0 && ((uintptr_t)A.p & 15) == 0) ? 1 : 0;
-    AVL_LAUNCH(skinny_gemm_kernel, dim3(avl_div_up(M, SK_BM), avl_div_up(N, SK_BN)), SK_THREADS, 0, L.s, A.p, A.s_row, B.p,
+    AVL_LAUNCH_PDL(skinny_gemm_kernel, dim3(avl_div_up(M, SK_BM), avl_div_up(N, SK_BN)), SK_THREADS, 0, L.s, A.p, A.s_row, B.p,
                B.s_row, C, ldc, M, N, K, ep.bias, ep.relu, ep.accumulate, ep.m_dev, vec);
     L.check();
     return;
@@ -315,7 +315,7 @@ static void lin_bwd_w(Launcher& L, const float* dY, long long ldy, const float* 
 static void ln_fwd(Launcher& L, const float* x, const float* res, const float* g, const float* b, float* y,
                    float* stats, const int* rows_dev, int rows, int cols) {
   if (rows <= 0) return;
-  AVL_LAUNCH(layernorm_fwd_kernel, avl_div_up(rows, 8), 256, 0, L.s, x, res, g, b, y, stats, stats ? stats + rows : nullptr,
+  AVL_LAUNCH_PDL(layernorm_fwd_kernel, avl_div_up(rows, 8), 256, 0, L.s, x, res, g, b, y, stats, stats ? stats + rows : nullptr,
                                                             rows_dev, rows, cols, 1e-5f);
   L.check();
 }
@@ -460,7 +460,7 @@ static void tf_forward(Launcher& L, const float* const* P, const TfBufs& t, cons
   lin_fwd(L, t.T1, D, P[TP_DEC_CA_IN_W], P[TP_DEC_CA_IN_B], t.Q, D, B, D, D, 0, nullptr);
   lin_fwd(L, t.MEM, D, P[TP_DEC_CA_IN_W] + (size_t)D * D, P[TP_DEC_CA_IN_B] + D, t.KV, 2 * D, Rcap, 2 * D, D, 0, total);
   if (D == 256)
-    AVL_LAUNCH(attn_cross_fwd256_kernel, B, 256, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, scale);
+    AVL_LAUNCH_PDL(attn_cross_fwd256_kernel, B, 256, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, scale);
   else
     AVL_LAUNCH(attn_cross_fwd_kernel, B, H * 32, H * ATT_MAXV * sizeof(float), L.s, t.Q, t.KV, off, t.C, t.PROBS, D, scale);
   L.check();
