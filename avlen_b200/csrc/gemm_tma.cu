@@ -31,6 +31,9 @@ struct TmaArgs {
   // CONV: A is the im2col view of an NHWC tensor, loaded by TMA in im2col mode (one box = 128 output pixels x 32 channels
   // of one filter tap); k-tile kt = tap * cblocks + channel block
   int OH, OW, Cin, KW, conv_stride, pad, cblocks;
+  // pixel shuffle (stride-2 data gradients): the N = 4 * ps_c output columns of row (n, oh, ow) are the ps_c channels of the
+  // four pixels (2 oh + pa, 2 ow + pb), column block pa * 2 + pb; C then points at a (N, 2 OH, 2 OW, ps_c) tensor
+  int ps_c;
 };
 
 // cp.async.bulk.tensor im2col mode: {c, w, h, n} = channel offset and the input coordinates of the FIRST output pixel of
@@ -144,11 +147,21 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
   // ---- epilogue: thread = one output row (TMEM lane), 16 columns at a time
   const int m = m0 + warp * 32 + lane;
   const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  long long ps_pix = 0;  // CONV pixel shuffle: pixel (2 oh, 2 ow) of the doubled grid
+  if (CONV && p.ps_c) {
+    const int mm = m < M ? m : 0;
+    const int ow = mm % p.OW, t = mm / p.OW;
+    ps_pix = ((long long)(t / p.OH) * (2 * p.OH) + 2 * (t % p.OH)) * (2 * p.OW) + 2 * ow;
+  }
   for (int c0 = 0; c0 < bn; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(taddr + c0, v);
     if (m < M) {
       float* crow = p.C + (long long)m * p.ldc + n0 + c0;
+      if (CONV && p.ps_c) {  // (ps_c is a multiple of 16: a 16-column chunk never straddles two pixels)
+        const int q = (n0 + c0) / p.ps_c, c = (n0 + c0) - q * p.ps_c;
+        crow = p.C + (ps_pix + (long long)(q >> 1) * (2 * p.OW) + (q & 1)) * p.ldc + c;
+      }
       const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
       if (p.vec_store && n0 + c0 + 16 <= p.N) {  // 16-byte stores: a 4-byte store per lane rewrites every sector 8 times
 #pragma unroll
@@ -242,13 +255,15 @@ EncodeIm2colFn encode_im2col() {
 // NHWC fp32 activations as a rank-4 im2col map (C, W, H, N): the pixel bounding box holds the input coordinates of tap
 // (0, 0) of every output pixel — [-pad, size + pad - (K - 1)) per spatial dimension — traversed with the convolution's
 // stride; one load = 128 pixels x 32 channels, SWIZZLE_128B (= the K-major UMMA operand tile).
-bool make_im2col_map(CUtensorMap* map, const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad) {
+bool make_im2col_map(CUtensorMap* map, const float* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                     int pad_hi = -1) {
   EncodeIm2colFn enc = encode_im2col();
   if (!enc) return false;
+  if (pad_hi < 0) pad_hi = pad;  // (asymmetric padding: pad rows / columns before, pad_hi after)
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)W * C * sizeof(float), (cuuint64_t)H * W * C * sizeof(float)};
   int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (KW - 1), pad - (KH - 1)};
+  int upper[2] = {pad_hi - (KW - 1), pad_hi - (KH - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, lower, upper,
                    (cuuint32_t)TM_BK, (cuuint32_t)TM_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -281,6 +296,54 @@ extern "C" bool avl_conv_tma_maps(CUtensorMap* ta, CUtensorMap* tb, const float*
     return false;
   return make_im2col_map(ta, x, N, H, W, C, KH, KW, stride, pad) && make_map(tb, w_packed, Cout, (long long)KH * KW * C,
                                                                              (long long)KH * KW * C, bn);
+}
+
+// Data gradient of a 3x3, stride-2, pad-1 convolution WITHOUT the zero-upsampled intermediate: dx[2a + pa, 2b + pb] only
+// sees dy[a + u, b + v], u, v in {0, 1} (rows a / a + 1 through kernel rows 1 | 2, 0 depending on the parity), so it is ONE
+// 2x2-tap stride-1 convolution of dy (no padding before, one row / column after) with 4 * Cin output columns — a column
+// block per output parity — whose epilogue stores the four pixels of the doubled grid.  16 Cout Cin MACs per dy pixel
+// instead of 36 on the upsampled tensor, and the 4x larger intermediate is never written or read.
+// w2: [4 * Cin][4 * Cout] (row = (pa, pb, ci), column = (u, v, co)); dx: (N, 2 OH, 2 OW, Cin).
+AVL_API int avl_tc_conv2d_dgrad_s2(const float* dy, int N, int OH, int OW, int Cout, const float* w2, int Cin, float* dx,
+                                   void* stream) {
+  if (N < 0 || OH < 1 || OW < 1 || Cout < 1 || Cin < 1) return AVL_ERR_ARG;
+  if (N == 0) return AVL_OK;
+  if (!dy || !w2 || !dx) return AVL_ERR_ARG;
+  if (!g_tma_conv_on || Cout < 16 || (Cout & 3) || (Cin & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)w2 & 15) ||
+      ((uintptr_t)dx & 15))
+    return AVL_ERR_UNSUPPORTED;
+  const long long M = (long long)N * OH * OW;
+  if (M > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  const int Ng = 4 * Cin, K = 4 * Cout;
+  TmaArgs p = {};
+  p.C = dx; p.ldc = Cin; p.M = (int)M; p.N = Ng; p.relu = 0; p.m_dev = nullptr;
+  p.OH = OH; p.OW = OW; p.Cin = Cout; p.KW = 2; p.conv_stride = 1; p.pad = 0; p.ps_c = Cin;
+  p.bn = Ng < 128 ? Ng : 128;
+  const int mtiles = avl_div_up(M, TM_BM);
+  if ((long long)mtiles * avl_div_up(Ng, p.bn) < 2LL * avl_num_sms()) return AVL_ERR_UNSUPPORTED;
+  p.cblocks = avl_div_up(Cout, TM_BK);
+  p.K = 4 * p.cblocks;
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap ta, tb;
+  if (!make_im2col_map(&ta, dy, N, OH, OW, Cout, 2, 2, 1, 0, 1) || !make_map(&tb, w2, Ng, K, K, p.bn)) return AVL_ERR_UNSUPPORTED;
+  const size_t stage = (TM_BM + (size_t)p.bn) * 128;
+  p.stages = (int)((100 * 1024) / stage);
+  if (p.stages > TM_MAX_STAGES) p.stages = TM_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  p.vec_store = 1;
+  const size_t smem = (size_t)p.stages * stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(mtiles, avl_div_up(Ng, p.bn));
+  tc_gemm_tma_kernel<true><<<grid, TM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, p);
+  AVL_LAUNCH_CHECK();
+  ++g_tma_conv_launches;
+  return AVL_OK;
 }
 
 // Number of convolutions this process has launched on the TMA im2col kernel (tests assert that the path is taken).

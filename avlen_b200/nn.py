@@ -37,6 +37,7 @@ _lib.register({
     "avl_set_tc_conv_l1": [I],
     "avl_set_attn_tc": [I],
     "avl_set_tc_conv_tma": [I],
+    "avl_tc_conv2d_dgrad_s2": [P, I, I, I, I, P, I, P, P],
     "avl_set_pdl": [I],
     "avl_set_tc_conv_halo_tma": [I],
     "avl_tc_conv_tma_count": [],
@@ -189,12 +190,12 @@ def _packed_weight(w, c_pad=None, dgrad=False):
     wc = w.detach()
     if not wc.is_contiguous():
         wc = wc.contiguous()
-    if dgrad:
-        cp = Cout if c_pad is None else c_pad
-        pk = torch.empty((C, KH, KW, cp), device=w.device, dtype=torch.float32)
-    else:
-        cp = C if c_pad is None else c_pad
-        pk = torch.empty((Cout, KH, KW, cp), device=w.device, dtype=torch.float32)
+    cp = (Cout if dgrad else C) if c_pad is None else c_pad
+    shape = (C, KH, KW, cp) if dgrad else (Cout, KH, KW, cp)
+    # a stale entry is re-packed IN PLACE: the packed weight keeps its device address for the life of the parameter, so
+    # a rollout step captured into a CUDA graph (which also captures this re-pack when it follows an optimizer step)
+    # stays valid after the weights change — trainable encoders replay their step graphs like frozen ones
+    pk = hit[1] if (hit is not None and tuple(hit[1].shape) == shape) else torch.empty(shape, device=w.device, dtype=torch.float32)
     call("avl_pack_conv_weight", fptr(wc), Cout, C, KH, KW, cp, int(bool(dgrad)), fptr(pk), stream())
     cache[key] = (w._version, pk)
     return pk
@@ -297,6 +298,42 @@ def zero_upsample2(gy, H, W):
     return up
 
 
+_S2_ROW = ((1, None), (2, 0))  # kernel row read by output parity pa through dy row a + u: _S2_ROW[pa][u]
+
+
+def _dgrad_s2_weight(w):
+    """(Cout, Cin, 3, 3) -> [4 * Cin][4 * Cout] weight of the 2x2-tap data-gradient convolution (row (pa, pb, ci), column
+    (u, v, co)); TF32-rounded, cached on the parameter per version like ``_packed_weight``."""
+    owner = w._base if w._base is not None else w
+    cache = getattr(owner, "_avl_packed", None)
+    if cache is None:
+        cache = {}
+        try:
+            owner._avl_packed = cache
+        except AttributeError:
+            pass
+    key = (tuple(w.shape), "s2", w.data_ptr())
+    hit = cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    Cout, Cin = w.shape[0], w.shape[1]
+    wd = w.detach()
+    w2 = torch.zeros((2, 2, Cin, 2, 2, Cout), device=w.device, dtype=torch.float32)
+    for pa in range(2):
+        for u in range(2):
+            r = _S2_ROW[pa][u]
+            if r is None:
+                continue
+            for pb in range(2):
+                for v in range(2):
+                    sx = _S2_ROW[pb][v]
+                    if sx is not None:
+                        w2[pa, pb, :, u, v, :] = wd[:, :, r, sx].t()
+    w2 = round_to_tf32(w2.view(4 * Cin, 4 * Cout))
+    cache[key] = (w._version, w2)
+    return w2
+
+
 def conv2d_dgrad_tc(gy, w, H, W, stride, pad):
     """dx (N, H, W, C) of y = conv(x, w, stride, pad) on the forward tensor-core kernels: a stride-1 convolution of gy
     (zero-upsampled when the forward stride was 2) with the flipped, channel-transposed weight.  Returns None when
@@ -305,6 +342,15 @@ def conv2d_dgrad_tc(gy, w, H, W, stride, pad):
     if stride not in (1, 2) or Cout % 4 or pad > KH - 1 or pad > KW - 1:
         return None
     cp = (C + 3) // 4 * 4
+    if (stride == 2 and KH == 3 and KW == 3 and pad == 1 and H % 2 == 0 and W % 2 == 0 and C % 16 == 0 and Cout >= 16
+            and gy.shape[1] * 2 == H and gy.shape[2] * 2 == W and gy.is_contiguous()):
+        gx = torch.empty((gy.shape[0], H, W, C), device=gy.device, dtype=torch.float32)
+        rc = _lib.lib().avl_tc_conv2d_dgrad_s2(fptr(gy), gy.shape[0], gy.shape[1], gy.shape[2], Cout, fptr(_dgrad_s2_weight(w)), C,
+                                               fptr(gx), stream())
+        if rc == 0:
+            return gx
+        if rc != -2:
+            _lib.check(rc, "avl_tc_conv2d_dgrad_s2")
     pk = _packed_weight(w, Cout, dgrad=True)  # (C, KH, KW, Cout)
     if cp != C:  # the result is cropped below; pad the packed rows instead of the activations
         pk = torch.nn.functional.pad(pk, (0, 0, 0, 0, 0, 0, 0, cp - C))

@@ -198,22 +198,26 @@ class DDPPOTrainer(PPOTrainer):
     # ``s`` in the rollout (storage slot s / s + 1, persistent env / belief / memory state, the ring position lives in
     # device memory), so step ``s`` is captured ONCE (during the second rollout, after an eager warm-up rollout) and
     # replayed afterwards: one graph launch per step, every dependency resolved on the device.
-    # Conditions: plain SMT policy, frozen encoders (a trained encoder re-packs its weights into new buffers),
-    # device-resident env (host frames are staged by the host every step), no preemption.
+    # Conditions: plain SMT policy (or the interactive triple), no preemption.  Trainable encoders qualify because their
+    # packed weights keep their addresses (re-packed in place, the re-pack after an optimizer step being part of the first
+    # step's graph: the capture happens during the second rollout, i.e. right after an update); host frames: two graphs
+    # per step (below).
     def _step_graphs_possible(self):
         cfg = self.config
         if not (getattr(cfg, "step_graphs", False) and not cfg.use_preemption and getattr(self, "_step_graphs_ok", True)):
             return False
         if cfg.host_buffers:
             # host frames: a step is TWO graphs around the point where the env worker needs the actions on the host
-            # (``_capture_step_split``); plain SMT policy with frozen encoders on the synthetic env only
-            return (cfg.policy_type == "smt" and cfg.freeze_encoders and getattr(self.envs, "fused_step", False)
+            # (``_capture_step_split``); plain SMT policy on the synthetic env only
+            return (cfg.policy_type == "smt" and getattr(self.envs, "fused_step", False)
                     and getattr(self.envs, "host_buffers", False) and hasattr(self.envs, "stage_frames"))
         if cfg.policy_type == "interactive":
             # pi_g / pi_l are frozen, pi_q never trains its encoders (policy.py:1034-1036): no packed weight changes
             # between rollouts; env / bookkeeping / memory / CLIP-cache state lives in persistent device buffers
             return hasattr(self.envs, "_gstate")
-        return cfg.policy_type == "smt" and cfg.freeze_encoders and getattr(self.envs, "fused_step", False)
+        # (trainable encoders: their packed tensor-core weights are re-packed in place, and the re-pack that follows an
+        # optimizer step is itself captured in the first step's graph — see nn._packed_weight)
+        return cfg.policy_type == "smt" and getattr(self.envs, "fused_step", False)
 
     def _capture_step(self, s):
         # (capture_begin / capture_end directly: the torch.cuda.graph context synchronises the device, runs the garbage

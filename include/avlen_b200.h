@@ -334,6 +334,11 @@ int avl_set_tc_stages(int stages); /* ring depth of the generic tensor-core kern
 int avl_set_tc_splitk_cluster(int on); /* 1 (default): the k-slices of a tile form a thread-block cluster, partial tiles are summed in slice order through distributed shared memory inside the kernel (deterministic, no helper launches); 0: atomic partial sums + separate zero / epilogue kernels; returns old */
 int avl_set_tc_conv_l1(int on);   /* im2col gathers through L1 (cp.async.ca, default) or L2 only; returns old */
 int avl_set_tc_conv_tma(int on);  /* 1 (default): convolutions with >= 16 input channels and enough output tiles are fed by TMA in im2col mode (cuTensorMapEncodeIm2col, cp.async.bulk.tensor...im2col); 0: the cp.async gather everywhere; returns old */
+/* Data gradient of a 3x3 stride-2 pad-1 convolution (stage-entry convolutions of the ResNet-18s, smt_resnet.py:132-149 under
+ * autograd) as one 2x2-tap TMA convolution of dy with a pixel-shuffle epilogue; w2 [4*Cin][4*Cout] (row (pa, pb, ci), column
+ * (u, v, co)); dy (N, OH, OW, Cout) -> dx (N, 2 OH, 2 OW, Cin).  -2: shape not covered (zero-upsample path).                 */
+int avl_tc_conv2d_dgrad_s2(const float* dy, int N, int OH, int OW, int Cout, const float* w2, int Cin, float* dx,
+                           void* stream);
 long long avl_tc_conv_tma_count(void); /* convolutions launched on the TMA im2col kernel so far (diagnostic) */
 int avl_set_tc_conv_halo_tma(int on); /* 1 (default): the halo-strip kernel's input strips arrive by TMA (rank-5 tiled map, halo zero-filled by the unit); 0: cp.async gathers; returns old */
 int avl_set_pdl(int on);          /* 1 (default): the convolution / GroupNorm kernels of the encoder chains are launched with programmatic stream serialization (their prologues overlap the previous kernel; every kernel waits with griddepcontrol.wait before touching activations); 0: plain launches; returns old */

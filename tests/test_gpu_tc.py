@@ -523,3 +523,33 @@ def test_tma_im2col_conv_matches_the_cp_async_kernel_and_torch(shape):
                   + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     assert rel(outs[1], tref) < TOL_TC
     assert rel(outs[1], outs[0]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(600, 64, 64, 16, 32), (640, 32, 32, 32, 64), (1300, 16, 16, 64, 128), (700, 18, 10, 48, 32)])
+def test_stride2_data_gradient_without_upsampling(shape):
+    """Backward of the stage-entry convolutions (3x3, stride 2, pad 1; smt_resnet.py:132-149 under autograd): the 2x2-tap
+    TMA convolution of dy with the pixel-shuffle epilogue against torch's autograd and against the zero-upsample path."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    N, H, W, C, Co = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, C, H, W, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5).cuda()
+    y = F.conv2d(x, w, None, 2, 1)
+    gy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(gy)
+    ref = x.grad.permute(0, 2, 3, 1).contiguous()
+    gy_nhwc = gy.permute(0, 2, 3, 1).contiguous()
+    n0 = int(_lib.lib().avl_tc_conv_tma_count())
+    gx = K.conv2d_dgrad_tc(gy_nhwc, w, H, W, 2, 1)
+    torch.cuda.synchronize()
+    assert gx is not None and gx.shape == ref.shape
+    assert rel(gx, ref) < TOL_TC
+    old = _lib.lib().avl_set_tc_conv_tma(0)   # (the new entry refuses when the TMA convolutions are off: upsample path)
+    try:
+        gx_up = K.conv2d_dgrad_tc(gy_nhwc, w, H, W, 2, 1)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().avl_set_tc_conv_tma(old)
+    assert rel(gx, gx_up) < TOL_TC
+    assert int(_lib.lib().avl_tc_conv_tma_count()) - n0 >= 1
