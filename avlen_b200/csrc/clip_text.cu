@@ -97,6 +97,8 @@ __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const in
 __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ counts,
                                                         int L, float* out) {
   AVL_DYN_SMEM(smem_raw);
+  avl_pdl_wait();
+  avl_pdl_trigger();
   const int s = blockIdx.x, h = blockIdx.y;
   if (s >= counts[0]) return;
   float* Ks = reinterpret_cast<float*>(smem_raw);  // [L][65]
@@ -151,6 +153,8 @@ __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict_
 
 // x * sigmoid(1.702 x) in place (openai/CLIP QuickGELU)
 __global__ void quickgelu_kernel(float* x, const int* __restrict__ rows_dev, long long rows_max, int cols) {
+  avl_pdl_wait();
+  avl_pdl_trigger();
   const long long n = min((long long)*rows_dev, rows_max) * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -219,8 +223,8 @@ static void clip_lin(ClipCtx& c, const float* X, const float* W, const float* b,
 }
 
 static void clip_ln(ClipCtx& c, const float* x, const float* g, const float* b, float* y, const int* rows_dev, int rows) {
-  AVL_LAUNCH(layernorm_fwd_kernel, avl_div_up(rows, 8), 256, 0, c.s, x, (const float*)nullptr, g, b, y, (float*)nullptr,
-             (float*)nullptr, rows_dev, rows, CL_W, 1e-5f);
+  AVL_LAUNCH_PDL(layernorm_fwd_kernel, avl_div_up(rows, 8), 256, 0, c.s, x, (const float*)nullptr, g, b, y, (float*)nullptr,
+                 (float*)nullptr, rows_dev, rows, CL_W, 1e-5f);
   c.check();
 }
 
@@ -287,12 +291,12 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const lon
     const float* const* P = params + CP_LAYER0 + l * CL_PER_LAYER;
     clip_ln(c, b.X, P[CL_LN1_W], P[CL_LN1_B], b.XN, n_rows, R);
     clip_lin(c, b.XN, P[CL_IN_W], P[CL_IN_B], nullptr, b.QKV, R, 3 * CL_W, CL_W, n_rows);
-    AVL_LAUNCH(clip_attn_kernel, dim3(S, CL_HEADS), 256, attn_smem, c.s, b.QKV, n_seq, L, b.ATT);
+    AVL_LAUNCH_PDL(clip_attn_kernel, dim3(S, CL_HEADS), 256, attn_smem, c.s, b.QKV, n_seq, L, b.ATT);
     c.check();
     clip_lin(c, b.ATT, P[CL_OUT_W], P[CL_OUT_B], b.X, b.X, R, CL_W, CL_W, n_rows);  // x += out_proj(att)
     clip_ln(c, b.X, P[CL_LN2_W], P[CL_LN2_B], b.XN, n_rows, R);
     clip_lin(c, b.XN, P[CL_FC_W], P[CL_FC_B], nullptr, b.H, R, CL_FF, CL_W, n_rows);
-    AVL_LAUNCH(quickgelu_kernel, ew, 256, 0, c.s, b.H, n_rows, (long long)R, CL_FF);
+    AVL_LAUNCH_PDL(quickgelu_kernel, ew, 256, 0, c.s, b.H, n_rows, (long long)R, CL_FF);
     c.check();
     clip_lin(c, b.H, P[CL_PROJ_W], P[CL_PROJ_B], b.X, b.X, R, CL_W, CL_FF, n_rows);  // x += c_proj(h)
   }

@@ -58,7 +58,10 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
   __shared__ uint32_t tmem_base_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = p.M;
-  if (p.m_dev) M = min(M, *p.m_dev);
+  if (p.m_dev) {
+    avl_pdl_wait();  // the device-side row count may come from the kernel just before this one
+    M = min(M, *p.m_dev);
+  }
   const int m0 = blockIdx.x * TM_BM;
   if (m0 >= M) return;
   const int n0 = blockIdx.y * p.bn;
@@ -433,6 +436,10 @@ int avl_tc_gemm_tma_try(const float* A, long long lda, const float* B, float* C,
   p.bn = 64;
   for (int bn = 256; bn >= 64; bn >>= 1)
     if ((long long)mtiles * avl_div_up(N, bn) >= sms) { p.bn = bn; break; }
+  // a device-side row count means M is an upper bound (packed transformer rows, the CLIP tower's distinct sequences):
+  // at rollout sizes a few row tiles are live, so the launch is a latency chain of K / 32 k-tiles per CTA — narrow tiles (4
+  // ring slots instead of 2, 4x the CTAs) keep more loads in flight; large problems keep the wide tiles
+  if (m_dev && K >= 512 && mtiles <= 32) p.bn = 64;
   if (p.bn > n16) p.bn = n16;
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
@@ -452,7 +459,7 @@ int avl_tc_gemm_tma_try(const float* A, long long lda, const float* B, float* C,
     attr_set = true;
   }
   dim3 grid(avl_div_up(M, TM_BM), avl_div_up(N, p.bn));
-  tc_gemm_tma_kernel<false><<<grid, TM_THREADS, smem, stream>>>(ta, tb, p);
+  AVL_LAUNCH_PDL(tc_gemm_tma_kernel<false>, grid, TM_THREADS, smem, stream, ta, tb, p);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

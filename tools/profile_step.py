@@ -27,7 +27,11 @@ def main():
     over = {}
     if os.environ.get("AVL_REGIME") == "trainable":  # savi_pretraining.yaml: freeze_encoders False, pretraining True
         over = dict(freeze_encoders=False, pretraining=os.environ.get("AVL_FULL_MEMORY") != "1")
-    cfg = savi_config(NUM_PROCESSES=64, num_steps=steps, **over)
+    envs = 64
+    if os.environ.get("AVL_POLICY") == "interactive":  # BASELINE config 2: savi_interactive_2nd_stage.yaml at 32 envs / GPU
+        over.update(policy_type="interactive", freeze_encoders=False)
+        envs = 32
+    cfg = savi_config(NUM_PROCESSES=envs, num_steps=steps, step_graphs=False, **over)
     tr = DDPPOTrainer(cfg).setup()
     tr.collect_rollout()
     tr._update_agent(cfg, tr.rollouts)
