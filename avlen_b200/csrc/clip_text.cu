@@ -93,7 +93,7 @@ __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const in
   for (int c = threadIdx.x; c < CL_W; c += blockDim.x) o[c] = e[c] + p[c];
 }
 
-// causal multi-head attention, head dim 64; qkv rows [q | k | v] of width 3*512; one CTA per (sequence, head)
+// causal multi-head attention, head dim 64; qkv rows [q | k | v] of width 3*512; gridDim.z CTAs per (sequence, head)
 __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ counts,
                                                         int L, float* out) {
   AVL_DYN_SMEM(smem_raw);
@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict_
   __syncthreads();
   float* ps = Ps + warp * CL_MAXL;
   float* qs = Qs + warp * CL_HD;
-  for (int i = warp; i < L; i += 8) {
+  // gridDim.z CTAs share one (sequence, head): queries are dealt out round-robin over (CTA, warp) — at rollout batch a
+  // handful of sequences is live and the ~10 queries a warp walked one after the other were the kernel's latency
+  for (int i = warp + 8 * blockIdx.z; i < L; i += 8 * gridDim.z) {
     qs[lane] = base[(size_t)i * ld + lane] * 0.125f;
     qs[lane + 32] = base[(size_t)i * ld + lane + 32] * 0.125f;
     __syncwarp();
@@ -291,7 +293,7 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const lon
     const float* const* P = params + CP_LAYER0 + l * CL_PER_LAYER;
     clip_ln(c, b.X, P[CL_LN1_W], P[CL_LN1_B], b.XN, n_rows, R);
     clip_lin(c, b.XN, P[CL_IN_W], P[CL_IN_B], nullptr, b.QKV, R, 3 * CL_W, CL_W, n_rows);
-    AVL_LAUNCH_PDL(clip_attn_kernel, dim3(S, CL_HEADS), 256, attn_smem, c.s, b.QKV, n_seq, L, b.ATT);
+    AVL_LAUNCH_PDL(clip_attn_kernel, dim3(S, CL_HEADS, S <= 64 ? 4 : 1), 256, attn_smem, c.s, b.QKV, n_seq, L, b.ATT);
     c.check();
     clip_lin(c, b.ATT, P[CL_OUT_W], P[CL_OUT_B], b.X, b.X, R, CL_W, CL_W, n_rows);  // x += out_proj(att)
     clip_ln(c, b.X, P[CL_LN2_W], P[CL_LN2_B], b.XN, n_rows, R);
