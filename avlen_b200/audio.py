@@ -53,7 +53,9 @@ class AudioRenderer:
 
     @property
     def max_rir_len(self):
-        return 32768 - self.sr + 1
+        # one 32768-point circular convolution per ear up to 16769 Hz; above (Replica, 44.1 kHz) the partitioned path
+        # (blocks of 16384 samples) takes RIRs of up to three partitions
+        return 32768 - self.sr + 1 if self.sr <= 16769 else 3 * 16384
 
     def render(self, sounds, clip_off, index, rirs, rir_off, rir_len, silent, d_clip_off=None, d_rir_off=None,
                d_rir_len=None, want_audiogoal=True, out_audiogoal=None, out_spectrogram=None):

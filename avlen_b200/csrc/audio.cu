@@ -562,6 +562,157 @@ spectrogram_kernel(const float* audio, int n, int sr, float* spectrogram, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Partitioned convolution for sampling rates / RIR lengths beyond one 32768-point circular convolution
+// (sr + L - 1 > 32768: Replica's 44.1 kHz clips, nav.py:87-101 -> (65, 69, 2) spectrograms).  Uniformly partitioned
+// overlap-save with blocks of B = 16384 samples on the SAME 16384-point complex FFT machinery:
+//     y[k B + n] = sum_q  circ_P( h_q , u_{k-q} )[n],   n in [0, B),   P = 2 B
+//     h_q[t] = rir[q B + t]  (t < B),        u_j[m] = src[base + j B + m]  (m < B),  u_j[P - i] = src[base + j B - i]  (i < B)
+// Spectra X_j of the source windows and the accumulators Y_{c,k} live in a per-CTA global scratch (L2 resident); per
+// (term, channel, partition) one forward FFT of the RIR partition is multiplied into every output block it reaches; one
+// inverse FFT per (channel, block).  The waveform goes to global memory (the audiogoal output or a per-CTA scratch) and
+// the STFT reads it back with coherent loads.
+struct GmemSamplesCg {  // written earlier by this CTA: coherent loads (not the read-only path)
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return __ldcg(p + i); }
+};
+
+// packed window j of the source: see the formulas above.  lim = first sample index that must read as zero (base + sr)
+__device__ void load_window(cf* buf, const float* src, long long w0, long long lim) {
+  for (int n = threadIdx.x; n < kM; n += kThreads) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = 2 * n + h;
+      long long idx = -1;
+      if (m < kM) idx = w0 + m;
+      else if (m > kP - kM) idx = w0 - (kP - m);
+      v[h] = (idx >= 0 && idx < lim) ? __ldg(src + idx) : 0.f;
+    }
+    buf[padi(n)] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+}
+
+// packed partition q of channel c of an interleaved (L, 2) RIR
+__device__ void load_rir_part(cf* buf, const float* rir, int L, int c, int q) {
+  const long long o = (long long)q * kM;
+  for (int n = threadIdx.x; n < kM; n += kThreads) {
+    const long long k0 = o + 2 * n, k1 = k0 + 1;
+    const float a = (2 * n < kM && k0 < L) ? __ldg(rir + 2 * k0 + c) : 0.f;
+    const float b = (2 * n + 1 < kM && k1 < L) ? __ldg(rir + 2 * k1 + c) : 0.f;
+    buf[padi(n)] = make_float2(a, b);
+  }
+  __syncthreads();
+}
+
+// buf <- half-size spectrum (digit-reversed, scaled by 1 / M) of the packed real signal whose spectrum is Y[0..kM]
+__device__ void load_repacked(cf* buf, const cf* __restrict__ tw, const cf* Y) {
+  const float scale = 1.0f / (float)kM;
+  for (int k = threadIdx.x; k <= kM / 2; k += kThreads) {
+    if (k == 0) {
+      const cf y0 = __ldcg(&Y[0]), yM = __ldcg(&Y[kM]);
+      buf[padi(0)] = make_float2(0.5f * (y0.x + yM.x) * scale, 0.5f * (y0.x - yM.x) * scale);
+      continue;
+    }
+    const cf yk = __ldcg(&Y[k]), ymc = cconj(__ldcg(&Y[kM - k]));
+    const cf wk = tw[k];
+    const cf e = make_float2(0.5f * (yk.x + ymc.x), 0.5f * (yk.y + ymc.y));
+    const cf d = make_float2(0.5f * (yk.x - ymc.x), 0.5f * (yk.y - ymc.y));
+    const cf o = cmulc(d, wk);
+    buf[padi(rev_big(k))] = make_float2((e.x - o.y) * scale, (e.y + o.x) * scale);
+    if (k != kM / 2) {
+      const cf o2 = cmul(cconj(d), wk);
+      buf[padi(rev_big(kM - k))] = make_float2((e.x - o2.y) * scale, (-e.y + o2.x) * scale);
+    }
+  }
+  __syncthreads();
+}
+
+struct PartArgs {
+  int K;         // output blocks: ceil(sr / B)
+  int Qmax;      // RIR partitions the scratch is sized for
+  cf* scratch;   // per CTA: (K + Qmax - 1) source spectra, then 2 K accumulators, (kM + 1) complex each
+  float* wave;   // per CTA 2 * sr floats (used when no audiogoal output is requested)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) audio_render_part_kernel(RenderArgs a, PartArgs pa) {
+  AVL_DYN_SMEM(smem_raw);
+  cf* buf = reinterpret_cast<cf*>(smem_raw);
+  cf* fb = buf + kBufElems;
+  float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
+  fill_window(win);
+  const int sr = a.sr, K = pa.K, Qmax = pa.Qmax;
+  const size_t spec = (size_t)(kM + 1);
+  cf* Xs = pa.scratch + (size_t)blockIdx.x * (size_t)(K + Qmax - 1 + 2 * K) * spec;
+  cf* Ys = Xs + (size_t)(K + Qmax - 1) * spec;
+  const int n_tb = ((1 + sr / kHop) + 3) >> 2;
+  __syncthreads();
+  for (int e = blockIdx.x; e < a.n_envs; e += gridDim.x) {
+    EnvTerm term[2];
+    int nterms = 0;
+    if (a.silent[e] == 0) {
+      int L = a.rir_len[e];
+      if (L > Qmax * kM) { L = Qmax * kM; if (threadIdx.x == 0) atomicExch(a.status, 1); }
+      if (L > 0) {
+        term[nterms].src = a.sounds + a.clip_off[e];
+        term[nterms].base = (long long)a.index[e] * sr;
+        term[nterms].rir = a.rirs + 2 * a.rir_off[e];
+        term[nterms].L = L;
+        ++nterms;
+      }
+      if (a.d_clip_off != nullptr) {
+        int Ld = a.d_rir_len[e];
+        if (Ld > Qmax * kM) { Ld = Qmax * kM; if (threadIdx.x == 0) atomicExch(a.status, 1); }
+        if (Ld > 0) {
+          term[nterms].src = a.sounds + a.d_clip_off[e];
+          term[nterms].base = 0;
+          term[nterms].rir = a.rirs + 2 * a.d_rir_off[e];
+          term[nterms].L = Ld;
+          ++nterms;
+        }
+      }
+    }
+    float* spec_out = a.spectrogram + (size_t)e * kFB * n_tb * 2;
+    float* wave = a.audiogoal ? a.audiogoal + (size_t)e * 2 * sr : pa.wave + (size_t)blockIdx.x * 2 * sr;
+    if (nterms == 0) {
+      for (int i = threadIdx.x; i < kFB * n_tb * 2; i += kThreads) spec_out[i] = 0.f;
+      if (a.audiogoal)
+        for (int i = threadIdx.x; i < 2 * sr; i += kThreads) wave[i] = 0.f;
+      continue;
+    }
+    for (int t = 0; t < nterms; ++t) {
+      const int Q = (term[t].L + kM - 1) / kM;
+      for (int j = -(Q - 1); j < K; ++j) {
+        load_window(buf, term[t].src, term[t].base + (long long)j * kM, term[t].base + sr);
+        fft_big_fwd(buf, a.tw);
+        store_spectrum(buf, a.tw, Xs + (size_t)(j + Qmax - 1) * spec);
+      }
+      for (int c = 0; c < 2; ++c)
+        for (int q = 0; q < Q; ++q) {
+          load_rir_part(buf, term[t].rir, term[t].L, c, q);
+          fft_big_fwd(buf, a.tw);
+          for (int k = 0; k < K; ++k)  // (t, q) = (0, 0) is the first product every accumulator receives
+            spectral_multiply(buf, a.tw, Xs + (size_t)(k - q + Qmax - 1) * spec, Ys + (size_t)(c * K + k) * spec,
+                              t > 0 || q > 0, false);
+        }
+    }
+    for (int c = 0; c < 2; ++c) {
+      for (int k = 0; k < K; ++k) {
+        load_repacked(buf, a.tw, Ys + (size_t)(c * K + k) * spec);
+        fft_big_inv(buf, a.tw);
+        SmemSamples y{reinterpret_cast<const float*>(buf)};
+        const int n_out = min(kM, sr - k * kM);
+        float* wc = wave + (size_t)c * sr + (size_t)k * kM;
+        for (int i = threadIdx.x; i < n_out; i += kThreads) __stcg(wc + i, y(i));
+        __syncthreads();
+      }
+      GmemSamplesCg yc{wave + (size_t)c * sr};
+      stft_channel(yc, sr, fb, win, a.tw, spec_out, c);
+    }
+  }
+}
+
 __global__ void twiddle_init_kernel(cf* tw) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k <= kM) {
@@ -578,7 +729,13 @@ struct AudioCtx {
   cf* tw;
   cf* scratch;
   int* status;
+  // partitioned path (sr + L - 1 may exceed one 32768-point convolution): allocated when sr > 16769
+  int part_K, part_Qmax;
+  cf* part_scratch;
+  float* part_wave;
 };
+
+constexpr int kPartQmax = 3;  // RIRs up to 3 * 16384 = 49152 samples (1.1 s at 44.1 kHz)
 
 constexpr size_t kRenderSmem = (size_t)(kBufElems + kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
 constexpr size_t kSpecSmem = (size_t)(kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
@@ -589,7 +746,7 @@ constexpr size_t kSpecSmem = (size_t)(kWarps * 2 * kFrameElems) * sizeof(cf) + k
 
 #ifndef AVL_HOST_EMUL
 // Creates the audio context (twiddle table + per-CTA spectrum scratch).  The
-// only allocation the audio path ever makes.  sr must satisfy 512 <= sr <= 16769.
+// only allocation the audio path ever makes.  sr >= 512; above 16769 Hz the partitioned-convolution path is set up.
 AVL_API int avl_audio_create(int sr, void** handle) {
   if (!handle) return AVL_ERR_ARG;
   if (sr < kNfft) return AVL_ERR_UNSUPPORTED;
@@ -602,6 +759,15 @@ AVL_API int avl_audio_create(int sr, void** handle) {
   AVL_CUDA_CHECK(cudaMemset(ctx->status, 0, sizeof(int)));
   twiddle_init_kernel<<<avl_div_up(kM + 1, 256), 256>>>(ctx->tw);
   AVL_LAUNCH_CHECK();
+  ctx->part_K = 0; ctx->part_Qmax = 0; ctx->part_scratch = nullptr; ctx->part_wave = nullptr;
+  if (sr > kP / 2 + 385) {
+    ctx->part_K = (sr + kM - 1) / kM;
+    ctx->part_Qmax = kPartQmax;
+    const size_t spectra = (size_t)(ctx->part_K + ctx->part_Qmax - 1 + 2 * ctx->part_K);
+    AVL_CUDA_CHECK(cudaMalloc(&ctx->part_scratch, sizeof(cf) * spectra * (kM + 1) * (size_t)ctx->grid));
+    AVL_CUDA_CHECK(cudaMalloc(&ctx->part_wave, sizeof(float) * 2 * (size_t)sr * (size_t)ctx->grid));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_render_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRenderSmem));
+  }
   AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRenderSmem));
   AVL_CUDA_CHECK(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem));
   AVL_CUDA_CHECK(cudaDeviceSynchronize());
@@ -615,12 +781,14 @@ AVL_API int avl_audio_destroy(void* handle) {
   cudaFree(ctx->tw);
   cudaFree(ctx->scratch);
   cudaFree(ctx->status);
+  if (ctx->part_scratch) cudaFree(ctx->part_scratch);
+  if (ctx->part_wave) cudaFree(ctx->part_wave);
   delete ctx;
   return AVL_OK;
 }
 
 // Sticky device-side status of earlier render calls (synchronises the device):
-// 0 ok, 1 = some RIR was longer than 32768 - sr + 1 samples and was truncated.
+// 0 ok, 1 = some RIR was longer than 32768 - sr + 1 samples (49152 on the partitioned path) and was truncated.
 AVL_API int avl_audio_status(void* handle, int* status_out) {
   AudioCtx* ctx = static_cast<AudioCtx*>(handle);
   if (!ctx || !status_out) return AVL_ERR_ARG;
@@ -647,13 +815,21 @@ AVL_API int avl_audio_render_spectrogram(void* handle, int n_envs, const float* 
   if (n_envs == 0) return AVL_OK;
   if (!sounds || !clip_off || !index || !rirs || !rir_off || !rir_len || !silent || !spectrogram_out) return AVL_ERR_ARG;
   if ((d_clip_off != nullptr) != (d_rir_off != nullptr) || (d_clip_off != nullptr) != (d_rir_len != nullptr)) return AVL_ERR_ARG;
-  if (ctx->sr > kP / 2 + 385) return AVL_ERR_UNSUPPORTED;  // fused path needs sr + L - 1 <= 32768
   RenderArgs a;
   a.n_envs = n_envs; a.sr = ctx->sr; a.sounds = sounds; a.clip_off = clip_off; a.index = index;
   a.rirs = rirs; a.rir_off = rir_off; a.rir_len = rir_len; a.silent = silent;
   a.d_clip_off = d_clip_off; a.d_rir_off = d_rir_off; a.d_rir_len = d_rir_len;
   a.audiogoal = audiogoal_out; a.spectrogram = spectrogram_out; a.tw = ctx->tw; a.scratch = ctx->scratch;
   a.status = ctx->status;
+  if (ctx->part_K > 0) {  // sr + L - 1 may exceed one 32768-point convolution: partitioned overlap-save
+    a.split = 0;
+    PartArgs pa;
+    pa.K = ctx->part_K; pa.Qmax = ctx->part_Qmax; pa.scratch = ctx->part_scratch; pa.wave = ctx->part_wave;
+    const int g = n_envs < ctx->grid ? n_envs : ctx->grid;
+    audio_render_part_kernel<<<g, kThreads, kRenderSmem, (cudaStream_t)stream>>>(a, pa);
+    AVL_LAUNCH_CHECK();
+    return AVL_OK;
+  }
   a.split = (2 * n_envs <= ctx->grid && g_audio_split) ? 1 : 0;
   const int items = a.split ? 2 * n_envs : n_envs;
   int grid = items < ctx->grid ? items : ctx->grid;

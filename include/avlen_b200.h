@@ -38,7 +38,9 @@ int avl_audio_status(void* handle, int* status_out /* host; synchronises; 1 = an
 /* sounds: flat bank of mono clips; clip_off[i]: start of env i's clip; index[i]: _audio_index (second rendered);
  * rirs: bank of interleaved (L,2) RIRs; rir_off[i] in frames; rir_len[i] (0 = empty file -> zeros);
  * silent[i] != 0 -> exact zeros; d_*: optional distractor source/RIR (all three or none);
- * audiogoal_out (N,2,sr) may be NULL; spectrogram_out (N,65,ceil((1+sr/160)/4),2).                             */
+ * audiogoal_out (N,2,sr) may be NULL; spectrogram_out (N,65,ceil((1+sr/160)/4),2): (65,26,2) at 16 kHz, (65,69,2) at
+ * 44.1 kHz (nav.py:78).  sr <= 16769: one 32768-point circular convolution per ear, RIRs up to 32768 - sr + 1 samples;
+ * above (Replica): partitioned overlap-save over 16384-sample blocks, RIRs up to 49152 samples.                */
 int avl_audio_render_spectrogram(void* handle, int n_envs, const float* sounds, const long long* clip_off,
                                  const int* index, const float* rirs, const long long* rir_off, const int* rir_len,
                                  const int* silent, const long long* d_clip_off, const long long* d_rir_off,

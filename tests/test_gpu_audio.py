@@ -131,3 +131,35 @@ def test_channel_split_small_batches_bitwise(renderer, distractor):
     assert np.array_equal(ag0, ag1) and np.array_equal(sp0, sp1)
     ag_ref, sp_ref = oracle_render(b)
     assert rel_err(ag1, ag_ref) < TOL
+
+
+@pytest.mark.parametrize("distractor", [False, True])
+@pytest.mark.parametrize("fixed_len", [9000, 30000, 44100])
+def test_render_at_44100_hz_partitioned_convolution(distractor, fixed_len):
+    """Replica's sampling rate (nav.py:87-101 -> a (65, 69, 2) spectrogram): sr + L - 1 exceeds one 32768-point circular
+    convolution, so the render runs as a partitioned overlap-save over 16384-sample blocks; against scipy's fftconvolve."""
+    from avlen_b200.audio import AudioRenderer, spectrogram_shape
+    sr = 44100
+    r = AudioRenderer(sr)
+    try:
+        b = synth.make_audio_batch(400 + fixed_len, 10, sr=sr, distractor=distractor, fixed_len=fixed_len, max_seconds=6,
+                                   silent_frac=0.1, n_clips=6)
+        b["silent"][0] = 1
+        b["rir_len"][1] = 0
+        ag_ref, sp_ref = oracle_render(b)
+        ag, sp = _render(r, b)
+        assert spectrogram_shape(sr) == (65, 69, 2)
+        assert ag.shape == (10, 2, sr) and sp.shape == (10, 65, 69, 2)
+        assert np.all(ag[0] == 0) and np.all(sp[0] == 0)
+        if not distractor:
+            assert np.all(ag[1] == 0) and np.all(sp[1] == 0)   # empty RIR file (with a distractor its term remains)
+        assert rel_err(ag, ag_ref) < TOL
+        assert np.abs(sp - sp_ref).max() < TOL * max(1.0, np.abs(sp_ref).max())
+        assert r.status() == 0
+        _, sp2 = _render(r, b, want_audiogoal=False)      # waveform through the per-CTA scratch instead of the output
+        assert np.array_equal(sp, sp2)
+        # the stand-alone spectrogram (row B) of the reference waveform at this rate
+        sp3 = r.compute_spectrogram(torch.from_numpy(ag_ref.astype(np.float32)).cuda()).cpu().numpy()
+        assert np.abs(sp3 - sp_ref).max() < TOL * max(1.0, np.abs(sp_ref).max())
+    finally:
+        r.close()
