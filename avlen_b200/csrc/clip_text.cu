@@ -12,6 +12,9 @@
 // Dense layers run on the tcgen05 TF32 GEMM (gemm_tc.cu) when tensor cores are enabled (the reference runs this
 // tower in fp16 on CUDA), fp32 SIMT otherwise.
 #include "nn_kernels.cuh"
+#ifndef AVL_HOST_EMUL
+#include <cuda_fp16.h>
+#endif
 
 namespace {
 
@@ -94,8 +97,9 @@ __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const in
 }
 
 // causal multi-head attention, head dim 64; qkv rows [q | k | v] of width 3*512; gridDim.z CTAs per (sequence, head)
+template <bool OUT16>
 __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ counts,
-                                                        int L, float* out) {
+                                                        int L, void* out_) {
   AVL_DYN_SMEM(smem_raw);
   avl_pdl_wait();
   avl_pdl_trigger();
@@ -146,9 +150,18 @@ __global__ void __launch_bounds__(256) clip_attn_kernel(const float* __restrict_
       o1 = fmaf(p, Vs[j * 65 + lane + 32], o1);
     }
     const float inv = 1.f / sum;
-    float* o = out + ((size_t)s * L + i) * CL_W + h * CL_HD;
-    o[lane] = o0 * inv;
-    o[lane + 32] = o1 * inv;
+#ifndef AVL_HOST_EMUL
+    if (OUT16) {  // (fp16 operand of the out-projection GEMM)
+      __half* o = reinterpret_cast<__half*>(out_) + ((size_t)s * L + i) * CL_W + h * CL_HD;
+      o[lane] = __float2half_rn(o0 * inv);
+      o[lane + 32] = __float2half_rn(o1 * inv);
+    } else
+#endif
+    {
+      float* o = reinterpret_cast<float*>(out_) + ((size_t)s * L + i) * CL_W + h * CL_HD;
+      o[lane] = o0 * inv;
+      o[lane + 32] = o1 * inv;
+    }
     __syncwarp();
   }
 }
@@ -163,6 +176,47 @@ __global__ void quickgelu_kernel(float* x, const int* __restrict__ rows_dev, lon
     x[i] = v / (1.f + __expf(-1.702f * v));
   }
 }
+
+#ifndef AVL_HOST_EMUL
+// LayerNorm over 512 columns, warp per row, fp16 output (the A operand of the next fp16 GEMM); fp32 statistics
+__global__ void __launch_bounds__(256) clip_ln16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __half* y,
+                                                        const int* __restrict__ rows_dev, int rows_max) {
+  avl_pdl_wait();
+  avl_pdl_trigger();
+  const int rows = min(*rows_dev, rows_max);
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * CL_W);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / CL_W);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / CL_W) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const __half2 lo = __floats2half2_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    const __half2 hi = __floats2half2_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + (size_t)row * CL_W + 4 * c4) = u;
+  }
+}
+#endif
 
 // xe[s, :] = x[s*L + eot[s], :]
 __global__ void clip_take_eot_kernel(const float* __restrict__ x, const int* __restrict__ eot,
@@ -233,6 +287,7 @@ static void clip_ln(ClipCtx& c, const float* x, const float* g, const float* b, 
 struct ClipBufs {
   int *slot, *src, *eot, *counts;
   float *X, *XN, *QKV, *ATT, *H, *XE, *EMB;
+  void *XN16, *ATT16, *H16;  // fp16 operands of the kind::f16 GEMMs (half the size of their fp32 twins)
 };
 static size_t clip_layout(char* base, ClipBufs& b, size_t B, size_t L) {
   size_t off = 0;
@@ -247,6 +302,7 @@ static size_t clip_layout(char* base, ClipBufs& b, size_t B, size_t L) {
   b.X = (float*)take(4 * R * CL_W); b.XN = (float*)take(4 * R * CL_W); b.QKV = (float*)take(4 * R * 3 * CL_W);
   b.ATT = (float*)take(4 * R * CL_W); b.H = (float*)take(4 * R * CL_FF);
   b.XE = (float*)take(4 * S * CL_W); b.EMB = (float*)take(4 * S * CL_W);
+  b.XN16 = take(2 * R * CL_W); b.ATT16 = take(2 * R * CL_W); b.H16 = take(2 * R * CL_FF);
   return off + 256;
 }
 
@@ -263,8 +319,31 @@ AVL_API long long avl_clip_text_workspace_bytes(int B, int L) {
 // params: avl_clip_text_param_count(layers) device pointers in the order of avlen_b200/savi/models/clip_text.py::CLIP_PARAM_KEYS;
 // out (B, 512) fp32.  dedupe != 0: all-zero rows are encoded once (see header).  counts_out (optional, device,
 // 2 ints): distinct sequences / rows actually processed.
+#ifndef AVL_HOST_EMUL
+extern "C" int avl_tc_gemm_tma_f16(const void* A, long long lda, const void* W, void* C, long long ldc, int M, int N, int K,
+                                   const float* bias, const float* residual, long long ldr, int act, int out16,
+                                   const int* m_dev, cudaStream_t stream);  // gemm_tma.cu
+#endif
+static int clip_forward(int B, int L, int vocab, int layers, const long long* tokens, const float* const* params,
+                        const void* const* params16, float* out, void* workspace, int dedupe, void* stream);
+
 AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const long long* tokens,
                                   const float* const* params, float* out, void* workspace, int dedupe, void* stream) {
+  return clip_forward(B, L, vocab, layers, tokens, params, nullptr, out, workspace, dedupe, stream);
+}
+
+// The same tower with its four linears per layer on fp16 operands (tcgen05 kind::f16, fp32 accumulation, fp32 residual
+// stream, LayerNorm / softmax statistics in fp32) — the dtype the reference itself runs CLIP in on CUDA (policy.py:761,
+// `clip.load` converts the weights to fp16).  params16: 4 * layers device pointers to fp16 copies of
+// (in_proj_weight, out_proj.weight, c_fc.weight, c_proj.weight) per layer; NULL = avl_clip_text_forward.
+AVL_API int avl_clip_text_forward_f16(int B, int L, int vocab, int layers, const long long* tokens,
+                                      const float* const* params, const void* const* params16, float* out, void* workspace,
+                                      int dedupe, void* stream) {
+  return clip_forward(B, L, vocab, layers, tokens, params, params16, out, workspace, dedupe, stream);
+}
+
+static int clip_forward(int B, int L, int vocab, int layers, const long long* tokens, const float* const* params,
+                        const void* const* params16, float* out, void* workspace, int dedupe, void* stream) {
   if (B < 0 || L < 1 || L > CL_MAXL || vocab < 1 || layers < 1 || layers > CL_MAX_LAYERS) return AVL_ERR_ARG;
   if (B == 0) return AVL_OK;
   if (!tokens || !params || !out || !workspace) return AVL_ERR_ARG;
@@ -276,7 +355,8 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const lon
 #ifndef AVL_HOST_EMUL
   static bool attr = false;
   if (!attr) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(clip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(clip_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(clip_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
 #endif
@@ -289,11 +369,37 @@ AVL_API int avl_clip_text_forward(int B, int L, int vocab, int layers, const lon
   int ew = avl_div_up((long long)R * CL_FF, 1024);
   int cap = avl_num_sms() * 16;
   if (ew > cap) ew = cap;
-  for (int l = 0; l < layers; ++l) {
+#ifndef AVL_HOST_EMUL
+  const bool f16 = params16 != nullptr && clip_tc_ok(R);
+  for (int l = 0; f16 && l < layers; ++l) {
+    const float* const* P = params + CP_LAYER0 + l * CL_PER_LAYER;
+    const void* const* W16 = params16 + 4 * l;
+    cudaStream_t cs = (cudaStream_t)stream;
+    int rc;
+    AVL_LAUNCH_PDL(clip_ln16_kernel, avl_div_up(R, 8), 256, 0, cs, b.X, P[CL_LN1_W], P[CL_LN1_B], (__half*)b.XN16, n_rows, R);
+    c.check();
+    rc = avl_tc_gemm_tma_f16(b.XN16, CL_W, W16[0], b.QKV, 3 * CL_W, R, 3 * CL_W, CL_W, P[CL_IN_B], nullptr, 0, 0, 0, n_rows, cs);
+    if (rc && !c.err) c.err = rc;
+    AVL_LAUNCH_PDL(clip_attn_kernel<true>, dim3(S, CL_HEADS, S <= 64 ? 4 : 1), 256, attn_smem, cs, b.QKV, n_seq, L, b.ATT16);
+    c.check();
+    rc = avl_tc_gemm_tma_f16(b.ATT16, CL_W, W16[1], b.X, CL_W, R, CL_W, CL_W, P[CL_OUT_B], b.X, CL_W, 0, 0, n_rows, cs);  // x += out_proj
+    if (rc && !c.err) c.err = rc;
+    AVL_LAUNCH_PDL(clip_ln16_kernel, avl_div_up(R, 8), 256, 0, cs, b.X, P[CL_LN2_W], P[CL_LN2_B], (__half*)b.XN16, n_rows, R);
+    c.check();
+    // c_fc with QuickGELU in the epilogue, fp16 result = operand of c_proj (no separate activation pass)
+    rc = avl_tc_gemm_tma_f16(b.XN16, CL_W, W16[2], b.H16, CL_FF, R, CL_FF, CL_W, P[CL_FC_B], nullptr, 0, 2, 1, n_rows, cs);
+    if (rc && !c.err) c.err = rc;
+    rc = avl_tc_gemm_tma_f16(b.H16, CL_FF, W16[3], b.X, CL_W, R, CL_W, CL_FF, P[CL_PROJ_B], b.X, CL_W, 0, 0, n_rows, cs);  // x += c_proj
+    if (rc && !c.err) c.err = rc;
+  }
+#else
+  const bool f16 = false;
+#endif
+  for (int l = 0; !f16 && l < layers; ++l) {
     const float* const* P = params + CP_LAYER0 + l * CL_PER_LAYER;
     clip_ln(c, b.X, P[CL_LN1_W], P[CL_LN1_B], b.XN, n_rows, R);
     clip_lin(c, b.XN, P[CL_IN_W], P[CL_IN_B], nullptr, b.QKV, R, 3 * CL_W, CL_W, n_rows);
-    AVL_LAUNCH_PDL(clip_attn_kernel, dim3(S, CL_HEADS, S <= 64 ? 4 : 1), 256, attn_smem, c.s, b.QKV, n_seq, L, b.ATT);
+    AVL_LAUNCH_PDL(clip_attn_kernel<false>, dim3(S, CL_HEADS, S <= 64 ? 4 : 1), 256, attn_smem, c.s, b.QKV, n_seq, L, (void*)b.ATT);
     c.check();
     clip_lin(c, b.ATT, P[CL_OUT_W], P[CL_OUT_B], b.X, b.X, R, CL_W, CL_W, n_rows);  // x += out_proj(att)
     clip_ln(c, b.X, P[CL_LN2_W], P[CL_LN2_B], b.XN, n_rows, R);

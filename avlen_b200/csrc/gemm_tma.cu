@@ -11,6 +11,7 @@
 
 #ifndef AVL_HOST_EMUL
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -34,6 +35,8 @@ struct TmaArgs {
   // pixel shuffle (stride-2 data gradients): the N = 4 * ps_c output columns of row (n, oh, ow) are the ps_c channels of the
   // four pixels (2 oh + pa, 2 ow + pb), column block pa * 2 + pb; C then points at a (N, 2 OH, 2 OW, ps_c) tensor
   int ps_c;
+  // F16 instantiation (fp16 A / B through TMA, kind::f16): C is fp32, or fp16 when out16; act 2 = QuickGELU x * sigmoid(1.702 x)
+  int out16, act;
 };
 
 // cp.async.bulk.tensor im2col mode: {c, w, h, n} = channel offset and the input coordinates of the FIRST output pixel of
@@ -49,7 +52,7 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tma
       : "memory");
 }
 
-template <bool CONV>
+template <bool CONV, bool F16 = false>
 __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TmaArgs p) {
   AVL_DYN_SMEM(smem);
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
   if (m0 >= M) return;
   const int n0 = blockIdx.y * p.bn;
   const int bn = p.bn;
-  const int KT = CONV ? p.K : (p.K + TM_BK - 1) / TM_BK;  // (CONV: the host passes the number of k-tiles)
+  constexpr int BKE = F16 ? 64 : TM_BK;  // elements per 128-byte k-tile row
+  const int KT = CONV ? p.K : (p.K + BKE - 1) / BKE;  // (CONV: the host passes the number of k-tiles)
   const uint32_t a_stage = TM_BM * 128u, b_stage = (uint32_t)bn * 128u, stage_bytes = a_stage + b_stage;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar0 = smem_u32(&bars[0]);
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TM_BM, bn);
+      const uint32_t idesc = F16 ? umma_idesc_f16_kmajor(TM_BM, bn) : umma_idesc_tf32(TM_BM, bn);
       for (int kt = 0; kt < KT; ++kt) {
         const int slot = kt % TM_STAGES;
         mbar_wait(FULL(slot), (uint32_t)((kt / TM_STAGES) & 1));
@@ -106,8 +110,10 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
         const uint32_t a_base = smem_base + slot * stage_bytes;
         const uint64_t ad0 = umma_desc_sw128(a_base), bd0 = umma_desc_sw128(a_base + a_stage);
 #pragma unroll
-        for (int q = 0; q < TM_BK / 8; ++q)
-          umma_tf32(tmem_base, ad0 + 2u * q, bd0 + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+        for (int q = 0; q < TM_BK / 8; ++q) {  // four MMAs per 128-byte row: K = 8 (tf32) or 16 (f16) each, 32 bytes apart
+          if (F16) umma_f16(tmem_base, ad0 + 2u * q, bd0 + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+          else umma_tf32(tmem_base, ad0 + 2u * q, bd0 + 2u * q, idesc, (kt > 0 || q > 0) ? 1u : 0u);
+        }
         umma_commit(EMPTY(slot));
       }
       umma_commit(DONE);
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
         tma_load_2d(a_dst + a_stage, &tmB, tap * p.Cin + cb * TM_BK, n0, FULL(slot));
         if (++cb == p.cblocks) { cb = 0; ++tap; }
       } else {
-        tma_load_2d(a_dst, &tmA, kt * TM_BK, m0, FULL(slot));
-        tma_load_2d(a_dst + a_stage, &tmB, kt * TM_BK, n0, FULL(slot));
+        tma_load_2d(a_dst, &tmA, kt * BKE, m0, FULL(slot));
+        tma_load_2d(a_dst + a_stage, &tmB, kt * BKE, n0, FULL(slot));
       }
     }
   }
@@ -166,7 +172,28 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
         crow = p.C + (ps_pix + (long long)(q >> 1) * (2 * p.OW) + (q & 1)) * p.ldc + c;
       }
       const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
-      if (p.vec_store && n0 + c0 + 16 <= p.N) {  // 16-byte stores: a 4-byte store per lane rewrites every sector 8 times
+      if (F16 && (p.out16 || p.act)) {  // (host: N % 16 == 0, rows 16-byte aligned) bias -> residual -> activation -> store
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias) x += __ldg(p.bias + n0 + c0 + j);
+          if (rrow) x += rrow[j];
+          if (p.act == 2) x = x / (1.f + __expf(-1.702f * x));
+          o[j] = x;
+        }
+        if (p.out16) {
+          __half2 h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + (long long)m * p.ldc + n0 + c0);
+          dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+          dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+      } else if (p.vec_store && n0 + c0 + 16 <= p.N) {  // 16-byte stores: a 4-byte store per lane rewrites every sector 8 times
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -418,6 +445,57 @@ AVL_API int avl_set_tc_tma(int on) {
   int old = g_tma_on;
   g_tma_on = on ? 1 : 0;
   return old;
+}
+
+bool make_map16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// fp16 operands (kind::f16, fp32 accumulation): C[M, N] = act(A[M, K] W[N, K]^T + bias + residual), C fp32 or fp16.
+// The CLIP text tower's linears (the reference runs that tower in fp16 on CUDA, policy.py:761).  N % 16 == 0, K % 8 == 0.
+extern "C" int avl_tc_gemm_tma_f16(const void* A, long long lda, const void* W, void* C, long long ldc, int M, int N, int K,
+                                   const float* bias, const float* residual, long long ldr, int act, int out16,
+                                   const int* m_dev, cudaStream_t stream) {
+  if (!g_tma_on || M < 1 || N < 1 || K < 1 || (N & 15) || (K & 7) || (lda & 7) || ((uintptr_t)A & 15) || ((uintptr_t)W & 15) ||
+      ((uintptr_t)C & 15) || (ldc & (out16 ? 7 : 3)) || (bias && ((uintptr_t)bias & 15)) ||
+      (residual && (((uintptr_t)residual & 15) || (ldr & 3))))
+    return AVL_ERR_UNSUPPORTED;
+  TmaArgs p = {};
+  p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.ldr = ldr;
+  p.m_dev = m_dev; p.out16 = out16; p.act = act; p.vec_store = 1;
+  const int mtiles = avl_div_up(M, TM_BM), sms = avl_num_sms();
+  p.bn = 64;
+  for (int bn = 256; bn >= 64; bn >>= 1)
+    if ((long long)mtiles * avl_div_up(N, bn) >= sms) { p.bn = bn; break; }
+  if (m_dev && K >= 512 && mtiles <= 32) p.bn = 64;  // rollout sizes: a latency chain — narrow tiles, deep ring (see the fp32 entry)
+  if (p.bn > N) p.bn = N;
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap ta, tb;
+  if (!make_map16(&ta, A, M, K, lda, TM_BM) || !make_map16(&tb, W, N, K, K, p.bn)) return AVL_ERR_UNSUPPORTED;
+  const size_t stage = (TM_BM + (size_t)p.bn) * 128;
+  p.stages = (int)((100 * 1024) / stage);
+  if (p.stages > TM_MAX_STAGES) p.stages = TM_MAX_STAGES;
+  if (p.stages < 2) p.stages = 2;
+  const size_t smem = (size_t)p.stages * stage;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVL_CUDA_CHECK((cudaFuncSetAttribute(tc_gemm_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    attr_set = true;
+  }
+  dim3 grid(mtiles, avl_div_up(N, p.bn));
+  AVL_LAUNCH_PDL((tc_gemm_tma_kernel<false, true>), grid, TM_THREADS, smem, stream, ta, tb, p);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
 }
 
 // Returns AVL_ERR_UNSUPPORTED (nothing launched) when the operands do not meet TMA's alignment rules (16-byte aligned

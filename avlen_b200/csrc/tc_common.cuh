@@ -98,6 +98,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 A / B, format 0; fp32 accumulate), K-major operands: one MMA covers K = 16
+__device__ __forceinline__ uint32_t umma_idesc_f16_kmajor(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Warp-uniform variants: the WHOLE warp runs the issue loop (so the compiler keeps descriptors and loop counters in
 // uniform registers and emits no per-instruction leader-election loop), and one elected lane — always the same one
 // for a full-warp mask — executes the tcgen05 instruction.

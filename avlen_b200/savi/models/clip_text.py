@@ -22,6 +22,9 @@ _lib.register({
     "avl_clip_text_workspace_bytes": [ctypes.c_int, ctypes.c_int],
     "avl_clip_text_forward": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p],
+    "avl_clip_text_forward_f16": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                  ctypes.c_void_p],
     "avl_clip_text_status": [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
                              ctypes.POINTER(ctypes.c_int)],
 }, {"avl_clip_text_workspace_bytes": ctypes.c_longlong})
@@ -72,6 +75,10 @@ class CLIPTextTower(nn.Module):
         self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
         self.dedupe_zero_rows, self.chunk = dedupe_zero_rows, chunk
         self._ptrs, self._ptr_key, self._ws = None, None, None
+        # fp16 copies of the four linear weights per layer for the kind::f16 tensor-core path (the dtype `clip.load` gives
+        # the tower on CUDA in the reference, policy.py:761); rebuilt when a weight's address or version changes
+        self.half_gemms = True
+        self._w16, self._w16_key, self._ptrs16 = None, None, None
         self.initialize_parameters()
         for p in self.parameters():
             p.requires_grad = False
@@ -100,6 +107,18 @@ class CLIPTextTower(nn.Module):
             self._ptr_key = key
         return self._ptrs
 
+    _W16_SUFFIXES = ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
+
+    def _table16(self):
+        sd = dict(self.named_parameters())
+        ws = [sd[f"transformer.resblocks.{i}.{sfx}"] for i in range(self.layers) for sfx in self._W16_SUFFIXES]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        if key != self._w16_key:
+            self._w16 = [w.detach().half().contiguous() for w in ws]
+            self._ptrs16 = (ctypes.c_void_p * len(ws))(*[w.data_ptr() for w in self._w16])
+            self._w16_key = key
+        return self._ptrs16
+
     @torch.no_grad()
     def encode_text(self, text):
         """text (B, L<=77) integer tokens -> (B, 512) fp32 (clip/model.py encode_text)."""
@@ -112,8 +131,13 @@ class CLIPTextTower(nn.Module):
             nbytes = int(_lib.lib().avl_clip_text_workspace_bytes(n, L))
             if self._ws is None or self._ws.numel() < nbytes:
                 self._ws = torch.empty(nbytes, dtype=torch.uint8, device=text.device)
-            _lib.call("avl_clip_text_forward", n, L, self.vocab_size, self.layers, text[b0:b0 + n].data_ptr(), tab,
-                      out[b0:b0 + n].data_ptr(), self._ws.data_ptr(), int(self.dedupe_zero_rows), _lib.stream())
+            if self.half_gemms:  # (the library still takes the fp32 path below 512 token rows or with tensor cores off)
+                _lib.call("avl_clip_text_forward_f16", n, L, self.vocab_size, self.layers, text[b0:b0 + n].data_ptr(), tab,
+                          ctypes.cast(self._table16(), ctypes.c_void_p), out[b0:b0 + n].data_ptr(), self._ws.data_ptr(),
+                          int(self.dedupe_zero_rows), _lib.stream())
+            else:
+                _lib.call("avl_clip_text_forward", n, L, self.vocab_size, self.layers, text[b0:b0 + n].data_ptr(), tab,
+                          out[b0:b0 + n].data_ptr(), self._ws.data_ptr(), int(self.dedupe_zero_rows), _lib.stream())
             self._last = (n, L)
         return out
 

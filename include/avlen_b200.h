@@ -392,6 +392,11 @@ long long avl_clip_text_workspace_bytes(int B, int L);
 int avl_clip_text_forward(int B, int L, int vocab, int layers, const long long* tokens,
                           const float* const* params /* host array */, float* out, void* workspace, int dedupe,
                           void* stream);
+/* The same tower with its four linears per layer on fp16 operands (tcgen05 kind::f16, fp32 accumulation / residual stream /
+ * LayerNorm and softmax statistics) — the dtype `clip.load` gives the tower on CUDA in the reference (policy.py:761).
+ * params16: 4 * layers device pointers to fp16 copies of (in_proj_weight, out_proj.weight, c_fc.weight, c_proj.weight). */
+int avl_clip_text_forward_f16(int B, int L, int vocab, int layers, const long long* tokens, const float* const* params,
+                              const void* const* params16, float* out, void* workspace, int dedupe, void* stream);
 int avl_clip_text_status(int B, int L, void* workspace, int* n_sequences /* host */, int* n_rows /* host */);
 
 #ifdef __cplusplus

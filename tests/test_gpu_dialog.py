@@ -41,10 +41,11 @@ def _dialogs(n, g, frac=0.5):
     return d
 
 
-@pytest.mark.parametrize("tc,tol", [(0, 1e-3), (1, 2e-2)])
-def test_clip_text_tower_matches_oracle(tc, tol):
-    """12-layer ViT-B/32 text tower, 77 tokens; fp32 SIMT (1e-3) and tcgen05 TF32 GEMMs (the reference runs this tower
-    in fp16 on CUDA; TF32 operands keep 10 mantissa bits like fp16: stated tolerance 2e-2 of the output range)."""
+@pytest.mark.parametrize("tc,half,tol", [(0, False, 1e-3), (1, False, 2e-2), (1, True, 2e-2)])
+def test_clip_text_tower_matches_oracle(tc, half, tol):
+    """12-layer ViT-B/32 text tower, 77 tokens; fp32 SIMT (1e-3), tcgen05 TF32 GEMMs and tcgen05 fp16 GEMMs (kind::f16 — the
+    reference runs this tower in fp16 on CUDA; TF32 operands keep 10 mantissa bits like fp16: stated tolerance 2e-2 of the
+    output range for both)."""
     from avlen_b200 import nn as K
     from avlen_b200.savi.models.clip_text import CLIPTextTower
     K.set_tensor_cores(tc)
@@ -54,6 +55,7 @@ def test_clip_text_tower_matches_oracle(tc, tol):
     t = CLIPTextTower()
     t.load_state_dict(sd)
     t = t.cuda()
+    t.half_gemms = half
     g = torch.Generator().manual_seed(2)
     n = 10 if tc == 0 else 24  # >= 512 token rows so that the TF32 path really runs on the tensor cores
     tokens = _dialogs(n, g, frac=0.7 if tc == 0 else 0.9)
