@@ -147,6 +147,10 @@ class DDPPOTrainer(PPOTrainer):
         local_rank, self.world_rank, self.world_size = init_distrib(cfg.distrib_backend)
         self.device = torch.device("cuda", local_rank)
         torch.cuda.set_device(self.device)
+        if self.world_size > 1 and cfg.host_buffers:
+            # one process per GPU on one host: the native frame-gather threads of all ranks share the host's cores
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", self.world_size))
+            _lib.lib().avl_set_host_gather_threads(max(1, min(8, (os.cpu_count() or 8) // (2 * max(1, local)))))
         torch.manual_seed(cfg.seed + self.world_rank)
         interactive = cfg.policy_type == "interactive"
         if envs is None:
