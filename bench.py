@@ -274,6 +274,17 @@ def kernel_shares(tr, cfg, rollout_steps):
         for _ in range(k):
             tr._collect_rollout_step(tr.rollouts)
     tr.rollouts.step = 0
+    # plain launches for this pass: under programmatic dependent launch a kernel is resident (and counted by CUPTI) while
+    # it still waits for its predecessor, which would credit the waiting time to whichever kernel comes second
+    from avlen_b200 import _lib
+    old_pdl = _lib.lib().avl_set_pdl(0)
+    try:
+        return _kernel_shares_body(tr, cfg, rollout_steps, collect, roll, k)
+    finally:
+        _lib.lib().avl_set_pdl(old_pdl)
+
+
+def _kernel_shares_body(tr, cfg, rollout_steps, collect, roll, k):
     a = collect(roll)
     for _ in range(rollout_steps - k):
         tr._collect_rollout_step(tr.rollouts)
@@ -398,7 +409,9 @@ def run_savi(args):
     roofline = dict(cands[0])
     roofline["others"] = cands[1:]
     roofline["share_source"] = ("CUPTI (torch.profiler) after the timed region: 10 rollout steps scaled to the rollout "
-                                "length + one full update, frozen regime; share of the summed kernel device time")
+                                "length + one full update, frozen regime, plain launches (no programmatic dependent launch: "
+                                "a kernel waiting for its predecessor would be counted as running); share of the summed "
+                                "kernel device time")
     roofline["top_kernels_by_device_time"] = top
     del flush
 

@@ -56,6 +56,20 @@ def main():
             _lib.call("avl_attn_self_fwd", qkv.data_ptr(), off.data_ptr(), B, D, out.data_ptr(), lse.data_ptr(), _lib.stream())
             _lib.call("avl_attn_self_bwd", qkv.data_ptr(), off.data_ptr(), B, D, out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
                       dqkv.data_ptr(), _lib.stream())
+    elif what in ("audio_render", "audio_spec"):
+        import numpy as np
+        from avlen_b200 import synth
+        from avlen_b200.audio import AudioRenderer
+        n = 1024
+        b = synth.make_audio_batch(1, n, fixed_len=16000, silent_frac=0.0, max_seconds=6)
+        r = AudioRenderer(b["sr"])
+        d = {k: torch.from_numpy(v).cuda() for k, v in b.items() if isinstance(v, np.ndarray)}
+        for _ in range(4):
+            if what == "audio_render":
+                r.render(d["sounds"], d["clip_off"], d["index"], d["rirs"], d["rir_off"], d["rir_len"], d["silent"],
+                         want_audiogoal=False)
+            else:
+                r.compute_spectrogram(torch.randn(n, 2, b["sr"], device="cuda"))
     torch.cuda.synchronize()
     print("ok")
 
