@@ -553,3 +553,46 @@ def test_stride2_data_gradient_without_upsampling(shape):
         _lib.lib().avl_set_tc_conv_tma(old)
     assert rel(gx, gx_up) < TOL_TC
     assert int(_lib.lib().avl_tc_conv_tma_count()) - n0 >= 1
+
+
+def test_programmatic_dependent_launch_changes_no_bit():
+    """Kernels of the encoder / transformer chains launched with programmatic stream serialization wait
+    (griddepcontrol.wait) before they touch activations: the policy's outputs must be bit-identical to plain launches,
+    eagerly and when the same step is replayed from a CUDA graph (the rollout's regime)."""
+    from avlen_b200 import _lib
+    from avlen_b200 import nn as K
+    from tests._policy_helpers import make_memory, make_obs, oracle_and_cuda_policies
+    torch.manual_seed(0)
+    _o, p = oracle_and_cuda_policies(5, False)
+    n, M = 64, 300
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}
+    obs = cu(make_obs(n, 11))
+    mem, masks = make_memory(M, n, 276, 12)
+    mem, masks = mem.cuda(), masks.cuda()
+    h, pa, mk = torch.zeros(1, n, 512).cuda(), torch.randint(0, 4, (n, 1)).cuda(), torch.ones(n, 1).cuda()
+    outs = {}
+    for pdl in (0, 1):
+        old = _lib.lib().avl_set_pdl(pdl)
+        try:
+            with torch.no_grad():
+                for _ in range(2):  # (second call: the per-network graphs of the fused ResNets replay)
+                    v, a, lp, _, x, pr = p.act(obs, h, pa, mk, mem, masks, deterministic=True)
+                torch.cuda.synchronize()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    g = torch.cuda.CUDAGraph()
+                    g.capture_begin(capture_error_mode="relaxed")
+                    vg, ag, lpg, _, xg, prg = p.act(obs, h, pa, mk, mem, masks, deterministic=True)
+                    K.sync_pending()
+                    g.capture_end()
+                    g.replay()
+                    g.replay()
+                s.synchronize()
+            outs[pdl] = [t.clone() for t in (v, a, lp, x, pr, vg, ag, lpg, xg, prg)]
+        finally:
+            _lib.lib().avl_set_pdl(old)
+    for t0, t1 in zip(outs[0], outs[1]):
+        assert torch.equal(t0, t1)
+    for i in range(5):  # graph replay == eager, in both modes
+        assert torch.equal(outs[1][i], outs[1][i + 5])
