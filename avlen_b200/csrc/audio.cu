@@ -105,16 +105,16 @@ __device__ __forceinline__ void tw_powers(cf w, cf (&t)[16]) {
 }
 
 // One radix-16 butterfly of an in-place DIF stage on a block of size n = 16*s:
-//   buf[base + j + q*s] <- (sum_m buf[base + j + m*s] w16^{mq}) * w_n^{jq}
-// PADF selects the padding function (big buffer / frame buffer).
-template <bool BIG>
-__device__ __forceinline__ int padx(int p) { return BIG ? padi(p) : padf(p); }
-
-template <bool BIG>
-__device__ __forceinline__ void r16_fwd(cf* buf, int base, int j, int s, bool twiddle, cf w) {
+//   buf[first + q*s] <- (sum_m buf[first + m*s] w16^{mq}) * w^q
+// addressed through the PADDED index of its first point and a compile-time padded stride SP: for every stage of the two
+// transforms the padding functions are linear along a butterfly's 16 points (the stride is a multiple of the padding
+// period, or the points stay inside one period), so padi / padf is evaluated once per butterfly instead of per point —
+// the per-point shifts and adds were a third of the kernel's instructions (profiles/r02_audio_render_ncu_full.txt).
+template <int SP>
+__device__ __forceinline__ void r16_fwd(cf* buf, int p0, bool twiddle, cf w) {
   cf x[16];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) x[m] = buf[padx<BIG>(base + j + m * s)];
+  for (int m = 0; m < 16; ++m) x[m] = buf[p0 + m * SP];
   fft16<-1>(x);
   if (twiddle) {
     cf t[16];
@@ -123,15 +123,15 @@ __device__ __forceinline__ void r16_fwd(cf* buf, int base, int j, int s, bool tw
     for (int q = 1; q < 16; ++q) x[o16(q)] = cmul(x[o16(q)], t[q]);
   }
 #pragma unroll
-  for (int q = 0; q < 16; ++q) buf[padx<BIG>(base + j + q * s)] = x[o16(q)];
+  for (int q = 0; q < 16; ++q) buf[p0 + q * SP] = x[o16(q)];
 }
 
 // Inverse of r16_fwd up to the factor 16.
-template <bool BIG>
-__device__ __forceinline__ void r16_inv(cf* buf, int base, int j, int s, bool twiddle, cf w) {
+template <int SP>
+__device__ __forceinline__ void r16_inv(cf* buf, int p0, bool twiddle, cf w) {
   cf x[16];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) x[q] = buf[padx<BIG>(base + j + q * s)];
+  for (int q = 0; q < 16; ++q) x[q] = buf[p0 + q * SP];
   if (twiddle) {
     cf t[16];
     tw_powers(w, t);
@@ -140,8 +140,12 @@ __device__ __forceinline__ void r16_inv(cf* buf, int base, int j, int s, bool tw
   }
   fft16<+1>(x);
 #pragma unroll
-  for (int m = 0; m < 16; ++m) buf[padx<BIG>(base + j + m * s)] = x[o16(m)];
+  for (int m = 0; m < 16; ++m) buf[p0 + m * SP] = x[o16(m)];
 }
+
+// padded strides of the big buffer (padi(p) = p + p/16 + p/256): 4096 -> 4368, 256 -> 273, 16 -> 17 (inside one block of
+// 256), 1 -> 1 (inside one block of 16); of a frame buffer (padf(p) = p + p/16): 16 -> 17, 1 -> 1
+constexpr int kSP4096 = 4096 + 256 + 16, kSP256 = 256 + 16 + 1, kSP16 = 17;
 
 // tw[k] = exp(-2*pi*i*k/32768), k in [0, 16384]
 // In-place DIF forward FFT of the 16384-point buffer; radices 4,16,16,16.
@@ -149,57 +153,59 @@ __device__ __forceinline__ void r16_inv(cf* buf, int base, int j, int s, bool tw
 __device__ void fft_big_fwd(cf* buf, const cf* __restrict__ tw) {
   const int tid = threadIdx.x;
   for (int u = tid; u < 4096; u += kThreads) {
-    cf a = buf[padi(u)], b = buf[padi(u + 4096)], c = buf[padi(u + 8192)], d = buf[padi(u + 12288)];
+    const int p = padi(u);
+    cf a = buf[p], b = buf[p + kSP4096], c = buf[p + 2 * kSP4096], d = buf[p + 3 * kSP4096];
     fft4<-1>(a, b, c, d);
     cf w1 = tw[2 * u];
     cf w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-    buf[padi(u)] = a;
-    buf[padi(u + 4096)] = cmul(b, w1);
-    buf[padi(u + 8192)] = cmul(c, w2);
-    buf[padi(u + 12288)] = cmul(d, w3);
+    buf[p] = a;
+    buf[p + kSP4096] = cmul(b, w1);
+    buf[p + 2 * kSP4096] = cmul(c, w2);
+    buf[p + 3 * kSP4096] = cmul(d, w3);
   }
   __syncthreads();
   for (int u = tid; u < 1024; u += kThreads) {
     int b = u >> 8, j = u & 255;
-    r16_fwd<true>(buf, b * 4096, j, 256, true, tw[8 * j]);  // w_4096^j
+    r16_fwd<kSP256>(buf, padi(b * 4096 + j), true, tw[8 * j]);  // w_4096^j
   }
   __syncthreads();
   for (int u = tid; u < 1024; u += kThreads) {
     int b = u >> 4, j = u & 15;
-    r16_fwd<true>(buf, b * 256, j, 16, true, tw[128 * j]);  // w_256^j
+    r16_fwd<kSP16>(buf, padi(b * 256 + j), true, tw[128 * j]);  // w_256^j
   }
   __syncthreads();
-  for (int u = tid; u < 1024; u += kThreads) r16_fwd<true>(buf, u * 16, 0, 1, false, make_float2(1.f, 0.f));
+  for (int u = tid; u < 1024; u += kThreads) r16_fwd<1>(buf, padi(u * 16), false, make_float2(1.f, 0.f));
   __syncthreads();
 }
 
 // Exact inverse of fft_big_fwd up to the factor 16384 (digit-reversed in, natural out).
 __device__ void fft_big_inv(cf* buf, const cf* __restrict__ tw) {
   const int tid = threadIdx.x;
-  for (int u = tid; u < 1024; u += kThreads) r16_inv<true>(buf, u * 16, 0, 1, false, make_float2(1.f, 0.f));
+  for (int u = tid; u < 1024; u += kThreads) r16_inv<1>(buf, padi(u * 16), false, make_float2(1.f, 0.f));
   __syncthreads();
   for (int u = tid; u < 1024; u += kThreads) {
     int b = u >> 4, j = u & 15;
-    r16_inv<true>(buf, b * 256, j, 16, true, tw[128 * j]);
+    r16_inv<kSP16>(buf, padi(b * 256 + j), true, tw[128 * j]);
   }
   __syncthreads();
   for (int u = tid; u < 1024; u += kThreads) {
     int b = u >> 8, j = u & 255;
-    r16_inv<true>(buf, b * 4096, j, 256, true, tw[8 * j]);
+    r16_inv<kSP256>(buf, padi(b * 4096 + j), true, tw[8 * j]);
   }
   __syncthreads();
   for (int u = tid; u < 4096; u += kThreads) {
+    const int p = padi(u);
     cf w1 = tw[2 * u];
     cf w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-    cf a = buf[padi(u)];
-    cf b = cmulc(buf[padi(u + 4096)], w1);
-    cf c = cmulc(buf[padi(u + 8192)], w2);
-    cf d = cmulc(buf[padi(u + 12288)], w3);
+    cf a = buf[p];
+    cf b = cmulc(buf[p + kSP4096], w1);
+    cf c = cmulc(buf[p + 2 * kSP4096], w2);
+    cf d = cmulc(buf[p + 3 * kSP4096], w3);
     fft4<+1>(a, b, c, d);
-    buf[padi(u)] = a;
-    buf[padi(u + 4096)] = b;
-    buf[padi(u + 8192)] = c;
-    buf[padi(u + 12288)] = d;
+    buf[p] = a;
+    buf[p + kSP4096] = b;
+    buf[p + 2 * kSP4096] = c;
+    buf[p + 3 * kSP4096] = d;
   }
   __syncthreads();
 }
@@ -335,10 +341,13 @@ __device__ void spectral_multiply(cf* buf, const cf* __restrict__ tw, const cf* 
 struct SmemSamples {  // waveform held in the big FFT buffer (packed, padded)
   const float* f;
   __device__ __forceinline__ float operator()(int i) const { return f[2 * padi(i >> 1) + (i & 1)]; }
+  // samples (i, i + 1), i even: one packed element
+  __device__ __forceinline__ float2 pair(int i) const { return reinterpret_cast<const float2*>(f)[padi(i >> 1)]; }
 };
-struct GmemSamples {
+struct GmemSamples {  // rows of an (N, 2, sr) tensor: 8-byte aligned when sr is even (checked by the host)
   const float* p;
   __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+  __device__ __forceinline__ float2 pair(int i) const { return __ldg(reinterpret_cast<const float2*>(p + i)); }
 };
 
 // STFT -> |.| -> 4x4 zero-padded block mean -> log1p for one channel.
@@ -351,6 +360,7 @@ __device__ void stft_channel(const Samples& y, int sr, cf* fb, const float* win,
   const int half = lane >> 4, l = lane & 15;
   const int n_frames = 1 + sr / kHop;
   const int n_tb = (n_frames + 3) >> 2;
+  const bool pair_ok = (sr & 1) == 0;  // rows of the waveform tensor stay 8-byte aligned
   cf* z = fb + (warp * 2 + half) * kFrameElems;
   const int rounds = (n_tb + 7) >> 3;
   for (int r = 0; r < rounds; ++r) {
@@ -360,27 +370,32 @@ __device__ void stft_channel(const Samples& y, int sr, cf* fb, const float* win,
     const int start = kHop * f - kNfft / 2;
 #pragma unroll 4
     for (int t = 0; t < 16; ++t) {
-      int j = l + 16 * t;
-      float v[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int i = 2 * j + h;
-        float x = 0.f;
-        if (valid && i >= (kNfft - kWin) / 2 && i < (kNfft + kWin) / 2) {
-          int idx = start + i;
-          if (idx < 0) idx = -idx;
-          if (idx >= sr) idx = 2 * (sr - 1) - idx;
-          x = win[i] * y(idx);
+      const int j = l + 16 * t;
+      const int i = 2 * j;  // even; the window's support [56, 456) has even bounds, so i and i + 1 are in or out together
+      float v0 = 0.f, v1 = 0.f;
+      if (valid && i >= (kNfft - kWin) / 2 && i < (kNfft + kWin) / 2) {
+        const int idx = start + i;  // even (start = 160 f - 256)
+        if (pair_ok && idx >= 0 && idx + 1 < sr) {  // interior: one 8-byte load for the two samples
+          const float2 s2 = y.pair(idx);
+          v0 = win[i] * s2.x;
+          v1 = win[i + 1] * s2.y;
+        } else {  // reflect padding at the clip's ends
+          int i0 = idx, i1 = idx + 1;
+          if (i0 < 0) i0 = -i0;
+          if (i0 >= sr) i0 = 2 * (sr - 1) - i0;
+          if (i1 < 0) i1 = -i1;
+          if (i1 >= sr) i1 = 2 * (sr - 1) - i1;
+          v0 = win[i] * y(i0);
+          v1 = win[i + 1] * y(i1);
         }
-        v[h] = x;
       }
-      z[padf(j)] = make_float2(v[0], v[1]);
+      z[j + (j >> 4)] = make_float2(v0, v1);
     }
     __syncwarp();
     // 256-point complex FFT = 16 x 16, one radix-16 butterfly per lane per stage
-    r16_fwd<false>(z, 0, l, 16, true, tw[128 * l]);  // w_256^l
+    r16_fwd<kSP16>(z, l, true, tw[128 * l]);  // points l + 16 m -> padf = l + 17 m;  w_256^l
     __syncwarp();
-    r16_fwd<false>(z, 16 * l, 0, 1, false, make_float2(1.f, 0.f));
+    r16_fwd<1>(z, 17 * l, false, make_float2(1.f, 0.f));  // points 16 l + m -> padf = 17 l + m
     __syncwarp();
     // real spectrum magnitudes: bins k and 256-k, k = 1..127 (8 per lane), plus 0, 128, 256
     float mg[18];
@@ -575,6 +590,7 @@ spectrogram_kernel(const float* audio, int n, int sr, float* spectrogram, const 
 struct GmemSamplesCg {  // written earlier by this CTA: coherent loads (not the read-only path)
   const float* p;
   __device__ __forceinline__ float operator()(int i) const { return __ldcg(p + i); }
+  __device__ __forceinline__ float2 pair(int i) const { return __ldcg(reinterpret_cast<const float2*>(p + i)); }
 };
 
 // packed window j of the source: see the formulas above.  lim = first sample index that must read as zero (base + sr)
