@@ -388,10 +388,24 @@ class AudioNavSMTNet(Net):
             self._observation_features_into(x, observations, visual=True, rest=False)
         if between is not None:
             between()
-        if visual_event is not None:
-            stream.wait_stream(main)
-        with torch.cuda.stream(stream):
+        # the audio CNN and the pose / category columns only need what the main stream has produced (the spectrogram):
+        # on a stream of their own they run NEXT TO the visual ResNet-18 chains instead of behind them (disjoint columns
+        # of x); the prefetch is complete when both streams are
+        rest = self.__dict__.get("_rest_stream")
+        if rest is None:
+            rest = self.__dict__["_rest_stream"] = torch.cuda.Stream()
+        rest.wait_stream(main)
+        x.record_stream(rest)
+        for k in (SPECTROGRAM, POSE, CATEGORY):
+            v = observations.get(k)
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(rest)
+        with torch.cuda.stream(rest):
             self._observation_features_into(x, observations, visual=False, rest=True)
+            ev_rest = torch.cuda.Event()
+            ev_rest.record(rest)
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev_rest)
             ev = torch.cuda.Event()
             ev.record(stream)
         self._prefetched()[key] = (x, ev)
