@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_tma_splitk_kernel(const __
 static int g_tc_ca = 1;
 static int g_tc_splitk = 1;
 static int g_tc_splitk_cluster = 1;
+static int g_tc_splitk_fill = 50;  // split-K aims at this many CTAs per 100 SMs (see avl_set_tc_splitk_fill)
 static int g_tc_cluster16 = -1;  // -1: not probed yet; 0: clusters of 16 CTAs unavailable; 1: available
 static int g_tc_swz = 1;
 static int g_tc_stages = 0;  // 0: automatic; 3 / 4: forced ring depth (diagnostic)
@@ -506,7 +507,7 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s, bool want_tma = false
     // split K over blockIdx.z so that ~2 CTAs per SM share the operand traffic; partial sums meet in C by atomics.
     if (p.bn > 64) p.bn = 64;
     const int ctas = mtiles * avl_div_up(p.N, p.bn);
-    int splits = (2 * sms + ctas - 1) / ctas;
+    int splits = (g_tc_splitk_fill * sms / 100 + ctas - 1) / ctas;
     if (splits > KT / 4) splits = KT / 4;
     if (splits > 1 && g_tc_splitk_cluster && p.swz) {
       // the slices of one tile as one cluster (portable size <= 8, a divisor of the 128 tile rows)
@@ -639,6 +640,17 @@ AVL_API int avl_set_tc_stages(int stages) {
   avl_bump_config_epoch();
   int old = g_tc_stages;
   g_tc_stages = stages;
+  return old;
+}
+
+// Split-K aims at `percent` CTAs per 100 SMs.  Default 50: a rollout step runs four to eight encoder chains next to each
+// other and is bound by SM time (shared-memory slots), not by one kernel's latency — measured on the whole step
+// (bench.py, 64 envs): 200 (two CTAs per SM, what a kernel running alone prefers) 53.5k env-steps/s, 100 56.3k, 60 56.9k,
+// 40 57.9k, 25 57.7k; the isolated launch latencies stay within 10 % (tools/small_batch_conv_probe.py).  Returns old.
+AVL_API int avl_set_tc_splitk_fill(int percent) {
+  avl_bump_config_epoch();
+  int old = g_tc_splitk_fill;
+  if (percent >= 25 && percent <= 400) g_tc_splitk_fill = percent;
   return old;
 }
 
