@@ -34,6 +34,10 @@ _SIGNATURES = {
     "avl_audio_render_spectrogram": [P, I, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "avl_audio_spectrogram": [P, I, P, P, P],
     "avl_set_audio_channel_split": [I],
+    "avl_audio_spectrum_bins": [],
+    "avl_audio_rir_spectra": [P, I, P, P, P, P, P],
+    "avl_audio_source_spectra": [P, I, P, P, P, P, P],
+    "avl_audio_render_spectral": [P, I, P, P, P, P, P, P, P, P, P, P, P],
     "avl_gae_f64": [P, P, P, P, P, I, I, I, D, D, P],
     "avl_advantages": [P, P, P, I, I, F, P],
     "avl_categorical_act": [P, P, I, I, P, P, P, P],

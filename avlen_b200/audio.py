@@ -83,6 +83,46 @@ class AudioRenderer:
                   _lib.dptr(d_rir_len, i32), _lib.fptr(ag), _lib.fptr(spec), _lib.stream())
         return ag, spec
 
+    # ---- spectral asset banks: forward transforms made once, renderings need one inverse transform per ear ----
+    @property
+    def spectrum_bins(self) -> int:
+        return int(_lib.lib().avl_audio_spectrum_bins())
+
+    def rir_spectra(self, rirs, rir_off, rir_len, out=None):
+        """Spectra of both ears of n RIRs of a packed bank: (n, 2, bins, 2) float32 (re, im); 256 KB per RIR."""
+        n = int(rir_off.shape[0])
+        spec = out if out is not None else torch.empty((n, 2, self.spectrum_bins, 2), device=self.device)
+        _lib.call("avl_audio_rir_spectra", self._h, n, _lib.fptr(rirs), _lib.dptr(rir_off, torch.int64),
+                  _lib.dptr(rir_len, torch.int32), _lib.fptr(spec), _lib.stream())
+        return spec
+
+    def source_spectra(self, sounds, clip_off, index, out=None):
+        """Spectra of n (clip, second) pairs of a sound bank: (n, bins, 2) float32; each row holds the second together
+        with the history a RIR of the maximum length reaches back to (simulator.py:661-681 reduce to this)."""
+        n = int(clip_off.shape[0])
+        spec = out if out is not None else torch.empty((n, self.spectrum_bins, 2), device=self.device)
+        _lib.call("avl_audio_source_spectra", self._h, n, _lib.fptr(sounds), _lib.dptr(clip_off, torch.int64),
+                  _lib.dptr(index, torch.int32), _lib.fptr(spec), _lib.stream())
+        return spec
+
+    def render_spectral(self, src_spectra, src_row0, index, rir_spectra, rir_row, silent, d_src_row0=None,
+                        d_rir_row=None, want_audiogoal=True, out_audiogoal=None, out_spectrogram=None):
+        """:meth:`render` on the spectral banks: env i renders source row ``src_row0[i] + index[i]`` through RIR row
+        ``rir_row[i]`` (< 0: empty file); the distractor pair renders second 0 of its clip."""
+        n = int(rir_row.shape[0])
+        dev = self.device
+        spec = out_spectrogram if out_spectrogram is not None else torch.empty(
+            (n,) + spectrogram_shape(self.sr), device=dev, dtype=torch.float32)
+        ag = None
+        if want_audiogoal:
+            ag = out_audiogoal if out_audiogoal is not None else torch.empty(
+                (n, 2, self.sr), device=dev, dtype=torch.float32)
+        i64, i32 = torch.int64, torch.int32
+        _lib.call("avl_audio_render_spectral", self._h, n, _lib.fptr(src_spectra), _lib.dptr(src_row0, i64),
+                  _lib.dptr(index, i32), _lib.fptr(rir_spectra), _lib.dptr(rir_row, i64), _lib.dptr(silent, i32),
+                  _lib.dptr(d_src_row0, i64), _lib.dptr(d_rir_row, i64), _lib.fptr(ag), _lib.fptr(spec), _lib.stream())
+        return ag, spec
+
     def compute_spectrogram(self, audio, out=None):
         """Row B alone for a batch: (N, 2, sr) float32 CUDA tensor -> (N, 65, 26, 2)."""
         n = int(audio.shape[0])
@@ -162,6 +202,17 @@ class RirBank:
         rirs = np.concatenate(chunks, 0) if at else np.zeros((1, 2), np.float32)
         return cls(rirs, off, ln, device)
 
+    def spectral(self, renderer: AudioRenderer):
+        """Spectral form of the bank: ``(spectra (4 V V, 2, bins, 2), row (4, V, V) int64)`` with row -1 for empty /
+        unreadable files — 256 KB per RIR (0.8 GB for a 28-node scene), built once per scene."""
+        if getattr(self, "_spectral", None) is None:
+            off, ln = self.off.reshape(-1), self.len.reshape(-1)
+            spectra = renderer.rir_spectra(self.rirs, off, ln)
+            row = torch.arange(off.numel(), device=self.device, dtype=torch.int64)
+            row = torch.where(ln > 0, row, torch.full_like(row, -1)).reshape(self.off.shape)
+            self._spectral = (spectra, row)
+        return self._spectral
+
     def save(self, path, half=False):
         np.savez_compressed(path, rirs=self.rirs.cpu().numpy().astype(np.float16 if half else np.float32),
                             off=self.off.cpu().numpy(), len=self.len.cpu().numpy())
@@ -170,6 +221,26 @@ class RirBank:
     def load(cls, path, device="cuda"):
         z = np.load(path)
         return cls(z["rirs"].astype(np.float32), z["off"], z["len"], device)
+
+
+class SpectralSoundBank:
+    """Every second of every clip of a sound bank as a resident spectrum row (128 KB each): row ``row0[clip] + second``.
+    The reference slices the waveform per step (simulator.py:661-681); the rows are what those slices transform to."""
+
+    def __init__(self, renderer: AudioRenderer, sounds, clip_off_all, clip_len_all):
+        sr = renderer.sr
+        clip_off_all = np.asarray(clip_off_all, np.int64)
+        secs = np.maximum(np.asarray(clip_len_all, np.int64) // sr, 1)
+        self.row0_np = np.concatenate([[0], np.cumsum(secs)[:-1]]).astype(np.int64)
+        dev = renderer.device
+        off = torch.from_numpy(np.repeat(clip_off_all, secs)).to(dev)
+        idx = torch.from_numpy(np.concatenate([np.arange(k, dtype=np.int32) for k in secs])).to(dev)
+        self.spectra = renderer.source_spectra(sounds, off, idx)
+        self.row0 = torch.from_numpy(self.row0_np).to(dev)
+
+    def rows(self, clip_id):
+        """(N,) int64 row of second 0 of each env's clip."""
+        return self.row0[torch.as_tensor(clip_id, device=self.row0.device, dtype=torch.int64)].contiguous()
 
 
 class SpectrogramCache:

@@ -350,9 +350,37 @@ struct GmemSamples {  // rows of an (N, 2, sr) tensor: 8-byte aligned when sr is
   __device__ __forceinline__ float2 pair(int i) const { return __ldg(reinterpret_cast<const float2*>(p + i)); }
 };
 
+// Shared-memory tables behind the 512-float window (filled by fill_window):
+//   st1[q * 16 + l] = w_256^(l q)   the twiddles of the first radix-16 stage of a frame (constant per lane)
+//   stw[k]          = w_512^k       k = 0 .. 128, the real-spectrum unpacking factors
+constexpr int kStftTabElems = 256 + 136;
+constexpr size_t kStftSmem = kNfft * sizeof(float) + kStftTabElems * sizeof(cf);
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// r16_fwd with the twiddles w^q read from a table (stride 16 between q's)
+template <int SP>
+__device__ __forceinline__ void r16_fwd_tab(cf* buf, int p0, const cf* tab) {
+  cf x[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) x[m] = buf[p0 + m * SP];
+  fft16<-1>(x);
+#pragma unroll
+  for (int q = 1; q < 16; ++q) x[o16(q)] = cmul(x[o16(q)], tab[16 * q]);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[p0 + q * SP] = x[o16(q)];
+}
+
 // STFT -> |.| -> 4x4 zero-padded block mean -> log1p for one channel.
-// fb: per-warp frame buffers (2 * kFrameElems float2 per warp); win: 512-float window in smem.
+// fb: per-warp frame buffers (2 * kFrameElems float2 per warp); win: 512-float window in smem followed by the tables above.
 // out: spectrogram base pointer for this env, layout (65, TB, 2); writes channel c.
+// Warp-local: a warp owns whole time blocks (4 frames, two at a time — one per half-warp), sums the magnitudes of its
+// four frames in registers and pools the 65 frequency blocks itself, so the warps of a CTA run out of phase and hide
+// one another's latencies; the only CTA-wide barrier is the one that releases the waveform at the end.
 template <class Samples>
 __device__ void stft_channel(const Samples& y, int sr, cf* fb, const float* win,
                              const cf* __restrict__ tw, float* out, int c) {
@@ -361,104 +389,124 @@ __device__ void stft_channel(const Samples& y, int sr, cf* fb, const float* win,
   const int n_frames = 1 + sr / kHop;
   const int n_tb = (n_frames + 3) >> 2;
   const bool pair_ok = (sr & 1) == 0;  // rows of the waveform tensor stay 8-byte aligned
+  const float2* win2 = reinterpret_cast<const float2*>(win);
+  const cf* st1 = reinterpret_cast<const cf*>(win + kNfft) + l;
+  const cf* stw = reinterpret_cast<const cf*>(win + kNfft) + 256;
   cf* z = fb + (warp * 2 + half) * kFrameElems;
-  const int rounds = (n_tb + 7) >> 3;
-  for (int r = 0; r < rounds; ++r) {
-    const int f = 32 * r + 2 * warp + half;
-    const bool valid = f < n_frames;
-    // windowed frame, packed as 256 complex
-    const int start = kHop * f - kNfft / 2;
-#pragma unroll 4
-    for (int t = 0; t < 16; ++t) {
-      const int j = l + 16 * t;
-      const int i = 2 * j;  // even; the window's support [56, 456) has even bounds, so i and i + 1 are in or out together
-      float v0 = 0.f, v1 = 0.f;
-      if (valid && i >= (kNfft - kWin) / 2 && i < (kNfft + kWin) / 2) {
-        const int idx = start + i;  // even (start = 160 f - 256)
-        if (pair_ok && idx >= 0 && idx + 1 < sr) {  // interior: one 8-byte load for the two samples
-          const float2 s2 = y.pair(idx);
-          v0 = win[i] * s2.x;
-          v1 = win[i + 1] * s2.y;
-        } else {  // reflect padding at the clip's ends
-          int i0 = idx, i1 = idx + 1;
-          if (i0 < 0) i0 = -i0;
-          if (i0 >= sr) i0 = 2 * (sr - 1) - i0;
-          if (i1 < 0) i1 = -i1;
-          if (i1 >= sr) i1 = 2 * (sr - 1) - i1;
-          v0 = win[i] * y(i0);
-          v1 = win[i + 1] * y(i1);
-        }
-      }
-      z[j + (j >> 4)] = make_float2(v0, v1);
-    }
-    __syncwarp();
-    // 256-point complex FFT = 16 x 16, one radix-16 butterfly per lane per stage
-    r16_fwd<kSP16>(z, l, true, tw[128 * l]);  // points l + 16 m -> padf = l + 17 m;  w_256^l
-    __syncwarp();
-    r16_fwd<1>(z, 17 * l, false, make_float2(1.f, 0.f));  // points 16 l + m -> padf = 17 l + m
-    __syncwarp();
-    // real spectrum magnitudes: bins k and 256-k, k = 1..127 (8 per lane), plus 0, 128, 256
-    float mg[18];
+  float* mag = reinterpret_cast<float*>(fb + warp * 2 * kFrameElems);  // 257 floats, after the frames are consumed
+  (void)tw;
+  for (int tb = warp; tb < n_tb; tb += kWarps) {
+    float acc[18];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      int k = 1 + l + 16 * t;  // 1..128
-      int km = 256 - k;
-      cf zk = z[padf(((k & 15) << 4) | (k >> 4))];
-      cf zm = z[padf(((km & 15) << 4) | (km >> 4))];
-      cf wk = tw[64 * k];  // exp(-2 pi i k / 512)
-      cf xk = unpack_bin(zk, cconj(zm), wk);
-      cf xm = unpack_bin(zm, cconj(zk), make_float2(-wk.x, wk.y));
-      mg[2 * t] = sqrtf(fmaf(xk.x, xk.x, xk.y * xk.y));
-      mg[2 * t + 1] = sqrtf(fmaf(xm.x, xm.x, xm.y * xm.y));
-    }
-    cf z0 = z[0];
-    mg[16] = fabsf(z0.x + z0.y);
-    mg[17] = fabsf(z0.x - z0.y);
-    __syncwarp();
-    float* mag = reinterpret_cast<float*>(z);  // 257 floats inside this frame's 544-float buffer
+    for (int i = 0; i < 18; ++i) acc[i] = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (4 * tb + 2 * pass >= n_frames) break;  // warp-uniform: both frames of the pass are padding
+      const int f = 4 * tb + 2 * pass + half;
+      const bool valid = f < n_frames;
+      // windowed frame, packed as 256 complex: element j = (samples 2j, 2j+1); the window's support is j in [28, 228)
+      const int start = kHop * f - kNfft / 2;  // even
+      const bool interior = valid && pair_ok && start + (kNfft - kWin) / 2 >= 0 && start + (kNfft + kWin) / 2 <= sr;
+      if (interior) {
+        z[l] = make_float2(0.f, 0.f);
+        z[l + 17 * 15] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      int k = 1 + l + 16 * t;
-      mag[k] = mg[2 * t];
-      if (k != 128) mag[256 - k] = mg[2 * t + 1];
-    }
-    if (l == 0) {
-      mag[0] = mg[16];
-      mag[256] = mg[17];
-    }
-    __syncthreads();
-    // 4x4 block mean (zero padded) + log1p for the 8 time blocks of this round
-    for (int o = threadIdx.x; o < 8 * kFB; o += kThreads) {
-      int gl = o / kFB, kb = o - gl * kFB;
-      int tb = 8 * r + gl;
-      if (tb < n_tb) {
-        float s = 0.f;
-#pragma unroll
-        for (int df = 0; df < 4; ++df) {
-          int fl = 4 * gl + df;  // frame index local to the round: warp = fl/2, half = fl&1
-          if (32 * r + fl < n_frames) {
-            const float* m = reinterpret_cast<const float*>(fb + fl * kFrameElems);
-#pragma unroll
-            for (int dk = 0; dk < 4; ++dk) {
-              int k = 4 * kb + dk;
-              if (k < kBins) s += m[k];
-            }
+        for (int t = 1; t < 15; ++t) {
+          const int j = l + 16 * t;
+          float2 v = make_float2(0.f, 0.f);
+          if ((t > 1 && t < 14) || (t == 1 && l >= 12) || (t == 14 && l < 4)) {
+            const float2 s2 = y.pair(start + 2 * j), w2 = win2[j];
+            v = make_float2(w2.x * s2.x, w2.y * s2.y);
           }
+          z[l + 17 * t] = v;
         }
-        out[(kb * n_tb + tb) * 2 + c] = log1pf(s * 0.0625f);
+      } else {
+#pragma unroll 4
+        for (int t = 0; t < 16; ++t) {
+          const int j = l + 16 * t;
+          const int i = 2 * j;
+          float v0 = 0.f, v1 = 0.f;
+          if (valid && i >= (kNfft - kWin) / 2 && i < (kNfft + kWin) / 2) {  // reflect padding at the clip's ends
+            int i0 = start + i, i1 = start + i + 1;
+            if (i0 < 0) i0 = -i0;
+            if (i0 >= sr) i0 = 2 * (sr - 1) - i0;
+            if (i1 < 0) i1 = -i1;
+            if (i1 >= sr) i1 = 2 * (sr - 1) - i1;
+            v0 = win[i] * y(i0);
+            v1 = win[i + 1] * y(i1);
+          }
+          z[l + 17 * t] = make_float2(v0, v1);
+        }
+      }
+      __syncwarp();
+      // 256-point complex FFT = 16 x 16, one radix-16 butterfly per lane per stage
+      r16_fwd_tab<kSP16>(z, l, st1);  // points l + 16 m -> padf = l + 17 m;  twiddles w_256^(l q)
+      __syncwarp();
+      r16_fwd<1>(z, 17 * l, false, make_float2(1.f, 0.f));  // points 16 l + m -> padf = 17 l + m
+      __syncwarp();
+      // real spectrum magnitudes: bins k and 256-k, k = 1..128 (8 per lane), plus 0 and 256
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = 1 + l + 16 * t;  // 1..128
+        const int km = 256 - k;
+        const cf zk = z[padf(((k & 15) << 4) | (k >> 4))];
+        const cf zm = z[padf(((km & 15) << 4) | (km >> 4))];
+        const cf wk = stw[k];  // exp(-2 pi i k / 512)
+        const cf xk = unpack_bin(zk, cconj(zm), wk);
+        const cf xm = unpack_bin(zm, cconj(zk), make_float2(-wk.x, wk.y));
+        acc[2 * t] += sqrt_approx(fmaf(xk.x, xk.x, xk.y * xk.y));
+        acc[2 * t + 1] += sqrt_approx(fmaf(xm.x, xm.x, xm.y * xm.y));
+      }
+      const cf z0 = z[0];
+      acc[16] += fabsf(z0.x + z0.y);
+      acc[17] += fabsf(z0.x - z0.y);
+      __syncwarp();
+    }
+    // the two half-warps hold the sums of frames (0, 2) and (1, 3) of the block
+#pragma unroll
+    for (int i = 0; i < 18; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    if (half == 0) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int k = 1 + l + 16 * t;
+        mag[k] = acc[2 * t];
+        if (k != 128) mag[256 - k] = acc[2 * t + 1];
+      }
+      if (l == 0) {
+        mag[0] = acc[16];
+        mag[256] = acc[17];
       }
     }
-    __syncthreads();
+    __syncwarp();
+    // 4x4 block mean (zero padded in both directions) + log1p
+    for (int kb = lane; kb < kFB; kb += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int dk = 0; dk < 4; ++dk) {
+        const int k = 4 * kb + dk;
+        if (k < kBins) s += mag[k];
+      }
+      out[(kb * n_tb + tb) * 2 + c] = log1pf(s * 0.0625f);
+    }
+    __syncwarp();
   }
+  __syncthreads();  // every warp is done with the waveform and the frame buffers
 }
 
-__device__ void fill_window(float* win) {
+__device__ void fill_window(float* win, const cf* __restrict__ tw) {
   for (int i = threadIdx.x; i < kNfft; i += kThreads) {
     int n = i - (kNfft - kWin) / 2;
     float w = 0.f;
     if (n >= 0 && n < kWin) w = (float)(0.5 - 0.5 * cospi(2.0 * (double)n / (double)kWin));
     win[i] = w;
   }
+  // tw[k] = exp(-2 pi i k / 32768):  w_256^m = tw[128 m],  w_512^k = tw[64 k]
+  cf* tab = reinterpret_cast<cf*>(win + kNfft);
+  for (int i = threadIdx.x; i < 256; i += kThreads) {
+    const int m = (i >> 4) * (i & 15);  // <= 225; the table stops at half a turn: w_256^m = -w_256^(m - 128)
+    const cf w = tw[128 * (m & 127)];
+    tab[i] = m < 128 ? w : make_float2(-w.x, -w.y);
+  }
+  for (int i = threadIdx.x; i <= 128; i += kThreads) tab[256 + i] = tw[64 * i];
 }
 
 struct RenderArgs {
@@ -489,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) audio_render_kernel(RenderArgs a)
   cf* buf = reinterpret_cast<cf*>(smem_raw);
   cf* fb = buf + kBufElems;
   float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
-  fill_window(win);
+  fill_window(win, a.tw);
   cf* xs0 = a.scratch + (size_t)blockIdx.x * 3 * (kM + 1);
   cf* xs1 = xs0 + (kM + 1);
   cf* yacc = xs1 + (kM + 1);
@@ -566,7 +614,7 @@ spectrogram_kernel(const float* audio, int n, int sr, float* spectrogram, const 
   AVL_DYN_SMEM(smem_raw);
   cf* fb = reinterpret_cast<cf*>(smem_raw);
   float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
-  fill_window(win);
+  fill_window(win, tw);
   __syncthreads();
   const int n_tb = ((1 + sr / kHop) + 3) >> 2;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
@@ -574,6 +622,139 @@ spectrogram_kernel(const float* audio, int n, int sr, float* spectrogram, const 
       GmemSamples y{audio + ((size_t)e * 2 + c) * sr};
       stft_channel(y, sr, fb, win, tw, spectrogram + (size_t)e * kFB * n_tb * 2, c);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Spectral asset banks.  Of the transforms of one rendering only the inverse depends on the step: the spectrum of a
+// scene's RIR (azimuth, receiver, source) and the spectrum of second `index` of a sound are properties of the assets.
+// With 180 GB of HBM they can stay resident next to (or instead of) the time-domain banks: 16385 complex bins per real
+// signal of the 32768-point circular convolution (128 KB; a binaural RIR 256 KB; a 28-node scene's 3136 RIRs 0.8 GB,
+// built in ~1 ms of GPU time per 148 transforms).  A rendering is then, per (env, ear):
+//     Y[k] = sum_terms A[k] X[k]  ->  one inverse FFT  ->  STFT / |.| / 4x4 mean / log1p
+// i.e. 1 big transform instead of 2.5 and no shared work between the ears, so every (env, ear) is its own work item at
+// every batch size.  The source row carries the whole history a RIR of the maximum length can reach
+// (u[P - j] = src[base - j], 1 <= j <= P - sr): shorter RIRs multiply the extra history by zero taps.
+struct SpectraArgs {
+  int n, sr, kind;            // kind 0: RIRs (two items per row: the ears), 1: source seconds
+  const float* bank;          // rirs (interleaved (L, 2)) / sounds
+  const long long* off;       // rir_off (frames) / clip_off (samples)
+  const int* len_or_index;    // rir_len / index (second of the clip)
+  cf* out;                    // kind 0: (n, 2, kM + 1), kind 1: (n, kM + 1); natural order
+  const cf* tw;
+  int* status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) audio_spectra_kernel(SpectraArgs a) {
+  AVL_DYN_SMEM(smem_raw);
+  cf* buf = reinterpret_cast<cf*>(smem_raw);
+  const int lmax = kP - a.sr + 1;
+  const int items = a.kind == 0 ? 2 * a.n : a.n;
+  for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    EnvTerm t;
+    if (a.kind == 0) {
+      const int r = w >> 1;
+      int L = a.len_or_index[r];
+      if (L > lmax) { L = lmax; if (threadIdx.x == 0) atomicExch(a.status, 1); }
+      t.src = nullptr; t.base = 0; t.rir = a.bank + 2 * a.off[r]; t.L = L < 0 ? 0 : L;
+      load_rir(buf, t, w & 1);
+    } else {
+      t.src = a.bank + a.off[w]; t.base = (long long)a.len_or_index[w] * a.sr; t.rir = nullptr; t.L = lmax;
+      load_source(buf, t, a.sr);
+    }
+    fft_big_fwd(buf, a.tw);
+    store_spectrum(buf, a.tw, a.out + (size_t)w * (kM + 1));
+  }
+}
+
+struct SpectralArgs {
+  int n_envs, sr;
+  const cf* src_spec;          // rows of kM + 1 bins
+  const long long* src_row0;   // row of second 0 of the env's clip; the rendered row is src_row0 + index
+  const int* index;
+  const cf* rir_spec;          // rows of (2, kM + 1) bins
+  const long long* rir_row;    // < 0: empty RIR file
+  const int* silent;
+  const long long* d_src_row0; // distractor (null when absent): always second 0 of its clip (simulator.py:682-697)
+  const long long* d_rir_row;
+  float* audiogoal;            // (N, 2, sr) or null
+  float* spectrogram;          // (N, 65, TB, 2)
+  const cf* tw;
+};
+
+// buf <- half-size spectrum (digit-reversed, scaled by 1 / M) of the packed real signal with spectrum sum_t A_t X_t
+__device__ void spectral_combine(cf* buf, const cf* __restrict__ tw, const cf* A0, const cf* X0, const cf* A1, const cf* X1) {
+  const float scale = 1.0f / (float)kM;
+  for (int k = threadIdx.x; k <= kM / 2; k += kThreads) {
+    cf yk = cmul(__ldg(A0 + k), __ldg(X0 + k));
+    cf ym = cmul(__ldg(A0 + kM - k), __ldg(X0 + kM - k));
+    if (A1 != nullptr) {  // distractor term
+      yk = cadd(yk, cmul(__ldg(A1 + k), __ldg(X1 + k)));
+      ym = cadd(ym, cmul(__ldg(A1 + kM - k), __ldg(X1 + kM - k)));
+    }
+    if (k == 0) {  // Y[0], Y[M] are real
+      const float e = 0.5f * (yk.x + ym.x), o = 0.5f * (yk.x - ym.x);
+      buf[padi(0)] = make_float2(e * scale, o * scale);
+      continue;
+    }
+    const cf wk = tw[k];
+    const cf ymc = cconj(ym);
+    const cf e = make_float2(0.5f * (yk.x + ymc.x), 0.5f * (yk.y + ymc.y));
+    const cf d = make_float2(0.5f * (yk.x - ymc.x), 0.5f * (yk.y - ymc.y));
+    const cf o = cmulc(d, wk);
+    buf[padi(rev_big(k))] = make_float2((e.x - o.y) * scale, (e.y + o.x) * scale);
+    if (k != kM / 2) {
+      const cf o2 = cmul(cconj(d), wk);
+      buf[padi(rev_big(kM - k))] = make_float2((e.x - o2.y) * scale, (-e.y + o2.x) * scale);
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) audio_render_spectral_kernel(SpectralArgs a) {
+  AVL_DYN_SMEM(smem_raw);
+  cf* buf = reinterpret_cast<cf*>(smem_raw);
+  cf* fb = buf + kBufElems;
+  float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
+  fill_window(win, a.tw);
+  const int sr = a.sr;
+  const int n_tb = ((1 + sr / kHop) + 3) >> 2;
+  __syncthreads();
+  for (int w = blockIdx.x; w < 2 * a.n_envs; w += gridDim.x) {
+    const int e = w >> 1, c = w & 1;
+    const cf *A0 = nullptr, *X0 = nullptr, *A1 = nullptr, *X1 = nullptr;
+    if (a.silent[e] == 0) {
+      const long long r = a.rir_row[e];
+      if (r >= 0) {
+        A0 = a.rir_spec + (size_t)(2 * r + c) * (kM + 1);
+        X0 = a.src_spec + (size_t)(a.src_row0[e] + (a.index ? a.index[e] : 0)) * (kM + 1);
+      }
+      if (a.d_src_row0 != nullptr) {
+        const long long rd = a.d_rir_row[e];
+        if (rd >= 0) {
+          A1 = a.rir_spec + (size_t)(2 * rd + c) * (kM + 1);
+          X1 = a.src_spec + (size_t)a.d_src_row0[e] * (kM + 1);
+        }
+      }
+      if (A0 == nullptr) { A0 = A1; X0 = X1; A1 = nullptr; X1 = nullptr; }
+    }
+    float* spec = a.spectrogram + (size_t)e * kFB * n_tb * 2;
+    if (A0 == nullptr) {  // exact zeros, as in audio_render_kernel
+      for (int i = threadIdx.x; i < kFB * n_tb; i += kThreads) spec[2 * i + c] = 0.f;
+      if (a.audiogoal) {
+        float* ag = a.audiogoal + ((size_t)e * 2 + c) * sr;
+        for (int i = threadIdx.x; i < sr; i += kThreads) ag[i] = 0.f;
+      }
+      continue;
+    }
+    spectral_combine(buf, a.tw, A0, X0, A1, X1);
+    fft_big_inv(buf, a.tw);
+    SmemSamples y{reinterpret_cast<const float*>(buf)};
+    if (a.audiogoal) {
+      float* ag = a.audiogoal + ((size_t)e * 2 + c) * sr;
+      for (int i = threadIdx.x; i < sr; i += kThreads) ag[i] = y(i);
+    }
+    stft_channel(y, sr, fb, win, a.tw, spec, c);
   }
 }
 
@@ -657,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) audio_render_part_kernel(RenderAr
   cf* buf = reinterpret_cast<cf*>(smem_raw);
   cf* fb = buf + kBufElems;
   float* win = reinterpret_cast<float*>(fb + kWarps * 2 * kFrameElems);
-  fill_window(win);
+  fill_window(win, a.tw);
   const int sr = a.sr, K = pa.K, Qmax = pa.Qmax;
   const size_t spec = (size_t)(kM + 1);
   cf* Xs = pa.scratch + (size_t)blockIdx.x * (size_t)(K + Qmax - 1 + 2 * K) * spec;
@@ -753,8 +934,9 @@ struct AudioCtx {
 
 constexpr int kPartQmax = 3;  // RIRs up to 3 * 16384 = 49152 samples (1.1 s at 44.1 kHz)
 
-constexpr size_t kRenderSmem = (size_t)(kBufElems + kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
-constexpr size_t kSpecSmem = (size_t)(kWarps * 2 * kFrameElems) * sizeof(cf) + kNfft * sizeof(float);
+constexpr size_t kRenderSmem = (size_t)(kBufElems + kWarps * 2 * kFrameElems) * sizeof(cf) + kStftSmem;
+constexpr size_t kSpectraSmem = (size_t)kBufElems * sizeof(cf);
+constexpr size_t kSpecSmem = (size_t)(kWarps * 2 * kFrameElems) * sizeof(cf) + kStftSmem;
 
 #endif  // AVL_HOST_EMUL
 
@@ -786,6 +968,8 @@ AVL_API int avl_audio_create(int sr, void** handle) {
   }
   AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRenderSmem));
   AVL_CUDA_CHECK(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem));
+  AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpectraSmem));
+  AVL_CUDA_CHECK(cudaFuncSetAttribute(audio_render_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRenderSmem));
   AVL_CUDA_CHECK(cudaDeviceSynchronize());
   *handle = ctx;
   return AVL_OK;
@@ -850,6 +1034,62 @@ AVL_API int avl_audio_render_spectrogram(void* handle, int n_envs, const float* 
   const int items = a.split ? 2 * n_envs : n_envs;
   int grid = items < ctx->grid ? items : ctx->grid;
   audio_render_kernel<<<grid, kThreads, kRenderSmem, (cudaStream_t)stream>>>(a);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+// Complex bins per spectrum row of the spectral banks (16385: bins 0 .. 16384 of the 32768-point transform).
+AVL_API int avl_audio_spectrum_bins(void) { return kM + 1; }
+
+static int audio_spectra(AudioCtx* ctx, int kind, int n, const float* bank, const long long* off, const int* len_or_index,
+                         float* out, void* stream) {
+  if (!ctx || n < 0) return AVL_ERR_ARG;
+  if (ctx->part_K > 0) return AVL_ERR_UNSUPPORTED;  // one 32768-point convolution only (sr <= 16769)
+  if (n == 0) return AVL_OK;
+  if (!bank || !off || !len_or_index || !out) return AVL_ERR_ARG;
+  SpectraArgs a;
+  a.n = n; a.sr = ctx->sr; a.kind = kind; a.bank = bank; a.off = off; a.len_or_index = len_or_index;
+  a.out = reinterpret_cast<cf*>(out); a.tw = ctx->tw; a.status = ctx->status;
+  const int items = kind == 0 ? 2 * n : n;
+  // 140 KB of shared memory per CTA: one CTA per SM, each walking over the items
+  audio_spectra_kernel<<<items < ctx->grid ? items : ctx->grid, kThreads, kSpectraSmem, (cudaStream_t)stream>>>(a);
+  AVL_LAUNCH_CHECK();
+  return AVL_OK;
+}
+
+// Spectral RIR bank: row i of spectra_out (n, 2, bins, 2) = spectra of the two ears of RIR i (rir_len 0: zeros; longer
+// than 32768 - sr + 1: truncated, avl_audio_status reports it).  Device pointers.
+AVL_API int avl_audio_rir_spectra(void* handle, int n, const float* rirs, const long long* rir_off, const int* rir_len,
+                                  float* spectra_out, void* stream) {
+  return audio_spectra(static_cast<AudioCtx*>(handle), 0, n, rirs, rir_off, rir_len, spectra_out, stream);
+}
+
+// Spectral sound bank: row i of spectra_out (n, bins, 2) = spectrum of second index[i] of the clip at clip_off[i] together
+// with the 32768 - sr samples before it (zeros before the clip's start).
+AVL_API int avl_audio_source_spectra(void* handle, int n, const float* sounds, const long long* clip_off, const int* index,
+                                     float* spectra_out, void* stream) {
+  return audio_spectra(static_cast<AudioCtx*>(handle), 1, n, sounds, clip_off, index, spectra_out, stream);
+}
+
+// Rows A + B from the spectral banks: same result as avl_audio_render_spectrogram on the time-domain assets the rows
+// were made from.  src_row0[i] + index[i] (index may be NULL: 0) is env i's source row; rir_row[i] < 0 = empty RIR file.
+AVL_API int avl_audio_render_spectral(void* handle, int n_envs, const float* src_spectra, const long long* src_row0,
+                                      const int* index, const float* rir_spectra, const long long* rir_row,
+                                      const int* silent, const long long* d_src_row0, const long long* d_rir_row,
+                                      float* audiogoal_out, float* spectrogram_out, void* stream) {
+  AudioCtx* ctx = static_cast<AudioCtx*>(handle);
+  if (!ctx || n_envs < 0) return AVL_ERR_ARG;
+  if (ctx->part_K > 0) return AVL_ERR_UNSUPPORTED;
+  if (n_envs == 0) return AVL_OK;
+  if (!src_spectra || !src_row0 || !rir_spectra || !rir_row || !silent || !spectrogram_out) return AVL_ERR_ARG;
+  if ((d_src_row0 != nullptr) != (d_rir_row != nullptr)) return AVL_ERR_ARG;
+  SpectralArgs a;
+  a.n_envs = n_envs; a.sr = ctx->sr; a.src_spec = reinterpret_cast<const cf*>(src_spectra); a.src_row0 = src_row0;
+  a.index = index; a.rir_spec = reinterpret_cast<const cf*>(rir_spectra); a.rir_row = rir_row; a.silent = silent;
+  a.d_src_row0 = d_src_row0; a.d_rir_row = d_rir_row; a.audiogoal = audiogoal_out; a.spectrogram = spectrogram_out;
+  a.tw = ctx->tw;
+  const int items = 2 * n_envs;
+  audio_render_spectral_kernel<<<items < ctx->grid ? items : ctx->grid, kThreads, kRenderSmem, (cudaStream_t)stream>>>(a);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

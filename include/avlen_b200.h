@@ -50,6 +50,23 @@ int avl_audio_spectrogram(void* handle, int n, const float* audio /* (N,2,sr) */
 /* 1 (default): batches of at most half the SM count render each ear in its own CTA (rollout latency); 0: one CTA per
  * env always.  Returns the old setting. */
 int avl_set_audio_channel_split(int on);
+/* Spectral asset banks (the resident form of simulator.py:650-659's RIR files and :661-681's source seconds): the
+ * forward transforms of a rendering depend on the assets only, so they are made once and kept in HBM; a rendering is then
+ * a spectral product and ONE inverse transform per (env, ear).  sr <= 16769 only (AVL_ERR_UNSUPPORTED above).
+ * avl_audio_spectrum_bins(): complex bins per spectrum row (16385).
+ * rir_spectra: row i of spectra_out (n, 2, bins, 2) = both ears of RIR i (rir_off in frames, rir_len 0 -> zeros).
+ * source_spectra: row i of spectra_out (n, bins, 2) = second index[i] of the clip at clip_off[i] with its history.
+ * render_spectral: same outputs as avl_audio_render_spectrogram; env i's source row is src_row0[i] + index[i] (index
+ * may be NULL), rir_row[i] < 0 = empty RIR file; the distractor pair (both or neither) renders second 0 of its clip. */
+int avl_audio_spectrum_bins(void);
+int avl_audio_rir_spectra(void* handle, int n, const float* rirs, const long long* rir_off, const int* rir_len,
+                          float* spectra_out, void* stream);
+int avl_audio_source_spectra(void* handle, int n, const float* sounds, const long long* clip_off, const int* index,
+                             float* spectra_out, void* stream);
+int avl_audio_render_spectral(void* handle, int n_envs, const float* src_spectra, const long long* src_row0,
+                              const int* index, const float* rir_spectra, const long long* rir_row, const int* silent,
+                              const long long* d_src_row0, const long long* d_rir_row, float* audiogoal_out,
+                              float* spectrogram_out, void* stream);
 
 /* ------------------------------------------------------------------------- rows N, O: returns / advantages
  * ss_baselines/savi/models/rollout_storage.py:394-412, ss_baselines/common/rollout_storage.py:114-132 (bit-exact)

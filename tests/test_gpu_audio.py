@@ -56,6 +56,82 @@ def test_render_matches_oracle(renderer, distractor, fixed_len):
     assert np.array_equal(sp, sp2)
 
 
+def _spectral_inputs(renderer, b):
+    """Spectral banks + per-env rows for a make_audio_batch descriptor set."""
+    from avlen_b200.audio import SpectralSoundBank
+    d = _to_dev(b)
+    n = len(b["clip_id"])
+    off, ln = d["rir_off"], d["rir_len"]
+    if "d_rir_off" in d:
+        off, ln = torch.cat([off, d["d_rir_off"]]), torch.cat([ln, d["d_rir_len"]])
+    rir_spec = renderer.rir_spectra(d["rirs"], off, ln)
+    row = torch.arange(off.numel(), device="cuda", dtype=torch.int64)
+    row = torch.where(ln > 0, row, torch.full_like(row, -1))
+    sb = SpectralSoundBank(renderer, d["sounds"], b["clip_off_all"], b["clip_len_all"])
+    out = dict(src=sb.spectra, src_row0=sb.rows(b["clip_id"]), index=d["index"], rir=rir_spec,
+               rir_row=row[:n].contiguous(), silent=d["silent"], d_src_row0=None, d_rir_row=None)
+    if "d_rir_off" in d:
+        out["d_src_row0"], out["d_rir_row"] = sb.rows(b["d_clip_id"]), row[n:].contiguous()
+    return out
+
+
+@pytest.mark.parametrize("distractor", [False, True])
+@pytest.mark.parametrize("fixed_len", [None, 16000])
+def test_render_from_spectral_banks(renderer, distractor, fixed_len):
+    """Spectral asset banks (rir_spectra / source_spectra + render_spectral) give what the time-domain call gives."""
+    b = synth.make_audio_batch(211 + (fixed_len or 0), 40, distractor=distractor, fixed_len=fixed_len,
+                               max_seconds=8, silent_frac=0.15)
+    b["silent"][0] = 1
+    b["silent"][1:4] = 0
+    b["rir_len"][1] = 0          # empty main RIR: distractor alone (or zeros)
+    b["index"][2] = 0            # no history before the clip's start
+    if distractor:
+        b["d_rir_len"][3] = 0
+        b["rir_len"][5] = 0
+        b["d_rir_len"][5] = 0
+        b["silent"][5] = 0
+    ag_ref, sp_ref = oracle_render(b)
+    ag_t, sp_t = _render(renderer, b)
+    s = _spectral_inputs(renderer, b)
+    ag, sp = renderer.render_spectral(s["src"], s["src_row0"], s["index"], s["rir"], s["rir_row"], s["silent"],
+                                      s["d_src_row0"], s["d_rir_row"])
+    torch.cuda.synchronize()
+    ag, sp = ag.cpu().numpy(), sp.cpu().numpy()
+    assert np.all(ag[0] == 0) and np.all(sp[0] == 0)
+    if distractor:
+        assert np.all(ag[5] == 0) and np.all(sp[5] == 0)
+    else:
+        assert np.all(ag[1] == 0) and np.all(sp[1] == 0)
+    assert rel_err(ag, ag_ref) < TOL
+    assert np.abs(sp - sp_ref).max() < TOL * max(1.0, np.abs(sp_ref).max())
+    # against the time-domain kernel: the same transforms in a different order of storage
+    assert rel_err(ag, ag_t) < 1e-5
+    assert np.abs(sp - sp_t).max() < 1e-4
+    assert renderer.status() == 0
+    _, sp2 = renderer.render_spectral(s["src"], s["src_row0"], s["index"], s["rir"], s["rir_row"], s["silent"],
+                                      s["d_src_row0"], s["d_rir_row"], want_audiogoal=False)
+    assert np.array_equal(sp, sp2.cpu().numpy())
+
+
+def test_spectral_banks_more_envs_than_sms(renderer):
+    b = synth.make_audio_batch(9, 333, max_seconds=6)
+    _, sp_t = _render(renderer, b, want_audiogoal=False)
+    s = _spectral_inputs(renderer, b)
+    _, sp = renderer.render_spectral(s["src"], s["src_row0"], s["index"], s["rir"], s["rir_row"], s["silent"],
+                                     want_audiogoal=False)
+    assert np.abs(sp.cpu().numpy() - sp_t).max() < 1e-4
+
+
+def test_spectral_banks_unsupported_above_one_convolution():
+    from avlen_b200 import _lib
+    from avlen_b200.audio import AudioRenderer
+    r = AudioRenderer(44100)
+    z64, z32 = torch.zeros(1, dtype=torch.int64, device="cuda"), torch.ones(1, dtype=torch.int32, device="cuda")
+    with pytest.raises(_lib.AvlenError):
+        r.rir_spectra(torch.zeros(8, 2, device="cuda"), z64, z32)
+    r.close()
+
+
 def test_more_envs_than_sms_and_determinism(renderer):
     b = synth.make_audio_batch(7, 333, max_seconds=6)
     ag1, sp1 = _render(renderer, b)
