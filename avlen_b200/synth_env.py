@@ -13,13 +13,13 @@ import numpy as np
 import torch
 
 from . import _lib, synth
-from .audio import AudioRenderer
+from .audio import AudioRenderer, SpectralSoundBank
 from .common.utils import batch_obs
 
 
 class SyntheticVectorEnv:
     def __init__(self, num_envs, device, seed=1234, sr=16000, pool=4, distractor=False, host_buffers=False,
-                 done_prob=1.0 / 80.0, rir_len=None, fused_step=True, compact=False):
+                 done_prob=1.0 / 80.0, rir_len=None, fused_step=True, compact=False, spectral_audio=True):
         self.num_envs, self.device, self.sr = num_envs, torch.device(device), sr
         self.host_buffers = host_buffers
         # compact: frames are handed over as uint8 rgb / fp16 depth (what the compact rollout storage keeps,
@@ -60,6 +60,21 @@ class SyntheticVectorEnv:
         self._audio = {k: torch.from_numpy(v).to(dev) for k, v in b.items() if isinstance(v, np.ndarray)}
         self._clip_secs = torch.from_numpy((b["clip_len_all"][b["clip_id"]] // sr).astype(np.int32)).to(dev)
         self.renderer = AudioRenderer(sr, dev)
+        # spectral asset banks (audio.SpectralSoundBank / rir_spectra): the RIRs' and source seconds' transforms are made
+        # once, a step's rendering is a spectral product + one inverse transform per ear (same outputs; sr <= 16769)
+        self._spectral = None
+        if spectral_audio and sr <= 16769:
+            a = self._audio
+            off, ln = a["rir_off"], a["rir_len"]
+            if distractor:
+                off, ln = torch.cat([off, a["d_rir_off"]]), torch.cat([ln, a["d_rir_len"]])
+            row = torch.arange(off.numel(), device=dev, dtype=torch.int64)
+            row = torch.where(ln > 0, row, torch.full_like(row, -1))
+            bank = SpectralSoundBank(self.renderer, a["sounds"], b["clip_off_all"], b["clip_len_all"])
+            self._spectral = {"src": bank.spectra, "src_row0": bank.rows(b["clip_id"]),
+                              "rir": self.renderer.rir_spectra(a["rirs"], off, ln), "rir_row": row[:n].contiguous(),
+                              "d_src_row0": bank.rows(b["d_clip_id"]) if distractor else None,
+                              "d_rir_row": row[n:].contiguous() if distractor else None}
         self.done_prob = done_prob
         self._t = 0
         self._episode_step = torch.zeros(n, device=dev)
@@ -123,9 +138,14 @@ class SyntheticVectorEnv:
         if silent is None:
             silent = (self._episode_step > self._silent_after).to(torch.int32)  # simulator.py:646
         rgb, depth = self._visual()
-        _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
-                                       silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
-                                       want_audiogoal=False)
+        sp = self._spectral
+        if sp is not None:
+            _, spec = self.renderer.render_spectral(sp["src"], sp["src_row0"], a["index"], sp["rir"], sp["rir_row"], silent,
+                                                    sp["d_src_row0"], sp["d_rir_row"], want_audiogoal=False)
+        else:
+            _, spec = self.renderer.render(a["sounds"], a["clip_off"], a["index"], a["rirs"], a["rir_off"], a["rir_len"],
+                                           silent, a.get("d_clip_off"), a.get("d_rir_off"), a.get("d_rir_len"),
+                                           want_audiogoal=False)
         if self.visual_ready_event is not None:
             main = torch.cuda.current_stream()
             main.wait_event(self.visual_ready_event)

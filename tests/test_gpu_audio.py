@@ -132,6 +132,29 @@ def test_spectral_banks_unsupported_above_one_convolution():
     r.close()
 
 
+@pytest.mark.parametrize("distractor", [False, True])
+def test_synthetic_env_spectral_audio_matches_time_domain(distractor):
+    """SyntheticVectorEnv renders from the spectral banks by default: same observations as the time-domain call."""
+    from avlen_b200.synth_env import SyntheticVectorEnv
+    a = SyntheticVectorEnv(7, "cuda", seed=5, done_prob=0.2, distractor=distractor, spectral_audio=True)
+    b = SyntheticVectorEnv(7, "cuda", seed=5, done_prob=0.2, distractor=distractor, spectral_audio=False)
+    assert a._spectral is not None and b._spectral is None
+    oa, ob = a.reset(), b.reset()
+    assert (oa["spectrogram"] - ob["spectrogram"]).abs().max().item() < 1e-4
+    g = torch.Generator().manual_seed(3)
+    for t in range(8):
+        actions = torch.randint(0, 4, (7, 1), generator=g).cuda()
+        torch.manual_seed(100 + t)
+        oa, ra, da = a.step(actions)
+        torch.manual_seed(100 + t)
+        ob, rb, db = b.step(actions)
+        assert torch.equal(da, db)
+        assert (oa["spectrogram"] - ob["spectrogram"]).abs().max().item() < 1e-4, t
+        assert float(oa["spectrogram"].abs().max()) > 0
+    a.close()
+    b.close()
+
+
 def test_more_envs_than_sms_and_determinism(renderer):
     b = synth.make_audio_batch(7, 333, max_seconds=6)
     ag1, sp1 = _render(renderer, b)
