@@ -258,9 +258,11 @@ class SpectrogramCache:
         self.valid = torch.zeros(num_envs, V * V * 4, dtype=torch.uint8, device=dev)
         self.cache = torch.empty(num_envs, V * V * 4, self.E, device=dev)
 
-    def render(self, sounds, clip_off, index, clip_secs, src, recv, az, silent, clear=None):
+    def render(self, sounds, clip_off, index, clip_secs, src, recv, az, silent, clear=None, sound_bank=None):
         """sounds / clip_off / index as in ``AudioRenderer.render``; clip_secs (N,) int32 clip lengths in seconds; src /
         recv / az (N,) int32 (az in quarter turns); silent (N,) int32.  ``index`` is advanced IN PLACE on misses.
+        With ``sound_bank`` (a :class:`SpectralSoundBank`; ``sounds`` is ignored and ``clip_off`` holds each env's
+        ``sound_bank.rows(clip_id)``) misses are rendered from the spectral banks (``RirBank.spectral``).
         Returns (spectrogram (N, 65, 26, 2), hit (N,) bool)."""
         n, dev, V = self.n, self.bank.device, self.bank.V
         i32, i64 = torch.int32, torch.int64
@@ -269,11 +271,20 @@ class SpectrogramCache:
         silent_eff = torch.empty(n, dtype=i32, device=dev)
         hit = torch.empty(n, dtype=torch.uint8, device=dev)
         cl = None if clear is None else clear.to(torch.uint8).contiguous()
+        if sound_bank is not None:
+            rir_spectra, table = self.bank.spectral(self.r)   # the table holds spectrum rows (-1: empty file)
+        else:
+            table = self.bank.off
         _lib.call("avl_spec_cache_lookup", n, V, _lib.dptr(src, i32), _lib.dptr(recv, i32), _lib.dptr(az, i32),
-                  _lib.dptr(self.bank.off, i64), _lib.dptr(self.bank.len, i32), None if cl is None else cl.data_ptr(),
+                  _lib.dptr(table, i64), _lib.dptr(self.bank.len, i32), None if cl is None else cl.data_ptr(),
                   self.valid.data_ptr(), _lib.dptr(silent, i32), _lib.dptr(rir_off, i64), _lib.dptr(rir_len, i32),
                   _lib.dptr(silent_eff, i32), hit.data_ptr(), _lib.stream())
-        _, spec = self.r.render(sounds, clip_off, index, self.bank.rirs, rir_off, rir_len, silent_eff, want_audiogoal=False)
+        if sound_bank is not None:
+            _, spec = self.r.render_spectral(sound_bank.spectra, clip_off, index, rir_spectra, rir_off, silent_eff,
+                                             want_audiogoal=False)
+        else:
+            _, spec = self.r.render(sounds, clip_off, index, self.bank.rirs, rir_off, rir_len, silent_eff,
+                                    want_audiogoal=False)
         _lib.call("avl_spec_cache_commit", n, V, self.E, _lib.dptr(src, i32), _lib.dptr(recv, i32), _lib.dptr(az, i32),
                   hit.data_ptr(), _lib.dptr(silent, i32), _lib.fptr(self.cache), self.valid.data_ptr(), _lib.fptr(spec),
                   _lib.dptr(index, i32), _lib.dptr(clip_secs, i32), _lib.stream())

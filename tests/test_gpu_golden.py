@@ -396,13 +396,14 @@ def test_interactive_bookkeeping_cuda_matches_reference_trainer_golden():
                               to_np=lambda a: a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a))
 
 
-def test_spectrogram_cache_follows_reference_cache_sequence(tmp_path):
+@pytest.mark.parametrize("spectral", [False, True])
+def test_spectrogram_cache_follows_reference_cache_sequence(tmp_path, spectral):
     """``RirBank.from_wav_dir`` (the reference's ``{azimuth}/{receiver}_{source}.wav`` layout) +
     ``SpectrogramCache.render`` against the recorded behaviour of the UNMODIFIED ``get_current_audiogoal_observation``
     (soundspaces/simulator.py:711-721, :668; tests/golden/make_golden.py:audiogoal): which visits are cache hits, which
     clip second each miss consumes, and the cached result returned on a hit."""
     from scipy.io import wavfile
-    from avlen_b200.audio import AudioRenderer, RirBank, SpectrogramCache
+    from avlen_b200.audio import AudioRenderer, RirBank, SpectralSoundBank, SpectrogramCache
     from oracle import audio_np as A
     from tests._audio_helpers import GOLDEN_AUDIO_SR, golden_audio_inputs
     g = load("audiogoal.npz")
@@ -424,11 +425,16 @@ def test_spectrogram_cache_follows_reference_cache_sequence(tmp_path):
     index = torch.zeros(1, dtype=i32, device="cuda")
     secs = torch.full((1,), len(src) // sr, dtype=i32, device="cuda")
     silent = torch.zeros(1, dtype=i32, device="cuda")
+    sb = None
+    if spectral:  # misses rendered from the spectral forms of the same assets (RirBank.spectral + SpectralSoundBank)
+        sb = SpectralSoundBank(r_, sounds, np.zeros(1, np.int64), np.array([len(src)], np.int64))
+        clip_off = sb.rows([0])
     seen = {}
     for step, (s_, rcv, az) in enumerate(keys):
         before = int(index.cpu())
         spec, hit = cache.render(sounds, clip_off, index, secs, torch.tensor([s_], dtype=i32).cuda(),
-                                 torch.tensor([rcv], dtype=i32).cuda(), torch.tensor([az // 90], dtype=i32).cuda(), silent)
+                                 torch.tensor([rcv], dtype=i32).cuda(), torch.tensor([az // 90], dtype=i32).cuda(), silent,
+                                 sound_bank=sb)
         used = int(g["cache_index_used"][step])
         assert bool(hit[0]) == (used < 0), step
         if used >= 0:
@@ -443,6 +449,7 @@ def test_spectrogram_cache_follows_reference_cache_sequence(tmp_path):
             assert torch.equal(spec[0], seen[(s_, rcv, az)]), step   # the cached spectrogram, bit for bit
     # a scene / sound change clears the env's cache (simulator.py:393-395)
     spec, hit = cache.render(sounds, clip_off, index, secs, torch.tensor([2], dtype=i32).cuda(), torch.tensor([1], dtype=i32).cuda(),
-                             torch.tensor([0], dtype=i32).cuda(), silent, clear=torch.ones(1, dtype=torch.bool, device="cuda"))
+                             torch.tensor([0], dtype=i32).cuda(), silent, clear=torch.ones(1, dtype=torch.bool, device="cuda"),
+                             sound_bank=sb)
     assert not bool(hit[0])
     r_.close()
