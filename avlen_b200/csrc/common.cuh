@@ -82,6 +82,11 @@ int avl_num_sms();
 __device__ __forceinline__ void avl_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void avl_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 extern "C" int avl_pdl_enabled();
+extern "C" int avl_wide_stores();
+// rows of `ld` elements of `esize` bytes starting at p are 32-byte aligned (and wide stores are on)
+static inline int avl_rows_32b(const void* p, long long ld, int esize) {
+  return (avl_wide_stores() && ((ld * esize) & 31) == 0 && ((uintptr_t)p & 31) == 0) ? 1 : 0;
+}
 static inline void avl_pdl_attr(cudaLaunchAttribute* at, unsigned* n) {
   if (avl_pdl_enabled()) {
     at[*n].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -83,6 +83,7 @@ struct HaloArgs {
   long long ldy, ldr;
   int relu;
   int vec_store;       // y rows are 16-byte aligned
+  int st256;           // y rows (and every 16-channel group) are 32-byte aligned: 32-byte stores
   int N, H, W, C, Cout, KH, KW;
   int os, OH, OW;      // output stride (1, or 2: only the even positions of the stride-1 grid are stored) / output map
   int R;               // output rows per strip
@@ -373,8 +374,23 @@ __global__ void __launch_bounds__(HL_THREADS) tc_conv_halo_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 8; ++j) h[j] = floats2half2_sat(o[2 * j], o[2 * j + 1]);
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + pix * p.ldy + c0);
-              dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
-              dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+              if (p.st256) {  // the pixel's 32 bytes as one full-sector store
+                uint32_t u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = *reinterpret_cast<const uint32_t*>(&h[j]);
+                st_global_256(dst, u);
+              } else {
+                dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+                dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+              }
+            } else if (p.st256) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                uint32_t u[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(o[j + i]);
+                st_global_256(yrow + j, u);
+              }
             } else if (p.vec_store) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
@@ -495,7 +511,9 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   const int cpc = in16 ? 8 : 4;  // channels per 16-byte chunk
   HaloArgs p = {};
   p.x = x; p.w = w_packed; p.y = y; p.bias = bias; p.scale = scale; p.residual = residual; p.ldy = ldy; p.ldr = ldr;
-  p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0; p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
+  p.relu = relu; p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0;
+  p.st256 = avl_rows_32b(y, ldy, out16 ? 2 : 4);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.KH = KH; p.KW = KW;
   p.os = stride; p.OH = (H + 2 * pad - KH) / stride + 1; p.OW = (W + 2 * pad - KW) / stride + 1;
   const int nc_ = C / cpc;
   const bool c4 = !in16 && C == 4;

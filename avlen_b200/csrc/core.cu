@@ -72,3 +72,14 @@ AVL_API int avl_set_pdl(int on) {
   avl_bump_config_epoch();
   return old;
 }
+
+// 32-byte global stores (sm_100 STG.256) in the row-per-thread TMEM epilogues: 1 (default) on, 0 = 16-byte stores
+// (diagnostic).  Returns the old value.
+static int g_wide_stores = 1;
+extern "C" int avl_wide_stores() { return g_wide_stores; }
+AVL_API int avl_set_wide_stores(int on) {
+  int old = g_wide_stores;
+  g_wide_stores = on ? 1 : 0;
+  avl_bump_config_epoch();
+  return old;
+}

@@ -31,6 +31,7 @@ struct X3Args {
   long long ldr;
   int relu;
   int vec_store;
+  int st256;  // rows of C are 32-byte aligned: 32-byte stores
   const int* m_dev;
 };
 
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
           float* crow = p.C + (long long)m * p.ldc + n0 + c0;
           const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
           if (p.vec_store && n0 + c0 + 16 <= p.N) {
+            float4 xs[4];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -202,8 +204,9 @@ __global__ void __launch_bounds__(X3_THREADS) tc_gemm_3x_kernel(const __grid_con
                 x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
               }
               if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              *reinterpret_cast<float4*>(crow + j) = x;
+              xs[j >> 2] = x;
             }
+            st_row16(crow, xs, p.st256 != 0);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -544,6 +547,7 @@ AVL_API int avl_tc_gemm_3x(const float* A, long long lda, const float* B, long l
   p.n_tiles = avl_div_up(N, p.bn);
   p.vec_store = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
                  (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
+  p.st256 = p.vec_store && avl_rows_32b(C, ldc, 4);
   CUtensorMap ta, tbh, tbl;
   if (!make_map3(&ta, A, M, K, lda, X3_BM) || !make_map3(&tbh, bhi, N, K, K, p.bn) || !make_map3(&tbl, blo, N, K, K, p.bn))
     return AVL_ERR_UNSUPPORTED;

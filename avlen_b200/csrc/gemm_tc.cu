@@ -48,6 +48,7 @@ struct TcArgs {
   const int* m_dev;
   int stages;        // 3..4 ring slots
   int vec_store;     // rows of C / residual and the scale / bias vectors are 16-byte aligned
+  int st256;         // rows of C are 32-byte aligned: 32-byte stores (tc_common.cuh st_row16)
   int swz;           // 1: SWIZZLE_128B K-major operand tiles (default); 0: SWIZZLE_NONE chunk planes
   int kt_per_split;  // k-tiles per blockIdx.z slice; splits > 1: raw partial sums are atomically added into C
   int splits;
@@ -359,6 +360,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcArgs& p, const CUtensorMap*
       const float* rrow = p.residual ? p.residual + (long long)m * p.ldr + n0 + c0 : nullptr;
       if (p.vec_store && p.splits == 1 && n0 + c0 + 16 <= p.N) {
         // 16-byte stores: a 4-byte store per lane rewrites every 32-byte sector 8 times on its way to L2
+        float4 xs[4];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -376,8 +378,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcArgs& p, const CUtensorMap*
             x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
           }
           if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-          *reinterpret_cast<float4*>(crow + j) = x;
+          xs[j >> 2] = x;
         }
+        st_row16(crow, xs, p.st256 != 0);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -501,6 +504,7 @@ static int tc_launch(bool conv, TcArgs& p, cudaStream_t s, bool want_tma = false
   p.vec_store = ((p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0 && (!p.bias || ((uintptr_t)p.bias & 15) == 0) &&
                  (!p.scale || ((uintptr_t)p.scale & 15) == 0) &&
                  (!p.residual || ((p.ldr & 3) == 0 && ((uintptr_t)p.residual & 15) == 0))) ? 1 : 0;
+  p.st256 = p.vec_store && avl_rows_32b(p.C, p.ldc, 4);
   if (g_tc_splitk && !p.m_dev && mtiles * avl_div_up(p.N, p.bn) * 2 <= sms && KT >= 8) {
     // few output tiles, long reduction (rollout-batch convolutions on small maps, belief-predictor layers): a
     // handful of CTAs would each stream the whole K extent through one SM's cp.async path.  Narrow the N tile and

@@ -23,6 +23,7 @@ struct TmaArgs {
   int M, N, K, bn, tmem_cols;
   int stages;     // 2..4: sized so that two CTAs fit one SM (one CTA's epilogue overlaps the other's main loop)
   int vec_store;  // rows of C (and of the residual) are 16-byte aligned
+  int st256;      // rows of C are 32-byte aligned: 32-byte stores
   const float* bias;
   const float* scale;
   const float* residual;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
       } else if (p.vec_store && n0 + c0 + 16 <= p.N) {  // 16-byte stores: a 4-byte store per lane rewrites every sector 8 times
+        float4 xs[4];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 x = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -211,8 +213,9 @@ __global__ void __launch_bounds__(TM_THREADS) tc_gemm_tma_kernel(const __grid_co
             x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
           }
           if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-          *reinterpret_cast<float4*>(crow + j) = x;
+          xs[j >> 2] = x;
         }
+        st_row16(crow, xs, p.st256 != 0);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -363,6 +366,7 @@ AVL_API int avl_tc_conv2d_dgrad_s2(const float* dy, int N, int OH, int OW, int C
   if (p.stages > TM_MAX_STAGES) p.stages = TM_MAX_STAGES;
   if (p.stages < 2) p.stages = 2;
   p.vec_store = 1;
+  p.st256 = avl_rows_32b(p.C, p.ldc, 4);
   const size_t smem = (size_t)p.stages * stage;
   static bool attr_set = false;
   if (!attr_set) {
@@ -417,6 +421,7 @@ int avl_tc_conv_tma_try(const float* x, int N, int H, int W, int C, const float*
   p.vec_store = ((ldy & 3) == 0 && ((uintptr_t)y & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
                  (!scale || ((uintptr_t)scale & 15) == 0) &&
                  (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
+  p.st256 = p.vec_store && avl_rows_32b(p.C, p.ldc, 4);
   const size_t smem = (size_t)p.stages * stage;
   static bool attr_set = false;
   if (!attr_set) {
@@ -470,7 +475,7 @@ extern "C" int avl_tc_gemm_tma_f16(const void* A, long long lda, const void* W, 
     return AVL_ERR_UNSUPPORTED;
   TmaArgs p = {};
   p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.residual = residual; p.ldr = ldr;
-  p.m_dev = m_dev; p.out16 = out16; p.act = act; p.vec_store = 1;
+  p.m_dev = m_dev; p.out16 = out16; p.act = act; p.vec_store = 1; p.st256 = 0;
   const int mtiles = avl_div_up(M, TM_BM), sms = avl_num_sms();
   p.bn = 64;
   for (int bn = 256; bn >= 64; bn >>= 1)
@@ -530,6 +535,7 @@ int avl_tc_gemm_tma_try(const float* A, long long lda, const float* B, float* C,
   if (p.stages < 2) p.stages = 2;
   p.vec_store = ((ldc & 3) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
                  (!residual || ((ldr & 3) == 0 && ((uintptr_t)residual & 15) == 0))) ? 1 : 0;
+  p.st256 = p.vec_store && avl_rows_32b(p.C, p.ldc, 4);
   const size_t smem = (size_t)p.stages * stage;
   static bool attr_set = false;
   if (!attr_set) {

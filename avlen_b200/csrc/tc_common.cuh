@@ -10,19 +10,47 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
 }
+#ifndef AVL_MBAR_HINT_NS
+#define AVL_MBAR_HINT_NS 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
     if (++spins > (1u << 24)) __trap();  // a lost arrival must fault, never hang the device
+    // with a suspend-time hint the thread sleeps in hardware until the phase completes (or the hint expires) instead of
+    // returning at once: the polling of waiting warps was a third of the instructions the halo-strip convolution issued
+    // (profiles/r02_halo_f16_l1_ncu_full.txt) and competes with the working warps of the same scheduler
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(AVL_MBAR_HINT_NS)
         : "memory");
   } while (!done);
+}
+// 32-byte global store / load (sm_100: STG.256 / LDG.256): a thread that owns 32 contiguous bytes writes one full sector
+// instead of two half-filled ones.  The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* dst, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// 16 consecutive floats of an output row (64-byte aligned when `wide`): two 32-byte stores, else four 16-byte stores
+__device__ __forceinline__ void st_row16(float* dst, const float4 (&x)[4], bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t u[8] = {__float_as_uint(x[2 * h].x),     __float_as_uint(x[2 * h].y),     __float_as_uint(x[2 * h].z),
+                             __float_as_uint(x[2 * h].w),     __float_as_uint(x[2 * h + 1].x), __float_as_uint(x[2 * h + 1].y),
+                             __float_as_uint(x[2 * h + 1].z), __float_as_uint(x[2 * h + 1].w)};
+      st_global_256(dst + 8 * h, u);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = x[q];
+  }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");

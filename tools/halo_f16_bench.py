@@ -32,7 +32,9 @@ def main():
         print("strip rows", sys.argv[2])
     tma = int(os.environ.get("AVL_HALO_TMA", "1"))
     lib.avl_set_tc_conv_halo_tma(tma)
-    print(f"-- halo strips by {'TMA' if tma else 'cp.async'}")
+    st256 = int(os.environ.get("AVL_HALO_ST256", "1"))
+    lib.avl_set_wide_stores(st256)
+    print(f"-- halo strips by {'TMA' if tma else 'cp.async'}, {'32' if st256 else '16'}-byte stores")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name, H, W, C, Co, k in (("layer1 3x3 16->16 @64", 64, 64, 16, 16, 3), ("layer2 3x3 32->32 @32", 32, 32, 32, 32, 3),
                                  ("layer3 3x3 64->64 @16", 16, 16, 64, 64, 3), ("conv1 7x7 4->16 @64", 64, 64, 4, 16, 7)):

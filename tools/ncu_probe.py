@@ -1,5 +1,6 @@
 """Launches ONE kernel of interest a few times (for `ncu -k regex:<name> -s 2 -c 1`); diagnostic.
-    python tools/ncu_probe.py wgrad_l1 | wgrad_l3 | gn_bwd_l1 | halo_s2 | resize_u8 | multi_copy"""
+    python tools/ncu_probe.py wgrad_l1 | wgrad_l3 | gn_bwd_l1 | halo_s2 | halo_f16_l1 | resize_u8 | tma_conv_l4[_b64] |
+    attn_tc_fwd | audio_render | audio_spec | audio_spectral"""
 import os
 import sys
 
@@ -70,6 +71,28 @@ def main():
                          want_audiogoal=False)
             else:
                 r.compute_spectrogram(torch.randn(n, 2, b["sr"], device="cuda"))
+    elif what == "audio_spectral":
+        import numpy as np
+        from avlen_b200 import synth
+        from avlen_b200.audio import AudioRenderer, SpectralSoundBank
+        n = 1024
+        b = synth.make_audio_batch(1, n, fixed_len=16000, silent_frac=0.0, max_seconds=6)
+        r = AudioRenderer(b["sr"])
+        d = {k: torch.from_numpy(v).cuda() for k, v in b.items() if isinstance(v, np.ndarray)}
+        rs = r.rir_spectra(d["rirs"], d["rir_off"], d["rir_len"])
+        sb = SpectralSoundBank(r, d["sounds"], b["clip_off_all"], b["clip_len_all"])
+        row = torch.arange(n, device="cuda", dtype=torch.int64)
+        for _ in range(4):
+            r.render_spectral(sb.spectra, sb.rows(b["clip_id"]), d["index"], rs, row, d["silent"], want_audiogoal=False)
+    elif what == "halo_f16_l1":
+        from avlen_b200 import _lib
+        x = torch.randn(B, 64, 64, 16, device="cuda").half()
+        w = (torch.randn(16, 3, 3, 16, device="cuda") / 12).half()
+        y = torch.empty(B, 64, 64, 16, device="cuda", dtype=torch.float16)
+        for _ in range(4):
+            rc = _lib.lib().avl_tc_conv_halo_f16(x.data_ptr(), 1, B, 64, 64, 16, w.data_ptr(), 16, 3, 3, 1, 0, y.data_ptr(), 1,
+                                                _lib.stream())
+            assert rc == 0, rc
     torch.cuda.synchronize()
     print("ok")
 
