@@ -47,10 +47,10 @@ def main():
             y = torch.empty(B, H, W, Co, device="cuda", dtype=torch.float16 if out16 else torch.float32)
 
             def f():
-                rc = lib.avl_tc_conv_halo_f16(x.data_ptr(), in16, B, H, W, C, w.data_ptr(), Co, k, k, k // 2, 0, y.data_ptr(),
-                                              out16, _lib.stream())
-                assert rc == 0, rc
-            f()
+                return lib.avl_tc_conv_halo_f16(x.data_ptr(), in16, B, H, W, C, w.data_ptr(), Co, k, k, k // 2, 0, y.data_ptr(),
+                                                out16, _lib.stream())
+            if f() != 0:  # -2: shape not covered by the halo-strip kernel (served by the TMA im2col kernel)
+                continue
             ms = timeit(f, flush)
             byts = x.numel() * x.element_size() + y.numel() * y.element_size()
             print(f"B={B} {name:24s} in={'f16' if in16 else 'f32'} out={'f16' if out16 else 'f32'} {ms * 1e3:9.1f} us "
