@@ -212,8 +212,6 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
                                                                      float* pgamma, float* pbeta, int HW, int C, int groups,
                                                                      float eps, int relu, int cl, int pix_per_cta) {
   extern __shared__ __align__(16) unsigned char gsm[];
-  __shared__ float ch[4][512];      // per-channel totals of this CTA: sum x, sum x^2, sum g, sum g*x
-  __shared__ float red[4][1024];    // per (slot, channel) partials, summed in a fixed order
   __shared__ double part[64][4];    // per group: S, Q, sum gamma*G, sum gamma*GX   (this CTA)
   __shared__ float g_mean[64], g_rstd[64], g_m1[64], g_m2[64];
   cg::cluster_group cluster = cg::this_cluster();
@@ -227,6 +225,13 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
   const size_t base4 = ((size_t)n * HW + p0) * nq;
   float4* tx = reinterpret_cast<float4*>(gsm);
   float4* tg = tx + (size_t)pix_per_cta * nq;
+  // reduction scratch behind the two slices, sized by C (as static arrays for C <= 512 they cost 24 KB and the third
+  // CTA of an SM): red[k][slot * C + c] per (slot, channel) partials, summed in a fixed order; ch[k][c] per-channel
+  // totals of this CTA (k: sum x, sum x^2, sum g, sum g*x)
+  const int n_slots = nq < 32 ? GNC_THREADS / 32 : GNC_THREADS / nq;
+  const int RS = n_slots * C;
+  float* red = reinterpret_cast<float*>(tg + (size_t)pix_per_cta * nq);
+  float* ch = red + 4 * RS;
   float a[4][4];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -279,21 +284,20 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
       for (int j = 0; j < 4; ++j) a[k][j] += __shfl_xor_sync(0xffffffffu, a[k][j], o);
   const int lane = tid & 31;
   const int c0 = (tid % nq) * 4;
-  const int n_slots = nq < 32 ? GNC_THREADS / 32 : GNC_THREADS / nq;
   if (nq >= 32 || lane < nq) {
     const int slot = nq < 32 ? (tid >> 5) : tid / nq;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red[k][(slot * nq + (tid % nq)) * 4 + j] = a[k][j];
+      for (int j = 0; j < 4; ++j) red[k * RS + (slot * nq + (tid % nq)) * 4 + j] = a[k][j];
   }
   __syncthreads();
   for (int c = tid; c < C; c += GNC_THREADS) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float S = 0.f;
-      for (int sl = 0; sl < n_slots; ++sl) S += red[k][(sl * nq + (c >> 2)) * 4 + (c & 3)];
-      ch[k][c] = S;
+      for (int sl = 0; sl < n_slots; ++sl) S += red[k * RS + (sl * nq + (c >> 2)) * 4 + (c & 3)];
+      ch[k * C + c] = S;
     }
   }
   __syncthreads();
@@ -302,10 +306,10 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
     double S = 0.0, Q = 0.0, P1 = 0.0, P2 = 0.0;
     for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
       const double ga = (double)__ldg(gamma + c);
-      S += (double)ch[0][c];
-      Q += (double)ch[1][c];
-      P1 += ga * (double)ch[2][c];
-      P2 += ga * (double)ch[3][c];
+      S += (double)ch[c];
+      Q += (double)ch[C + c];
+      P1 += ga * (double)ch[2 * C + c];
+      P2 += ga * (double)ch[3 * C + c];
     }
     part[tid][0] = S; part[tid][1] = Q; part[tid][2] = P1; part[tid][3] = P2;
   }
@@ -331,9 +335,9 @@ __global__ void __launch_bounds__(GNC_THREADS) gn_cluster_bwd_kernel(const float
     for (int c = tid; c < C; c += GNC_THREADS) {
       float G = 0.f, GX = 0.f;
       for (int r = 0; r < cl; ++r) {
-        const float* rc = cluster.map_shared_rank(&ch[0][0], r);
-        G += rc[2 * 512 + c];
-        GX += rc[3 * 512 + c];
+        const float* rc = cluster.map_shared_rank(ch, r);
+        G += rc[2 * C + c];
+        GX += rc[3 * C + c];
       }
       const int g = c / cpg;
       if (pgamma) pgamma[(size_t)n * C + c] = g_rstd[g] * (GX - g_mean[g] * G);
@@ -462,15 +466,22 @@ AVL_API int avl_groupnorm_bwd_cluster(const float* x, const float* y, const floa
   if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15) || ((uintptr_t)y & 15) || ((uintptr_t)dx & 15) || ((uintptr_t)dres & 15))
     return AVL_ERR_UNSUPPORTED;
   const long long sample_bytes = (long long)HW * C * 4;
+  const int nq = C >> 2;
+  const int n_slots = nq < 32 ? GNC_THREADS / 32 : GNC_THREADS / nq;
+  const size_t scratch_bytes = (size_t)4 * (n_slots + 1) * C * sizeof(float);  // reduction scratch (see the kernel)
+  // cluster size: the smallest one whose CTAs (x slice + g slice + scratch) fit three to an SM — the kernel alternates
+  // between a load phase and reduction / cluster barriers, and two CTAs per SM left the memory system idle too often
   int cl = 1;
-  while (cl < 8 && sample_bytes / cl > 32 * 1024) cl <<= 1;
+  while (cl < 8 && 2 * sample_bytes / cl + (long long)scratch_bytes > 72 * 1024) cl <<= 1;
   if (cl > HW) return AVL_ERR_UNSUPPORTED;
   const int pix_per_cta = avl_div_up(HW, cl);
-  const size_t smem = (size_t)pix_per_cta * C * 4 * 2;  // x slice + g slice
-  if (smem > 2 * (size_t)GNC_MAX_SLICE || (long long)N * cl > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  const size_t slices = (size_t)pix_per_cta * C * 4 * 2;  // x slice + g slice
+  if (slices > 2 * (size_t)GNC_MAX_SLICE || (long long)N * cl > 2147483647LL) return AVL_ERR_UNSUPPORTED;
+  const size_t smem = slices + scratch_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GNC_MAX_SLICE));
+    AVL_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * GNC_MAX_SLICE + 24 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
