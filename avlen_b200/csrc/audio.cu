@@ -685,17 +685,11 @@ struct SpectralArgs {
 // buf <- half-size spectrum (digit-reversed, scaled by 1 / M) of the packed real signal with spectrum sum_t A_t X_t
 __device__ void spectral_combine(cf* buf, const cf* __restrict__ tw, const cf* A0, const cf* X0, const cf* A1, const cf* X1) {
   const float scale = 1.0f / (float)kM;
-  for (int k = threadIdx.x; k <= kM / 2; k += kThreads) {
-    cf yk = cmul(__ldg(A0 + k), __ldg(X0 + k));
-    cf ym = cmul(__ldg(A0 + kM - k), __ldg(X0 + kM - k));
-    if (A1 != nullptr) {  // distractor term
-      yk = cadd(yk, cmul(__ldg(A1 + k), __ldg(X1 + k)));
-      ym = cadd(ym, cmul(__ldg(A1 + kM - k), __ldg(X1 + kM - k)));
-    }
+  auto place = [&](int k, cf yk, cf ym) {
     if (k == 0) {  // Y[0], Y[M] are real
       const float e = 0.5f * (yk.x + ym.x), o = 0.5f * (yk.x - ym.x);
       buf[padi(0)] = make_float2(e * scale, o * scale);
-      continue;
+      return;
     }
     const cf wk = tw[k];
     const cf ymc = cconj(ym);
@@ -707,6 +701,43 @@ __device__ void spectral_combine(cf* buf, const cf* __restrict__ tw, const cf* A
       const cf o2 = cmul(cconj(d), wk);
       buf[padi(rev_big(kM - k))] = make_float2((e.x - o2.y) * scale, (-e.y + o2.x) * scale);
     }
+  };
+  // the spectrum rows come from HBM / L2: the loads of four bins (and their mirrors) are issued before the first product
+  // (profiles/r02_audio_spectral_ncu_full.txt: 3.6 long-scoreboard stalls per issued instruction with one bin in flight)
+  constexpr int B = 4;
+  int k = threadIdx.x;
+  for (; k + (B - 1) * kThreads <= kM / 2; k += B * kThreads) {
+    cf ak[B], xk[B], am[B], xm[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int kk = k + j * kThreads;
+      ak[j] = __ldg(A0 + kk); xk[j] = __ldg(X0 + kk);
+      am[j] = __ldg(A0 + kM - kk); xm[j] = __ldg(X0 + kM - kk);
+    }
+    cf yk[B], ym[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) { yk[j] = cmul(ak[j], xk[j]); ym[j] = cmul(am[j], xm[j]); }
+    if (A1 != nullptr) {  // distractor term
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const int kk = k + j * kThreads;
+        ak[j] = __ldg(A1 + kk); xk[j] = __ldg(X1 + kk);
+        am[j] = __ldg(A1 + kM - kk); xm[j] = __ldg(X1 + kM - kk);
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) { yk[j] = cadd(yk[j], cmul(ak[j], xk[j])); ym[j] = cadd(ym[j], cmul(am[j], xm[j])); }
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) place(k + j * kThreads, yk[j], ym[j]);
+  }
+  for (; k <= kM / 2; k += kThreads) {
+    cf yk = cmul(__ldg(A0 + k), __ldg(X0 + k));
+    cf ym = cmul(__ldg(A0 + kM - k), __ldg(X0 + kM - k));
+    if (A1 != nullptr) {
+      yk = cadd(yk, cmul(__ldg(A1 + k), __ldg(X1 + k)));
+      ym = cadd(ym, cmul(__ldg(A1 + kM - k), __ldg(X1 + kM - k)));
+    }
+    place(k, yk, ym);
   }
   __syncthreads();
 }

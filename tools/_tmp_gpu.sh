@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/wgrad_conv_bench.py 2>&1 | grep "gn_bwd\|wgrad" | cut -c1-250 | tee gpurun_out/wgrad_conv_bench_gg.txt
-timeout 900 python -m pytest tests/test_gpu_nn.py tests/test_gpu_tc.py tests/test_gpu_avnav.py -x -q 2>&1 | tail -2
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu --no-eager --no-shares --no-e2e > gpurun_out/bench_gg.log 2>&1; grep '{"metric' gpurun_out/bench_gg.log | sed 's/^[^{]*//' | python -c "
+timeout 900 python -m pytest tests/test_gpu_audio.py -x -q 2>&1 | tail -2
+timeout 600 python bench.py --config audio_sweep --no-cpu > gpurun_out/bench_audio_b4.log 2>&1; grep '{"metric' gpurun_out/bench_audio_b4.log | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('default', d['value'], d['rollout_env_steps_per_s'], d['update_samples_per_s'], 'trainable', d['trainable']['env_steps_per_s'], d['trainable']['rollout_env_steps_per_s'], d['trainable']['update_samples_per_s'])"
+d=json.loads(sys.stdin.read()); print('audio', d['value'], d['roofline']['frac'], [ (p['n_envs'], p['ms'], p['env_steps_per_s'], p['hbm_frac']) for p in d['spectral_banks']['points']])"
