@@ -357,9 +357,13 @@ constexpr int kStftTabElems = 256 + 136;
 constexpr size_t kStftSmem = kNfft * sizeof(float) + kStftTabElems * sizeof(cf);
 
 __device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef AVL_HOST_EMUL
+  return sqrtf(x);
+#else
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 
 // r16_fwd with the twiddles w^q read from a table (stride 16 between q's)

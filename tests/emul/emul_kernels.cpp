@@ -38,6 +38,46 @@ EMUL_API int emul_audio_render(int n_envs, int sr, const float* sounds, const lo
   return status;
 }
 
+// Spectral asset banks: rows made by audio_spectra_kernel from the SAME time-domain descriptors (RIR i -> row i, with the
+// distractor RIRs behind them; source row i = (clip_off[i], index[i]), distractor source rows behind them at second 0),
+// then audio_render_spectral_kernel.
+EMUL_API int emul_audio_render_spectral(int n_envs, int sr, const float* sounds, const long long* clip_off, const int* index,
+                                        const float* rirs, const long long* rir_off, const int* rir_len, const int* silent,
+                                        const long long* d_clip_off, const long long* d_rir_off, const int* d_rir_len,
+                                        float* audiogoal, float* spectrogram, int grid) {
+  std::vector<cf> tw(kM + 1);
+  emul::launch(dim3((kM + 1 + 255) / 256), dim3(256), [&] { twiddle_init_kernel(tw.data()); });
+  const bool dis = d_clip_off != nullptr;
+  const int nr = dis ? 2 * n_envs : n_envs;
+  std::vector<long long> roff(nr), soff(nr), rir_row(n_envs), d_rir_row(n_envs), src_row0(n_envs), d_src_row0(n_envs);
+  std::vector<int> rlen(nr), sidx(nr);
+  for (int i = 0; i < n_envs; ++i) {
+    roff[i] = rir_off[i]; rlen[i] = rir_len[i]; soff[i] = clip_off[i]; sidx[i] = index[i];
+    rir_row[i] = rir_len[i] > 0 ? i : -1;
+    src_row0[i] = i;
+    if (dis) {
+      roff[n_envs + i] = d_rir_off[i]; rlen[n_envs + i] = d_rir_len[i]; soff[n_envs + i] = d_clip_off[i]; sidx[n_envs + i] = 0;
+      d_rir_row[i] = d_rir_len[i] > 0 ? n_envs + i : -1;
+      d_src_row0[i] = n_envs + i;
+    }
+  }
+  std::vector<cf> rspec((size_t)nr * 2 * (kM + 1)), sspec((size_t)nr * (kM + 1));
+  int status = 0;
+  SpectraArgs sa;
+  sa.n = nr; sa.sr = sr; sa.kind = 0; sa.bank = rirs; sa.off = roff.data(); sa.len_or_index = rlen.data(); sa.out = rspec.data();
+  sa.tw = tw.data(); sa.status = &status;
+  emul::launch(dim3(grid), dim3(kThreads), [&] { audio_spectra_kernel(sa); });
+  sa.kind = 1; sa.bank = sounds; sa.off = soff.data(); sa.len_or_index = sidx.data(); sa.out = sspec.data();
+  emul::launch(dim3(grid), dim3(kThreads), [&] { audio_spectra_kernel(sa); });
+  SpectralArgs a;
+  a.n_envs = n_envs; a.sr = sr; a.src_spec = sspec.data(); a.src_row0 = src_row0.data(); a.index = nullptr;
+  a.rir_spec = rspec.data(); a.rir_row = rir_row.data(); a.silent = silent;
+  a.d_src_row0 = dis ? d_src_row0.data() : nullptr; a.d_rir_row = dis ? d_rir_row.data() : nullptr;
+  a.audiogoal = audiogoal; a.spectrogram = spectrogram; a.tw = tw.data();
+  emul::launch(dim3(grid), dim3(kThreads), [&] { audio_render_spectral_kernel(a); });
+  return status;
+}
+
 EMUL_API int emul_spectrogram(int n, int sr, const float* audio, float* spectrogram, int grid) {
   std::vector<cf> tw(kM + 1);
   emul::launch(dim3((kM + 1 + 255) / 256), dim3(256), [&] { twiddle_init_kernel(tw.data()); });

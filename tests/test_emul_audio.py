@@ -37,6 +37,28 @@ def test_emulated_render_matches_oracle(emul_lib, distractor):
     assert np.abs(sp - sp_ref).max() < 1e-4 * max(1.0, np.abs(sp_ref).max())
 
 
+@pytest.mark.parametrize("distractor", [False, True])
+def test_emulated_spectral_banks_match_oracle(emul_lib, distractor):
+    """audio_spectra_kernel + audio_render_spectral_kernel (resident RIR / source spectra) on the host against scipy."""
+    b = synth.make_audio_batch(13, 4, max_seconds=6, distractor=distractor, silent_frac=0.0)
+    b["silent"][0] = 1
+    b["rir_len"][1] = 0  # empty main RIR: zeros, or the distractor alone
+    b["index"][2] = 0    # no history before the clip's start
+    ag_ref, sp_ref = oracle_render(b)
+    n = len(b["clip_off"])
+    ag = np.full((n, 2, SR), np.nan, np.float32)
+    sp = np.full((n, 65, 26, 2), np.nan, np.float32)
+    f, i64, i32 = ctypes.c_float, ctypes.c_longlong, ctypes.c_int
+    st = emul_lib.emul_audio_render_spectral(
+        n, SR, ptr(b["sounds"], f), ptr(b["clip_off"], i64), ptr(b["index"], i32), ptr(b["rirs"], f),
+        ptr(b["rir_off"], i64), ptr(b["rir_len"], i32), ptr(b["silent"], i32), ptr(b.get("d_clip_off"), i64),
+        ptr(b.get("d_rir_off"), i64), ptr(b.get("d_rir_len"), i32), ptr(ag, f), ptr(sp, f), 2)
+    assert st == 0
+    assert np.all(ag[0] == 0) and np.all(sp[0] == 0)
+    assert rel_err(ag, ag_ref) < 2e-5
+    assert np.abs(sp - sp_ref).max() < 1e-4 * max(1.0, np.abs(sp_ref).max())
+
+
 def test_emulated_render_channel_split_matches_unsplit(emul_lib):
     """One CTA per (env, ear) (small batches, RenderArgs::split) writes exactly what one CTA per env writes."""
     b = synth.make_audio_batch(12, 3, max_seconds=6, distractor=False, silent_frac=0.0)
