@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "avlen_b200", "libavlen_b200.so")
 MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCCP", "HMMA", "LDSM", "LDGSTS",
-             "UCGABAR", "ACQBULK", "SYNCS", "ATOM", "RED", "BAR.SYNC"]
+             "UCGABAR", "ACQBULK", "SYNCS", "ATOM", "RED", "BAR.SYNC", "STG.256"]
 
 
 def main():
@@ -36,6 +36,8 @@ def main():
             for k in MNEMONICS:
                 if op.startswith(k):
                     cur[k] += 1
+            if op.startswith("STG") and op.endswith(".256"):  # 32-byte global stores (sm_100)
+                cur["STG.256"] += 1
     print("# SASS mnemonic counts per kernel, %s (cuobjdump -sass; sm_100a)" % os.path.basename(LIB))
     print("# kernel | instructions | " + " ".join(MNEMONICS))
     tot = collections.Counter()
