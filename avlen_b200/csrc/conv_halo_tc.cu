@@ -445,6 +445,7 @@ static bool halo_make_map(CUtensorMap* map, const void* x, bool in16, int N, int
 }
 
 static int g_halo_on = 1;
+static int g_halo_small_grid_pct = 100;
 static int g_halo_tma = 1;
 static int g_halo_group = 0;  // pixel groups (G > 1): measured SLOWER on B200 (see header), kept as an opt-in
 static int g_halo_rows = 0;  // 0: chosen per shape (see avl_tc_conv_halo_typed)
@@ -478,6 +479,16 @@ AVL_API int avl_set_tc_conv_halo_tma(int on) {
   avl_bump_config_epoch();
   int old = g_halo_tma;
   g_halo_tma = on ? 1 : 0;
+  return old;
+}
+
+// Grid cap of the halo-strip kernel at rollout batches (N * H <= 8192 rows), in CTAs per 100 SMs; 0: none.  Default 100:
+// one CTA per SM walking over two or three strips instead of up to three CTAs per SM — the rollout phase is bound by SM
+// time across its concurrent encoder chains (rollout 61.6k -> 62.8k env-steps/s; 50: 60.7k).
+AVL_API int avl_set_tc_conv_halo_small_grid(int percent) {
+  avl_bump_config_epoch();
+  int old = g_halo_small_grid_pct;
+  g_halo_small_grid_pct = percent < 0 ? 0 : percent;
   return old;
 }
 
@@ -605,6 +616,10 @@ int avl_tc_conv_halo_typed(const void* x, int in16, int N, int H, int W, int C, 
   while (per_sm > 1 && per_sm * cols > 512) --per_sm;
   long long grid = (long long)avl_num_sms() * per_sm;
   if (grid > total) grid = total;
+  if (g_halo_small_grid_pct > 0 && (long long)N * H <= 8192) {  // rollout batches: see avl_set_tc_conv_halo_small_grid
+    const long long cap = (long long)avl_num_sms() * g_halo_small_grid_pct / 100;
+    if (grid > cap) grid = cap > 1 ? cap : 1;
+  }
   CUtensorMap tmx;
   memset(&tmx, 0, sizeof(tmx));
   p.tma = 0;
