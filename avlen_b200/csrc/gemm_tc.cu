@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_tma_splitk_kernel(const __
 static int g_tc_ca = 1;
 static int g_tc_splitk = 1;
 static int g_tc_splitk_cluster = 1;
-static int g_tc_splitk_fill = 50;  // split-K aims at this many CTAs per 100 SMs (see avl_set_tc_splitk_fill)
+static int g_tc_splitk_fill = 40;  // split-K aims at this many CTAs per 100 SMs (see avl_set_tc_splitk_fill)
 static int g_tc_cluster16 = -1;  // -1: not probed yet; 0: clusters of 16 CTAs unavailable; 1: available
 static int g_tc_swz = 1;
 static int g_tc_stages = 0;  // 0: automatic; 3 / 4: forced ring depth (diagnostic)
@@ -647,10 +647,11 @@ AVL_API int avl_set_tc_stages(int stages) {
   return old;
 }
 
-// Split-K aims at `percent` CTAs per 100 SMs.  Default 50: a rollout step runs four to eight encoder chains next to each
+// Split-K aims at `percent` CTAs per 100 SMs.  Default 40: a rollout step runs four to eight encoder chains next to each
 // other and is bound by SM time (shared-memory slots), not by one kernel's latency — measured on the whole step
 // (bench.py, 64 envs): 200 (two CTAs per SM, what a kernel running alone prefers) 53.5k env-steps/s, 100 56.3k, 60 56.9k,
-// 40 57.9k, 25 57.7k; the isolated launch latencies stay within 10 % (tools/small_batch_conv_probe.py).  Returns old.
+// 40 57.9k, 25 57.7k (final build: 50 62.6k, 40 63.7k, 30 63.7k); the isolated launch latencies stay within 10 %
+// (tools/small_batch_conv_probe.py).  Returns old.
 AVL_API int avl_set_tc_splitk_fill(int percent) {
   avl_bump_config_epoch();
   int old = g_tc_splitk_fill;

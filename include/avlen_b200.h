@@ -361,7 +361,7 @@ int avl_tc_conv2d_dgrad_s2(const float* dy, int N, int OH, int OW, int Cout, con
 long long avl_tc_conv_tma_count(void); /* convolutions launched on the TMA im2col kernel so far (diagnostic) */
 int avl_set_tc_conv_halo_tma(int on); /* 1 (default): the halo-strip kernel's input strips arrive by TMA (rank-5 tiled map, halo zero-filled by the unit); 0: cp.async gathers; returns old */
 int avl_set_pdl(int on);          /* 1 (default): the convolution / GroupNorm kernels of the encoder chains are launched with programmatic stream serialization (their prologues overlap the previous kernel; every kernel waits with griddepcontrol.wait before touching activations); 0: plain launches; returns old */
-int avl_set_tc_splitk_fill(int percent); /* split-K of the small-grid convolutions aims at this many CTAs per 100 SMs (25..400; default 50: a rollout step is bound by SM time across its concurrent encoder chains, measured 53.5k -> 57.9k env-steps/s against 200); returns old */
+int avl_set_tc_splitk_fill(int percent); /* split-K of the small-grid convolutions aims at this many CTAs per 100 SMs (25..400; default 40: a rollout step is bound by SM time across its concurrent encoder chains, measured 53.5k -> 57.9k env-steps/s against 200; on the final build 50 / 40 / 30: 62.6k / 63.7k / 63.7k); returns old */
 int avl_set_wide_stores(int on); /* 1 (default): 32-byte global stores (STG.256) in the row-per-thread TMEM epilogues of the conv / GEMM kernels; returns old */
 int avl_set_tc_conv_halo_small_grid(int percent); /* grid cap of the halo-strip kernel at rollout batches, CTAs per 100 SMs (default 100); 0: none; returns old */
 int avl_set_attn_tc(int on);      /* 1 (default): varlen self-attention (row F, smt_state_encoder.py:160-166) as 3xTF32 warp MMAs whenever the tensor-core level is >= 1; 0: register-tiled fp32 kernels; returns old */
