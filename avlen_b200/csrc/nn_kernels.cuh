@@ -283,12 +283,31 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
 // share the work, and the K loop moves 64-wide chunks through shared memory (A transposed, conflict-free).
 constexpr int SK_BM = 64, SK_BN = 4, SK_BK = 64, SK_THREADS = SK_BM * SK_BN;
 
+#ifndef AVL_HOST_EMUL
+// (16-byte asynchronous copy global -> shared, zero-filled when src_bytes == 0)
+__device__ __forceinline__ void sk_cp16(void* dst_smem, const void* src, unsigned src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+constexpr int SK_PITCH = SK_BK + 4;  // floats per staged A row: 16-byte aligned rows, conflict-free 16-byte reads
+#endif
+
+// vec: bit 0 = rows of A are 16-byte aligned and K % 4 == 0, bit 1 = the same for B
 __global__ void __launch_bounds__(SK_THREADS)
 skinny_gemm_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, float* C,
                    long long ldc, int M, int N, int K, const float* __restrict__ bias, int relu, int accumulate,
                    const int* m_dev, int vec) {
+#ifndef AVL_HOST_EMUL
+  __shared__ __align__(16) float xa[2][SK_BM][SK_PITCH];
+  __shared__ __align__(16) float wa[2][SK_BN][SK_BK];
+  float (*xs)[SK_BM + 1] = reinterpret_cast<float (*)[SK_BM + 1]>(&xa[0][0][0]);  // the scalar path's views (they fit)
+  float (*ws)[SK_BK] = wa[1];
+  static_assert(SK_BK * (SK_BM + 1) <= SK_BM * SK_PITCH, "transposed tile must fit the first buffer");
+#else
   __shared__ float xs[SK_BK][SK_BM + 1];
   __shared__ float ws[SK_BN][SK_BK];
+#endif
   avl_pdl_wait();
   avl_pdl_trigger();
   if (m_dev) M = min(M, *m_dev);
@@ -297,8 +316,62 @@ skinny_gemm_kernel(const float* __restrict__ A, long long lda, const float* __re
   const int tid = threadIdx.x;
   const int ml = tid & (SK_BM - 1), nl = tid >> 6;
   float acc = 0.f;
+#ifndef AVL_HOST_EMUL
+  if ((vec & 3) == 3) {
+    // Both operands arrive by 16-byte asynchronous copies, two K chunks in flight: the kernel is a chain of global-load
+    // latencies (64 x 256 x 256 is 4 chunks), so the next chunk is requested before the current one is multiplied.
+    const int chunks = (K + SK_BK - 1) / SK_BK;
+    auto request = [&](int c) {
+      const int k0 = c * SK_BK, buf = c & 1;
+#pragma unroll
+      for (int i = 0; i < (SK_BM * SK_BK / 4) / SK_THREADS; ++i) {
+        const int idx = tid + i * SK_THREADS;
+        const int r = idx >> 4, k4 = idx & 15;
+        const bool ok = m0 + r < M && k0 + 4 * k4 < K;
+        sk_cp16(&xa[buf][r][4 * k4], ok ? A + (long long)(m0 + r) * lda + k0 + 4 * k4 : A, ok ? 16u : 0u);
+      }
+      if (tid < SK_BN * SK_BK / 4) {
+        const int n = tid >> 4, k4 = tid & 15;
+        const bool ok = n0 + n < N && k0 + 4 * k4 < K;
+        sk_cp16(&wa[buf][n][4 * k4], ok ? B + (long long)(n0 + n) * ldb + k0 + 4 * k4 : B, ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    request(0);
+    for (int c = 0; c < chunks; ++c) {
+      if (c + 1 < chunks) {
+        request(c + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const float4* xr = reinterpret_cast<const float4*>(&xa[c & 1][ml][0]);
+      const float4* wr = reinterpret_cast<const float4*>(&wa[c & 1][nl][0]);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < SK_BK / 4; ++k4) {
+        const float4 x = xr[k4], w = wr[k4];
+        a0 = fmaf(x.x, w.x, a0);
+        a1 = fmaf(x.y, w.y, a1);
+        a2 = fmaf(x.z, w.z, a2);
+        a3 = fmaf(x.w, w.w, a3);
+      }
+      acc += (a0 + a1) + (a2 + a3);
+      __syncthreads();  // the buffer is requested again two chunks later
+    }
+    const int m = m0 + ml, n = n0 + nl;
+    if (m < M && n < N) {
+      if (bias) acc += bias[n];
+      if (relu) acc = fmaxf(acc, 0.f);
+      float* c = C + (long long)m * ldc + n;
+      *c = accumulate ? *c + acc : acc;
+    }
+    return;
+  }
+#endif
   for (int k0 = 0; k0 < K; k0 += SK_BK) {
-    if (vec) {  // rows 16-byte aligned, K % 4 == 0
+    if (vec & 1) {  // rows 16-byte aligned, K % 4 == 0
 #pragma unroll
       for (int i = 0; i < (SK_BM * SK_BK / 4) / SK_THREADS; ++i) {
         const int idx = tid + i * SK_THREADS;

@@ -183,7 +183,8 @@ static void launch_gemm(Launcher& L, GemmOperand A, bool a_kc, GemmOperand B, bo
   if (M <= 0 || N <= 0 || K <= 0) return;
   if (a_kc && b_kc && splits <= 1 && M <= 4 * SK_BM && !ep.scale && !ep.residual && !ep.k_dev) {
     // few rows (rollout batch): many small CTAs instead of 1-2 tiles of the 128 x 64 kernel
-    const int vec = ((A.s_row & 3) == 0 && (K & 3) == 0 && ((uintptr_t)A.p & 15) == 0) ? 1 : 0;
+    const int vec = (((A.s_row & 3) == 0 && (K & 3) == 0 && ((uintptr_t)A.p & 15) == 0) ? 1 : 0) |
+                    (((B.s_row & 3) == 0 && (K & 3) == 0 && ((uintptr_t)B.p & 15) == 0) ? 2 : 0);
     AVL_LAUNCH_PDL(skinny_gemm_kernel, dim3(avl_div_up(M, SK_BM), avl_div_up(N, SK_BN)), SK_THREADS, 0, L.s, A.p, A.s_row, B.p,
                B.s_row, C, ldc, M, N, K, ep.bias, ep.relu, ep.accumulate, ep.m_dev, vec);
     L.check();
