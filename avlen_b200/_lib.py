@@ -89,6 +89,8 @@ def lib():
         _apply(_lib, _SIGNATURES)
         if os.environ.get("AVL_HALO_SMALL_GRID"):  # diagnostic
             _lib.avl_set_tc_conv_halo_small_grid(int(os.environ["AVL_HALO_SMALL_GRID"]))
+        if os.environ.get("AVL_ATTN_QSPLIT"):  # diagnostic
+            _lib.avl_set_attn_qsplit(int(os.environ["AVL_ATTN_QSPLIT"]))
         if os.environ.get("AVL_WIDE_STORES"):  # diagnostic
             _lib.avl_set_wide_stores(int(os.environ["AVL_WIDE_STORES"]))
         if os.environ.get("AVL_SPLITK_FILL"):  # diagnostic: split-K CTA target per 100 SMs

@@ -123,7 +123,8 @@ attn_self_fwd_tc_kernel(const float* __restrict__ qkv, const int* __restrict__ o
     *reinterpret_cast<float4*>(Vs + j * AT_LD + 4 * c) = vv;
   }
   __syncthreads();
-  for (int qb = warp; qb * 16 < V; qb += AT_WARPS) {
+  // gridDim.z CTAs share a (sample, head): CTA z takes the query blocks z, z + gridDim.z, ... (each CTA stages all keys)
+  for (int qb = blockIdx.z + gridDim.z * warp; qb * 16 < V; qb += gridDim.z * AT_WARPS) {
     const int i0 = qb * 16 + g, i1 = i0 + 8;
     Frag q[4];
     {
@@ -323,6 +324,7 @@ size_t fwd_smem(int vcap) { return (size_t)2 * ((vcap + 31) & ~31) * AT_LD * siz
 size_t bwd_smem(int vcap) { return ((size_t)4 * ((vcap + 15) & ~15) * AT_LD + 2 * ((vcap + 15) & ~15)) * sizeof(float); }
 
 static int g_attn_tc = 1;
+static int g_attn_qsplit = 0;
 static bool g_attr_set = false;
 
 int ensure_attrs() {
@@ -336,6 +338,14 @@ int ensure_attrs() {
 }  // namespace
 
 AVL_API int avl_get_tensor_cores(void);
+
+// CTAs per (sample, head) of the forward kernel: 0 (default) automatic, 1 .. 4 forced (diagnostic).  Returns old.
+AVL_API int avl_set_attn_qsplit(int n) {
+  int old = g_attn_qsplit;
+  g_attn_qsplit = n < 0 ? 0 : (n > 4 ? 4 : n);
+  avl_bump_config_epoch();
+  return old;
+}
 
 // 1 (default): self-attention runs on the tensor cores (3xTF32 warp MMAs) whenever the tensor-core level is >= 1;
 // 0: the register-tiled fp32 kernels.  Returns the old value.
@@ -352,8 +362,12 @@ extern "C" int avl_attn_self_fwd_tc_try(const float* qkv, const int* off, int B,
     return AVL_ERR_UNSUPPORTED;
   int rc = ensure_attrs();
   if (rc) return rc;
-  AVL_LAUNCH_PDL(attn_self_fwd_tc_kernel, dim3(B, D / AT_HD), AT_WARPS * 32, fwd_smem(vcap), stream, qkv, off, out, lse, D, scale,
-                 vcap);
+  // rollout batches: B * heads CTAs are little more than one wave at three CTAs per SM, and 10 query blocks over 8 warps
+  // leave a CTA as long as its two-block warps — with the query blocks dealt out over two CTAs every warp has one block
+  int nz = g_attn_qsplit;
+  if (nz <= 0) nz = ((long long)B * (D / AT_HD) <= 1024 && vcap > 16 * AT_WARPS) ? 2 : 1;
+  AVL_LAUNCH_PDL(attn_self_fwd_tc_kernel, dim3(B, D / AT_HD, nz), AT_WARPS * 32, fwd_smem(vcap), stream, qkv, off, out, lse, D,
+                 scale, vcap);
   AVL_LAUNCH_CHECK();
   return AVL_OK;
 }

@@ -38,6 +38,7 @@ _lib.register({
     "avl_set_attn_tc": [I],
     "avl_set_tc_conv_tma": [I],
     "avl_set_wide_stores": [I],
+    "avl_set_attn_qsplit": [I],
     "avl_set_tc_conv_halo_small_grid": [I],
     "avl_set_tc_splitk_fill": [I],
     "avl_tc_conv2d_dgrad_s2": [P, I, I, I, I, P, I, P, P],

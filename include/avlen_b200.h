@@ -364,7 +364,8 @@ int avl_set_pdl(int on);          /* 1 (default): the convolution / GroupNorm ke
 int avl_set_tc_splitk_fill(int percent); /* split-K of the small-grid convolutions aims at this many CTAs per 100 SMs (25..400; default 40: a rollout step is bound by SM time across its concurrent encoder chains, measured 53.5k -> 57.9k env-steps/s against 200; on the final build 50 / 40 / 30: 62.6k / 63.7k / 63.7k); returns old */
 int avl_set_wide_stores(int on); /* 1 (default): 32-byte global stores (STG.256) in the row-per-thread TMEM epilogues of the conv / GEMM kernels; returns old */
 int avl_set_tc_conv_halo_small_grid(int percent); /* grid cap of the halo-strip kernel at rollout batches, CTAs per 100 SMs (default 100); 0: none; returns old */
-int avl_set_attn_tc(int on);      /* 1 (default): varlen self-attention (row F, smt_state_encoder.py:160-166) as 3xTF32 warp MMAs whenever the tensor-core level is >= 1; 0: register-tiled fp32 kernels; returns old */
+int avl_set_attn_tc(int on);
+int avl_set_attn_qsplit(int n); /* CTAs per (sample, head) of the tensor-core self-attention forward: 0 automatic (2 at rollout batches), 1..4 forced; returns old */      /* 1 (default): varlen self-attention (row F, smt_state_encoder.py:160-166) as 3xTF32 warp MMAs whenever the tensor-core level is >= 1; 0: register-tiled fp32 kernels; returns old */
 
 /* ----------------------------------------------------------------------------- row H: GRU state encoder
  * ss_baselines/av_nav/models/rnn_state_encoder.py:80-149 (single_forward T=1 / seq_forward) around
