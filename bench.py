@@ -429,7 +429,10 @@ def run_savi(args):
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": wl, "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps, "memory_size": 150,
                        "ppo_epoch": 2, "num_mini_batch": 2, "parallelism": f"dp{world}", "regime": regimes[0],
-                       "l2": "inputs larger than L2 (rollout storage > 1 GB, minibatch obs > 0.3 GB)"},
+                       "l2": "inputs larger than L2 (rollout storage > 1 GB, minibatch obs > 0.3 GB)",
+                       "audio": "rendered every step for every env from the spectral asset banks (spectra of the RIRs and "
+                                "of every second of every sound made once and kept in HBM; same outputs as the "
+                                "time-domain call, tests/test_gpu_audio.py)"},
             "rollout_env_steps_per_s": r0["rollout_env_steps_per_s"], "update_samples_per_s": r0["update_samples_per_s"],
             "ranks_params_equal": r0["ranks_params_equal"], "e2e": e2e, "gpu_launches": r0["gpu_launches"],
             "clocks": r0["clocks"], "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager}
