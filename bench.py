@@ -177,8 +177,8 @@ def roofline_halo_conv(dev, B, flush, hbm, how):
     return {"kernel": "tc_conv_halo_kernel<fp16 in, fp16 out> (tcgen05 kind::f16, fp32 accumulate, halo strips, no im2col)"
                       " on custom_resnet18 layer1 conv3x3 16->16 @64x64, batch %d" % B,
             "match": "tc_conv_halo_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-            "frac": round(ach / hbm, 5), "traffic": 1216954880 if B == 4800 else None,
-            "traffic_source": "profiles/r01_halo_conv_f16_layer1_ncu_full.txt (dram read + write of one launch)",
+            "frac": round(ach / hbm, 5), "traffic": 1211560704 if B == 4800 else None,
+            "traffic_source": "profiles/r02_halo_f16_l1_ncu_full.txt (dram read 629.3 MB + write 582.2 MB of one launch, final build)",
             "peak_source": how, "launch_ms": round(ms, 4), "algorithmic_bytes": int(nbytes),
             "tflops": round(2.0 * B * 64 * 64 * 16 * 144 / (ms * 1e-3) / 1e12, 2)}
 
